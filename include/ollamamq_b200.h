@@ -1,0 +1,243 @@
+/* ollamamq_b200.h — C ABI of libollamamq_b200.so
+ *
+ * Drop-in boundary for ollamaMQ's hot path.  The reference has no FFI; the seam is
+ * the reqwest call inside the executor task, /root/reference/src/dispatcher.rs:287-312, and the
+ * BackendStatus slot it occupies (:41-47).  A Rust front would bind exactly these symbols (INTEGRATION.md
+ * shows the `extern "C"` block); tests/ and bench.py bind them through ctypes.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative MQ_ERR_*;
+ * no C++ exception crosses this boundary; mq_last_error() is thread-local.  There is NO CPU fallback:
+ * every worker entry point fails with MQ_ERR_NODEV when no sm_100 GPU is present.
+ */
+#ifndef OLLAMAMQ_B200_H
+#define OLLAMAMQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MQ_OK 0
+#define MQ_ERR_INVAL (-22)
+#define MQ_ERR_NOMEM (-12)
+#define MQ_ERR_CUDA (-5)
+#define MQ_ERR_BUSY (-16)
+#define MQ_ERR_NODEV (-19)
+#define MQ_ERR_TIMEOUT (-110)
+#define MQ_ERR_CANCELED (-125)
+#define MQ_ERR_BLOCKED (-13)
+#define MQ_ERR_NOENT (-2)
+
+const char* mq_last_error(void);
+const char* mq_version(void);
+
+/* =====================================================================================================
+ * 1. Fair-share scheduler — the decision the reference keeps (dispatcher.rs:195-262) plus the completion
+ *    side effects that feed it (:314-341).  Pure state machine, no threads, no clock: the same object is
+ *    driven by the live dispatcher (section 3) and by the simulated-clock parity tests.
+ * ===================================================================================================== */
+typedef struct mq_sched mq_sched;
+
+#define MQ_USER_MAX 256
+
+typedef struct mq_dispatch {
+  uint64_t task_id;          /* id returned by mq_sched_enqueue                                        */
+  uint64_t user_seq;         /* 0-based index of this task among the user's enqueued tasks (FIFO, :244) */
+  int32_t backend;           /* selected backend index (:250-254)                                      */
+  int32_t reserved;
+  char user[MQ_USER_MAX];    /* NUL-terminated user id                                                 */
+} mq_dispatch;
+
+/* outcome codes for mq_sched_complete — the three exits of the executor task */
+#define MQ_DONE_PROCESSED 0  /* stream ended, client still there:  processed_counts[u]++ (:314-316)     */
+#define MQ_DONE_DROPPED 1    /* blocked / client gone / backend error: dropped_counts[u]++ (:280,:318,:326) */
+#define MQ_DONE_UNCOUNTED 2  /* Status send failed: neither counter moves (:299)                         */
+
+/* AppState::new (:67-96): all backends online, last_backend_idx = 0, global_counter = 0.
+ * capacity = in-flight requests per backend; the reference hard-wires 1 (:204).                         */
+mq_sched* mq_sched_new(int32_t n_backends, int32_t capacity);
+void mq_sched_free(mq_sched* s);
+
+/* proxy_handler enqueue (:397-405).  user == NULL means "anonymous" (:364-368).                         */
+int mq_sched_enqueue(mq_sched* s, const char* user, uint64_t* task_id_out);
+/* One iteration of the run_worker loop body (:195-262).  Returns 1 and fills *out when a task was
+ * dispatched (active_requests already bumped, :254), 0 when the loop would park on select! (:344-349).   */
+int mq_sched_next(mq_sched* s, mq_dispatch* out);
+/* Executor epilogue (:314-341): user counters by outcome, backend.active_requests-- (saturating),
+ * backend.processed_count++.                                                                            */
+int mq_sched_complete(mq_sched* s, int32_t backend, const char* user, int32_t outcome);
+/* executor pre-flight bookkeeping: processing_counts[u]++ (:283-284) / -- saturating (:330-333)          */
+int mq_sched_processing(mq_sched* s, const char* user, int32_t delta);
+
+/* TUI-driven flags (tui.rs:126-179): setting VIP on the Boost holder clears Boost and vice versa.
+ * NULL clears.  The reference has one VIP and one Boost slot (:57-58).                                  */
+int mq_sched_set_vip(mq_sched* s, const char* user);
+int mq_sched_set_boost(mq_sched* s, const char* user);
+/* health prober result (:185-189) */
+int mq_sched_set_online(mq_sched* s, int32_t backend, int32_t online);
+/* generalisations with reference defaults: capacity 1 (:204), boost every 2nd dispatch (:233)            */
+int mq_sched_set_capacity(mq_sched* s, int32_t capacity);
+int mq_sched_set_boost_mod(mq_sched* s, int32_t mod);
+
+/* counters (what the TUI snapshot reads, tui.rs:55-69) */
+typedef struct mq_user_stats {
+  uint64_t queued, processing, processed, dropped;
+} mq_user_stats;
+typedef struct mq_backend_stats {
+  uint64_t active_requests, processed_count;
+  int32_t is_online, reserved;
+} mq_backend_stats;
+int mq_sched_user_stats(mq_sched* s, const char* user, mq_user_stats* out);
+int mq_sched_backend_stats(mq_sched* s, int32_t backend, mq_backend_stats* out);
+int32_t mq_sched_user_count(mq_sched* s);
+/* users in TUI order (queued+processing desc, processed+dropped desc, name asc; tui.rs:70-80)           */
+int mq_sched_user_name(mq_sched* s, int32_t index, char* out, size_t cap);
+uint64_t mq_sched_counter(mq_sched* s);
+
+/* =====================================================================================================
+ * 2. GPU worker — replaces `client.request(method, backend_url + path).headers(h).body(b).send()` and
+ *    the byte-stream relay (dispatcher.rs:287-312) with an on-box sm_100a engine, one per B200.
+ * ===================================================================================================== */
+typedef struct mq_worker mq_worker;
+typedef struct mq_req mq_req;
+
+typedef struct mq_model_cfg {
+  int32_t vocab, hidden, ffn, n_layers, n_q_heads, n_kv_heads, head_dim;
+  int32_t qkv_bias;        /* 1: Qwen2-style bias on q/k/v                                              */
+  float rope_theta;
+  float rms_eps;
+  int32_t max_batch;       /* capacity: concurrent sequences per worker (reference semantics: 1)         */
+  int32_t max_seq;         /* max prompt + generated tokens per sequence                                 */
+  int32_t max_prefill_tokens; /* prompt tokens processed per prefill pass                               */
+  int32_t kv_pages;        /* paged KV cache size in 16-token pages (0 = derive from max_batch*max_seq)  */
+  int32_t use_graphs;      /* 1: CUDA-graph the decode step                                              */
+  int32_t use_pdl;         /* 1: programmatic dependent launch between kernels                           */
+  char model_name[64];     /* echoed in response JSON ("model" field)                                    */
+} mq_model_cfg;
+
+/* number of usable B200 workers on this box (the reference's `--ollama-urls` list length)                */
+int mq_worker_count(void);
+int mq_worker_open(int32_t gpu, const mq_model_cfg* cfg, mq_worker** out);
+void mq_worker_close(mq_worker* w);
+
+/* weights: names are "embed", "final_norm", "lm_head", "layers.<i>.{attn_norm,wqkv,bqkv,wo,mlp_norm,
+ * w_gate_up,w_down}" (bf16, torch Linear [out,in] layout; wqkv = [q;k;v] rows, w_gate_up = [gate;up]).
+ * src/dst may be host or device memory.                                                                 */
+int mq_worker_load_tensor(mq_worker* w, const char* name, const void* src, size_t nbytes);
+int mq_worker_read_tensor(mq_worker* w, const char* name, void* dst, size_t nbytes);
+/* random-init every tensor on the device: N(0, std^2) from a counter-based generator, norms = 1        */
+int mq_worker_init_random(mq_worker* w, uint64_t seed, float std);
+
+/* BackendStatus analogues: capacity (:204 generalised) and health (:181-189: any answer = online)        */
+int mq_worker_capacity(mq_worker* w);
+int mq_worker_healthy(mq_worker* w);
+
+/* endpoints the worker terminates (routes of main.rs:92-112 that carry generation)                      */
+#define MQ_EP_API_GENERATE 0   /* /api/generate            NDJSON */
+#define MQ_EP_API_CHAT 1       /* /api/chat                NDJSON */
+#define MQ_EP_V1_CHAT 2        /* /v1/chat/completions     SSE    */
+#define MQ_EP_V1_COMPLETIONS 3 /* /v1/completions          SSE    */
+#define MQ_EP_RAW_TOKENS 4     /* no framing: chunks are little-endian int32 token ids                    */
+
+typedef struct mq_request {
+  int32_t endpoint;          /* MQ_EP_*                                                                   */
+  int32_t stream;            /* 1: one chunk per token; 0: one chunk at the end                           */
+  const uint8_t* body;       /* request body as the client sent it (JSON) — may be NULL with raw tokens   */
+  size_t body_len;
+  const int32_t* prompt_tokens; /* optional pre-tokenised prompt (synthetic workloads); overrides body    */
+  int32_t n_prompt_tokens;
+  int32_t max_new_tokens;    /* generation length; <=0: take options.num_predict / max_tokens from body   */
+  int32_t ignore_eos;        /* benchmark mode: always generate max_new_tokens                            */
+  uint32_t timeout_ms;       /* whole-request timeout (reqwest Client::timeout, :165-167); 0 = none       */
+} mq_request;
+
+typedef struct mq_callbacks {
+  /* exactly once, first: ResponsePart::Status (:299).                                                    */
+  void (*on_status)(void* user, int32_t http_status, const char* content_type);
+  /* 0..N times in order: ResponsePart::Chunk (:305).  Buffer valid only during the call.  A non-zero
+   * return means the client is gone (send().is_err(), :305-308): the worker cancels the request.          */
+  int32_t (*on_chunk)(void* user, const uint8_t* data, size_t len);
+  /* exactly once, last.  rc = 0: stream ended.  rc < 0 before on_status: ResponsePart::Error (:323-325). */
+  void (*on_done)(void* user, int32_t rc, const char* errmsg);
+} mq_callbacks;
+
+/* Non-blocking (the scheduler loop must not stall, :270).  The body and token arrays are copied before
+ * returning.  Callbacks fire on the worker's own host thread, never from inside mq_submit.               */
+int mq_submit(mq_worker* w, const mq_request* r, const mq_callbacks* cb, void* user, mq_req** out);
+/* client disconnect (:305-308): frees the KV pages; on_done still fires (rc = MQ_ERR_CANCELED).          */
+void mq_cancel(mq_req* r);
+/* release the handle after on_done has fired */
+void mq_req_release(mq_req* r);
+
+/* per-request timing, valid after on_done: microseconds from mq_submit to first token / last token       */
+typedef struct mq_req_stats {
+  uint64_t ttft_us, total_us;
+  int32_t n_prompt, n_generated;
+} mq_req_stats;
+int mq_req_get_stats(mq_req* r, mq_req_stats* out);
+
+/* worker counters for the roofline: kernels launched and CUDA-event time spent in prefill / decode      */
+typedef struct mq_worker_stats {
+  uint64_t kernel_launches, graph_launches, decode_steps, prefill_passes, prefill_tokens, decode_tokens;
+  double decode_ms, prefill_ms;       /* CUDA-event durations, summed (only when timing is enabled)       */
+  double decode_bytes;                /* algorithmic bytes moved by the timed decode steps    */
+} mq_worker_stats;
+int mq_worker_get_stats(mq_worker* w, mq_worker_stats* out);
+int mq_worker_reset_stats(mq_worker* w);
+int mq_worker_set_timing(mq_worker* w, int32_t enable);
+
+/* kernel-level test ABI (not on the serving path): logits of the last position of `tokens` (fp32 [vocab]),
+ * or of every position when all_positions != 0 (fp32 [n][vocab]); logits_out is host memory.              */
+int mq_debug_forward(mq_worker* w, const int32_t* tokens, int32_t n, int32_t all_positions, float* logits_out);
+
+/* =====================================================================================================
+ * 3. Dispatcher — AppState + run_worker + executor bookkeeping (dispatcher.rs:49-96,164-352) driving a
+ *    pool of workers in-process.  This is what `main()` would own in a Rust front (main.rs:82-87).
+ * ===================================================================================================== */
+typedef struct mq_dispatcher mq_dispatcher;
+
+int mq_dispatcher_new(mq_worker** workers, int32_t n_workers, int32_t capacity_override, mq_dispatcher** out);
+void mq_dispatcher_free(mq_dispatcher* d);
+/* proxy_handler (:354-428) minus HTTP: 403 pre-checks, enqueue, notify.  ip may be NULL.  Returns
+ * MQ_ERR_BLOCKED for a blocked ip/user (:370-378).  The callbacks see Status/Chunk/Done exactly as the
+ * reference's mpsc receiver would.                                                                       */
+int mq_dispatcher_submit(mq_dispatcher* d, const char* user, const char* ip, const mq_request* r,
+                         const mq_callbacks* cb, void* user_data, uint64_t* task_id_out);
+mq_sched* mq_dispatcher_sched(mq_dispatcher* d); /* borrowed; guarded by the dispatcher's lock            */
+int mq_dispatcher_set_vip(mq_dispatcher* d, const char* user);
+int mq_dispatcher_set_boost(mq_dispatcher* d, const char* user);
+int mq_dispatcher_block_user(mq_dispatcher* d, const char* user, int32_t blocked);   /* :127-153 */
+int mq_dispatcher_block_ip(mq_dispatcher* d, const char* ip, int32_t blocked);       /* :117-144 */
+/* dispatch log: (user, user_seq, backend) of every dispatch so far, in order — the parity observable     */
+int mq_dispatcher_log(mq_dispatcher* d, mq_dispatch* out, int32_t cap, int32_t* n_out);
+/* block until every submitted task has completed */
+int mq_dispatcher_drain(mq_dispatcher* d, uint32_t timeout_ms);
+
+/* =====================================================================================================
+ * 4. Kernel-level test ABI (device pointers).  See csrc/debug_api.cu.
+ * ===================================================================================================== */
+int mq_debug_gemm(const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T, int epi,
+                  void* out, int ldo, int splits, long long split_stride, int a2_row_off, int pdl, int reps,
+                  float* ms_out);
+int mq_debug_embed(const int* token_ids, const void* embed, float* h, int T, int H);
+int mq_debug_add_rmsnorm(float* h, const void* partial, int partial_is_f32, int n_planes, long long plane_stride,
+                         const void* gamma, void* x, const int* row_idx, int rows, int H, float eps);
+int mq_debug_rope_kv(const void* qkv, int qkv_is_f32, int n_planes, long long plane_stride, const void* bias,
+                     const int* pos, const int* slot_of_tok, const int* block_table, int max_pages,
+                     const float* inv_freq, void* q_out, void* k_cache, void* v_cache, int T, int n_q, int n_kv);
+int mq_debug_attn_prefill(const void* q, const void* k_cache, const void* v_cache, const int* block_table,
+                          int max_pages, const int* tiles, int n_tiles, void* out, int n_q, int n_kv, int T,
+                          float scale);
+int mq_debug_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* block_table,
+                         int max_pages, const int* pos, void* out, float* part_o, float* part_ml, int n_q, int n_kv,
+                         int n_slots, int n_splits, int kv_chunk, float scale);
+int mq_debug_argmax(const float* logits, int rows, int V, int ldl, int* out_tokens, const int* dst_slot,
+                    int* cur_token, int* pos_inc, const int* active);
+int mq_debug_init_normal(void* w, unsigned long long n, unsigned long long seed, float std);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OLLAMAMQ_B200_H */

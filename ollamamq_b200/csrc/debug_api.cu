@@ -1,0 +1,124 @@
+// Kernel-level test ABI ("plus a kernel-level test ABI, not on the serving path").
+// Plain C symbols taking raw DEVICE pointers so tests/ can compare every kernel with a torch reference
+// without going through the serving engine.  Nothing here is used by mq_submit().
+#include "../../include/ollamamq_b200.h"
+#include "gemm_host.cuh"
+#include "kernels.cuh"
+#include <cstdio>
+
+using namespace mq;
+
+namespace mq {
+void set_last_error(const char* fmt, ...);
+}
+
+static int check_cuda(const char* what) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    mq::set_last_error("%s: %s", what, cudaGetErrorString(e));
+    return MQ_ERR_CUDA;
+  }
+  return MQ_OK;
+}
+
+extern "C" {
+
+int mq_debug_gemm(const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T, int epi,
+                  void* out, int ldo, int splits, long long split_stride, int a2_row_off, int pdl, int reps,
+                  float* ms_out) {
+  GemmPlan g;
+  if (!gemm_plan(&g, W, w_rows, n_out, K, X, x_rows_alloc, T, epi, out, ldo, splits, split_stride, a2_row_off)) {
+    mq::set_last_error("gemm_plan failed (K%%64, splits, or cuTensorMapEncodeTiled)");
+    return MQ_ERR_INVAL;
+  }
+  LaunchCfg lc{0, pdl != 0};
+  cudaError_t e = gemm_launch(g, lc);
+  if (e != cudaSuccess) {
+    mq::set_last_error("gemm_launch: %s", cudaGetErrorString(e));
+    return MQ_ERR_CUDA;
+  }
+  int rc = check_cuda("mq_debug_gemm");
+  if (rc != MQ_OK) return rc;
+  if (reps > 0 && ms_out) {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, 0);
+    for (int i = 0; i < reps; ++i) gemm_launch(g, lc);
+    cudaEventRecord(b, 0);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    *ms_out = ms / reps;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return check_cuda("mq_debug_gemm(timed)");
+  }
+  return MQ_OK;
+}
+
+int mq_debug_embed(const int* token_ids, const void* embed, float* h, int T, int H) {
+  launch_embed(LaunchCfg{0, false}, token_ids, (const __nv_bfloat16*)embed, h, T, H);
+  return check_cuda("mq_debug_embed");
+}
+
+int mq_debug_add_rmsnorm(float* h, const void* partial, int partial_is_f32, int n_planes, long long plane_stride,
+                         const void* gamma, void* x, const int* row_idx, int rows, int H, float eps) {
+  if (H % 512 != 0) {
+    mq::set_last_error("H must be a multiple of 512");
+    return MQ_ERR_INVAL;
+  }
+  launch_add_rmsnorm(LaunchCfg{0, false}, h, partial, partial_is_f32 != 0, n_planes, plane_stride,
+                     (const __nv_bfloat16*)gamma, (__nv_bfloat16*)x, row_idx, rows, H, eps);
+  return check_cuda("mq_debug_add_rmsnorm");
+}
+
+int mq_debug_rope_kv(const void* qkv, int qkv_is_f32, int n_planes, long long plane_stride, const void* bias,
+                     const int* pos, const int* slot_of_tok, const int* block_table, int max_pages,
+                     const float* inv_freq, void* q_out, void* k_cache, void* v_cache, int T, int n_q, int n_kv) {
+  RopeKvParams p;
+  p.qkv = qkv; p.qkv_is_f32 = qkv_is_f32 != 0; p.n_planes = n_planes; p.plane_stride = plane_stride;
+  p.bias = (const __nv_bfloat16*)bias; p.pos = pos; p.slot_of_tok = slot_of_tok; p.block_table = block_table;
+  p.max_pages = max_pages; p.inv_freq = inv_freq; p.q_out = (__nv_bfloat16*)q_out;
+  p.k_cache = (__nv_bfloat16*)k_cache; p.v_cache = (__nv_bfloat16*)v_cache; p.T = T; p.n_q = n_q; p.n_kv = n_kv;
+  launch_rope_kv(LaunchCfg{0, false}, p);
+  return check_cuda("mq_debug_rope_kv");
+}
+
+int mq_debug_attn_prefill(const void* q, const void* k_cache, const void* v_cache, const int* block_table,
+                          int max_pages, const int* tiles /* int4 per tile */, int n_tiles, void* out, int n_q,
+                          int n_kv, int T, float scale) {
+  AttnParams p = {};
+  p.q = (const __nv_bfloat16*)q; p.k_cache = (const __nv_bfloat16*)k_cache; p.v_cache = (const __nv_bfloat16*)v_cache;
+  p.block_table = block_table; p.max_pages = max_pages; p.tiles = (const int4*)tiles; p.out = (__nv_bfloat16*)out;
+  p.n_q = n_q; p.n_kv = n_kv; p.T = T; p.n_splits = 1; p.kv_chunk = 1 << 30;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  launch_attn_prefill(LaunchCfg{0, false}, p, n_tiles);
+  return check_cuda("mq_debug_attn_prefill");
+}
+
+int mq_debug_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* block_table,
+                         int max_pages, const int* pos, void* out, float* part_o, float* part_ml, int n_q, int n_kv,
+                         int n_slots, int n_splits, int kv_chunk, float scale) {
+  AttnParams p = {};
+  p.q = (const __nv_bfloat16*)q; p.k_cache = (const __nv_bfloat16*)k_cache; p.v_cache = (const __nv_bfloat16*)v_cache;
+  p.block_table = block_table; p.max_pages = max_pages; p.pos = pos; p.out = (__nv_bfloat16*)out;
+  p.part_o = part_o; p.part_ml = part_ml; p.n_q = n_q; p.n_kv = n_kv; p.T = n_slots; p.n_splits = n_splits;
+  p.kv_chunk = kv_chunk; p.scale_log2 = scale * 1.4426950408889634f;
+  launch_attn_decode(LaunchCfg{0, false}, p, n_slots);
+  return check_cuda("mq_debug_attn_decode");
+}
+
+int mq_debug_argmax(const float* logits, int rows, int V, int ldl, int* out_tokens, const int* dst_slot,
+                    int* cur_token, int* pos_inc, const int* active) {
+  launch_argmax(LaunchCfg{0, false}, logits, rows, V, ldl, out_tokens, dst_slot, cur_token, pos_inc, active);
+  return check_cuda("mq_debug_argmax");
+}
+
+int mq_debug_init_normal(void* w, unsigned long long n, unsigned long long seed, float std) {
+  launch_init_normal(0, (__nv_bfloat16*)w, (size_t)n, seed, std);
+  return check_cuda("mq_debug_init_normal");
+}
+
+}  // extern "C"

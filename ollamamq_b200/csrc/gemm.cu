@@ -1,0 +1,111 @@
+// Host side of the tcgen05 GEMM: TMA descriptor construction + template dispatch.
+#include "gemm_host.cuh"
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace mq {
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    // Resolved through the runtime so libollamamq_b200.so carries no link-time dependency on libcuda.so
+    // (the library must dlopen on a CPU-only box for the symbol-export test).
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+bool tmap_encode_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {cols * 2};  // bytes, dim 1
+  const cuuint32_t box[2] = {(cuuint32_t)kBlockK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN, int EPI>
+static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid,
+                              const LaunchCfg& lc) {
+  constexpr int smem = gemm_smem_bytes(BN, EPI);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_wx_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lc.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, gemm_wx_kernel<BN, EPI>, a, b, p);
+}
+
+template <int EPI>
+static cudaError_t launch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid,
+                             const LaunchCfg& lc) {
+  switch (bn) {
+    case 16: return launch_one<16, EPI>(a, b, p, grid, lc);
+    case 32: return launch_one<32, EPI>(a, b, p, grid, lc);
+    case 64: return launch_one<64, EPI>(a, b, p, grid, lc);
+    case 128: return launch_one<128, EPI>(a, b, p, grid, lc);
+    case 256: return launch_one<256, EPI>(a, b, p, grid, lc);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
+  dim3 grid((g.p.n_out + kBlockM - 1) / kBlockM, (g.p.T + g.bn - 1) / g.bn, g.splits);
+  switch (g.epi) {
+    case EPI_F32: return launch_bn<EPI_F32>(g.bn, g.tmA, g.tmB, g.p, grid, lc);
+    case EPI_BF16: return launch_bn<EPI_BF16>(g.bn, g.tmA, g.tmB, g.p, grid, lc);
+    case EPI_SILU_BF16: return launch_bn<EPI_SILU_BF16>(g.bn, g.tmA, g.tmB, g.p, grid, lc);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+int gemm_pick_bn(int T) {
+  if (T <= 16) return 16;
+  if (T <= 32) return 32;
+  if (T <= 64) return 64;
+  if (T <= 128) return 128;
+  return 256;
+}
+
+bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T,
+               int epi, void* out, int ldo, int splits, long long split_stride, int a2_row_off) {
+  if (K % kBlockK != 0) return false;
+  const int kb = K / kBlockK;
+  if (splits < 1 || kb % splits != 0) return false;
+  g->bn = gemm_pick_bn(T);
+  g->epi = epi;
+  g->splits = splits;
+  if (!tmap_encode_2d(&g->tmA, W, (uint64_t)w_rows, (uint64_t)K, kBlockM)) return false;
+  if (!tmap_encode_2d(&g->tmB, X, (uint64_t)x_rows_alloc, (uint64_t)K, (uint32_t)g->bn)) return false;
+  g->p.out = out;
+  g->p.split_stride = split_stride;
+  g->p.ldo = ldo;
+  g->p.T = T;
+  g->p.n_out = n_out;
+  g->p.k_blocks = kb;
+  g->p.kb_per_split = kb / splits;
+  g->p.a2_row_off = a2_row_off;
+  return true;
+}
+
+}  // namespace mq

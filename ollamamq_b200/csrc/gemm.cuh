@@ -1,0 +1,204 @@
+// Weight-stationary-A tcgen05 GEMM for the forward pass (replaces the arithmetic behind the reference's
+// backend call, /root/reference/src/dispatcher.rs:287-290).
+//
+//   out[t, f] = sum_k X[t, k] * W[f, k]          X: [T, K] bf16 row-major (activations)
+//                                                W: [N_out, K] bf16 row-major (torch Linear layout)
+//
+// The UMMA "A" operand (M = 128 TMEM lanes) is a 128-row tile of W, the "B" operand (N = BN TMEM columns)
+// is a BN-row tile of X.  One kernel therefore serves both regimes:
+//   * decode  (T = running sequences <= 256): the weights stream through the tensor core at HBM rate while
+//     the whole batch sits in one N tile; split-K (gridDim.z) fills the 148 SMs and the fp32 partial
+//     planes are summed by the consumer kernel (rmsnorm / rope), so the residual add is fused for free;
+//   * prefill (T = thousands of prompt tokens): BN = 256 tiles, tensor-pipe bound.
+//
+// Pipeline per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> global).  Weight tiles of the first ring pass are requested
+// BEFORE griddepcontrol.wait, so under programmatic dependent launch the HBM stream of this GEMM starts
+// while the previous kernel is still draining.
+#pragma once
+#include <cuda.h>
+#include "ptx.cuh"
+
+namespace mq {
+
+enum GemmEpilogue : int {
+  EPI_F32 = 0,       // out_f32[z][t][f] = acc                       (split-K partial planes)
+  EPI_BF16 = 1,      // out_bf16[t][f]   = acc
+  EPI_SILU_BF16 = 2  // out_bf16[t][f]   = silu(acc_gate) * acc_up   (two A tiles: rows f and f + a2_row_off)
+};
+
+struct GemmParams {
+  void* out;
+  long long split_stride;  // elements between split-K planes of `out`
+  int ldo;                 // leading dimension of out (elements)
+  int T;                   // valid rows of X
+  int n_out;               // valid output features
+  int k_blocks;            // K / 64
+  int kb_per_split;        // k-blocks handled by one blockIdx.z
+  int a2_row_off;          // EPI_SILU_BF16: row offset of the "up" half inside W
+};
+
+constexpr int kGemmThreads = 192;
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
+
+__host__ __device__ constexpr int gemm_stage_bytes(int bn, int epi) {
+  return kATileBytes * (epi == EPI_SILU_BF16 ? 2 : 1) + bn * kBlockK * 2;
+}
+__host__ __device__ constexpr int gemm_stages(int bn, int epi) {
+  int s = (200 * 1024) / gemm_stage_bytes(bn, epi);
+  return s > 8 ? 8 : s;
+}
+__host__ __device__ constexpr int gemm_smem_bytes(int bn, int epi) {
+  return gemm_stages(bn, epi) * gemm_stage_bytes(bn, epi) + 1024 /*align*/ + 256 /*barriers*/;
+}
+__host__ __device__ constexpr uint32_t gemm_tmem_cols(int bn, int epi) {
+  int need = bn * (epi == EPI_SILU_BF16 ? 2 : 1);
+  return need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmParams p) {
+  constexpr bool kDual = (EPI == EPI_SILU_BF16);
+  constexpr int STAGES = gemm_stages(BN, EPI);
+  constexpr int STAGE_BYTES = gemm_stage_bytes(BN, EPI);
+  constexpr int B_OFF = kATileBytes * (kDual ? 2 : 1);
+  constexpr uint32_t TMEM_COLS = gemm_tmem_cols(BN, EPI);
+  constexpr uint32_t IDESC = umma_idesc_bf16(kBlockM, BN);
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
+  static_assert(!kDual || BN * 2 <= 512, "dual accumulator must fit TMEM");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBlockM;
+  const int n0 = blockIdx.y * BN;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int nkb = min(p.kb_per_split, p.k_blocks - kb0);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  // Let the next kernel in the stream begin its own prologue (it still waits for our completion
+  // through griddepcontrol.wait before touching anything we write).
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      const int npre = nkb < STAGES ? nkb : STAGES;
+      for (int s = 0; s < npre; ++s) {
+        uint8_t* st = smem + s * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        tma_load_2d(st, &tmA, &full_bar[s], (kb0 + s) * kBlockK, m0, kEvictFirst);
+        if (kDual) tma_load_2d(st + kATileBytes, &tmA, &full_bar[s], (kb0 + s) * kBlockK, m0 + p.a2_row_off, kEvictFirst);
+      }
+      pdl_wait();  // activations are produced by the previous kernel
+      for (int s = 0; s < npre; ++s)
+        tma_load_2d(smem + s * STAGE_BYTES + B_OFF, &tmB, &full_bar[s], (kb0 + s) * kBlockK, n0, kEvictLast);
+      for (int kb = npre; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* st = smem + s * STAGE_BYTES;
+        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        tma_load_2d(st, &tmA, &full_bar[s], (kb0 + kb) * kBlockK, m0, kEvictFirst);
+        if (kDual) tma_load_2d(st + kATileBytes, &tmA, &full_bar[s], (kb0 + kb) * kBlockK, m0 + p.a2_row_off, kEvictFirst);
+        tma_load_2d(st + B_OFF, &tmB, &full_bar[s], (kb0 + kb) * kBlockK, n0, kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer (single thread) ----------------
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + B_OFF;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t db = umma_desc_sw128(b_addr + k * 32);
+          const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+          umma_bf16(tmem_base, umma_desc_sw128(a_addr + k * 32), db, IDESC, acc);
+          if (kDual) umma_bf16(tmem_base + BN, umma_desc_sw128(a_addr + kATileBytes + k * 32), db, IDESC, acc);
+        }
+        umma_commit(&empty_bar[s]);  // smem slot reusable once these MMAs retire
+      }
+      umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: TMEM lane = output feature, TMEM column = token ----------------
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    const int f = m0 + q * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const bool f_ok = f < p.n_out;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      if (n0 + c0 >= p.T) break;  // warp-uniform
+      uint32_t v[16];
+      tmem_ld16(t_lane + c0, v);
+      if constexpr (kDual) {
+        uint32_t u[16];
+        tmem_ld16(t_lane + BN + c0, u);
+        tmem_ld_wait();
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int t = n0 + c0 + j;
+          const float g = __uint_as_float(v[j]);
+          const float up = __uint_as_float(u[j]);
+          const float r = g / (1.0f + __expf(-g)) * up;
+          if (f_ok && t < p.T) o[(long long)t * p.ldo + f] = __float2bfloat16(r);
+        }
+      } else {
+        tmem_ld_wait();
+        if constexpr (EPI == EPI_F32) {
+          float* o = reinterpret_cast<float*>(p.out) + (long long)blockIdx.z * p.split_stride;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int t = n0 + c0 + j;
+            if (f_ok && t < p.T) o[(long long)t * p.ldo + f] = __uint_as_float(v[j]);
+          }
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int t = n0 + c0 + j;
+            if (f_ok && t < p.T) o[(long long)t * p.ldo + f] = __float2bfloat16(__uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+}  // namespace mq

@@ -1,0 +1,31 @@
+// Host-side plan for one tcgen05 GEMM launch (TMA maps + params are built once and re-used every step).
+#pragma once
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace mq {
+
+struct GemmPlan {
+  CUtensorMap tmA;  // weights  [w_rows, K], box {64, 128}
+  CUtensorMap tmB;  // activations [x_rows, K], box {64, bn}
+  GemmParams p;
+  int bn;
+  int epi;
+  int splits;
+};
+
+// Encode a row-major bf16 [rows, cols] tensor with a {64, box_rows} box and the 128-byte swizzle.
+bool tmap_encode_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+
+// Token-tile width for T activation rows.
+int gemm_pick_bn(int T);
+
+// out[t, f] (+ split planes) = X[t, :] . W[f, :]
+//   w_rows       rows of the weight tensor (n_out, or 2*n_out for the gate|up tensor)
+//   x_rows_alloc rows the activation buffer really has (TMA bounds; rows >= T read as-is, >= alloc as zero)
+bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T,
+               int epi, void* out, int ldo, int splits, long long split_stride, int a2_row_off);
+
+cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc);
+
+}  // namespace mq

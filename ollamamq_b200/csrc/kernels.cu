@@ -1,0 +1,533 @@
+// Non-GEMM kernels of the transformer forward pass, hand-written for sm_100a.
+//
+// These are the HBM/latency-bound pieces around the tcgen05 GEMMs (gemm.cuh).  Together they stand in for
+// the arithmetic the reference delegates to a remote Ollama server (/root/reference/src/dispatcher.rs:287-290).
+// All of them call griddepcontrol.wait first and griddepcontrol.launch_dependents right after, so a whole
+// decode step can be chained with programmatic dependent launch without ever reading stale data.
+//
+//   embed            gather rows of the embedding table into the fp32 residual stream
+//   add_rmsnorm      residual += sum(split-K partial planes); x = RMSNorm(residual) * gamma   (fused)
+//   rope_kv          sum QKV partials (+bias), rotate q/k (rotate-half RoPE), write K/V into the paged cache
+//   paged_attn       FlashAttention-2 style online softmax over the paged KV cache; GQA group fused into
+//                    the M dimension (row = token x head-in-group), 128-bit cp.async loads, mma.sync QK^T/PV,
+//                    quad warp-shuffle softmax; decode variant is split-KV with one warp per CTA
+//   attn_combine     merge the split-KV partials
+//   argmax           greedy sampler + device-side advance of (cur_token, pos) so decode steps chain on the GPU
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace mq {
+
+// ------------------------------------------------------------------------------------------------
+// launch helper
+// ------------------------------------------------------------------------------------------------
+template <typename... KArgs, typename... Args>
+static void launch_k(const LaunchCfg& lc, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lc.pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding gather
+// ------------------------------------------------------------------------------------------------
+__global__ void embed_kernel(const int* __restrict__ token_ids, const __nv_bfloat16* __restrict__ embed,
+                             float* __restrict__ h, int H) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int t = blockIdx.x;
+  const int tok = token_ids[t];
+  const uint4* src = reinterpret_cast<const uint4*>(embed + (size_t)tok * H);
+  float4* dst = reinterpret_cast<float4*>(h + (size_t)t * H);
+  for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
+    const uint4 v = src[i];
+    dst[2 * i] = make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
+    dst[2 * i + 1] = make_float4(bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w));
+  }
+}
+void launch_embed(const LaunchCfg& lc, const int* token_ids, const __nv_bfloat16* embed, float* h, int T, int H) {
+  launch_k(lc, embed_kernel, dim3(T), dim3(128), 0, token_ids, embed, h, H);
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused residual-add + RMSNorm.  One CTA per row, blockDim = H/16, every thread keeps 16 values in registers.
+// ------------------------------------------------------------------------------------------------
+template <bool F32>
+__global__ void add_rmsnorm_kernel(float* __restrict__ h, const void* __restrict__ partial, int n_planes,
+                                   long long plane_stride, const __nv_bfloat16* __restrict__ gamma,
+                                   __nv_bfloat16* __restrict__ x, const int* __restrict__ row_idx, int H, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.x;
+  const int src = row_idx ? row_idx[row] : row;
+  const int nthr = blockDim.x;
+  float4 v[4];
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i4 = threadIdx.x + j * nthr;  // float4 index inside the row
+    float4 a = reinterpret_cast<const float4*>(h + (size_t)src * H)[i4];
+    if (F32) {
+      const float* pp = reinterpret_cast<const float*>(partial);
+      for (int s = 0; s < n_planes; ++s) {
+        const float4 b = reinterpret_cast<const float4*>(pp + s * plane_stride + (size_t)src * H)[i4];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+    } else if (n_planes > 0) {
+      const uint2 b = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(partial) + (size_t)src * H)[i4];
+      a.x += bf16_lo(b.x); a.y += bf16_hi(b.x); a.z += bf16_lo(b.y); a.w += bf16_hi(b.y);
+    }
+    v[j] = a;
+    ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    if (!row_idx) reinterpret_cast<float4*>(h + (size_t)src * H)[i4] = a;
+  }
+  __shared__ float red[32];
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < (nthr + 31) / 32; ++w) tot += red[w];
+  const float rstd = rsqrtf(tot / (float)H + eps);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int i4 = threadIdx.x + j * nthr;
+    const uint2 gm = reinterpret_cast<const uint2*>(gamma)[i4];
+    uint2 o;
+    o.x = pack_bf16(v[j].x * rstd * bf16_lo(gm.x), v[j].y * rstd * bf16_hi(gm.x));
+    o.y = pack_bf16(v[j].z * rstd * bf16_lo(gm.y), v[j].w * rstd * bf16_hi(gm.y));
+    reinterpret_cast<uint2*>(x + (size_t)row * H)[i4] = o;
+  }
+}
+void launch_add_rmsnorm(const LaunchCfg& lc, float* h, const void* partial, bool partial_is_f32, int n_planes,
+                        long long plane_stride, const __nv_bfloat16* gamma, __nv_bfloat16* x, const int* row_idx,
+                        int rows, int H, float eps) {
+  const int thr = H / 16;  // H % 512 == 0 is checked at model load
+  if (partial_is_f32)
+    launch_k(lc, add_rmsnorm_kernel<true>, dim3(rows), dim3(thr), 0, h, partial, n_planes, plane_stride, gamma, x,
+             row_idx, H, eps);
+  else
+    launch_k(lc, add_rmsnorm_kernel<false>, dim3(rows), dim3(thr), 0, h, partial, n_planes, plane_stride, gamma, x,
+             row_idx, H, eps);
+}
+
+// ------------------------------------------------------------------------------------------------
+// RoPE + paged KV write.  One CTA (256 threads) per token; a thread owns the rotation pair (i, i+64).
+// ------------------------------------------------------------------------------------------------
+template <bool F32>
+__device__ __forceinline__ float qkv_at(const RopeKvParams& p, int t, int col, int qkv_dim) {
+  float v;
+  if (F32) {
+    const float* pp = reinterpret_cast<const float*>(p.qkv);
+    v = 0.f;
+    for (int s = 0; s < p.n_planes; ++s) v += pp[s * p.plane_stride + (size_t)t * qkv_dim + col];
+  } else {
+    v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.qkv)[(size_t)t * qkv_dim + col]);
+  }
+  if (p.bias) v += __bfloat162float(p.bias[col]);
+  return v;
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  constexpr int D = kHeadDim, HALF = D / 2;
+  const int t = blockIdx.x;
+  const int pos = p.pos[t];
+  const int slot = p.slot_of_tok[t];
+  const int qkv_dim = (p.n_q + 2 * p.n_kv) * D;
+  const int i = threadIdx.x & (HALF - 1);  // pair index
+  const int hsub = threadIdx.x >> 6;       // 4 heads per pass
+  float sn, cs;
+  sincosf((float)pos * p.inv_freq[i], &sn, &cs);
+  const int page = p.block_table[(size_t)slot * p.max_pages + pos / kPageSize];
+  const int in_page = pos % kPageSize;
+  // q heads then k heads: rotate
+  for (int hd = hsub; hd < p.n_q + p.n_kv; hd += 4) {
+    const int col = hd * D + i;
+    const float a = qkv_at<F32>(p, t, col, qkv_dim);
+    const float b = qkv_at<F32>(p, t, col + HALF, qkv_dim);
+    const __nv_bfloat16 r0 = __float2bfloat16(a * cs - b * sn);
+    const __nv_bfloat16 r1 = __float2bfloat16(b * cs + a * sn);
+    if (hd < p.n_q) {
+      __nv_bfloat16* q = p.q_out + (size_t)t * p.n_q * D + hd * D;
+      q[i] = r0;
+      q[i + HALF] = r1;
+    } else {
+      const int kvh = hd - p.n_q;
+      __nv_bfloat16* k = p.k_cache + (((size_t)page * p.n_kv + kvh) * kPageSize + in_page) * D;
+      k[i] = r0;
+      k[i + HALF] = r1;
+    }
+  }
+  // v heads: plain copy
+  for (int e = threadIdx.x; e < p.n_kv * D; e += blockDim.x) {
+    const int kvh = e / D, d = e % D;
+    const float v = qkv_at<F32>(p, t, (p.n_q + p.n_kv) * D + e, qkv_dim);
+    p.v_cache[(((size_t)page * p.n_kv + kvh) * kPageSize + in_page) * D + d] = __float2bfloat16(v);
+  }
+}
+void launch_rope_kv(const LaunchCfg& lc, const RopeKvParams& p) {
+  if (p.qkv_is_f32)
+    launch_k(lc, rope_kv_kernel<true>, dim3(p.T), dim3(256), 0, p);
+  else
+    launch_k(lc, rope_kv_kernel<false>, dim3(p.T), dim3(256), 0, p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// paged flash attention (prefill + decode)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Rows of Q/K/V tiles are 256 B (128 bf16) = 16 chunks of 16 B; chunk index is XOR-swizzled with (row & 7)
+// so ldmatrix (8 rows x 16 B at one logical chunk column) is bank-conflict free.
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return (uint32_t)(row * 16 + (chunk ^ (row & 7))) * 16u; }
+
+template <int NW, int TN, bool DECODE>
+__global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p) {
+  constexpr int D = kHeadDim;
+  constexpr int R = NW * 16;
+  constexpr int NT = TN / 8;  // score n-tiles per kv tile
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* Qs = smem;
+  uint8_t* Ks = Qs + R * D * 2;
+  uint8_t* Vs = Ks + 2 * TN * D * 2;
+
+  pdl_wait();
+  pdl_launch_dependents();
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const int kvh = blockIdx.y;
+  const int G = p.n_q / p.n_kv;
+  int tok0, ntok, slot, pos0;
+  if (DECODE) {
+    slot = blockIdx.x; tok0 = slot; ntok = 1; pos0 = p.pos[slot];
+  } else {
+    const int4 t = p.tiles[blockIdx.x];
+    tok0 = t.x; ntok = t.y; slot = t.z; pos0 = t.w;
+  }
+  const int n_rows = ntok * G;
+  int kv_begin = 0, kv_end = pos0 + ntok;
+  if (DECODE) {
+    kv_begin = blockIdx.z * p.kv_chunk;
+    kv_end = min(kv_end, kv_begin + p.kv_chunk);
+  }
+  const int* btab = p.block_table + (size_t)slot * p.max_pages;
+
+  if (kv_begin >= kv_end) {  // empty split (decode only): neutral partial
+    if (DECODE) {
+      for (int r = tid; r < n_rows; r += NW * 32) {
+        const int head = kvh * G + r;
+        float* ml = p.part_ml + (((size_t)blockIdx.z * p.T + tok0) * p.n_q + head) * 2;
+        ml[0] = -INFINITY;
+        ml[1] = 0.f;
+      }
+    }
+    return;
+  }
+
+  // ---- Q tile -> smem (zero-filled beyond the valid rows)
+  for (int i = tid; i < R * 16; i += NW * 32) {
+    const int r = i >> 4, ch = i & 15;
+    const bool ok = r < n_rows;
+    const int rr = ok ? r : 0;
+    const int tok = tok0 + rr / G, head = kvh * G + rr % G;
+    cp_async16(Qs + tile_off(r, ch), p.q + ((size_t)tok * p.n_q + head) * D + ch * 8, ok ? 16 : 0);
+  }
+  auto load_kv = [&](int stage, int t0) {
+    uint8_t* kst = Ks + stage * TN * D * 2;
+    uint8_t* vst = Vs + stage * TN * D * 2;
+    for (int i = tid; i < TN * 16; i += NW * 32) {
+      const int j = i >> 4, ch = i & 15;
+      const int kvpos = t0 + j;
+      const bool ok = kvpos < kv_end;
+      const int pp = ok ? kvpos : kv_end - 1;
+      const int page = btab[pp / kPageSize];
+      const size_t off = (((size_t)page * p.n_kv + kvh) * kPageSize + pp % kPageSize) * D + ch * 8;
+      cp_async16(kst + tile_off(j, ch), p.k_cache + off, ok ? 16 : 0);
+      cp_async16(vst + tile_off(j, ch), p.v_cache + off, ok ? 16 : 0);
+    }
+  };
+  load_kv(0, kv_begin);
+  cp_async_commit();
+
+  float o[16][4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY};
+  float l_run[2] = {0.f, 0.f};
+  uint32_t qf[8][4];
+
+  const int row_a = warp * 16 + g, row_b = row_a + 8;
+  const int qpos_a = pos0 + row_a / G, qpos_b = pos0 + row_b / G;
+  const int n_tiles = (kv_end - kv_begin + TN - 1) / TN;
+
+  for (int it = 0; it < n_tiles; ++it) {
+    const int t0 = kv_begin + it * TN;
+    if (it + 1 < n_tiles) {
+      load_kv((it + 1) & 1, t0 + TN);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    if (it == 0) {
+      const uint32_t qbase = smem_u32(Qs);
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const int r = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+        ldsm_x4(qbase + tile_off(r, ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+      }
+    }
+    const uint32_t kbase = smem_u32(Ks + (it & 1) * TN * D * 2);
+    const uint32_t vbase = smem_u32(Vs + (it & 1) * TN * D * 2);
+
+    // ---- S = Q K^T
+    float s[NT][4];
+#pragma unroll
+    for (int n2 = 0; n2 < NT / 2; ++n2) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[2 * n2][e] = s[2 * n2 + 1][e] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const int r = n2 * 16 + (lane & 7) + 8 * (lane >> 4);
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(kbase + tile_off(r, ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+        mma_bf16_16816(s[2 * n2], qf[ks], b0, b1);
+        mma_bf16_16816(s[2 * n2 + 1], qf[ks], b2, b3);
+      }
+    }
+    // ---- mask + online softmax (rows g and g+8 of this warp's 16-row slab)
+    float mx_a = -INFINITY, mx_b = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = t0 + n * 8 + 2 * c + (e & 1);
+        const int qpos = (e < 2) ? qpos_a : qpos_b;
+        const bool ok = (col <= qpos) && (col < kv_end);
+        const float v = ok ? s[n][e] * p.scale_log2 : -INFINITY;
+        s[n][e] = v;
+        if (e < 2) mx_a = fmaxf(mx_a, v); else mx_b = fmaxf(mx_b, v);
+      }
+    }
+    mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
+    mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+    mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
+    mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+    const float mn_a = fmaxf(m_run[0], mx_a), mn_b = fmaxf(m_run[1], mx_b);
+    const float mu_a = (mn_a == -INFINITY) ? 0.f : mn_a;
+    const float mu_b = (mn_b == -INFINITY) ? 0.f : mn_b;
+    const float al_a = exp2f(m_run[0] - mu_a), al_b = exp2f(m_run[1] - mu_b);
+    m_run[0] = mn_a; m_run[1] = mn_b;
+    float sum_a = 0.f, sum_b = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      s[n][0] = exp2f(s[n][0] - mu_a); s[n][1] = exp2f(s[n][1] - mu_a);
+      s[n][2] = exp2f(s[n][2] - mu_b); s[n][3] = exp2f(s[n][3] - mu_b);
+      sum_a += s[n][0] + s[n][1];
+      sum_b += s[n][2] + s[n][3];
+    }
+    l_run[0] = l_run[0] * al_a + sum_a;
+    l_run[1] = l_run[1] * al_b + sum_b;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { o[i][0] *= al_a; o[i][1] *= al_a; o[i][2] *= al_b; o[i][3] *= al_b; }
+    // ---- O += P V
+#pragma unroll
+    for (int kt = 0; kt < TN / 16; ++kt) {
+      uint32_t a[4];
+      a[0] = pack_bf16(s[2 * kt][0], s[2 * kt][1]);
+      a[1] = pack_bf16(s[2 * kt][2], s[2 * kt][3]);
+      a[2] = pack_bf16(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+      a[3] = pack_bf16(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+#pragma unroll
+      for (int d2 = 0; d2 < 8; ++d2) {
+        const int r = kt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4_t(vbase + tile_off(r, d2 * 2 + (lane >> 4)), b0, b1, b2, b3);
+        mma_bf16_16816(o[2 * d2], a, b0, b1);
+        mma_bf16_16816(o[2 * d2 + 1], a, b2, b3);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- finalize
+  float l_a = l_run[0], l_b = l_run[1];
+  l_a += __shfl_xor_sync(0xffffffffu, l_a, 1); l_a += __shfl_xor_sync(0xffffffffu, l_a, 2);
+  l_b += __shfl_xor_sync(0xffffffffu, l_b, 1); l_b += __shfl_xor_sync(0xffffffffu, l_b, 2);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int row = half ? row_b : row_a;
+    if (row >= n_rows) continue;
+    const int tok = tok0 + row / G, head = kvh * G + row % G;
+    const float l = half ? l_b : l_a;
+    if (DECODE) {
+      const size_t base = ((size_t)blockIdx.z * p.T + tok) * p.n_q + head;
+      float* po = p.part_o + base * D;
+#pragma unroll
+      for (int n = 0; n < 16; ++n)
+        *reinterpret_cast<float2*>(po + n * 8 + 2 * c) = make_float2(o[n][2 * half], o[n][2 * half + 1]);
+      if (c == 0) {
+        p.part_ml[base * 2] = m_run[half];
+        p.part_ml[base * 2 + 1] = l;
+      }
+    } else {
+      const float inv = 1.f / l;
+      __nv_bfloat16* po = p.out + ((size_t)tok * p.n_q + head) * D;
+#pragma unroll
+      for (int n = 0; n < 16; ++n)
+        *reinterpret_cast<uint32_t*>(po + n * 8 + 2 * c) = pack_bf16(o[n][2 * half] * inv, o[n][2 * half + 1] * inv);
+    }
+  }
+}
+
+// merge split-KV partials: one CTA of 128 threads per (slot, q head)
+__global__ void __launch_bounds__(128) attn_combine_kernel(const AttnParams p) {
+  pdl_wait();
+  pdl_launch_dependents();
+  constexpr int D = kHeadDim;
+  const int tok = blockIdx.x, head = blockIdx.y, d = threadIdx.x;
+  float M = -INFINITY;
+  for (int s = 0; s < p.n_splits; ++s) M = fmaxf(M, p.part_ml[(((size_t)s * p.T + tok) * p.n_q + head) * 2]);
+  float acc = 0.f, L = 0.f;
+  for (int s = 0; s < p.n_splits; ++s) {
+    const size_t base = ((size_t)s * p.T + tok) * p.n_q + head;
+    const float m = p.part_ml[base * 2];
+    if (m == -INFINITY) continue;
+    const float w = exp2f(m - M);
+    L += p.part_ml[base * 2 + 1] * w;
+    acc += p.part_o[base * D + d] * w;
+  }
+  p.out[((size_t)tok * p.n_q + head) * D + d] = __float2bfloat16(L > 0.f ? acc / L : 0.f);
+}
+
+void launch_attn_prefill(const LaunchCfg& lc, const AttnParams& p, int n_tiles) {
+  constexpr int NW = kPrefillTileRows / 16, TN = 64;
+  constexpr int smem = (NW * 16 + 4 * TN) * kHeadDim * 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(paged_attn_kernel<NW, TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_set = true;
+  }
+  launch_k(lc, paged_attn_kernel<NW, TN, false>, dim3(n_tiles, p.n_kv, 1), dim3(NW * 32), smem, p);
+}
+void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots) {
+  constexpr int NW = 1, TN = 32;
+  constexpr int smem = (NW * 16 + 4 * TN) * kHeadDim * 2;
+  launch_k(lc, paged_attn_kernel<NW, TN, true>, dim3(n_slots, p.n_kv, p.n_splits), dim3(NW * 32), smem, p);
+  launch_k(lc, attn_combine_kernel, dim3(n_slots, p.n_q), dim3(128), 0, p);
+}
+
+// ------------------------------------------------------------------------------------------------
+// greedy sampler: argmax over the vocabulary (lowest index wins ties), then advance the slot state
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int V, int ldl,
+                                                      int* __restrict__ out_tokens, const int* __restrict__ dst_slot,
+                                                      int* __restrict__ cur_token, int* __restrict__ pos_inc,
+                                                      const int* __restrict__ active) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int row = blockIdx.x;
+  const float4* lp = reinterpret_cast<const float4*>(logits + (size_t)row * ldl);
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V / 4; i += blockDim.x) {
+    const float4 v = lp[i];
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = i * 4 + e;
+      if (vv[e] > best || (vv[e] == best && idx < bi)) { best = vv[e]; bi = idx; }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  __shared__ float sb[32];
+  __shared__ int si[32];
+  if ((threadIdx.x & 31) == 0) { sb[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (sb[w] > best || (sb[w] == best && si[w] < bi)) { best = sb[w]; bi = si[w]; }
+    out_tokens[row] = bi;
+    const int slot = dst_slot ? dst_slot[row] : row;
+    if (cur_token) cur_token[slot] = bi;
+    if (pos_inc && (!active || active[slot])) pos_inc[slot] += 1;
+  }
+}
+void launch_argmax(const LaunchCfg& lc, const float* logits, int rows, int V, int ldl, int* out_tokens,
+                   const int* dst_slot, int* cur_token, int* pos_inc, const int* active) {
+  launch_k(lc, argmax_kernel, dim3(rows), dim3(1024), 0, logits, V, ldl, out_tokens, dst_slot, cur_token, pos_inc,
+           active);
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic weight init (counter-based; the oracle restates it in numpy: oracle/weights.py)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void init_normal_kernel(__nv_bfloat16* w, size_t n, uint64_t seed, float std) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint64_t r = splitmix64(seed ^ (i * 0xD1342543DE82EF95ull));
+    const float u1 = ((float)(uint32_t)(r >> 40) + 0.5f) * (1.0f / 16777216.0f);         // (0,1)
+    const float u2 = ((float)(uint32_t)((r >> 16) & 0xFFFFFF)) * (1.0f / 16777216.0f);   // [0,1)
+    const float z = sqrtf(-2.0f * __logf(u1)) * __cosf(6.2831853071795864f * u2);
+    w[i] = __float2bfloat16(z * std);
+  }
+}
+void launch_init_normal(cudaStream_t st, __nv_bfloat16* w, size_t n, uint64_t seed, float std) {
+  init_normal_kernel<<<148 * 8, 256, 0, st>>>(w, n, seed, std);
+}
+__global__ void fill_bf16_kernel(__nv_bfloat16* w, size_t n, float v) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) w[i] = __float2bfloat16(v);
+}
+void launch_fill_bf16(cudaStream_t st, __nv_bfloat16* w, size_t n, float v) {
+  fill_bf16_kernel<<<148, 256, 0, st>>>(w, n, v);
+}
+
+}  // namespace mq

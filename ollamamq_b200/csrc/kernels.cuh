@@ -1,0 +1,72 @@
+// Launch wrappers for the non-GEMM kernels of the forward pass (see kernels.cu for the designs).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace mq {
+
+constexpr int kPageSize = 16;  // tokens per KV page
+constexpr int kHeadDim = 128;  // only head_dim 128 is instantiated (Llama-3, Qwen2.5)
+
+struct LaunchCfg {
+  cudaStream_t stream;
+  bool pdl;  // launch with programmatic stream serialization
+};
+
+// h_f32[t,:] = embed[token_ids[t], :]
+void launch_embed(const LaunchCfg& lc, const int* token_ids, const __nv_bfloat16* embed, float* h, int T, int H);
+
+// v = h[src,:] + sum_s partial[s][src,:];  if (!row_idx) h[src,:] = v;  x[row,:] = bf16(v * rsqrt(mean v^2 + eps) * gamma)
+// partial_is_f32: planes are fp32 (decode split-K) else one bf16 plane (prefill).
+void launch_add_rmsnorm(const LaunchCfg& lc, float* h, const void* partial, bool partial_is_f32, int n_planes,
+                        long long plane_stride, const __nv_bfloat16* gamma, __nv_bfloat16* x, const int* row_idx,
+                        int rows, int H, float eps);
+
+struct RopeKvParams {
+  const void* qkv;        // partial planes [S][T][qkv_dim] fp32, or one bf16 plane
+  bool qkv_is_f32;
+  int n_planes;
+  long long plane_stride;
+  const __nv_bfloat16* bias;  // nullable, [qkv_dim]
+  const int* pos;             // [T] position of each token
+  const int* slot_of_tok;     // [T] sequence slot of each token
+  const int* block_table;     // [slots][max_pages]
+  int max_pages;
+  const float* inv_freq;      // [d/2]
+  __nv_bfloat16* q_out;       // [T][n_q*d]
+  __nv_bfloat16* k_cache;     // layer base: [pages][n_kv][kPageSize][d]
+  __nv_bfloat16* v_cache;
+  int T, n_q, n_kv;
+};
+void launch_rope_kv(const LaunchCfg& lc, const RopeKvParams& p);
+
+struct AttnParams {
+  const __nv_bfloat16* q;        // [T][n_q*d]
+  const __nv_bfloat16* k_cache;  // layer base
+  const __nv_bfloat16* v_cache;
+  const int* block_table;
+  int max_pages;
+  const int4* tiles;   // prefill: {tok0, ntok, slot, pos0} per q tile
+  const int* pos;      // decode: pos[slot] (kv length = pos+1)
+  __nv_bfloat16* out;  // [T][n_q*d]
+  float* part_o;       // decode split partials [splits][T][n_q][d]
+  float* part_ml;      // [splits][T][n_q][2]
+  int n_q, n_kv, T;
+  int n_splits;        // decode only
+  int kv_chunk;        // tokens per split (decode)
+  float scale_log2;    // softmax scale * log2(e)
+};
+void launch_attn_prefill(const LaunchCfg& lc, const AttnParams& p, int n_tiles);
+void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots);
+constexpr int kPrefillTileRows = 64;  // q rows (token x group-head) per prefill CTA
+
+// next[b] = argmax_v logits[b][v]; optional: cur_token[slot]=next, pos[slot]+=1 for active slots
+void launch_argmax(const LaunchCfg& lc, const float* logits, int rows, int V, int ldl, int* out_tokens,
+                   const int* dst_slot, int* cur_token, int* pos_inc, const int* active);
+
+// deterministic counter-based N(0, std^2) fill (splitmix64 + Box-Muller), bf16
+void launch_init_normal(cudaStream_t st, __nv_bfloat16* w, size_t n, uint64_t seed, float std);
+void launch_fill_bf16(cudaStream_t st, __nv_bfloat16* w, size_t n, float v);
+
+}  // namespace mq

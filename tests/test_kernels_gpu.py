@@ -1,0 +1,307 @@
+"""Kernel-level parity: every sm_100a kernel vs a plain torch fp32 reference of the same op, through the
+C ABI's device-pointer test entry points (include/ollamamq_b200.h section 4).
+
+Floating-point tolerances are stated per test.  bf16 outputs: one bf16 rounding of an fp32-accumulated value
+(rel 2^-8) plus accumulation-order noise.
+"""
+import ctypes as C
+import math
+
+import pytest
+
+torch = pytest.importorskip("torch")
+
+pytestmark = pytest.mark.gpu
+
+PAGE = 16
+D = 128
+
+
+def _lib():
+    import ollamamq_b200 as m
+    return m
+
+
+def P(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _relerr(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-30)).item()
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+GEMM_CASES = [
+    # T, n_out, K, splits, epi(0 f32 / 1 bf16), x_rows_alloc
+    (64, 6144, 4096, 1, 0, 64),
+    (64, 6144, 4096, 4, 0, 64),
+    (8, 4096, 14336, 7, 0, 16),
+    (1, 512, 256, 1, 0, 1),
+    (33, 1000, 512, 2, 0, 64),     # n_out not a multiple of 128, T not a multiple of BN
+    (128, 1024, 1024, 1, 1, 128),
+    (300, 768, 4096, 1, 1, 300),   # BN=256 + ragged second tile, TMA OOB rows
+    (2048, 1024, 4096, 1, 1, 2048),
+]
+
+
+@pytest.mark.parametrize("T,n_out,K,splits,epi,xa", GEMM_CASES)
+def test_gemm_tcgen05(T, n_out, K, splits, epi, xa):
+    m = _lib()
+    g = torch.Generator(device="cuda").manual_seed(T * 7 + n_out)
+    W = (torch.randn(n_out, K, device=dev(), generator=g) * 0.05).bfloat16()
+    X = torch.randn(xa, K, device=dev(), generator=g).bfloat16()
+    ref = X[:T].float() @ W.float().T
+    if epi == 0:
+        out = torch.full((splits, T, n_out), float("nan"), device=dev(), dtype=torch.float32)
+    else:
+        out = torch.full((T, n_out), float("nan"), device=dev(), dtype=torch.bfloat16)
+    rc = m.lib.mq_debug_gemm(P(W), n_out, n_out, K, P(X), xa, T, epi, P(out), n_out, splits, T * n_out, 0, 0, 0, None)
+    assert rc == 0, m.last_error()
+    got = out.sum(0) if epi == 0 else out.float()
+    assert torch.isfinite(got).all(), "non-finite / unwritten outputs"
+    err = _relerr(got, ref)
+    tol = 2e-3 if epi == 0 else 6e-3
+    assert err < tol, f"rel err {err} (tol {tol})"
+
+
+@pytest.mark.parametrize("T,I,K", [(64, 1024, 4096), (16, 256, 512), (300, 512, 1024)])
+def test_gemm_silu_dual(T, I, K):
+    m = _lib()
+    g = torch.Generator(device="cuda").manual_seed(T + I)
+    W = (torch.randn(2 * I, K, device=dev(), generator=g) * 0.03).bfloat16()
+    X = torch.randn(T, K, device=dev(), generator=g).bfloat16()
+    gate = X.float() @ W[:I].float().T
+    up = X.float() @ W[I:].float().T
+    ref = torch.nn.functional.silu(gate) * up
+    out = torch.full((T, I), float("nan"), device=dev(), dtype=torch.bfloat16)
+    rc = m.lib.mq_debug_gemm(P(W), 2 * I, I, K, P(X), T, T, 2, P(out), I, 1, 0, I, 0, 0, None)
+    assert rc == 0, m.last_error()
+    assert torch.isfinite(out.float()).all()
+    err = _relerr(out, ref)
+    assert err < 8e-3, f"rel err {err}"
+
+
+def test_gemm_pdl_flag_matches():
+    """Same result with the programmatic-dependent-launch attribute set."""
+    m = _lib()
+    W = (torch.randn(1024, 2048, device=dev()) * 0.05).bfloat16()
+    X = torch.randn(64, 2048, device=dev()).bfloat16()
+    o0 = torch.zeros(1, 64, 1024, device=dev())
+    o1 = torch.zeros(1, 64, 1024, device=dev())
+    assert m.lib.mq_debug_gemm(P(W), 1024, 1024, 2048, P(X), 64, 64, 0, P(o0), 1024, 1, 0, 0, 0, 0, None) == 0
+    assert m.lib.mq_debug_gemm(P(W), 1024, 1024, 2048, P(X), 64, 64, 0, P(o1), 1024, 1, 0, 0, 1, 0, None) == 0
+    assert torch.equal(o0, o1)
+
+
+# ---------------------------------------------------------------------------------------------- small kernels
+def test_embed():
+    m = _lib()
+    V, H, T = 1000, 4096, 37
+    E = torch.randn(V, H, device=dev()).bfloat16()
+    ids = torch.randint(0, V, (T,), device=dev(), dtype=torch.int32)
+    h = torch.zeros(T, H, device=dev())
+    assert m.lib.mq_debug_embed(P(ids), P(E), P(h), T, H) == 0, m.last_error()
+    assert torch.equal(h, E[ids.long()].float())
+
+
+@pytest.mark.parametrize("H,rows,planes,f32", [(4096, 64, 4, True), (3584, 5, 1, True), (4096, 33, 1, False),
+                                               (4096, 7, 0, True)])
+def test_add_rmsnorm(H, rows, planes, f32):
+    m = _lib()
+    eps = 1e-5
+    h = torch.randn(rows, H, device=dev())
+    gamma = (1 + 0.1 * torch.randn(H, device=dev())).bfloat16()
+    if f32:
+        part = torch.randn(max(planes, 1), rows, H, device=dev())
+    else:
+        part = torch.randn(1, rows, H, device=dev()).bfloat16()
+    v = h + (part[:planes].float().sum(0) if planes else 0)
+    ref_x = v * torch.rsqrt(v.pow(2).mean(-1, keepdim=True) + eps) * gamma.float()
+    x = torch.zeros(rows, H, device=dev(), dtype=torch.bfloat16)
+    h2 = h.clone()
+    rc = m.lib.mq_debug_add_rmsnorm(P(h2), P(part), int(f32), planes, rows * H, P(gamma), P(x), None, rows, H, eps)
+    assert rc == 0, m.last_error()
+    assert torch.allclose(h2, v, atol=1e-5, rtol=1e-5)
+    assert _relerr(x, ref_x) < 4e-3
+    # gather mode: rows picked through row_idx, residual untouched
+    idx = torch.tensor([rows - 1, 0], device=dev(), dtype=torch.int32)
+    x2 = torch.zeros(2, H, device=dev(), dtype=torch.bfloat16)
+    h3 = h.clone()
+    rc = m.lib.mq_debug_add_rmsnorm(P(h3), P(part), int(f32), planes, rows * H, P(gamma), P(x2), P(idx), 2, H, eps)
+    assert rc == 0, m.last_error()
+    assert torch.equal(h3, h)
+    assert _relerr(x2, ref_x[idx.long()]) < 4e-3
+
+
+def _inv_freq(theta):
+    return 1.0 / (theta ** (torch.arange(0, D, 2, dtype=torch.float32) / D))
+
+
+def _rope_ref(x, pos, inv_freq):
+    # x [T, heads, D] fp32; HF rotate_half convention
+    ang = pos.float()[:, None] * inv_freq[None, :]
+    cos = torch.cat([ang.cos(), ang.cos()], -1)[:, None, :]
+    sin = torch.cat([ang.sin(), ang.sin()], -1)[:, None, :]
+    x1, x2 = x[..., : D // 2], x[..., D // 2:]
+    rot = torch.cat([-x2, x1], -1)
+    return x * cos + rot * sin
+
+
+def _make_cache(n_slots, max_pages, n_kv, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    n_pages = n_slots * max_pages + 1
+    perm = torch.randperm(n_pages - 1, generator=g) + 1  # page 0 reserved as scratch
+    bt = perm.view(n_slots, max_pages).to(torch.int32)
+    k = torch.zeros(n_pages, n_kv, PAGE, D, dtype=torch.bfloat16)
+    v = torch.zeros(n_pages, n_kv, PAGE, D, dtype=torch.bfloat16)
+    return bt, k, v
+
+
+@pytest.mark.parametrize("f32,planes,bias", [(True, 3, False), (False, 1, True)])
+def test_rope_kv(f32, planes, bias):
+    m = _lib()
+    n_q, n_kv, T, n_slots, max_pages = 32, 8, 40, 3, 8
+    qkv_dim = (n_q + 2 * n_kv) * D
+    theta = 500000.0
+    inv = _inv_freq(theta).to(dev())
+    bt, kc, vc = _make_cache(n_slots, max_pages, n_kv)
+    bt, kc, vc = bt.to(dev()), kc.to(dev()), vc.to(dev())
+    slot = torch.randint(0, n_slots, (T,), dtype=torch.int32)
+    # unique (slot, pos) pairs
+    pos = torch.zeros(T, dtype=torch.int32)
+    used = {}
+    for t in range(T):
+        s = int(slot[t])
+        pos[t] = used.get(s, 3)
+        used[s] = int(pos[t]) + 5
+    slot, pos = slot.to(dev()), pos.to(dev())
+    if f32:
+        qkv = torch.randn(planes, T, qkv_dim, device=dev())
+        full = qkv.sum(0)
+    else:
+        qkv = torch.randn(1, T, qkv_dim, device=dev()).bfloat16()
+        full = qkv[0].float()
+    b = torch.randn(qkv_dim, device=dev()).bfloat16() if bias else None
+    if bias:
+        full = full + b.float()
+    q_out = torch.zeros(T, n_q * D, device=dev(), dtype=torch.bfloat16)
+    rc = m.lib.mq_debug_rope_kv(P(qkv), int(f32), planes, T * qkv_dim, P(b), P(pos), P(slot), P(bt), max_pages,
+                                P(inv), P(q_out), P(kc), P(vc), T, n_q, n_kv)
+    assert rc == 0, m.last_error()
+    q_ref = _rope_ref(full[:, : n_q * D].view(T, n_q, D), pos, inv)
+    k_ref = _rope_ref(full[:, n_q * D:(n_q + n_kv) * D].view(T, n_kv, D), pos, inv)
+    v_ref = full[:, (n_q + n_kv) * D:].view(T, n_kv, D)
+    assert _relerr(q_out.view(T, n_q, D), q_ref) < 4e-3
+    for t in range(T):
+        pg = int(bt[int(slot[t]), int(pos[t]) // PAGE])
+        off = int(pos[t]) % PAGE
+        assert _relerr(kc[pg, :, off, :], k_ref[t]) < 5e-3, f"K token {t}"
+        assert _relerr(vc[pg, :, off, :], v_ref[t]) < 5e-3, f"V token {t}"
+
+
+def _attn_ref(q, k, v, q_pos):
+    """q [Lq, n_q, D], k/v [Lk, n_kv, D] fp32, q_pos [Lq] absolute positions; causal on absolute positions."""
+    n_q, n_kv = q.shape[1], k.shape[1]
+    G = n_q // n_kv
+    kk = k.repeat_interleave(G, dim=1)
+    vv = v.repeat_interleave(G, dim=1)
+    s = torch.einsum("qhd,khd->hqk", q, kk) / math.sqrt(D)
+    kpos = torch.arange(k.shape[0], device=q.device)
+    mask = kpos[None, :] <= q_pos[:, None]
+    s = s.masked_fill(~mask[None], float("-inf"))
+    p = torch.softmax(s, -1)
+    return torch.einsum("hqk,khd->qhd", p, vv)
+
+
+def _gather_kv(kc, vc, bt_row, L):
+    idx = torch.arange(L, device=kc.device)
+    pages = bt_row[(idx // PAGE).long()].long()
+    off = (idx % PAGE).long()
+    return kc[pages, :, off, :].float(), vc[pages, :, off, :].float()
+
+
+@pytest.mark.parametrize("n_q,n_kv", [(32, 8), (28, 4)])
+def test_attn_prefill(n_q, n_kv):
+    m = _lib()
+    G = n_q // n_kv
+    tok_per_tile = 64 // G
+    n_slots, max_pages = 3, 40
+    bt, kc, vc = _make_cache(n_slots, max_pages, n_kv, seed=1)
+    kc = torch.randn_like(kc.float()).bfloat16()
+    vc = torch.randn_like(vc.float()).bfloat16()
+    bt, kc, vc = bt.to(dev()), kc.to(dev()), vc.to(dev())
+    # (slot, context already in cache, new tokens): a fresh prompt, a chunk with context, a ragged one
+    seqs = [(0, 0, 512), (1, 100, 77), (2, 0, 5)]
+    T = sum(s[2] for s in seqs)
+    q = torch.randn(T, n_q, D, device=dev()).bfloat16()
+    tiles = []
+    r0 = 0
+    for slot, ctx, L in seqs:
+        for i in range(0, L, tok_per_tile):
+            tiles.append([r0 + i, min(tok_per_tile, L - i), slot, ctx + i])
+        r0 += L
+    tiles_t = torch.tensor(tiles, dtype=torch.int32, device=dev())
+    out = torch.zeros(T, n_q, D, device=dev(), dtype=torch.bfloat16)
+    rc = m.lib.mq_debug_attn_prefill(P(q), P(kc), P(vc), P(bt), max_pages, P(tiles_t), len(tiles), P(out), n_q,
+                                     n_kv, T, 1.0 / math.sqrt(D))
+    assert rc == 0, m.last_error()
+    r0 = 0
+    for slot, ctx, L in seqs:
+        k, v = _gather_kv(kc, vc, bt[slot], ctx + L)
+        qpos = torch.arange(ctx, ctx + L, device=dev())
+        ref = _attn_ref(q[r0:r0 + L].float(), k, v, qpos)
+        err = _relerr(out[r0:r0 + L], ref)
+        assert err < 1e-2, f"slot {slot}: rel err {err}"
+        r0 += L
+
+
+@pytest.mark.parametrize("n_q,n_kv,n_splits,chunk", [(32, 8, 4, 256), (32, 8, 1, 4096), (28, 4, 3, 64)])
+def test_attn_decode(n_q, n_kv, n_splits, chunk):
+    m = _lib()
+    n_slots, max_pages = 6, 48
+    bt, kc, vc = _make_cache(n_slots, max_pages, n_kv, seed=2)
+    kc = torch.randn_like(kc.float()).bfloat16()
+    vc = torch.randn_like(vc.float()).bfloat16()
+    bt, kc, vc = bt.to(dev()), kc.to(dev()), vc.to(dev())
+    pos_list = [0, 15, 16, 575, 100, 31]
+    if chunk * n_splits < max(pos_list) + 1:
+        pos_list = [min(p, chunk * n_splits - 1) for p in pos_list]
+    pos = torch.tensor(pos_list, dtype=torch.int32, device=dev())
+    q = torch.randn(n_slots, n_q, D, device=dev()).bfloat16()
+    out = torch.zeros(n_slots, n_q, D, device=dev(), dtype=torch.bfloat16)
+    part_o = torch.full((n_splits, n_slots, n_q, D), float("nan"), device=dev())
+    part_ml = torch.full((n_splits, n_slots, n_q, 2), float("nan"), device=dev())
+    rc = m.lib.mq_debug_attn_decode(P(q), P(kc), P(vc), P(bt), max_pages, P(pos), P(out), P(part_o), P(part_ml), n_q,
+                                    n_kv, n_slots, n_splits, chunk, 1.0 / math.sqrt(D))
+    assert rc == 0, m.last_error()
+    for s in range(n_slots):
+        L = int(pos[s]) + 1
+        k, v = _gather_kv(kc, vc, bt[s], L)
+        ref = _attn_ref(q[s:s + 1].float(), k, v, torch.tensor([L - 1], device=dev()))
+        err = _relerr(out[s:s + 1], ref)
+        assert err < 1e-2, f"slot {s} (ctx {L}): rel err {err}"
+
+
+def test_argmax_and_advance():
+    m = _lib()
+    rows, V = 5, 128256
+    logits = torch.randn(rows, V, device=dev())
+    logits[2, 777] = 50.0
+    logits[3, 5] = 60.0
+    logits[3, 9000] = 60.0  # tie: lowest index wins
+    out = torch.zeros(rows, dtype=torch.int32, device=dev())
+    dst = torch.tensor([4, 3, 2, 1, 0], dtype=torch.int32, device=dev())
+    cur = torch.full((rows,), -1, dtype=torch.int32, device=dev())
+    pos = torch.tensor([10, 20, 30, 40, 50], dtype=torch.int32, device=dev())
+    act = torch.tensor([1, 0, 1, 1, 1], dtype=torch.int32, device=dev())
+    rc = m.lib.mq_debug_argmax(P(logits), rows, V, V, P(out), P(dst), P(cur), P(pos), P(act))
+    assert rc == 0, m.last_error()
+    ref = logits.argmax(-1).int()
+    ref[3] = 5
+    assert torch.equal(out, ref)
+    assert torch.equal(cur[dst.long()], ref)
+    assert pos.tolist() == [11, 20, 31, 41, 51]
