@@ -1,0 +1,142 @@
+// GPU worker runtime: one per B200.  Owns the weights, the paged KV cache, the slot table and a host thread
+// that runs continuous batching (prefill passes + CUDA-graphed decode steps) and fires the C-ABI callbacks.
+// This is what stands where the reference has `reqwest -> remote Ollama` (dispatcher.rs:287-312).
+#pragma once
+#include "../../include/ollamamq_b200.h"
+#include "gemm_host.cuh"
+#include "kernels.cuh"
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace mq {
+using Clock = std::chrono::steady_clock;
+
+struct DevTensor {
+  void* ptr = nullptr;
+  size_t bytes = 0;
+};
+
+struct LayerWeights {
+  __nv_bfloat16 *attn_norm, *wqkv, *bqkv, *wo, *mlp_norm, *w_gate_up, *w_down;
+};
+
+// All GEMM plans for one activation-row count T (decode bucket or prefill pass size).
+struct PassPlans {
+  int T = 0;
+  bool decode = false;
+  int s_qkv = 1, s_o = 1, s_down = 1;
+  std::vector<GemmPlan> qkv, o, gate_up, down;  // per layer
+};
+
+}  // namespace mq
+
+struct mq_req {
+  std::atomic<int> refs{2};  // caller handle + engine
+  mq_worker* w = nullptr;
+  mq_request rq{};
+  std::vector<int32_t> prompt;
+  std::string body;
+  mq_callbacks cb{};
+  void* user = nullptr;
+  int slot = -1;
+  int n_prefilled = 0;   // prompt tokens whose KV is (or is scheduled to be) in the cache
+  int n_sched = 0;       // generated tokens scheduled on the GPU so far
+  int n_emitted = 0;     // generated tokens delivered to the callback
+  int max_new = 0;
+  std::atomic<bool> cancel{false};
+  bool status_sent = false;
+  bool finished = false;
+  int done_rc = 0;
+  std::string agg;       // stream=0: aggregated text
+  std::vector<int32_t> agg_tokens;
+  std::vector<int> pages;
+  mq::Clock::time_point t_submit, t_first, t_last, deadline;
+  bool has_deadline = false;
+};
+
+struct mq_worker {
+  mq_model_cfg cfg{};
+  int gpu = 0;
+  cudaStream_t stream = nullptr;
+  int qkv_dim = 0, max_pages = 0, n_pages = 0, MT = 0, MB = 0;
+  double p_mm_bytes = 0, kv_bytes_per_tok = 0;
+
+  // weights
+  std::map<std::string, mq::DevTensor> tensors;
+  std::vector<mq::LayerWeights> layers;
+  __nv_bfloat16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr;
+  __nv_bfloat16 *k_cache = nullptr, *v_cache = nullptr;  // [layers][pages][n_kv][16][128]
+  size_t cache_layer_stride = 0;
+
+  // activations
+  float* h = nullptr;
+  __nv_bfloat16 *x = nullptr, *q = nullptr, *attn = nullptr, *act = nullptr, *x_last = nullptr;
+  void *qkv_part = nullptr, *proj_part = nullptr;
+  float *logits = nullptr, *part_o = nullptr, *part_ml = nullptr, *inv_freq = nullptr;
+  // metadata (device)
+  int *d_tok = nullptr, *d_pos_tok = nullptr, *d_slot_tok = nullptr, *d_last_idx = nullptr, *d_dst_slot = nullptr;
+  int4* d_tiles = nullptr;
+  int *d_cur_token = nullptr, *d_pos = nullptr, *d_active = nullptr, *d_block_table = nullptr, *d_identity = nullptr;
+  int* d_out_ring = nullptr;  // [kRing][MB]
+  // pinned host mirrors / staging
+  int *h_pos = nullptr, *h_active = nullptr, *h_block_table = nullptr;
+  int* h_stage = nullptr;     // ring of staging areas for metadata uploads
+  int* h_out_ring = nullptr;  // [kRing][MB]
+  size_t stage_ints = 0;
+  int stage_next = 0;
+  std::vector<cudaEvent_t> stage_ev;
+
+  std::map<int, mq::PassPlans> plans_decode, plans_prefill;
+  std::map<long long, cudaGraphExec_t> graphs;  // key: Bcap * 1024 + n_splits
+  std::vector<mq::GemmPlan> lm_plans_cache_dummy;
+  std::map<int, mq::GemmPlan> lm_plans;          // key: rows
+
+  // slots / pages
+  std::vector<mq_req*> slot_req;
+  std::vector<int> free_pages;
+  bool slots_dirty = false;
+
+  // threading
+  std::thread thr;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<mq_req*> inbox;
+  std::deque<std::function<void()>> jobs;
+  bool stop = false;
+  std::atomic<bool> healthy{true};
+  std::string fatal;
+
+  // in-flight GPU work (FIFO)
+  struct Flight {
+    cudaEvent_t ev;
+    cudaEvent_t ev_begin;  // timing only
+    bool timed = false;
+    bool decode = false;
+    int ring = 0;
+    double bytes = 0;
+    std::vector<std::pair<mq_req*, int>> emits;  // (request, index into h_out_ring row)
+  };
+  std::deque<Flight> flights;
+  std::vector<cudaEvent_t> ev_pool;
+  int ring_next = 0;
+
+  std::deque<mq_req*> waiting;   // admitted-pending (no slot yet)
+  std::deque<mq_req*> prefilling;  // have a slot, prompt not fully prefilled
+
+  // stats
+  mq_worker_stats stats{};
+  bool timing = false;
+  std::mutex stats_mu;
+};
+
+namespace mq {
+int engine_forward_logits(mq_worker* w, const int32_t* tokens, int n, int all_positions, float* out);
+}
