@@ -143,7 +143,7 @@ int mq_worker_healthy(mq_worker* w);
 
 typedef struct mq_request {
   int32_t endpoint;          /* MQ_EP_*                                                                   */
-  int32_t stream;            /* 1: one chunk per token; 0: one chunk at the end                           */
+  int32_t stream;            /* 1: one chunk per token; 0: one chunk at the end; <0: take "stream" from body  */
   const uint8_t* body;       /* request body as the client sent it (JSON) — may be NULL with raw tokens   */
   size_t body_len;
   const int32_t* prompt_tokens; /* optional pre-tokenised prompt (synthetic workloads); overrides body    */
@@ -214,6 +214,20 @@ int mq_dispatcher_block_ip(mq_dispatcher* d, const char* ip, int32_t blocked);  
 int mq_dispatcher_log(mq_dispatcher* d, mq_dispatch* out, int32_t cap, int32_t* n_out);
 /* block until every submitted task has completed */
 int mq_dispatcher_drain(mq_dispatcher* d, uint32_t timeout_ms);
+/* health prober result for one backend (:185-189); like the reference, recovery does not wake the scheduler */
+int mq_dispatcher_set_online(mq_dispatcher* d, int32_t backend, int32_t online);
+/* the HTTP connection behind a queued / in-flight task closed (responder.is_closed(), :278; send error, :305) */
+int mq_dispatcher_client_gone(mq_dispatcher* d, uint64_t task_id);
+/* block until the run_worker thread is parked on {notify, backend_freed} with nothing pending (:344-349)   */
+int mq_dispatcher_wait_parked(mq_dispatcher* d, uint32_t timeout_ms);
+
+/* Step-driven MOCK backends (test/dev infrastructure — the fake backend the reference never shipped): a
+ * submitted request stays in flight until mq_dispatcher_mock_complete() is called, so a test can impose the
+ * completion order of a simulated clock on the live, threaded dispatcher.  Emits fake chunks; never used by
+ * mq_dispatcher_new and never a substitute for a GPU worker.                                             */
+int mq_dispatcher_new_mock(int32_t n_backends, int32_t capacity, mq_dispatcher** out);
+int mq_dispatcher_mock_complete(mq_dispatcher* d, int32_t backend, int32_t rc);
+int mq_dispatcher_mock_fail_next(mq_dispatcher* d, int32_t backend, int32_t n);
 
 /* =====================================================================================================
  * 4. Kernel-level test ABI (device pointers).  See csrc/debug_api.cu.

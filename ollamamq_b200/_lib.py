@@ -130,6 +130,12 @@ _sig("mq_dispatcher_block_user", C.c_int, [P, C.c_char_p, C.c_int32])
 _sig("mq_dispatcher_block_ip", C.c_int, [P, C.c_char_p, C.c_int32])
 _sig("mq_dispatcher_log", C.c_int, [P, C.POINTER(Dispatch), C.c_int32, C.POINTER(C.c_int32)])
 _sig("mq_dispatcher_drain", C.c_int, [P, C.c_uint32])
+_sig("mq_dispatcher_set_online", C.c_int, [P, C.c_int32, C.c_int32])
+_sig("mq_dispatcher_client_gone", C.c_int, [P, C.c_uint64])
+_sig("mq_dispatcher_wait_parked", C.c_int, [P, C.c_uint32])
+_sig("mq_dispatcher_new_mock", C.c_int, [C.c_int32, C.c_int32, C.POINTER(P)])
+_sig("mq_dispatcher_mock_complete", C.c_int, [P, C.c_int32, C.c_int32])
+_sig("mq_dispatcher_mock_fail_next", C.c_int, [P, C.c_int32, C.c_int32])
 # kernel-level test ABI
 _sig("mq_debug_gemm", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int,
                                  C.c_longlong, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)])

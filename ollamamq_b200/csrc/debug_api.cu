@@ -28,6 +28,7 @@ int mq_debug_gemm(const void* W, int w_rows, int n_out, int K, const void* X, in
                   void* out, int ldo, int splits, long long split_stride, int a2_row_off, int pdl, int reps,
                   float* ms_out) {
   GemmPlan g;
+  gemm_set_attrs();
   if (!gemm_plan(&g, W, w_rows, n_out, K, X, x_rows_alloc, T, epi, out, ldo, splits, split_stride, a2_row_off)) {
     mq::set_last_error("gemm_plan failed (K%%64, splits, or cuTensorMapEncodeTiled)");
     return MQ_ERR_INVAL;
@@ -94,6 +95,7 @@ int mq_debug_attn_prefill(const void* q, const void* k_cache, const void* v_cach
   p.block_table = block_table; p.max_pages = max_pages; p.tiles = (const int4*)tiles; p.out = (__nv_bfloat16*)out;
   p.n_q = n_q; p.n_kv = n_kv; p.T = T; p.n_splits = 1; p.kv_chunk = 1 << 30;
   p.scale_log2 = scale * 1.4426950408889634f;
+  attn_set_attrs();
   launch_attn_prefill(LaunchCfg{0, false}, p, n_tiles);
   return check_cuda("mq_debug_attn_prefill");
 }

@@ -1,0 +1,1115 @@
+// GPU worker runtime (see engine.hpp).  Reference seam: /root/reference/src/dispatcher.rs:287-312.
+#include "engine.hpp"
+#include "framing.hpp"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace mq {
+void set_last_error(const char* fmt, ...);
+
+constexpr int kRing = 16;        // output-token ring (decode steps / prefill passes in flight)
+constexpr int kStageSlots = 32;  // metadata staging ring
+constexpr int kMaxFlightsDecode = 4;
+constexpr int kMaxFlightsPrefill = 2;
+constexpr int kDecodeKvChunk = 256;  // tokens per split-KV CTA
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return MQ_ERR_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ------------------------------------------------------------------------------------------------
+// allocation / weights
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int dalloc(T** p, size_t n_elems) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, n_elems * sizeof(T));
+  if (e != cudaSuccess) {
+    set_last_error("cudaMalloc(%zu bytes): %s", n_elems * sizeof(T), cudaGetErrorString(e));
+    return MQ_ERR_NOMEM;
+  }
+  *p = reinterpret_cast<T*>(q);
+  return MQ_OK;
+}
+
+static int add_tensor(mq_worker* w, const std::string& name, size_t n_elems, __nv_bfloat16** out) {
+  __nv_bfloat16* p = nullptr;
+  int rc = dalloc(&p, n_elems);
+  if (rc) return rc;
+  w->tensors[name] = DevTensor{p, n_elems * 2};
+  *out = p;
+  return MQ_OK;
+}
+
+static int decode_splits(int m_tiles, int k_blocks) {
+  int s = 148 / m_tiles;
+  if (s < 1) s = 1;
+  while (s > 1 && (k_blocks + s - 1) / s < 8) --s;       // keep >= 8 k-blocks (32 KiB of weights per row tile)
+  while (s > 1 && (s - 1) * ((k_blocks + s - 1) / s) >= k_blocks) --s;  // every split non-empty
+  return s;
+}
+
+static int worker_alloc(mq_worker* w) {
+  const mq_model_cfg& c = w->cfg;
+  const int H = c.hidden, I = c.ffn, V = c.vocab, L = c.n_layers, D = c.head_dim;
+  w->qkv_dim = (c.n_q_heads + 2 * c.n_kv_heads) * D;
+  w->MB = c.max_batch;
+  w->MT = std::max(c.max_prefill_tokens, c.max_batch);
+  w->max_pages = (c.max_seq + kPageSize - 1) / kPageSize;
+  w->n_pages = c.kv_pages > 0 ? c.kv_pages : w->MB * w->max_pages + 1;
+  int rc;
+  if ((rc = add_tensor(w, "embed", (size_t)V * H, &w->embed))) return rc;
+  if ((rc = add_tensor(w, "final_norm", H, &w->final_norm))) return rc;
+  if ((rc = add_tensor(w, "lm_head", (size_t)V * H, &w->lm_head))) return rc;
+  w->layers.resize(L);
+  for (int l = 0; l < L; ++l) {
+    const std::string p = "layers." + std::to_string(l) + ".";
+    LayerWeights& lw = w->layers[l];
+    if ((rc = add_tensor(w, p + "attn_norm", H, &lw.attn_norm))) return rc;
+    if ((rc = add_tensor(w, p + "wqkv", (size_t)w->qkv_dim * H, &lw.wqkv))) return rc;
+    lw.bqkv = nullptr;
+    if (c.qkv_bias && (rc = add_tensor(w, p + "bqkv", w->qkv_dim, &lw.bqkv))) return rc;
+    if ((rc = add_tensor(w, p + "wo", (size_t)H * c.n_q_heads * D, &lw.wo))) return rc;
+    if ((rc = add_tensor(w, p + "mlp_norm", H, &lw.mlp_norm))) return rc;
+    if ((rc = add_tensor(w, p + "w_gate_up", (size_t)2 * I * H, &lw.w_gate_up))) return rc;
+    if ((rc = add_tensor(w, p + "w_down", (size_t)H * I, &lw.w_down))) return rc;
+  }
+  // algorithmic bytes: matmul weights incl. LM head, excl. embedding table
+  const double p_mm = (double)L * ((double)w->qkv_dim * H + (double)H * c.n_q_heads * D + 3.0 * I * H) + (double)V * H;
+  w->p_mm_bytes = 2.0 * p_mm;
+  w->kv_bytes_per_tok = 2.0 * L * c.n_kv_heads * D * 2.0;
+
+  w->cache_layer_stride = (size_t)w->n_pages * c.n_kv_heads * kPageSize * D;
+  if ((rc = dalloc(&w->k_cache, w->cache_layer_stride * L))) return rc;
+  if ((rc = dalloc(&w->v_cache, w->cache_layer_stride * L))) return rc;
+  cudaMemsetAsync(w->k_cache, 0, w->cache_layer_stride * L * 2, w->stream);
+  cudaMemsetAsync(w->v_cache, 0, w->cache_layer_stride * L * 2, w->stream);
+
+  const int MT = w->MT, MB = w->MB;
+  const int qd = c.n_q_heads * D;
+  // split-K plane counts for decode (fixed per model shape)
+  const int kbH = H / 64, kbI = I / 64, kbQ = qd / 64;
+  const int s_qkv = decode_splits((w->qkv_dim + 127) / 128, kbH);
+  const int s_o = decode_splits((H + 127) / 128, kbQ);
+  const int s_d = decode_splits((H + 127) / 128, kbI);
+  const int MBp = round_up(MB, 16);
+  if ((rc = dalloc(&w->h, (size_t)MT * H))) return rc;
+  if ((rc = dalloc(&w->x, (size_t)MT * H))) return rc;
+  if ((rc = dalloc(&w->q, (size_t)MT * qd))) return rc;
+  if ((rc = dalloc(&w->attn, (size_t)MT * qd))) return rc;
+  if ((rc = dalloc(&w->act, (size_t)MT * I))) return rc;
+  if ((rc = dalloc(&w->x_last, (size_t)MBp * H))) return rc;
+  const size_t qkv_bytes = std::max((size_t)MT * w->qkv_dim * 2, (size_t)s_qkv * MBp * w->qkv_dim * 4);
+  const size_t proj_bytes = std::max((size_t)MT * H * 2, (size_t)std::max(s_o, s_d) * MBp * H * 4);
+  uint8_t* tmp;
+  if ((rc = dalloc(&tmp, qkv_bytes))) return rc;
+  w->qkv_part = tmp;
+  if ((rc = dalloc(&tmp, proj_bytes))) return rc;
+  w->proj_part = tmp;
+  if ((rc = dalloc(&w->logits, (size_t)MBp * V))) return rc;
+  const int max_splits = (c.max_seq + kDecodeKvChunk - 1) / kDecodeKvChunk;
+  if ((rc = dalloc(&w->part_o, (size_t)max_splits * MBp * c.n_q_heads * D))) return rc;
+  if ((rc = dalloc(&w->part_ml, (size_t)max_splits * MBp * c.n_q_heads * 2))) return rc;
+  if ((rc = dalloc(&w->inv_freq, D / 2))) return rc;
+  if ((rc = dalloc(&w->d_tok, MT))) return rc;
+  if ((rc = dalloc(&w->d_pos_tok, MT))) return rc;
+  if ((rc = dalloc(&w->d_slot_tok, MT))) return rc;
+  if ((rc = dalloc(&w->d_last_idx, MBp))) return rc;
+  if ((rc = dalloc(&w->d_dst_slot, MBp))) return rc;
+  if ((rc = dalloc(&w->d_tiles, MT + MB))) return rc;
+  if ((rc = dalloc(&w->d_cur_token, MBp))) return rc;
+  if ((rc = dalloc(&w->d_pos, MBp))) return rc;
+  if ((rc = dalloc(&w->d_active, MBp))) return rc;
+  if ((rc = dalloc(&w->d_identity, MBp))) return rc;
+  if ((rc = dalloc(&w->d_block_table, (size_t)MBp * w->max_pages))) return rc;
+  if ((rc = dalloc(&w->d_out_ring, (size_t)kRing * MBp))) return rc;
+  CUDA_TRY(cudaMemsetAsync(w->d_cur_token, 0, MBp * 4, w->stream));
+  CUDA_TRY(cudaMemsetAsync(w->d_pos, 0, MBp * 4, w->stream));
+  CUDA_TRY(cudaMemsetAsync(w->d_active, 0, MBp * 4, w->stream));
+  CUDA_TRY(cudaMemsetAsync(w->d_block_table, 0, (size_t)MBp * w->max_pages * 4, w->stream));  // scratch page 0
+
+  // pinned host
+  CUDA_TRY(cudaMallocHost((void**)&w->h_pos, MBp * 4));
+  CUDA_TRY(cudaMallocHost((void**)&w->h_active, MBp * 4));
+  CUDA_TRY(cudaMallocHost((void**)&w->h_block_table, (size_t)MBp * w->max_pages * 4));
+  memset(w->h_pos, 0, MBp * 4);
+  memset(w->h_active, 0, MBp * 4);
+  memset(w->h_block_table, 0, (size_t)MBp * w->max_pages * 4);
+  w->stage_ints = (size_t)3 * MT + 4 * (size_t)(MT + MB) + 4 * (size_t)MBp + (size_t)MBp * w->max_pages + 64;
+  CUDA_TRY(cudaMallocHost((void**)&w->h_stage, w->stage_ints * 4 * kStageSlots));
+  CUDA_TRY(cudaMallocHost((void**)&w->h_out_ring, (size_t)kRing * MBp * 4));
+  w->stage_ev.resize(kStageSlots);
+  for (auto& e : w->stage_ev) CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+
+  std::vector<int> ident(MBp);
+  for (int i = 0; i < MBp; ++i) ident[i] = i;
+  CUDA_TRY(cudaMemcpyAsync(w->d_identity, ident.data(), MBp * 4, cudaMemcpyHostToDevice, w->stream));
+  std::vector<float> invf(D / 2);
+  for (int i = 0; i < D / 2; ++i)  // HF: 1.0 / (base ** (arange(0, dim, 2).float() / dim)), fp32
+    invf[i] = 1.0f / powf(c.rope_theta, (float)(2 * i) / (float)D);
+  CUDA_TRY(cudaMemcpyAsync(w->inv_freq, invf.data(), D / 2 * 4, cudaMemcpyHostToDevice, w->stream));
+  CUDA_TRY(cudaStreamSynchronize(w->stream));
+
+  w->slot_req.assign(MB, nullptr);
+  w->free_pages.clear();
+  for (int p = w->n_pages - 1; p >= 1; --p) w->free_pages.push_back(p);  // page 0 = scratch
+  return MQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM plans
+// ------------------------------------------------------------------------------------------------
+static int build_plans(mq_worker* w, PassPlans* pp, int T, bool decode) {
+  const mq_model_cfg& c = w->cfg;
+  const int H = c.hidden, I = c.ffn, D = c.head_dim, qd = c.n_q_heads * D;
+  pp->T = T;
+  pp->decode = decode;
+  const int MBp = round_up(w->MB, 16);
+  if (decode) {
+    pp->s_qkv = decode_splits((w->qkv_dim + 127) / 128, H / 64);
+    pp->s_o = decode_splits((H + 127) / 128, qd / 64);
+    pp->s_down = decode_splits((H + 127) / 128, I / 64);
+  } else {
+    pp->s_qkv = pp->s_o = pp->s_down = 1;
+  }
+  const int epi_part = decode ? EPI_F32 : EPI_BF16;
+  const int x_rows = w->MT;
+  pp->qkv.resize(c.n_layers); pp->o.resize(c.n_layers); pp->gate_up.resize(c.n_layers); pp->down.resize(c.n_layers);
+  for (int l = 0; l < c.n_layers; ++l) {
+    const LayerWeights& lw = w->layers[l];
+    bool ok = true;
+    ok &= gemm_plan(&pp->qkv[l], lw.wqkv, w->qkv_dim, w->qkv_dim, H, w->x, x_rows, T, epi_part, w->qkv_part,
+                    w->qkv_dim, pp->s_qkv, (long long)MBp * w->qkv_dim, 0);
+    ok &= gemm_plan(&pp->o[l], lw.wo, H, H, qd, w->attn, x_rows, T, epi_part, w->proj_part, H, pp->s_o,
+                    (long long)MBp * H, 0);
+    ok &= gemm_plan(&pp->gate_up[l], lw.w_gate_up, 2 * I, I, H, w->x, x_rows, T, EPI_SILU_BF16, w->act, I, 1, 0, I);
+    ok &= gemm_plan(&pp->down[l], lw.w_down, H, H, I, w->act, x_rows, T, epi_part, w->proj_part, H, pp->s_down,
+                    (long long)MBp * H, 0);
+    if (!ok) {
+      set_last_error("gemm_plan failed (layer %d, T=%d)", l, T);
+      return MQ_ERR_CUDA;
+    }
+  }
+  return MQ_OK;
+}
+
+static PassPlans* get_plans(mq_worker* w, int T, bool decode) {
+  auto& m = decode ? w->plans_decode : w->plans_prefill;
+  auto it = m.find(T);
+  if (it != m.end()) return &it->second;
+  PassPlans pp;
+  if (build_plans(w, &pp, T, decode) != MQ_OK) return nullptr;
+  return &(m[T] = std::move(pp));
+}
+
+static GemmPlan* get_lm_plan(mq_worker* w, int rows) {
+  auto it = w->lm_plans.find(rows);
+  if (it != w->lm_plans.end()) return &it->second;
+  GemmPlan g;
+  const int MBp = round_up(w->MB, 16);
+  if (!gemm_plan(&g, w->lm_head, w->cfg.vocab, w->cfg.vocab, w->cfg.hidden, w->x_last, MBp, rows, EPI_F32, w->logits,
+                 w->cfg.vocab, 1, 0, 0)) {
+    set_last_error("gemm_plan(lm_head) failed");
+    return nullptr;
+  }
+  return &(w->lm_plans[rows] = g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// one forward pass over T activation rows (all launches on w->stream; capturable when decode)
+// ------------------------------------------------------------------------------------------------
+struct PassArgs {
+  int T;
+  bool decode;
+  int n_splits;                // decode
+  int n_tiles;                 // prefill
+  const int* tok;              // [T] token ids (device)
+  const int* pos;              // [T]
+  const int* slot_of_tok;      // [T]
+};
+
+
+static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* n_launch) {
+  const mq_model_cfg& c = w->cfg;
+  const LaunchCfg lc{w->stream, c.use_pdl != 0};
+  const int H = c.hidden;
+  const int MBp = round_up(w->MB, 16);
+  const bool f32p = a.decode;
+  uint64_t nl = 0;
+  launch_embed(lc, a.tok, w->embed, w->h, a.T, H); ++nl;
+  int prev_planes = 0;
+  for (int l = 0; l < c.n_layers; ++l) {
+    const LayerWeights& lw = w->layers[l];
+    launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, prev_planes, (long long)MBp * H, lw.attn_norm, w->x, nullptr, a.T,
+                       H, c.rms_eps); ++nl;
+    if (gemm_launch(pp->qkv[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
+    RopeKvParams rp;
+    rp.qkv = w->qkv_part; rp.qkv_is_f32 = f32p; rp.n_planes = pp->s_qkv; rp.plane_stride = (long long)MBp * w->qkv_dim;
+    rp.bias = lw.bqkv; rp.pos = a.pos; rp.slot_of_tok = a.slot_of_tok; rp.block_table = w->d_block_table;
+    rp.max_pages = w->max_pages; rp.inv_freq = w->inv_freq; rp.q_out = w->q;
+    rp.k_cache = w->k_cache + (size_t)l * w->cache_layer_stride;
+    rp.v_cache = w->v_cache + (size_t)l * w->cache_layer_stride;
+    rp.T = a.T; rp.n_q = c.n_q_heads; rp.n_kv = c.n_kv_heads;
+    launch_rope_kv(lc, rp); ++nl;
+    AttnParams ap = {};
+    ap.q = w->q; ap.k_cache = rp.k_cache; ap.v_cache = rp.v_cache; ap.block_table = w->d_block_table;
+    ap.max_pages = w->max_pages; ap.tiles = w->d_tiles; ap.pos = a.pos; ap.out = w->attn; ap.part_o = w->part_o;
+    ap.part_ml = w->part_ml; ap.n_q = c.n_q_heads; ap.n_kv = c.n_kv_heads; ap.T = a.T; ap.n_splits = a.n_splits;
+    ap.kv_chunk = kDecodeKvChunk; ap.scale_log2 = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
+    if (a.decode) { launch_attn_decode(lc, ap, a.T); nl += 2; }
+    else { launch_attn_prefill(lc, ap, a.n_tiles); ++nl; }
+    if (gemm_launch(pp->o[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
+    launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, pp->s_o, (long long)MBp * H, lw.mlp_norm, w->x, nullptr, a.T, H,
+                       c.rms_eps); ++nl;
+    if (gemm_launch(pp->gate_up[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
+    if (gemm_launch(pp->down[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
+    prev_planes = pp->s_down;
+  }
+  *n_launch += nl;
+  return MQ_OK;
+}
+
+// final norm (+ last partial) on `rows` gathered rows -> lm head -> logits[rows][V]
+static int run_head(mq_worker* w, bool decode, const int* row_idx, int rows, PassPlans* pp, uint64_t* n_launch) {
+  const mq_model_cfg& c = w->cfg;
+  const LaunchCfg lc{w->stream, c.use_pdl != 0};
+  const int MBp = round_up(w->MB, 16);
+  launch_add_rmsnorm(lc, w->h, w->proj_part, decode, pp->s_down, (long long)MBp * c.hidden, w->final_norm, w->x_last,
+                     row_idx, rows, c.hidden, c.rms_eps);
+  GemmPlan* g = get_lm_plan(w, rows);
+  if (!g) return MQ_ERR_CUDA;
+  if (gemm_launch(*g, lc) != cudaSuccess) return MQ_ERR_CUDA;
+  *n_launch += 2;
+  return MQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// staging ring for metadata uploads
+// ------------------------------------------------------------------------------------------------
+static int* stage_acquire(mq_worker* w, int* slot_out) {
+  const int s = w->stage_next;
+  w->stage_next = (s + 1) % kStageSlots;
+  cudaEventSynchronize(w->stage_ev[s]);  // no-op unless we lapped the GPU
+  *slot_out = s;
+  return w->h_stage + (size_t)s * w->stage_ints;
+}
+static void stage_release(mq_worker* w, int slot) { cudaEventRecord(w->stage_ev[slot], w->stream); }
+
+static cudaEvent_t ev_get(mq_worker* w) {
+  if (!w->ev_pool.empty()) {
+    cudaEvent_t e = w->ev_pool.back();
+    w->ev_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+// upload the host mirrors of the slot table (pos / active / block table) when they changed
+static void upload_slots(mq_worker* w) {
+  if (!w->slots_dirty) return;
+  const int MBp = round_up(w->MB, 16);
+  int ss;
+  int* st = stage_acquire(w, &ss);
+  int* s_pos = st;
+  int* s_act = st + MBp;
+  int* s_bt = st + 2 * MBp;
+  memcpy(s_pos, w->h_pos, MBp * 4);
+  memcpy(s_act, w->h_active, MBp * 4);
+  memcpy(s_bt, w->h_block_table, (size_t)MBp * w->max_pages * 4);
+  cudaMemcpyAsync(w->d_pos, s_pos, MBp * 4, cudaMemcpyHostToDevice, w->stream);
+  cudaMemcpyAsync(w->d_active, s_act, MBp * 4, cudaMemcpyHostToDevice, w->stream);
+  cudaMemcpyAsync(w->d_block_table, s_bt, (size_t)MBp * w->max_pages * 4, cudaMemcpyHostToDevice, w->stream);
+  stage_release(w, ss);
+  w->slots_dirty = false;
+}
+
+// ------------------------------------------------------------------------------------------------
+// request lifecycle helpers (worker thread only)
+// ------------------------------------------------------------------------------------------------
+static void req_unref(mq_req* r) {
+  if (r->refs.fetch_sub(1) == 1) delete r;
+}
+
+static void free_slot(mq_worker* w, mq_req* r) {
+  if (r->slot < 0) return;
+  const int s = r->slot;
+  for (int p : r->pages) w->free_pages.push_back(p);
+  r->pages.clear();
+  w->slot_req[s] = nullptr;
+  w->h_active[s] = 0;
+  w->h_pos[s] = 0;
+  for (int i = 0; i < w->max_pages; ++i) w->h_block_table[(size_t)s * w->max_pages + i] = 0;  // scratch page
+  w->slots_dirty = true;
+  r->slot = -1;
+}
+
+static void send_status(mq_req* r) {
+  if (r->status_sent) return;
+  r->status_sent = true;
+  if (r->cb.on_status) r->cb.on_status(r->user, 200, content_type_for(r->rq.endpoint, r->rq.stream));
+}
+
+static void finish_req(mq_worker* w, mq_req* r, int rc, const char* msg) {
+  if (r->finished) return;
+  r->finished = true;
+  r->done_rc = rc;
+  r->t_last = Clock::now();
+  free_slot(w, r);
+  if (rc == 0) {
+    send_status(r);
+    std::string tail = frame_final(r->rq.endpoint, r->rq.stream, w->cfg.model_name, r->agg, (int)r->prompt.size(),
+                                   r->n_emitted);
+    if (!tail.empty() && r->cb.on_chunk) r->cb.on_chunk(r->user, (const uint8_t*)tail.data(), tail.size());
+  }
+  if (r->cb.on_done) r->cb.on_done(r->user, rc, msg ? msg : "");
+  req_unref(r);
+}
+
+static void emit_token(mq_worker* w, mq_req* r, int tok) {
+  if (r->finished) return;
+  if (r->n_emitted == 0) r->t_first = Clock::now();
+  r->n_emitted++;
+  send_status(r);
+  if (r->rq.stream) {
+    uint8_t raw[4];
+    std::string s;
+    const uint8_t* data;
+    size_t len;
+    if (r->rq.endpoint == MQ_EP_RAW_TOKENS) {
+      memcpy(raw, &tok, 4);
+      data = raw; len = 4;
+    } else {
+      s = frame_token(r->rq.endpoint, w->cfg.model_name, tok);
+      data = (const uint8_t*)s.data(); len = s.size();
+    }
+    if (r->cb.on_chunk && r->cb.on_chunk(r->user, data, len) != 0) r->cancel.store(true);  // client gone (:305-308)
+  } else {
+    if (r->rq.endpoint == MQ_EP_RAW_TOKENS) r->agg.append((const char*)&tok, 4);
+    else r->agg += token_text(tok);
+  }
+  if (r->n_emitted >= r->max_new) finish_req(w, r, 0, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// prefill pass
+// ------------------------------------------------------------------------------------------------
+struct PrefillItem { mq_req* r; int n_tok; bool completes; };
+
+static int launch_prefill(mq_worker* w, std::vector<PrefillItem>& items) {
+  const mq_model_cfg& c = w->cfg;
+  const int G = c.n_q_heads / c.n_kv_heads;
+  const int tok_per_tile = kPrefillTileRows / G;
+  int T = 0;
+  for (auto& it : items) T += it.n_tok;
+  int ss;
+  int* st = stage_acquire(w, &ss);
+  int* s_tok = st;
+  int* s_pos = st + w->MT;
+  int* s_slot = st + 2 * w->MT;
+  int* s_tiles = st + 3 * w->MT;                 // int4 per tile
+  int* s_last = s_tiles + 4 * (w->MT + w->MB);
+  int* s_dst = s_last + round_up(w->MB, 16);
+  int n_tiles = 0, n_last = 0, row = 0;
+  for (auto& it : items) {
+    mq_req* r = it.r;
+    const int p0 = r->n_prefilled;
+    for (int i = 0; i < it.n_tok; ++i) {
+      s_tok[row + i] = r->prompt[p0 + i];
+      s_pos[row + i] = p0 + i;
+      s_slot[row + i] = r->slot;
+    }
+    for (int i = 0; i < it.n_tok; i += tok_per_tile) {
+      int* t = s_tiles + 4 * n_tiles++;
+      t[0] = row + i; t[1] = std::min(tok_per_tile, it.n_tok - i); t[2] = r->slot; t[3] = p0 + i;
+    }
+    if (it.completes) {
+      s_last[n_last] = row + it.n_tok - 1;
+      s_dst[n_last] = r->slot;
+      ++n_last;
+    }
+    row += it.n_tok;
+    r->n_prefilled += it.n_tok;
+  }
+  cudaMemcpyAsync(w->d_tok, s_tok, T * 4, cudaMemcpyHostToDevice, w->stream);
+  cudaMemcpyAsync(w->d_pos_tok, s_pos, T * 4, cudaMemcpyHostToDevice, w->stream);
+  cudaMemcpyAsync(w->d_slot_tok, s_slot, T * 4, cudaMemcpyHostToDevice, w->stream);
+  cudaMemcpyAsync(w->d_tiles, s_tiles, (size_t)n_tiles * 16, cudaMemcpyHostToDevice, w->stream);
+  if (n_last) {
+    cudaMemcpyAsync(w->d_last_idx, s_last, n_last * 4, cudaMemcpyHostToDevice, w->stream);
+    cudaMemcpyAsync(w->d_dst_slot, s_dst, n_last * 4, cudaMemcpyHostToDevice, w->stream);
+  }
+  stage_release(w, ss);
+  upload_slots(w);
+
+  PassPlans* pp = get_plans(w, T, false);
+  if (!pp) return MQ_ERR_CUDA;
+  mq_worker::Flight f;
+  f.timed = w->timing;
+  if (f.timed) { f.ev_begin = ev_get(w); cudaEventRecord(f.ev_begin, w->stream); }
+  PassArgs a{T, false, 1, n_tiles, w->d_tok, w->d_pos_tok, w->d_slot_tok};
+  uint64_t nl = 0;
+  int rc = run_layers(w, a, pp, &nl);
+  if (rc) return rc;
+  const int ring = w->ring_next;
+  w->ring_next = (ring + 1) % (kRing - 1);  // row kRing-1 is the fixed output row of captured graphs
+  const int MBp = round_up(w->MB, 16);
+  if (n_last) {
+    rc = run_head(w, false, w->d_last_idx, n_last, pp, &nl);
+    if (rc) return rc;
+    const LaunchCfg lc{w->stream, c.use_pdl != 0};
+    launch_argmax(lc, w->logits, n_last, c.vocab, c.vocab, w->d_out_ring + (size_t)ring * MBp, w->d_dst_slot,
+                  w->d_cur_token, nullptr, nullptr);
+    ++nl;
+    cudaMemcpyAsync(w->h_out_ring + (size_t)ring * MBp, w->d_out_ring + (size_t)ring * MBp, n_last * 4,
+                    cudaMemcpyDeviceToHost, w->stream);
+  }
+  f.ev = ev_get(w);
+  cudaEventRecord(f.ev, w->stream);
+  f.decode = false;
+  f.ring = ring;
+  int k = 0;
+  for (auto& it : items)
+    if (it.completes) {
+      // the sequence joins the decode batch: first generated token sits in cur_token[slot], pos = prompt length
+      mq_req* r = it.r;
+      r->n_sched = 1;
+      w->h_pos[r->slot] = (int)r->prompt.size();
+      w->h_active[r->slot] = r->max_new > 1 ? 1 : 0;
+      w->slots_dirty = true;
+      f.emits.push_back({r, k++});
+    }
+  w->flights.push_back(std::move(f));
+  {
+    std::lock_guard<std::mutex> g(w->stats_mu);
+    w->stats.kernel_launches += nl;
+    w->stats.prefill_passes += 1;
+    w->stats.prefill_tokens += T;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("prefill launch: %s", cudaGetErrorString(e));
+    return MQ_ERR_CUDA;
+  }
+  return MQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode step
+// ------------------------------------------------------------------------------------------------
+static int decode_body(mq_worker* w, int Bcap, int n_splits, int ring, uint64_t* nl) {
+  const mq_model_cfg& c = w->cfg;
+  PassPlans* pp = get_plans(w, Bcap, true);
+  if (!pp) return MQ_ERR_CUDA;
+  PassArgs a{Bcap, true, n_splits, 0, w->d_cur_token, w->d_pos, w->d_identity};
+  int rc = run_layers(w, a, pp, nl);
+  if (rc) return rc;
+  rc = run_head(w, true, w->d_identity, Bcap, pp, nl);
+  if (rc) return rc;
+  const LaunchCfg lc{w->stream, c.use_pdl != 0};
+  const int MBp = round_up(w->MB, 16);
+  // NOTE: the ring slot is baked into a captured graph, so graphs write to a fixed staging row (ring 0 of the
+  // graph area) and the copy-out below moves it into the real ring slot.
+  launch_argmax(lc, w->logits, Bcap, c.vocab, c.vocab, w->d_out_ring + (size_t)ring * MBp, nullptr, w->d_cur_token,
+                w->d_pos, w->d_active);
+  *nl += 1;
+  return MQ_OK;
+}
+
+static int launch_decode(mq_worker* w) {
+  const int MBp = round_up(w->MB, 16);
+  int hi = -1, max_ctx = 1, n_active = 0;
+  double kv_tokens = 0;
+  for (int s = 0; s < w->MB; ++s)
+    if (w->h_active[s]) {
+      hi = s;
+      ++n_active;
+      max_ctx = std::max(max_ctx, w->h_pos[s] + 1);
+      kv_tokens += w->h_pos[s] + 1;
+    }
+  if (hi < 0) return MQ_OK;
+  const int Bcap = std::min(MBp, round_up(hi + 1, 16));
+  const int n_splits = (max_ctx + kDecodeKvChunk - 1) / kDecodeKvChunk;
+  upload_slots(w);
+
+  mq_worker::Flight f;
+  f.timed = w->timing;
+  if (f.timed) { f.ev_begin = ev_get(w); cudaEventRecord(f.ev_begin, w->stream); }
+  const int ring = w->ring_next;
+  w->ring_next = (ring + 1) % (kRing - 1);  // row kRing-1 is the fixed output row of captured graphs
+  uint64_t nl = 0;
+  bool graph_launched = false;
+  if (w->cfg.use_graphs) {
+    // graphs always write their tokens to ring row 0's alias at the end of the ring buffer (fixed address)
+    const long long key = (long long)Bcap * 1024 + n_splits;
+    auto it = w->graphs.find(key);
+    if (it == w->graphs.end()) {
+      if (!get_plans(w, Bcap, true) || !get_lm_plan(w, Bcap)) return MQ_ERR_CUDA;
+      // warm-up launch outside capture so every kernel's attributes are set before capturing
+      uint64_t tmp = 0;
+      cudaGraph_t g = nullptr;
+      cudaError_t e = cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal);
+      int rc = e == cudaSuccess ? decode_body(w, Bcap, n_splits, kRing - 1, &tmp) : MQ_ERR_CUDA;
+      cudaError_t e2 = cudaStreamEndCapture(w->stream, &g);
+      if (rc != MQ_OK || e2 != cudaSuccess || !g) {
+        set_last_error("graph capture failed: %s", cudaGetErrorString(e2 != cudaSuccess ? e2 : cudaGetLastError()));
+        return MQ_ERR_CUDA;
+      }
+      cudaGraphExec_t ge = nullptr;
+      e = cudaGraphInstantiate(&ge, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess) {
+        set_last_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        return MQ_ERR_CUDA;
+      }
+      it = w->graphs.emplace(key, ge).first;
+      std::lock_guard<std::mutex> gl(w->stats_mu);
+      w->stats.kernel_launches += 0;
+    }
+    cudaError_t e = cudaGraphLaunch(it->second, w->stream);
+    if (e != cudaSuccess) {
+      set_last_error("cudaGraphLaunch: %s", cudaGetErrorString(e));
+      return MQ_ERR_CUDA;
+    }
+    graph_launched = true;
+    // graph wrote to the fixed row kRing-1; move it to this step's ring slot on the host side copy
+    cudaMemcpyAsync(w->h_out_ring + (size_t)ring * MBp, w->d_out_ring + (size_t)(kRing - 1) * MBp, Bcap * 4,
+                    cudaMemcpyDeviceToHost, w->stream);
+    nl = (uint64_t)(1 + w->cfg.n_layers * 9 + 3);
+  } else {
+    int rc = decode_body(w, Bcap, n_splits, ring, &nl);
+    if (rc) return rc;
+    cudaMemcpyAsync(w->h_out_ring + (size_t)ring * MBp, w->d_out_ring + (size_t)ring * MBp, Bcap * 4,
+                    cudaMemcpyDeviceToHost, w->stream);
+  }
+  f.ev = ev_get(w);
+  cudaEventRecord(f.ev, w->stream);
+  f.decode = true;
+  f.ring = ring;
+  f.bytes = w->p_mm_bytes + (kv_tokens + n_active) * w->kv_bytes_per_tok;
+  for (int s = 0; s < w->MB; ++s)
+    if (w->h_active[s]) {
+      mq_req* r = w->slot_req[s];
+      f.emits.push_back({r, s});
+      w->h_pos[s] += 1;  // mirrors the device-side pos++ of the sampler kernel
+      r->n_sched += 1;
+      if (r->n_sched >= r->max_new) {  // last token scheduled: slot leaves the batch at the next step
+        w->h_active[s] = 0;
+        w->slots_dirty = true;
+      }
+    }
+  w->flights.push_back(std::move(f));
+  {
+    std::lock_guard<std::mutex> g(w->stats_mu);
+    w->stats.kernel_launches += nl;
+    w->stats.graph_launches += graph_launched ? 1 : 0;
+    w->stats.decode_steps += 1;
+    w->stats.decode_tokens += n_active;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("decode launch: %s", cudaGetErrorString(e));
+    return MQ_ERR_CUDA;
+  }
+  return MQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// completion of GPU work -> callbacks
+// ------------------------------------------------------------------------------------------------
+static void retire_flight(mq_worker* w, mq_worker::Flight& f) {
+  const int MBp = round_up(w->MB, 16);
+  if (f.timed) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, f.ev_begin, f.ev);
+    std::lock_guard<std::mutex> g(w->stats_mu);
+    if (f.decode) { w->stats.decode_ms += ms; w->stats.decode_bytes += f.bytes; }
+    else w->stats.prefill_ms += ms;
+    w->ev_pool.push_back(f.ev_begin);
+  }
+  w->ev_pool.push_back(f.ev);
+  const int* row = w->h_out_ring + (size_t)f.ring * MBp;
+  for (auto& em : f.emits) {
+    mq_req* r = em.first;
+    if (r->finished) continue;
+    if (r->cancel.load()) continue;  // handled by the cancel sweep
+    emit_token(w, r, row[em.second]);
+  }
+  for (auto& em : f.emits) req_unref(em.first);
+}
+
+static void poll_flights(mq_worker* w, bool block_oldest) {
+  while (!w->flights.empty()) {
+    mq_worker::Flight& f = w->flights.front();
+    cudaError_t e = block_oldest ? cudaEventSynchronize(f.ev) : cudaEventQuery(f.ev);
+    block_oldest = false;
+    if (e == cudaErrorNotReady) return;
+    if (e != cudaSuccess) {
+      w->fatal = std::string("GPU fault: ") + cudaGetErrorString(e);
+      w->healthy.store(false);
+      return;
+    }
+    mq_worker::Flight done = std::move(f);
+    w->flights.pop_front();
+    retire_flight(w, done);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the worker thread
+// ------------------------------------------------------------------------------------------------
+static void fail_all(mq_worker* w, const char* msg) {
+  auto kill = [&](mq_req* r) { if (r && !r->finished) finish_req(w, r, MQ_ERR_CUDA, msg); };
+  for (auto& f : w->flights) for (auto& em : f.emits) req_unref(em.first);
+  w->flights.clear();
+  for (mq_req* r : w->waiting) kill(r);
+  w->waiting.clear();
+  for (mq_req* r : w->prefilling) kill(r);
+  w->prefilling.clear();
+  for (int s = 0; s < w->MB; ++s) kill(w->slot_req[s]);
+}
+
+static bool admit(mq_worker* w, mq_req* r) {
+  int slot = -1;
+  for (int s = 0; s < w->MB; ++s)
+    if (!w->slot_req[s]) { slot = s; break; }
+  if (slot < 0) return false;
+  const int need = ((int)r->prompt.size() + r->max_new + kPageSize - 1) / kPageSize;
+  if ((int)w->free_pages.size() < need) return false;
+  r->slot = slot;
+  w->slot_req[slot] = r;
+  r->pages.resize(need);
+  for (int i = 0; i < need; ++i) {
+    r->pages[i] = w->free_pages.back();
+    w->free_pages.pop_back();
+    w->h_block_table[(size_t)slot * w->max_pages + i] = r->pages[i];
+  }
+  w->h_pos[slot] = 0;
+  w->h_active[slot] = 0;
+  w->slots_dirty = true;
+  return true;
+}
+
+static void sweep_cancels(mq_worker* w) {
+  const auto now = Clock::now();
+  // returns true when the request was finished here (the pointer may be dangling afterwards)
+  auto check = [&](mq_req* r) -> bool {
+    if (!r || r->finished) return false;
+    if (r->cancel.load()) { finish_req(w, r, MQ_ERR_CANCELED, "canceled"); return true; }
+    if (r->has_deadline && now > r->deadline) { finish_req(w, r, MQ_ERR_TIMEOUT, "request timed out"); return true; }
+    return false;
+  };
+  for (auto it = w->waiting.begin(); it != w->waiting.end();) it = check(*it) ? w->waiting.erase(it) : it + 1;
+  for (auto it = w->prefilling.begin(); it != w->prefilling.end();) it = check(*it) ? w->prefilling.erase(it) : it + 1;
+  for (int s = 0; s < w->MB; ++s) check(w->slot_req[s]);
+}
+
+static void worker_main(mq_worker* w) {
+  cudaSetDevice(w->gpu);
+  for (;;) {
+    // ---- intake
+    {
+      std::unique_lock<std::mutex> lk(w->mu);
+      const bool idle = w->flights.empty() && w->waiting.empty() && w->prefilling.empty() &&
+                        std::none_of(w->h_active, w->h_active + w->MB, [](int a) { return a != 0; });
+      if (idle && w->inbox.empty() && w->jobs.empty() && !w->stop)
+        w->cv.wait_for(lk, std::chrono::milliseconds(50));
+      if (w->stop) break;
+      while (!w->inbox.empty()) { w->waiting.push_back(w->inbox.front()); w->inbox.pop_front(); }
+      if (idle && !w->jobs.empty()) {
+        auto job = std::move(w->jobs.front());
+        w->jobs.pop_front();
+        lk.unlock();
+        job();
+        continue;
+      }
+    }
+    if (!w->healthy.load()) { fail_all(w, w->fatal.c_str()); continue; }
+    sweep_cancels(w);
+
+    // ---- admit + build one prefill pass (prefill has priority: it grows the decode batch)
+    while (!w->waiting.empty() && admit(w, w->waiting.front())) {
+      w->prefilling.push_back(w->waiting.front());
+      w->waiting.pop_front();
+    }
+    bool launched = false;
+    int n_prefill_flights = 0, n_decode_flights = 0;
+    for (auto& f : w->flights) (f.decode ? n_decode_flights : n_prefill_flights)++;
+    if (!w->prefilling.empty()) {
+      if (n_prefill_flights < kMaxFlightsPrefill) {
+        std::vector<PrefillItem> items;
+        int budget = w->cfg.max_prefill_tokens;
+        while (!w->prefilling.empty() && budget > 0 && (int)items.size() < w->MB) {
+          mq_req* r = w->prefilling.front();
+          const int remaining = (int)r->prompt.size() - r->n_prefilled;
+          if (remaining > budget && !items.empty()) break;  // keep whole prompts together when possible
+          const int n = std::min(remaining, budget);
+          const bool completes = n == remaining;
+          items.push_back({r, n, completes});
+          budget -= n;
+          if (completes) { w->prefilling.pop_front(); r->refs.fetch_add(1); }
+          else break;  // a chunked prompt owns the rest of this pass
+        }
+        if (!items.empty()) {
+          if (launch_prefill(w, items) != MQ_OK) { w->fatal = mq_last_error(); w->healthy.store(false); continue; }
+          launched = true;
+        }
+      }
+    } else if (n_decode_flights < kMaxFlightsDecode) {
+      bool any = false;
+      for (int s = 0; s < w->MB; ++s) any |= w->h_active[s] != 0;
+      if (any) {
+        for (int s = 0; s < w->MB; ++s)
+          if (w->h_active[s]) w->slot_req[s]->refs.fetch_add(1);
+        if (launch_decode(w) != MQ_OK) { w->fatal = mq_last_error(); w->healthy.store(false); continue; }
+        launched = true;
+      }
+    }
+    // ---- completions: block only when nothing else can be launched
+    poll_flights(w, !launched && !w->flights.empty());
+  }
+  // shutdown: drain
+  cudaStreamSynchronize(w->stream);
+  poll_flights(w, false);
+  fail_all(w, "worker closed");
+}
+
+// ------------------------------------------------------------------------------------------------
+// debug forward (kernel-level test ABI): runs on the worker thread when idle
+// ------------------------------------------------------------------------------------------------
+int engine_forward_logits(mq_worker* w, const int32_t* tokens, int n, int all_positions, float* out) {
+  const mq_model_cfg& c = w->cfg;
+  if (n < 1 || n > c.max_seq) {
+    set_last_error("mq_debug_forward: n=%d out of range (max_seq %d)", n, c.max_seq);
+    return MQ_ERR_INVAL;
+  }
+  const int MBp = round_up(w->MB, 16);
+  const int G = c.n_q_heads / c.n_kv_heads, tok_per_tile = kPrefillTileRows / G;
+  const int need = (n + kPageSize - 1) / kPageSize;
+  if ((int)w->free_pages.size() < need || w->slot_req[0]) {
+    set_last_error("mq_debug_forward: worker busy");
+    return MQ_ERR_BUSY;
+  }
+  // temporary block table for slot 0
+  std::vector<int> pages(need);
+  for (int i = 0; i < need; ++i) { pages[i] = w->free_pages.back(); w->free_pages.pop_back(); }
+  for (int i = 0; i < need; ++i) w->h_block_table[i] = pages[i];
+  w->slots_dirty = true;
+  uint64_t nl = 0;
+  int rc = MQ_OK;
+  for (int p0 = 0; p0 < n && rc == MQ_OK; p0 += c.max_prefill_tokens) {
+    const int T = std::min(c.max_prefill_tokens, n - p0);
+    std::vector<int> tok(T), pos(T), slot(T, 0), tiles;
+    for (int i = 0; i < T; ++i) { tok[i] = tokens[p0 + i]; pos[i] = p0 + i; }
+    for (int i = 0; i < T; i += tok_per_tile) {
+      tiles.push_back(i); tiles.push_back(std::min(tok_per_tile, T - i)); tiles.push_back(0); tiles.push_back(p0 + i);
+    }
+    cudaMemcpyAsync(w->d_tok, tok.data(), T * 4, cudaMemcpyHostToDevice, w->stream);
+    cudaMemcpyAsync(w->d_pos_tok, pos.data(), T * 4, cudaMemcpyHostToDevice, w->stream);
+    cudaMemcpyAsync(w->d_slot_tok, slot.data(), T * 4, cudaMemcpyHostToDevice, w->stream);
+    cudaMemcpyAsync(w->d_tiles, tiles.data(), tiles.size() * 4, cudaMemcpyHostToDevice, w->stream);
+    upload_slots(w);
+    cudaStreamSynchronize(w->stream);  // host vectors above go out of scope
+    PassPlans* pp = get_plans(w, T, false);
+    if (!pp) { rc = MQ_ERR_CUDA; break; }
+    PassArgs a{T, false, 1, (int)tiles.size() / 4, w->d_tok, w->d_pos_tok, w->d_slot_tok};
+    rc = run_layers(w, a, pp, &nl);
+    if (rc) break;
+    // logits for the requested rows, MBp rows at a time
+    const int first = all_positions ? 0 : (p0 + T == n ? T - 1 : T);
+    for (int r0 = first; r0 < T && rc == MQ_OK; r0 += MBp) {
+      const int rows = std::min(MBp, T - r0);
+      std::vector<int> idx(rows);
+      for (int i = 0; i < rows; ++i) idx[i] = r0 + i;
+      cudaMemcpyAsync(w->d_last_idx, idx.data(), rows * 4, cudaMemcpyHostToDevice, w->stream);
+      cudaStreamSynchronize(w->stream);
+      rc = run_head(w, false, w->d_last_idx, rows, pp, &nl);
+      if (rc) break;
+      float* dst = all_positions ? out + (size_t)(p0 + r0) * c.vocab : out;
+      if (cudaMemcpyAsync(dst, w->logits, (size_t)rows * c.vocab * 4, cudaMemcpyDeviceToHost, w->stream) != cudaSuccess)
+        rc = MQ_ERR_CUDA;
+      cudaStreamSynchronize(w->stream);
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(w->stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { set_last_error("mq_debug_forward: %s", cudaGetErrorString(e)); rc = MQ_ERR_CUDA; }
+  for (int i = 0; i < need; ++i) { w->free_pages.push_back(pages[i]); w->h_block_table[i] = 0; }
+  w->slots_dirty = true;
+  return rc;
+}
+
+static int run_job(mq_worker* w, std::function<int()> fn) {
+  std::mutex m;
+  std::condition_variable cv;
+  bool done = false;
+  int rc = 0;
+  std::string err;
+  {
+    std::lock_guard<std::mutex> g(w->mu);
+    w->jobs.push_back([&] {
+      rc = fn();
+      err = mq_last_error();
+      std::lock_guard<std::mutex> g2(m);
+      done = true;
+      cv.notify_all();
+    });
+  }
+  w->cv.notify_all();
+  std::unique_lock<std::mutex> lk(m);
+  cv.wait(lk, [&] { return done; });
+  if (rc != MQ_OK) set_last_error("%s", err.c_str());
+  return rc;
+}
+
+}  // namespace mq
+
+// ================================================================================================ C ABI
+using namespace mq;
+
+extern "C" {
+
+int mq_worker_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+int mq_worker_open(int32_t gpu, const mq_model_cfg* cfg, mq_worker** out) {
+  if (!cfg || !out) return MQ_ERR_INVAL;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || gpu < 0 || gpu >= n) {
+    cudaGetLastError();
+    set_last_error("no CUDA device %d (this library has no CPU fallback)", gpu);
+    return MQ_ERR_NODEV;
+  }
+  cudaDeviceProp prop;
+  CUDA_TRY(cudaGetDeviceProperties(&prop, gpu));
+  if (prop.major != 10) {
+    set_last_error("device %d is sm_%d%d; this library is built for sm_100a only", gpu, prop.major, prop.minor);
+    return MQ_ERR_NODEV;
+  }
+  const mq_model_cfg& c = *cfg;
+  if (c.head_dim != kHeadDim || c.hidden % 512 != 0 || c.hidden % 64 != 0 || c.ffn % 128 != 0 ||
+      c.n_q_heads % c.n_kv_heads != 0 || kPrefillTileRows / (c.n_q_heads / c.n_kv_heads) < 1 || c.vocab % 4 != 0 ||
+      c.max_batch < 1 || c.max_batch > 256 || c.max_seq < 1 || c.max_prefill_tokens < 16 || c.n_layers < 1) {
+    set_last_error("unsupported model geometry (need head_dim 128, hidden %% 512 == 0, ffn %% 128 == 0, "
+                   "vocab %% 4 == 0, 1 <= max_batch <= 256)");
+    return MQ_ERR_INVAL;
+  }
+  CUDA_TRY(cudaSetDevice(gpu));
+  mq_worker* w = new (std::nothrow) mq_worker();
+  if (!w) return MQ_ERR_NOMEM;
+  w->cfg = c;
+  w->cfg.model_name[sizeof(w->cfg.model_name) - 1] = 0;
+  w->gpu = gpu;
+  CUDA_TRY(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+  gemm_set_attrs();
+  attn_set_attrs();
+  int rc = worker_alloc(w);
+  if (rc != MQ_OK) {
+    mq_worker_close(w);
+    return rc;
+  }
+  w->thr = std::thread(worker_main, w);
+  *out = w;
+  return MQ_OK;
+}
+
+void mq_worker_close(mq_worker* w) {
+  if (!w) return;
+  if (w->thr.joinable()) {
+    { std::lock_guard<std::mutex> g(w->mu); w->stop = true; }
+    w->cv.notify_all();
+    w->thr.join();
+  }
+  cudaSetDevice(w->gpu);
+  {
+    std::lock_guard<std::mutex> g(w->mu);
+    for (mq_req* r : w->inbox) {
+      if (r->cb.on_done) r->cb.on_done(r->user, MQ_ERR_CANCELED, "worker closed");
+      req_unref(r);
+    }
+    w->inbox.clear();
+  }
+  if (w->stream) cudaStreamSynchronize(w->stream);
+  for (auto& kv : w->graphs) cudaGraphExecDestroy(kv.second);
+  for (auto& kv : w->tensors) cudaFree(kv.second.ptr);
+  void* bufs[] = {w->k_cache, w->v_cache, w->h, w->x, w->q, w->attn, w->act, w->x_last, w->qkv_part, w->proj_part,
+                  w->logits, w->part_o, w->part_ml, w->inv_freq, w->d_tok, w->d_pos_tok, w->d_slot_tok, w->d_last_idx,
+                  w->d_dst_slot, w->d_tiles, w->d_cur_token, w->d_pos, w->d_active, w->d_block_table, w->d_identity,
+                  w->d_out_ring};
+  for (void* b : bufs) if (b) cudaFree(b);
+  void* pinned[] = {w->h_pos, w->h_active, w->h_block_table, w->h_stage, w->h_out_ring};
+  for (void* b : pinned) if (b) cudaFreeHost(b);
+  for (auto e : w->stage_ev) cudaEventDestroy(e);
+  for (auto e : w->ev_pool) cudaEventDestroy(e);
+  if (w->stream) cudaStreamDestroy(w->stream);
+  delete w;
+}
+
+static DevTensor* find_tensor(mq_worker* w, const char* name) {
+  if (!w || !name) return nullptr;
+  auto it = w->tensors.find(name);
+  if (it == w->tensors.end()) {
+    set_last_error("unknown tensor '%s'", name);
+    return nullptr;
+  }
+  return &it->second;
+}
+
+int mq_worker_load_tensor(mq_worker* w, const char* name, const void* src, size_t nbytes) {
+  DevTensor* t = find_tensor(w, name);
+  if (!t) return MQ_ERR_NOENT;
+  if (nbytes != t->bytes) {
+    set_last_error("tensor '%s': got %zu bytes, expected %zu", name, nbytes, t->bytes);
+    return MQ_ERR_INVAL;
+  }
+  cudaSetDevice(w->gpu);
+  CUDA_TRY(cudaMemcpy(t->ptr, src, nbytes, cudaMemcpyDefault));
+  return MQ_OK;
+}
+
+int mq_worker_read_tensor(mq_worker* w, const char* name, void* dst, size_t nbytes) {
+  DevTensor* t = find_tensor(w, name);
+  if (!t) return MQ_ERR_NOENT;
+  if (nbytes != t->bytes) {
+    set_last_error("tensor '%s': asked %zu bytes, tensor has %zu", name, nbytes, t->bytes);
+    return MQ_ERR_INVAL;
+  }
+  cudaSetDevice(w->gpu);
+  CUDA_TRY(cudaMemcpy(dst, t->ptr, nbytes, cudaMemcpyDefault));
+  return MQ_OK;
+}
+
+int mq_worker_init_random(mq_worker* w, uint64_t seed, float std) {
+  if (!w) return MQ_ERR_INVAL;
+  cudaSetDevice(w->gpu);
+  uint64_t k = 0;
+  for (auto& kv : w->tensors) {  // std::map: deterministic name order
+    const bool is_norm = kv.first.find("norm") != std::string::npos;
+    const bool is_bias = kv.first.find("bqkv") != std::string::npos;
+    __nv_bfloat16* p = (__nv_bfloat16*)kv.second.ptr;
+    const size_t n = kv.second.bytes / 2;
+    if (is_norm) launch_fill_bf16(0, p, n, 1.0f);
+    else if (is_bias) launch_fill_bf16(0, p, n, 0.0f);
+    else launch_init_normal(0, p, n, seed * 0x9E3779B97F4A7C15ull + (++k) * 0xD6E8FEB86659FD93ull, std);
+  }
+  CUDA_TRY(cudaDeviceSynchronize());
+  return MQ_OK;
+}
+
+int mq_worker_capacity(mq_worker* w) { return w ? w->MB : 0; }
+int mq_worker_healthy(mq_worker* w) { return w && w->healthy.load() ? 1 : 0; }
+
+int mq_submit(mq_worker* w, const mq_request* rq, const mq_callbacks* cb, void* user, mq_req** out) {
+  if (!w || !rq || !cb) return MQ_ERR_INVAL;
+  if (!w->healthy.load()) {
+    set_last_error("worker unhealthy: %s", w->fatal.c_str());
+    return MQ_ERR_CUDA;
+  }
+  mq_req* r = new (std::nothrow) mq_req();
+  if (!r) return MQ_ERR_NOMEM;
+  r->w = w;
+  r->rq = *rq;
+  r->cb = *cb;
+  r->user = user;
+  r->t_submit = Clock::now();
+  if (rq->body && rq->body_len) r->body.assign((const char*)rq->body, rq->body_len);
+  ParsedBody pb;
+  if (!r->body.empty()) parse_body(r->body, rq->endpoint, &pb);
+  if (rq->prompt_tokens && rq->n_prompt_tokens > 0)
+    r->prompt.assign(rq->prompt_tokens, rq->prompt_tokens + rq->n_prompt_tokens);
+  else if (!pb.tokens.empty())
+    r->prompt = pb.tokens;
+  else
+    r->prompt = byte_tokenize(pb.text, w->cfg.vocab);
+  if (r->prompt.empty()) r->prompt.push_back(0);
+  for (int32_t& t : r->prompt) if (t < 0 || t >= w->cfg.vocab) t = 0;
+  r->rq.body = nullptr; r->rq.prompt_tokens = nullptr;
+  if (pb.has_stream && rq->stream < 0) r->rq.stream = pb.stream ? 1 : 0;
+  if (r->rq.stream < 0) r->rq.stream = 1;
+  r->max_new = rq->max_new_tokens > 0 ? rq->max_new_tokens : (pb.num_predict > 0 ? pb.num_predict : 128);
+  if ((int)r->prompt.size() + r->max_new > w->cfg.max_seq) {
+    const int n = (int)r->prompt.size();
+    delete r;
+    set_last_error("prompt (%d) + max_new_tokens exceeds max_seq %d", n, w->cfg.max_seq);
+    return MQ_ERR_INVAL;
+  }
+  if (((int)r->prompt.size() + r->max_new + kPageSize - 1) / kPageSize > w->n_pages - 1) {
+    delete r;
+    set_last_error("request needs more KV pages than the worker owns (%d)", w->n_pages - 1);
+    return MQ_ERR_NOMEM;
+  }
+  if (rq->timeout_ms) {
+    r->has_deadline = true;
+    r->deadline = r->t_submit + std::chrono::milliseconds(rq->timeout_ms);
+  }
+  if (out) *out = r; else r->refs.store(1);
+  {
+    std::lock_guard<std::mutex> g(w->mu);
+    w->inbox.push_back(r);
+  }
+  w->cv.notify_all();
+  return MQ_OK;
+}
+
+void mq_cancel(mq_req* r) {
+  if (!r) return;
+  r->cancel.store(true);
+  if (r->w) r->w->cv.notify_all();
+}
+
+void mq_req_release(mq_req* r) {
+  if (r) req_unref(r);
+}
+
+int mq_req_get_stats(mq_req* r, mq_req_stats* out) {
+  if (!r || !out) return MQ_ERR_INVAL;
+  using us = std::chrono::microseconds;
+  out->n_prompt = (int)r->prompt.size();
+  out->n_generated = r->n_emitted;
+  out->ttft_us = r->n_emitted > 0 ? (uint64_t)std::chrono::duration_cast<us>(r->t_first - r->t_submit).count() : 0;
+  out->total_us = r->finished ? (uint64_t)std::chrono::duration_cast<us>(r->t_last - r->t_submit).count() : 0;
+  return MQ_OK;
+}
+
+int mq_worker_get_stats(mq_worker* w, mq_worker_stats* out) {
+  if (!w || !out) return MQ_ERR_INVAL;
+  std::lock_guard<std::mutex> g(w->stats_mu);
+  *out = w->stats;
+  return MQ_OK;
+}
+int mq_worker_reset_stats(mq_worker* w) {
+  if (!w) return MQ_ERR_INVAL;
+  std::lock_guard<std::mutex> g(w->stats_mu);
+  w->stats = mq_worker_stats{};
+  return MQ_OK;
+}
+int mq_worker_set_timing(mq_worker* w, int32_t enable) {
+  if (!w) return MQ_ERR_INVAL;
+  w->timing = enable != 0;
+  return MQ_OK;
+}
+
+int mq_debug_forward(mq_worker* w, const int32_t* tokens, int32_t n, int32_t all_positions, float* logits_out) {
+  if (!w || !tokens || !logits_out) return MQ_ERR_INVAL;
+  return run_job(w, [=] { return engine_forward_logits(w, tokens, n, all_positions, logits_out); });
+}
+
+}  // extern "C"

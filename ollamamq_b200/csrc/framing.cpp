@@ -1,0 +1,307 @@
+#include "framing.hpp"
+#include "../../include/ollamamq_b200.h"
+#include <cctype>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+
+namespace mq {
+
+// ------------------------------------------------------------------ minimal JSON walker
+namespace {
+struct J {
+  const char* p;
+  const char* e;
+  void ws() { while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p; }
+  bool lit(const char* s) {
+    size_t n = strlen(s);
+    if ((size_t)(e - p) >= n && memcmp(p, s, n) == 0) { p += n; return true; }
+    return false;
+  }
+  bool str(std::string* out) {
+    ws();
+    if (p >= e || *p != '"') return false;
+    ++p;
+    while (p < e && *p != '"') {
+      if (*p == '\\' && p + 1 < e) {
+        ++p;
+        char c = *p++;
+        switch (c) {
+          case 'n': if (out) out->push_back('\n'); break;
+          case 't': if (out) out->push_back('\t'); break;
+          case 'r': if (out) out->push_back('\r'); break;
+          case 'b': if (out) out->push_back('\b'); break;
+          case 'f': if (out) out->push_back('\f'); break;
+          case 'u': {
+            unsigned cp = 0;
+            for (int i = 0; i < 4 && p < e; ++i, ++p) cp = cp * 16 + (unsigned)(isdigit((unsigned char)*p) ? *p - '0' : (tolower(*p) - 'a' + 10));
+            if (out) {
+              if (cp < 0x80) out->push_back((char)cp);
+              else if (cp < 0x800) { out->push_back((char)(0xC0 | (cp >> 6))); out->push_back((char)(0x80 | (cp & 0x3F))); }
+              else { out->push_back((char)(0xE0 | (cp >> 12))); out->push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out->push_back((char)(0x80 | (cp & 0x3F))); }
+            }
+            break;
+          }
+          default: if (out) out->push_back(c);
+        }
+      } else {
+        if (out) out->push_back(*p);
+        ++p;
+      }
+    }
+    if (p >= e) return false;
+    ++p;
+    return true;
+  }
+  bool skip() {  // skip any value
+    ws();
+    if (p >= e) return false;
+    if (*p == '"') return str(nullptr);
+    if (*p == '{' || *p == '[') {
+      const char open = *p, close = open == '{' ? '}' : ']';
+      ++p;
+      ws();
+      if (p < e && *p == close) { ++p; return true; }
+      for (;;) {
+        if (open == '{') { if (!str(nullptr)) return false; ws(); if (p >= e || *p != ':') return false; ++p; }
+        if (!skip()) return false;
+        ws();
+        if (p < e && *p == ',') { ++p; continue; }
+        if (p < e && *p == close) { ++p; return true; }
+        return false;
+      }
+    }
+    while (p < e && *p != ',' && *p != '}' && *p != ']' && !isspace((unsigned char)*p)) ++p;
+    return true;
+  }
+  bool number(double* v) {
+    ws();
+    char* end = nullptr;
+    *v = strtod(p, &end);
+    if (end == p) return false;
+    p = end;
+    return true;
+  }
+  bool int_array(std::vector<int32_t>* out) {
+    ws();
+    if (p >= e || *p != '[') return false;
+    ++p;
+    ws();
+    if (p < e && *p == ']') { ++p; return true; }
+    for (;;) {
+      double v;
+      if (!number(&v)) return false;
+      out->push_back((int32_t)v);
+      ws();
+      if (p < e && *p == ',') { ++p; continue; }
+      if (p < e && *p == ']') { ++p; return true; }
+      return false;
+    }
+  }
+};
+
+void parse_content(J& j, std::string* text) {  // string or [{type:text,text:..},..]
+  j.ws();
+  if (j.p < j.e && *j.p == '"') { std::string s; if (j.str(&s)) *text += s; return; }
+  if (j.p < j.e && *j.p == '[') {
+    ++j.p;
+    for (;;) {
+      j.ws();
+      if (j.p < j.e && *j.p == ']') { ++j.p; return; }
+      if (j.p < j.e && *j.p == '{') {
+        ++j.p;
+        for (;;) {
+          std::string k;
+          j.ws();
+          if (j.p < j.e && *j.p == '}') { ++j.p; break; }
+          if (!j.str(&k)) return;
+          j.ws(); if (j.p < j.e && *j.p == ':') ++j.p;
+          if (k == "text") { std::string s; if (j.str(&s)) *text += s; } else if (!j.skip()) return;
+          j.ws(); if (j.p < j.e && *j.p == ',') ++j.p;
+        }
+      } else if (!j.skip()) return;
+      j.ws(); if (j.p < j.e && *j.p == ',') ++j.p;
+    }
+  }
+  j.skip();
+}
+
+void parse_messages(J& j, std::string* text) {
+  j.ws();
+  if (j.p >= j.e || *j.p != '[') { j.skip(); return; }
+  ++j.p;
+  for (;;) {
+    j.ws();
+    if (j.p < j.e && *j.p == ']') { ++j.p; return; }
+    if (j.p >= j.e || *j.p != '{') return;
+    ++j.p;
+    for (;;) {
+      j.ws();
+      if (j.p < j.e && *j.p == '}') { ++j.p; break; }
+      std::string k;
+      if (!j.str(&k)) return;
+      j.ws(); if (j.p < j.e && *j.p == ':') ++j.p;
+      if (k == "content") { parse_content(j, text); text->push_back('\n'); }
+      else if (!j.skip()) return;
+      j.ws(); if (j.p < j.e && *j.p == ',') ++j.p;
+    }
+    j.ws(); if (j.p < j.e && *j.p == ',') ++j.p;
+  }
+}
+}  // namespace
+
+bool parse_body(const std::string& body, int endpoint, ParsedBody* out) {
+  (void)endpoint;
+  J j{body.data(), body.data() + body.size()};
+  j.ws();
+  if (j.p >= j.e || *j.p != '{') return false;
+  ++j.p;
+  for (;;) {
+    j.ws();
+    if (j.p < j.e && *j.p == '}') return true;
+    std::string k;
+    if (!j.str(&k)) return false;
+    j.ws();
+    if (j.p >= j.e || *j.p != ':') return false;
+    ++j.p;
+    j.ws();
+    if (k == "model") { if (!j.str(&out->model)) return false; }
+    else if (k == "prompt") {
+      if (j.p < j.e && *j.p == '[') { if (!j.int_array(&out->tokens)) return false; }
+      else if (!j.str(&out->text)) { if (!j.skip()) return false; }
+    }
+    else if (k == "context") { if (!j.int_array(&out->tokens)) return false; }
+    else if (k == "messages") parse_messages(j, &out->text);
+    else if (k == "stream") {
+      out->has_stream = true;
+      if (j.lit("true")) out->stream = true; else if (j.lit("false")) out->stream = false; else if (!j.skip()) return false;
+    }
+    else if (k == "max_tokens" || k == "max_completion_tokens" || k == "num_predict") {
+      double v; if (!j.number(&v)) { if (!j.skip()) return false; } else out->num_predict = (int)v;
+    }
+    else if (k == "options") {
+      j.ws();
+      if (j.p < j.e && *j.p == '{') {
+        ++j.p;
+        for (;;) {
+          j.ws();
+          if (j.p < j.e && *j.p == '}') { ++j.p; break; }
+          std::string ok;
+          if (!j.str(&ok)) return false;
+          j.ws(); if (j.p < j.e && *j.p == ':') ++j.p;
+          if (ok == "num_predict") { double v; if (j.number(&v)) out->num_predict = (int)v; else if (!j.skip()) return false; }
+          else if (!j.skip()) return false;
+          j.ws(); if (j.p < j.e && *j.p == ',') ++j.p;
+        }
+      } else if (!j.skip()) return false;
+    }
+    else if (!j.skip()) return false;
+    j.ws();
+    if (j.p < j.e && *j.p == ',') ++j.p;
+  }
+}
+
+// deterministic byte-level tokenizer: random-init weights have no vocabulary
+std::vector<int32_t> byte_tokenize(const std::string& text, int vocab) {
+  std::vector<int32_t> t;
+  t.reserve(text.size());
+  for (unsigned char c : text) t.push_back((int32_t)(c % (unsigned)vocab));
+  return t;
+}
+
+std::string token_text(int tok) {
+  char b[24];
+  snprintf(b, sizeof(b), " t%d", tok);
+  return b;
+}
+
+const char* content_type_for(int endpoint, int stream) {
+  if (endpoint == MQ_EP_RAW_TOKENS) return "application/octet-stream";
+  if (!stream) return "application/json";
+  return (endpoint == MQ_EP_V1_CHAT || endpoint == MQ_EP_V1_COMPLETIONS) ? "text/event-stream" : "application/x-ndjson";
+}
+
+static std::string json_escape(const std::string& s) {
+  std::string o;
+  for (unsigned char c : s) {
+    if (c == '"' || c == '\\') { o.push_back('\\'); o.push_back((char)c); }
+    else if (c < 0x20) { char b[8]; snprintf(b, sizeof(b), "\\u%04x", c); o += b; }
+    else o.push_back((char)c);
+  }
+  return o;
+}
+
+static std::string now_iso() {
+  char b[40];
+  time_t t = time(nullptr);
+  struct tm tmv;
+  gmtime_r(&t, &tmv);
+  strftime(b, sizeof(b), "%Y-%m-%dT%H:%M:%SZ", &tmv);
+  return b;
+}
+
+std::string frame_token(int endpoint, const char* model, int tok) {
+  const std::string m = json_escape(model), txt = json_escape(token_text(tok));
+  char buf[512];
+  switch (endpoint) {
+    case MQ_EP_API_GENERATE:
+      snprintf(buf, sizeof(buf), "{\"model\":\"%s\",\"created_at\":\"%s\",\"response\":\"%s\",\"done\":false}\n",
+               m.c_str(), now_iso().c_str(), txt.c_str());
+      break;
+    case MQ_EP_API_CHAT:
+      snprintf(buf, sizeof(buf),
+               "{\"model\":\"%s\",\"created_at\":\"%s\",\"message\":{\"role\":\"assistant\",\"content\":\"%s\"},\"done\":false}\n",
+               m.c_str(), now_iso().c_str(), txt.c_str());
+      break;
+    case MQ_EP_V1_CHAT:
+      snprintf(buf, sizeof(buf),
+               "data: {\"id\":\"chatcmpl-mq\",\"object\":\"chat.completion.chunk\",\"created\":%ld,\"model\":\"%s\","
+               "\"choices\":[{\"index\":0,\"delta\":{\"content\":\"%s\"},\"finish_reason\":null}]}\n\n",
+               (long)time(nullptr), m.c_str(), txt.c_str());
+      break;
+    default:
+      snprintf(buf, sizeof(buf),
+               "data: {\"id\":\"cmpl-mq\",\"object\":\"text_completion\",\"created\":%ld,\"model\":\"%s\","
+               "\"choices\":[{\"text\":\"%s\",\"index\":0,\"finish_reason\":null}]}\n\n",
+               (long)time(nullptr), m.c_str(), txt.c_str());
+  }
+  return buf;
+}
+
+std::string frame_final(int endpoint, int stream, const char* model, const std::string& agg, int n_prompt, int n_gen) {
+  if (endpoint == MQ_EP_RAW_TOKENS) return stream ? std::string() : agg;
+  const std::string m = json_escape(model), txt = json_escape(agg);
+  std::string o;
+  char buf[512];
+  if (endpoint == MQ_EP_API_GENERATE || endpoint == MQ_EP_API_CHAT) {
+    o = "{\"model\":\"" + m + "\",\"created_at\":\"" + now_iso() + "\",";
+    if (endpoint == MQ_EP_API_GENERATE) o += "\"response\":\"" + (stream ? std::string() : txt) + "\",";
+    else o += "\"message\":{\"role\":\"assistant\",\"content\":\"" + (stream ? std::string() : txt) + "\"},";
+    snprintf(buf, sizeof(buf), "\"done\":true,\"done_reason\":\"length\",\"prompt_eval_count\":%d,\"eval_count\":%d}\n",
+             n_prompt, n_gen);
+    return o + buf;
+  }
+  const bool chat = endpoint == MQ_EP_V1_CHAT;
+  if (stream) {
+    snprintf(buf, sizeof(buf),
+             chat ? "data: {\"id\":\"chatcmpl-mq\",\"object\":\"chat.completion.chunk\",\"created\":%ld,\"model\":\"%s\","
+                    "\"choices\":[{\"index\":0,\"delta\":{},\"finish_reason\":\"length\"}]}\n\ndata: [DONE]\n\n"
+                  : "data: {\"id\":\"cmpl-mq\",\"object\":\"text_completion\",\"created\":%ld,\"model\":\"%s\","
+                    "\"choices\":[{\"text\":\"\",\"index\":0,\"finish_reason\":\"length\"}]}\n\ndata: [DONE]\n\n",
+             (long)time(nullptr), m.c_str());
+    return buf;
+  }
+  snprintf(buf, sizeof(buf), "\"usage\":{\"prompt_tokens\":%d,\"completion_tokens\":%d,\"total_tokens\":%d}}", n_prompt,
+           n_gen, n_prompt + n_gen);
+  if (chat)
+    o = "{\"id\":\"chatcmpl-mq\",\"object\":\"chat.completion\",\"model\":\"" + m +
+        "\",\"choices\":[{\"index\":0,\"message\":{\"role\":\"assistant\",\"content\":\"" + txt +
+        "\"},\"finish_reason\":\"length\"}],";
+  else
+    o = "{\"id\":\"cmpl-mq\",\"object\":\"text_completion\",\"model\":\"" + m + "\",\"choices\":[{\"text\":\"" + txt +
+        "\",\"index\":0,\"finish_reason\":\"length\"}],";
+  return o + buf;
+}
+
+}  // namespace mq

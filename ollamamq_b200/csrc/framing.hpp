@@ -1,0 +1,28 @@
+// Request-body parsing and response framing for the endpoints the worker terminates.
+// The reference relays opaque bytes (dispatcher.rs:287-312), so these formats follow the public Ollama /
+// OpenAI wire shapes seen in the reference's own client script (test_dispatcher.sh:37-39,69,93) and README.
+// Parity here is UNPINNED by the reference (SURVEY.md 7 "hard parts").
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace mq {
+
+struct ParsedBody {
+  std::string model;
+  std::string text;             // prompt / concatenated message contents
+  std::vector<int32_t> tokens;  // "context": [ids] (Ollama /api/generate) or "prompt": [ids] (OpenAI completions)
+  bool has_stream = false;
+  bool stream = true;
+  int num_predict = 0;          // options.num_predict | max_tokens | max_completion_tokens
+};
+
+bool parse_body(const std::string& body, int endpoint, ParsedBody* out);
+std::vector<int32_t> byte_tokenize(const std::string& text, int vocab);
+std::string token_text(int tok);
+const char* content_type_for(int endpoint, int stream);
+std::string frame_token(int endpoint, const char* model, int tok);
+std::string frame_final(int endpoint, int stream, const char* model, const std::string& agg, int n_prompt, int n_gen);
+
+}  // namespace mq

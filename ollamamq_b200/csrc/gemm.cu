@@ -37,12 +37,7 @@ template <int BN, int EPI>
 static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid,
                               const LaunchCfg& lc) {
   constexpr int smem = gemm_smem_bytes(BN, EPI);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_wx_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
+  // dynamic-smem opt-in happens once per device in gemm_set_attrs() (never inside a graph capture)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kGemmThreads);
@@ -79,6 +74,22 @@ cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
   }
 }
 
+template <int EPI>
+static void set_attrs_epi() {
+  cudaFuncSetAttribute(gemm_wx_kernel<16, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(16, EPI));
+  cudaFuncSetAttribute(gemm_wx_kernel<32, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(32, EPI));
+  cudaFuncSetAttribute(gemm_wx_kernel<64, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(64, EPI));
+  cudaFuncSetAttribute(gemm_wx_kernel<128, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI));
+  cudaFuncSetAttribute(gemm_wx_kernel<256, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI));
+}
+// Opt every instantiation into its dynamic shared memory size up front (per device), so nothing but
+// launches happens while a decode step is being captured into a CUDA graph.
+void gemm_set_attrs() {
+  set_attrs_epi<EPI_F32>();
+  set_attrs_epi<EPI_BF16>();
+  set_attrs_epi<EPI_SILU_BF16>();
+}
+
 int gemm_pick_bn(int T) {
   if (T <= 16) return 16;
   if (T <= 32) return 32;
@@ -91,7 +102,9 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
                int epi, void* out, int ldo, int splits, long long split_stride, int a2_row_off) {
   if (K % kBlockK != 0) return false;
   const int kb = K / kBlockK;
-  if (splits < 1 || kb % splits != 0) return false;
+  if (splits < 1) return false;
+  const int kbps = (kb + splits - 1) / splits;  // uneven split-K: the last plane may get fewer k-blocks
+  if ((splits - 1) * kbps >= kb) return false;   // but never zero
   g->bn = gemm_pick_bn(T);
   g->epi = epi;
   g->splits = splits;
@@ -103,7 +116,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   g->p.T = T;
   g->p.n_out = n_out;
   g->p.k_blocks = kb;
-  g->p.kb_per_split = kb / splits;
+  g->p.kb_per_split = kbps;
   g->p.a2_row_off = a2_row_off;
   return true;
 }

@@ -27,5 +27,6 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
                int epi, void* out, int ldo, int splits, long long split_stride, int a2_row_off);
 
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc);
+void gemm_set_attrs();
 
 }  // namespace mq

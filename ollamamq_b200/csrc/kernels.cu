@@ -436,14 +436,14 @@ __global__ void __launch_bounds__(128) attn_combine_kernel(const AttnParams p) {
   p.out[((size_t)tok * p.n_q + head) * D + d] = __float2bfloat16(L > 0.f ? acc / L : 0.f);
 }
 
+void attn_set_attrs() {
+  constexpr int NW = kPrefillTileRows / 16, TN = 64;
+  cudaFuncSetAttribute(paged_attn_kernel<NW, TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (NW * 16 + 4 * TN) * kHeadDim * 2);
+}
 void launch_attn_prefill(const LaunchCfg& lc, const AttnParams& p, int n_tiles) {
   constexpr int NW = kPrefillTileRows / 16, TN = 64;
   constexpr int smem = (NW * 16 + 4 * TN) * kHeadDim * 2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(paged_attn_kernel<NW, TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_set = true;
-  }
   launch_k(lc, paged_attn_kernel<NW, TN, false>, dim3(n_tiles, p.n_kv, 1), dim3(NW * 32), smem, p);
 }
 void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots) {

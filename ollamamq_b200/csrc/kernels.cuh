@@ -59,6 +59,7 @@ struct AttnParams {
 };
 void launch_attn_prefill(const LaunchCfg& lc, const AttnParams& p, int n_tiles);
 void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots);
+void attn_set_attrs();
 constexpr int kPrefillTileRows = 64;  // q rows (token x group-head) per prefill CTA
 
 // next[b] = argmax_v logits[b][v]; optional: cur_token[slot]=next, pos[slot]+=1 for active slots

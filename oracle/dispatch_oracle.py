@@ -161,7 +161,7 @@ class OracleC:
 
 
 def simulate(orc, arrivals: List[Tuple[int, Optional[str]]], service_time: Callable[[str, int, int], int],
-             vip=None, boost=None, outcomes=None, events=None) -> List[Tuple[str, int, int]]:
+             vip=None, boost=None, outcomes=None, events=None, on_complete=None) -> List[Tuple[str, int, int]]:
     """Event model of SURVEY.md 3.2, restated independently of the product harness.
 
     A completion = {user counter++, backend freed} atomically (dispatcher.rs:314-341 has no .await between
@@ -215,6 +215,8 @@ def simulate(orc, arrivals: List[Tuple[int, Optional[str]]], service_time: Calla
             x = min(due, key=lambda y: (y[1], y[2]))
             inflight.remove(x)
             orc.complete(x[1], x[3], 0 if outcomes is None else outcomes(x[3], x[4]))
+            if on_complete is not None:
+                on_complete(t, x[1], x[3], x[4])
             run()
         if ta == t:
             while ai < len(pend) and arrivals[pend[ai]][0] == t:
