@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the hot path (BASELINE.json: tokens/sec whole box + p50 TTFT, 64 users,
+Llama-3-8B, 1/2/4/8 B200).
+
+    python bench.py --gpus N --steps K --warmup W              # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path on the host cores
+
+One "step" = one pass of the hot path over the whole synthetic trace: 64 users x (512-token prompt + 128 greedy
+tokens), all arriving at t=0, dispatched by the fair-share scheduler and executed by the on-box GPU workers.
+
+Printed JSON (rank 0, one line):
+  value     whole-job tokens/s from DEVICE time: sum of the CUDA-event durations of every prefill pass and decode
+            step of the timed steps (token ids are already in HBM when each event pair starts), max over ranks
+  e2e       the same metric end to end through the public API (Dispatcher.submit -> C ABI, HOST token buffers,
+            H2D of every prompt and D2H of every generated token inside the timed region), barrier-bracketed
+            wall clock, max over ranks; also p50/p95 TTFT
+  roofline  the decode step (one CUDA-graph launch): algorithmic bytes / CUDA-event time vs the
+            measured HBM peak; plus prefill tensor-pipe numbers
+  cpu_baseline  the oracle port of the forward pass on this box's host cores, bounded sample (rank 0, N=1 only)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+USERS = 64
+PROMPT_LEN = 512
+GEN_LEN = 128
+METRIC = "tokens/sec whole box + p50 TTFT, 64 users, Llama-3-8B"
+UNIT = "tokens/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+def prompts():
+    import numpy as np
+    from oracle.llama_ref import LLAMA3_8B
+    return [np.random.default_rng(u).integers(0, LLAMA3_8B["vocab"], PROMPT_LEN).astype("int32").tolist()
+            for u in range(USERS)]
+
+
+def shard_users(n_backends: int):
+    """Partition of the 64 users over the workers = the reference's own backend pick (least connections,
+    round-robin tie-break; dispatcher.rs:247-254) on the t=0 arrival trace.  Every rank computes it alone."""
+    import ollamamq_b200 as mq
+    s = mq.Scheduler(n_backends, capacity=USERS)
+    for u in range(USERS):
+        s.enqueue("user%02d" % u)
+    out = [[] for _ in range(n_backends)]
+    for d in s.drain():
+        out[d.backend].append(int(d.user[4:]))
+    return out
+
+
+class ClockSampler:
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(suffix=".csv")
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        # "under load": upper half of the samples (idle samples between steps drag the median down)
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ollamamq_b200 as mq
+    from oracle.llama_ref import LLAMA3_8B
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        log("warning: WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
+    n = max(world, 1)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    my_users = shard_users(n)[rank]
+    P = prompts()
+    pdl = int(os.environ.get("MQ_PDL", "1"))
+    graphs = int(os.environ.get("MQ_GRAPHS", "1"))
+    cfg = mq.model_cfg(LLAMA3_8B, max_batch=USERS, max_seq=PROMPT_LEN + GEN_LEN + 16,
+                       max_prefill_tokens=int(os.environ.get("MQ_PREFILL_TOKENS", "2048")), use_graphs=graphs,
+                       use_pdl=pdl, model_name="llama-3-8b-random-init")
+    t0 = time.time()
+    wk = mq.Worker(local, cfg)
+    wk.init_random(seed=0, std=0.02)
+    wk.set_timing(True)
+    disp = mq.Dispatcher([wk], capacity=USERS)
+    log("[rank %d] worker up in %.1fs, %d users" % (rank, time.time() - t0, len(my_users)))
+
+    def one_step():
+        streams = []
+        t_start = time.perf_counter()
+        for u in my_users:
+            streams.append(disp.submit("user%02d" % u, prompt_tokens=P[u], max_new_tokens=GEN_LEN, stream=1))
+        for s in streams:
+            s.wait(600)
+        t_end = time.perf_counter()
+        ttft = []
+        ntok = 0
+        for s in streams:
+            if s.rc != 0:
+                raise RuntimeError("request failed: rc=%s %s" % (s.rc, s.err))
+            ntok += len(s.body) // 4
+            ttft.append(s.chunk_times[0] - t_start)
+        return t_end - t_start, ntok, ttft
+
+    for _ in range(args.warmup):
+        one_step()
+    barrier()
+    wk.reset_stats()
+    sampler = ClockSampler(local) if rank == 0 else None
+    wall, toks, ttfts = 0.0, 0, []
+    barrier()
+    t_all0 = time.perf_counter()
+    for _ in range(args.steps):
+        barrier()
+        dt, ntok, tt = one_step()
+        barrier()
+        wall += allmax(dt)
+        toks += ntok
+        ttfts += tt
+    t_all = time.perf_counter() - t_all0
+    clocks = sampler.stop() if sampler else None
+    st = wk.stats()
+    dev_ms = st["decode_ms"] + st["prefill_ms"]
+    dev_ms_max = allmax(dev_ms)
+    toks_all = allsum(toks)
+    launches = allsum(st["kernel_launches"])
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, ttfts)
+        ttfts = [x for g in gathered for x in g]
+    ttfts.sort()
+    pk = peaks()
+    # roofline of the decode step on this rank (rank 0 reports its own)
+    dec_steps = max(1, st["decode_steps"])
+    dec_gbs = st["decode_bytes"] / (st["decode_ms"] * 1e-3) / 1e9 if st["decode_ms"] > 0 else 0.0
+    # prefill flops: 2*P_mm*T + causal attention
+    g = LLAMA3_8B
+    p_mm = g["n_layers"] * ((g["n_q_heads"] + 2 * g["n_kv_heads"]) * 128 * g["hidden"] + g["hidden"] * g["hidden"]
+                            + 3 * g["ffn"] * g["hidden"]) + g["vocab"] * g["hidden"]
+    per_prompt = 2.0 * (p_mm - g["vocab"] * g["hidden"]) * PROMPT_LEN + 2.0 * g["vocab"] * g["hidden"] \
+        + g["n_layers"] * 4.0 * PROMPT_LEN * PROMPT_LEN * g["n_q_heads"] * 128 / 2
+    prefill_tf = per_prompt * len(my_users) * args.steps / (st["prefill_ms"] * 1e-3) / 1e12 if st["prefill_ms"] > 0 else 0.0
+    bytes_h2d = sum(len(P[u]) for u in my_users) * 4
+    bytes_d2h = len(my_users) * GEN_LEN * 4
+    line = {
+        "metric": METRIC, "value": toks_all / (dev_ms_max * 1e-3), "unit": UNIT, "n_gpus": n, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic (random-init weights, uniform random token ids)",
+        "config": {"workload": "BASELINE configs[1]: Llama-3-8B bf16, 64 concurrent users, 512-token prompt / "
+                               "128-token greedy decode, token stream per request",
+                   "users": USERS, "prompt_len": PROMPT_LEN, "gen_len": GEN_LEN,
+                   "parallelism": "%d independent workers (replicated weights), users sharded by the reference "
+                                  "backend pick, no collective on the data path" % n,
+                   "l2": "inputs larger than L2: 15 GB of weights + the KV cache stream through HBM every decode step",
+                   "pdl": pdl, "cuda_graphs": graphs, "prefill_tokens_per_pass": cfg.max_prefill_tokens},
+        "e2e": {"value": toks_all / wall, "unit": UNIT, "h2d_bytes_per_step": bytes_h2d * n,
+                "d2h_bytes_per_step": bytes_d2h * n, "ms_per_step": wall / args.steps * 1e3,
+                "ttft_p50_ms": ttfts[len(ttfts) // 2] * 1e3, "ttft_p95_ms": ttfts[int(len(ttfts) * 0.95)] * 1e3},
+        "ttft_p50_ms": ttfts[len(ttfts) // 2] * 1e3,
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "decode step (1 CUDA graph launch = 292 kernels; tcgen05 weight-streaming "
+                                               "GEMMs + paged-KV attention)",
+                     "achieved": dec_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dec_gbs / pk["hbm_gbs"],
+                     "peak_src": pk["src"], "traffic": None,
+                     "decode_ms_per_step": st["decode_ms"] / dec_steps,
+                     "decode_bytes_per_step": st["decode_bytes"] / dec_steps,
+                     "prefill": {"bound": "tensor", "achieved": prefill_tf, "peak": pk["tf_sustained"],
+                                 "unit": "TFLOP/s", "frac": prefill_tf / pk["tf_sustained"],
+                                 "prefill_ms_per_step": st["prefill_ms"] / args.steps}},
+        "clocks": clocks,
+        "wall_s_timed_region": t_all,
+    }
+    disp.close()
+    wk.close()
+    if rank == 0 and n == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def _fast_cpu_weights(cfg):
+    """bf16 weights for a TIMING run: values do not matter, so tile one random block instead of drawing 8e9
+    normals (same shapes / bytes as make_weights)."""
+    import torch
+    from oracle.llama_ref import tensor_shapes
+    blk = (torch.randn(1 << 22) * 0.02).to(torch.bfloat16)
+    w = {}
+    for name, shape in tensor_shapes(cfg).items():
+        n = 1
+        for s in shape:
+            n *= s
+        if name.endswith("norm"):
+            w[name] = torch.ones(shape, dtype=torch.bfloat16)
+        else:
+            reps = (n + blk.numel() - 1) // blk.numel()
+            w[name] = blk.repeat(reps)[:n].view(shape).contiguous()
+    return w
+
+
+_CPU_W = None
+
+
+def cpu_reference_step(n_users=1, gen=8):
+    """The reference path on the host cores: the dispatch oracle in front of the CPU port of the forward pass,
+    reference semantics (one in-flight request per backend, one backend).  Bounded sample: n_users requests of
+    512 prompt tokens + `gen` greedy tokens, served one after the other."""
+    import torch
+    from oracle.dispatch_oracle import OraclePy, simulate
+    from oracle.llama_ref import LLAMA3_8B, forward
+    global _CPU_W
+    if _CPU_W is None:
+        _CPU_W = _fast_cpu_weights(LLAMA3_8B)
+    P = prompts()
+    order = simulate(OraclePy(1), [(0, "user%02d" % u) for u in range(n_users)], lambda u, s, b: 1)
+    t0 = time.perf_counter()
+    ttft = []
+    ntok = 0
+    for user, _, _ in order:
+        u = int(user[4:])
+        kv = []
+        logits = forward(_CPU_W, LLAMA3_8B, P[u], torch.bfloat16, 0, kv)
+        tok = int(logits[-1].float().argmax())
+        ttft.append(time.perf_counter() - t0)
+        ntok += 1
+        for i in range(gen - 1):
+            logits = forward(_CPU_W, LLAMA3_8B, [tok], torch.bfloat16, PROMPT_LEN + i, kv)
+            tok = int(logits[-1].float().argmax())
+            ntok += 1
+    return time.perf_counter() - t0, ntok, ttft
+
+
+def cpu_baseline_sample():
+    import torch
+    t0 = time.time()
+    dt, ntok, ttft = cpu_reference_step(1, 8)
+    if dt < 8:
+        dt2, ntok2, ttft2 = cpu_reference_step(2, 8)
+        dt, ntok, ttft = dt2, ntok2, ttft2
+    return {"value": ntok / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "%d request(s) x (512-token prompt + 8 greedy tokens), Llama-3-8B bf16 via the torch CPU port "
+                      "(oracle/llama_ref.py) behind the dispatch oracle, capacity 1 like the reference; %.1fs incl. "
+                      "weight setup" % (len(ttft), time.time() - t0),
+            "ttft_first_request_ms": ttft[0] * 1e3}
+
+
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(1, 4)
+    tot_t, tot_tok, ttfts = 0.0, 0, []
+    for _ in range(args.steps):
+        dt, ntok, tt = cpu_reference_step(2, 8)
+        tot_t += dt
+        tot_tok += ntok
+        ttfts += tt
+    v = tot_tok / tot_t
+    sample = ("each step: 2 requests x (512-token prompt + 8 greedy tokens) of the 64-user trace, served one at a "
+              "time (reference capacity 1); Llama-3-8B bf16 torch CPU port (oracle/llama_ref.py) behind the dispatch "
+              "oracle; the reference itself (Rust + Ollama/llama.cpp) cannot be built or installed in this image")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1] (bounded sample): Llama-3-8B bf16, 512-token prompt, greedy decode",
+                       "users": USERS, "prompt_len": PROMPT_LEN, "gen_len": GEN_LEN},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                    "ttft_first_request_ms": ttfts[0] * 1e3},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -153,14 +153,15 @@ class Worker:
         check(lib.mq_debug_forward(self._h, arr, n, 1 if all_positions else 0, out.ctypes.data_as(C.c_void_p)))
         return out
 
-    def submit(self, stream: Stream, **kw) -> Stream:
+    def submit(self, sink: Stream, **kw) -> Stream:
+        """kw: endpoint, prompt_tokens, body, max_new_tokens, stream (1/0/-1), timeout_ms."""
         r, keep = make_request(**kw)
         h = C.c_void_p()
-        stream.t_submit = time.perf_counter()
-        check(lib.mq_submit(self._h, C.byref(r), C.byref(stream.cb), None, C.byref(h)))
-        stream.handle = h
-        stream._worker = self
-        return stream
+        sink.t_submit = time.perf_counter()
+        check(lib.mq_submit(self._h, C.byref(r), C.byref(sink.cb), None, C.byref(h)))
+        sink.handle = h
+        sink._worker = self
+        return sink
 
     def generate(self, prompt_tokens: Sequence[int], max_new_tokens: int, timeout=120) -> List[int]:
         s = self.submit(Stream(), prompt_tokens=list(prompt_tokens), max_new_tokens=max_new_tokens)
@@ -202,17 +203,17 @@ class Dispatcher:
             lib.mq_dispatcher_free(self._h)
             self._h = None
 
-    def submit(self, user: Optional[str], stream: Optional[Stream] = None, ip: Optional[str] = None, **kw) -> Stream:
-        stream = stream or Stream()
+    def submit(self, user: Optional[str], sink: Optional[Stream] = None, ip: Optional[str] = None, **kw) -> Stream:
+        sink = sink or Stream()
         r, keep = make_request(**kw)
         tid = C.c_uint64()
-        stream.t_submit = time.perf_counter()
+        sink.t_submit = time.perf_counter()
         check(lib.mq_dispatcher_submit(self._h, None if user is None else user.encode(),
-                                       None if ip is None else ip.encode(), C.byref(r), C.byref(stream.cb), None,
+                                       None if ip is None else ip.encode(), C.byref(r), C.byref(sink.cb), None,
                                        C.byref(tid)))
-        stream.task_id = tid.value
-        self._streams.append(stream)
-        return stream
+        sink.task_id = tid.value
+        self._streams.append(sink)
+        return sink
 
     def set_vip(self, user):
         check(lib.mq_dispatcher_set_vip(self._h, None if user is None else user.encode()))

@@ -118,7 +118,7 @@ def test_client_disconnect_paths():
         # (a) mid-stream: the chunk send fails -> relay stops, dropped++ (:305-308,:318-319)
         got = []
         s = mq.Stream(on_chunk=lambda b: (got.append(b), False)[1])
-        d.submit("alice", stream=s, max_new_tokens=5)
+        d.submit("alice", sink=s, max_new_tokens=5)
         d.wait_parked()
         assert d.mock_complete(0)
         s.wait(5)
