@@ -263,18 +263,19 @@ def run_ours(args):
 
 # ------------------------------------------------------------------------------------------------ CPU arm
 def _fast_cpu_weights(cfg):
-    """bf16 weights for a TIMING run: values do not matter, so tile one random block instead of drawing 8e9
-    normals (same shapes / bytes as make_weights)."""
+    """Weights for a TIMING run of the CPU port: values do not matter, so tile one random block instead of drawing
+    8e9 normals.  Stored as fp32: torch's CPU bf16 GEMV path is ~20x slower than its fp32 path on this Xeon
+    (measured 2.5 s/token vs 0.2 s/token), and the baseline should be the CPU's best foot forward."""
     import torch
     from oracle.llama_ref import tensor_shapes
-    blk = (torch.randn(1 << 22) * 0.02).to(torch.bfloat16)
+    blk = torch.randn(1 << 22) * 0.02
     w = {}
     for name, shape in tensor_shapes(cfg).items():
         n = 1
         for s in shape:
             n *= s
         if name.endswith("norm"):
-            w[name] = torch.ones(shape, dtype=torch.bfloat16)
+            w[name] = torch.ones(shape, dtype=torch.float32)
         else:
             reps = (n + blk.numel() - 1) // blk.numel()
             w[name] = blk.repeat(reps)[:n].view(shape).contiguous()
@@ -302,12 +303,12 @@ def cpu_reference_step(n_users=1, gen=8):
     for user, _, _ in order:
         u = int(user[4:])
         kv = []
-        logits = forward(_CPU_W, LLAMA3_8B, P[u], torch.bfloat16, 0, kv)
+        logits = forward(_CPU_W, LLAMA3_8B, P[u], torch.float32, 0, kv)
         tok = int(logits[-1].float().argmax())
         ttft.append(time.perf_counter() - t0)
         ntok += 1
         for i in range(gen - 1):
-            logits = forward(_CPU_W, LLAMA3_8B, [tok], torch.bfloat16, PROMPT_LEN + i, kv)
+            logits = forward(_CPU_W, LLAMA3_8B, [tok], torch.float32, PROMPT_LEN + i, kv)
             tok = int(logits[-1].float().argmax())
             ntok += 1
     return time.perf_counter() - t0, ntok, ttft
@@ -321,9 +322,9 @@ def cpu_baseline_sample():
         dt2, ntok2, ttft2 = cpu_reference_step(2, 8)
         dt, ntok, ttft = dt2, ntok2, ttft2
     return {"value": ntok / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d request(s) x (512-token prompt + 8 greedy tokens), Llama-3-8B bf16 via the torch CPU port "
-                      "(oracle/llama_ref.py) behind the dispatch oracle, capacity 1 like the reference; %.1fs incl. "
-                      "weight setup" % (len(ttft), time.time() - t0),
+            "sample": "%d request(s) x (512-token prompt + 8 greedy tokens), Llama-3-8B (fp32 math on the CPU) via the "
+                      "torch CPU port (oracle/llama_ref.py) behind the dispatch oracle, capacity 1 like the reference; "
+                      "%.1fs incl. weight setup" % (len(ttft), time.time() - t0),
             "ttft_first_request_ms": ttft[0] * 1e3}
 
 
@@ -342,11 +343,11 @@ def run_reference(args):
         ttfts += tt
     v = tot_tok / tot_t
     sample = ("each step: 2 requests x (512-token prompt + 8 greedy tokens) of the 64-user trace, served one at a "
-              "time (reference capacity 1); Llama-3-8B bf16 torch CPU port (oracle/llama_ref.py) behind the dispatch "
+              "time (reference capacity 1); Llama-3-8B torch CPU port, fp32 math (oracle/llama_ref.py) behind the dispatch "
               "oracle; the reference itself (Rust + Ollama/llama.cpp) cannot be built or installed in this image")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "BASELINE configs[1] (bounded sample): Llama-3-8B bf16, 512-token prompt, greedy decode",
                        "users": USERS, "prompt_len": PROMPT_LEN, "gen_len": GEN_LEN},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
