@@ -156,7 +156,7 @@ def run_ours(args):
     pdl = int(os.environ.get("MQ_PDL", "1"))
     graphs = int(os.environ.get("MQ_GRAPHS", "1"))
     cfg = mq.model_cfg(LLAMA3_8B, max_batch=USERS, max_seq=PROMPT_LEN + GEN_LEN + 16,
-                       max_prefill_tokens=int(os.environ.get("MQ_PREFILL_TOKENS", "2048")), use_graphs=graphs,
+                       max_prefill_tokens=int(os.environ.get("MQ_PREFILL_TOKENS", "9472")), use_graphs=graphs,
                        use_pdl=pdl, model_name="llama-3-8b-random-init")
     t0 = time.time()
     wk = mq.Worker(local, cfg)
@@ -238,8 +238,8 @@ def run_ours(args):
                 "ttft_p50_ms": ttfts[len(ttfts) // 2] * 1e3, "ttft_p95_ms": ttfts[int(len(ttfts) * 0.95)] * 1e3},
         "ttft_p50_ms": ttfts[len(ttfts) // 2] * 1e3,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "decode step (1 CUDA graph launch = 292 kernels; tcgen05 weight-streaming "
-                                               "GEMMs + paged-KV attention)",
+        "roofline": {"bound": "hbm", "kernel": "decode step (1 CUDA graph launch = %d kernels; tcgen05 weight-streaming "
+                                               "GEMMs + paged-KV attention)" % (1 + 32 * 8 + 3),
                      "achieved": dec_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dec_gbs / pk["hbm_gbs"],
                      "peak_src": pk["src"], "traffic": None,
                      "decode_ms_per_step": st["decode_ms"] / dec_steps,

@@ -245,8 +245,8 @@ int mq_debug_attn_prefill(const void* q, const void* k_cache, const void* v_cach
                           int max_pages, const int* tiles, int n_tiles, void* out, int n_q, int n_kv, int T,
                           float scale);
 int mq_debug_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* block_table,
-                         int max_pages, const int* pos, void* out, float* part_o, float* part_ml, int n_q, int n_kv,
-                         int n_slots, int n_splits, int kv_chunk, float scale);
+                         int max_pages, const int* pos, void* out, float* part_o, float* part_ml, int* split_counter,
+                         int n_q, int n_kv, int n_slots, int n_splits, float scale);
 int mq_debug_argmax(const float* logits, int rows, int V, int ldl, int* out_tokens, const int* dst_slot,
                     int* cur_token, int* pos_inc, const int* active);
 int mq_debug_init_normal(void* w, unsigned long long n, unsigned long long seed, float std);

@@ -93,7 +93,7 @@ int mq_debug_attn_prefill(const void* q, const void* k_cache, const void* v_cach
   AttnParams p = {};
   p.q = (const __nv_bfloat16*)q; p.k_cache = (const __nv_bfloat16*)k_cache; p.v_cache = (const __nv_bfloat16*)v_cache;
   p.block_table = block_table; p.max_pages = max_pages; p.tiles = (const int4*)tiles; p.out = (__nv_bfloat16*)out;
-  p.n_q = n_q; p.n_kv = n_kv; p.T = T; p.n_splits = 1; p.kv_chunk = 1 << 30;
+  p.n_q = n_q; p.n_kv = n_kv; p.T = T; p.n_splits = 1;
   p.scale_log2 = scale * 1.4426950408889634f;
   attn_set_attrs();
   launch_attn_prefill(LaunchCfg{0, false}, p, n_tiles);
@@ -101,13 +101,13 @@ int mq_debug_attn_prefill(const void* q, const void* k_cache, const void* v_cach
 }
 
 int mq_debug_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* block_table,
-                         int max_pages, const int* pos, void* out, float* part_o, float* part_ml, int n_q, int n_kv,
-                         int n_slots, int n_splits, int kv_chunk, float scale) {
+                         int max_pages, const int* pos, void* out, float* part_o, float* part_ml, int* split_counter,
+                         int n_q, int n_kv, int n_slots, int n_splits, float scale) {
   AttnParams p = {};
   p.q = (const __nv_bfloat16*)q; p.k_cache = (const __nv_bfloat16*)k_cache; p.v_cache = (const __nv_bfloat16*)v_cache;
   p.block_table = block_table; p.max_pages = max_pages; p.pos = pos; p.out = (__nv_bfloat16*)out;
-  p.part_o = part_o; p.part_ml = part_ml; p.n_q = n_q; p.n_kv = n_kv; p.T = n_slots; p.n_splits = n_splits;
-  p.kv_chunk = kv_chunk; p.scale_log2 = scale * 1.4426950408889634f;
+  p.part_o = part_o; p.part_ml = part_ml; p.split_counter = split_counter; p.n_q = n_q; p.n_kv = n_kv; p.T = n_slots;
+  p.n_splits = n_splits; p.scale_log2 = scale * 1.4426950408889634f;
   launch_attn_decode(LaunchCfg{0, false}, p, n_slots);
   return check_cuda("mq_debug_attn_decode");
 }

@@ -12,7 +12,6 @@ constexpr int kRing = 16;        // output-token ring (decode steps / prefill pa
 constexpr int kStageSlots = 32;  // metadata staging ring
 constexpr int kMaxFlightsDecode = 4;
 constexpr int kMaxFlightsPrefill = 2;
-constexpr int kDecodeKvChunk = 256;  // tokens per split-KV CTA
 
 #define CUDA_TRY(expr)                                                                   \
   do {                                                                                   \
@@ -115,9 +114,10 @@ static int worker_alloc(mq_worker* w) {
   if ((rc = dalloc(&tmp, proj_bytes))) return rc;
   w->proj_part = tmp;
   if ((rc = dalloc(&w->logits, (size_t)MBp * V))) return rc;
-  const int max_splits = (c.max_seq + kDecodeKvChunk - 1) / kDecodeKvChunk;
-  if ((rc = dalloc(&w->part_o, (size_t)max_splits * MBp * c.n_q_heads * D))) return rc;
-  if ((rc = dalloc(&w->part_ml, (size_t)max_splits * MBp * c.n_q_heads * 2))) return rc;
+  if ((rc = dalloc(&w->part_o, (size_t)kMaxDecodeSplits * MBp * c.n_q_heads * D))) return rc;
+  if ((rc = dalloc(&w->part_ml, (size_t)kMaxDecodeSplits * MBp * c.n_q_heads * 2))) return rc;
+  if ((rc = dalloc(&w->d_split_counter, (size_t)MBp * c.n_kv_heads))) return rc;
+  CUDA_TRY(cudaMemsetAsync(w->d_split_counter, 0, (size_t)MBp * c.n_kv_heads * 4, w->stream));
   if ((rc = dalloc(&w->inv_freq, D / 2))) return rc;
   if ((rc = dalloc(&w->d_tok, MT))) return rc;
   if ((rc = dalloc(&w->d_pos_tok, MT))) return rc;
@@ -263,8 +263,8 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
     ap.q = w->q; ap.k_cache = rp.k_cache; ap.v_cache = rp.v_cache; ap.block_table = w->d_block_table;
     ap.max_pages = w->max_pages; ap.tiles = w->d_tiles; ap.pos = a.pos; ap.out = w->attn; ap.part_o = w->part_o;
     ap.part_ml = w->part_ml; ap.n_q = c.n_q_heads; ap.n_kv = c.n_kv_heads; ap.T = a.T; ap.n_splits = a.n_splits;
-    ap.kv_chunk = kDecodeKvChunk; ap.scale_log2 = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
-    if (a.decode) { launch_attn_decode(lc, ap, a.T); nl += 2; }
+    ap.split_counter = w->d_split_counter; ap.scale_log2 = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
+    if (a.decode) { launch_attn_decode(lc, ap, a.T); ++nl; }
     else { launch_attn_prefill(lc, ap, a.n_tiles); ++nl; }
     if (gemm_launch(pp->o[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, pp->s_o, (long long)MBp * H, lw.mlp_norm, w->x, nullptr, a.T, H,
@@ -538,7 +538,9 @@ static int launch_decode(mq_worker* w) {
     }
   if (hi < 0) return MQ_OK;
   const int Bcap = std::min(MBp, round_up(hi + 1, 16));
-  const int n_splits = (max_ctx + kDecodeKvChunk - 1) / kDecodeKvChunk;
+  // split-KV count: fill the GPU with one wave of single-warp CTAs, keep >= 64 tokens per split
+  int n_splits = attn_decode_resident_ctas() / (Bcap * w->cfg.n_kv_heads);
+  n_splits = std::max(1, std::min({n_splits, kMaxDecodeSplits, std::max(1, max_ctx / 64)}));
   upload_slots(w);
 
   mq_worker::Flight f;
@@ -584,7 +586,7 @@ static int launch_decode(mq_worker* w) {
     // graph wrote to the fixed row kRing-1; move it to this step's ring slot on the host side copy
     cudaMemcpyAsync(w->h_out_ring + (size_t)ring * MBp, w->d_out_ring + (size_t)(kRing - 1) * MBp, Bcap * 4,
                     cudaMemcpyDeviceToHost, w->stream);
-    nl = (uint64_t)(1 + w->cfg.n_layers * 9 + 3);
+    nl = (uint64_t)(1 + w->cfg.n_layers * 8 + 3);
   } else {
     int rc = decode_body(w, Bcap, n_splits, ring, &nl);
     if (rc) return rc;
@@ -715,6 +717,8 @@ static void sweep_cancels(mq_worker* w) {
 
 static void worker_main(mq_worker* w) {
   cudaSetDevice(w->gpu);
+  Clock::time_point last_arrival = Clock::now(), window_start = last_arrival;
+  bool in_window = false;
   for (;;) {
     // ---- intake
     {
@@ -724,6 +728,7 @@ static void worker_main(mq_worker* w) {
       if (idle && w->inbox.empty() && w->jobs.empty() && !w->stop)
         w->cv.wait_for(lk, std::chrono::milliseconds(50));
       if (w->stop) break;
+      if (!w->inbox.empty()) last_arrival = Clock::now();
       while (!w->inbox.empty()) { w->waiting.push_back(w->inbox.front()); w->inbox.pop_front(); }
       if (idle && !w->jobs.empty()) {
         auto job = std::move(w->jobs.front());
@@ -741,6 +746,20 @@ static void worker_main(mq_worker* w) {
       w->prefilling.push_back(w->waiting.front());
       w->waiting.pop_front();
     }
+    // Batching window: a burst of arrivals on an idle GPU (64 users hitting "send" together) is prefilled as
+    // full passes instead of a lone first prompt.  Wait while requests keep arriving <200 us apart, 2 ms at most.
+    if (!w->prefilling.empty() && w->flights.empty()) {
+      const auto now = Clock::now();
+      if (!in_window) { in_window = true; window_start = now; }
+      int queued_tokens = 0;
+      for (mq_req* r : w->prefilling) queued_tokens += (int)r->prompt.size() - r->n_prefilled;
+      if (queued_tokens < w->cfg.max_prefill_tokens && now - last_arrival < std::chrono::microseconds(200) &&
+          now - window_start < std::chrono::milliseconds(2)) {
+        std::this_thread::sleep_for(std::chrono::microseconds(30));
+        continue;
+      }
+    }
+    in_window = false;
     bool launched = false;
     int n_prefill_flights = 0, n_decode_flights = 0;
     for (auto& f : w->flights) (f.decode ? n_decode_flights : n_prefill_flights)++;
@@ -953,7 +972,7 @@ void mq_worker_close(mq_worker* w) {
   void* bufs[] = {w->k_cache, w->v_cache, w->h, w->x, w->q, w->attn, w->act, w->x_last, w->qkv_part, w->proj_part,
                   w->logits, w->part_o, w->part_ml, w->inv_freq, w->d_tok, w->d_pos_tok, w->d_slot_tok, w->d_last_idx,
                   w->d_dst_slot, w->d_tiles, w->d_cur_token, w->d_pos, w->d_active, w->d_block_table, w->d_identity,
-                  w->d_out_ring};
+                  w->d_out_ring, w->d_split_counter};
   for (void* b : bufs) if (b) cudaFree(b);
   void* pinned[] = {w->h_pos, w->h_active, w->h_block_table, w->h_stage, w->h_out_ring};
   for (void* b : pinned) if (b) cudaFreeHost(b);

@@ -86,6 +86,7 @@ struct mq_worker {
   int4* d_tiles = nullptr;
   int *d_cur_token = nullptr, *d_pos = nullptr, *d_active = nullptr, *d_block_table = nullptr, *d_identity = nullptr;
   int* d_out_ring = nullptr;  // [kRing][MB]
+  int* d_split_counter = nullptr;  // [MB][n_kv] arrival counters of the split-KV decode attention
   // pinned host mirrors / staging
   int *h_pos = nullptr, *h_active = nullptr, *h_block_table = nullptr;
   int* h_stage = nullptr;     // ring of staging areas for metadata uploads

@@ -33,9 +33,30 @@ bool tmap_encode_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
   return r == CUDA_SUCCESS;
 }
 
+// output tile map: row-major [.., T, ldo] with the feature dimension innermost; rows >= T and features >= n_out are
+// outside the tensor and therefore dropped by the TMA store
+static bool tmap_encode_out(CUtensorMap* out, void* base, int epi, int n_out, int T, int ldo, int splits,
+                            long long split_stride, int bn) {
+  auto fn = get_encode_fn();
+  if (!fn) return false;
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (epi == EPI_F32) {
+    const cuuint64_t dims[3] = {(cuuint64_t)n_out, (cuuint64_t)T, (cuuint64_t)splits};
+    const cuuint64_t strides[2] = {(cuuint64_t)ldo * 4, (cuuint64_t)(splits > 1 ? split_stride : (long long)T * ldo) * 4};
+    const cuuint32_t box[3] = {(cuuint32_t)kBlockM, (cuuint32_t)bn, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)n_out, (cuuint64_t)T};
+  const cuuint64_t strides[1] = {(cuuint64_t)ldo * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kBlockM, (cuuint32_t)bn};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN, int EPI>
-static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid,
-                              const LaunchCfg& lc) {
+static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmParams& p,
+                              dim3 grid, const LaunchCfg& lc) {
   constexpr int smem = gemm_smem_bytes(BN, EPI);
   // dynamic-smem opt-in happens once per device in gemm_set_attrs() (never inside a graph capture)
   cudaLaunchConfig_t cfg = {};
@@ -48,18 +69,18 @@ static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = lc.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gemm_wx_kernel<BN, EPI>, a, b, p);
+  return cudaLaunchKernelEx(&cfg, gemm_wx_kernel<BN, EPI>, a, b, c, p);
 }
 
 template <int EPI>
-static cudaError_t launch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, dim3 grid,
-                             const LaunchCfg& lc) {
+static cudaError_t launch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                             const GemmParams& p, dim3 grid, const LaunchCfg& lc) {
   switch (bn) {
-    case 16: return launch_one<16, EPI>(a, b, p, grid, lc);
-    case 32: return launch_one<32, EPI>(a, b, p, grid, lc);
-    case 64: return launch_one<64, EPI>(a, b, p, grid, lc);
-    case 128: return launch_one<128, EPI>(a, b, p, grid, lc);
-    case 256: return launch_one<256, EPI>(a, b, p, grid, lc);
+    case 16: return launch_one<16, EPI>(a, b, c, p, grid, lc);
+    case 32: return launch_one<32, EPI>(a, b, c, p, grid, lc);
+    case 64: return launch_one<64, EPI>(a, b, c, p, grid, lc);
+    case 128: return launch_one<128, EPI>(a, b, c, p, grid, lc);
+    case 256: return launch_one<256, EPI>(a, b, c, p, grid, lc);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -67,9 +88,9 @@ static cudaError_t launch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b,
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
   dim3 grid((g.p.n_out + kBlockM - 1) / kBlockM, (g.p.T + g.bn - 1) / g.bn, g.splits);
   switch (g.epi) {
-    case EPI_F32: return launch_bn<EPI_F32>(g.bn, g.tmA, g.tmB, g.p, grid, lc);
-    case EPI_BF16: return launch_bn<EPI_BF16>(g.bn, g.tmA, g.tmB, g.p, grid, lc);
-    case EPI_SILU_BF16: return launch_bn<EPI_SILU_BF16>(g.bn, g.tmA, g.tmB, g.p, grid, lc);
+    case EPI_F32: return launch_bn<EPI_F32>(g.bn, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
+    case EPI_BF16: return launch_bn<EPI_BF16>(g.bn, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
+    case EPI_SILU_BF16: return launch_bn<EPI_SILU_BF16>(g.bn, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -110,6 +131,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   g->splits = splits;
   if (!tmap_encode_2d(&g->tmA, W, (uint64_t)w_rows, (uint64_t)K, kBlockM)) return false;
   if (!tmap_encode_2d(&g->tmB, X, (uint64_t)x_rows_alloc, (uint64_t)K, (uint32_t)g->bn)) return false;
+  if (!tmap_encode_out(&g->tmC, out, epi, n_out, T, ldo, splits, split_stride, g->bn)) return false;
   g->p.out = out;
   g->p.split_stride = split_stride;
   g->p.ldo = ldo;

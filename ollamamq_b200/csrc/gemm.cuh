@@ -12,7 +12,7 @@
 //   * prefill (T = thousands of prompt tokens): BN = 256 tiles, tensor-pipe bound.
 //
 // Pipeline per CTA (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..5 = epilogue (TMEM -> registers -> global).  Weight tiles of the first ring pass are requested
+// warps 2..5 = epilogue (TMEM -> registers -> smem tile -> one TMA tensor store).  Weight tiles of the first ring pass are requested
 // BEFORE griddepcontrol.wait, so under programmatic dependent launch the HBM stream of this GEMM starts
 // while the previous kernel is still draining.
 #pragma once
@@ -28,7 +28,7 @@ enum GemmEpilogue : int {
 };
 
 struct GemmParams {
-  void* out;
+  void* out;               // (kept for reference; the epilogue writes through the tmC tensor map)
   long long split_stride;  // elements between split-K planes of `out`
   int ldo;                 // leading dimension of out (elements)
   int T;                   // valid rows of X
@@ -50,6 +50,9 @@ __host__ __device__ constexpr int gemm_stages(int bn, int epi) {
   int s = (200 * 1024) / gemm_stage_bytes(bn, epi);
   return s > 8 ? 8 : s;
 }
+__host__ __device__ constexpr int gemm_out_tile_bytes(int bn, int epi) {
+  return bn * kBlockM * (epi == EPI_F32 ? 4 : 2);  // epilogue staging tile [BN tokens][128 features]
+}
 __host__ __device__ constexpr int gemm_smem_bytes(int bn, int epi) {
   return gemm_stages(bn, epi) * gemm_stage_bytes(bn, epi) + 1024 /*align*/ + 256 /*barriers*/;
 }
@@ -61,7 +64,7 @@ __host__ __device__ constexpr uint32_t gemm_tmem_cols(int bn, int epi) {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   constexpr bool kDual = (EPI == EPI_SILU_BF16);
   constexpr int STAGES = gemm_stages(BN, EPI);
   constexpr int STAGE_BYTES = gemm_stage_bytes(BN, EPI);
@@ -70,6 +73,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr uint32_t IDESC = umma_idesc_bf16(kBlockM, BN);
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N for M=128");
   static_assert(!kDual || BN * 2 <= 512, "dual accumulator must fit TMEM");
+  static_assert(gemm_out_tile_bytes(BN, EPI) <= STAGES * STAGE_BYTES, "epilogue tile is staged in the pipeline smem");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -88,6 +92,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -151,48 +156,51 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ---------------- epilogue: TMEM lane = output feature, TMEM column = token ----------------
+    // The accumulator is transposed on its way out: each thread owns one feature (TMEM lane) and walks the
+    // token columns, writing a [token][128 features] tile into the (now idle) pipeline smem; one TMA tensor
+    // store then moves the whole tile to global memory, coalesced and clipped to the tensor bounds.
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int q = warp & 3;  // TMEM lane quarter this warp may read
-    const int f = m0 + q * 32 + lane;
+    const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const bool f_ok = f < p.n_out;
+    uint8_t* stg = smem;  // every MMA has retired (tmem_full), so all stage buffers are free
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
-      if (n0 + c0 >= p.T) break;  // warp-uniform
+      if (n0 + c0 >= p.T) break;  // warp-uniform; columns past T are clipped by the store anyway
       uint32_t v[16];
       tmem_ld16(t_lane + c0, v);
       if constexpr (kDual) {
         uint32_t u[16];
         tmem_ld16(t_lane + BN + c0, u);
         tmem_ld_wait();
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out);
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(stg) + c0 * kBlockM + row;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int t = n0 + c0 + j;
           const float g = __uint_as_float(v[j]);
           const float up = __uint_as_float(u[j]);
-          const float r = g / (1.0f + __expf(-g)) * up;
-          if (f_ok && t < p.T) o[(long long)t * p.ldo + f] = __float2bfloat16(r);
+          o[j * kBlockM] = __float2bfloat16(g / (1.0f + __expf(-g)) * up);
         }
       } else {
         tmem_ld_wait();
         if constexpr (EPI == EPI_F32) {
-          float* o = reinterpret_cast<float*>(p.out) + (long long)blockIdx.z * p.split_stride;
+          float* o = reinterpret_cast<float*>(stg) + c0 * kBlockM + row;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int t = n0 + c0 + j;
-            if (f_ok && t < p.T) o[(long long)t * p.ldo + f] = __uint_as_float(v[j]);
-          }
+          for (int j = 0; j < 16; ++j) o[j * kBlockM] = __uint_as_float(v[j]);
         } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out);
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(stg) + c0 * kBlockM + row;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int t = n0 + c0 + j;
-            if (f_ok && t < p.T) o[(long long)t * p.ldo + f] = __float2bfloat16(__uint_as_float(v[j]));
-          }
+          for (int j = 0; j < 16; ++j) o[j * kBlockM] = __float2bfloat16(__uint_as_float(v[j]));
         }
       }
+    }
+    fence_proxy_async();                                   // generic-proxy smem writes -> visible to the TMA engine
+    asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps only
+    if (warp == 2 && lane == 0) {
+      if constexpr (EPI == EPI_F32) tma_store_3d(&tmC, stg, m0, n0, blockIdx.z);
+      else tma_store_2d(&tmC, stg, m0, n0);
+      tma_store_commit();
+      tma_store_wait_read();                               // smem must stay intact until the engine has read it
     }
   }
 

@@ -8,6 +8,7 @@ namespace mq {
 struct GemmPlan {
   CUtensorMap tmA;  // weights  [w_rows, K], box {64, 128}
   CUtensorMap tmB;  // activations [x_rows, K], box {64, bn}
+  CUtensorMap tmC;  // output [T, n_out] (bf16, 2-D) or [splits, T, n_out] (fp32, 3-D), box {128, bn(,1)}, no swizzle
   GemmParams p;
   int bn;
   int epi;

@@ -41,8 +41,8 @@ static void launch_k(const LaunchCfg& lc, void (*kern)(KArgs...), dim3 grid, dim
 // ------------------------------------------------------------------------------------------------
 __global__ void embed_kernel(const int* __restrict__ token_ids, const __nv_bfloat16* __restrict__ embed,
                              float* __restrict__ h, int H) {
+  pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
   pdl_wait();
-  pdl_launch_dependents();
   const int t = blockIdx.x;
   const int tok = token_ids[t];
   const uint4* src = reinterpret_cast<const uint4*>(embed + (size_t)tok * H);
@@ -64,8 +64,8 @@ template <bool F32>
 __global__ void add_rmsnorm_kernel(float* __restrict__ h, const void* __restrict__ partial, int n_planes,
                                    long long plane_stride, const __nv_bfloat16* __restrict__ gamma,
                                    __nv_bfloat16* __restrict__ x, const int* __restrict__ row_idx, int H, float eps) {
+  pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
   pdl_wait();
-  pdl_launch_dependents();
   const int row = blockIdx.x;
   const int src = row_idx ? row_idx[row] : row;
   const int nthr = blockDim.x;
@@ -119,7 +119,8 @@ void launch_add_rmsnorm(const LaunchCfg& lc, float* h, const void* partial, bool
 }
 
 // ------------------------------------------------------------------------------------------------
-// RoPE + paged KV write.  One CTA (256 threads) per token; a thread owns the rotation pair (i, i+64).
+// RoPE + paged KV write.  One CTA (256 threads) per (token, 4 heads); a thread owns the rotation pair (i, i+64).
+// (v1 used one CTA per token: 64 CTAs at decode, 30 us of pure load latency per layer — r01 launch shares.)
 // ------------------------------------------------------------------------------------------------
 template <bool F32>
 __device__ __forceinline__ float qkv_at(const RopeKvParams& p, int t, int col, int qkv_dim) {
@@ -137,24 +138,23 @@ __device__ __forceinline__ float qkv_at(const RopeKvParams& p, int t, int col, i
 
 template <bool F32>
 __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
+  pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
   pdl_wait();
-  pdl_launch_dependents();
   constexpr int D = kHeadDim, HALF = D / 2;
   const int t = blockIdx.x;
+  const int hd = blockIdx.y * 4 + (threadIdx.x >> 6);  // q heads, then k heads, then v heads
+  const int n_heads = p.n_q + 2 * p.n_kv;
+  if (hd >= n_heads) return;
   const int pos = p.pos[t];
   const int slot = p.slot_of_tok[t];
-  const int qkv_dim = (p.n_q + 2 * p.n_kv) * D;
+  const int qkv_dim = n_heads * D;
   const int i = threadIdx.x & (HALF - 1);  // pair index
-  const int hsub = threadIdx.x >> 6;       // 4 heads per pass
-  float sn, cs;
-  sincosf((float)pos * p.inv_freq[i], &sn, &cs);
-  const int page = p.block_table[(size_t)slot * p.max_pages + pos / kPageSize];
-  const int in_page = pos % kPageSize;
-  // q heads then k heads: rotate
-  for (int hd = hsub; hd < p.n_q + p.n_kv; hd += 4) {
-    const int col = hd * D + i;
-    const float a = qkv_at<F32>(p, t, col, qkv_dim);
-    const float b = qkv_at<F32>(p, t, col + HALF, qkv_dim);
+  const int col = hd * D + i;
+  const float a = qkv_at<F32>(p, t, col, qkv_dim);
+  const float b = qkv_at<F32>(p, t, col + HALF, qkv_dim);
+  if (hd < p.n_q + p.n_kv) {
+    float sn, cs;
+    sincosf((float)pos * p.inv_freq[i], &sn, &cs);
     const __nv_bfloat16 r0 = __float2bfloat16(a * cs - b * sn);
     const __nv_bfloat16 r1 = __float2bfloat16(b * cs + a * sn);
     if (hd < p.n_q) {
@@ -162,24 +162,24 @@ __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
       q[i] = r0;
       q[i + HALF] = r1;
     } else {
-      const int kvh = hd - p.n_q;
-      __nv_bfloat16* k = p.k_cache + (((size_t)page * p.n_kv + kvh) * kPageSize + in_page) * D;
+      const int page = p.block_table[(size_t)slot * p.max_pages + pos / kPageSize];
+      __nv_bfloat16* k = p.k_cache + (((size_t)page * p.n_kv + (hd - p.n_q)) * kPageSize + pos % kPageSize) * D;
       k[i] = r0;
       k[i + HALF] = r1;
     }
-  }
-  // v heads: plain copy
-  for (int e = threadIdx.x; e < p.n_kv * D; e += blockDim.x) {
-    const int kvh = e / D, d = e % D;
-    const float v = qkv_at<F32>(p, t, (p.n_q + p.n_kv) * D + e, qkv_dim);
-    p.v_cache[(((size_t)page * p.n_kv + kvh) * kPageSize + in_page) * D + d] = __float2bfloat16(v);
+  } else {
+    const int page = p.block_table[(size_t)slot * p.max_pages + pos / kPageSize];
+    __nv_bfloat16* v = p.v_cache + (((size_t)page * p.n_kv + (hd - p.n_q - p.n_kv)) * kPageSize + pos % kPageSize) * D;
+    v[i] = __float2bfloat16(a);
+    v[i + HALF] = __float2bfloat16(b);
   }
 }
 void launch_rope_kv(const LaunchCfg& lc, const RopeKvParams& p) {
+  const dim3 grid(p.T, (p.n_q + 2 * p.n_kv + 3) / 4);
   if (p.qkv_is_f32)
-    launch_k(lc, rope_kv_kernel<true>, dim3(p.T), dim3(256), 0, p);
+    launch_k(lc, rope_kv_kernel<true>, grid, dim3(256), 0, p);
   else
-    launch_k(lc, rope_kv_kernel<false>, dim3(p.T), dim3(256), 0, p);
+    launch_k(lc, rope_kv_kernel<false>, grid, dim3(256), 0, p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -215,18 +215,19 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 // so ldmatrix (8 rows x 16 B at one logical chunk column) is bank-conflict free.
 __device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return (uint32_t)(row * 16 + (chunk ^ (row & 7))) * 16u; }
 
-template <int NW, int TN, bool DECODE>
+template <int NW, int TN, int STAGES, bool DECODE>
 __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p) {
   constexpr int D = kHeadDim;
   constexpr int R = NW * 16;
   constexpr int NT = TN / 8;  // score n-tiles per kv tile
+  static_assert(TN % 16 == 0 && STAGES >= 2, "tile shape");
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* Qs = smem;
   uint8_t* Ks = Qs + R * D * 2;
-  uint8_t* Vs = Ks + 2 * TN * D * 2;
+  uint8_t* Vs = Ks + STAGES * TN * D * 2;
 
+  pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
   pdl_wait();
-  pdl_launch_dependents();
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, c = lane & 3;
@@ -241,149 +242,142 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
   }
   const int n_rows = ntok * G;
   int kv_begin = 0, kv_end = pos0 + ntok;
-  if (DECODE) {
-    kv_begin = blockIdx.z * p.kv_chunk;
-    kv_end = min(kv_end, kv_begin + p.kv_chunk);
+  const bool split = DECODE && p.n_splits > 1;
+  if (split) {
+    // every sequence is cut into n_splits equal 16-aligned ranges of ITS OWN length (balanced CTAs, and no
+    // host-side parameter that changes from step to step -> the CUDA graph stays valid as contexts grow)
+    const int chunk = (((kv_end + p.n_splits - 1) / p.n_splits) + 15) & ~15;
+    kv_begin = blockIdx.z * chunk;
+    kv_end = min(kv_end, kv_begin + chunk);
   }
   const int* btab = p.block_table + (size_t)slot * p.max_pages;
-
-  if (kv_begin >= kv_end) {  // empty split (decode only): neutral partial
-    if (DECODE) {
-      for (int r = tid; r < n_rows; r += NW * 32) {
-        const int head = kvh * G + r;
-        float* ml = p.part_ml + (((size_t)blockIdx.z * p.T + tok0) * p.n_q + head) * 2;
-        ml[0] = -INFINITY;
-        ml[1] = 0.f;
-      }
-    }
-    return;
-  }
-
-  // ---- Q tile -> smem (zero-filled beyond the valid rows)
-  for (int i = tid; i < R * 16; i += NW * 32) {
-    const int r = i >> 4, ch = i & 15;
-    const bool ok = r < n_rows;
-    const int rr = ok ? r : 0;
-    const int tok = tok0 + rr / G, head = kvh * G + rr % G;
-    cp_async16(Qs + tile_off(r, ch), p.q + ((size_t)tok * p.n_q + head) * D + ch * 8, ok ? 16 : 0);
-  }
-  auto load_kv = [&](int stage, int t0) {
-    uint8_t* kst = Ks + stage * TN * D * 2;
-    uint8_t* vst = Vs + stage * TN * D * 2;
-    for (int i = tid; i < TN * 16; i += NW * 32) {
-      const int j = i >> 4, ch = i & 15;
-      const int kvpos = t0 + j;
-      const bool ok = kvpos < kv_end;
-      const int pp = ok ? kvpos : kv_end - 1;
-      const int page = btab[pp / kPageSize];
-      const size_t off = (((size_t)page * p.n_kv + kvh) * kPageSize + pp % kPageSize) * D + ch * 8;
-      cp_async16(kst + tile_off(j, ch), p.k_cache + off, ok ? 16 : 0);
-      cp_async16(vst + tile_off(j, ch), p.v_cache + off, ok ? 16 : 0);
-    }
-  };
-  load_kv(0, kv_begin);
-  cp_async_commit();
+  const int n_tiles = kv_begin < kv_end ? (kv_end - kv_begin + TN - 1) / TN : 0;
 
   float o[16][4];
 #pragma unroll
   for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY};
   float l_run[2] = {0.f, 0.f};
-  uint32_t qf[8][4];
-
   const int row_a = warp * 16 + g, row_b = row_a + 8;
-  const int qpos_a = pos0 + row_a / G, qpos_b = pos0 + row_b / G;
-  const int n_tiles = (kv_end - kv_begin + TN - 1) / TN;
 
-  for (int it = 0; it < n_tiles; ++it) {
-    const int t0 = kv_begin + it * TN;
-    if (it + 1 < n_tiles) {
-      load_kv((it + 1) & 1, t0 + TN);
+  if (n_tiles > 0) {
+    // ---- Q tile -> smem (zero-filled beyond the valid rows)
+    for (int i = tid; i < R * 16; i += NW * 32) {
+      const int r = i >> 4, ch = i & 15;
+      const bool ok = r < n_rows;
+      const int rr = ok ? r : 0;
+      const int tok = tok0 + rr / G, head = kvh * G + rr % G;
+      cp_async16(Qs + tile_off(r, ch), p.q + ((size_t)tok * p.n_q + head) * D + ch * 8, ok ? 16 : 0);
+    }
+    auto load_kv = [&](int stage, int t0) {
+      uint8_t* kst = Ks + stage * TN * D * 2;
+      uint8_t* vst = Vs + stage * TN * D * 2;
+      for (int i = tid; i < TN * 16; i += NW * 32) {
+        const int j = i >> 4, ch = i & 15;
+        const int kvpos = t0 + j;
+        const bool ok = kvpos < kv_end;
+        const int pp = ok ? kvpos : kv_end - 1;
+        const int page = btab[pp / kPageSize];
+        const size_t off = (((size_t)page * p.n_kv + kvh) * kPageSize + pp % kPageSize) * D + ch * 8;
+        cp_async16(kst + tile_off(j, ch), p.k_cache + off, ok ? 16 : 0);
+        cp_async16(vst + tile_off(j, ch), p.v_cache + off, ok ? 16 : 0);
+      }
+    };
+    // prologue: STAGES-1 tiles in flight (one commit group per tile slot, empty groups keep the count uniform)
+#pragma unroll
+    for (int s0 = 0; s0 < STAGES - 1; ++s0) {
+      if (s0 < n_tiles) load_kv(s0, kv_begin + s0 * TN);
       cp_async_commit();
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
     }
-    __syncthreads();
-    if (it == 0) {
-      const uint32_t qbase = smem_u32(Qs);
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const int r = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
-        ldsm_x4(qbase + tile_off(r, ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
-      }
-    }
-    const uint32_t kbase = smem_u32(Ks + (it & 1) * TN * D * 2);
-    const uint32_t vbase = smem_u32(Vs + (it & 1) * TN * D * 2);
+    uint32_t qf[8][4];
+    const int qpos_a = pos0 + row_a / G, qpos_b = pos0 + row_b / G;
 
-    // ---- S = Q K^T
-    float s[NT][4];
+    for (int it = 0; it < n_tiles; ++it) {
+      const int t0 = kv_begin + it * TN;
+      if (it + STAGES - 1 < n_tiles) load_kv((it + STAGES - 1) % STAGES, t0 + (STAGES - 1) * TN);
+      cp_async_commit();
+      cp_async_wait<STAGES - 1>();
+      __syncthreads();
+      if (it == 0) {
+        const uint32_t qbase = smem_u32(Qs);
 #pragma unroll
-    for (int n2 = 0; n2 < NT / 2; ++n2) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) s[2 * n2][e] = s[2 * n2 + 1][e] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const int r = n2 * 16 + (lane & 7) + 8 * (lane >> 4);
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4(kbase + tile_off(r, ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
-        mma_bf16_16816(s[2 * n2], qf[ks], b0, b1);
-        mma_bf16_16816(s[2 * n2 + 1], qf[ks], b2, b3);
+        for (int ks = 0; ks < 8; ++ks) {
+          const int r = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+          ldsm_x4(qbase + tile_off(r, ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+        }
       }
-    }
-    // ---- mask + online softmax (rows g and g+8 of this warp's 16-row slab)
-    float mx_a = -INFINITY, mx_b = -INFINITY;
+      const uint32_t kbase = smem_u32(Ks + (it % STAGES) * TN * D * 2);
+      const uint32_t vbase = smem_u32(Vs + (it % STAGES) * TN * D * 2);
+
+      // ---- S = Q K^T
+      float s[NT][4];
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
+      for (int n2 = 0; n2 < NT / 2; ++n2) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int col = t0 + n * 8 + 2 * c + (e & 1);
-        const int qpos = (e < 2) ? qpos_a : qpos_b;
-        const bool ok = (col <= qpos) && (col < kv_end);
-        const float v = ok ? s[n][e] * p.scale_log2 : -INFINITY;
-        s[n][e] = v;
-        if (e < 2) mx_a = fmaxf(mx_a, v); else mx_b = fmaxf(mx_b, v);
+        for (int e = 0; e < 4; ++e) s[2 * n2][e] = s[2 * n2 + 1][e] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const int r = n2 * 16 + (lane & 7) + 8 * (lane >> 4);
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4(kbase + tile_off(r, ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+          mma_bf16_16816(s[2 * n2], qf[ks], b0, b1);
+          mma_bf16_16816(s[2 * n2 + 1], qf[ks], b2, b3);
+        }
       }
-    }
-    mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
-    mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
-    mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
-    mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
-    const float mn_a = fmaxf(m_run[0], mx_a), mn_b = fmaxf(m_run[1], mx_b);
-    const float mu_a = (mn_a == -INFINITY) ? 0.f : mn_a;
-    const float mu_b = (mn_b == -INFINITY) ? 0.f : mn_b;
-    const float al_a = exp2f(m_run[0] - mu_a), al_b = exp2f(m_run[1] - mu_b);
-    m_run[0] = mn_a; m_run[1] = mn_b;
-    float sum_a = 0.f, sum_b = 0.f;
+      // ---- mask + online softmax (rows g and g+8 of this warp's 16-row slab)
+      float mx_a = -INFINITY, mx_b = -INFINITY;
 #pragma unroll
-    for (int n = 0; n < NT; ++n) {
-      s[n][0] = exp2f(s[n][0] - mu_a); s[n][1] = exp2f(s[n][1] - mu_a);
-      s[n][2] = exp2f(s[n][2] - mu_b); s[n][3] = exp2f(s[n][3] - mu_b);
-      sum_a += s[n][0] + s[n][1];
-      sum_b += s[n][2] + s[n][3];
-    }
-    l_run[0] = l_run[0] * al_a + sum_a;
-    l_run[1] = l_run[1] * al_b + sum_b;
+      for (int n = 0; n < NT; ++n) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { o[i][0] *= al_a; o[i][1] *= al_a; o[i][2] *= al_b; o[i][3] *= al_b; }
-    // ---- O += P V
-#pragma unroll
-    for (int kt = 0; kt < TN / 16; ++kt) {
-      uint32_t a[4];
-      a[0] = pack_bf16(s[2 * kt][0], s[2 * kt][1]);
-      a[1] = pack_bf16(s[2 * kt][2], s[2 * kt][3]);
-      a[2] = pack_bf16(s[2 * kt + 1][0], s[2 * kt + 1][1]);
-      a[3] = pack_bf16(s[2 * kt + 1][2], s[2 * kt + 1][3]);
-#pragma unroll
-      for (int d2 = 0; d2 < 8; ++d2) {
-        const int r = kt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
-        uint32_t b0, b1, b2, b3;
-        ldsm_x4_t(vbase + tile_off(r, d2 * 2 + (lane >> 4)), b0, b1, b2, b3);
-        mma_bf16_16816(o[2 * d2], a, b0, b1);
-        mma_bf16_16816(o[2 * d2 + 1], a, b2, b3);
+        for (int e = 0; e < 4; ++e) {
+          const int col = t0 + n * 8 + 2 * c + (e & 1);
+          const int qpos = (e < 2) ? qpos_a : qpos_b;
+          const bool ok = (col <= qpos) && (col < kv_end);
+          const float v = ok ? s[n][e] * p.scale_log2 : -INFINITY;
+          s[n][e] = v;
+          if (e < 2) mx_a = fmaxf(mx_a, v); else mx_b = fmaxf(mx_b, v);
+        }
       }
+      mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1));
+      mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+      mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1));
+      mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+      const float mn_a = fmaxf(m_run[0], mx_a), mn_b = fmaxf(m_run[1], mx_b);
+      const float mu_a = (mn_a == -INFINITY) ? 0.f : mn_a;
+      const float mu_b = (mn_b == -INFINITY) ? 0.f : mn_b;
+      const float al_a = exp2f(m_run[0] - mu_a), al_b = exp2f(m_run[1] - mu_b);
+      m_run[0] = mn_a; m_run[1] = mn_b;
+      float sum_a = 0.f, sum_b = 0.f;
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        s[n][0] = exp2f(s[n][0] - mu_a); s[n][1] = exp2f(s[n][1] - mu_a);
+        s[n][2] = exp2f(s[n][2] - mu_b); s[n][3] = exp2f(s[n][3] - mu_b);
+        sum_a += s[n][0] + s[n][1];
+        sum_b += s[n][2] + s[n][3];
+      }
+      l_run[0] = l_run[0] * al_a + sum_a;
+      l_run[1] = l_run[1] * al_b + sum_b;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { o[i][0] *= al_a; o[i][1] *= al_a; o[i][2] *= al_b; o[i][3] *= al_b; }
+      // ---- O += P V
+#pragma unroll
+      for (int kt = 0; kt < TN / 16; ++kt) {
+        uint32_t a[4];
+        a[0] = pack_bf16(s[2 * kt][0], s[2 * kt][1]);
+        a[1] = pack_bf16(s[2 * kt][2], s[2 * kt][3]);
+        a[2] = pack_bf16(s[2 * kt + 1][0], s[2 * kt + 1][1]);
+        a[3] = pack_bf16(s[2 * kt + 1][2], s[2 * kt + 1][3]);
+#pragma unroll
+        for (int d2 = 0; d2 < 8; ++d2) {
+          const int r = kt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(vbase + tile_off(r, d2 * 2 + (lane >> 4)), b0, b1, b2, b3);
+          mma_bf16_16816(o[2 * d2], a, b0, b1);
+          mma_bf16_16816(o[2 * d2 + 1], a, b2, b3);
+        }
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
 
   // ---- finalize
@@ -396,7 +390,7 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
     if (row >= n_rows) continue;
     const int tok = tok0 + row / G, head = kvh * G + row % G;
     const float l = half ? l_b : l_a;
-    if (DECODE) {
+    if (split) {
       const size_t base = ((size_t)blockIdx.z * p.T + tok) * p.n_q + head;
       float* po = p.part_o + base * D;
 #pragma unroll
@@ -407,50 +401,67 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
         p.part_ml[base * 2 + 1] = l;
       }
     } else {
-      const float inv = 1.f / l;
+      const float inv = l > 0.f ? 1.f / l : 0.f;
       __nv_bfloat16* po = p.out + ((size_t)tok * p.n_q + head) * D;
 #pragma unroll
       for (int n = 0; n < 16; ++n)
         *reinterpret_cast<uint32_t*>(po + n * 8 + 2 * c) = pack_bf16(o[n][2 * half] * inv, o[n][2 * half + 1] * inv);
     }
   }
+  if constexpr (DECODE && NW == 1) {
+    if (split) {
+      // ---- in-kernel combine: the split CTA that arrives last merges all partials of this (slot, kv head)
+      __threadfence();
+      int old = 0;
+      if (lane == 0) old = atomicAdd(p.split_counter + slot * p.n_kv + kvh, 1);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old == p.n_splits - 1) {
+        __threadfence();
+        for (int hg = 0; hg < G; ++hg) {
+          const int head = kvh * G + hg;
+          float M = -INFINITY;
+          for (int sp = 0; sp < p.n_splits; ++sp)
+            M = fmaxf(M, __ldcg(p.part_ml + (((size_t)sp * p.T + slot) * p.n_q + head) * 2));
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+          float L = 0.f;
+          for (int sp = 0; sp < p.n_splits; ++sp) {
+            const size_t base = ((size_t)sp * p.T + slot) * p.n_q + head;
+            const float m = __ldcg(p.part_ml + base * 2);
+            if (m == -INFINITY) continue;
+            const float wgt = exp2f(m - M);
+            L += __ldcg(p.part_ml + base * 2 + 1) * wgt;
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(p.part_o + base * D) + lane);
+            acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
+          }
+          const float inv = L > 0.f ? 1.f / L : 0.f;
+          uint2 ov;
+          ov.x = pack_bf16(acc.x * inv, acc.y * inv);
+          ov.y = pack_bf16(acc.z * inv, acc.w * inv);
+          *reinterpret_cast<uint2*>(p.out + ((size_t)slot * p.n_q + head) * D + lane * 4) = ov;
+        }
+        if (lane == 0) p.split_counter[slot * p.n_kv + kvh] = 0;  // self-resetting for the next launch
+      }
+    }
+  }
 }
 
-// merge split-KV partials: one CTA of 128 threads per (slot, q head)
-__global__ void __launch_bounds__(128) attn_combine_kernel(const AttnParams p) {
-  pdl_wait();
-  pdl_launch_dependents();
-  constexpr int D = kHeadDim;
-  const int tok = blockIdx.x, head = blockIdx.y, d = threadIdx.x;
-  float M = -INFINITY;
-  for (int s = 0; s < p.n_splits; ++s) M = fmaxf(M, p.part_ml[(((size_t)s * p.T + tok) * p.n_q + head) * 2]);
-  float acc = 0.f, L = 0.f;
-  for (int s = 0; s < p.n_splits; ++s) {
-    const size_t base = ((size_t)s * p.T + tok) * p.n_q + head;
-    const float m = p.part_ml[base * 2];
-    if (m == -INFINITY) continue;
-    const float w = exp2f(m - M);
-    L += p.part_ml[base * 2 + 1] * w;
-    acc += p.part_o[base * D + d] * w;
-  }
-  p.out[((size_t)tok * p.n_q + head) * D + d] = __float2bfloat16(L > 0.f ? acc / L : 0.f);
-}
+constexpr int kPrefillNW = kPrefillTileRows / 16, kPrefillTN = 64, kPrefillStages = 2;
+constexpr int kDecodeTN = 16, kDecodeStages = 3;
+constexpr int attn_smem(int nw, int tn, int stages) { return (nw * 16 + 2 * stages * tn) * kHeadDim * 2; }
 
 void attn_set_attrs() {
-  constexpr int NW = kPrefillTileRows / 16, TN = 64;
-  cudaFuncSetAttribute(paged_attn_kernel<NW, TN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (NW * 16 + 4 * TN) * kHeadDim * 2);
+  cudaFuncSetAttribute(paged_attn_kernel<kPrefillNW, kPrefillTN, kPrefillStages, false>,
+                       cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem(kPrefillNW, kPrefillTN, kPrefillStages));
 }
 void launch_attn_prefill(const LaunchCfg& lc, const AttnParams& p, int n_tiles) {
-  constexpr int NW = kPrefillTileRows / 16, TN = 64;
-  constexpr int smem = (NW * 16 + 4 * TN) * kHeadDim * 2;
-  launch_k(lc, paged_attn_kernel<NW, TN, false>, dim3(n_tiles, p.n_kv, 1), dim3(NW * 32), smem, p);
+  launch_k(lc, paged_attn_kernel<kPrefillNW, kPrefillTN, kPrefillStages, false>, dim3(n_tiles, p.n_kv, 1),
+           dim3(kPrefillNW * 32), attn_smem(kPrefillNW, kPrefillTN, kPrefillStages), p);
 }
+// CTAs of the decode kernel that can be resident at once on one B200 (28 KiB smem, ~150 regs, 1 warp each)
+int attn_decode_resident_ctas() { return 148 * 8; }
 void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots) {
-  constexpr int NW = 1, TN = 32;
-  constexpr int smem = (NW * 16 + 4 * TN) * kHeadDim * 2;
-  launch_k(lc, paged_attn_kernel<NW, TN, true>, dim3(n_slots, p.n_kv, p.n_splits), dim3(NW * 32), smem, p);
-  launch_k(lc, attn_combine_kernel, dim3(n_slots, p.n_q), dim3(128), 0, p);
+  launch_k(lc, paged_attn_kernel<1, kDecodeTN, kDecodeStages, true>, dim3(n_slots, p.n_kv, p.n_splits), dim3(32),
+           attn_smem(1, kDecodeTN, kDecodeStages), p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -460,8 +471,8 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ 
                                                       int* __restrict__ out_tokens, const int* __restrict__ dst_slot,
                                                       int* __restrict__ cur_token, int* __restrict__ pos_inc,
                                                       const int* __restrict__ active) {
+  pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
   pdl_wait();
-  pdl_launch_dependents();
   const int row = blockIdx.x;
   const float4* lp = reinterpret_cast<const float4*>(logits + (size_t)row * ldl);
   float best = -INFINITY;

@@ -53,13 +53,15 @@ struct AttnParams {
   float* part_o;       // decode split partials [splits][T][n_q][d]
   float* part_ml;      // [splits][T][n_q][2]
   int n_q, n_kv, T;
-  int n_splits;        // decode only
-  int kv_chunk;        // tokens per split (decode)
+  int n_splits;        // decode only: every sequence is cut into n_splits equal 16-aligned ranges
+  int* split_counter;  // decode only: [slots][n_kv] arrival counters (zero between launches)
   float scale_log2;    // softmax scale * log2(e)
 };
 void launch_attn_prefill(const LaunchCfg& lc, const AttnParams& p, int n_tiles);
 void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots);
 void attn_set_attrs();
+int attn_decode_resident_ctas();
+constexpr int kMaxDecodeSplits = 8;
 constexpr int kPrefillTileRows = 64;  // q rows (token x group-head) per prefill CTA
 
 // next[b] = argmax_v logits[b][v]; optional: cur_token[slot]=next, pos[slot]+=1 for active slots

@@ -259,31 +259,33 @@ def test_attn_prefill(n_q, n_kv):
         r0 += L
 
 
-@pytest.mark.parametrize("n_q,n_kv,n_splits,chunk", [(32, 8, 4, 256), (32, 8, 1, 4096), (28, 4, 3, 64)])
-def test_attn_decode(n_q, n_kv, n_splits, chunk):
+@pytest.mark.parametrize("n_q,n_kv,n_splits", [(32, 8, 4), (32, 8, 1), (28, 4, 3), (32, 8, 8), (32, 8, 2)])
+def test_attn_decode(n_q, n_kv, n_splits):
     m = _lib()
-    n_slots, max_pages = 6, 48
+    n_slots, max_pages = 7, 48
     bt, kc, vc = _make_cache(n_slots, max_pages, n_kv, seed=2)
     kc = torch.randn_like(kc.float()).bfloat16()
     vc = torch.randn_like(vc.float()).bfloat16()
     bt, kc, vc = bt.to(dev()), kc.to(dev()), vc.to(dev())
-    pos_list = [0, 15, 16, 575, 100, 31]
-    if chunk * n_splits < max(pos_list) + 1:
-        pos_list = [min(p, chunk * n_splits - 1) for p in pos_list]
+    pos_list = [0, 15, 16, 575, 100, 31, 639]   # ctx 1 (most splits empty), page edges, long
     pos = torch.tensor(pos_list, dtype=torch.int32, device=dev())
     q = torch.randn(n_slots, n_q, D, device=dev()).bfloat16()
     out = torch.zeros(n_slots, n_q, D, device=dev(), dtype=torch.bfloat16)
     part_o = torch.full((n_splits, n_slots, n_q, D), float("nan"), device=dev())
     part_ml = torch.full((n_splits, n_slots, n_q, 2), float("nan"), device=dev())
-    rc = m.lib.mq_debug_attn_decode(P(q), P(kc), P(vc), P(bt), max_pages, P(pos), P(out), P(part_o), P(part_ml), n_q,
-                                    n_kv, n_slots, n_splits, chunk, 1.0 / math.sqrt(D))
-    assert rc == 0, m.last_error()
-    for s in range(n_slots):
-        L = int(pos[s]) + 1
-        k, v = _gather_kv(kc, vc, bt[s], L)
-        ref = _attn_ref(q[s:s + 1].float(), k, v, torch.tensor([L - 1], device=dev()))
-        err = _relerr(out[s:s + 1], ref)
-        assert err < 1e-2, f"slot {s} (ctx {L}): rel err {err}"
+    counter = torch.zeros(n_slots * n_kv, dtype=torch.int32, device=dev())
+    for rep in range(2):  # second launch checks the arrival counters reset themselves
+        out.zero_()
+        rc = m.lib.mq_debug_attn_decode(P(q), P(kc), P(vc), P(bt), max_pages, P(pos), P(out), P(part_o), P(part_ml),
+                                        P(counter), n_q, n_kv, n_slots, n_splits, 1.0 / math.sqrt(D))
+        assert rc == 0, m.last_error()
+        assert int(counter.abs().sum()) == 0
+        for s in range(n_slots):
+            L = int(pos[s]) + 1
+            k, v = _gather_kv(kc, vc, bt[s], L)
+            ref = _attn_ref(q[s:s + 1].float(), k, v, torch.tensor([L - 1], device=dev()))
+            err = _relerr(out[s:s + 1], ref)
+            assert err < 1e-2, f"rep {rep} slot {s} (ctx {L}): rel err {err}"
 
 
 def test_argmax_and_advance():

@@ -21,7 +21,7 @@ users = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 gen = int(sys.argv[2]) if len(sys.argv) > 2 else 6
 pdl = int(os.environ.get("MQ_PDL", "1"))
 P = [np.random.default_rng(u).integers(0, LLAMA3_8B["vocab"], 512).astype("int32").tolist() for u in range(users)]
-wk = mq.Worker(0, mq.model_cfg(LLAMA3_8B, max_batch=64, max_seq=512 + 128 + 16, max_prefill_tokens=2048, use_graphs=1,
+wk = mq.Worker(0, mq.model_cfg(LLAMA3_8B, max_batch=64, max_seq=512 + 128 + 16, max_prefill_tokens=int(os.environ.get("MQ_PREFILL_TOKENS", "9472")), use_graphs=1,
                                use_pdl=pdl))
 wk.init_random(0, 0.02)
 wk.set_timing(True)
