@@ -156,7 +156,7 @@ def run_ours(args):
     pdl = int(os.environ.get("MQ_PDL", "1"))
     graphs = int(os.environ.get("MQ_GRAPHS", "1"))
     cfg = mq.model_cfg(LLAMA3_8B, max_batch=USERS, max_seq=PROMPT_LEN + GEN_LEN + 16,
-                       max_prefill_tokens=int(os.environ.get("MQ_PREFILL_TOKENS", "9472")), use_graphs=graphs,
+                       max_prefill_tokens=int(os.environ.get("MQ_PREFILL_TOKENS", "4736")), use_graphs=graphs,
                        use_pdl=pdl, model_name="llama-3-8b-random-init")
     t0 = time.time()
     wk = mq.Worker(local, cfg)

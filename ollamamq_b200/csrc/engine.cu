@@ -747,14 +747,14 @@ static void worker_main(mq_worker* w) {
       w->waiting.pop_front();
     }
     // Batching window: a burst of arrivals on an idle GPU (64 users hitting "send" together) is prefilled as
-    // full passes instead of a lone first prompt.  Wait while requests keep arriving <200 us apart, 2 ms at most.
+    // full passes instead of a lone first prompt.  Wait while requests keep arriving <500 us apart, 4 ms at most.
     if (!w->prefilling.empty() && w->flights.empty()) {
       const auto now = Clock::now();
       if (!in_window) { in_window = true; window_start = now; }
       int queued_tokens = 0;
       for (mq_req* r : w->prefilling) queued_tokens += (int)r->prompt.size() - r->n_prefilled;
-      if (queued_tokens < w->cfg.max_prefill_tokens && now - last_arrival < std::chrono::microseconds(200) &&
-          now - window_start < std::chrono::milliseconds(2)) {
+      if (queued_tokens < w->cfg.max_prefill_tokens && now - last_arrival < std::chrono::microseconds(500) &&
+          now - window_start < std::chrono::milliseconds(4)) {
         std::this_thread::sleep_for(std::chrono::microseconds(30));
         continue;
       }
@@ -925,10 +925,10 @@ int mq_worker_open(int32_t gpu, const mq_model_cfg* cfg, mq_worker** out) {
   }
   const mq_model_cfg& c = *cfg;
   if (c.head_dim != kHeadDim || c.hidden % 512 != 0 || c.hidden % 64 != 0 || c.ffn % 128 != 0 ||
-      c.n_q_heads % c.n_kv_heads != 0 || kPrefillTileRows / (c.n_q_heads / c.n_kv_heads) < 1 || c.vocab % 4 != 0 ||
+      c.n_q_heads % c.n_kv_heads != 0 || c.n_q_heads / c.n_kv_heads > 8 || kPrefillTileRows / (c.n_q_heads / c.n_kv_heads) < 1 || c.vocab % 4 != 0 ||
       c.max_batch < 1 || c.max_batch > 256 || c.max_seq < 1 || c.max_prefill_tokens < 16 || c.n_layers < 1) {
     set_last_error("unsupported model geometry (need head_dim 128, hidden %% 512 == 0, ffn %% 128 == 0, "
-                   "vocab %% 4 == 0, 1 <= max_batch <= 256)");
+                   "vocab %% 4 == 0, GQA group <= 8, 1 <= max_batch <= 256)");
     return MQ_ERR_INVAL;
   }
   CUDA_TRY(cudaSetDevice(gpu));

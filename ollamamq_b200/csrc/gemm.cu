@@ -1,6 +1,7 @@
 // Host side of the tcgen05 GEMM: TMA descriptor construction + template dispatch.
 #include "gemm_host.cuh"
 #include <cudaTypedefs.h>
+#include <cstdlib>
 #include <mutex>
 
 namespace mq {
@@ -54,10 +55,10 @@ static bool tmap_encode_out(CUtensorMap* out, void* base, int epi, int n_out, in
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool DEEP>
 static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmParams& p,
                               dim3 grid, const LaunchCfg& lc) {
-  constexpr int smem = gemm_smem_bytes(BN, EPI);
+  constexpr int smem = gemm_smem_bytes(BN, EPI, DEEP);
   // dynamic-smem opt-in happens once per device in gemm_set_attrs() (never inside a graph capture)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -69,18 +70,24 @@ static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = lc.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gemm_wx_kernel<BN, EPI>, a, b, c, p);
+  return cudaLaunchKernelEx(&cfg, gemm_wx_kernel<BN, EPI, DEEP>, a, b, c, p);
 }
 
 template <int EPI>
-static cudaError_t launch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+static cudaError_t launch_bn(int bn, bool deep, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
                              const GemmParams& p, dim3 grid, const LaunchCfg& lc) {
+  if (!deep) switch (bn) {  // only the decode tile widths have a shallow variant
+      case 16: return launch_one<16, EPI, false>(a, b, c, p, grid, lc);
+      case 32: return launch_one<32, EPI, false>(a, b, c, p, grid, lc);
+      case 64: return launch_one<64, EPI, false>(a, b, c, p, grid, lc);
+      default: break;
+    }
   switch (bn) {
-    case 16: return launch_one<16, EPI>(a, b, c, p, grid, lc);
-    case 32: return launch_one<32, EPI>(a, b, c, p, grid, lc);
-    case 64: return launch_one<64, EPI>(a, b, c, p, grid, lc);
-    case 128: return launch_one<128, EPI>(a, b, c, p, grid, lc);
-    case 256: return launch_one<256, EPI>(a, b, c, p, grid, lc);
+    case 16: return launch_one<16, EPI, true>(a, b, c, p, grid, lc);
+    case 32: return launch_one<32, EPI, true>(a, b, c, p, grid, lc);
+    case 64: return launch_one<64, EPI, true>(a, b, c, p, grid, lc);
+    case 128: return launch_one<128, EPI, true>(a, b, c, p, grid, lc);
+    case 256: return launch_one<256, EPI, true>(a, b, c, p, grid, lc);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -88,20 +95,28 @@ static cudaError_t launch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b,
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
   dim3 grid((g.p.n_out + kBlockM - 1) / kBlockM, (g.p.T + g.bn - 1) / g.bn, g.splits);
   switch (g.epi) {
-    case EPI_F32: return launch_bn<EPI_F32>(g.bn, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
-    case EPI_BF16: return launch_bn<EPI_BF16>(g.bn, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
-    case EPI_SILU_BF16: return launch_bn<EPI_SILU_BF16>(g.bn, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
+    case EPI_F32: return launch_bn<EPI_F32>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
+    case EPI_BF16: return launch_bn<EPI_BF16>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
+    case EPI_SILU_BF16: return launch_bn<EPI_SILU_BF16>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
     default: return cudaErrorInvalidValue;
   }
 }
 
+template <int BN, int EPI>
+static void set_attrs_one() {
+  cudaFuncSetAttribute(gemm_wx_kernel<BN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       gemm_smem_bytes(BN, EPI, true));
+  if (BN <= 64)
+    cudaFuncSetAttribute(gemm_wx_kernel<(BN <= 64 ? BN : 64), EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         gemm_smem_bytes(BN <= 64 ? BN : 64, EPI, false));
+}
 template <int EPI>
 static void set_attrs_epi() {
-  cudaFuncSetAttribute(gemm_wx_kernel<16, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(16, EPI));
-  cudaFuncSetAttribute(gemm_wx_kernel<32, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(32, EPI));
-  cudaFuncSetAttribute(gemm_wx_kernel<64, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(64, EPI));
-  cudaFuncSetAttribute(gemm_wx_kernel<128, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI));
-  cudaFuncSetAttribute(gemm_wx_kernel<256, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI));
+  set_attrs_one<16, EPI>();
+  set_attrs_one<32, EPI>();
+  set_attrs_one<64, EPI>();
+  set_attrs_one<128, EPI>();
+  set_attrs_one<256, EPI>();
 }
 // Opt every instantiation into its dynamic shared memory size up front (per device), so nothing but
 // launches happens while a decode step is being captured into a CUDA graph.
@@ -109,6 +124,16 @@ void gemm_set_attrs() {
   set_attrs_epi<EPI_F32>();
   set_attrs_epi<EPI_BF16>();
   set_attrs_epi<EPI_SILU_BF16>();
+}
+
+// MQ_GEMM_DEEP=1 forces the deep (one CTA per SM) pipeline for decode tiles too (A/B switch for profiling)
+static bool decode_tiles_shallow() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MQ_GEMM_DEEP");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int gemm_pick_bn(int T) {
@@ -127,6 +152,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   const int kbps = (kb + splits - 1) / splits;  // uneven split-K: the last plane may get fewer k-blocks
   if ((splits - 1) * kbps >= kb) return false;   // but never zero
   g->bn = gemm_pick_bn(T);
+  g->deep = !(g->bn <= 64 && decode_tiles_shallow());
   g->epi = epi;
   g->splits = splits;
   if (!tmap_encode_2d(&g->tmA, W, (uint64_t)w_rows, (uint64_t)K, kBlockM)) return false;

@@ -46,27 +46,32 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 __host__ __device__ constexpr int gemm_stage_bytes(int bn, int epi) {
   return kATileBytes * (epi == EPI_SILU_BF16 ? 2 : 1) + bn * kBlockK * 2;
 }
-__host__ __device__ constexpr int gemm_stages(int bn, int epi) {
-  int s = (200 * 1024) / gemm_stage_bytes(bn, epi);
-  return s > 8 ? 8 : s;
+// deep = true : fill the SM (up to 8 stages / 200 KiB) - one CTA per SM, best for tensor-bound prefill tiles.
+// deep = false: decode tiles (BN <= 64) stay under ~120 KiB so that the CTA of the NEXT kernel in the PDL chain
+//               can already be resident on the same SM and stream its first weight tiles while this one drains.
+__host__ __device__ constexpr int gemm_stages(int bn, int epi, bool deep = true) {
+  int budget = 200 * 1024;
+  if (!deep && bn <= 64) budget = (epi == EPI_SILU_BF16 ? 122 : 98) * 1024;
+  int s = budget / gemm_stage_bytes(bn, epi);
+  return s > 8 ? 8 : (s < 2 ? 2 : s);
 }
 __host__ __device__ constexpr int gemm_out_tile_bytes(int bn, int epi) {
   return bn * kBlockM * (epi == EPI_F32 ? 4 : 2);  // epilogue staging tile [BN tokens][128 features]
 }
-__host__ __device__ constexpr int gemm_smem_bytes(int bn, int epi) {
-  return gemm_stages(bn, epi) * gemm_stage_bytes(bn, epi) + 1024 /*align*/ + 256 /*barriers*/;
+__host__ __device__ constexpr int gemm_smem_bytes(int bn, int epi, bool deep = true) {
+  return gemm_stages(bn, epi, deep) * gemm_stage_bytes(bn, epi) + 1024 /*align*/ + 256 /*barriers*/;
 }
 __host__ __device__ constexpr uint32_t gemm_tmem_cols(int bn, int epi) {
   int need = bn * (epi == EPI_SILU_BF16 ? 2 : 1);
   return need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool DEEP>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   constexpr bool kDual = (EPI == EPI_SILU_BF16);
-  constexpr int STAGES = gemm_stages(BN, EPI);
+  constexpr int STAGES = gemm_stages(BN, EPI, DEEP);
   constexpr int STAGE_BYTES = gemm_stage_bytes(BN, EPI);
   constexpr int B_OFF = kATileBytes * (kDual ? 2 : 1);
   constexpr uint32_t TMEM_COLS = gemm_tmem_cols(BN, EPI);

@@ -13,6 +13,7 @@ struct GemmPlan {
   int bn;
   int epi;
   int splits;
+  bool deep;  // pipeline depth variant (see gemm_stages)
 };
 
 // Encode a row-major bf16 [rows, cols] tensor with a {64, box_rows} box and the 128-byte swizzle.

@@ -445,9 +445,208 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// decode attention (one query token per sequence): one warp per (slot, kv head, kv split)
+//
+//   S   [16 x 16 tokens] = Q [16 rows: G real heads, rest zero] . K^T      mma.m16n8k16 x 16 per page
+//   O^T [128 dims x 8 heads] += V^T [128 x 16 tokens] . P^T [16 tokens x 8 heads]
+// The C fragments of S are exactly the B fragments of P^T, so the probabilities never leave registers, and the
+// transposed second product needs half the accumulators / MMAs of the row-major form.  A KV tile is one 16-token
+// page = one contiguous 4 KiB block per tensor: one block-table lookup and 16 trivially addressed cp.async per
+// lane per tile.  Masking only happens on the boundary tile.  (r01 v2 capture: the generic kernel was issue-bound
+// at 7 warps/SM, 37% issue-active, 3.5 TB/s.)
+// ------------------------------------------------------------------------------------------------
+template <int STAGES>
+__global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
+  constexpr int D = kHeadDim, TN = kPageSize;
+  static_assert(TN == 16, "a KV tile is one page");
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* Ks = smem;
+  uint8_t* Vs = smem + STAGES * TN * D * 2;
+
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const int lane = threadIdx.x;
+  const int g = lane >> 2, c = lane & 3;
+  const int slot = blockIdx.x, kvh = blockIdx.y;
+  const int G = p.n_q / p.n_kv;  // <= 8 (checked on the host)
+  const int kv_len = p.pos[slot] + 1;
+  int kv_begin = 0, kv_end = kv_len;
+  const bool split = p.n_splits > 1;
+  if (split) {
+    const int chunk = (((kv_len + p.n_splits - 1) / p.n_splits) + 15) & ~15;
+    kv_begin = blockIdx.z * chunk;
+    kv_end = min(kv_len, kv_begin + chunk);
+  }
+  const int* btab = p.block_table + (size_t)slot * p.max_pages;
+  const int n_tiles = kv_begin < kv_end ? (kv_end - kv_begin + TN - 1) / TN : 0;
+
+  float ot[8][4];  // O^T: [m-tile of 16 dims][rows g / g+8, heads 2c / 2c+1]
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ot[i][0] = ot[i][1] = ot[i][2] = ot[i][3] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;  // softmax state of head g (replicated over the quad)
+
+  if (n_tiles > 0) {
+    auto load_kv = [&](int stage, int t0) {
+      const int page = btab[t0 / kPageSize];
+      const size_t base = ((size_t)page * p.n_kv + kvh) * kPageSize * D;  // contiguous [16][128] block
+      const int valid = kv_end - t0;                                       // rows >= valid are zero-filled
+      uint8_t* kst = Ks + stage * TN * D * 2;
+      uint8_t* vst = Vs + stage * TN * D * 2;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = lane + 32 * k, j = i >> 4, ch = i & 15;
+        const int nb = j < valid ? 16 : 0;
+        cp_async16(kst + tile_off(j, ch), p.k_cache + base + (size_t)i * 8, nb);
+        cp_async16(vst + tile_off(j, ch), p.v_cache + base + (size_t)i * 8, nb);
+      }
+    };
+#pragma unroll
+    for (int s0 = 0; s0 < STAGES - 1; ++s0) {
+      if (s0 < n_tiles) load_kv(s0, kv_begin + s0 * TN);
+      cp_async_commit();
+    }
+    // Q fragments straight from global memory: row g = head g of the group (zero for g >= G), rows 8..15 zero
+    uint32_t qf[8][2];
+    {
+      const bool ok = g < G;
+      const __nv_bfloat16* qp = p.q + ((size_t)slot * p.n_q + kvh * G + (ok ? g : 0)) * D + 2 * c;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        qf[ks][0] = ok ? *reinterpret_cast<const uint32_t*>(qp + ks * 16) : 0u;
+        qf[ks][1] = ok ? *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 8) : 0u;
+      }
+    }
+    for (int it = 0; it < n_tiles; ++it) {
+      const int t0 = kv_begin + it * TN;
+      if (it + STAGES - 1 < n_tiles) load_kv((it + STAGES - 1) % STAGES, t0 + (STAGES - 1) * TN);
+      cp_async_commit();
+      cp_async_wait<STAGES - 1>();
+      __syncwarp();
+      const uint32_t kbase = smem_u32(Ks + (it % STAGES) * TN * D * 2);
+      const uint32_t vbase = smem_u32(Vs + (it % STAGES) * TN * D * 2);
+      // ---- S = Q K^T for the 16 tokens of this page
+      float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const int r = (lane & 7) + 8 * (lane >> 4);
+        uint32_t b0, b1, b2, b3;
+        ldsm_x4(kbase + tile_off(r, ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
+        const uint32_t a[4] = {qf[ks][0], 0u, qf[ks][1], 0u};
+        mma_bf16_16816(s0, a, b0, b1);
+        mma_bf16_16816(s1, a, b2, b3);
+      }
+      float v0 = s0[0] * p.scale_log2, v1 = s0[1] * p.scale_log2, v2 = s1[0] * p.scale_log2, v3 = s1[1] * p.scale_log2;
+      if (t0 + TN > kv_end) {  // boundary page (warp-uniform)
+        const int col = t0 + 2 * c;
+        if (col >= kv_end) v0 = -INFINITY;
+        if (col + 1 >= kv_end) v1 = -INFINITY;
+        if (col + 8 >= kv_end) v2 = -INFINITY;
+        if (col + 9 >= kv_end) v3 = -INFINITY;
+      }
+      float mx = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float mn = fmaxf(m_run, mx);            // finite: every tile holds at least one valid token
+      const float al = exp2f(m_run - mn);
+      m_run = mn;
+      v0 = exp2f(v0 - mn); v1 = exp2f(v1 - mn); v2 = exp2f(v2 - mn); v3 = exp2f(v3 - mn);
+      l_run = l_run * al + (v0 + v1) + (v2 + v3);   // quad-partial sum
+      // rescale O^T: this thread holds heads 2c, 2c+1; their factors live in the lanes with g == head
+      const float al_a = __shfl_sync(0xffffffffu, al, (2 * c) * 4);
+      const float al_b = __shfl_sync(0xffffffffu, al, ((2 * c + 1) & 7) * 4);
+      if (__any_sync(0xffffffffu, al != 1.f)) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ot[i][0] *= al_a; ot[i][1] *= al_b; ot[i][2] *= al_a; ot[i][3] *= al_b; }
+      }
+      // ---- O^T += V^T P^T   (B fragments = the probabilities just computed)
+      const uint32_t pb0 = pack_bf16(v0, v1), pb1 = pack_bf16(v2, v3);
+#pragma unroll
+      for (int mt = 0; mt < 8; ++mt) {
+        const int r = (lane & 7) + 8 * (lane >> 4);
+        uint32_t a[4];
+        ldsm_x4_t(vbase + tile_off(r, mt * 2 + ((lane >> 3) & 1)), a[0], a[1], a[2], a[3]);
+        mma_bf16_16816(ot[mt], a, pb0, pb1);
+      }
+      __syncwarp();
+    }
+  }
+
+  // ---- finalize: l of head g -> full row sum; this thread needs the sums of heads 2c, 2c+1
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+  const int h_a = 2 * c, h_b = 2 * c + 1;
+  const float l_a = __shfl_sync(0xffffffffu, l_run, h_a * 4), l_b = __shfl_sync(0xffffffffu, l_run, (h_b & 7) * 4);
+  if (split) {
+    if (c == 0 && g < G) {
+      const size_t base = ((size_t)blockIdx.z * p.T + slot) * p.n_q + kvh * G + g;
+      p.part_ml[base * 2] = m_run;
+      p.part_ml[base * 2 + 1] = l_run;
+    }
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int head = hh ? h_b : h_a;
+      if (head >= G) continue;
+      float* po = p.part_o + (((size_t)blockIdx.z * p.T + slot) * p.n_q + kvh * G + head) * D;
+#pragma unroll
+      for (int mt = 0; mt < 8; ++mt) {
+        po[mt * 16 + g] = ot[mt][hh];
+        po[mt * 16 + g + 8] = ot[mt][2 + hh];
+      }
+    }
+    // ---- in-kernel combine: the split that arrives last merges all partials of this (slot, kv head)
+    __threadfence();
+    int old = 0;
+    if (lane == 0) old = atomicAdd(p.split_counter + slot * p.n_kv + kvh, 1);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old == p.n_splits - 1) {
+      __threadfence();
+      for (int hg = 0; hg < G; ++hg) {
+        const int head = kvh * G + hg;
+        float M = -INFINITY;
+        for (int sp = 0; sp < p.n_splits; ++sp)
+          M = fmaxf(M, __ldcg(p.part_ml + (((size_t)sp * p.T + slot) * p.n_q + head) * 2));
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float L = 0.f;
+        for (int sp = 0; sp < p.n_splits; ++sp) {
+          const size_t base = ((size_t)sp * p.T + slot) * p.n_q + head;
+          const float m = __ldcg(p.part_ml + base * 2);
+          if (m == -INFINITY) continue;
+          const float wgt = exp2f(m - M);
+          L += __ldcg(p.part_ml + base * 2 + 1) * wgt;
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(p.part_o + base * D) + lane);
+          acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
+        }
+        const float inv = L > 0.f ? 1.f / L : 0.f;
+        uint2 ov;
+        ov.x = pack_bf16(acc.x * inv, acc.y * inv);
+        ov.y = pack_bf16(acc.z * inv, acc.w * inv);
+        *reinterpret_cast<uint2*>(p.out + ((size_t)slot * p.n_q + head) * D + lane * 4) = ov;
+      }
+      if (lane == 0) p.split_counter[slot * p.n_kv + kvh] = 0;  // self-resetting for the next launch
+    }
+  } else {
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int head = hh ? h_b : h_a;
+      if (head >= G) continue;
+      const float l = hh ? l_b : l_a;
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      __nv_bfloat16* po = p.out + ((size_t)slot * p.n_q + kvh * G + head) * D;
+#pragma unroll
+      for (int mt = 0; mt < 8; ++mt) {
+        po[mt * 16 + g] = __float2bfloat16(ot[mt][hh] * inv);
+        po[mt * 16 + g + 8] = __float2bfloat16(ot[mt][2 + hh] * inv);
+      }
+    }
+  }
+}
+
 constexpr int kPrefillNW = kPrefillTileRows / 16, kPrefillTN = 64, kPrefillStages = 2;
-constexpr int kDecodeTN = 16, kDecodeStages = 3;
+constexpr int kDecodeStages = 3;
 constexpr int attn_smem(int nw, int tn, int stages) { return (nw * 16 + 2 * stages * tn) * kHeadDim * 2; }
+constexpr int kDecodeSmem = 2 * kDecodeStages * kPageSize * kHeadDim * 2;
 
 void attn_set_attrs() {
   cudaFuncSetAttribute(paged_attn_kernel<kPrefillNW, kPrefillTN, kPrefillStages, false>,
@@ -457,11 +656,22 @@ void launch_attn_prefill(const LaunchCfg& lc, const AttnParams& p, int n_tiles) 
   launch_k(lc, paged_attn_kernel<kPrefillNW, kPrefillTN, kPrefillStages, false>, dim3(n_tiles, p.n_kv, 1),
            dim3(kPrefillNW * 32), attn_smem(kPrefillNW, kPrefillTN, kPrefillStages), p);
 }
-// CTAs of the decode kernel that can be resident at once on one B200 (28 KiB smem, ~150 regs, 1 warp each)
-int attn_decode_resident_ctas() { return 148 * 8; }
+// one-warp decode CTAs that can be resident at once on this GPU (occupancy query, cached per process)
+int attn_decode_resident_ctas() {
+  static int cached = 0;
+  if (!cached) {
+    int per_sm = 0, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_attn_kernel<kDecodeStages>, 32, kDecodeSmem) !=
+            cudaSuccess || per_sm < 1)
+      per_sm = 8;
+    cached = per_sm * sms;
+  }
+  return cached;
+}
 void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots) {
-  launch_k(lc, paged_attn_kernel<1, kDecodeTN, kDecodeStages, true>, dim3(n_slots, p.n_kv, p.n_splits), dim3(32),
-           attn_smem(1, kDecodeTN, kDecodeStages), p);
+  launch_k(lc, decode_attn_kernel<kDecodeStages>, dim3(n_slots, p.n_kv, p.n_splits), dim3(32), kDecodeSmem, p);
 }
 
 // ------------------------------------------------------------------------------------------------
