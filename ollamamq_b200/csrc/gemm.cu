@@ -1,6 +1,7 @@
 // Host side of the tcgen05 GEMM: TMA descriptor construction + template dispatch.
 #include "gemm_host.cuh"
 #include <cudaTypedefs.h>
+#include <cmath>
 #include <cstdlib>
 #include <mutex>
 
@@ -93,7 +94,7 @@ static cudaError_t launch_bn(int bn, bool deep, const CUtensorMap& a, const CUte
 }
 
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
-  dim3 grid((g.p.n_out + kBlockM - 1) / kBlockM, (g.p.T + g.bn - 1) / g.bn, g.splits);
+  dim3 grid(g.p.m_tiles * g.p.n_tiles, 1, g.splits);
   switch (g.epi) {
     case EPI_F32: return launch_bn<EPI_F32>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
     case EPI_BF16: return launch_bn<EPI_BF16>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
@@ -167,6 +168,16 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   g->p.k_blocks = kb;
   g->p.kb_per_split = kbps;
   g->p.a2_row_off = a2_row_off;
+  g->p.m_tiles = (n_out + kBlockM - 1) / kBlockM;
+  g->p.n_tiles = (T + g->bn - 1) / g->bn;
+  // super-tile height: minimise the bytes one wave of 148 CTAs must pull through L2,
+  //   group_m * (weight tile bytes) + (148 / group_m) * (activation tile bytes)
+  const double wt = (double)kBlockM * (epi == EPI_SILU_BF16 ? 2 : 1), xt = (double)g->bn;
+  int gm = (int)(sqrt(148.0 * xt / wt) + 0.5);
+  if (gm < 1) gm = 1;
+  if (gm > g->p.m_tiles) gm = g->p.m_tiles;
+  g->p.group_m = g->p.n_tiles == 1 ? g->p.m_tiles : gm;
+  g->p.w_policy = g->p.n_tiles == 1 ? kEvictFirst : kEvictNormal;  // decode streams weights exactly once
   return true;
 }
 

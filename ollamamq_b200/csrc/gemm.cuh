@@ -36,6 +36,9 @@ struct GemmParams {
   int k_blocks;            // K / 64
   int kb_per_split;        // k-blocks handled by one blockIdx.z
   int a2_row_off;          // EPI_SILU_BF16: row offset of the "up" half inside W
+  int m_tiles, n_tiles;    // tile grid; blockIdx.x = linear tile id, rasterised in groups of `group_m` weight tiles
+  int group_m;             // so that one wave of 148 CTAs touches ~group_m weight tiles x ~148/group_m token tiles
+  unsigned long long w_policy;  // L2 policy for weight tiles: stream-once (decode) vs re-used inside a wave (prefill)
 };
 
 constexpr int kGemmThreads = 192;
@@ -89,8 +92,20 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kBlockM;
-  const int n0 = blockIdx.y * BN;
+  // Grouped rasterisation.  With m-tiles fastest (r01 v1-v3) every wave of a prefill GEMM re-streamed the whole
+  // weight matrix from HBM (ncu: 8.2 GB of DRAM reads for the 0.57 GB gate/up GEMM, L2 hit rate 46 %).
+  int tile_m, tile_n;
+  {
+    const int pid = blockIdx.x;
+    const int per_group = p.group_m * p.n_tiles;
+    const int first_m = (pid / per_group) * p.group_m;
+    const int gsz = min(p.m_tiles - first_m, p.group_m);
+    const int r = pid % per_group;
+    tile_m = first_m + r % gsz;
+    tile_n = r / gsz;
+  }
+  const int m0 = tile_m * kBlockM;
+  const int n0 = tile_n * BN;
   const int kb0 = blockIdx.z * p.kb_per_split;
   const int nkb = min(p.kb_per_split, p.k_blocks - kb0);
 
@@ -121,8 +136,8 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int s = 0; s < npre; ++s) {
         uint8_t* st = smem + s * STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_2d(st, &tmA, &full_bar[s], (kb0 + s) * kBlockK, m0, kEvictFirst);
-        if (kDual) tma_load_2d(st + kATileBytes, &tmA, &full_bar[s], (kb0 + s) * kBlockK, m0 + p.a2_row_off, kEvictFirst);
+        tma_load_2d(st, &tmA, &full_bar[s], (kb0 + s) * kBlockK, m0, p.w_policy);
+        if (kDual) tma_load_2d(st + kATileBytes, &tmA, &full_bar[s], (kb0 + s) * kBlockK, m0 + p.a2_row_off, p.w_policy);
       }
       pdl_wait();  // activations are produced by the previous kernel
       for (int s = 0; s < npre; ++s)
@@ -133,8 +148,8 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + s * STAGE_BYTES;
         mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-        tma_load_2d(st, &tmA, &full_bar[s], (kb0 + kb) * kBlockK, m0, kEvictFirst);
-        if (kDual) tma_load_2d(st + kATileBytes, &tmA, &full_bar[s], (kb0 + kb) * kBlockK, m0 + p.a2_row_off, kEvictFirst);
+        tma_load_2d(st, &tmA, &full_bar[s], (kb0 + kb) * kBlockK, m0, p.w_policy);
+        if (kDual) tma_load_2d(st + kATileBytes, &tmA, &full_bar[s], (kb0 + kb) * kBlockK, m0 + p.a2_row_off, p.w_policy);
         tma_load_2d(st + B_OFF, &tmB, &full_bar[s], (kb0 + kb) * kBlockK, n0, kEvictLast);
       }
     }
