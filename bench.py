@@ -72,6 +72,14 @@ def shard_users(n_backends: int):
     return out
 
 
+def _decode_traffic():
+    """dram__bytes_read+write of one decode step from the committed ncu capture (profiles/), or None."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_decode_traffic.json")))["decode_step_dram_bytes"]
+    except Exception:
+        return None
+
+
 class ClockSampler:
     def __init__(self, gpu_index: int):
         self.path = tempfile.mktemp(suffix=".csv")
@@ -241,7 +249,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": "decode step (1 CUDA graph launch = %d kernels; tcgen05 weight-streaming "
                                                "GEMMs + paged-KV attention)" % (1 + 32 * 8 + 3),
                      "achieved": dec_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dec_gbs / pk["hbm_gbs"],
-                     "peak_src": pk["src"], "traffic": None,
+                     "peak_src": pk["src"], "traffic": _decode_traffic(),
                      "decode_ms_per_step": st["decode_ms"] / dec_steps,
                      "decode_bytes_per_step": st["decode_bytes"] / dec_steps,
                      "prefill": {"bound": "tensor", "achieved": prefill_tf, "peak": pk["tf_sustained"],
