@@ -155,3 +155,28 @@ def test_dispatcher_over_gpu_worker_least_connections():
             assert d.user_stats("alice")["processed"] == 3
         finally:
             d.close()
+
+
+def test_full_size_llama3_8b_logits_and_decode():
+    """BASELINE configs[1] at FULL size: Llama-3-8B geometry, weights random-initialised on the device by the
+    worker, read back through the C ABI so the fp32 oracle runs on the very same bf16 weights.
+    Checks (a) last-position logits of a 512-token prompt, (b) 12 greedy tokens, teacher-forced."""
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs ~60 GB of HBM")
+    cfg = R.LLAMA3_8B
+    with mq.Worker(0, mq.model_cfg(cfg, max_batch=16, max_seq=640, max_prefill_tokens=1024, use_graphs=1,
+                                   use_pdl=1)) as wk:
+        wk.init_random(seed=5, std=0.02)
+        w = {}
+        for name, shape in R.tensor_shapes(cfg).items():
+            w[name] = wk.read_tensor(name, torch.empty(shape, dtype=torch.bfloat16, device="cuda"))
+        assert abs(float(w["layers.3.wqkv"].float().std()) - 0.02) < 2e-3       # N(0, 0.02^2) as documented
+        prompt = np.random.default_rng(0).integers(0, cfg["vocab"], 512).astype("int32").tolist()
+        got = wk.forward_logits(prompt)[0]
+        ref = R.forward(w, cfg, prompt, torch.float32)[-1].cpu().numpy()
+        scale = np.abs(ref).max()
+        err = np.abs(got - ref).max()
+        assert err <= TOL * scale, (err, scale)
+        gen = wk.generate(prompt, 12)
+        assert len(gen) == 12
+        _check_greedy(w, cfg, prompt, gen)
