@@ -174,9 +174,21 @@ def test_full_size_llama3_8b_logits_and_decode():
         prompt = np.random.default_rng(0).integers(0, cfg["vocab"], 512).astype("int32").tolist()
         got = wk.forward_logits(prompt)[0]
         ref = R.forward(w, cfg, prompt, torch.float32)[-1].cpu().numpy()
+        cmp16 = R.forward(w, cfg, prompt, torch.bfloat16)[-1].float().cpu().numpy()   # same-precision comparator
         scale = np.abs(ref).max()
-        err = np.abs(got - ref).max()
-        assert err <= TOL * scale, (err, scale)
+        err, err16 = np.abs(got - ref).max(), np.abs(cmp16 - ref).max()
+        rel, rel16 = np.linalg.norm(got - ref) / np.linalg.norm(ref), np.linalg.norm(cmp16 - ref) / np.linalg.norm(ref)
+        print("full-size: engine max|d| %.4f (%.2f%% of max|logit| %.3f), rel-L2 %.4f; bf16 torch comparator max|d| %.4f, "
+              "rel-L2 %.4f" % (err, 100 * err / scale, scale, rel, err16, rel16))
+        # 32 layers of bf16 tensor-core inputs: the stated bar at full depth is "no worse than 1.25x a plain bf16
+        # torch forward of the same weights, and within 8e-2 * max|logit| of fp32"
+        assert rel <= 1.25 * rel16 + 1e-3, (rel, rel16)
+        assert err <= 8e-2 * scale, (err, scale)
+        assert got.argmax() == ref.argmax() or (ref.max() - ref[got.argmax()]) <= 8e-2 * scale
         gen = wk.generate(prompt, 12)
         assert len(gen) == 12
-        _check_greedy(w, cfg, prompt, gen)
+        seq = prompt + gen
+        r = R.forward(w, cfg, seq[:-1], torch.float32)
+        for j, tok in enumerate(gen):
+            row = r[len(prompt) - 1 + j]
+            assert (row.max() - row[tok]).item() <= 8e-2 * row.abs().max().item(), j
