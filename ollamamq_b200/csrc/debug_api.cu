@@ -29,7 +29,16 @@ int mq_debug_gemm(const void* W, int w_rows, int n_out, int K, const void* X, in
                   float* ms_out) {
   GemmPlan g;
   gemm_set_attrs();
-  if (!gemm_plan(&g, W, w_rows, n_out, K, X, x_rows_alloc, T, epi, out, ldo, splits, split_stride, a2_row_off)) {
+  // splits < 0 selects the persistent stream-K kernel (decode tile widths only); the scratch lives for the process
+  static StreamKWorkspace sk_ws;
+  const bool want_sk = splits < 0;
+  if (want_sk && !sk_ws.ws && streamk_workspace_alloc(&sk_ws) != 0) {
+    mq::set_last_error("stream-K workspace allocation failed");
+    return MQ_ERR_NOMEM;
+  }
+  if (want_sk) splits = 1;
+  if (!gemm_plan(&g, W, w_rows, n_out, K, X, x_rows_alloc, T, epi, out, ldo, splits, split_stride, a2_row_off,
+                 want_sk ? &sk_ws : nullptr)) {
     mq::set_last_error("gemm_plan failed (K%%64, splits, or cuTensorMapEncodeTiled)");
     return MQ_ERR_INVAL;
   }

@@ -158,6 +158,10 @@ static int worker_alloc(mq_worker* w) {
   CUDA_TRY(cudaMemcpyAsync(w->inv_freq, invf.data(), D / 2 * 4, cudaMemcpyHostToDevice, w->stream));
   CUDA_TRY(cudaStreamSynchronize(w->stream));
 
+  if (streamk_enabled() && streamk_workspace_alloc(&w->sk_ws) != 0) {
+    set_last_error("stream-K workspace allocation failed");
+    return MQ_ERR_NOMEM;
+  }
   w->slot_req.assign(MB, nullptr);
   w->free_pages.clear();
   for (int p = w->n_pages - 1; p >= 1; --p) w->free_pages.push_back(p);  // page 0 = scratch
@@ -173,7 +177,8 @@ static int build_plans(mq_worker* w, PassPlans* pp, int T, bool decode) {
   pp->T = T;
   pp->decode = decode;
   const int MBp = round_up(w->MB, 16);
-  if (decode) {
+  const StreamKWorkspace* sk = (decode && T <= 64 && w->sk_ws.ws) ? &w->sk_ws : nullptr;
+  if (decode && !sk) {
     pp->s_qkv = decode_splits((w->qkv_dim + 127) / 128, H / 64);
     pp->s_o = decode_splits((H + 127) / 128, qd / 64);
     pp->s_down = decode_splits((H + 127) / 128, I / 64);
@@ -187,12 +192,12 @@ static int build_plans(mq_worker* w, PassPlans* pp, int T, bool decode) {
     const LayerWeights& lw = w->layers[l];
     bool ok = true;
     ok &= gemm_plan(&pp->qkv[l], lw.wqkv, w->qkv_dim, w->qkv_dim, H, w->x, x_rows, T, epi_part, w->qkv_part,
-                    w->qkv_dim, pp->s_qkv, (long long)MBp * w->qkv_dim, 0);
+                    w->qkv_dim, pp->s_qkv, (long long)MBp * w->qkv_dim, 0, sk);
     ok &= gemm_plan(&pp->o[l], lw.wo, H, H, qd, w->attn, x_rows, T, epi_part, w->proj_part, H, pp->s_o,
-                    (long long)MBp * H, 0);
-    ok &= gemm_plan(&pp->gate_up[l], lw.w_gate_up, 2 * I, I, H, w->x, x_rows, T, EPI_SILU_BF16, w->act, I, 1, 0, I);
+                    (long long)MBp * H, 0, sk);
+    ok &= gemm_plan(&pp->gate_up[l], lw.w_gate_up, 2 * I, I, H, w->x, x_rows, T, EPI_SILU_BF16, w->act, I, 1, 0, I, sk);
     ok &= gemm_plan(&pp->down[l], lw.w_down, H, H, I, w->act, x_rows, T, epi_part, w->proj_part, H, pp->s_down,
-                    (long long)MBp * H, 0);
+                    (long long)MBp * H, 0, sk);
     if (!ok) {
       set_last_error("gemm_plan failed (layer %d, T=%d)", l, T);
       return MQ_ERR_CUDA;
@@ -216,7 +221,7 @@ static GemmPlan* get_lm_plan(mq_worker* w, int rows) {
   GemmPlan g;
   const int MBp = round_up(w->MB, 16);
   if (!gemm_plan(&g, w->lm_head, w->cfg.vocab, w->cfg.vocab, w->cfg.hidden, w->x_last, MBp, rows, EPI_F32, w->logits,
-                 w->cfg.vocab, 1, 0, 0)) {
+                 w->cfg.vocab, 1, 0, 0, (rows <= 64 && w->sk_ws.ws) ? &w->sk_ws : nullptr)) {
     set_last_error("gemm_plan(lm_head) failed");
     return nullptr;
   }
@@ -969,6 +974,7 @@ void mq_worker_close(mq_worker* w) {
   if (w->stream) cudaStreamSynchronize(w->stream);
   for (auto& kv : w->graphs) cudaGraphExecDestroy(kv.second);
   for (auto& kv : w->tensors) cudaFree(kv.second.ptr);
+  streamk_workspace_free(&w->sk_ws);
   void* bufs[] = {w->k_cache, w->v_cache, w->h, w->x, w->q, w->attn, w->act, w->x_last, w->qkv_part, w->proj_part,
                   w->logits, w->part_o, w->part_ml, w->inv_freq, w->d_tok, w->d_pos_tok, w->d_slot_tok, w->d_last_idx,
                   w->d_dst_slot, w->d_tiles, w->d_cur_token, w->d_pos, w->d_active, w->d_block_table, w->d_identity,

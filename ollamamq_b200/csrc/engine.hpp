@@ -95,6 +95,7 @@ struct mq_worker {
   int stage_next = 0;
   std::vector<cudaEvent_t> stage_ev;
 
+  mq::StreamKWorkspace sk_ws;
   std::map<int, mq::PassPlans> plans_decode, plans_prefill;
   std::map<long long, cudaGraphExec_t> graphs;  // key: Bcap * 1024 + n_splits
   std::vector<mq::GemmPlan> lm_plans_cache_dummy;

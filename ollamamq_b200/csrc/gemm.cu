@@ -93,7 +93,37 @@ static cudaError_t launch_bn(int bn, bool deep, const CUtensorMap& a, const CUte
   }
 }
 
+template <int BN, int EPI>
+static cudaError_t launch_sk(const GemmPlan& g, const LaunchCfg& lc) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g.sk.n_ctas);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = sk_smem_bytes(BN, EPI);
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lc.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, gemm_streamk_kernel<BN, EPI>, g.tmA, g.tmB, g.tmC, g.sk);
+}
+template <int EPI>
+static cudaError_t launch_sk_bn(const GemmPlan& g, const LaunchCfg& lc) {
+  switch (g.bn) {
+    case 16: return launch_sk<16, EPI>(g, lc);
+    case 32: return launch_sk<32, EPI>(g, lc);
+    case 64: return launch_sk<64, EPI>(g, lc);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
+  if (g.streamk) switch (g.epi) {
+      case EPI_F32: return launch_sk_bn<EPI_F32>(g, lc);
+      case EPI_BF16: return launch_sk_bn<EPI_BF16>(g, lc);
+      case EPI_SILU_BF16: return launch_sk_bn<EPI_SILU_BF16>(g, lc);
+      default: return cudaErrorInvalidValue;
+    }
   dim3 grid(g.p.m_tiles * g.p.n_tiles, 1, g.splits);
   switch (g.epi) {
     case EPI_F32: return launch_bn<EPI_F32>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
@@ -103,6 +133,10 @@ cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
   }
 }
 
+template <int BN, int EPI>
+static void set_attrs_sk() {
+  cudaFuncSetAttribute(gemm_streamk_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, sk_smem_bytes(BN, EPI));
+}
 template <int BN, int EPI>
 static void set_attrs_one() {
   cudaFuncSetAttribute(gemm_wx_kernel<BN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -125,6 +159,35 @@ void gemm_set_attrs() {
   set_attrs_epi<EPI_F32>();
   set_attrs_epi<EPI_BF16>();
   set_attrs_epi<EPI_SILU_BF16>();
+  set_attrs_sk<16, EPI_F32>(); set_attrs_sk<32, EPI_F32>(); set_attrs_sk<64, EPI_F32>();
+  set_attrs_sk<16, EPI_BF16>(); set_attrs_sk<32, EPI_BF16>(); set_attrs_sk<64, EPI_BF16>();
+  set_attrs_sk<16, EPI_SILU_BF16>(); set_attrs_sk<32, EPI_SILU_BF16>(); set_attrs_sk<64, EPI_SILU_BF16>();
+}
+
+bool streamk_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MQ_STREAMK");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+int streamk_workspace_alloc(StreamKWorkspace* w) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  w->n_ctas = sms;
+  const size_t ws_bytes = (size_t)sms * 2 * 64 * kBlockM * sizeof(float);  // dual planes, BN <= 64
+  if (cudaMalloc((void**)&w->ws, ws_bytes) != cudaSuccess) return -1;
+  if (cudaMalloc((void**)&w->flags, sms * sizeof(int)) != cudaSuccess) return -1;
+  if (cudaMemset(w->flags, 0, sms * sizeof(int)) != cudaSuccess) return -1;
+  return 0;
+}
+void streamk_workspace_free(StreamKWorkspace* w) {
+  if (w->ws) cudaFree(w->ws);
+  if (w->flags) cudaFree(w->flags);
+  w->ws = nullptr;
+  w->flags = nullptr;
 }
 
 // MQ_GEMM_SHALLOW=1 selects the co-residency-friendly (<=120 KiB) pipeline for decode tiles.  Measured on B200
@@ -147,9 +210,12 @@ int gemm_pick_bn(int T) {
 }
 
 bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T,
-               int epi, void* out, int ldo, int splits, long long split_stride, int a2_row_off) {
+               int epi, void* out, int ldo, int splits, long long split_stride, int a2_row_off,
+               const StreamKWorkspace* sk) {
   if (K % kBlockK != 0) return false;
   const int kb = K / kBlockK;
+  g->streamk = sk != nullptr && sk->ws != nullptr && T <= 64 && streamk_enabled();
+  if (g->streamk) splits = 1;  // the kernel finishes shared tiles itself: one complete plane
   if (splits < 1) return false;
   const int kbps = (kb + splits - 1) / splits;  // uneven split-K: the last plane may get fewer k-blocks
   if ((splits - 1) * kbps >= kb) return false;   // but never zero
@@ -178,6 +244,18 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   if (gm > g->p.m_tiles) gm = g->p.m_tiles;
   g->p.group_m = g->p.n_tiles == 1 ? g->p.m_tiles : gm;
   g->p.w_policy = g->p.n_tiles == 1 ? kEvictFirst : kEvictNormal;  // decode streams weights exactly once
+  if (g->streamk) {
+    const long long U = (long long)g->p.m_tiles * kb;
+    g->sk.T = T;
+    g->sk.n_out = n_out;
+    g->sk.k_blocks = kb;
+    g->sk.m_tiles = g->p.m_tiles;
+    g->sk.a2_row_off = a2_row_off;
+    g->sk.n_ctas = (int)(U < sk->n_ctas ? U : sk->n_ctas);  // every CTA owns >= 1 unit (the fix-up relies on it)
+    g->sk.ws = sk->ws;
+    g->sk.flags = sk->flags;
+    g->sk.w_policy = kEvictFirst;
+  }
   return true;
 }
 

@@ -85,6 +85,56 @@ def test_gemm_silu_dual(T, I, K):
     assert err < 8e-3, f"rel err {err}"
 
 
+SK_CASES = [
+    # T, n_out, K, epi
+    (64, 6144, 4096, 0),     # QKV decode shape: 48 tiles x 64 k-blocks over 148 CTAs
+    (64, 4096, 14336, 0),    # down-proj: 32 tiles x 224 k-blocks, every tile shared by ~4.6 CTAs
+    (8, 4096, 4096, 0),      # BN=16
+    (33, 1000, 512, 0),      # ragged everything
+    (1, 512, 256, 0),        # 16 units only: fewer CTAs than SMs
+    (64, 25600, 4096, 0),    # LM-head-like: 200 tiles, CTAs own whole tiles plus a head and a tail
+    (64, 4096, 4096, 1),     # bf16 output
+]
+
+
+@pytest.mark.parametrize("T,n_out,K,epi", SK_CASES)
+def test_gemm_streamk(T, n_out, K, epi):
+    """Persistent stream-K decode GEMM (splits = -1 in the test ABI): complete sums in ONE plane, and the arrival
+    counters re-arm themselves (second launch must give the same answer)."""
+    m = _lib()
+    g = torch.Generator(device="cuda").manual_seed(T * 3 + n_out)
+    W = (torch.randn(n_out, K, device=dev(), generator=g) * 0.05).bfloat16()
+    X = torch.randn(64, K, device=dev(), generator=g).bfloat16()
+    ref = X[:T].float() @ W.float().T
+    outs = []
+    for rep in range(2):
+        out = torch.full((T, n_out), float("nan"), device=dev(), dtype=torch.float32 if epi == 0 else torch.bfloat16)
+        rc = m.lib.mq_debug_gemm(P(W), n_out, n_out, K, P(X), 64, T, epi, P(out), n_out, -1, 0, 0, rep, 0, None)
+        assert rc == 0, m.last_error()
+        assert torch.isfinite(out.float()).all(), "non-finite / unwritten outputs"
+        err = _relerr(out, ref)
+        assert err < (2e-3 if epi == 0 else 6e-3), f"rep {rep}: rel err {err}"
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1]), "fixed-order fix-up must be deterministic"
+
+
+@pytest.mark.parametrize("T,I,K", [(64, 14336, 4096), (16, 256, 512), (40, 1152, 1024)])
+def test_gemm_streamk_silu_dual(T, I, K):
+    m = _lib()
+    g = torch.Generator(device="cuda").manual_seed(T + I)
+    W = (torch.randn(2 * I, K, device=dev(), generator=g) * 0.03).bfloat16()
+    X = torch.randn(64, K, device=dev(), generator=g).bfloat16()
+    gate = X[:T].float() @ W[:I].float().T
+    up = X[:T].float() @ W[I:].float().T
+    ref = torch.nn.functional.silu(gate) * up
+    for rep in range(2):
+        out = torch.full((T, I), float("nan"), device=dev(), dtype=torch.bfloat16)
+        rc = m.lib.mq_debug_gemm(P(W), 2 * I, I, K, P(X), 64, T, 2, P(out), I, -1, 0, I, 0, 0, None)
+        assert rc == 0, m.last_error()
+        assert torch.isfinite(out.float()).all()
+        assert _relerr(out, ref) < 8e-3
+
+
 def test_gemm_pdl_flag_matches():
     """Same result with the programmatic-dependent-launch attribute set."""
     m = _lib()
