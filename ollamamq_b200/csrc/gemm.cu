@@ -105,7 +105,7 @@ static cudaError_t launch_sk(const GemmPlan& g, const LaunchCfg& lc) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = lc.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gemm_streamk_kernel<BN, EPI>, g.tmA, g.tmB, g.tmC, g.sk);
+  return cudaLaunchKernelEx(&cfg, gemm_streamk_kernel<BN, EPI>, g.tmA, g.tmB, g.sk);
 }
 template <int EPI>
 static cudaError_t launch_sk_bn(const GemmPlan& g, const LaunchCfg& lc) {
@@ -246,6 +246,8 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   g->p.w_policy = g->p.n_tiles == 1 ? kEvictFirst : kEvictNormal;  // decode streams weights exactly once
   if (g->streamk) {
     const long long U = (long long)g->p.m_tiles * kb;
+    g->sk.out = out;
+    g->sk.ldo = ldo;
     g->sk.T = T;
     g->sk.n_out = n_out;
     g->sk.k_blocks = kb;

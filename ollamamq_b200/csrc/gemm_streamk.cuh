@@ -20,6 +20,8 @@
 namespace mq {
 
 struct StreamKParams {
+  void* out;       // [T][ldo] fp32 or bf16
+  int ldo;
   int T;           // valid activation rows (<= BN)
   int n_out;
   int k_blocks;    // K / 64
@@ -31,12 +33,15 @@ struct StreamKParams {
   unsigned long long w_policy;
 };
 
+// No smem staging tile here: with <= 64 token columns the finisher stores straight from registers (a warp writes
+// 32 consecutive features of one token = 128 B fp32 / 64 B bf16), which keeps the TMA ring as deep as the
+// split-K kernel's (r01: a 6-stage ring + staged store made every stream-K launch ~7 us slower than split-K).
 __host__ __device__ constexpr int sk_stages(int bn, int epi) {
-  int s = (200 * 1024 - gemm_out_tile_bytes(bn, epi)) / gemm_stage_bytes(bn, epi);
+  int s = (200 * 1024) / gemm_stage_bytes(bn, epi);
   return s > 8 ? 8 : s;
 }
 __host__ __device__ constexpr int sk_smem_bytes(int bn, int epi) {
-  return sk_stages(bn, epi) * gemm_stage_bytes(bn, epi) + gemm_out_tile_bytes(bn, epi) + 1024 + 256;
+  return sk_stages(bn, epi) * gemm_stage_bytes(bn, epi) + 1024 + 256;
 }
 __host__ __device__ constexpr uint32_t sk_tmem_cols(int bn, int epi) {
   int need = 2 * bn * (epi == EPI_SILU_BF16 ? 2 : 1);  // two accumulator buffers
@@ -52,7 +57,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmC, const StreamKParams p) {
+                    const StreamKParams p) {
   constexpr bool kDual = (EPI == EPI_SILU_BF16);
   constexpr int STAGES = sk_stages(BN, EPI);
   constexpr int STAGE_BYTES = gemm_stage_bytes(BN, EPI);
@@ -66,8 +71,7 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stg = smem + STAGES * STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + gemm_out_tile_bytes(BN, EPI));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]
@@ -87,7 +91,6 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -254,32 +257,32 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if constexpr (kDual) u[j] += __ldcg(w + TILE + j * kBlockM);
             }
           }
-          if constexpr (kDual) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(stg) + c0 * kBlockM + row;
+          const int f = t * kBlockM + row;
+          if (f < p.n_out) {
+            if constexpr (kDual) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)c0 * p.ldo + f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j * kBlockM] = __float2bfloat16(v[j] / (1.0f + __expf(-v[j])) * u[j]);
-          } else if constexpr (EPI == EPI_F32) {
-            float* o = reinterpret_cast<float*>(stg) + c0 * kBlockM + row;
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.T) o[(size_t)j * p.ldo] = __float2bfloat16(v[j] / (1.0f + __expf(-v[j])) * u[j]);
+            } else if constexpr (EPI == EPI_F32) {
+              float* o = reinterpret_cast<float*>(p.out) + (size_t)c0 * p.ldo + f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j * kBlockM] = v[j];
-          } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(stg) + c0 * kBlockM + row;
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.T) o[(size_t)j * p.ldo] = v[j];
+            } else {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)c0 * p.ldo + f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j * kBlockM] = __float2bfloat16(v[j]);
+              for (int j = 0; j < 16; ++j)
+                if (c0 + j < p.T) o[(size_t)j * p.ldo] = __float2bfloat16(v[j]);
+            }
           }
         }
         tc_fence_before();
-        fence_proxy_async();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (leader) {
           mbar_arrive(&tempty_bar[buf]);
-          if constexpr (EPI == EPI_F32) tma_store_3d(&tmC, stg, t * kBlockM, 0, 0);
-          else tma_store_2d(&tmC, stg, t * kBlockM, 0);
-          tma_store_commit();
-          tma_store_wait_read();
           if (a > 0) p.flags[c] = 0;  // every contributor has arrived; re-arm for the next launch
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // staging tile is free again
       }
     }
   }
