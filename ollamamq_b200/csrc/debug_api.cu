@@ -37,6 +37,7 @@ int mq_debug_gemm(const void* W, int w_rows, int n_out, int K, const void* X, in
     return MQ_ERR_NOMEM;
   }
   if (want_sk) splits = 1;
+  sk_ws.force = true;
   if (!gemm_plan(&g, W, w_rows, n_out, K, X, x_rows_alloc, T, epi, out, ldo, splits, split_stride, a2_row_off,
                  want_sk ? &sk_ws : nullptr)) {
     mq::set_last_error("gemm_plan failed (K%%64, splits, or cuTensorMapEncodeTiled)");

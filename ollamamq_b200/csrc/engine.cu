@@ -3,6 +3,7 @@
 #include "framing.hpp"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace mq {
@@ -177,7 +178,10 @@ static int build_plans(mq_worker* w, PassPlans* pp, int T, bool decode) {
   pp->T = T;
   pp->decode = decode;
   const int MBp = round_up(w->MB, 16);
-  const StreamKWorkspace* sk = (decode && T <= 64 && w->sk_ws.ws) ? &w->sk_ws : nullptr;
+  // per-layer GEMMs: stream-K only when forced (MQ_STREAMK=1); auto mode reserves it for the LM head
+  const char* sk_env = getenv("MQ_STREAMK");
+  const StreamKWorkspace* sk = (decode && T <= 64 && w->sk_ws.ws && sk_env && sk_env[0] == '1') ? &w->sk_ws : nullptr;
+  w->sk_ws.force = sk != nullptr;
   if (decode && !sk) {
     pp->s_qkv = decode_splits((w->qkv_dim + 127) / 128, H / 64);
     pp->s_o = decode_splits((H + 127) / 128, qd / 64);

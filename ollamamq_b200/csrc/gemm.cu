@@ -164,13 +164,23 @@ void gemm_set_attrs() {
   set_attrs_sk<16, EPI_SILU_BF16>(); set_attrs_sk<32, EPI_SILU_BF16>(); set_attrs_sk<64, EPI_SILU_BF16>();
 }
 
-bool streamk_enabled() {
-  static int v = -1;
-  if (v < 0) {
+// MQ_STREAMK: "1" = every decode GEMM, "0" = none, unset = auto.  Measured on B200 (r01, Llama-3-8B, B=64):
+// the in-kernel fix-up tail (contributor epilogue -> fence -> flag -> finisher reads partials) costs ~6 us per
+// launch, more than the balance gain on the per-layer GEMMs (QKV 22.3 vs 16.5 us, O 21.9 vs 13.8, down 33 vs 27,
+// gate/up 53 vs 49) but less than it on the LM head, where every CTA owns ~6.8 whole tiles (162 vs 185 us).
+// Auto therefore uses stream-K only when a CTA owns at least two whole weight tiles.
+static int streamk_mode() {
+  static int v = -2;
+  if (v == -2) {
     const char* e = getenv("MQ_STREAMK");
-    v = (e && e[0] == '0') ? 0 : 1;
+    v = !e ? -1 : (e[0] == '0' ? 0 : 1);
   }
-  return v == 1;
+  return v;
+}
+bool streamk_enabled() { return streamk_mode() != 0; }
+static bool streamk_pick(int m_tiles, const StreamKWorkspace* sk) {
+  const int m = streamk_mode();
+  return sk->force || m == 1 || (m == -1 && m_tiles >= 2 * sk->n_ctas);
 }
 int streamk_workspace_alloc(StreamKWorkspace* w) {
   int dev = 0, sms = 0;
@@ -214,7 +224,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
                const StreamKWorkspace* sk) {
   if (K % kBlockK != 0) return false;
   const int kb = K / kBlockK;
-  g->streamk = sk != nullptr && sk->ws != nullptr && T <= 64 && streamk_enabled();
+  g->streamk = sk != nullptr && sk->ws != nullptr && T <= 64 && streamk_pick((n_out + kBlockM - 1) / kBlockM, sk);
   if (g->streamk) splits = 1;  // the kernel finishes shared tiles itself: one complete plane
   if (splits < 1) return false;
   const int kbps = (kb + splits - 1) / splits;  // uneven split-K: the last plane may get fewer k-blocks

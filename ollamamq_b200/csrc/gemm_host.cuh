@@ -24,6 +24,7 @@ struct StreamKWorkspace {
   float* ws = nullptr;
   int* flags = nullptr;
   int n_ctas = 0;  // persistent CTAs = SM count of the device
+  bool force = false;  // use stream-K for every decode-width GEMM planned with this workspace (tests, MQ_STREAMK=1)
 };
 int streamk_workspace_alloc(StreamKWorkspace* w);   // cudaMalloc on the current device
 void streamk_workspace_free(StreamKWorkspace* w);

@@ -119,63 +119,83 @@ void launch_add_rmsnorm(const LaunchCfg& lc, float* h, const void* partial, bool
 }
 
 // ------------------------------------------------------------------------------------------------
-// RoPE + paged KV write.  One CTA (256 threads) per (token, 4 heads); a thread owns the rotation pair (i, i+64).
-// (v1 used one CTA per token: 64 CTAs at decode, 30 us of pure load latency per layer — r01 launch shares.)
+// RoPE + paged KV write (v1: one CTA per token = 64 CTAs at decode, 30 us of pure load latency per layer;
+// v2: (token, 4 heads) CTAs with 2-byte accesses; v3 below: 8/16-byte accesses).
 // ------------------------------------------------------------------------------------------------
+// 4 consecutive qkv values of token t starting at column col: sum of the split-K planes (+ bias)
 template <bool F32>
-__device__ __forceinline__ float qkv_at(const RopeKvParams& p, int t, int col, int qkv_dim) {
-  float v;
+__device__ __forceinline__ float4 qkv_at4(const RopeKvParams& p, int t, int col, int qkv_dim) {
+  float4 v;
   if (F32) {
     const float* pp = reinterpret_cast<const float*>(p.qkv);
-    v = 0.f;
-    for (int s = 0; s < p.n_planes; ++s) v += pp[s * p.plane_stride + (size_t)t * qkv_dim + col];
+    v = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < p.n_planes; ++s) {
+      const float4 a = *reinterpret_cast<const float4*>(pp + s * p.plane_stride + (size_t)t * qkv_dim + col);
+      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    }
   } else {
-    v = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.qkv)[(size_t)t * qkv_dim + col]);
+    const uint2 a = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.qkv) + (size_t)t * qkv_dim + col);
+    v = make_float4(bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y));
   }
-  if (p.bias) v += __bfloat162float(p.bias[col]);
+  if (p.bias) {
+    const uint2 b = *reinterpret_cast<const uint2*>(p.bias + col);
+    v.x += bf16_lo(b.x); v.y += bf16_hi(b.x); v.z += bf16_lo(b.y); v.w += bf16_hi(b.y);
+  }
   return v;
 }
+__device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
+  uint2 o;
+  o.x = pack_bf16(a, b);
+  o.y = pack_bf16(c, d);
+  return o;
+}
 
+// One CTA (256 threads) per (token, 16 heads); a thread owns 4 consecutive rotation pairs (i..i+3, i+64..i+67)
+// of one head, so every access is 8 B (bf16) or 16 B (fp32 planes).
 template <bool F32>
 __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
   pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
   pdl_wait();
   constexpr int D = kHeadDim, HALF = D / 2;
   const int t = blockIdx.x;
-  const int hd = blockIdx.y * 4 + (threadIdx.x >> 6);  // q heads, then k heads, then v heads
+  const int hd = blockIdx.y * 16 + (threadIdx.x >> 4);  // q heads, then k heads, then v heads
   const int n_heads = p.n_q + 2 * p.n_kv;
   if (hd >= n_heads) return;
   const int pos = p.pos[t];
   const int slot = p.slot_of_tok[t];
   const int qkv_dim = n_heads * D;
-  const int i = threadIdx.x & (HALF - 1);  // pair index
+  const int i = (threadIdx.x & 15) * 4;  // first of 4 pair indices
   const int col = hd * D + i;
-  const float a = qkv_at<F32>(p, t, col, qkv_dim);
-  const float b = qkv_at<F32>(p, t, col + HALF, qkv_dim);
+  const float4 a = qkv_at4<F32>(p, t, col, qkv_dim);
+  const float4 b = qkv_at4<F32>(p, t, col + HALF, qkv_dim);
+  uint2 lo, hi;
   if (hd < p.n_q + p.n_kv) {
-    float sn, cs;
-    sincosf((float)pos * p.inv_freq[i], &sn, &cs);
-    const __nv_bfloat16 r0 = __float2bfloat16(a * cs - b * sn);
-    const __nv_bfloat16 r1 = __float2bfloat16(b * cs + a * sn);
-    if (hd < p.n_q) {
-      __nv_bfloat16* q = p.q_out + (size_t)t * p.n_q * D + hd * D;
-      q[i] = r0;
-      q[i + HALF] = r1;
-    } else {
-      const int page = p.block_table[(size_t)slot * p.max_pages + pos / kPageSize];
-      __nv_bfloat16* k = p.k_cache + (((size_t)page * p.n_kv + (hd - p.n_q)) * kPageSize + pos % kPageSize) * D;
-      k[i] = r0;
-      k[i + HALF] = r1;
-    }
+    const float4 fr = *reinterpret_cast<const float4*>(p.inv_freq + i);
+    float s0, c0, s1, c1, s2, c2, s3, c3;
+    sincosf((float)pos * fr.x, &s0, &c0);
+    sincosf((float)pos * fr.y, &s1, &c1);
+    sincosf((float)pos * fr.z, &s2, &c2);
+    sincosf((float)pos * fr.w, &s3, &c3);
+    lo = pack4_bf16(a.x * c0 - b.x * s0, a.y * c1 - b.y * s1, a.z * c2 - b.z * s2, a.w * c3 - b.w * s3);
+    hi = pack4_bf16(b.x * c0 + a.x * s0, b.y * c1 + a.y * s1, b.z * c2 + a.z * s2, b.w * c3 + a.w * s3);
+  } else {
+    lo = pack4_bf16(a.x, a.y, a.z, a.w);
+    hi = pack4_bf16(b.x, b.y, b.z, b.w);
+  }
+  __nv_bfloat16* dst;
+  if (hd < p.n_q) {
+    dst = p.q_out + (size_t)t * p.n_q * D + hd * D;
   } else {
     const int page = p.block_table[(size_t)slot * p.max_pages + pos / kPageSize];
-    __nv_bfloat16* v = p.v_cache + (((size_t)page * p.n_kv + (hd - p.n_q - p.n_kv)) * kPageSize + pos % kPageSize) * D;
-    v[i] = __float2bfloat16(a);
-    v[i + HALF] = __float2bfloat16(b);
+    const bool is_k = hd < p.n_q + p.n_kv;
+    const int kvh = is_k ? hd - p.n_q : hd - p.n_q - p.n_kv;
+    dst = (is_k ? p.k_cache : p.v_cache) + (((size_t)page * p.n_kv + kvh) * kPageSize + pos % kPageSize) * D;
   }
+  *reinterpret_cast<uint2*>(dst + i) = lo;
+  *reinterpret_cast<uint2*>(dst + i + HALF) = hi;
 }
 void launch_rope_kv(const LaunchCfg& lc, const RopeKvParams& p) {
-  const dim3 grid(p.T, (p.n_q + 2 * p.n_kv + 3) / 4);
+  const dim3 grid(p.T, (p.n_q + 2 * p.n_kv + 15) / 16);
   if (p.qkv_is_f32)
     launch_k(lc, rope_kv_kernel<true>, grid, dim3(256), 0, p);
   else

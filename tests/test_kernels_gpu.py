@@ -101,7 +101,7 @@ SK_CASES = [
 def test_gemm_streamk(T, n_out, K, epi):
     """Persistent stream-K decode GEMM (splits = -1 in the test ABI): complete sums in ONE plane, and the arrival
     counters re-arm themselves (second launch must give the same answer)."""
-    m = _lib()
+    m = _lib()   # splits = -1 forces stream-K whatever MQ_STREAMK says
     g = torch.Generator(device="cuda").manual_seed(T * 3 + n_out)
     W = (torch.randn(n_out, K, device=dev(), generator=g) * 0.05).bfloat16()
     X = torch.randn(64, K, device=dev(), generator=g).bfloat16()
