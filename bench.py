@@ -293,10 +293,11 @@ def _fast_cpu_weights(cfg):
 _CPU_W = None
 
 
-def cpu_reference_step(n_users=1, gen=8):
+def cpu_reference_step(gen=4):
     """The reference path on the host cores: the dispatch oracle in front of the CPU port of the forward pass,
-    reference semantics (one in-flight request per backend, one backend).  Bounded sample: n_users requests of
-    512 prompt tokens + `gen` greedy tokens, served one after the other."""
+    reference semantics (one in-flight request per backend, one backend => requests are served one after the other).
+    Bounded sample: ONE request of the trace, the full 512-token prompt + `gen` greedy tokens.
+    Returns (t_prefill_s, t_per_decode_token_s, wall_s)."""
     import torch
     from oracle.dispatch_oracle import OraclePy, simulate
     from oracle.llama_ref import LLAMA3_8B, forward
@@ -304,36 +305,40 @@ def cpu_reference_step(n_users=1, gen=8):
     if _CPU_W is None:
         _CPU_W = _fast_cpu_weights(LLAMA3_8B)
     P = prompts()
-    order = simulate(OraclePy(1), [(0, "user%02d" % u) for u in range(n_users)], lambda u, s, b: 1)
+    (user, _, _), = simulate(OraclePy(1), [(0, "user00")], lambda u, s, b: 1)
+    u = int(user[4:])
     t0 = time.perf_counter()
-    ttft = []
-    ntok = 0
-    for user, _, _ in order:
-        u = int(user[4:])
-        kv = []
-        logits = forward(_CPU_W, LLAMA3_8B, P[u], torch.float32, 0, kv)
-        tok = int(logits[-1].float().argmax())
-        ttft.append(time.perf_counter() - t0)
-        ntok += 1
-        for i in range(gen - 1):
-            logits = forward(_CPU_W, LLAMA3_8B, [tok], torch.float32, PROMPT_LEN + i, kv)
-            tok = int(logits[-1].float().argmax())
-            ntok += 1
-    return time.perf_counter() - t0, ntok, ttft
+    kv = []
+    logits = forward(_CPU_W, LLAMA3_8B, P[u], torch.float32, 0, kv, last_only=True)
+    tok = int(logits[-1].argmax())
+    t1 = time.perf_counter()
+    for i in range(gen - 1):
+        logits = forward(_CPU_W, LLAMA3_8B, [tok], torch.float32, PROMPT_LEN + i, kv, last_only=True)
+        tok = int(logits[-1].argmax())
+    t2 = time.perf_counter()
+    return t1 - t0, (t2 - t1) / max(1, gen - 1), t2 - t0
+
+
+def _cpu_trace_rate(t_prefill, t_tok):
+    """tokens/s of the 64 x (512 + 128) trace when requests are served one at a time (capacity 1): every request costs
+    t_prefill + 127 * t_tok and yields 128 tokens, so the trace rate equals the per-request rate."""
+    return GEN_LEN / (t_prefill + (GEN_LEN - 1) * t_tok)
+
+
+def _cpu_sample_text(n):
+    return ("%d x [1 request of the trace: the 512-token prompt prefilled + 4 greedy tokens decoded, Llama-3-8B geometry, "
+            "fp32 math, torch CPU port (oracle/llama_ref.py) behind the dispatch oracle, capacity 1 like the reference]; "
+            "value = 128 / (t_prefill + 127 * t_decode_token) from the two MEASURED components, i.e. a linear "
+            "extrapolation of the bounded sample to the 128-token requests of the trace; the reference itself "
+            "(Rust + Ollama/llama.cpp) cannot be built or installed in this image" % n)
 
 
 def cpu_baseline_sample():
     import torch
-    t0 = time.time()
-    dt, ntok, ttft = cpu_reference_step(1, 8)
-    if dt < 8:
-        dt2, ntok2, ttft2 = cpu_reference_step(2, 8)
-        dt, ntok, ttft = dt2, ntok2, ttft2
-    return {"value": ntok / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": "%d request(s) x (512-token prompt + 8 greedy tokens), Llama-3-8B (fp32 math on the CPU) via the "
-                      "torch CPU port (oracle/llama_ref.py) behind the dispatch oracle, capacity 1 like the reference; "
-                      "%.1fs incl. weight setup" % (len(ttft), time.time() - t0),
-            "ttft_first_request_ms": ttft[0] * 1e3}
+    tp, tt, _ = cpu_reference_step(4)
+    return {"value": _cpu_trace_rate(tp, tt), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": _cpu_sample_text(1), "prefill_s": tp, "decode_s_per_token": tt,
+            "ttft_first_request_ms": tp * 1e3}
 
 
 def run_reference(args):
@@ -341,27 +346,28 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    for _ in range(min(args.warmup, 1)):
-        cpu_reference_step(1, 4)
-    tot_t, tot_tok, ttfts = 0.0, 0, []
+    if args.warmup > 0:
+        cpu_reference_step(2)          # one short warm-up is enough for a CPU loop (weights get paged in)
+    tps, tts, wall = [], [], 0.0
     for _ in range(args.steps):
-        dt, ntok, tt = cpu_reference_step(2, 8)
-        tot_t += dt
-        tot_tok += ntok
-        ttfts += tt
-    v = tot_tok / tot_t
-    sample = ("each step: 2 requests x (512-token prompt + 8 greedy tokens) of the 64-user trace, served one at a "
-              "time (reference capacity 1); Llama-3-8B torch CPU port, fp32 math (oracle/llama_ref.py) behind the dispatch "
-              "oracle; the reference itself (Rust + Ollama/llama.cpp) cannot be built or installed in this image")
+        tp, tt, w = cpu_reference_step(4)
+        tps.append(tp)
+        tts.append(tt)
+        wall += w
+    tp, tt = sum(tps) / len(tps), sum(tts) / len(tts)
+    v = _cpu_trace_rate(tp, tt)
+    # with capacity 1 the k-th of 64 simultaneous users waits for k-1 whole requests: p50 TTFT of the trace
+    ttft_p50 = (32 * (tp + (GEN_LEN - 1) * tt) + tp) * 1e3
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3, "higher_is_better": True,
+            "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1] (bounded sample): Llama-3-8B bf16, 512-token prompt, greedy decode",
+            "config": {"workload": "BASELINE configs[1] (bounded sample): Llama-3-8B, 512-token prompt, greedy decode",
                        "users": USERS, "prompt_len": PROMPT_LEN, "gen_len": GEN_LEN},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": _cpu_sample_text(args.steps), "prefill_s": tp, "decode_s_per_token": tt},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                    "ttft_first_request_ms": ttfts[0] * 1e3},
-            "gpu_launches": 0}
+                    "ttft_p50_ms_extrapolated": ttft_p50, "ttft_first_request_ms": tp * 1e3},
+            "ttft_p50_ms": ttft_p50, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 

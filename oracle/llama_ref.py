@@ -75,9 +75,9 @@ def _rope(x, pos, theta):
 
 @torch.no_grad()
 def forward(w: Dict[str, torch.Tensor], cfg: dict, tokens, dtype=torch.float32,
-            start_pos: int = 0, kv: Optional[List] = None) -> torch.Tensor:
-    """Logits [T, vocab] for a token sequence.  With `kv` (list of per-layer [k, v]) the call appends to the
-    cache and attends over the whole context (used for step-by-step greedy decoding)."""
+            start_pos: int = 0, kv: Optional[List] = None, last_only: bool = False) -> torch.Tensor:
+    """Logits [T, vocab] for a token sequence ([1, vocab] with last_only).  With `kv` (list of per-layer [k, v])
+    the call appends to the cache and attends over the whole context (used for step-by-step greedy decoding)."""
     dev = next(iter(w.values())).device
     tokens = torch.as_tensor(tokens, dtype=torch.long, device=dev)
     T = tokens.shape[0]
@@ -114,6 +114,8 @@ def forward(w: Dict[str, torch.Tensor], cfg: dict, tokens, dtype=torch.float32,
         x = _rmsnorm(h, w[p + "mlp_norm"].to(dtype), eps)
         gu = x @ w[p + "w_gate_up"].to(dtype).T
         h = h + (torch.nn.functional.silu(gu[:, :I]) * gu[:, I:]) @ w[p + "w_down"].to(dtype).T
+    if last_only:
+        h = h[-1:]
     x = _rmsnorm(h, w["final_norm"].to(dtype), eps)
     return x @ w["lm_head"].to(dtype).T
 
