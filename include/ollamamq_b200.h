@@ -140,6 +140,9 @@ int mq_worker_healthy(mq_worker* w);
 #define MQ_EP_V1_CHAT 2        /* /v1/chat/completions     SSE    */
 #define MQ_EP_V1_COMPLETIONS 3 /* /v1/completions          SSE    */
 #define MQ_EP_RAW_TOKENS 4     /* no framing: chunks are little-endian int32 token ids                    */
+#define MQ_EP_OTHER 5          /* any other routed path (main.rs:92-112): answered by the worker without
+                                  touching the GPU (model listings, version) or with 501 (embeddings, model
+                                  management); still queued and dispatched like every request               */
 
 typedef struct mq_request {
   int32_t endpoint;          /* MQ_EP_*                                                                   */
@@ -151,6 +154,7 @@ typedef struct mq_request {
   int32_t max_new_tokens;    /* generation length; <=0: take options.num_predict / max_tokens from body   */
   int32_t ignore_eos;        /* benchmark mode: always generate max_new_tokens                            */
   uint32_t timeout_ms;       /* whole-request timeout (reqwest Client::timeout, :165-167); 0 = none       */
+  const char* path;          /* request path (uri.path(), :362); only consulted for MQ_EP_OTHER; may be NULL  */
 } mq_request;
 
 typedef struct mq_callbacks {
@@ -228,6 +232,17 @@ int mq_dispatcher_wait_parked(mq_dispatcher* d, uint32_t timeout_ms);
 int mq_dispatcher_new_mock(int32_t n_backends, int32_t capacity, mq_dispatcher** out);
 int mq_dispatcher_mock_complete(mq_dispatcher* d, int32_t backend, int32_t rc);
 int mq_dispatcher_mock_fail_next(mq_dispatcher* d, int32_t backend, int32_t n);
+
+/* =====================================================================================================
+ * 3b. HTTP/1.1 ingress: the route table of main.rs:89-121 and the proxy_handler
+ *     semantics of dispatcher.rs:354-428 (X-User-ID, 403 / 500 bodies, streamed relay) over a dispatcher.
+ * ===================================================================================================== */
+typedef struct mq_http_server mq_http_server;
+/* port 0 picks a free port (read it back with mq_http_server_port).  allow_all_routes = --allow-all-routes.   */
+int mq_http_server_start(mq_dispatcher* d, const char* bind_addr, int32_t port, int32_t allow_all_routes,
+                         mq_http_server** out);
+int mq_http_server_port(mq_http_server* s);
+void mq_http_server_stop(mq_http_server* s);
 
 /* =====================================================================================================
  * 4. Kernel-level test ABI (device pointers).  See csrc/debug_api.cu.

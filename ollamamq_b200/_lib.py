@@ -51,7 +51,7 @@ class ModelCfg(C.Structure):
 class Request(C.Structure):
     _fields_ = [("endpoint", C.c_int32), ("stream", C.c_int32), ("body", C.c_void_p), ("body_len", C.c_size_t),
                 ("prompt_tokens", C.c_void_p), ("n_prompt_tokens", C.c_int32), ("max_new_tokens", C.c_int32),
-                ("ignore_eos", C.c_int32), ("timeout_ms", C.c_uint32)]
+                ("ignore_eos", C.c_int32), ("timeout_ms", C.c_uint32), ("path", C.c_char_p)]
 
 
 ON_STATUS = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_char_p)
@@ -136,6 +136,9 @@ _sig("mq_dispatcher_wait_parked", C.c_int, [P, C.c_uint32])
 _sig("mq_dispatcher_new_mock", C.c_int, [C.c_int32, C.c_int32, C.POINTER(P)])
 _sig("mq_dispatcher_mock_complete", C.c_int, [P, C.c_int32, C.c_int32])
 _sig("mq_dispatcher_mock_fail_next", C.c_int, [P, C.c_int32, C.c_int32])
+_sig("mq_http_server_start", C.c_int, [P, C.c_char_p, C.c_int32, C.c_int32, C.POINTER(P)])
+_sig("mq_http_server_port", C.c_int, [P])
+_sig("mq_http_server_stop", None, [P])
 # kernel-level test ABI
 _sig("mq_debug_gemm", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int,
                                  C.c_longlong, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)])

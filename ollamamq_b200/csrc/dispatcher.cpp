@@ -118,6 +118,7 @@ struct mq_dispatcher {
     mq_request rq;
     std::vector<uint8_t> body;
     std::vector<int32_t> tokens;
+    std::string path;
     mq_callbacks cb;
     void* user_data;
     mq_dispatcher* d;
@@ -240,6 +241,7 @@ void run_worker(mq_dispatcher* d) {
     rq.body_len = t->body.size();
     rq.prompt_tokens = t->tokens.empty() ? nullptr : t->tokens.data();
     rq.n_prompt_tokens = (int32_t)t->tokens.size();
+    rq.path = t->path.empty() ? nullptr : t->path.c_str();
     mq_callbacks cb{cb_status, cb_chunk, cb_done};
     Backend* be = d->backends[sd.backend].get();
     lk.unlock();  // the reference spawns the executor and loops immediately (:270)
@@ -343,6 +345,7 @@ int mq_dispatcher_submit(mq_dispatcher* d, const char* user, const char* ip, con
   t->rq = *r;
   if (r->body && r->body_len) t->body.assign(r->body, r->body + r->body_len);
   if (r->prompt_tokens && r->n_prompt_tokens > 0) t->tokens.assign(r->prompt_tokens, r->prompt_tokens + r->n_prompt_tokens);
+  if (r->path) t->path = r->path;
   t->cb = *cb;
   t->user_data = user_data;
   t->d = d;

@@ -728,7 +728,20 @@ static void worker_main(mq_worker* w) {
   cudaSetDevice(w->gpu);
   Clock::time_point last_arrival = Clock::now(), window_start = last_arrival;
   bool in_window = false;
+  std::vector<mq_req*> others;
   for (;;) {
+    for (mq_req* r : others) {  // non-generation routes: immediate answer, same Status/Chunk/Done sequence
+      int status = 200;
+      std::string ctype, body;
+      other_route_response(r->path, w->cfg.model_name, &status, &ctype, &body);
+      r->t_first = r->t_last = Clock::now();
+      r->finished = true;
+      if (r->cb.on_status) r->cb.on_status(r->user, status, ctype.c_str());
+      if (r->cb.on_chunk) r->cb.on_chunk(r->user, (const uint8_t*)body.data(), body.size());
+      if (r->cb.on_done) r->cb.on_done(r->user, 0, "");
+      req_unref(r);
+    }
+    others.clear();
     // ---- intake
     {
       std::unique_lock<std::mutex> lk(w->mu);
@@ -738,7 +751,12 @@ static void worker_main(mq_worker* w) {
         w->cv.wait_for(lk, std::chrono::milliseconds(50));
       if (w->stop) break;
       if (!w->inbox.empty()) last_arrival = Clock::now();
-      while (!w->inbox.empty()) { w->waiting.push_back(w->inbox.front()); w->inbox.pop_front(); }
+      while (!w->inbox.empty()) {
+        mq_req* r = w->inbox.front();
+        w->inbox.pop_front();
+        if (r->rq.endpoint == MQ_EP_OTHER) others.push_back(r);
+        else w->waiting.push_back(r);
+      }
       if (idle && !w->jobs.empty()) {
         auto job = std::move(w->jobs.front());
         w->jobs.pop_front();
@@ -1060,6 +1078,15 @@ int mq_submit(mq_worker* w, const mq_request* rq, const mq_callbacks* cb, void* 
   r->user = user;
   r->t_submit = Clock::now();
   if (rq->body && rq->body_len) r->body.assign((const char*)rq->body, rq->body_len);
+  if (rq->path) r->path = rq->path;
+  r->rq.path = nullptr;
+  if (rq->endpoint == MQ_EP_OTHER) {  // answered on the worker thread without touching the GPU
+    r->rq.body = nullptr; r->rq.prompt_tokens = nullptr;
+    if (out) *out = r; else r->refs.store(1);
+    { std::lock_guard<std::mutex> g(w->mu); w->inbox.push_back(r); }
+    w->cv.notify_all();
+    return MQ_OK;
+  }
   ParsedBody pb;
   if (!r->body.empty()) parse_body(r->body, rq->endpoint, &pb);
   if (rq->prompt_tokens && rq->n_prompt_tokens > 0)

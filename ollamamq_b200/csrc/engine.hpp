@@ -44,6 +44,7 @@ struct mq_req {
   mq_request rq{};
   std::vector<int32_t> prompt;
   std::string body;
+  std::string path;
   mq_callbacks cb{};
   void* user = nullptr;
   int slot = -1;

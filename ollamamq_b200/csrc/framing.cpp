@@ -269,6 +269,29 @@ std::string frame_token(int endpoint, const char* model, int tok) {
   return buf;
 }
 
+void other_route_response(const std::string& path, const char* model, int* status, std::string* ctype, std::string* body) {
+  const std::string m = json_escape(model);
+  *status = 200;
+  *ctype = "application/json";
+  if (path == "/") {
+    *ctype = "text/plain; charset=utf-8";
+    *body = "Ollama is running";
+  } else if (path == "/api/version") {
+    *body = "{\"version\":\"0.0.0-ollamamq-b200\"}";
+  } else if (path == "/api/tags" || path == "/api/ps") {
+    *body = "{\"models\":[{\"name\":\"" + m + "\",\"model\":\"" + m + "\",\"details\":{\"format\":\"bf16\",\"family\":\"llama\"}}]}";
+  } else if (path == "/api/show") {
+    *body = "{\"details\":{\"format\":\"bf16\",\"family\":\"llama\"},\"model_info\":{\"general.name\":\"" + m + "\"}}";
+  } else if (path == "/v1/models") {
+    *body = "{\"object\":\"list\",\"data\":[{\"id\":\"" + m + "\",\"object\":\"model\",\"owned_by\":\"ollamamq-b200\"}]}";
+  } else if (path.rfind("/v1/models/", 0) == 0) {
+    *body = "{\"id\":\"" + json_escape(path.substr(11)) + "\",\"object\":\"model\",\"owned_by\":\"ollamamq-b200\"}";
+  } else {
+    *status = 501;  // embeddings and model management are not served by this worker
+    *body = "{\"error\":\"" + json_escape(path) + " is not implemented by the B200 worker\"}";
+  }
+}
+
 std::string frame_final(int endpoint, int stream, const char* model, const std::string& agg, int n_prompt, int n_gen) {
   if (endpoint == MQ_EP_RAW_TOKENS) return stream ? std::string() : agg;
   const std::string m = json_escape(model), txt = json_escape(agg);

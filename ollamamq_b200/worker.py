@@ -84,8 +84,10 @@ class Stream:
 
 
 def make_request(endpoint=EP_RAW_TOKENS, prompt_tokens: Optional[Sequence[int]] = None, body: Optional[bytes] = None,
-                 max_new_tokens=16, stream=1, timeout_ms=0):
+                 max_new_tokens=16, stream=1, timeout_ms=0, path: Optional[str] = None):
     r = _lib.Request()
+    if path is not None:
+        r.path = path.encode()
     r.endpoint, r.stream, r.max_new_tokens, r.ignore_eos, r.timeout_ms = endpoint, stream, max_new_tokens, 1, timeout_ms
     keep = []
     if body is not None:
@@ -199,6 +201,7 @@ class Dispatcher:
         self._streams = []
 
     def close(self):
+        self.stop_http()
         if self._h:
             lib.mq_dispatcher_free(self._h)
             self._h = None
@@ -244,6 +247,18 @@ class Dispatcher:
 
     def drain(self, timeout_ms=600000):
         check(lib.mq_dispatcher_drain(self._h, timeout_ms))
+
+    def serve_http(self, port: int = 0, bind: str = "127.0.0.1", allow_all_routes: bool = False) -> int:
+        """Start the HTTP/1.1 ingress (route table of main.rs:89-121) on this dispatcher; returns the port."""
+        h = C.c_void_p()
+        check(lib.mq_http_server_start(self._h, bind.encode(), port, 1 if allow_all_routes else 0, C.byref(h)))
+        self._http = h
+        return lib.mq_http_server_port(h)
+
+    def stop_http(self):
+        if getattr(self, "_http", None):
+            lib.mq_http_server_stop(self._http)
+            self._http = None
 
     def log(self):
         n = C.c_int32()
