@@ -220,6 +220,12 @@ int mq_dispatcher_log(mq_dispatcher* d, mq_dispatch* out, int32_t cap, int32_t* 
 int mq_dispatcher_drain(mq_dispatcher* d, uint32_t timeout_ms);
 /* health prober result for one backend (:185-189); like the reference, recovery does not wake the scheduler */
 int mq_dispatcher_set_online(mq_dispatcher* d, int32_t backend, int32_t online);
+/* block list persistence: load `path` now (AppState::new, :69,:98-105) and rewrite it on every block / unblock
+ * (:107-115).  Format pinned by the reference: pretty JSON {"ips": [...], "users": [...]} (:21-25); the reference
+ * uses "blocked_items.json" in the working directory (:19).                                                   */
+int mq_dispatcher_set_block_file(mq_dispatcher* d, const char* path);
+/* health prober (:171-193): every period_ms (reference: 10 000) copy mq_worker_healthy() into is_online         */
+int mq_dispatcher_start_health(mq_dispatcher* d, uint32_t period_ms);
 /* the HTTP connection behind a queued / in-flight task closed (responder.is_closed(), :278; send error, :305) */
 int mq_dispatcher_client_gone(mq_dispatcher* d, uint64_t task_id);
 /* block until the run_worker thread is parked on {notify, backend_freed} with nothing pending (:344-349)   */

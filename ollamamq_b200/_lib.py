@@ -131,6 +131,8 @@ _sig("mq_dispatcher_block_ip", C.c_int, [P, C.c_char_p, C.c_int32])
 _sig("mq_dispatcher_log", C.c_int, [P, C.POINTER(Dispatch), C.c_int32, C.POINTER(C.c_int32)])
 _sig("mq_dispatcher_drain", C.c_int, [P, C.c_uint32])
 _sig("mq_dispatcher_set_online", C.c_int, [P, C.c_int32, C.c_int32])
+_sig("mq_dispatcher_set_block_file", C.c_int, [P, C.c_char_p])
+_sig("mq_dispatcher_start_health", C.c_int, [P, C.c_uint32])
 _sig("mq_dispatcher_client_gone", C.c_int, [P, C.c_uint64])
 _sig("mq_dispatcher_wait_parked", C.c_int, [P, C.c_uint32])
 _sig("mq_dispatcher_new_mock", C.c_int, [C.c_int32, C.c_int32, C.POINTER(P)])

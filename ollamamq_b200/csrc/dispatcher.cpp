@@ -15,6 +15,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <cstdio>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -139,6 +140,9 @@ struct mq_dispatcher {
   std::map<std::string, std::string> user_ips;
   std::set<std::string> blocked_users, blocked_ips;
   std::vector<mq_dispatch> log;
+  std::string block_file;           // BLOCKED_FILE = "blocked_items.json" in the reference (:19); empty = no persistence
+  std::thread health_thr;
+  uint32_t health_period_ms = 0;
   uint64_t outstanding = 0;
   uint64_t wake_seq = 0, handled_seq = 0;
   bool parked = false;
@@ -262,6 +266,69 @@ void run_worker(mq_dispatcher* d) {
   }
 }
 
+// blocked_items.json: pretty JSON {"ips": [...], "users": [...]} (BlockedConfig, :21-25; load :98-105, save :107-115)
+void save_blocked(mq_dispatcher* d) {  // caller holds d->mu
+  if (d->block_file.empty()) return;
+  std::string o = "{\n  \"ips\": [";
+  bool first = true;
+  for (const auto& ip : d->blocked_ips) { o += first ? "\n    \"" : ",\n    \""; o += ip + "\""; first = false; }
+  o += first ? "],\n  \"users\": [" : "\n  ],\n  \"users\": [";
+  first = true;
+  for (const auto& u : d->blocked_users) {
+    o += first ? "\n    \"" : ",\n    \"";
+    for (char c : u) { if (c == '"' || c == '\\') o.push_back('\\'); o.push_back(c); }
+    o += "\"";
+    first = false;
+  }
+  o += first ? "]\n}" : "\n  ]\n}";
+  FILE* f = fopen(d->block_file.c_str(), "w");
+  if (!f) return;  // the reference ignores write errors too (`let _ = fs::write`, :113)
+  fwrite(o.data(), 1, o.size(), f);
+  fclose(f);
+}
+
+// tolerant reader for the two string arrays
+void load_blocked(mq_dispatcher* d) {  // caller holds d->mu
+  FILE* f = fopen(d->block_file.c_str(), "r");
+  if (!f) return;
+  std::string txt;
+  char buf[4096];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof(buf), f)) > 0) txt.append(buf, n);
+  fclose(f);
+  auto read_array = [&](const char* key, std::set<std::string>* out) {
+    size_t k = txt.find(std::string("\"") + key + "\"");
+    if (k == std::string::npos) return;
+    size_t b = txt.find('[', k), e = txt.find(']', k);
+    if (b == std::string::npos || e == std::string::npos || e < b) return;
+    size_t p = b;
+    while (true) {
+      size_t q1 = txt.find('"', p + 1);
+      if (q1 == std::string::npos || q1 > e) break;
+      std::string v;
+      size_t q = q1 + 1;
+      while (q < txt.size() && txt[q] != '"') {
+        if (txt[q] == '\\' && q + 1 < txt.size()) ++q;
+        v.push_back(txt[q++]);
+      }
+      out->insert(v);
+      p = q;
+    }
+  };
+  read_array("ips", &d->blocked_ips);
+  read_array("users", &d->blocked_users);
+}
+
+// health prober (:171-193): periodically asks every backend whether it still answers; flipping a backend back
+// online does not wake the scheduler, exactly like the reference
+void health_loop(mq_dispatcher* d) {
+  std::unique_lock<std::mutex> lk(d->mu);
+  while (!d->stop) {
+    for (size_t i = 0; i < d->backends.size(); ++i) d->sched->s.set_online((int)i, d->backends[i]->healthy());
+    d->cv_idle.wait_for(lk, std::chrono::milliseconds(d->health_period_ms), [&] { return d->stop; });
+  }
+}
+
 mq_dispatcher* make_dispatcher(std::vector<std::unique_ptr<Backend>> bes, int capacity) {
   auto* d = new (std::nothrow) mq_dispatcher();
   if (!d) return nullptr;
@@ -323,7 +390,9 @@ void mq_dispatcher_free(mq_dispatcher* d) {
     d->wake_seq++;
   }
   d->cv.notify_all();
+  d->cv_idle.notify_all();
   if (d->thr.joinable()) d->thr.join();
+  if (d->health_thr.joinable()) d->health_thr.join();
   // in-flight tasks belong to backends that outlive us only for GPU workers; drain what the mocks hold
   for (auto* m : d->mocks) while (m->complete_oldest(MQ_ERR_CANCELED)) {}
   mq_dispatcher_drain(d, 5000);
@@ -400,12 +469,29 @@ int mq_dispatcher_block_user(mq_dispatcher* d, const char* user, int32_t blocked
   if (!d || !user) return MQ_ERR_INVAL;
   std::lock_guard<std::mutex> g(d->mu);
   if (blocked) d->blocked_users.insert(user); else d->blocked_users.erase(user);
+  save_blocked(d);  // rewritten on every change (:107-115)
   return MQ_OK;
 }
 int mq_dispatcher_block_ip(mq_dispatcher* d, const char* ip, int32_t blocked) {
   if (!d || !ip) return MQ_ERR_INVAL;
   std::lock_guard<std::mutex> g(d->mu);
   if (blocked) d->blocked_ips.insert(ip); else d->blocked_ips.erase(ip);
+  save_blocked(d);
+  return MQ_OK;
+}
+int mq_dispatcher_set_block_file(mq_dispatcher* d, const char* path) {
+  if (!d || !path) return MQ_ERR_INVAL;
+  std::lock_guard<std::mutex> g(d->mu);
+  d->block_file = path;
+  load_blocked(d);  // AppState::new -> load_blocked_items (:69, :98-105)
+  return MQ_OK;
+}
+int mq_dispatcher_start_health(mq_dispatcher* d, uint32_t period_ms) {
+  if (!d || period_ms == 0) return MQ_ERR_INVAL;
+  std::lock_guard<std::mutex> g(d->mu);
+  if (d->health_thr.joinable()) return MQ_ERR_BUSY;
+  d->health_period_ms = period_ms;
+  d->health_thr = std::thread(health_loop, d);
   return MQ_OK;
 }
 int mq_dispatcher_set_online(mq_dispatcher* d, int32_t backend, int32_t online) {

@@ -233,6 +233,12 @@ class Dispatcher:
     def set_online(self, backend, online):
         check(lib.mq_dispatcher_set_online(self._h, backend, 1 if online else 0))
 
+    def set_block_file(self, path: str):
+        check(lib.mq_dispatcher_set_block_file(self._h, path.encode()))
+
+    def start_health(self, period_ms: int = 10000):
+        check(lib.mq_dispatcher_start_health(self._h, period_ms))
+
     def client_gone(self, task_id):
         return lib.mq_dispatcher_client_gone(self._h, task_id)
 

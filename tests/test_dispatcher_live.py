@@ -164,3 +164,49 @@ def test_no_cpu_fallback_for_the_forward_pass():
     with pytest.raises(mq.MQError) as e:
         mq.Worker(0, mq.model_cfg(TINY_LLAMA, max_batch=4, max_seq=64, max_prefill_tokens=64))
     assert e.value.rc == -19
+
+
+def test_block_list_persistence_format(tmp_path):
+    """blocked_items.json round trip; format pinned by BlockedConfig (dispatcher.rs:21-25,98-115)."""
+    import json
+    path = str(tmp_path / "blocked_items.json")
+    d = mq.Dispatcher(mock_backends=1)
+    try:
+        d.set_block_file(path)                      # nothing to load yet
+        d.block_user("mallory")
+        d.block_ip("10.1.2.3")
+        d.block_user('we"ird')
+        cfg = json.load(open(path))
+        assert sorted(cfg) == ["ips", "users"]
+        assert cfg["ips"] == ["10.1.2.3"] and sorted(cfg["users"]) == sorted(["mallory", 'we"ird'])
+        assert open(path).read().startswith('{\n  "ips": [')          # serde_json::to_string_pretty layout
+        d.block_user("mallory", False)              # unblock rewrites the file too
+        assert json.load(open(path))["users"] == ['we"ird']
+    finally:
+        d.close()
+    d2 = mq.Dispatcher(mock_backends=1)            # restart: the list survives (SURVEY.md 5, checkpoint/resume)
+    try:
+        d2.set_block_file(path)
+        with pytest.raises(mq.MQError) as e:
+            d2.submit('we"ird', max_new_tokens=1)
+        assert e.value.rc == -13
+        with pytest.raises(mq.MQError):
+            d2.submit("bob", ip="10.1.2.3", max_new_tokens=1)
+        d2.submit("bob", ip="10.9.9.9", max_new_tokens=1)
+        d2.wait_parked()
+        assert d2.mock_complete(0)
+        d2.drain(2000)
+    finally:
+        d2.close()
+
+
+def test_health_prober_keeps_mock_backends_online():
+    d = mq.Dispatcher(mock_backends=2)
+    try:
+        d.set_online(1, False)
+        d.start_health(20)                          # reference period is 10 s; mocks always answer
+        import time
+        time.sleep(0.15)
+        assert d.backend_stats(1)["is_online"]
+    finally:
+        d.close()

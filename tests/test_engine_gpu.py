@@ -192,3 +192,41 @@ def test_full_size_llama3_8b_logits_and_decode():
         for j, tok in enumerate(gen):
             row = r[len(prompt) - 1 + j]
             assert (row.max() - row[tok]).item() <= 8e-2 * row.abs().max().item(), j
+
+
+def test_http_end_to_end_over_gpu_worker():
+    """curl-style requests through the HTTP ingress -> dispatcher -> GPU worker."""
+    import http.client
+    cfg = MID
+    w = R.make_weights(cfg, seed=51, device="cuda")
+    with _open(cfg, w, max_batch=4) as wk:
+        d = mq.Dispatcher([wk], capacity=4)
+        try:
+            port = d.serve_http(0)
+            c = http.client.HTTPConnection("127.0.0.1", port, timeout=60)
+            c.request("GET", "/health")
+            r = c.getresponse()
+            assert (r.status, r.read()) == (200, b"OK")
+            body = json.dumps({"model": "m", "messages": [{"role": "user", "content": "Req 1"}], "stream": True,
+                               "options": {"num_predict": 5}})
+            c.request("POST", "/api/chat", body=body, headers={"X-User-ID": "alice", "Content-Type": "application/json"})
+            r = c.getresponse()
+            lines = [json.loads(x) for x in r.read().decode().strip().split("\n")]
+            assert r.status == 200 and r.getheader("Content-Type") == "application/x-ndjson"
+            assert len(lines) == 6 and lines[-1]["done"] and lines[-1]["eval_count"] == 5
+            # OpenAI route, stream omitted -> one JSON document; raw token prompt through "prompt": [ids]
+            c.request("POST", "/v1/completions", body=json.dumps({"model": "m", "prompt": [5, 6, 7], "max_tokens": 4}),
+                      headers={"X-User-ID": "bob"})
+            r = c.getresponse()
+            obj = json.loads(r.read())
+            assert r.status == 200 and obj["object"] == "text_completion" and obj["usage"]["completion_tokens"] == 4
+            c.request("GET", "/api/tags", headers={"X-User-ID": "bob"})
+            r = c.getresponse()
+            assert r.status == 200 and "models" in json.loads(r.read())
+            c.request("POST", "/api/embed", body="{}", headers={"X-User-ID": "bob"})
+            r = c.getresponse()
+            assert r.status == 501 and r.read()
+            c.close()
+            assert d.user_stats("alice")["processed"] == 1 and d.user_stats("bob")["processed"] == 3
+        finally:
+            d.close()
