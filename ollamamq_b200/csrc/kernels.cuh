@@ -62,7 +62,7 @@ void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots);
 void attn_set_attrs();
 int attn_decode_resident_ctas();
 constexpr int kMaxDecodeSplits = 8;
-constexpr int kPrefillTileRows = 128;  // q rows (token x group-head) per prefill CTA (8 warps share each K/V tile)
+constexpr int kPrefillTileRows = 64;  // q rows (token x group-head) per prefill CTA (r01: 128 rows / 8 warps was 20% slower: 1 CTA/SM by registers)
 
 // next[b] = argmax_v logits[b][v]; optional: cur_token[slot]=next, pos[slot]+=1 for active slots
 void launch_argmax(const LaunchCfg& lc, const float* logits, int rows, int V, int ldl, int* out_tokens,

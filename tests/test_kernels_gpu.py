@@ -278,7 +278,7 @@ def _gather_kv(kc, vc, bt_row, L):
 def test_attn_prefill(n_q, n_kv):
     m = _lib()
     G = n_q // n_kv
-    tok_per_tile = 128 // G   # kPrefillTileRows / G
+    tok_per_tile = 64 // G   # kPrefillTileRows / G
     n_slots, max_pages = 3, 40
     bt, kc, vc = _make_cache(n_slots, max_pages, n_kv, seed=1)
     kc = torch.randn_like(kc.float()).bfloat16()
