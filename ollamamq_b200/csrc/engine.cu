@@ -117,6 +117,12 @@ static int worker_alloc(mq_worker* w) {
   if ((rc = dalloc(&w->logits, (size_t)MBp * V))) return rc;
   if ((rc = dalloc(&w->part_o, (size_t)kMaxDecodeSplits * MBp * c.n_q_heads * D))) return rc;
   if ((rc = dalloc(&w->part_ml, (size_t)kMaxDecodeSplits * MBp * c.n_q_heads * 2))) return rc;
+  if ((rc = dalloc(&w->d_norm_counters, (size_t)2 * L + 2))) return rc;
+  CUDA_TRY(cudaMemsetAsync(w->d_norm_counters, 0, ((size_t)2 * L + 2) * 4, w->stream));
+  {
+    const char* e = getenv("MQ_FUSE_NORM");
+    w->fuse_norm = !(e && e[0] == '0');
+  }
   if ((rc = dalloc(&w->d_split_counter, (size_t)MBp * c.n_kv_heads))) return rc;
   CUDA_TRY(cudaMemsetAsync(w->d_split_counter, 0, (size_t)MBp * c.n_kv_heads * 4, w->stream));
   if ((rc = dalloc(&w->inv_freq, D / 2))) return rc;
@@ -206,6 +212,13 @@ static int build_plans(mq_worker* w, PassPlans* pp, int T, bool decode) {
       set_last_error("gemm_plan failed (layer %d, T=%d)", l, T);
       return MQ_ERR_CUDA;
     }
+    if (decode && w->fuse_norm && T <= 64 && !pp->qkv[l].streamk && !pp->gate_up[l].streamk) {
+      pp->fused_norm = true;
+      gemm_plan_fuse_norm(&pp->qkv[l], w->h, (const float*)w->proj_part, l == 0 ? 0 : pp->s_down, (long long)MBp * H,
+                          lw.attn_norm, w->x, H, c.rms_eps, w->d_norm_counters + 2 * l);
+      gemm_plan_fuse_norm(&pp->gate_up[l], w->h, (const float*)w->proj_part, pp->s_o, (long long)MBp * H, lw.mlp_norm,
+                          w->x, H, c.rms_eps, w->d_norm_counters + 2 * l + 1);
+    }
   }
   return MQ_OK;
 }
@@ -253,12 +266,15 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
   const int MBp = round_up(w->MB, 16);
   const bool f32p = a.decode;
   uint64_t nl = 0;
-  launch_embed(lc, a.tok, w->embed, w->h, a.T, H); ++nl;
+  launch_embed(lc, a.tok, w->embed, w->h, a.T, H, w->d_norm_counters, 2 * c.n_layers); ++nl;
+  const bool fused = a.decode && pp->fused_norm;
   int prev_planes = 0;
   for (int l = 0; l < c.n_layers; ++l) {
     const LayerWeights& lw = w->layers[l];
-    launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, prev_planes, (long long)MBp * H, lw.attn_norm, w->x, nullptr, a.T,
-                       H, c.rms_eps); ++nl;
+    if (!fused) {
+      launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, prev_planes, (long long)MBp * H, lw.attn_norm, w->x, nullptr, a.T,
+                         H, c.rms_eps); ++nl;
+    }
     if (gemm_launch(pp->qkv[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     RopeKvParams rp;
     rp.qkv = w->qkv_part; rp.qkv_is_f32 = f32p; rp.n_planes = pp->s_qkv; rp.plane_stride = (long long)MBp * w->qkv_dim;
@@ -276,8 +292,10 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
     if (a.decode) { launch_attn_decode(lc, ap, a.T); ++nl; }
     else { launch_attn_prefill(lc, ap, a.n_tiles); ++nl; }
     if (gemm_launch(pp->o[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
-    launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, pp->s_o, (long long)MBp * H, lw.mlp_norm, w->x, nullptr, a.T, H,
-                       c.rms_eps); ++nl;
+    if (!fused) {
+      launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, pp->s_o, (long long)MBp * H, lw.mlp_norm, w->x, nullptr, a.T, H,
+                         c.rms_eps); ++nl;
+    }
     if (gemm_launch(pp->gate_up[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     if (gemm_launch(pp->down[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     prev_planes = pp->s_down;
@@ -595,7 +613,7 @@ static int launch_decode(mq_worker* w) {
     // graph wrote to the fixed row kRing-1; move it to this step's ring slot on the host side copy
     cudaMemcpyAsync(w->h_out_ring + (size_t)ring * MBp, w->d_out_ring + (size_t)(kRing - 1) * MBp, Bcap * 4,
                     cudaMemcpyDeviceToHost, w->stream);
-    nl = (uint64_t)(1 + w->cfg.n_layers * 8 + 3);
+    nl = (uint64_t)(1 + w->cfg.n_layers * (get_plans(w, Bcap, true)->fused_norm ? 6 : 8) + 3);
   } else {
     int rc = decode_body(w, Bcap, n_splits, ring, &nl);
     if (rc) return rc;
@@ -1000,7 +1018,7 @@ void mq_worker_close(mq_worker* w) {
   void* bufs[] = {w->k_cache, w->v_cache, w->h, w->x, w->q, w->attn, w->act, w->x_last, w->qkv_part, w->proj_part,
                   w->logits, w->part_o, w->part_ml, w->inv_freq, w->d_tok, w->d_pos_tok, w->d_slot_tok, w->d_last_idx,
                   w->d_dst_slot, w->d_tiles, w->d_cur_token, w->d_pos, w->d_active, w->d_block_table, w->d_identity,
-                  w->d_out_ring, w->d_split_counter};
+                  w->d_out_ring, w->d_split_counter, w->d_norm_counters};
   for (void* b : bufs) if (b) cudaFree(b);
   void* pinned[] = {w->h_pos, w->h_active, w->h_block_table, w->h_stage, w->h_out_ring};
   for (void* b : pinned) if (b) cudaFreeHost(b);

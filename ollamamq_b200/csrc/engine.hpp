@@ -33,6 +33,7 @@ struct PassPlans {
   int T = 0;
   bool decode = false;
   int s_qkv = 1, s_o = 1, s_down = 1;
+  bool fused_norm = false;  // decode: norm1/norm2 run inside the QKV / gate-up GEMM prologues
   std::vector<GemmPlan> qkv, o, gate_up, down;  // per layer
 };
 
@@ -88,6 +89,8 @@ struct mq_worker {
   int *d_cur_token = nullptr, *d_pos = nullptr, *d_active = nullptr, *d_block_table = nullptr, *d_identity = nullptr;
   int* d_out_ring = nullptr;  // [kRing][MB]
   int* d_split_counter = nullptr;  // [MB][n_kv] arrival counters of the split-KV decode attention
+  int* d_norm_counters = nullptr;  // [2 * layers] arrival counters of the fused norm prologues (zeroed by embed)
+  bool fuse_norm = true;
   // pinned host mirrors / staging
   int *h_pos = nullptr, *h_active = nullptr, *h_block_table = nullptr;
   int* h_stage = nullptr;     // ring of staging areas for metadata uploads

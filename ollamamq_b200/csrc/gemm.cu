@@ -211,6 +211,23 @@ static bool decode_tiles_shallow() {
   return v == 1;
 }
 
+void gemm_plan_fuse_norm(GemmPlan* g, float* h, const float* partial, int n_planes, long long plane_stride,
+                         const void* gamma, void* x, int H, float eps, int* counter) {
+  if (g->streamk || g->p.n_tiles != 1) return;  // decode tile widths, split-K kernel only
+  g->p.norm_h = h;
+  g->p.norm_partial = partial;
+  g->p.norm_planes = n_planes;
+  g->p.norm_plane_stride = plane_stride;
+  g->p.norm_gamma = gamma;
+  g->p.norm_x = x;
+  g->p.norm_H = H;
+  g->p.norm_eps = eps;
+  g->p.norm_counter = counter;
+  const int ctas = g->p.m_tiles * g->splits;
+  // rows go to the lowest CTA ids only: those are scheduled first, so the spin in the producers cannot starve them
+  g->p.norm_ctas = ctas < 96 ? ctas : 96;
+}
+
 int gemm_pick_bn(int T) {
   if (T <= 16) return 16;
   if (T <= 32) return 32;
@@ -236,6 +253,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   if (!tmap_encode_2d(&g->tmA, W, (uint64_t)w_rows, (uint64_t)K, kBlockM)) return false;
   if (!tmap_encode_2d(&g->tmB, X, (uint64_t)x_rows_alloc, (uint64_t)K, (uint32_t)g->bn)) return false;
   if (!tmap_encode_out(&g->tmC, out, epi, n_out, T, ldo, splits, split_stride, g->bn)) return false;
+  g->p = GemmParams{};
   g->p.out = out;
   g->p.split_stride = split_stride;
   g->p.ldo = ldo;

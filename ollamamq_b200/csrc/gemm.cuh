@@ -39,6 +39,17 @@ struct GemmParams {
   int m_tiles, n_tiles;    // tile grid; blockIdx.x = linear tile id, rasterised in groups of `group_m` weight tiles
   int group_m;             // so that one wave of 148 CTAs touches ~group_m weight tiles x ~148/group_m token tiles
   unsigned long long w_policy;  // L2 policy for weight tiles: stream-once (decode) vs re-used inside a wave (prefill)
+  // ---- optional fused prologue (decode): h += sum(partial planes); x = RMSNorm(h) * gamma, where x IS this GEMM's
+  // activation operand.  Row r is normalised by the epilogue warps of CTA (r % norm_ctas) while every producer
+  // already streams weights; producers wait for `norm_counter` to reach T before they load activations.
+  float* norm_h;                 // nullptr = no fused prologue
+  const float* norm_partial;     // fp32 planes [n_planes][plane_stride] (row-major [T][H])
+  const void* norm_gamma;        // bf16 [H]
+  void* norm_x;                  // bf16 [T][H]
+  int* norm_counter;             // zero at kernel start, += 1 per finished row
+  long long norm_plane_stride;
+  int norm_planes, norm_H, norm_ctas;
+  float norm_eps;
 };
 
 constexpr int kGemmThreads = 192;
@@ -140,6 +151,11 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (kDual) tma_load_2d(st + kATileBytes, &tmA, &full_bar[s], (kb0 + s) * kBlockK, m0 + p.a2_row_off, p.w_policy);
       }
       pdl_wait();  // activations are produced by the previous kernel
+      if (p.norm_h) {  // ... or by the fused norm prologue of this very grid
+        while (ld_acquire_s32(p.norm_counter) < p.T) {
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");  // rows were written through the generic proxy
+      }
       for (int s = 0; s < npre; ++s)
         tma_load_2d(smem + s * STAGE_BYTES + B_OFF, &tmB, &full_bar[s], (kb0 + s) * kBlockK, n0, kEvictLast);
       for (int kb = npre; kb < nkb; ++kb) {
@@ -179,6 +195,52 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // The accumulator is transposed on its way out: each thread owns one feature (TMEM lane) and walks the
     // token columns, writing a [token][128 features] tile into the (now idle) pipeline smem; one TMA tensor
     // store then moves the whole tile to global memory, coalesced and clipped to the tensor bounds.
+    if (p.norm_h) {
+      // ---- fused prologue: residual add + split-K reduce + RMSNorm of the rows this CTA owns (128 threads)
+      const int cta = blockIdx.x + gridDim.x * blockIdx.z;
+      if (cta < p.norm_ctas) {
+        pdl_wait();  // the planes come from the previous kernel
+        float* red = reinterpret_cast<float*>(tmem_slot + 2);  // 4 floats behind the barriers
+        const int tid = threadIdx.x - 64;                      // 0..127
+        const int nvec = p.norm_H >> 2;                        // float4 per row
+        for (int r = cta; r < p.T; r += p.norm_ctas) {
+          float4 v[16];  // H <= 8192
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int i4 = tid + j * 128;
+            if (i4 < nvec) {
+              float4 a = reinterpret_cast<const float4*>(p.norm_h + (size_t)r * p.norm_H)[i4];
+              for (int s2 = 0; s2 < p.norm_planes; ++s2) {
+                const float4 b = reinterpret_cast<const float4*>(p.norm_partial + s2 * p.norm_plane_stride + (size_t)r * p.norm_H)[i4];
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+              }
+              v[j] = a;
+              ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+              reinterpret_cast<float4*>(p.norm_h + (size_t)r * p.norm_H)[i4] = a;
+            }
+          }
+          ss = warp_sum(ss);
+          if (lane == 0) red[warp - 2] = ss;
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          const float rstd = rsqrtf((red[0] + red[1] + red[2] + red[3]) / (float)p.norm_H + p.norm_eps);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int i4 = tid + j * 128;
+            if (i4 < nvec) {
+              const uint2 gm = reinterpret_cast<const uint2*>(p.norm_gamma)[i4];
+              uint2 o;
+              o.x = pack_bf16(v[j].x * rstd * bf16_lo(gm.x), v[j].y * rstd * bf16_hi(gm.x));
+              o.y = pack_bf16(v[j].z * rstd * bf16_lo(gm.y), v[j].w * rstd * bf16_hi(gm.y));
+              reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.norm_x) + (size_t)r * p.norm_H)[i4] = o;
+            }
+          }
+          __threadfence();
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (tid == 0) atomicAdd(p.norm_counter, 1);
+        }
+      }
+    }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int q = warp & 3;  // TMEM lane quarter this warp may read

@@ -43,6 +43,9 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
                int epi, void* out, int ldo, int splits, long long split_stride, int a2_row_off,
                const StreamKWorkspace* sk = nullptr);  // with sk (and T <= 64): stream-K, `splits` is ignored (1 plane)
 
+// Attach the fused residual-add + RMSNorm prologue (decode only; split-K kernel only): see GemmParams::norm_*.
+void gemm_plan_fuse_norm(GemmPlan* g, float* h, const float* partial, int n_planes, long long plane_stride,
+                         const void* gamma, void* x, int H, float eps, int* counter);
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc);
 void gemm_set_attrs();
 

@@ -40,9 +40,11 @@ static void launch_k(const LaunchCfg& lc, void (*kern)(KArgs...), dim3 grid, dim
 // embedding gather
 // ------------------------------------------------------------------------------------------------
 __global__ void embed_kernel(const int* __restrict__ token_ids, const __nv_bfloat16* __restrict__ embed,
-                             float* __restrict__ h, int H) {
+                             float* __restrict__ h, int H, int* __restrict__ zero, int n_zero) {
   pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
   pdl_wait();
+  if (blockIdx.x == 0)  // first kernel of a pass: re-arm the arrival counters of the fused norm prologues
+    for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero[i] = 0;
   const int t = blockIdx.x;
   const int tok = token_ids[t];
   const uint4* src = reinterpret_cast<const uint4*>(embed + (size_t)tok * H);
@@ -53,8 +55,9 @@ __global__ void embed_kernel(const int* __restrict__ token_ids, const __nv_bfloa
     dst[2 * i + 1] = make_float4(bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w));
   }
 }
-void launch_embed(const LaunchCfg& lc, const int* token_ids, const __nv_bfloat16* embed, float* h, int T, int H) {
-  launch_k(lc, embed_kernel, dim3(T), dim3(128), 0, token_ids, embed, h, H);
+void launch_embed(const LaunchCfg& lc, const int* token_ids, const __nv_bfloat16* embed, float* h, int T, int H,
+                  int* zero, int n_zero) {
+  launch_k(lc, embed_kernel, dim3(T), dim3(128), 0, token_ids, embed, h, H, zero, n_zero);
 }
 
 // ------------------------------------------------------------------------------------------------

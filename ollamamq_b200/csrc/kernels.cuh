@@ -15,7 +15,8 @@ struct LaunchCfg {
 };
 
 // h_f32[t,:] = embed[token_ids[t], :]
-void launch_embed(const LaunchCfg& lc, const int* token_ids, const __nv_bfloat16* embed, float* h, int T, int H);
+void launch_embed(const LaunchCfg& lc, const int* token_ids, const __nv_bfloat16* embed, float* h, int T, int H,
+                  int* zero = nullptr, int n_zero = 0);  // also zeroes `zero[0..n_zero)` (arrival counters)
 
 // v = h[src,:] + sum_s partial[s][src,:];  if (!row_idx) h[src,:] = v;  x[row,:] = bf16(v * rsqrt(mean v^2 + eps) * gamma)
 // partial_is_f32: planes are fp32 (decode split-K) else one bf16 plane (prefill).

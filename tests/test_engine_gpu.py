@@ -103,6 +103,32 @@ def test_generation_single_and_concurrent(pdl, graphs):
             mq.lib.mq_req_release(s.handle)
 
 
+def test_generation_without_fused_norm_prologue(monkeypatch):
+    """MQ_FUSE_NORM=0: the standalone add+RMSNorm kernels instead of the GEMM-prologue fusion (both must hold parity)."""
+    monkeypatch.setenv("MQ_FUSE_NORM", "0")
+    cfg = MID
+    w = R.make_weights(cfg, seed=23, device="cuda")
+    g = torch.Generator().manual_seed(4)
+    prompts = [torch.randint(0, cfg["vocab"], (n,), generator=g).tolist() for n in (9, 70, 33)]
+    with _open(cfg, w, max_batch=4, use_pdl=1, use_graphs=1) as wk:
+        streams = [wk.submit(mq.Stream(), prompt_tokens=p, max_new_tokens=10) for p in prompts]
+        for p, s in zip(prompts, streams):
+            s.wait(120)
+            assert s.rc == 0, s.err
+            _check_greedy(w, cfg, p, s.tokens())
+            mq.lib.mq_req_release(s.handle)
+        n_fused_off = wk.stats()["kernel_launches"]
+    monkeypatch.setenv("MQ_FUSE_NORM", "1")
+    with _open(cfg, w, max_batch=4, use_pdl=1, use_graphs=1) as wk:
+        streams = [wk.submit(mq.Stream(), prompt_tokens=p, max_new_tokens=10) for p in prompts]
+        for p, s in zip(prompts, streams):
+            s.wait(120)
+            assert s.rc == 0, s.err
+            _check_greedy(w, cfg, p, s.tokens())
+            mq.lib.mq_req_release(s.handle)
+        assert wk.stats()["kernel_launches"] < n_fused_off      # two launches per layer fewer in every decode step
+
+
 def test_cancel_timeout_and_framing():
     cfg = MID
     w = R.make_weights(cfg, seed=31, device="cuda")
