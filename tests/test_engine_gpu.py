@@ -103,8 +103,9 @@ def test_generation_single_and_concurrent(pdl, graphs):
             mq.lib.mq_req_release(s.handle)
 
 
-def test_generation_without_fused_norm_prologue(monkeypatch):
-    """MQ_FUSE_NORM=0: the standalone add+RMSNorm kernels instead of the GEMM-prologue fusion (both must hold parity)."""
+def test_generation_with_and_without_fused_norm_prologue(monkeypatch):
+    """MQ_FUSE_NORM=1 moves add+RMSNorm into the consuming GEMM's prologue (opt-in: measured slower); both paths
+    must hold parity."""
     monkeypatch.setenv("MQ_FUSE_NORM", "0")
     cfg = MID
     w = R.make_weights(cfg, seed=23, device="cuda")
