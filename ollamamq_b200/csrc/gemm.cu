@@ -117,7 +117,26 @@ static cudaError_t launch_sk_bn(const GemmPlan& g, const LaunchCfg& lc) {
   }
 }
 
+template <int BN, int EPI>
+static cudaError_t launch_pk(const GemmPlan& g, const LaunchCfg& lc) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g.pk.n_ctas);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = gemm_smem_bytes(BN, EPI, true);
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lc.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, gemm_persist_kernel<BN, EPI>, g.tmA, g.tmB, g.pk);
+}
+
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
+  if (g.persist) {
+    if (g.bn == 256) return g.epi == EPI_F32 ? launch_pk<256, EPI_F32>(g, lc) : launch_pk<256, EPI_BF16>(g, lc);
+    return g.epi == EPI_F32 ? launch_pk<128, EPI_F32>(g, lc) : launch_pk<128, EPI_BF16>(g, lc);
+  }
   if (g.streamk) switch (g.epi) {
       case EPI_F32: return launch_sk_bn<EPI_F32>(g, lc);
       case EPI_BF16: return launch_sk_bn<EPI_BF16>(g, lc);
@@ -162,6 +181,26 @@ void gemm_set_attrs() {
   set_attrs_sk<16, EPI_F32>(); set_attrs_sk<32, EPI_F32>(); set_attrs_sk<64, EPI_F32>();
   set_attrs_sk<16, EPI_BF16>(); set_attrs_sk<32, EPI_BF16>(); set_attrs_sk<64, EPI_BF16>();
   set_attrs_sk<16, EPI_SILU_BF16>(); set_attrs_sk<32, EPI_SILU_BF16>(); set_attrs_sk<64, EPI_SILU_BF16>();
+  cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_BF16, true));
+  cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_F32, true));
+  cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_BF16, true));
+  cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_F32, true));
+}
+
+// MQ_PERSIST=0 turns the persistent prefill kernel off (A/B switch)
+static bool persist_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MQ_PERSIST");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+static int device_sm_count() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
 }
 
 // MQ_STREAMK: "1" = every decode GEMM, "0" = none, unset = auto.  Measured on B200 (r01, Llama-3-8B, B=64):
@@ -272,6 +311,17 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   if (gm > g->p.m_tiles) gm = g->p.m_tiles;
   g->p.group_m = g->p.n_tiles == 1 ? g->p.m_tiles : gm;
   g->p.w_policy = g->p.n_tiles == 1 ? kEvictFirst : kEvictNormal;  // decode streams weights exactly once
+  g->persist = false;
+  if (!g->streamk && epi != EPI_SILU_BF16 && g->bn >= 128 && splits == 1 && persist_enabled()) {
+    const int sms = device_sm_count();
+    const int tiles = g->p.m_tiles * g->p.n_tiles;
+    if (tiles >= 2 * sms) {  // at least two tiles per CTA, otherwise there is nothing to overlap
+      g->persist = true;
+      g->pk.out = out; g->pk.ldo = ldo; g->pk.T = T; g->pk.n_out = n_out; g->pk.k_blocks = kb;
+      g->pk.m_tiles = g->p.m_tiles; g->pk.n_tiles = g->p.n_tiles; g->pk.group_m = g->p.group_m;
+      g->pk.n_ctas = sms; g->pk.w_policy = g->p.w_policy;
+    }
+  }
   if (g->streamk) {
     const long long U = (long long)g->p.m_tiles * kb;
     g->sk.out = out;

@@ -2,6 +2,7 @@
 #pragma once
 #include "gemm.cuh"
 #include "gemm_streamk.cuh"
+#include "gemm_persist.cuh"
 #include "kernels.cuh"
 
 namespace mq {
@@ -15,6 +16,8 @@ struct GemmPlan {
   int epi;
   int splits;
   bool deep;  // pipeline depth variant (see gemm_stages)
+  bool persist;      // prefill regime, single accumulator: persistent double-buffered kernel (gemm_persist.cuh)
+  PersistParams pk;
   bool streamk;      // decode regime: persistent stream-K kernel (gemm_streamk.cuh), output is one complete plane
   StreamKParams sk;
 };

@@ -85,6 +85,24 @@ def test_gemm_silu_dual(T, I, K):
     assert err < 8e-3, f"rel err {err}"
 
 
+@pytest.mark.parametrize("T,n_out,K,epi", [(4608, 6144, 512, 1), (4500, 6100, 256, 1), (2304, 16384, 128, 0),
+                                           (1100, 32000, 192, 1)])
+def test_gemm_persistent_prefill(T, n_out, K, epi):
+    """>= 2 tiles per SM: gemm_plan picks the persistent double-buffered kernel (gemm_persist.cuh); BN = 256 and
+    ragged last tiles in both dimensions."""
+    m = _lib()
+    g = torch.Generator(device="cuda").manual_seed(T + n_out)
+    W = (torch.randn(n_out, K, device=dev(), generator=g) * 0.05).bfloat16()
+    X = torch.randn(T, K, device=dev(), generator=g).bfloat16()
+    ref = X.float() @ W.float().T
+    out = torch.full((T, n_out), float("nan"), device=dev(), dtype=torch.float32 if epi == 0 else torch.bfloat16)
+    rc = m.lib.mq_debug_gemm(P(W), n_out, n_out, K, P(X), T, T, epi, P(out), n_out, 1, T * n_out, 0, 1, 0, None)
+    assert rc == 0, m.last_error()
+    assert torch.isfinite(out.float()).all(), "non-finite / unwritten outputs"
+    err = _relerr(out, ref)
+    assert err < (2e-3 if epi == 0 else 6e-3), f"rel err {err}"
+
+
 SK_CASES = [
     # T, n_out, K, epi
     (64, 6144, 4096, 0),     # QKV decode shape: 48 tiles x 64 k-blocks over 148 CTAs
