@@ -132,7 +132,28 @@ static cudaError_t launch_pk(const GemmPlan& g, const LaunchCfg& lc) {
   return cudaLaunchKernelEx(&cfg, gemm_persist_kernel<BN, EPI>, g.tmA, g.tmB, g.pk);
 }
 
+template <int EPI>
+static cudaError_t launch_c2(const GemmPlan& g, const LaunchCfg& lc) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * g.c2.m_tiles * g.c2.n_tiles);  // cluster dims (2,1,1) are compiled into the kernel
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = c2_smem_bytes(EPI);
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lc.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, gemm_2cta_kernel<EPI>, g.tmA, g.tmB, g.tmC, g.c2);
+}
+
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
+  if (g.twocta) switch (g.epi) {
+      case EPI_F32: return launch_c2<EPI_F32>(g, lc);
+      case EPI_BF16: return launch_c2<EPI_BF16>(g, lc);
+      case EPI_SILU_BF16: return launch_c2<EPI_SILU_BF16>(g, lc);
+      default: return cudaErrorInvalidValue;
+    }
   if (g.persist) {
     if (g.bn == 256) return g.epi == EPI_F32 ? launch_pk<256, EPI_F32>(g, lc) : launch_pk<256, EPI_BF16>(g, lc);
     return g.epi == EPI_F32 ? launch_pk<128, EPI_F32>(g, lc) : launch_pk<128, EPI_BF16>(g, lc);
@@ -181,12 +202,24 @@ void gemm_set_attrs() {
   set_attrs_sk<16, EPI_F32>(); set_attrs_sk<32, EPI_F32>(); set_attrs_sk<64, EPI_F32>();
   set_attrs_sk<16, EPI_BF16>(); set_attrs_sk<32, EPI_BF16>(); set_attrs_sk<64, EPI_BF16>();
   set_attrs_sk<16, EPI_SILU_BF16>(); set_attrs_sk<32, EPI_SILU_BF16>(); set_attrs_sk<64, EPI_SILU_BF16>();
+  cudaFuncSetAttribute(gemm_2cta_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_F32));
+  cudaFuncSetAttribute(gemm_2cta_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_BF16));
+  cudaFuncSetAttribute(gemm_2cta_kernel<EPI_SILU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_SILU_BF16));
   cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_BF16, true));
   cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_F32, true));
   cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_BF16, true));
   cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_F32, true));
 }
 
+// MQ_2CTA=0 turns the cta_group::2 prefill kernel off (A/B switch)
+static bool twocta_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MQ_2CTA");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 // MQ_PERSIST=0 turns the persistent prefill kernel off (A/B switch)
 static bool persist_enabled() {
   static int v = -1;
@@ -311,8 +344,20 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   if (gm > g->p.m_tiles) gm = g->p.m_tiles;
   g->p.group_m = g->p.n_tiles == 1 ? g->p.m_tiles : gm;
   g->p.w_policy = g->p.n_tiles == 1 ? kEvictFirst : kEvictNormal;  // decode streams weights exactly once
+  g->twocta = !g->streamk && g->bn == 256 && splits == 1 && n_out % 256 == 0 && twocta_enabled();
+  if (g->twocta) {
+    // the pair computes 256 features x 256 tokens: every CTA stages only its own 128-token half of the activation tile
+    if (!tmap_encode_2d(&g->tmB, X, (uint64_t)x_rows_alloc, (uint64_t)K, 128)) return false;
+    g->c2.T = T; g->c2.n_out = n_out; g->c2.k_blocks = kb; g->c2.a2_row_off = a2_row_off;
+    g->c2.m_tiles = n_out / 256;
+    g->c2.n_tiles = (T + 255) / 256;
+    int gm2 = (int)(sqrt(74.0 * 256.0 / (epi == EPI_SILU_BF16 ? 512.0 : 256.0)) + 0.5);
+    if (gm2 > g->c2.m_tiles) gm2 = g->c2.m_tiles;
+    g->c2.group_m = gm2 < 1 ? 1 : gm2;
+    g->c2.w_policy = g->p.w_policy;
+  }
   g->persist = false;
-  if (!g->streamk && epi != EPI_SILU_BF16 && g->bn >= 128 && splits == 1 && persist_enabled()) {
+  if (!g->twocta && !g->streamk && epi != EPI_SILU_BF16 && g->bn >= 128 && splits == 1 && persist_enabled()) {
     const int sms = device_sm_count();
     const int tiles = g->p.m_tiles * g->p.n_tiles;
     if (tiles >= 2 * sms) {  // at least two tiles per CTA, otherwise there is nothing to overlap

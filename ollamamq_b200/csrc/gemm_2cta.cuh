@@ -1,0 +1,250 @@
+// 2-CTA (cta_group::2) variant of the prefill tcgen05 GEMM: one 256-feature x 256-token tile per CTA PAIR.
+//
+// Why (r01 ncu, prefill tiles): the 1-CTA kernel keeps the tensor pipe only 57-79 % busy and a persistent,
+// epilogue-overlapped variant changed nothing, i.e. the MMAs wait on operands, not on epilogues.  Per 128x256x16
+// MMA an SM reads 12 KiB of operands from shared memory while TMA writes another 12 KiB per 128 cycles into the
+// same memory.  With cta_group::2 the pair computes a 256x256 tile: each CTA stages its OWN 128 weight rows and
+// only HALF of the token tile (the tensor cores read the other half from the peer's shared memory), so the bytes
+// written into each SM's shared memory (and pulled through L2) per MMA drop by a third (single accumulator) or a
+// quarter (gate/up dual accumulator), and the stage count rises from 4/3 to 6/4.
+//
+// Protocol (CTA rank 0 = leader):
+//   * both producers issue cp.async.bulk.tensor ... .cta_group::2 loads that complete_tx on the LEADER's full barrier
+//     (count 2: leader arrive.expect_tx(2 x stage bytes) + one remote arrive from the peer's producer);
+//   * the leader's MMA thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256) and releases a stage with a
+//     multicast tcgen05.commit that arrives on the empty barrier of BOTH CTAs; the final commit arrives on both
+//     tmem_full barriers;
+//   * each CTA drains its own 128 TMEM lanes (its half of the features) and TMA-stores its half tile.
+#pragma once
+#include "gemm.cuh"
+
+namespace mq {
+
+struct TwoCtaParams {
+  int T, n_out, k_blocks, a2_row_off;
+  int m_tiles, n_tiles, group_m;  // tiles of 256 features x 256 tokens
+  unsigned long long w_policy;
+};
+
+__host__ __device__ constexpr int c2_stage_bytes(int epi) { return kATileBytes * (epi == EPI_SILU_BF16 ? 2 : 1) + 128 * kBlockK * 2; }
+__host__ __device__ constexpr int c2_stages(int epi) {
+  int s = (200 * 1024) / c2_stage_bytes(epi);
+  return s > 8 ? 8 : s;
+}
+__host__ __device__ constexpr int c2_smem_bytes(int epi) { return c2_stages(epi) * c2_stage_bytes(epi) + 1024 + 256; }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> leader's copy
+__device__ __forceinline__ void tma_load_2d_2cta(void* smem_dst, const void* tmap, uint64_t* bar_leader_local, int c0,
+                                                 int c1, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar_leader_local) & kPeerBitMask),
+        "r"(c0), "r"(c1), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {  // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const TwoCtaParams p) {
+  constexpr bool kDual = (EPI == EPI_SILU_BF16);
+  constexpr int BN = 256;                       // token columns of the pair's accumulator
+  constexpr int STAGES = c2_stages(EPI);
+  constexpr int STAGE_BYTES = c2_stage_bytes(EPI);
+  constexpr int B_OFF = kATileBytes * (kDual ? 2 : 1);
+  constexpr uint32_t TMEM_COLS = kDual ? 512u : 256u;
+  constexpr uint32_t IDESC = umma_idesc_bf16(256, BN);
+  static_assert(gemm_out_tile_bytes(BN, EPI) <= STAGES * STAGE_BYTES, "epilogue tile is staged in the pipeline smem");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // used in the leader only
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader_cta = rank == 0;
+  int tile_m, tile_n;
+  {
+    const int pid = blockIdx.x >> 1;
+    const int per_group = p.group_m * p.n_tiles;
+    const int first_m = (pid / per_group) * p.group_m;
+    const int gsz = min(p.m_tiles - first_m, p.group_m);
+    const int r = pid % per_group;
+    tile_m = first_m + r % gsz;
+    tile_n = r / gsz;
+  }
+  const int m0 = tile_m * 256 + (int)rank * kBlockM;  // my 128 weight rows
+  const int n0 = tile_n * BN;                         // the pair's 256 tokens
+  const int nb0 = n0 + (int)rank * 128;               // my half of the token tile
+  const int nkb = p.k_blocks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx + the peer producer's remote arrive
+      mbar_init(&empty_bar[s], 1);  // multicast commit from the leader's MMA thread
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  cluster_sync_all();  // barrier inits + TMEM allocation visible to both CTAs before any remote arrive / multicast
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer (both CTAs): own weight rows + own half of the token tile ----------------
+      auto arm = [&](int s) {
+        if (leader_cta) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
+        else mbar_arrive_remote(&full_bar[s], 0);
+      };
+      auto load_a = [&](int s, int kb) {
+        uint8_t* st = smem + s * STAGE_BYTES;
+        tma_load_2d_2cta(st, &tmA, &full_bar[s], kb * kBlockK, m0, p.w_policy);
+        if (kDual) tma_load_2d_2cta(st + kATileBytes, &tmA, &full_bar[s], kb * kBlockK, m0 + p.a2_row_off, p.w_policy);
+      };
+      const int npre = nkb < STAGES ? nkb : STAGES;
+      for (int s = 0; s < npre; ++s) {
+        arm(s);
+        load_a(s, s);
+      }
+      pdl_wait();  // activations are produced by the previous kernel
+      for (int s = 0; s < npre; ++s)
+        tma_load_2d_2cta(smem + s * STAGE_BYTES + B_OFF, &tmB, &full_bar[s], s * kBlockK, nb0, kEvictLast);
+      for (int kb = npre; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        arm(s);
+        load_a(s, kb);
+        tma_load_2d_2cta(smem + s * STAGE_BYTES + B_OFF, &tmB, &full_bar[s], kb * kBlockK, nb0, kEvictLast);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader_cta) {
+      // ---------------- MMA issuer: leader CTA only, one thread for the pair ----------------
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+        const uint32_t b_addr = a_addr + B_OFF;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t db = umma_desc_sw128(b_addr + k * 32);
+          const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+          umma_bf16_2cta(tmem_base, umma_desc_sw128(a_addr + k * 32), db, IDESC, acc);
+          if (kDual) umma_bf16_2cta(tmem_base + BN, umma_desc_sw128(a_addr + kATileBytes + k * 32), db, IDESC, acc);
+        }
+        umma_commit_2cta(&empty_bar[s]);  // stage s reusable in BOTH CTAs once these MMAs retire
+      }
+      umma_commit_2cta(tmem_full_bar);  // accumulators complete, in both CTAs
+    }
+  } else {
+    // ---------------- epilogue (both CTAs): my 128 TMEM lanes = my 128 features, 256 token columns ----------------
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint8_t* stg = smem;  // every MMA of the pair has retired: all stage buffers of this CTA are free
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      if (n0 + c0 >= p.T) break;
+      uint32_t v[16];
+      tmem_ld16(t_lane + c0, v);
+      if constexpr (kDual) {
+        uint32_t u[16];
+        tmem_ld16(t_lane + BN + c0, u);
+        tmem_ld_wait();
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(stg) + c0 * kBlockM + row;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float g = __uint_as_float(v[j]);
+          o[j * kBlockM] = __float2bfloat16(g / (1.0f + __expf(-g)) * __uint_as_float(u[j]));
+        }
+      } else {
+        tmem_ld_wait();
+        if constexpr (EPI == EPI_F32) {
+          float* o = reinterpret_cast<float*>(stg) + c0 * kBlockM + row;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j * kBlockM] = __uint_as_float(v[j]);
+        } else {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(stg) + c0 * kBlockM + row;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) o[j * kBlockM] = __float2bfloat16(__uint_as_float(v[j]));
+        }
+      }
+    }
+    fence_proxy_async();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (warp == 2 && lane == 0) {
+      if constexpr (EPI == EPI_F32) tma_store_3d(&tmC, stg, m0, n0, 0);
+      else tma_store_2d(&tmC, stg, m0, n0);
+      tma_store_commit();
+      tma_store_wait_read();
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // neither CTA may free TMEM / exit while the pair's MMAs or epilogues still use its memory
+  if (warp == 1) tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
+}
+
+}  // namespace mq

@@ -3,6 +3,7 @@
 #include "gemm.cuh"
 #include "gemm_streamk.cuh"
 #include "gemm_persist.cuh"
+#include "gemm_2cta.cuh"
 #include "kernels.cuh"
 
 namespace mq {
@@ -16,6 +17,8 @@ struct GemmPlan {
   int epi;
   int splits;
   bool deep;  // pipeline depth variant (see gemm_stages)
+  bool twocta;       // prefill regime: cta_group::2 kernel (gemm_2cta.cuh); tmB then has a 128-row box
+  TwoCtaParams c2;
   bool persist;      // prefill regime, single accumulator: persistent double-buffered kernel (gemm_persist.cuh)
   PersistParams pk;
   bool streamk;      // decode regime: persistent stream-K kernel (gemm_streamk.cuh), output is one complete plane
