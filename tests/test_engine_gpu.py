@@ -257,3 +257,19 @@ def test_http_end_to_end_over_gpu_worker():
             assert d.user_stats("alice")["processed"] == 1 and d.user_stats("bob")["processed"] == 3
         finally:
             d.close()
+
+
+def test_qwen25_7b_geometry_logits():
+    """BASELINE configs[2] geometry (Qwen2.5-7B: hidden 3584, 28 q / 4 kv heads -> GQA group 7, q/k/v bias,
+    ffn 18944 = 148 weight tiles) with 4 layers: engine logits vs the fp32 oracle on identical weights."""
+    cfg = dict(R.QWEN25_7B, n_layers=4, vocab=32768)
+    w = R.make_weights(cfg, seed=61, device="cuda")
+    toks = torch.randint(0, cfg["vocab"], (200,), generator=torch.Generator().manual_seed(6)).tolist()
+    ref = R.forward(w, cfg, toks, torch.float32).cpu().numpy()
+    with _open(cfg, w, max_batch=8, max_seq=512, max_prefill_tokens=256) as wk:
+        got = wk.forward_logits(toks, all_positions=True)
+        scale = np.abs(ref).max()
+        err = np.abs(got - ref).max()
+        assert err <= TOL * scale, (err, scale)
+        gen = wk.generate(toks[:77], 16)
+        _check_greedy(w, cfg, toks[:77], gen)
