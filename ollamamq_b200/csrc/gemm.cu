@@ -136,7 +136,7 @@ template <int EPI>
 static cudaError_t launch_c2(const GemmPlan& g, const LaunchCfg& lc) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * g.c2.m_tiles * g.c2.n_tiles);  // cluster dims (2,1,1) are compiled into the kernel
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(kC2Threads);
   cfg.dynamicSmemBytes = c2_smem_bytes(EPI);
   cfg.stream = lc.stream;
   cudaLaunchAttribute attr[1];

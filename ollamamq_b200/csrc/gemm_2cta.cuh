@@ -89,8 +89,10 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
 
+constexpr int kC2Threads = 64 + 256;  // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC2Threads, 1)
 gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const TwoCtaParams p) {
   constexpr bool kDual = (EPI == EPI_SILU_BF16);
@@ -200,12 +202,13 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ---------------- epilogue (both CTAs): my 128 TMEM lanes = my 128 features, 256 token columns ----------------
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int q = warp & 3;
+    const int q = warp & 3;                 // TMEM lane quarter (warps w and w+4 share one)
+    const int chalf = (warp - 2) >> 2;      // which half of the 256 token columns this warp drains
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint8_t* stg = smem;  // every MMA of the pair has retired: all stage buffers of this CTA are free
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
+    for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 16) {
       if (n0 + c0 >= p.T) break;
       uint32_t v[16];
       tmem_ld16(t_lane + c0, v);
@@ -233,7 +236,7 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     fence_proxy_async();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (warp == 2 && lane == 0) {
       if constexpr (EPI == EPI_F32) tma_store_3d(&tmC, stg, m0, n0, 0);
       else tma_store_2d(&tmC, stg, m0, n0);
