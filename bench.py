@@ -54,7 +54,7 @@ def peaks():
 
 def prompts():
     import numpy as np
-    from oracle.llama_ref import LLAMA3_8B
+    from ollamamq_b200.models import LLAMA3_8B
     return [np.random.default_rng(u).integers(0, LLAMA3_8B["vocab"], PROMPT_LEN).astype("int32").tolist()
             for u in range(USERS)]
 
@@ -127,7 +127,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     import ollamamq_b200 as mq
-    from oracle.llama_ref import LLAMA3_8B
+    from ollamamq_b200.models import LLAMA3_8B      # the product arm never touches oracle/
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

@@ -15,7 +15,7 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 import ollamamq_b200 as mq  # noqa: E402
-from oracle.llama_ref import LLAMA3_8B  # noqa: E402
+from ollamamq_b200.models import LLAMA3_8B  # noqa: E402
 
 users = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 gen = int(sys.argv[2]) if len(sys.argv) > 2 else 6
