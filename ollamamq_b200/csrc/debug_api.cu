@@ -93,6 +93,7 @@ int mq_debug_rope_kv(const void* qkv, int qkv_is_f32, int n_planes, long long pl
   p.bias = (const __nv_bfloat16*)bias; p.pos = pos; p.slot_of_tok = slot_of_tok; p.block_table = block_table;
   p.max_pages = max_pages; p.inv_freq = inv_freq; p.q_out = (__nv_bfloat16*)q_out;
   p.k_cache = (__nv_bfloat16*)k_cache; p.v_cache = (__nv_bfloat16*)v_cache; p.T = T; p.n_q = n_q; p.n_kv = n_kv;
+  p.pf = L2Prefetch{nullptr, 0};
   launch_rope_kv(LaunchCfg{0, false}, p);
   return check_cuda("mq_debug_rope_kv");
 }

@@ -124,6 +124,8 @@ static int worker_alloc(mq_worker* w) {
     // (4.75 vs 4.44 ms per decode step), so it is opt-in.
     const char* e = getenv("MQ_FUSE_NORM");
     w->fuse_norm = e && e[0] == '1';
+    const char* e2 = getenv("MQ_L2_PREFETCH");
+    w->l2_prefetch = !(e2 && e2[0] == '0');
   }
   if ((rc = dalloc(&w->d_split_counter, (size_t)MBp * c.n_kv_heads))) return rc;
   CUDA_TRY(cudaMemsetAsync(w->d_split_counter, 0, (size_t)MBp * c.n_kv_heads * 4, w->stream));
@@ -273,9 +275,18 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
   int prev_planes = 0;
   for (int l = 0; l < c.n_layers; ++l) {
     const LayerWeights& lw = w->layers[l];
+    // decode: bytes of upcoming weights that the latency-bound kernels pull into L2 while HBM idles
+    const bool pfon = a.decode && w->l2_prefetch;
+    const size_t b_qkv = (size_t)w->qkv_dim * H * 2, b_o = (size_t)H * c.n_q_heads * c.head_dim * 2;
+    const size_t b_gu = (size_t)2 * c.ffn * H * 2;
+    const L2Prefetch pf_none{nullptr, 0};
+    const L2Prefetch pf_norm1 = pfon ? L2Prefetch{lw.wqkv, b_qkv} : pf_none;                         // before the QKV GEMM
+    const L2Prefetch pf_rope = pf_none;                                                              // KV stream follows: too early
+    const L2Prefetch pf_attn = pfon ? L2Prefetch{lw.wo, b_o} : pf_none;                              // tail of attention -> O GEMM
+    const L2Prefetch pf_norm2 = pfon ? L2Prefetch{lw.w_gate_up, std::min(b_gu, (size_t)64 << 20)} : pf_none;  // -> gate/up GEMM
     if (!fused) {
       launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, prev_planes, (long long)MBp * H, lw.attn_norm, w->x, nullptr, a.T,
-                         H, c.rms_eps); ++nl;
+                         H, c.rms_eps, pf_norm1); ++nl;
     }
     if (gemm_launch(pp->qkv[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     RopeKvParams rp;
@@ -285,18 +296,20 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
     rp.k_cache = w->k_cache + (size_t)l * w->cache_layer_stride;
     rp.v_cache = w->v_cache + (size_t)l * w->cache_layer_stride;
     rp.T = a.T; rp.n_q = c.n_q_heads; rp.n_kv = c.n_kv_heads;
+    rp.pf = pf_rope;
     launch_rope_kv(lc, rp); ++nl;
     AttnParams ap = {};
     ap.q = w->q; ap.k_cache = rp.k_cache; ap.v_cache = rp.v_cache; ap.block_table = w->d_block_table;
     ap.max_pages = w->max_pages; ap.tiles = w->d_tiles; ap.pos = a.pos; ap.out = w->attn; ap.part_o = w->part_o;
     ap.part_ml = w->part_ml; ap.n_q = c.n_q_heads; ap.n_kv = c.n_kv_heads; ap.T = a.T; ap.n_splits = a.n_splits;
+    ap.pf = pf_attn;
     ap.split_counter = w->d_split_counter; ap.scale_log2 = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
     if (a.decode) { launch_attn_decode(lc, ap, a.T); ++nl; }
     else { launch_attn_prefill(lc, ap, a.n_tiles); ++nl; }
     if (gemm_launch(pp->o[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     if (!fused) {
       launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, pp->s_o, (long long)MBp * H, lw.mlp_norm, w->x, nullptr, a.T, H,
-                         c.rms_eps); ++nl;
+                         c.rms_eps, pf_norm2); ++nl;
     }
     if (gemm_launch(pp->gate_up[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     if (gemm_launch(pp->down[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;

@@ -91,6 +91,7 @@ struct mq_worker {
   int* d_split_counter = nullptr;  // [MB][n_kv] arrival counters of the split-KV decode attention
   int* d_norm_counters = nullptr;  // [2 * layers] arrival counters of the fused norm prologues (zeroed by embed)
   bool fuse_norm = true;
+  bool l2_prefetch = true;   // decode: small kernels pull the next GEMM's weights into L2 (MQ_L2_PREFETCH=0 disables)
   // pinned host mirrors / staging
   int *h_pos = nullptr, *h_active = nullptr, *h_block_table = nullptr;
   int* h_stage = nullptr;     // ring of staging areas for metadata uploads

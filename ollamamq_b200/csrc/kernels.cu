@@ -66,8 +66,10 @@ void launch_embed(const LaunchCfg& lc, const int* token_ids, const __nv_bfloat16
 template <bool F32>
 __global__ void add_rmsnorm_kernel(float* __restrict__ h, const void* __restrict__ partial, int n_planes,
                                    long long plane_stride, const __nv_bfloat16* __restrict__ gamma,
-                                   __nv_bfloat16* __restrict__ x, const int* __restrict__ row_idx, int H, float eps) {
+                                   __nv_bfloat16* __restrict__ x, const int* __restrict__ row_idx, int H, float eps,
+                                   L2Prefetch pf) {
   pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
+  if (threadIdx.x == 0) l2_prefetch_slice(pf, blockIdx.x, gridDim.x);  // weights: independent of the previous kernel
   pdl_wait();
   const int row = blockIdx.x;
   const int src = row_idx ? row_idx[row] : row;
@@ -111,14 +113,14 @@ __global__ void add_rmsnorm_kernel(float* __restrict__ h, const void* __restrict
 }
 void launch_add_rmsnorm(const LaunchCfg& lc, float* h, const void* partial, bool partial_is_f32, int n_planes,
                         long long plane_stride, const __nv_bfloat16* gamma, __nv_bfloat16* x, const int* row_idx,
-                        int rows, int H, float eps) {
+                        int rows, int H, float eps, L2Prefetch pf) {
   const int thr = H / 16;  // H % 512 == 0 is checked at model load
   if (partial_is_f32)
     launch_k(lc, add_rmsnorm_kernel<true>, dim3(rows), dim3(thr), 0, h, partial, n_planes, plane_stride, gamma, x,
-             row_idx, H, eps);
+             row_idx, H, eps, pf);
   else
     launch_k(lc, add_rmsnorm_kernel<false>, dim3(rows), dim3(thr), 0, h, partial, n_planes, plane_stride, gamma, x,
-             row_idx, H, eps);
+             row_idx, H, eps, pf);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -158,6 +160,7 @@ __device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) 
 template <bool F32>
 __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
   pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
+  if (threadIdx.x == 0) l2_prefetch_slice(p.pf, blockIdx.x + gridDim.x * blockIdx.y, gridDim.x * gridDim.y);
   pdl_wait();
   constexpr int D = kHeadDim, HALF = D / 2;
   const int t = blockIdx.x;
@@ -595,6 +598,11 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
       __syncwarp();
     }
   }
+
+  // KV streaming of this CTA is over: use the combine tail to pull the O-projection weights towards L2
+  // (issued late on purpose - the 135 MB KV stream would evict anything prefetched earlier)
+  if (lane == 0)
+    l2_prefetch_slice(p.pf, blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z), gridDim.x * gridDim.y * gridDim.z);
 
   // ---- finalize: l of head g -> full row sum; this thread needs the sums of heads 2c, 2c+1
   l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);

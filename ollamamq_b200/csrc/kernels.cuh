@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include "ptx.cuh"
 
 namespace mq {
 
@@ -22,7 +23,7 @@ void launch_embed(const LaunchCfg& lc, const int* token_ids, const __nv_bfloat16
 // partial_is_f32: planes are fp32 (decode split-K) else one bf16 plane (prefill).
 void launch_add_rmsnorm(const LaunchCfg& lc, float* h, const void* partial, bool partial_is_f32, int n_planes,
                         long long plane_stride, const __nv_bfloat16* gamma, __nv_bfloat16* x, const int* row_idx,
-                        int rows, int H, float eps);
+                        int rows, int H, float eps, L2Prefetch pf = L2Prefetch{nullptr, 0});
 
 struct RopeKvParams {
   const void* qkv;        // partial planes [S][T][qkv_dim] fp32, or one bf16 plane
@@ -39,6 +40,7 @@ struct RopeKvParams {
   __nv_bfloat16* k_cache;     // layer base: [pages][n_kv][kPageSize][d]
   __nv_bfloat16* v_cache;
   int T, n_q, n_kv;
+  L2Prefetch pf;              // optional: weights of an upcoming GEMM to pull into L2
 };
 void launch_rope_kv(const LaunchCfg& lc, const RopeKvParams& p);
 
@@ -57,6 +59,7 @@ struct AttnParams {
   int n_splits;        // decode only: every sequence is cut into n_splits equal 16-aligned ranges
   int* split_counter;  // decode only: [slots][n_kv] arrival counters (zero between launches)
   float scale_log2;    // softmax scale * log2(e)
+  L2Prefetch pf;       // optional: weights of an upcoming GEMM to pull into L2 (decode)
 };
 void launch_attn_prefill(const LaunchCfg& lc, const AttnParams& p, int n_tiles);
 void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots);

@@ -91,6 +91,31 @@ __device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// Asynchronous L2 prefetch of a contiguous global range (hint only; bytes must be a multiple of 16).
+__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
+}
+// Every CTA of a grid prefetches its slice of [ptr, ptr + bytes): used by the small / latency-bound kernels of the
+// decode chain to pull the NEXT GEMM's weights towards L2 while HBM would otherwise idle (r01 profiles).
+struct L2Prefetch {
+  const void* ptr;
+  unsigned long long bytes;
+};
+__device__ __forceinline__ void l2_prefetch_slice(const L2Prefetch& pf, unsigned cta, unsigned n_ctas) {
+  if (pf.ptr == nullptr || pf.bytes == 0) return;
+  unsigned long long per = ((pf.bytes / n_ctas) + 15ull) & ~15ull;
+  const unsigned long long off = per * cta;
+  if (off >= pf.bytes) return;
+  if (off + per > pf.bytes) per = (pf.bytes - off) & ~15ull;
+  const char* base = reinterpret_cast<const char*>(pf.ptr) + off;
+  while (per > 0) {  // keep single requests modest
+    const unsigned chunk = per > 65536ull ? 65536u : (unsigned)per;
+    l2_prefetch_bulk(base, chunk);
+    base += chunk;
+    per -= chunk;
+  }
+}
+
 // ---------------------------------------------------------------- PDL (programmatic dependent launch)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() {
