@@ -124,8 +124,9 @@ static int worker_alloc(mq_worker* w) {
     // (4.75 vs 4.44 ms per decode step), so it is opt-in.
     const char* e = getenv("MQ_FUSE_NORM");
     w->fuse_norm = e && e[0] == '1';
+    // Measured on B200 (r01): the hints make the decode step slower (4.71 vs 4.44 ms): opt-in only.
     const char* e2 = getenv("MQ_L2_PREFETCH");
-    w->l2_prefetch = !(e2 && e2[0] == '0');
+    w->l2_prefetch = e2 && e2[0] == '1';
   }
   if ((rc = dalloc(&w->d_split_counter, (size_t)MBp * c.n_kv_heads))) return rc;
   CUDA_TRY(cudaMemsetAsync(w->d_split_counter, 0, (size_t)MBp * c.n_kv_heads * 4, w->stream));

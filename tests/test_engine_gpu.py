@@ -273,3 +273,32 @@ def test_qwen25_7b_geometry_logits():
         assert err <= TOL * scale, (err, scale)
         gen = wk.generate(toks[:77], 16)
         _check_greedy(w, cfg, toks[:77], gen)
+
+
+def test_one_dispatcher_over_two_gpu_workers():
+    """The product topology of SURVEY.md 8(e): ONE scheduler thread driving one worker per GPU in-process;
+    the backend pick (least connections, round-robin tie-break, dispatcher.rs:247-254) spreads the users."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cfg = MID
+    ws = [R.make_weights(cfg, seed=71, device="cuda:%d" % i) for i in range(2)]
+    wks = [mq.Worker(i, mq.model_cfg(cfg, max_batch=4, max_seq=512, max_prefill_tokens=256)) for i in range(2)]
+    try:
+        for wk, w in zip(wks, ws):
+            wk.load_weights(w)
+        d = mq.Dispatcher(wks, capacity=4)
+        try:
+            prompts = [[7, 8, 9, i] for i in range(8)]
+            streams = [d.submit("user%d" % (i % 4), prompt_tokens=p, max_new_tokens=6) for i, p in enumerate(prompts)]
+            d.drain(120000)
+            for p, s in zip(prompts, streams):
+                assert s.rc == 0 and len(s.tokens()) == 6
+                _check_greedy(ws[0], cfg, p, s.tokens())
+            backends = [b for _, _, b in d.log()]
+            assert sorted(backends) == [0, 0, 0, 0, 1, 1, 1, 1]          # 8 tasks, two workers, 4 slots each
+            assert all(d.backend_stats(b)["processed_count"] == 4 for b in range(2))
+        finally:
+            d.close()
+    finally:
+        for wk in wks:
+            wk.close()
