@@ -101,25 +101,29 @@ class ClockSampler:
             self.p.wait(5)
         except Exception:
             pass
-        sm, mx, reasons = [], 0, set()
+        sm, pw, mx, reasons = [], [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 7:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx = max(mx, float(f[1]))
+                c, m, w = float(f[0]), float(f[1]), float(f[2])
             except ValueError:
                 continue
+            sm.append(c)
+            pw.append(w)
+            mx = max(mx, m)
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        sm.sort()
-        # "under load": upper half of the samples (idle samples between steps drag the median down)
-        load = sm[len(sm) // 2:] if sm else []
+        # "under load" = samples drawing at least half of the highest power seen during the timed region
+        thr = 0.5 * max(pw) if pw else 0.0
+        load = sorted(c for c, w in zip(sm, pw) if w >= thr)
         med = load[len(load) // 2] if load else None
-        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": med, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm),
+                "samples_under_load": len(load), "sm_mhz_min_under_load": load[0] if load else None,
+                "power_w_max": max(pw) if pw else None}
 
 
 # ------------------------------------------------------------------------------------------------ ours
