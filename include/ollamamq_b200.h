@@ -75,6 +75,10 @@ int mq_sched_processing(mq_sched* s, const char* user, int32_t delta);
  * NULL clears.  The reference has one VIP and one Boost slot (:57-58).                                  */
 int mq_sched_set_vip(mq_sched* s, const char* user);
 int mq_sched_set_boost(mq_sched* s, const char* user);
+/* EXTENSION (BASELINE config 3: "2 VIP + 4 Boost"; the reference has no semantics for this): flags become sets;
+ * the winner is the first member in the reference sort order (:224-228).  With <= 1 member: the reference.     */
+int mq_sched_add_vip(mq_sched* s, const char* user);
+int mq_sched_add_boost(mq_sched* s, const char* user);
 /* health prober result (:185-189) */
 int mq_sched_set_online(mq_sched* s, int32_t backend, int32_t online);
 /* generalisations with reference defaults: capacity 1 (:204), boost every 2nd dispatch (:233)            */

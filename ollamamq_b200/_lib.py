@@ -93,6 +93,8 @@ _sig("mq_sched_complete", C.c_int, [P, C.c_int32, C.c_char_p, C.c_int32])
 _sig("mq_sched_processing", C.c_int, [P, C.c_char_p, C.c_int32])
 _sig("mq_sched_set_vip", C.c_int, [P, C.c_char_p])
 _sig("mq_sched_set_boost", C.c_int, [P, C.c_char_p])
+_sig("mq_sched_add_vip", C.c_int, [P, C.c_char_p])
+_sig("mq_sched_add_boost", C.c_int, [P, C.c_char_p])
 _sig("mq_sched_set_online", C.c_int, [P, C.c_int32, C.c_int32])
 _sig("mq_sched_set_capacity", C.c_int, [P, C.c_int32])
 _sig("mq_sched_set_boost_mod", C.c_int, [P, C.c_int32])

@@ -52,16 +52,14 @@ bool Scheduler::next(SchedDispatch* out) {
     }
   if (!any || active_.empty()) return false;
 
-  // 2. user selection (:230-240)
+  // 2. user selection (:230-240).  active_ is sorted, so the first member met is the winner of a multi-member set.
   User* target = nullptr;
-  if (has_vip_) {
-    auto it = users_.find(vip_);
-    if (it != users_.end() && is_active(&it->second)) target = &it->second;
-  }
-  if (!target && has_boost_ && counter_ % (uint64_t)boost_mod_ == 0) {
-    auto it = users_.find(boost_);
-    if (it != users_.end() && is_active(&it->second)) target = &it->second;
-  }
+  if (!vip_.empty())
+    for (User* u : active_)
+      if (std::find(vip_.begin(), vip_.end(), u->name) != vip_.end()) { target = u; break; }
+  if (!target && !boost_.empty() && counter_ % (uint64_t)boost_mod_ == 0)
+    for (User* u : active_)
+      if (std::find(boost_.begin(), boost_.end(), u->name) != boost_.end()) { target = u; break; }
   if (!target) {
     if (current_idx_ >= active_.size()) current_idx_ = 0;
     target = active_[current_idx_];
@@ -130,15 +128,24 @@ void Scheduler::processing(const std::string& user, int delta) {
   else u.processing = u.processing >= (uint64_t)(-delta) ? u.processing - (uint64_t)(-delta) : 0;
 }
 
+static void erase_name(std::vector<std::string>& v, const std::string& n) {
+  v.erase(std::remove(v.begin(), v.end(), n), v.end());
+}
 void Scheduler::set_vip(const char* user) {
-  has_vip_ = user != nullptr;
-  vip_ = user ? user : "";
-  if (has_vip_ && has_boost_ && boost_ == vip_) { has_boost_ = false; boost_.clear(); }  // tui.rs:142-148
+  vip_.clear();
+  if (user) add_vip(user);
 }
 void Scheduler::set_boost(const char* user) {
-  has_boost_ = user != nullptr;
-  boost_ = user ? user : "";
-  if (has_boost_ && has_vip_ && vip_ == boost_) { has_vip_ = false; vip_.clear(); }  // tui.rs:169-175
+  boost_.clear();
+  if (user) add_boost(user);
+}
+void Scheduler::add_vip(const std::string& user) {
+  erase_name(boost_, user);  // a user holds at most one flag (tui.rs:142-148)
+  if (std::find(vip_.begin(), vip_.end(), user) == vip_.end()) vip_.push_back(user);
+}
+void Scheduler::add_boost(const std::string& user) {
+  erase_name(vip_, user);  // tui.rs:169-175
+  if (std::find(boost_.begin(), boost_.end(), user) == boost_.end()) boost_.push_back(user);
 }
 void Scheduler::set_online(int backend, bool online) {
   if (backend >= 0 && backend < (int)backends_.size()) backends_[backend].online = online;
@@ -222,6 +229,16 @@ int mq_sched_set_vip(mq_sched* s, const char* user) {
 int mq_sched_set_boost(mq_sched* s, const char* user) {
   if (!s) return MQ_ERR_INVAL;
   s->s.set_boost(user);
+  return MQ_OK;
+}
+int mq_sched_add_vip(mq_sched* s, const char* user) {
+  if (!s || !user) return MQ_ERR_INVAL;
+  s->s.add_vip(user);
+  return MQ_OK;
+}
+int mq_sched_add_boost(mq_sched* s, const char* user) {
+  if (!s || !user) return MQ_ERR_INVAL;
+  s->s.add_boost(user);
   return MQ_OK;
 }
 int mq_sched_set_online(mq_sched* s, int32_t backend, int32_t online) {

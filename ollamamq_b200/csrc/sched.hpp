@@ -8,6 +8,7 @@
 #pragma once
 #include <cstdint>
 #include <deque>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -30,8 +31,12 @@ class Scheduler {
   void complete(int backend, const std::string& user, int outcome);
   void processing(const std::string& user, int delta);
 
-  void set_vip(const char* user);
+  void set_vip(const char* user);    // reference semantics: ONE slot (nullptr clears every VIP)
   void set_boost(const char* user);
+  // EXTENSION (BASELINE config 3, "2 VIP + 4 Boost"; no reference semantics): sets of users.  The
+  // winner is the first member in the reference sort order (:224-228); with <= 1 member this is the reference.
+  void add_vip(const std::string& user);
+  void add_boost(const std::string& user);
   void set_online(int backend, bool online);
   void set_capacity(int c) { capacity_ = c < 1 ? 1 : c; }
   void set_boost_mod(int m) { boost_mod_ = m < 1 ? 1 : m; }
@@ -69,8 +74,7 @@ class Scheduler {
   std::map<std::string, User> users_;  // entries are never removed (:399-402; TUI list only grows)
   std::vector<User*> active_;          // users with a non-empty queue, sorted by key_less
   std::vector<Backend> backends_;
-  std::string vip_, boost_;
-  bool has_vip_ = false, has_boost_ = false;
+  std::vector<std::string> vip_, boost_;  // sets (tiny): the reference has one Option<String> each (:57-58)
   uint64_t counter_ = 0;       // global_counter (:89)
   size_t current_idx_ = 0;     // run_worker local (:169)
   size_t last_backend_ = 0;    // last_backend_idx (:93)

@@ -82,6 +82,13 @@ class Scheduler:
     def set_boost(self, user: Optional[str]):
         check(lib.mq_sched_set_boost(self._h, self._b(user)))
 
+    def add_vip(self, user: str):
+        """Extension (config 3): several VIPs; first in the reference sort order wins."""
+        check(lib.mq_sched_add_vip(self._h, self._b(user)))
+
+    def add_boost(self, user: str):
+        check(lib.mq_sched_add_boost(self._h, self._b(user)))
+
     def set_online(self, backend: int, online: bool):
         check(lib.mq_sched_set_online(self._h, backend, 1 if online else 0))
 
@@ -124,10 +131,10 @@ def simulate(sched: Scheduler, arrivals, service_time, vip=None, boost=None, out
     """
     import heapq
 
-    if vip is not None:
-        sched.set_vip(vip)
-    if boost is not None:
-        sched.set_boost(boost)
+    for v in ([vip] if isinstance(vip, str) else (vip or [])):
+        sched.add_vip(v)
+    for b in ([boost] if isinstance(boost, str) else (boost or [])):
+        sched.add_boost(b)
     arr = sorted(enumerate(arrivals), key=lambda x: (x[1][0], x[0]))
     ai = 0
     heap = []  # (finish_time, backend, order, user, seq)

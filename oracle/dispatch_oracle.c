@@ -39,8 +39,9 @@ typedef struct orc {
   int n_users, cap_users;
   orc_backend* backends;
   int n_backends;
-  char vip[ORC_NAME_MAX], boost[ORC_NAME_MAX];
-  int has_vip, has_boost;
+  /* EXTENSION (BASELINE config 3): up to ORC_SET_MAX VIP / Boost users; the reference has one slot each (:57-58) */
+  char vip[8][ORC_NAME_MAX], boost[8][ORC_NAME_MAX];
+  int n_vip, n_boost;
   unsigned long global_counter; /* :89 */
   size_t current_idx;           /* :169 */
   size_t last_backend_idx;      /* :93 */
@@ -80,15 +81,34 @@ static orc_user* find_user(orc* o, const char* name, int create) {
 void orc_enqueue(orc* o, const char* user) { /* :364-368, :397-403 */
   find_user(o, user ? user : "anonymous", 1)->queued += 1;
 }
+static int set_find(char (*set)[ORC_NAME_MAX], int n, const char* u) {
+  for (int i = 0; i < n; ++i)
+    if (strcmp(set[i], u) == 0) return i;
+  return -1;
+}
+static void set_del(char (*set)[ORC_NAME_MAX], int* n, const char* u) {
+  int i = set_find(set, *n, u);
+  if (i < 0) return;
+  for (; i + 1 < *n; ++i) memcpy(set[i], set[i + 1], ORC_NAME_MAX);
+  *n -= 1;
+}
+void orc_add_vip(orc* o, const char* u) {
+  set_del(o->boost, &o->n_boost, u); /* tui.rs:142-148 */
+  if (set_find(o->vip, o->n_vip, u) < 0 && o->n_vip < 8) strncpy(o->vip[o->n_vip++], u, ORC_NAME_MAX - 1);
+}
+void orc_add_boost(orc* o, const char* u) {
+  set_del(o->vip, &o->n_vip, u); /* tui.rs:169-175 */
+  if (set_find(o->boost, o->n_boost, u) < 0 && o->n_boost < 8) strncpy(o->boost[o->n_boost++], u, ORC_NAME_MAX - 1);
+}
 void orc_set_vip(orc* o, const char* u) {
-  o->has_vip = u != NULL;
-  if (u) strncpy(o->vip, u, ORC_NAME_MAX - 1);
-  if (u && o->has_boost && strcmp(o->boost, u) == 0) o->has_boost = 0; /* tui.rs:142-148 */
+  o->n_vip = 0;
+  memset(o->vip, 0, sizeof(o->vip));
+  if (u) orc_add_vip(o, u);
 }
 void orc_set_boost(orc* o, const char* u) {
-  o->has_boost = u != NULL;
-  if (u) strncpy(o->boost, u, ORC_NAME_MAX - 1);
-  if (u && o->has_vip && strcmp(o->vip, u) == 0) o->has_vip = 0; /* tui.rs:169-175 */
+  o->n_boost = 0;
+  memset(o->boost, 0, sizeof(o->boost));
+  if (u) orc_add_boost(o, u);
 }
 void orc_set_online(orc* o, int b, int online) { o->backends[b].is_online = online; }
 void orc_set_capacity(orc* o, int c) { o->capacity = c; }
@@ -120,13 +140,12 @@ int orc_next(orc* o, char* user_out, int cap, long* seq_out, int* backend_out) {
   qsort(active, (size_t)n_active, sizeof(int), cmp_users);
 
   int target = -1;
-  if (o->has_vip) /* :230 */
-    for (int i = 0; i < n_active; ++i)
-      if (strcmp(o->users[active[i]].name, o->vip) == 0) target = active[i];
-  if (target < 0 && o->has_boost) /* :231-235 */
-    for (int i = 0; i < n_active; ++i)
-      if (strcmp(o->users[active[i]].name, o->boost) == 0 && o->global_counter % (unsigned long)o->boost_mod == 0)
-        target = active[i];
+  /* :230 — with one VIP exactly `active_users.contains(v)`; with several, the first in sorted order wins */
+  for (int i = 0; i < n_active && target < 0; ++i)
+    if (set_find(o->vip, o->n_vip, o->users[active[i]].name) >= 0) target = active[i];
+  if (target < 0 && o->n_boost > 0 && o->global_counter % (unsigned long)o->boost_mod == 0) /* :231-235 */
+    for (int i = 0; i < n_active && target < 0; ++i)
+      if (set_find(o->boost, o->n_boost, o->users[active[i]].name) >= 0) target = active[i];
   if (target < 0) { /* :236-240 */
     if (o->current_idx >= (size_t)n_active) o->current_idx = 0;
     target = active[o->current_idx];

@@ -29,8 +29,8 @@ class OraclePy:
         self.dropped: Dict[str, int] = {}
         self.popped: Dict[str, int] = {}
         self.backends = [{"active": 0, "processed": 0, "online": True} for _ in range(n_backends)]
-        self.vip: Optional[str] = None
-        self.boost: Optional[str] = None
+        self.vip: List[str] = []      # EXTENSION (config 3): sets; the reference has one Option<String> each
+        self.boost: List[str] = []
         self.counter = 0
         self.current_idx = 0
         self.last_idx = 0
@@ -41,15 +41,27 @@ class OraclePy:
         u = "anonymous" if user is None else user
         self.queues.setdefault(u, deque()).append(object())
 
+    def add_vip(self, u):
+        if u in self.boost:
+            self.boost.remove(u)
+        if u not in self.vip:
+            self.vip.append(u)
+
+    def add_boost(self, u):
+        if u in self.vip:
+            self.vip.remove(u)
+        if u not in self.boost:
+            self.boost.append(u)
+
     def set_vip(self, u):
-        self.vip = u
-        if u is not None and self.boost == u:
-            self.boost = None
+        self.vip = []
+        if u is not None:
+            self.add_vip(u)
 
     def set_boost(self, u):
-        self.boost = u
-        if u is not None and self.vip == u:
-            self.vip = None
+        self.boost = []
+        if u is not None:
+            self.add_boost(u)
 
     def set_online(self, b, online):
         self.backends[b]["online"] = bool(online)
@@ -64,11 +76,15 @@ class OraclePy:
         # byte-wise string order, like Rust's String Ord
         active.sort(key=lambda u: (self.processed.get(u, 0), u.encode("utf-8")))
         target = None
-        if self.vip is not None and self.vip in active:
-            target = self.vip
-        if target is None and self.boost is not None:
-            if self.boost in active and self.counter % self.boost_mod == 0:
-                target = self.boost
+        for u in active:                      # sorted: the first VIP met wins (one VIP: `active.contains(vip)`, :230)
+            if u in self.vip:
+                target = u
+                break
+        if target is None and self.boost and self.counter % self.boost_mod == 0:
+            for u in active:
+                if u in self.boost:
+                    target = u
+                    break
         if target is None:
             if self.current_idx >= len(active):
                 self.current_idx = 0
@@ -116,6 +132,8 @@ class OracleC:
             L.orc_enqueue.argtypes = [C.c_void_p, C.c_char_p]
             L.orc_set_vip.argtypes = [C.c_void_p, C.c_char_p]
             L.orc_set_boost.argtypes = [C.c_void_p, C.c_char_p]
+            L.orc_add_vip.argtypes = [C.c_void_p, C.c_char_p]
+            L.orc_add_boost.argtypes = [C.c_void_p, C.c_char_p]
             L.orc_set_online.argtypes = [C.c_void_p, C.c_int, C.c_int]
             L.orc_next.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_long), C.POINTER(C.c_int)]
             L.orc_complete.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
@@ -147,6 +165,12 @@ class OracleC:
     def set_boost(self, u):
         self.L.orc_set_boost(self.h, None if u is None else u.encode())
 
+    def add_vip(self, u):
+        self.L.orc_add_vip(self.h, u.encode())
+
+    def add_boost(self, u):
+        self.L.orc_add_boost(self.h, u.encode())
+
     def set_online(self, b, online):
         self.L.orc_set_online(self.h, b, 1 if online else 0)
 
@@ -161,7 +185,8 @@ class OracleC:
 
 
 def simulate(orc, arrivals: List[Tuple[int, Optional[str]]], service_time: Callable[[str, int, int], int],
-             vip=None, boost=None, outcomes=None, events=None, on_complete=None) -> List[Tuple[str, int, int]]:
+             vip=None, boost=None, outcomes=None, events=None, on_complete=None,
+             on_dispatch=None) -> List[Tuple[str, int, int]]:
     """Event model of SURVEY.md 3.2, restated independently of the product harness.
 
     A completion = {user counter++, backend freed} atomically (dispatcher.rs:314-341 has no .await between
@@ -170,10 +195,10 @@ def simulate(orc, arrivals: List[Tuple[int, Optional[str]]], service_time: Calla
     completions at time t precede arrivals at time t.  `events`: optional {time: [(kind, arg...)]} control
     events applied before anything else at that time (("vip", u), ("boost", u), ("online", b, flag)).
     """
-    if vip is not None:
-        orc.set_vip(vip)
-    if boost is not None:
-        orc.set_boost(boost)
+    for v in ([vip] if isinstance(vip, str) else (vip or [])):
+        orc.add_vip(v)
+    for b in ([boost] if isinstance(boost, str) else (boost or [])):
+        orc.add_boost(b)
     pend = sorted(range(len(arrivals)), key=lambda i: (arrivals[i][0], i))
     inflight = []  # [finish, backend, order, user, seq]
     out = []
@@ -191,6 +216,8 @@ def simulate(orc, arrivals: List[Tuple[int, Optional[str]]], service_time: Calla
             if d is None:
                 return
             out.append(d)
+            if on_dispatch is not None:
+                on_dispatch(t, *d)
             inflight.append([t + int(service_time(*d)), d[2], order, d[0], d[1]])
             order += 1
 

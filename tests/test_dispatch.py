@@ -256,3 +256,67 @@ def test_scheduler_rejects_bad_arguments():
         s.enqueue("x" * 300)
     with pytest.raises(mq.MQError):
         s.complete(5, "u", PROCESSED)
+
+
+# ----------------------------------------------------------------------------------- config 3 (extension)
+def _zipf_counts(n_users=32, total=256, s=1.1, seed=0):
+    """Request counts proportional to Zipf(s) over the users, totalling `total`."""
+    import numpy as np
+    w = 1.0 / np.arange(1, n_users + 1) ** s
+    raw = w / w.sum() * total
+    counts = np.maximum(1, np.floor(raw).astype(int))
+    rng = np.random.default_rng(seed)
+    while counts.sum() < total:
+        counts[rng.integers(0, n_users)] += 1
+    while counts.sum() > total:
+        i = int(np.argmax(counts))
+        counts[i] -= 1
+    return counts.tolist()
+
+
+def test_config3_multi_vip_boost_extension_priority_fairness():
+    """BASELINE config 3: 32 users, Zipf-skewed arrivals, 2 VIP + 4 Boost.  The reference has ONE VIP and ONE Boost
+    slot (dispatcher.rs:57-58); the set semantics are an extension (first member in the :224-228 sort order wins)
+    that must (a) be identical in product and both oracles, (b) reduce to the reference with one member, and
+    (c) order mean queue wait VIP < Boost < everyone else under load."""
+    import numpy as np
+    users = ["user%02d" % i for i in range(32)]
+    counts = _zipf_counts()
+    rng = np.random.default_rng(0)
+    arrivals = []
+    for u, c in zip(users, counts):
+        arrivals += [(int(t), u) for t in rng.integers(0, 40, c)]
+    vips, boosts = ["user09", "user20"], ["user03", "user12", "user25", "user30"]
+    svc = lambda u, s, b: 2 + (hash((u, s)) % 3 == 0)        # deterministic within the process
+    ref = oracle_simulate(OracleC(4), arrivals, svc, vip=vips, boost=boosts)
+    ref2 = oracle_simulate(OraclePy(4), arrivals, svc, vip=vips, boost=boosts)
+    got = product_simulate(mq.Scheduler(4), arrivals, svc, vip=vips, boost=boosts)
+    assert ref == ref2 and [d.key() for d in got] == ref and len(ref) == 256
+    # (b) singleton sets == the reference's single slots
+    one = oracle_simulate(OracleC(4), arrivals, svc, vip=["user09"], boost=["user03"])
+    assert one == oracle_simulate(OracleC(4), arrivals, svc, vip="user09", boost="user03")
+    # (c) priority fairness: mean queue wait on the simulated clock (dispatch time - arrival time), per class
+    t_disp = {}
+    oracle_simulate(OracleC(4), arrivals, svc, vip=vips, boost=boosts,
+                    on_dispatch=lambda t, u, s, b: t_disp.__setitem__((u, s), t))
+    t_arr = {}
+    for t, u in sorted(arrivals, key=lambda x: x[0]):       # FIFO inside a user: seq-th arrival = seq-th dispatch
+        t_arr.setdefault(u, []).append(t)
+
+    def mean_wait(group):
+        return float(np.mean([t_disp[(u, s)] - t_arr[u][s] for u in group for s in range(len(t_arr[u]))]))
+
+    others = [u for u in users if u not in vips + boosts]
+    assert mean_wait(vips) < mean_wait(boosts) < mean_wait(others), (mean_wait(vips), mean_wait(boosts), mean_wait(others))
+
+
+def test_a_user_holds_at_most_one_flag_in_the_extension():
+    s = mq.Scheduler(1)
+    s.add_vip("a")
+    s.add_vip("b")
+    s.add_boost("a")          # moves a from VIP to Boost (tui.rs:169-175 generalised)
+    for u in ("a", "b", "c"):
+        s.enqueue(u)
+    assert [s.next().user for _ in range(1)] == ["b"]     # the only VIP left
+    s.complete(0, "b", PROCESSED)
+    assert s.next().user in ("a", "c")                     # counter is odd: ordinary round-robin turn
