@@ -302,3 +302,33 @@ def test_one_dispatcher_over_two_gpu_workers():
     finally:
         for wk in wks:
             wk.close()
+
+
+def test_config4_shape_256_users_short_prompts_sse():
+    """BASELINE configs[3] load shape: 256 concurrent users, 32-token prompts, SSE on /v1/chat/completions (high-fanout
+    TTFT).  Geometry is the mid-size head_dim-128 model (Phi-3's head_dim 96 is not instantiated): the point is the
+    256-slot path - decode GEMMs with 256-token tiles, 256 x n_kv attention CTAs, ragged completion."""
+    cfg = MID
+    w = R.make_weights(cfg, seed=81, device="cuda")
+    g = torch.Generator().manual_seed(8)
+    prompts = [torch.randint(0, cfg["vocab"], (32,), generator=g).tolist() for _ in range(256)]
+    with _open(cfg, w, max_batch=256, max_seq=128, max_prefill_tokens=2048) as wk:
+        d = mq.Dispatcher([wk], capacity=256)
+        try:
+            streams = [d.submit("user%03d" % i, endpoint=2, prompt_tokens=p, max_new_tokens=8 + (i % 5), stream=1)
+                       for i, p in enumerate(prompts)]
+            d.drain(240000)
+            for i, s in enumerate(streams):
+                assert s.rc == 0 and s.content_type == "text/event-stream", (i, s.rc, s.err)
+                events = [e for e in s.body.decode().split("\n\n") if e]
+                assert events[-1] == "data: [DONE]" and len(events) == 8 + (i % 5) + 2
+            # parity of a few of them (teacher-forced): token ids are embedded in the SSE deltas as " t<id>"
+            import re
+            for i in (0, 77, 255):
+                toks = [int(x) for x in re.findall(r'"content":" t(\d+)"', streams[i].body.decode())]
+                assert len(toks) == 8 + (i % 5)
+                _check_greedy(w, cfg, prompts[i], toks)
+            st = wk.stats()
+            assert st["decode_steps"] > 0 and d.user_stats("user255")["processed"] == 1
+        finally:
+            d.close()
