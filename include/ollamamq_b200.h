@@ -265,13 +265,14 @@ int mq_debug_add_rmsnorm(float* h, const void* partial, int partial_is_f32, int 
                          const void* gamma, void* x, const int* row_idx, int rows, int H, float eps);
 int mq_debug_rope_kv(const void* qkv, int qkv_is_f32, int n_planes, long long plane_stride, const void* bias,
                      const int* pos, const int* slot_of_tok, const int* block_table, int max_pages,
-                     const float* inv_freq, void* q_out, void* k_cache, void* v_cache, int T, int n_q, int n_kv);
+                     const float* inv_freq, void* q_out, void* k_cache, void* v_cache, int T, int n_q, int n_kv,
+                     int head_dim /* 128, 96 or 64 */);
 int mq_debug_attn_prefill(const void* q, const void* k_cache, const void* v_cache, const int* block_table,
                           int max_pages, const int* tiles, int n_tiles, void* out, int n_q, int n_kv, int T,
-                          float scale);
+                          float scale, int head_dim);
 int mq_debug_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* block_table,
                          int max_pages, const int* pos, void* out, float* part_o, float* part_ml, int* split_counter,
-                         int n_q, int n_kv, int n_slots, int n_splits, float scale);
+                         int n_q, int n_kv, int n_slots, int n_splits, float scale, int head_dim);
 int mq_debug_argmax(const float* logits, int rows, int V, int ldl, int* out_tokens, const int* dst_slot,
                     int* cur_token, int* pos_inc, const int* active);
 int mq_debug_init_normal(void* w, unsigned long long n, unsigned long long seed, float std);

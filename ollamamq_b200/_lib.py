@@ -149,10 +149,11 @@ _sig("mq_debug_gemm", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_in
 _sig("mq_debug_embed", C.c_int, [P, P, P, C.c_int, C.c_int])
 _sig("mq_debug_add_rmsnorm", C.c_int, [P, P, C.c_int, C.c_int, C.c_longlong, P, P, P, C.c_int, C.c_int, C.c_float])
 _sig("mq_debug_rope_kv", C.c_int, [P, C.c_int, C.c_int, C.c_longlong, P, P, P, P, C.c_int, P, P, P, P, C.c_int,
-                                    C.c_int, C.c_int])
-_sig("mq_debug_attn_prefill", C.c_int, [P, P, P, P, C.c_int, P, C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_float])
+                                    C.c_int, C.c_int, C.c_int])
+_sig("mq_debug_attn_prefill", C.c_int, [P, P, P, P, C.c_int, P, C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_float,
+                                         C.c_int])
 _sig("mq_debug_attn_decode", C.c_int, [P, P, P, P, C.c_int, P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int,
-                                        C.c_float])
+                                        C.c_float, C.c_int])
 _sig("mq_debug_argmax", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, P, P, P, P])
 _sig("mq_debug_init_normal", C.c_int, [P, C.c_ulonglong, C.c_ulonglong, C.c_float])
 

@@ -87,12 +87,15 @@ int mq_debug_add_rmsnorm(float* h, const void* partial, int partial_is_f32, int 
 
 int mq_debug_rope_kv(const void* qkv, int qkv_is_f32, int n_planes, long long plane_stride, const void* bias,
                      const int* pos, const int* slot_of_tok, const int* block_table, int max_pages,
-                     const float* inv_freq, void* q_out, void* k_cache, void* v_cache, int T, int n_q, int n_kv) {
+                     const float* inv_freq, void* q_out, void* k_cache, void* v_cache, int T, int n_q, int n_kv,
+                     int head_dim) {
+  if (!head_dim_supported(head_dim)) { mq::set_last_error("head_dim must be 128, 96 or 64"); return MQ_ERR_INVAL; }
   RopeKvParams p;
   p.qkv = qkv; p.qkv_is_f32 = qkv_is_f32 != 0; p.n_planes = n_planes; p.plane_stride = plane_stride;
   p.bias = (const __nv_bfloat16*)bias; p.pos = pos; p.slot_of_tok = slot_of_tok; p.block_table = block_table;
   p.max_pages = max_pages; p.inv_freq = inv_freq; p.q_out = (__nv_bfloat16*)q_out;
   p.k_cache = (__nv_bfloat16*)k_cache; p.v_cache = (__nv_bfloat16*)v_cache; p.T = T; p.n_q = n_q; p.n_kv = n_kv;
+  p.head_dim = head_dim;
   p.pf = L2Prefetch{nullptr, 0};
   launch_rope_kv(LaunchCfg{0, false}, p);
   return check_cuda("mq_debug_rope_kv");
@@ -100,8 +103,10 @@ int mq_debug_rope_kv(const void* qkv, int qkv_is_f32, int n_planes, long long pl
 
 int mq_debug_attn_prefill(const void* q, const void* k_cache, const void* v_cache, const int* block_table,
                           int max_pages, const int* tiles /* int4 per tile */, int n_tiles, void* out, int n_q,
-                          int n_kv, int T, float scale) {
+                          int n_kv, int T, float scale, int head_dim) {
+  if (!head_dim_supported(head_dim)) { mq::set_last_error("head_dim must be 128, 96 or 64"); return MQ_ERR_INVAL; }
   AttnParams p = {};
+  p.head_dim = head_dim;
   p.q = (const __nv_bfloat16*)q; p.k_cache = (const __nv_bfloat16*)k_cache; p.v_cache = (const __nv_bfloat16*)v_cache;
   p.block_table = block_table; p.max_pages = max_pages; p.tiles = (const int4*)tiles; p.out = (__nv_bfloat16*)out;
   p.n_q = n_q; p.n_kv = n_kv; p.T = T; p.n_splits = 1;
@@ -113,8 +118,10 @@ int mq_debug_attn_prefill(const void* q, const void* k_cache, const void* v_cach
 
 int mq_debug_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* block_table,
                          int max_pages, const int* pos, void* out, float* part_o, float* part_ml, int* split_counter,
-                         int n_q, int n_kv, int n_slots, int n_splits, float scale) {
+                         int n_q, int n_kv, int n_slots, int n_splits, float scale, int head_dim) {
+  if (!head_dim_supported(head_dim)) { mq::set_last_error("head_dim must be 128, 96 or 64"); return MQ_ERR_INVAL; }
   AttnParams p = {};
+  p.head_dim = head_dim;
   p.q = (const __nv_bfloat16*)q; p.k_cache = (const __nv_bfloat16*)k_cache; p.v_cache = (const __nv_bfloat16*)v_cache;
   p.block_table = block_table; p.max_pages = max_pages; p.pos = pos; p.out = (__nv_bfloat16*)out;
   p.part_o = part_o; p.part_ml = part_ml; p.split_counter = split_counter; p.n_q = n_q; p.n_kv = n_kv; p.T = n_slots;

@@ -296,10 +296,11 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
     rp.max_pages = w->max_pages; rp.inv_freq = w->inv_freq; rp.q_out = w->q;
     rp.k_cache = w->k_cache + (size_t)l * w->cache_layer_stride;
     rp.v_cache = w->v_cache + (size_t)l * w->cache_layer_stride;
-    rp.T = a.T; rp.n_q = c.n_q_heads; rp.n_kv = c.n_kv_heads;
+    rp.T = a.T; rp.n_q = c.n_q_heads; rp.n_kv = c.n_kv_heads; rp.head_dim = c.head_dim;
     rp.pf = pf_rope;
     launch_rope_kv(lc, rp); ++nl;
     AttnParams ap = {};
+    ap.head_dim = c.head_dim;
     ap.q = w->q; ap.k_cache = rp.k_cache; ap.v_cache = rp.v_cache; ap.block_table = w->d_block_table;
     ap.max_pages = w->max_pages; ap.tiles = w->d_tiles; ap.pos = a.pos; ap.out = w->attn; ap.part_o = w->part_o;
     ap.part_ml = w->part_ml; ap.n_q = c.n_q_heads; ap.n_kv = c.n_kv_heads; ap.T = a.T; ap.n_splits = a.n_splits;
@@ -985,10 +986,10 @@ int mq_worker_open(int32_t gpu, const mq_model_cfg* cfg, mq_worker** out) {
     return MQ_ERR_NODEV;
   }
   const mq_model_cfg& c = *cfg;
-  if (c.head_dim != kHeadDim || c.hidden % 512 != 0 || c.hidden % 64 != 0 || c.ffn % 128 != 0 ||
+  if (!head_dim_supported(c.head_dim) || (c.n_q_heads * c.head_dim) % 64 != 0 || c.hidden % 512 != 0 || c.hidden % 64 != 0 || c.ffn % 128 != 0 ||
       c.n_q_heads % c.n_kv_heads != 0 || c.n_q_heads / c.n_kv_heads > 8 || kPrefillTileRows / (c.n_q_heads / c.n_kv_heads) < 1 || c.vocab % 4 != 0 ||
       c.max_batch < 1 || c.max_batch > 256 || c.max_seq < 1 || c.max_prefill_tokens < 16 || c.n_layers < 1) {
-    set_last_error("unsupported model geometry (need head_dim 128, hidden %% 512 == 0, ffn %% 128 == 0, "
+    set_last_error("unsupported model geometry (need head_dim 128 / 96 / 64, hidden %% 512 == 0, ffn %% 128 == 0, "
                    "vocab %% 4 == 0, GQA group <= 8, 1 <= max_batch <= 256)");
     return MQ_ERR_INVAL;
   }

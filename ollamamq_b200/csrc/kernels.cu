@@ -14,6 +14,7 @@
 //   attn_combine     merge the split-KV partials
 //   argmax           greedy sampler + device-side advance of (cur_token, pos) so decode steps chain on the GPU
 #include "kernels.cuh"
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace mq {
@@ -157,16 +158,27 @@ __device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) 
 
 // One CTA (256 threads) per (token, 16 heads); a thread owns 4 consecutive rotation pairs (i..i+3, i+64..i+67)
 // of one head, so every access is 8 B (bf16) or 16 B (fp32 planes).
-template <bool F32>
+// head_dim is a compile-time constant of the rope / attention kernels; 128 (Llama-3, Qwen2.5), 96 (Phi-3) and 64 are built
+template <typename F>
+static void dispatch_head_dim(int d, F&& f) {
+  switch (d) {
+    case 128: f(std::integral_constant<int, 128>{}); break;
+    case 96: f(std::integral_constant<int, 96>{}); break;
+    case 64: f(std::integral_constant<int, 64>{}); break;
+    default: break;  // rejected at mq_worker_open / by the debug ABI before any launch
+  }
+}
+
+template <bool F32, int D>
 __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
   pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
   if (threadIdx.x == 0) l2_prefetch_slice(p.pf, blockIdx.x + gridDim.x * blockIdx.y, gridDim.x * gridDim.y);
   pdl_wait();
-  constexpr int D = kHeadDim, HALF = D / 2;
+  constexpr int HALF = D / 2;  // 16 threads per head x 4 pairs cover HALF <= 64 (threads beyond HALF idle: d = 96, 64)
   const int t = blockIdx.x;
   const int hd = blockIdx.y * 16 + (threadIdx.x >> 4);  // q heads, then k heads, then v heads
   const int n_heads = p.n_q + 2 * p.n_kv;
-  if (hd >= n_heads) return;
+  if (hd >= n_heads || (int)(threadIdx.x & 15) * 4 >= HALF) return;
   const int pos = p.pos[t];
   const int slot = p.slot_of_tok[t];
   const int qkv_dim = n_heads * D;
@@ -202,10 +214,14 @@ __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
 }
 void launch_rope_kv(const LaunchCfg& lc, const RopeKvParams& p) {
   const dim3 grid(p.T, (p.n_q + 2 * p.n_kv + 15) / 16);
-  if (p.qkv_is_f32)
-    launch_k(lc, rope_kv_kernel<true>, grid, dim3(256), 0, p);
-  else
-    launch_k(lc, rope_kv_kernel<false>, grid, dim3(256), 0, p);
+  auto go = [&](auto dtag) {
+    constexpr int D = decltype(dtag)::value;
+    if (p.qkv_is_f32)
+      launch_k(lc, rope_kv_kernel<true, D>, grid, dim3(256), 0, p);
+    else
+      launch_k(lc, rope_kv_kernel<false, D>, grid, dim3(256), 0, p);
+  };
+  dispatch_head_dim(p.head_dim, go);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -238,19 +254,22 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 }
 
 // Rows of Q/K/V tiles are 256 B (128 bf16) = 16 chunks of 16 B; chunk index is XOR-swizzled with (row & 7)
-// so ldmatrix (8 rows x 16 B at one logical chunk column) is bank-conflict free.
+// so ldmatrix (8 rows x 16 B at one logical chunk column) is bank-conflict free.  head_dim 96 / 64 keep the
+// 256-byte pitch (chunks >= head_dim / 8 are never written nor read), so one swizzle serves all three.
+constexpr int kTilePitch = 128;  // elements per smem tile row, whatever the head_dim
 __device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return (uint32_t)(row * 16 + (chunk ^ (row & 7))) * 16u; }
 
-template <int NW, int TN, int STAGES, bool DECODE>
+template <int NW, int TN, int STAGES, bool DECODE, int D>
 __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p) {
-  constexpr int D = kHeadDim;
+  constexpr int P = kTilePitch;  // smem row pitch in elements (256 B for every head_dim: keeps the XOR swizzle valid)
+  constexpr int CH = D / 8;      // 16-byte chunks per row that hold data
   constexpr int R = NW * 16;
   constexpr int NT = TN / 8;  // score n-tiles per kv tile
   static_assert(TN % 16 == 0 && STAGES >= 2, "tile shape");
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* Qs = smem;
-  uint8_t* Ks = Qs + R * D * 2;
-  uint8_t* Vs = Ks + STAGES * TN * D * 2;
+  uint8_t* Ks = Qs + R * P * 2;
+  uint8_t* Vs = Ks + STAGES * TN * P * 2;
 
   pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
   pdl_wait();
@@ -279,27 +298,27 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
   const int* btab = p.block_table + (size_t)slot * p.max_pages;
   const int n_tiles = kv_begin < kv_end ? (kv_end - kv_begin + TN - 1) / TN : 0;
 
-  float o[16][4];
+  float o[D / 8][4];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  for (int i = 0; i < D / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY};
   float l_run[2] = {0.f, 0.f};
   const int row_a = warp * 16 + g, row_b = row_a + 8;
 
   if (n_tiles > 0) {
     // ---- Q tile -> smem (zero-filled beyond the valid rows)
-    for (int i = tid; i < R * 16; i += NW * 32) {
-      const int r = i >> 4, ch = i & 15;
+    for (int i = tid; i < R * CH; i += NW * 32) {
+      const int r = i / CH, ch = i % CH;
       const bool ok = r < n_rows;
       const int rr = ok ? r : 0;
       const int tok = tok0 + rr / G, head = kvh * G + rr % G;
       cp_async16(Qs + tile_off(r, ch), p.q + ((size_t)tok * p.n_q + head) * D + ch * 8, ok ? 16 : 0);
     }
     auto load_kv = [&](int stage, int t0) {
-      uint8_t* kst = Ks + stage * TN * D * 2;
-      uint8_t* vst = Vs + stage * TN * D * 2;
-      for (int i = tid; i < TN * 16; i += NW * 32) {
-        const int j = i >> 4, ch = i & 15;
+      uint8_t* kst = Ks + stage * TN * P * 2;
+      uint8_t* vst = Vs + stage * TN * P * 2;
+      for (int i = tid; i < TN * CH; i += NW * 32) {
+        const int j = i / CH, ch = i % CH;
         const int kvpos = t0 + j;
         const bool ok = kvpos < kv_end;
         const int pp = ok ? kvpos : kv_end - 1;
@@ -315,7 +334,7 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
       if (s0 < n_tiles) load_kv(s0, kv_begin + s0 * TN);
       cp_async_commit();
     }
-    uint32_t qf[8][4];
+    uint32_t qf[D / 16][4];
     const int qpos_a = pos0 + row_a / G, qpos_b = pos0 + row_b / G;
 
     for (int it = 0; it < n_tiles; ++it) {
@@ -327,13 +346,13 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
       if (it == 0) {
         const uint32_t qbase = smem_u32(Qs);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
+        for (int ks = 0; ks < D / 16; ++ks) {
           const int r = warp * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
           ldsm_x4(qbase + tile_off(r, ks * 2 + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
         }
       }
-      const uint32_t kbase = smem_u32(Ks + (it % STAGES) * TN * D * 2);
-      const uint32_t vbase = smem_u32(Vs + (it % STAGES) * TN * D * 2);
+      const uint32_t kbase = smem_u32(Ks + (it % STAGES) * TN * P * 2);
+      const uint32_t vbase = smem_u32(Vs + (it % STAGES) * TN * P * 2);
 
       // ---- S = Q K^T
       float s[NT][4];
@@ -342,7 +361,7 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
 #pragma unroll
         for (int e = 0; e < 4; ++e) s[2 * n2][e] = s[2 * n2 + 1][e] = 0.f;
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
+        for (int ks = 0; ks < D / 16; ++ks) {
           const int r = n2 * 16 + (lane & 7) + 8 * (lane >> 4);
           uint32_t b0, b1, b2, b3;
           ldsm_x4(kbase + tile_off(r, ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
@@ -384,7 +403,7 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
       l_run[0] = l_run[0] * al_a + sum_a;
       l_run[1] = l_run[1] * al_b + sum_b;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { o[i][0] *= al_a; o[i][1] *= al_a; o[i][2] *= al_b; o[i][3] *= al_b; }
+      for (int i = 0; i < D / 8; ++i) { o[i][0] *= al_a; o[i][1] *= al_a; o[i][2] *= al_b; o[i][3] *= al_b; }
       // ---- O += P V
 #pragma unroll
       for (int kt = 0; kt < TN / 16; ++kt) {
@@ -394,7 +413,7 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
         a[2] = pack_bf16(s[2 * kt + 1][0], s[2 * kt + 1][1]);
         a[3] = pack_bf16(s[2 * kt + 1][2], s[2 * kt + 1][3]);
 #pragma unroll
-        for (int d2 = 0; d2 < 8; ++d2) {
+        for (int d2 = 0; d2 < D / 16; ++d2) {
           const int r = kt * 16 + (lane & 7) + 8 * ((lane >> 3) & 1);
           uint32_t b0, b1, b2, b3;
           ldsm_x4_t(vbase + tile_off(r, d2 * 2 + (lane >> 4)), b0, b1, b2, b3);
@@ -420,7 +439,7 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
       const size_t base = ((size_t)blockIdx.z * p.T + tok) * p.n_q + head;
       float* po = p.part_o + base * D;
 #pragma unroll
-      for (int n = 0; n < 16; ++n)
+      for (int n = 0; n < D / 8; ++n)
         *reinterpret_cast<float2*>(po + n * 8 + 2 * c) = make_float2(o[n][2 * half], o[n][2 * half + 1]);
       if (c == 0) {
         p.part_ml[base * 2] = m_run[half];
@@ -430,43 +449,8 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
       const float inv = l > 0.f ? 1.f / l : 0.f;
       __nv_bfloat16* po = p.out + ((size_t)tok * p.n_q + head) * D;
 #pragma unroll
-      for (int n = 0; n < 16; ++n)
+      for (int n = 0; n < D / 8; ++n)
         *reinterpret_cast<uint32_t*>(po + n * 8 + 2 * c) = pack_bf16(o[n][2 * half] * inv, o[n][2 * half + 1] * inv);
-    }
-  }
-  if constexpr (DECODE && NW == 1) {
-    if (split) {
-      // ---- in-kernel combine: the split CTA that arrives last merges all partials of this (slot, kv head)
-      __threadfence();
-      int old = 0;
-      if (lane == 0) old = atomicAdd(p.split_counter + slot * p.n_kv + kvh, 1);
-      old = __shfl_sync(0xffffffffu, old, 0);
-      if (old == p.n_splits - 1) {
-        __threadfence();
-        for (int hg = 0; hg < G; ++hg) {
-          const int head = kvh * G + hg;
-          float M = -INFINITY;
-          for (int sp = 0; sp < p.n_splits; ++sp)
-            M = fmaxf(M, __ldcg(p.part_ml + (((size_t)sp * p.T + slot) * p.n_q + head) * 2));
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-          float L = 0.f;
-          for (int sp = 0; sp < p.n_splits; ++sp) {
-            const size_t base = ((size_t)sp * p.T + slot) * p.n_q + head;
-            const float m = __ldcg(p.part_ml + base * 2);
-            if (m == -INFINITY) continue;
-            const float wgt = exp2f(m - M);
-            L += __ldcg(p.part_ml + base * 2 + 1) * wgt;
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(p.part_o + base * D) + lane);
-            acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
-          }
-          const float inv = L > 0.f ? 1.f / L : 0.f;
-          uint2 ov;
-          ov.x = pack_bf16(acc.x * inv, acc.y * inv);
-          ov.y = pack_bf16(acc.z * inv, acc.w * inv);
-          *reinterpret_cast<uint2*>(p.out + ((size_t)slot * p.n_q + head) * D + lane * 4) = ov;
-        }
-        if (lane == 0) p.split_counter[slot * p.n_kv + kvh] = 0;  // self-resetting for the next launch
-      }
     }
   }
 }
@@ -482,13 +466,13 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
 // lane per tile.  Masking only happens on the boundary tile.  (r01 v2 capture: the generic kernel was issue-bound
 // at 7 warps/SM, 37% issue-active, 3.5 TB/s.)
 // ------------------------------------------------------------------------------------------------
-template <int STAGES>
+template <int STAGES, int D>
 __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
-  constexpr int D = kHeadDim, TN = kPageSize;
+  constexpr int TN = kPageSize, P = kTilePitch, CH = D / 8, KS = D / 16;
   static_assert(TN == 16, "a KV tile is one page");
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* Ks = smem;
-  uint8_t* Vs = smem + STAGES * TN * D * 2;
+  uint8_t* Vs = smem + STAGES * TN * P * 2;
 
   pdl_launch_dependents();
   pdl_wait();
@@ -508,21 +492,21 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
   const int* btab = p.block_table + (size_t)slot * p.max_pages;
   const int n_tiles = kv_begin < kv_end ? (kv_end - kv_begin + TN - 1) / TN : 0;
 
-  float ot[8][4];  // O^T: [m-tile of 16 dims][rows g / g+8, heads 2c / 2c+1]
+  float ot[KS][4];  // O^T: [m-tile of 16 dims][rows g / g+8, heads 2c / 2c+1]
 #pragma unroll
-  for (int i = 0; i < 8; ++i) ot[i][0] = ot[i][1] = ot[i][2] = ot[i][3] = 0.f;
+  for (int i = 0; i < KS; ++i) ot[i][0] = ot[i][1] = ot[i][2] = ot[i][3] = 0.f;
   float m_run = -INFINITY, l_run = 0.f;  // softmax state of head g (replicated over the quad)
 
   if (n_tiles > 0) {
     auto load_kv = [&](int stage, int t0) {
       const int page = btab[t0 / kPageSize];
-      const size_t base = ((size_t)page * p.n_kv + kvh) * kPageSize * D;  // contiguous [16][128] block
+      const size_t base = ((size_t)page * p.n_kv + kvh) * kPageSize * D;  // contiguous [16][D] block
       const int valid = kv_end - t0;                                       // rows >= valid are zero-filled
-      uint8_t* kst = Ks + stage * TN * D * 2;
-      uint8_t* vst = Vs + stage * TN * D * 2;
+      uint8_t* kst = Ks + stage * TN * P * 2;
+      uint8_t* vst = Vs + stage * TN * P * 2;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int i = lane + 32 * k, j = i >> 4, ch = i & 15;
+      for (int k = 0; k < TN * CH / 32; ++k) {
+        const int i = lane + 32 * k, j = i / CH, ch = i % CH;
         const int nb = j < valid ? 16 : 0;
         cp_async16(kst + tile_off(j, ch), p.k_cache + base + (size_t)i * 8, nb);
         cp_async16(vst + tile_off(j, ch), p.v_cache + base + (size_t)i * 8, nb);
@@ -534,12 +518,12 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
       cp_async_commit();
     }
     // Q fragments straight from global memory: row g = head g of the group (zero for g >= G), rows 8..15 zero
-    uint32_t qf[8][2];
+    uint32_t qf[KS][2];
     {
       const bool ok = g < G;
       const __nv_bfloat16* qp = p.q + ((size_t)slot * p.n_q + kvh * G + (ok ? g : 0)) * D + 2 * c;
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
+      for (int ks = 0; ks < KS; ++ks) {
         qf[ks][0] = ok ? *reinterpret_cast<const uint32_t*>(qp + ks * 16) : 0u;
         qf[ks][1] = ok ? *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 8) : 0u;
       }
@@ -550,12 +534,12 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
       cp_async_commit();
       cp_async_wait<STAGES - 1>();
       __syncwarp();
-      const uint32_t kbase = smem_u32(Ks + (it % STAGES) * TN * D * 2);
-      const uint32_t vbase = smem_u32(Vs + (it % STAGES) * TN * D * 2);
+      const uint32_t kbase = smem_u32(Ks + (it % STAGES) * TN * P * 2);
+      const uint32_t vbase = smem_u32(Vs + (it % STAGES) * TN * P * 2);
       // ---- S = Q K^T for the 16 tokens of this page
       float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
+      for (int ks = 0; ks < KS; ++ks) {
         const int r = (lane & 7) + 8 * (lane >> 4);
         uint32_t b0, b1, b2, b3;
         ldsm_x4(kbase + tile_off(r, ks * 2 + ((lane >> 3) & 1)), b0, b1, b2, b3);
@@ -584,12 +568,12 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
       const float al_b = __shfl_sync(0xffffffffu, al, ((2 * c + 1) & 7) * 4);
       if (__any_sync(0xffffffffu, al != 1.f)) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { ot[i][0] *= al_a; ot[i][1] *= al_b; ot[i][2] *= al_a; ot[i][3] *= al_b; }
+        for (int i = 0; i < KS; ++i) { ot[i][0] *= al_a; ot[i][1] *= al_b; ot[i][2] *= al_a; ot[i][3] *= al_b; }
       }
       // ---- O^T += V^T P^T   (B fragments = the probabilities just computed)
       const uint32_t pb0 = pack_bf16(v0, v1), pb1 = pack_bf16(v2, v3);
 #pragma unroll
-      for (int mt = 0; mt < 8; ++mt) {
+      for (int mt = 0; mt < KS; ++mt) {
         const int r = (lane & 7) + 8 * (lane >> 4);
         uint32_t a[4];
         ldsm_x4_t(vbase + tile_off(r, mt * 2 + ((lane >> 3) & 1)), a[0], a[1], a[2], a[3]);
@@ -621,7 +605,7 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
       if (head >= G) continue;
       float* po = p.part_o + (((size_t)blockIdx.z * p.T + slot) * p.n_q + kvh * G + head) * D;
 #pragma unroll
-      for (int mt = 0; mt < 8; ++mt) {
+      for (int mt = 0; mt < KS; ++mt) {
         po[mt * 16 + g] = ot[mt][hh];
         po[mt * 16 + g + 8] = ot[mt][2 + hh];
       }
@@ -646,14 +630,16 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
           if (m == -INFINITY) continue;
           const float wgt = exp2f(m - M);
           L += __ldcg(p.part_ml + base * 2 + 1) * wgt;
-          const float4 v = __ldcg(reinterpret_cast<const float4*>(p.part_o + base * D) + lane);
-          acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
+          if (lane * 4 < D) {
+            const float4 v = __ldcg(reinterpret_cast<const float4*>(p.part_o + base * D) + lane);
+            acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
+          }
         }
         const float inv = L > 0.f ? 1.f / L : 0.f;
         uint2 ov;
         ov.x = pack_bf16(acc.x * inv, acc.y * inv);
         ov.y = pack_bf16(acc.z * inv, acc.w * inv);
-        *reinterpret_cast<uint2*>(p.out + ((size_t)slot * p.n_q + head) * D + lane * 4) = ov;
+        if (lane * 4 < D) *reinterpret_cast<uint2*>(p.out + ((size_t)slot * p.n_q + head) * D + lane * 4) = ov;
       }
       if (lane == 0) p.split_counter[slot * p.n_kv + kvh] = 0;  // self-resetting for the next launch
     }
@@ -666,7 +652,7 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
       const float inv = l > 0.f ? 1.f / l : 0.f;
       __nv_bfloat16* po = p.out + ((size_t)slot * p.n_q + kvh * G + head) * D;
 #pragma unroll
-      for (int mt = 0; mt < 8; ++mt) {
+      for (int mt = 0; mt < KS; ++mt) {
         po[mt * 16 + g] = __float2bfloat16(ot[mt][hh] * inv);
         po[mt * 16 + g + 8] = __float2bfloat16(ot[mt][2 + hh] * inv);
       }
@@ -676,33 +662,46 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
 
 constexpr int kPrefillNW = kPrefillTileRows / 16, kPrefillTN = 64, kPrefillStages = 2;
 constexpr int kDecodeStages = 3;
-constexpr int attn_smem(int nw, int tn, int stages) { return (nw * 16 + 2 * stages * tn) * kHeadDim * 2; }
-constexpr int kDecodeSmem = 2 * kDecodeStages * kPageSize * kHeadDim * 2;
+constexpr int attn_smem(int nw, int tn, int stages) { return (nw * 16 + 2 * stages * tn) * kTilePitch * 2; }
+constexpr int kDecodeSmem = 2 * kDecodeStages * kPageSize * kTilePitch * 2;
 
 void attn_set_attrs() {
-  cudaFuncSetAttribute(paged_attn_kernel<kPrefillNW, kPrefillTN, kPrefillStages, false>,
-                       cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem(kPrefillNW, kPrefillTN, kPrefillStages));
+  auto go = [&](auto dtag) {
+    constexpr int D = decltype(dtag)::value;
+    cudaFuncSetAttribute(paged_attn_kernel<kPrefillNW, kPrefillTN, kPrefillStages, false, D>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem(kPrefillNW, kPrefillTN, kPrefillStages));
+  };
+  go(std::integral_constant<int, 128>{});
+  go(std::integral_constant<int, 96>{});
+  go(std::integral_constant<int, 64>{});
 }
 void launch_attn_prefill(const LaunchCfg& lc, const AttnParams& p, int n_tiles) {
-  launch_k(lc, paged_attn_kernel<kPrefillNW, kPrefillTN, kPrefillStages, false>, dim3(n_tiles, p.n_kv, 1),
-           dim3(kPrefillNW * 32), attn_smem(kPrefillNW, kPrefillTN, kPrefillStages), p);
+  dispatch_head_dim(p.head_dim, [&](auto dtag) {
+    constexpr int D = decltype(dtag)::value;
+    launch_k(lc, paged_attn_kernel<kPrefillNW, kPrefillTN, kPrefillStages, false, D>, dim3(n_tiles, p.n_kv, 1),
+             dim3(kPrefillNW * 32), attn_smem(kPrefillNW, kPrefillTN, kPrefillStages), p);
+  });
 }
-// one-warp decode CTAs that can be resident at once on this GPU (occupancy query, cached per process)
+// one-warp decode CTAs that can be resident at once on this GPU (occupancy query, cached per process; the
+// three head_dim instantiations use the same shared-memory footprint, registers never bind before it does)
 int attn_decode_resident_ctas() {
   static int cached = 0;
   if (!cached) {
     int per_sm = 0, dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_attn_kernel<kDecodeStages>, 32, kDecodeSmem) !=
-            cudaSuccess || per_sm < 1)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_attn_kernel<kDecodeStages, 128>, 32,
+                                                      kDecodeSmem) != cudaSuccess || per_sm < 1)
       per_sm = 8;
     cached = per_sm * sms;
   }
   return cached;
 }
 void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots) {
-  launch_k(lc, decode_attn_kernel<kDecodeStages>, dim3(n_slots, p.n_kv, p.n_splits), dim3(32), kDecodeSmem, p);
+  dispatch_head_dim(p.head_dim, [&](auto dtag) {
+    constexpr int D = decltype(dtag)::value;
+    launch_k(lc, decode_attn_kernel<kDecodeStages, D>, dim3(n_slots, p.n_kv, p.n_splits), dim3(32), kDecodeSmem, p);
+  });
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -8,7 +8,7 @@
 namespace mq {
 
 constexpr int kPageSize = 16;  // tokens per KV page
-constexpr int kHeadDim = 128;  // only head_dim 128 is instantiated (Llama-3, Qwen2.5)
+inline bool head_dim_supported(int d) { return d == 128 || d == 96 || d == 64; }  // Llama-3 / Qwen2.5, Phi-3, small models
 
 struct LaunchCfg {
   cudaStream_t stream;
@@ -40,6 +40,7 @@ struct RopeKvParams {
   __nv_bfloat16* k_cache;     // layer base: [pages][n_kv][kPageSize][d]
   __nv_bfloat16* v_cache;
   int T, n_q, n_kv;
+  int head_dim;               // 128, 96 or 64
   L2Prefetch pf;              // optional: weights of an upcoming GEMM to pull into L2
 };
 void launch_rope_kv(const LaunchCfg& lc, const RopeKvParams& p);
@@ -56,6 +57,7 @@ struct AttnParams {
   float* part_o;       // decode split partials [splits][T][n_q][d]
   float* part_ml;      // [splits][T][n_q][2]
   int n_q, n_kv, T;
+  int head_dim;        // 128, 96 or 64
   int n_splits;        // decode only: every sequence is cut into n_splits equal 16-aligned ranges
   int* split_counter;  // decode only: [slots][n_kv] arrival counters (zero between launches)
   float scale_log2;    // softmax scale * log2(e)

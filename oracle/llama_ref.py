@@ -6,9 +6,10 @@ external Ollama / llama.cpp server (call site /root/reference/src/dispatcher.rs:
 NOT in /root/reference, not in Cargo.lock and not pinned to any version, so the published
 algorithm restated here is the Llama architecture as implemented by HuggingFace transformers 5.5.0
 (models/llama/modeling_llama.py: LlamaRMSNorm, rotate_half / apply_rotary_pos_emb, LlamaAttention with
-repeat_kv GQA, LlamaMLP SwiGLU; models/qwen2 adds a bias on q/k/v).
+repeat_kv GQA, LlamaMLP SwiGLU; models/qwen2 adds a bias on q/k/v; models/phi3 is the same arithmetic with the
+q/k/v and gate/up matrices stored fused - exactly the layout used here - and head_dim 96).
 
-Pinned against: HF LlamaForCausalLM / Qwen2ForCausalLM outputs on seeded random-init weights
+Pinned against: HF LlamaForCausalLM / Qwen2ForCausalLM / Phi3ForCausalLM outputs on seeded random-init weights
 (tests/golden/llama_tiny.json, generated in the build container by tests/golden/make_llama_golden.py).
 The reference itself pins nothing at this boundary.
 
@@ -155,6 +156,21 @@ def to_hf_state_dict(w: Dict[str, torch.Tensor], cfg: dict) -> Dict[str, torch.T
     return sd
 
 
+def to_hf_phi3_state_dict(w: Dict[str, torch.Tensor], cfg: dict) -> Dict[str, torch.Tensor]:
+    """HF Phi3 keeps qkv_proj = [q; k; v] and gate_up_proj = [gate; up] fused (modeling_phi3.py Phi3Attention /
+    Phi3MLP), i.e. our wqkv / w_gate_up verbatim."""
+    sd = {"model.embed_tokens.weight": w["embed"], "model.norm.weight": w["final_norm"], "lm_head.weight": w["lm_head"]}
+    for l in range(cfg["n_layers"]):
+        p, hp = f"layers.{l}.", f"model.layers.{l}."
+        sd[hp + "self_attn.qkv_proj.weight"] = w[p + "wqkv"]
+        sd[hp + "self_attn.o_proj.weight"] = w[p + "wo"]
+        sd[hp + "input_layernorm.weight"] = w[p + "attn_norm"]
+        sd[hp + "post_attention_layernorm.weight"] = w[p + "mlp_norm"]
+        sd[hp + "mlp.gate_up_proj.weight"] = w[p + "w_gate_up"]
+        sd[hp + "mlp.down_proj.weight"] = w[p + "w_down"]
+    return sd
+
+
 # named model geometries (BASELINE.json configs)
 LLAMA3_8B = dict(vocab=128256, hidden=4096, ffn=14336, n_layers=32, n_q_heads=32, n_kv_heads=8, head_dim=128,
                  qkv_bias=0, rope_theta=500000.0, rms_eps=1e-5)
@@ -164,3 +180,7 @@ TINY_LLAMA = dict(vocab=512, hidden=512, ffn=1024, n_layers=2, n_q_heads=4, n_kv
                   qkv_bias=0, rope_theta=500000.0, rms_eps=1e-5)
 TINY_QWEN = dict(vocab=512, hidden=512, ffn=1024, n_layers=2, n_q_heads=4, n_kv_heads=1, head_dim=128,
                  qkv_bias=1, rope_theta=1000000.0, rms_eps=1e-6)
+PHI3_MINI = dict(vocab=32064, hidden=3072, ffn=8192, n_layers=32, n_q_heads=32, n_kv_heads=32, head_dim=96,
+                 qkv_bias=0, rope_theta=10000.0, rms_eps=1e-5, family="phi3")
+TINY_PHI3 = dict(vocab=512, hidden=1536, ffn=1024, n_layers=2, n_q_heads=16, n_kv_heads=16, head_dim=96,
+                 qkv_bias=0, rope_theta=10000.0, rms_eps=1e-5, family="phi3")

@@ -6,6 +6,7 @@ max|delta| <= 2e-2 * max|logit|, and the engine's greedy token must be an oracle
 within 2e-2 * max|logit| of the oracle maximum (exact greedy-token equality with an fp32 run is not claimed)."""
 import json
 import os
+import time
 
 import numpy as np
 import pytest
@@ -17,7 +18,7 @@ import ollamamq_b200 as mq  # noqa: E402
 from oracle import llama_ref as R  # noqa: E402
 
 GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "llama_tiny.json")))
-CFGS = {"tiny_llama": R.TINY_LLAMA, "tiny_qwen": R.TINY_QWEN}
+CFGS = {"tiny_llama": R.TINY_LLAMA, "tiny_qwen": R.TINY_QWEN, "tiny_phi3": R.TINY_PHI3}
 MID = dict(vocab=2048, hidden=1024, ffn=2816, n_layers=3, n_q_heads=8, n_kv_heads=2, head_dim=128, qkv_bias=0,
            rope_theta=500000.0, rms_eps=1e-5)
 TOL = 2e-2
@@ -330,5 +331,57 @@ def test_config4_shape_256_users_short_prompts_sse():
                 _check_greedy(w, cfg, prompts[i], toks)
             st = wk.stats()
             assert st["decode_steps"] > 0 and d.user_stats("user255")["processed"] == 1
+        finally:
+            d.close()
+
+
+def test_full_size_phi3_mini_config4_logits_and_256_user_sse():
+    """BASELINE configs[3] at FULL size: Phi-3-mini geometry (hidden 3072, 32 MHA heads of head_dim 96, vocab 32 064 =
+    250.5 weight tiles, fused qkv / gate_up exactly as HF stores them), 256 users x 32-token prompts x 32 tokens over
+    /v1/chat/completions SSE.  Weights are initialised on the device and read back so the fp32 oracle sees the same
+    bf16 values."""
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs ~40 GB of HBM")
+    cfg = R.PHI3_MINI
+    rng = np.random.default_rng(4)
+    prompts = [rng.integers(0, cfg["vocab"], 32).astype("int32").tolist() for _ in range(256)]
+    with mq.Worker(0, mq.model_cfg(cfg, max_batch=256, max_seq=96, max_prefill_tokens=4096, use_graphs=1,
+                                   use_pdl=1)) as wk:
+        wk.init_random(seed=9, std=0.02)
+        w = {}
+        for name, shape in R.tensor_shapes(cfg).items():
+            w[name] = wk.read_tensor(name, torch.empty(shape, dtype=torch.bfloat16, device="cuda"))
+        long_prompt = rng.integers(0, cfg["vocab"], 300).astype("int32").tolist()
+        got = wk.forward_logits(long_prompt)[0]
+        ref = R.forward(w, cfg, long_prompt, torch.float32)[-1].cpu().numpy()
+        cmp16 = R.forward(w, cfg, long_prompt, torch.bfloat16)[-1].float().cpu().numpy()
+        scale = np.abs(ref).max()
+        rel, rel16 = np.linalg.norm(got - ref) / np.linalg.norm(ref), np.linalg.norm(cmp16 - ref) / np.linalg.norm(ref)
+        print("phi3-mini full size: engine rel-L2 %.4f, bf16 torch comparator rel-L2 %.4f, max|d| %.4f of max|logit| %.3f"
+              % (rel, rel16, np.abs(got - ref).max(), scale))
+        assert rel <= 1.25 * rel16 + 1e-3, (rel, rel16)          # same bar as the Llama-3-8B full-size test
+        assert np.abs(got - ref).max() <= 8e-2 * scale
+        d = mq.Dispatcher([wk], capacity=256)
+        try:
+            t0 = time.time()
+            streams = [d.submit("user%03d" % i, endpoint=2, prompt_tokens=p, max_new_tokens=32, stream=1)
+                       for i, p in enumerate(prompts)]
+            d.drain(240000)
+            dt = time.time() - t0
+            import re
+            for i, s in enumerate(streams):
+                assert s.rc == 0 and s.content_type == "text/event-stream", (i, s.rc, s.err)
+                events = [e for e in s.body.decode().split("\n\n") if e]
+                assert events[-1] == "data: [DONE]" and len(events) == 32 + 2
+            for i in (0, 131, 255):
+                toks = [int(x) for x in re.findall(r'"content":" t(\d+)"', streams[i].body.decode())]
+                seq = prompts[i] + toks
+                r = R.forward(w, cfg, seq[:-1], torch.float32)
+                for j, tok in enumerate(toks):
+                    row = r[len(prompts[i]) - 1 + j]
+                    assert (row.max() - row[tok]).item() <= 8e-2 * row.abs().max().item(), (i, j)
+            st = wk.stats()
+            print("config 4: 256 users x 32/32 in %.2f s wall (%.0f tok/s incl. python callbacks), decode steps %d"
+                  % (dt, 256 * 32 / dt, st["decode_steps"]))
         finally:
             d.close()

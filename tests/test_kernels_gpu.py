@@ -205,7 +205,7 @@ def test_add_rmsnorm(H, rows, planes, f32):
     assert _relerr(x2, ref_x[idx.long()]) < 4e-3
 
 
-def _inv_freq(theta):
+def _inv_freq(theta, D=D):
     return 1.0 / (theta ** (torch.arange(0, D, 2, dtype=torch.float32) / D))
 
 
@@ -214,12 +214,13 @@ def _rope_ref(x, pos, inv_freq):
     ang = pos.float()[:, None] * inv_freq[None, :]
     cos = torch.cat([ang.cos(), ang.cos()], -1)[:, None, :]
     sin = torch.cat([ang.sin(), ang.sin()], -1)[:, None, :]
+    D = x.shape[-1]
     x1, x2 = x[..., : D // 2], x[..., D // 2:]
     rot = torch.cat([-x2, x1], -1)
     return x * cos + rot * sin
 
 
-def _make_cache(n_slots, max_pages, n_kv, seed=0):
+def _make_cache(n_slots, max_pages, n_kv, seed=0, D=D):
     g = torch.Generator().manual_seed(seed)
     n_pages = n_slots * max_pages + 1
     perm = torch.randperm(n_pages - 1, generator=g) + 1  # page 0 reserved as scratch
@@ -229,14 +230,16 @@ def _make_cache(n_slots, max_pages, n_kv, seed=0):
     return bt, k, v
 
 
-@pytest.mark.parametrize("f32,planes,bias", [(True, 3, False), (False, 1, True)])
-def test_rope_kv(f32, planes, bias):
+@pytest.mark.parametrize("f32,planes,bias,D,n_kv", [(True, 3, False, 128, 8), (False, 1, True, 128, 8),
+                                                     (True, 2, False, 96, 32), (False, 1, False, 96, 32),
+                                                     (True, 4, True, 64, 4)])
+def test_rope_kv(f32, planes, bias, D, n_kv):
     m = _lib()
-    n_q, n_kv, T, n_slots, max_pages = 32, 8, 40, 3, 8
+    n_q, T, n_slots, max_pages = 32, 40, 3, 8
     qkv_dim = (n_q + 2 * n_kv) * D
-    theta = 500000.0
-    inv = _inv_freq(theta).to(dev())
-    bt, kc, vc = _make_cache(n_slots, max_pages, n_kv)
+    theta = 500000.0 if D == 128 else 10000.0
+    inv = _inv_freq(theta, D).to(dev())
+    bt, kc, vc = _make_cache(n_slots, max_pages, n_kv, D=D)
     bt, kc, vc = bt.to(dev()), kc.to(dev()), vc.to(dev())
     slot = torch.randint(0, n_slots, (T,), dtype=torch.int32)
     # unique (slot, pos) pairs
@@ -258,7 +261,7 @@ def test_rope_kv(f32, planes, bias):
         full = full + b.float()
     q_out = torch.zeros(T, n_q * D, device=dev(), dtype=torch.bfloat16)
     rc = m.lib.mq_debug_rope_kv(P(qkv), int(f32), planes, T * qkv_dim, P(b), P(pos), P(slot), P(bt), max_pages,
-                                P(inv), P(q_out), P(kc), P(vc), T, n_q, n_kv)
+                                P(inv), P(q_out), P(kc), P(vc), T, n_q, n_kv, D)
     assert rc == 0, m.last_error()
     q_ref = _rope_ref(full[:, : n_q * D].view(T, n_q, D), pos, inv)
     k_ref = _rope_ref(full[:, n_q * D:(n_q + n_kv) * D].view(T, n_kv, D), pos, inv)
@@ -277,7 +280,7 @@ def _attn_ref(q, k, v, q_pos):
     G = n_q // n_kv
     kk = k.repeat_interleave(G, dim=1)
     vv = v.repeat_interleave(G, dim=1)
-    s = torch.einsum("qhd,khd->hqk", q, kk) / math.sqrt(D)
+    s = torch.einsum("qhd,khd->hqk", q, kk) / math.sqrt(q.shape[-1])
     kpos = torch.arange(k.shape[0], device=q.device)
     mask = kpos[None, :] <= q_pos[:, None]
     s = s.masked_fill(~mask[None], float("-inf"))
@@ -292,13 +295,13 @@ def _gather_kv(kc, vc, bt_row, L):
     return kc[pages, :, off, :].float(), vc[pages, :, off, :].float()
 
 
-@pytest.mark.parametrize("n_q,n_kv", [(32, 8), (28, 4)])
-def test_attn_prefill(n_q, n_kv):
+@pytest.mark.parametrize("n_q,n_kv,D", [(32, 8, 128), (28, 4, 128), (32, 32, 96), (12, 4, 96), (8, 2, 64)])
+def test_attn_prefill(n_q, n_kv, D):
     m = _lib()
     G = n_q // n_kv
     tok_per_tile = 64 // G   # kPrefillTileRows / G
     n_slots, max_pages = 3, 40
-    bt, kc, vc = _make_cache(n_slots, max_pages, n_kv, seed=1)
+    bt, kc, vc = _make_cache(n_slots, max_pages, n_kv, seed=1, D=D)
     kc = torch.randn_like(kc.float()).bfloat16()
     vc = torch.randn_like(vc.float()).bfloat16()
     bt, kc, vc = bt.to(dev()), kc.to(dev()), vc.to(dev())
@@ -315,7 +318,7 @@ def test_attn_prefill(n_q, n_kv):
     tiles_t = torch.tensor(tiles, dtype=torch.int32, device=dev())
     out = torch.zeros(T, n_q, D, device=dev(), dtype=torch.bfloat16)
     rc = m.lib.mq_debug_attn_prefill(P(q), P(kc), P(vc), P(bt), max_pages, P(tiles_t), len(tiles), P(out), n_q,
-                                     n_kv, T, 1.0 / math.sqrt(D))
+                                     n_kv, T, 1.0 / math.sqrt(D), D)
     assert rc == 0, m.last_error()
     r0 = 0
     for slot, ctx, L in seqs:
@@ -327,11 +330,13 @@ def test_attn_prefill(n_q, n_kv):
         r0 += L
 
 
-@pytest.mark.parametrize("n_q,n_kv,n_splits", [(32, 8, 4), (32, 8, 1), (28, 4, 3), (32, 8, 8), (32, 8, 2)])
-def test_attn_decode(n_q, n_kv, n_splits):
+@pytest.mark.parametrize("n_q,n_kv,n_splits,D", [(32, 8, 4, 128), (32, 8, 1, 128), (28, 4, 3, 128), (32, 8, 8, 128),
+                                                  (32, 8, 2, 128), (32, 32, 1, 96), (32, 32, 3, 96), (12, 4, 2, 96),
+                                                  (8, 2, 4, 64), (8, 1, 1, 64)])
+def test_attn_decode(n_q, n_kv, n_splits, D):
     m = _lib()
     n_slots, max_pages = 7, 48
-    bt, kc, vc = _make_cache(n_slots, max_pages, n_kv, seed=2)
+    bt, kc, vc = _make_cache(n_slots, max_pages, n_kv, seed=2, D=D)
     kc = torch.randn_like(kc.float()).bfloat16()
     vc = torch.randn_like(vc.float()).bfloat16()
     bt, kc, vc = bt.to(dev()), kc.to(dev()), vc.to(dev())
@@ -345,7 +350,7 @@ def test_attn_decode(n_q, n_kv, n_splits):
     for rep in range(2):  # second launch checks the arrival counters reset themselves
         out.zero_()
         rc = m.lib.mq_debug_attn_decode(P(q), P(kc), P(vc), P(bt), max_pages, P(pos), P(out), P(part_o), P(part_ml),
-                                        P(counter), n_q, n_kv, n_slots, n_splits, 1.0 / math.sqrt(D))
+                                        P(counter), n_q, n_kv, n_slots, n_splits, 1.0 / math.sqrt(D), D)
         assert rc == 0, m.last_error()
         assert int(counter.abs().sum()) == 0
         for s in range(n_slots):
