@@ -345,7 +345,7 @@ def test_full_size_phi3_mini_config4_logits_and_256_user_sse():
     cfg = R.PHI3_MINI
     rng = np.random.default_rng(4)
     prompts = [rng.integers(0, cfg["vocab"], 32).astype("int32").tolist() for _ in range(256)]
-    with mq.Worker(0, mq.model_cfg(cfg, max_batch=256, max_seq=96, max_prefill_tokens=4096, use_graphs=1,
+    with mq.Worker(0, mq.model_cfg(cfg, max_batch=256, max_seq=320, max_prefill_tokens=4096, use_graphs=1,
                                    use_pdl=1)) as wk:
         wk.init_random(seed=9, std=0.02)
         w = {}
