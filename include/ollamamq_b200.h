@@ -273,6 +273,11 @@ int mq_debug_attn_prefill(const void* q, const void* k_cache, const void* v_cach
 int mq_debug_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* block_table,
                          int max_pages, const int* pos, void* out, float* part_o, float* part_ml, int* split_counter,
                          int n_q, int n_kv, int n_slots, int n_splits, float scale, int head_dim);
+/* Timeline of the worker's most recent decode step (worker opened with MQ_TRACE=1 in the environment): for launch
+ * slot i, out[4*i+0..3] = %globaltimer ns of {first CTA start, first CTA past its dependency wait, first CTA end,
+ * ~(last CTA end)}; untouched slots read as all-ones.  Slots: 1 + 8*layer + {0 norm, 1 qkv, 2 rope, 3 attention,
+ * 4 o-proj, 5 norm, 6 gate/up, 7 down}; 510 final norm, 511 LM head.  Returns the slot count copied (<= 512). */
+int mq_debug_trace_read(mq_worker* w, unsigned long long* out, int32_t max_slots);
 int mq_debug_argmax(const float* logits, int rows, int V, int ldl, int* out_tokens, const int* dst_slot,
                     int* cur_token, int* pos_inc, const int* active);
 int mq_debug_init_normal(void* w, unsigned long long n, unsigned long long seed, float std);

@@ -90,7 +90,7 @@ int mq_debug_rope_kv(const void* qkv, int qkv_is_f32, int n_planes, long long pl
                      const float* inv_freq, void* q_out, void* k_cache, void* v_cache, int T, int n_q, int n_kv,
                      int head_dim) {
   if (!head_dim_supported(head_dim)) { mq::set_last_error("head_dim must be 128, 96 or 64"); return MQ_ERR_INVAL; }
-  RopeKvParams p;
+  RopeKvParams p = {};
   p.qkv = qkv; p.qkv_is_f32 = qkv_is_f32 != 0; p.n_planes = n_planes; p.plane_stride = plane_stride;
   p.bias = (const __nv_bfloat16*)bias; p.pos = pos; p.slot_of_tok = slot_of_tok; p.block_table = block_table;
   p.max_pages = max_pages; p.inv_freq = inv_freq; p.q_out = (__nv_bfloat16*)q_out;
@@ -126,6 +126,7 @@ int mq_debug_attn_decode(const void* q, const void* k_cache, const void* v_cache
   p.block_table = block_table; p.max_pages = max_pages; p.pos = pos; p.out = (__nv_bfloat16*)out;
   p.part_o = part_o; p.part_ml = part_ml; p.split_counter = split_counter; p.n_q = n_q; p.n_kv = n_kv; p.T = n_slots;
   p.n_splits = n_splits; p.scale_log2 = scale * 1.4426950408889634f;
+  attn_set_attrs();
   launch_attn_decode(LaunchCfg{0, false}, p, n_slots);
   return check_cuda("mq_debug_attn_decode");
 }

@@ -50,7 +50,7 @@ static int add_tensor(mq_worker* w, const std::string& name, size_t n_elems, __n
 }
 
 static int decode_splits(int m_tiles, int k_blocks) {
-  int s = 148 / m_tiles;
+  int s = std::min(148 / m_tiles, kMaxSplitPlanes);  // the reduce kernels sum at most kMaxSplitPlanes planes
   if (s < 1) s = 1;
   while (s > 1 && (k_blocks + s - 1) / s < 8) --s;       // keep >= 8 k-blocks (32 KiB of weights per row tile)
   while (s > 1 && (s - 1) * ((k_blocks + s - 1) / s) >= k_blocks) --s;  // every split non-empty
@@ -127,6 +127,16 @@ static int worker_alloc(mq_worker* w) {
     // Measured on B200 (r01): the hints make the decode step slower (4.71 vs 4.44 ms): opt-in only.
     const char* e2 = getenv("MQ_L2_PREFETCH");
     w->l2_prefetch = e2 && e2[0] == '1';
+    // MQ_TRACE=1: per-launch %globaltimer stamps of the most recent pass (tools/decode_timeline.py)
+    const char* e3 = getenv("MQ_TRACE");
+    if (e3 && e3[0] == '1') {
+      if (8 * c.n_layers + 1 > kTraceSlots - 2) {
+        set_last_error("MQ_TRACE: more launches per pass than trace slots");
+        return MQ_ERR_INVAL;
+      }
+      if ((rc = dalloc(&w->d_trace, (size_t)kTraceSlots * 4))) return rc;
+      CUDA_TRY(cudaMemsetAsync(w->d_trace, 0xFF, (size_t)kTraceSlots * 4 * 8, w->stream));
+    }
   }
   if ((rc = dalloc(&w->d_split_counter, (size_t)MBp * c.n_kv_heads))) return rc;
   CUDA_TRY(cudaMemsetAsync(w->d_split_counter, 0, (size_t)MBp * c.n_kv_heads * 4, w->stream));
@@ -285,10 +295,13 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
     const L2Prefetch pf_rope = pf_none;                                                              // KV stream follows: too early
     const L2Prefetch pf_attn = pfon ? L2Prefetch{lw.wo, b_o} : pf_none;                              // tail of attention -> O GEMM
     const L2Prefetch pf_norm2 = pfon ? L2Prefetch{lw.w_gate_up, std::min(b_gu, (size_t)64 << 20)} : pf_none;  // -> gate/up GEMM
+    auto tr = [&]() { return Trace{w->d_trace, (int)nl}; };  // timeline slot of the launch about to be issued
+    auto tr_gemm = [&](GemmPlan& g) { g.p.tr = tr(); g.sk.tr = tr(); };
     if (!fused) {
       launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, prev_planes, (long long)MBp * H, lw.attn_norm, w->x, nullptr, a.T,
-                         H, c.rms_eps, pf_norm1); ++nl;
+                         H, c.rms_eps, pf_norm1, tr()); ++nl;
     }
+    tr_gemm(pp->qkv[l]);
     if (gemm_launch(pp->qkv[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     RopeKvParams rp;
     rp.qkv = w->qkv_part; rp.qkv_is_f32 = f32p; rp.n_planes = pp->s_qkv; rp.plane_stride = (long long)MBp * w->qkv_dim;
@@ -298,6 +311,7 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
     rp.v_cache = w->v_cache + (size_t)l * w->cache_layer_stride;
     rp.T = a.T; rp.n_q = c.n_q_heads; rp.n_kv = c.n_kv_heads; rp.head_dim = c.head_dim;
     rp.pf = pf_rope;
+    rp.tr = tr();
     launch_rope_kv(lc, rp); ++nl;
     AttnParams ap = {};
     ap.head_dim = c.head_dim;
@@ -305,15 +319,19 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
     ap.max_pages = w->max_pages; ap.tiles = w->d_tiles; ap.pos = a.pos; ap.out = w->attn; ap.part_o = w->part_o;
     ap.part_ml = w->part_ml; ap.n_q = c.n_q_heads; ap.n_kv = c.n_kv_heads; ap.T = a.T; ap.n_splits = a.n_splits;
     ap.pf = pf_attn;
+    ap.tr = tr();
     ap.split_counter = w->d_split_counter; ap.scale_log2 = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
     if (a.decode) { launch_attn_decode(lc, ap, a.T); ++nl; }
     else { launch_attn_prefill(lc, ap, a.n_tiles); ++nl; }
+    tr_gemm(pp->o[l]);
     if (gemm_launch(pp->o[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     if (!fused) {
       launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, pp->s_o, (long long)MBp * H, lw.mlp_norm, w->x, nullptr, a.T, H,
-                         c.rms_eps, pf_norm2); ++nl;
+                         c.rms_eps, pf_norm2, tr()); ++nl;
     }
+    tr_gemm(pp->gate_up[l]);
     if (gemm_launch(pp->gate_up[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
+    tr_gemm(pp->down[l]);
     if (gemm_launch(pp->down[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     prev_planes = pp->s_down;
   }
@@ -327,9 +345,10 @@ static int run_head(mq_worker* w, bool decode, const int* row_idx, int rows, Pas
   const LaunchCfg lc{w->stream, c.use_pdl != 0};
   const int MBp = round_up(w->MB, 16);
   launch_add_rmsnorm(lc, w->h, w->proj_part, decode, pp->s_down, (long long)MBp * c.hidden, w->final_norm, w->x_last,
-                     row_idx, rows, c.hidden, c.rms_eps);
+                     row_idx, rows, c.hidden, c.rms_eps, L2Prefetch{nullptr, 0}, Trace{w->d_trace, kTraceSlots - 2});
   GemmPlan* g = get_lm_plan(w, rows);
   if (!g) return MQ_ERR_CUDA;
+  g->p.tr = g->sk.tr = Trace{w->d_trace, kTraceSlots - 1};
   if (gemm_launch(*g, lc) != cudaSuccess) return MQ_ERR_CUDA;
   *n_launch += 2;
   return MQ_OK;
@@ -583,9 +602,16 @@ static int launch_decode(mq_worker* w) {
   if (hi < 0) return MQ_OK;
   const int Bcap = std::min(MBp, round_up(hi + 1, 16));
   // split-KV count: fill the GPU with one wave of single-warp CTAs, keep >= 64 tokens per split
-  int n_splits = attn_decode_resident_ctas() / (Bcap * w->cfg.n_kv_heads);
-  n_splits = std::max(1, std::min({n_splits, kMaxDecodeSplits, std::max(1, max_ctx / 64)}));
+  // split the KV range only when (slots x kv heads) alone leaves SMs idle: every split pays for partial rows, a fence,
+  // a counter and the combine (r01 timeline: 64 slots x 8 kv heads unsplit 25 us per layer, 2-way split 33 us)
+  const int base_ctas = Bcap * w->cfg.n_kv_heads, sms = w->sm_count;
+  int n_splits = 1;
+  if (base_ctas < 2 * sms) n_splits = (3 * sms + base_ctas - 1) / base_ctas;
+  n_splits = std::max(1, std::min({n_splits, attn_decode_resident_ctas() / base_ctas, kMaxDecodeSplits,
+                                   std::max(1, max_ctx / 64)}));
+  if (const char* e = getenv("MQ_ATTN_SPLITS")) n_splits = std::max(1, std::min(atoi(e), kMaxDecodeSplits));  // experiments
   upload_slots(w);
+  if (w->d_trace) cudaMemsetAsync(w->d_trace, 0xFF, (size_t)kTraceSlots * 4 * 8, w->stream);  // re-arm the timeline
 
   mq_worker::Flight f;
   f.timed = w->timing;
@@ -999,6 +1025,7 @@ int mq_worker_open(int32_t gpu, const mq_model_cfg* cfg, mq_worker** out) {
   w->cfg = c;
   w->cfg.model_name[sizeof(w->cfg.model_name) - 1] = 0;
   w->gpu = gpu;
+  w->sm_count = prop.multiProcessorCount;
   CUDA_TRY(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
   gemm_set_attrs();
   attn_set_attrs();
@@ -1191,6 +1218,20 @@ int mq_worker_reset_stats(mq_worker* w) {
   std::lock_guard<std::mutex> g(w->stats_mu);
   w->stats = mq_worker_stats{};
   return MQ_OK;
+}
+int mq_debug_trace_read(mq_worker* w, unsigned long long* out, int32_t max_slots) {
+  if (!w || !out || max_slots < 1) return MQ_ERR_INVAL;
+  if (!w->d_trace) {
+    set_last_error("mq_debug_trace_read: the worker was opened without MQ_TRACE=1");
+    return MQ_ERR_INVAL;
+  }
+  const int n = std::min((int)max_slots, kTraceSlots);
+  const int rc = run_job(w, [=] {
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) return (int)MQ_ERR_CUDA;
+    if (cudaMemcpy(out, w->d_trace, (size_t)n * 4 * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return (int)MQ_ERR_CUDA;
+    return (int)MQ_OK;
+  });
+  return rc < 0 ? rc : n;
 }
 int mq_worker_set_timing(mq_worker* w, int32_t enable) {
   if (!w) return MQ_ERR_INVAL;

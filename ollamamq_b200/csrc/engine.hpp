@@ -64,9 +64,12 @@ struct mq_req {
   bool has_deadline = false;
 };
 
+constexpr int kTraceSlots = 512;
+
 struct mq_worker {
   mq_model_cfg cfg{};
   int gpu = 0;
+  int sm_count = 148;
   cudaStream_t stream = nullptr;
   int qkv_dim = 0, max_pages = 0, n_pages = 0, MT = 0, MB = 0;
   double p_mm_bytes = 0, kv_bytes_per_tok = 0;
@@ -91,6 +94,7 @@ struct mq_worker {
   int* d_split_counter = nullptr;  // [MB][n_kv] arrival counters of the split-KV decode attention
   int* d_norm_counters = nullptr;  // [2 * layers] arrival counters of the fused norm prologues (zeroed by embed)
   bool fuse_norm = true;
+  unsigned long long* d_trace = nullptr;  // MQ_TRACE=1: [kTraceSlots][4] %globaltimer stamps of the latest pass
   bool l2_prefetch = true;   // decode: small kernels pull the next GEMM's weights into L2 (MQ_L2_PREFETCH=0 disables)
   // pinned host mirrors / staging
   int *h_pos = nullptr, *h_active = nullptr, *h_block_table = nullptr;

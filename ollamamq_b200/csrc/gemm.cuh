@@ -50,6 +50,7 @@ struct GemmParams {
   long long norm_plane_stride;
   int norm_planes, norm_H, norm_ctas;
   float norm_eps;
+  Trace tr;                      // optional timeline stamps (MQ_TRACE=1)
 };
 
 constexpr int kGemmThreads = 192;
@@ -121,6 +122,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int nkb = min(p.kb_per_split, p.k_blocks - kb0);
 
   if (warp == 0 && lane == 0) {
+    trace_begin(p.tr);
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmC);
@@ -151,6 +153,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (kDual) tma_load_2d(st + kATileBytes, &tmA, &full_bar[s], (kb0 + s) * kBlockK, m0 + p.a2_row_off, p.w_policy);
       }
       pdl_wait();  // activations are produced by the previous kernel
+      trace_waited(p.tr);
       if (p.norm_h) {  // ... or by the fused norm prologue of this very grid
         while (ld_acquire_s32(p.norm_counter) < p.T) {
         }
@@ -289,6 +292,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (threadIdx.x == 0) trace_end(p.tr);
 }
 
 }  // namespace mq

@@ -31,6 +31,7 @@ struct StreamKParams {
   float* ws;       // [P][planes][BN*128] fp32 partial accumulators
   int* flags;      // [P] arrival counters, zero between launches
   unsigned long long w_policy;
+  Trace tr;        // optional timeline stamps (MQ_TRACE=1)
 };
 
 // No smem staging tile here: with <= 64 token columns the finisher stores straight from registers (a warp writes
@@ -107,6 +108,7 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
+  if (threadIdx.x == 0) trace_begin(p.tr);
 
   if (warp == 0) {
     if (lane == 0 && total > 0) {
@@ -127,6 +129,7 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         advance(t, kb, kb_end);
       }
       pdl_wait();
+      trace_waited(p.tr);
       {
         int t2 = tile_last, k2 = seg_a(t2), ke2 = seg_b(t2);
         for (int i = 0; i < npre; ++i) {
@@ -290,6 +293,7 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (threadIdx.x == 0) trace_end(p.tr);
 }
 
 }  // namespace mq

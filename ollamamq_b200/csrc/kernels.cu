@@ -15,6 +15,8 @@
 //   argmax           greedy sampler + device-side advance of (cur_token, pos) so decode steps chain on the GPU
 #include "kernels.cuh"
 #include <type_traits>
+#include <cstdlib>
+#include <algorithm>
 #include "ptx.cuh"
 
 namespace mq {
@@ -68,10 +70,11 @@ template <bool F32>
 __global__ void add_rmsnorm_kernel(float* __restrict__ h, const void* __restrict__ partial, int n_planes,
                                    long long plane_stride, const __nv_bfloat16* __restrict__ gamma,
                                    __nv_bfloat16* __restrict__ x, const int* __restrict__ row_idx, int H, float eps,
-                                   L2Prefetch pf) {
+                                   L2Prefetch pf, Trace tr) {
   pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
-  if (threadIdx.x == 0) l2_prefetch_slice(pf, blockIdx.x, gridDim.x);  // weights: independent of the previous kernel
+  if (threadIdx.x == 0) { trace_begin(tr); l2_prefetch_slice(pf, blockIdx.x, gridDim.x); }  // weights: independent of the previous kernel
   pdl_wait();
+  if (threadIdx.x == 0) trace_waited(tr);
   const int row = blockIdx.x;
   const int src = row_idx ? row_idx[row] : row;
   const int nthr = blockDim.x;
@@ -111,17 +114,18 @@ __global__ void add_rmsnorm_kernel(float* __restrict__ h, const void* __restrict
     o.y = pack_bf16(v[j].z * rstd * bf16_lo(gm.y), v[j].w * rstd * bf16_hi(gm.y));
     reinterpret_cast<uint2*>(x + (size_t)row * H)[i4] = o;
   }
+  if (threadIdx.x == 0) trace_end(tr);
 }
 void launch_add_rmsnorm(const LaunchCfg& lc, float* h, const void* partial, bool partial_is_f32, int n_planes,
                         long long plane_stride, const __nv_bfloat16* gamma, __nv_bfloat16* x, const int* row_idx,
-                        int rows, int H, float eps, L2Prefetch pf) {
+                        int rows, int H, float eps, L2Prefetch pf, Trace tr) {
   const int thr = H / 16;  // H % 512 == 0 is checked at model load
   if (partial_is_f32)
     launch_k(lc, add_rmsnorm_kernel<true>, dim3(rows), dim3(thr), 0, h, partial, n_planes, plane_stride, gamma, x,
-             row_idx, H, eps, pf);
+             row_idx, H, eps, pf, tr);
   else
     launch_k(lc, add_rmsnorm_kernel<false>, dim3(rows), dim3(thr), 0, h, partial, n_planes, plane_stride, gamma, x,
-             row_idx, H, eps, pf);
+             row_idx, H, eps, pf, tr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -172,8 +176,9 @@ static void dispatch_head_dim(int d, F&& f) {
 template <bool F32, int D>
 __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
   pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
-  if (threadIdx.x == 0) l2_prefetch_slice(p.pf, blockIdx.x + gridDim.x * blockIdx.y, gridDim.x * gridDim.y);
+  if (threadIdx.x == 0) { trace_begin(p.tr); l2_prefetch_slice(p.pf, blockIdx.x + gridDim.x * blockIdx.y, gridDim.x * gridDim.y); }
   pdl_wait();
+  if (threadIdx.x == 0) trace_waited(p.tr);
   constexpr int HALF = D / 2;  // 16 threads per head x 4 pairs cover HALF <= 64 (threads beyond HALF idle: d = 96, 64)
   const int t = blockIdx.x;
   const int hd = blockIdx.y * 16 + (threadIdx.x >> 4);  // q heads, then k heads, then v heads
@@ -211,6 +216,7 @@ __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
   }
   *reinterpret_cast<uint2*>(dst + i) = lo;
   *reinterpret_cast<uint2*>(dst + i + HALF) = hi;
+  if (threadIdx.x == 0) trace_end(p.tr);  // thread 0 always owns a live (head, pair) of its CTA
 }
 void launch_rope_kv(const LaunchCfg& lc, const RopeKvParams& p) {
   const dim3 grid(p.T, (p.n_q + 2 * p.n_kv + 15) / 16);
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
   uint8_t* Vs = smem + STAGES * TN * P * 2;
 
   pdl_launch_dependents();
-  pdl_wait();
+  if (threadIdx.x == 0) trace_begin(p.tr);
 
   const int lane = threadIdx.x;
   const int g = lane >> 2, c = lane & 3;
@@ -512,10 +518,25 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
         cp_async16(vst + tile_off(j, ch), p.v_cache + base + (size_t)i * 8, nb);
       }
     };
+    // The first STAGES-1 pages are requested BEFORE the dependency wait whenever they hold only tokens of earlier
+    // steps (everything but the row the rope kernel of this very step is writing): this CTA is usually resident a
+    // few us before the wait returns, and the r01 timeline shows ~6 us of prologue + first-load latency per layer.
+    const bool early = kv_begin + min(STAGES - 1, n_tiles) * TN <= kv_len - 1;
+    if (early) {
 #pragma unroll
-    for (int s0 = 0; s0 < STAGES - 1; ++s0) {
-      if (s0 < n_tiles) load_kv(s0, kv_begin + s0 * TN);
-      cp_async_commit();
+      for (int s0 = 0; s0 < STAGES - 1; ++s0) {
+        if (s0 < n_tiles) load_kv(s0, kv_begin + s0 * TN);
+        cp_async_commit();
+      }
+    }
+    pdl_wait();
+    if (lane == 0) trace_waited(p.tr);
+    if (!early) {
+#pragma unroll
+      for (int s0 = 0; s0 < STAGES - 1; ++s0) {
+        if (s0 < n_tiles) load_kv(s0, kv_begin + s0 * TN);
+        cp_async_commit();
+      }
     }
     // Q fragments straight from global memory: row g = head g of the group (zero for g >= G), rows 8..15 zero
     uint32_t qf[KS][2];
@@ -583,6 +604,10 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
     }
   }
 
+  if (n_tiles == 0) {  // empty split: still order this CTA's writes after the previous kernel
+    pdl_wait();
+    if (lane == 0) trace_waited(p.tr);
+  }
   // KV streaming of this CTA is over: use the combine tail to pull the O-projection weights towards L2
   // (issued late on purpose - the 135 MB KV stream would evict anything prefetched earlier)
   if (lane == 0)
@@ -610,36 +635,53 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
         po[mt * 16 + g + 8] = ot[mt][2 + hh];
       }
     }
-    // ---- in-kernel combine: the split that arrives last merges all partials of this (slot, kv head)
+    // ---- in-kernel combine: the split that arrives last merges all partials of this (slot, kv head).
+    // r01 timeline: the first version walked head by head with three dependent L2 round trips each (~8 us of
+    // tail per layer); here the (m, l) pairs of all heads x splits arrive in one round trip, the weights are
+    // formed from shared memory, and every head's partial rows are requested before the first one is consumed.
     __threadfence();
     int old = 0;
     if (lane == 0) old = atomicAdd(p.split_counter + slot * p.n_kv + kvh, 1);
     old = __shfl_sync(0xffffffffu, old, 0);
     if (old == p.n_splits - 1) {
       __threadfence();
+      const int S = p.n_splits;  // <= kMaxDecodeSplits
+      float2* ml = reinterpret_cast<float2*>(smem);  // [G][S]; the KV ring is idle by now
+      __syncwarp();
+      for (int i = lane; i < G * S; i += 32) {
+        const int hg = i / S, sp = i % S;
+        const size_t base = ((size_t)sp * p.T + slot) * p.n_q + kvh * G + hg;
+        ml[i] = __ldcg(reinterpret_cast<const float2*>(p.part_ml + base * 2));
+      }
+      __syncwarp();
+      const bool act = lane * 4 < D;
       for (int hg = 0; hg < G; ++hg) {
         const int head = kvh * G + hg;
+        float4 v[kMaxDecodeSplits];
+#pragma unroll
+        for (int sp = 0; sp < kMaxDecodeSplits; ++sp) {
+          v[sp] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (sp < S && act)
+            v[sp] = __ldcg(reinterpret_cast<const float4*>(p.part_o + (((size_t)sp * p.T + slot) * p.n_q + head) * D) + lane);
+        }
         float M = -INFINITY;
-        for (int sp = 0; sp < p.n_splits; ++sp)
-          M = fmaxf(M, __ldcg(p.part_ml + (((size_t)sp * p.T + slot) * p.n_q + head) * 2));
+        for (int sp = 0; sp < S; ++sp) M = fmaxf(M, ml[hg * S + sp].x);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         float L = 0.f;
-        for (int sp = 0; sp < p.n_splits; ++sp) {
-          const size_t base = ((size_t)sp * p.T + slot) * p.n_q + head;
-          const float m = __ldcg(p.part_ml + base * 2);
-          if (m == -INFINITY) continue;
-          const float wgt = exp2f(m - M);
-          L += __ldcg(p.part_ml + base * 2 + 1) * wgt;
-          if (lane * 4 < D) {
-            const float4 v = __ldcg(reinterpret_cast<const float4*>(p.part_o + base * D) + lane);
-            acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
+#pragma unroll
+        for (int sp = 0; sp < kMaxDecodeSplits; ++sp) {
+          if (sp < S) {
+            const float2 e = ml[hg * S + sp];
+            const float wgt = e.x == -INFINITY ? 0.f : exp2f(e.x - M);
+            L += e.y * wgt;
+            acc.x += v[sp].x * wgt; acc.y += v[sp].y * wgt; acc.z += v[sp].z * wgt; acc.w += v[sp].w * wgt;
           }
         }
         const float inv = L > 0.f ? 1.f / L : 0.f;
         uint2 ov;
         ov.x = pack_bf16(acc.x * inv, acc.y * inv);
         ov.y = pack_bf16(acc.z * inv, acc.w * inv);
-        if (lane * 4 < D) *reinterpret_cast<uint2*>(p.out + ((size_t)slot * p.n_q + head) * D + lane * 4) = ov;
+        if (act) *reinterpret_cast<uint2*>(p.out + ((size_t)slot * p.n_q + head) * D + lane * 4) = ov;
       }
       if (lane == 0) p.split_counter[slot * p.n_kv + kvh] = 0;  // self-resetting for the next launch
     }
@@ -657,11 +699,11 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
         po[mt * 16 + g + 8] = __float2bfloat16(ot[mt][2 + hh] * inv);
       }
     }
-  }
+  }  if (lane == 0) trace_end(p.tr);
 }
 
 constexpr int kPrefillNW = kPrefillTileRows / 16, kPrefillTN = 64, kPrefillStages = 2;
-constexpr int kDecodeStages = 3;
+constexpr int kDecodeStages = 6;
 constexpr int attn_smem(int nw, int tn, int stages) { return (nw * 16 + 2 * stages * tn) * kTilePitch * 2; }
 constexpr int kDecodeSmem = 2 * kDecodeStages * kPageSize * kTilePitch * 2;
 
@@ -670,6 +712,11 @@ void attn_set_attrs() {
     constexpr int D = decltype(dtag)::value;
     cudaFuncSetAttribute(paged_attn_kernel<kPrefillNW, kPrefillTN, kPrefillStages, false, D>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem(kPrefillNW, kPrefillTN, kPrefillStages));
+    cudaFuncSetAttribute(decode_attn_kernel<2, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(decode_attn_kernel<3, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(decode_attn_kernel<4, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(decode_attn_kernel<6, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(decode_attn_kernel<7, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   };
   go(std::integral_constant<int, 128>{});
   go(std::integral_constant<int, 96>{});
@@ -692,15 +739,37 @@ int attn_decode_resident_ctas() {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_attn_kernel<kDecodeStages, 128>, 32,
                                                       kDecodeSmem) != cudaSuccess || per_sm < 1)
-      per_sm = 8;
+      per_sm = 4;
     cached = per_sm * sms;
   }
   return cached;
 }
+// Pipeline depth of the decode kernel.  r01 live timelines (profiles/r01_decode_timeline_v*.txt, 64 slots x 8 kv
+// heads, ctx 576): 1024 CTAs (2 KV splits) x 3 stages 33.1 us per layer; 512 CTAs (no split) x 3 stages 26.2 us,
+// x 6 stages 24.6 us (floor 21 us).  What hurt was not bytes in flight but the split epilogue (partials ->
+// fence -> counter -> serial combine) and the extra CTAs; so: few, long CTAs with a deep ring, and KV splits only
+// when the batch alone cannot fill the GPU (engine.cu: launch_decode).  MQ_ATTN_STAGES=2..7 overrides (experiments).
+static int decode_stages() {
+  static const int st = [] {
+    const char* e = getenv("MQ_ATTN_STAGES");
+    const int v = e ? atoi(e) : kDecodeStages;
+    return (v == 2 || v == 3 || v == 4 || v == 6 || v == 7) ? v : kDecodeStages;
+  }();
+  return st;
+}
+static int decode_smem() { return 2 * decode_stages() * kPageSize * kTilePitch * 2; }
 void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots) {
+  const int smem = decode_smem();
   dispatch_head_dim(p.head_dim, [&](auto dtag) {
     constexpr int D = decltype(dtag)::value;
-    launch_k(lc, decode_attn_kernel<kDecodeStages, D>, dim3(n_slots, p.n_kv, p.n_splits), dim3(32), kDecodeSmem, p);
+    const dim3 grid(n_slots, p.n_kv, p.n_splits);
+    switch (decode_stages()) {
+      case 2: launch_k(lc, decode_attn_kernel<2, D>, grid, dim3(32), smem, p); break;
+      case 3: launch_k(lc, decode_attn_kernel<3, D>, grid, dim3(32), smem, p); break;
+      case 4: launch_k(lc, decode_attn_kernel<4, D>, grid, dim3(32), smem, p); break;
+      case 7: launch_k(lc, decode_attn_kernel<7, D>, grid, dim3(32), smem, p); break;
+      default: launch_k(lc, decode_attn_kernel<kDecodeStages, D>, grid, dim3(32), smem, p); break;
+    }
   });
 }
 

@@ -8,6 +8,7 @@
 namespace mq {
 
 constexpr int kPageSize = 16;  // tokens per KV page
+constexpr int kMaxSplitPlanes = 8;  // split-K planes a reduce kernel (add_rmsnorm / rope_kv) may have to sum
 inline bool head_dim_supported(int d) { return d == 128 || d == 96 || d == 64; }  // Llama-3 / Qwen2.5, Phi-3, small models
 
 struct LaunchCfg {
@@ -23,7 +24,8 @@ void launch_embed(const LaunchCfg& lc, const int* token_ids, const __nv_bfloat16
 // partial_is_f32: planes are fp32 (decode split-K) else one bf16 plane (prefill).
 void launch_add_rmsnorm(const LaunchCfg& lc, float* h, const void* partial, bool partial_is_f32, int n_planes,
                         long long plane_stride, const __nv_bfloat16* gamma, __nv_bfloat16* x, const int* row_idx,
-                        int rows, int H, float eps, L2Prefetch pf = L2Prefetch{nullptr, 0});
+                        int rows, int H, float eps, L2Prefetch pf = L2Prefetch{nullptr, 0},
+                        Trace tr = Trace{nullptr, 0});
 
 struct RopeKvParams {
   const void* qkv;        // partial planes [S][T][qkv_dim] fp32, or one bf16 plane
@@ -42,6 +44,7 @@ struct RopeKvParams {
   int T, n_q, n_kv;
   int head_dim;               // 128, 96 or 64
   L2Prefetch pf;              // optional: weights of an upcoming GEMM to pull into L2
+  Trace tr;                   // optional timeline stamps (MQ_TRACE=1)
 };
 void launch_rope_kv(const LaunchCfg& lc, const RopeKvParams& p);
 
@@ -62,6 +65,7 @@ struct AttnParams {
   int* split_counter;  // decode only: [slots][n_kv] arrival counters (zero between launches)
   float scale_log2;    // softmax scale * log2(e)
   L2Prefetch pf;       // optional: weights of an upcoming GEMM to pull into L2 (decode)
+  Trace tr;            // optional timeline stamps (MQ_TRACE=1)
 };
 void launch_attn_prefill(const LaunchCfg& lc, const AttnParams& p, int n_tiles);
 void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots);

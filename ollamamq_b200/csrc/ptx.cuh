@@ -116,6 +116,35 @@ __device__ __forceinline__ void l2_prefetch_slice(const L2Prefetch& pf, unsigned
   }
 }
 
+// ---------------------------------------------------------------- per-launch timeline stamps (diagnostics)
+// MQ_TRACE=1: every kernel of a step records %globaltimer (ns) into buf[4 * id + k]:
+//   k = 0 first CTA entered the kernel (min)      k = 1 first CTA got past griddepcontrol.wait (min)
+//   k = 2 first CTA finished (min)                k = 3 last CTA finished (max, stored as ~t)
+// This is the only way to see the OVERLAPPED timeline of a PDL chain inside a CUDA graph (ncu serialises
+// launches, there is no nsys in the image).  buf == nullptr (the default) costs one predictable branch.
+struct Trace {
+  unsigned long long* buf;
+  int id;
+};
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_begin(const Trace& t) {
+  if (t.buf) atomicMin(t.buf + 4 * t.id, globaltimer_ns());
+}
+__device__ __forceinline__ void trace_waited(const Trace& t) {
+  if (t.buf) atomicMin(t.buf + 4 * t.id + 1, globaltimer_ns());
+}
+__device__ __forceinline__ void trace_end(const Trace& t) {
+  if (t.buf) {
+    const unsigned long long now = globaltimer_ns();
+    atomicMin(t.buf + 4 * t.id + 2, now);
+    atomicMin(t.buf + 4 * t.id + 3, ~now);  // max(end), stored complemented: one 0xFF memset re-arms all four slots
+  }
+}
+
 // ---------------------------------------------------------------- PDL (programmatic dependent launch)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() {
