@@ -80,6 +80,10 @@ int mq_debug_add_rmsnorm(float* h, const void* partial, int partial_is_f32, int 
     mq::set_last_error("H must be a multiple of 512");
     return MQ_ERR_INVAL;
   }
+  if (n_planes < 0 || n_planes > kMaxSplitPlanes) {
+    mq::set_last_error("n_planes must be 0..%d", kMaxSplitPlanes);
+    return MQ_ERR_INVAL;
+  }
   launch_add_rmsnorm(LaunchCfg{0, false}, h, partial, partial_is_f32 != 0, n_planes, plane_stride,
                      (const __nv_bfloat16*)gamma, (__nv_bfloat16*)x, row_idx, rows, H, eps);
   return check_cuda("mq_debug_add_rmsnorm");
@@ -90,6 +94,10 @@ int mq_debug_rope_kv(const void* qkv, int qkv_is_f32, int n_planes, long long pl
                      const float* inv_freq, void* q_out, void* k_cache, void* v_cache, int T, int n_q, int n_kv,
                      int head_dim) {
   if (!head_dim_supported(head_dim)) { mq::set_last_error("head_dim must be 128, 96 or 64"); return MQ_ERR_INVAL; }
+  if (n_planes < 1 || n_planes > kMaxSplitPlanes) {
+    mq::set_last_error("n_planes must be 1..%d", kMaxSplitPlanes);
+    return MQ_ERR_INVAL;
+  }
   RopeKvParams p = {};
   p.qkv = qkv; p.qkv_is_f32 = qkv_is_f32 != 0; p.n_planes = n_planes; p.plane_stride = plane_stride;
   p.bias = (const __nv_bfloat16*)bias; p.pos = pos; p.slot_of_tok = slot_of_tok; p.block_table = block_table;

@@ -66,37 +66,53 @@ void launch_embed(const LaunchCfg& lc, const int* token_ids, const __nv_bfloat16
 // ------------------------------------------------------------------------------------------------
 // fused residual-add + RMSNorm.  One CTA per row, blockDim = H/16, every thread keeps 16 values in registers.
 // ------------------------------------------------------------------------------------------------
-template <bool F32>
-__global__ void add_rmsnorm_kernel(float* __restrict__ h, const void* __restrict__ partial, int n_planes,
-                                   long long plane_stride, const __nv_bfloat16* __restrict__ gamma,
-                                   __nv_bfloat16* __restrict__ x, const int* __restrict__ row_idx, int H, float eps,
-                                   L2Prefetch pf, Trace tr) {
+// NP = number of split-K planes, a compile-time constant so that EVERY load of the thread (residual, planes,
+// gamma) is issued before the first use: with a run-time plane loop the kernel was a chain of ~20 dependent L2
+// round trips (r01 timeline: 4.7 - 6 us busy per launch, three launches per layer).
+template <bool F32, int NP>
+__global__ void add_rmsnorm_kernel(float* __restrict__ h, const void* __restrict__ partial, long long plane_stride,
+                                   const __nv_bfloat16* __restrict__ gamma, __nv_bfloat16* __restrict__ x,
+                                   const int* __restrict__ row_idx, int H, float eps, L2Prefetch pf, Trace tr) {
   pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
   if (threadIdx.x == 0) { trace_begin(tr); l2_prefetch_slice(pf, blockIdx.x, gridDim.x); }  // weights: independent of the previous kernel
+  const int row = blockIdx.x;
+  const int nthr = blockDim.x;
+  uint2 gm[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) gm[j] = reinterpret_cast<const uint2*>(gamma)[threadIdx.x + j * nthr];  // weights: no dependency
   pdl_wait();
   if (threadIdx.x == 0) trace_waited(tr);
-  const int row = blockIdx.x;
   const int src = row_idx ? row_idx[row] : row;
-  const int nthr = blockDim.x;
+  const float4* h4 = reinterpret_cast<const float4*>(h + (size_t)src * H);
   float4 v[4];
+  float4 b[4][F32 ? (NP > 0 ? NP : 1) : 1];
+  uint2 bb[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) v[j] = h4[threadIdx.x + j * nthr];
+  if constexpr (F32) {
+    const float* pp = reinterpret_cast<const float*>(partial) + (size_t)src * H;
+#pragma unroll
+    for (int s = 0; s < NP; ++s)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j][s] = reinterpret_cast<const float4*>(pp + s * plane_stride)[threadIdx.x + j * nthr];
+  } else if constexpr (NP > 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      bb[j] = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(partial) + (size_t)src * H)[threadIdx.x + j * nthr];
+  }
   float ss = 0.f;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int i4 = threadIdx.x + j * nthr;  // float4 index inside the row
-    float4 a = reinterpret_cast<const float4*>(h + (size_t)src * H)[i4];
-    if (F32) {
-      const float* pp = reinterpret_cast<const float*>(partial);
-      for (int s = 0; s < n_planes; ++s) {
-        const float4 b = reinterpret_cast<const float4*>(pp + s * plane_stride + (size_t)src * H)[i4];
-        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-      }
-    } else if (n_planes > 0) {
-      const uint2 b = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(partial) + (size_t)src * H)[i4];
-      a.x += bf16_lo(b.x); a.y += bf16_hi(b.x); a.z += bf16_lo(b.y); a.w += bf16_hi(b.y);
+    float4 a = v[j];
+    if constexpr (F32) {
+#pragma unroll
+      for (int s = 0; s < NP; ++s) { a.x += b[j][s].x; a.y += b[j][s].y; a.z += b[j][s].z; a.w += b[j][s].w; }
+    } else if constexpr (NP > 0) {
+      a.x += bf16_lo(bb[j].x); a.y += bf16_hi(bb[j].x); a.z += bf16_lo(bb[j].y); a.w += bf16_hi(bb[j].y);
     }
     v[j] = a;
     ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
-    if (!row_idx) reinterpret_cast<float4*>(h + (size_t)src * H)[i4] = a;
+    if (!row_idx) reinterpret_cast<float4*>(h + (size_t)src * H)[threadIdx.x + j * nthr] = a;
   }
   __shared__ float red[32];
   ss = warp_sum(ss);
@@ -107,12 +123,10 @@ __global__ void add_rmsnorm_kernel(float* __restrict__ h, const void* __restrict
   const float rstd = rsqrtf(tot / (float)H + eps);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int i4 = threadIdx.x + j * nthr;
-    const uint2 gm = reinterpret_cast<const uint2*>(gamma)[i4];
     uint2 o;
-    o.x = pack_bf16(v[j].x * rstd * bf16_lo(gm.x), v[j].y * rstd * bf16_hi(gm.x));
-    o.y = pack_bf16(v[j].z * rstd * bf16_lo(gm.y), v[j].w * rstd * bf16_hi(gm.y));
-    reinterpret_cast<uint2*>(x + (size_t)row * H)[i4] = o;
+    o.x = pack_bf16(v[j].x * rstd * bf16_lo(gm[j].x), v[j].y * rstd * bf16_hi(gm[j].x));
+    o.y = pack_bf16(v[j].z * rstd * bf16_lo(gm[j].y), v[j].w * rstd * bf16_hi(gm[j].y));
+    reinterpret_cast<uint2*>(x + (size_t)row * H)[threadIdx.x + j * nthr] = o;
   }
   if (threadIdx.x == 0) trace_end(tr);
 }
@@ -120,38 +134,63 @@ void launch_add_rmsnorm(const LaunchCfg& lc, float* h, const void* partial, bool
                         long long plane_stride, const __nv_bfloat16* gamma, __nv_bfloat16* x, const int* row_idx,
                         int rows, int H, float eps, L2Prefetch pf, Trace tr) {
   const int thr = H / 16;  // H % 512 == 0 is checked at model load
-  if (partial_is_f32)
-    launch_k(lc, add_rmsnorm_kernel<true>, dim3(rows), dim3(thr), 0, h, partial, n_planes, plane_stride, gamma, x,
-             row_idx, H, eps, pf, tr);
-  else
-    launch_k(lc, add_rmsnorm_kernel<false>, dim3(rows), dim3(thr), 0, h, partial, n_planes, plane_stride, gamma, x,
-             row_idx, H, eps, pf, tr);
+  auto go = [&](auto f32tag, auto nptag) {
+    launch_k(lc, add_rmsnorm_kernel<decltype(f32tag)::value, decltype(nptag)::value>, dim3(rows), dim3(thr), 0, h,
+             partial, plane_stride, gamma, x, row_idx, H, eps, pf, tr);
+  };
+  using T = std::true_type;
+  using F = std::false_type;
+  if (!partial_is_f32) {
+    if (n_planes > 0) go(F{}, std::integral_constant<int, 1>{}); else go(F{}, std::integral_constant<int, 0>{});
+    return;
+  }
+  switch (n_planes) {  // 0 .. kMaxSplitPlanes
+    case 0: go(T{}, std::integral_constant<int, 0>{}); break;
+    case 1: go(T{}, std::integral_constant<int, 1>{}); break;
+    case 2: go(T{}, std::integral_constant<int, 2>{}); break;
+    case 3: go(T{}, std::integral_constant<int, 3>{}); break;
+    case 4: go(T{}, std::integral_constant<int, 4>{}); break;
+    case 5: go(T{}, std::integral_constant<int, 5>{}); break;
+    case 6: go(T{}, std::integral_constant<int, 6>{}); break;
+    case 7: go(T{}, std::integral_constant<int, 7>{}); break;
+    default: go(T{}, std::integral_constant<int, 8>{}); break;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
 // RoPE + paged KV write (v1: one CTA per token = 64 CTAs at decode, 30 us of pure load latency per layer;
 // v2: (token, 4 heads) CTAs with 2-byte accesses; v3 below: 8/16-byte accesses).
 // ------------------------------------------------------------------------------------------------
-// 4 consecutive qkv values of token t starting at column col: sum of the split-K planes (+ bias)
-template <bool F32>
-__device__ __forceinline__ float4 qkv_at4(const RopeKvParams& p, int t, int col, int qkv_dim) {
-  float4 v;
-  if (F32) {
-    const float* pp = reinterpret_cast<const float*>(p.qkv);
-    v = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < p.n_planes; ++s) {
-      const float4 a = *reinterpret_cast<const float4*>(pp + s * p.plane_stride + (size_t)t * qkv_dim + col);
-      v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+// 4 consecutive qkv values of token t starting at columns col and col + half: sum of the NP split-K planes
+// (+ bias).  NP is a compile-time constant so that all 2 * NP loads are in flight together.
+template <bool F32, int NP>
+__device__ __forceinline__ void qkv_pair4(const RopeKvParams& p, int t, int col, int half, int qkv_dim, float4& va,
+                                          float4& vb) {
+  if constexpr (F32) {
+    const float* pp = reinterpret_cast<const float*>(p.qkv) + (size_t)t * qkv_dim + col;
+    float4 a[NP], b[NP];
+#pragma unroll
+    for (int s = 0; s < NP; ++s) {
+      a[s] = *reinterpret_cast<const float4*>(pp + s * p.plane_stride);
+      b[s] = *reinterpret_cast<const float4*>(pp + s * p.plane_stride + half);
+    }
+    va = a[0]; vb = b[0];
+#pragma unroll
+    for (int s = 1; s < NP; ++s) {
+      va.x += a[s].x; va.y += a[s].y; va.z += a[s].z; va.w += a[s].w;
+      vb.x += b[s].x; vb.y += b[s].y; vb.z += b[s].z; vb.w += b[s].w;
     }
   } else {
-    const uint2 a = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.qkv) + (size_t)t * qkv_dim + col);
-    v = make_float4(bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y));
+    const __nv_bfloat16* pp = reinterpret_cast<const __nv_bfloat16*>(p.qkv) + (size_t)t * qkv_dim + col;
+    const uint2 a = *reinterpret_cast<const uint2*>(pp);
+    const uint2 b = *reinterpret_cast<const uint2*>(pp + half);
+    va = make_float4(bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y));
+    vb = make_float4(bf16_lo(b.x), bf16_hi(b.x), bf16_lo(b.y), bf16_hi(b.y));
   }
-  if (p.bias) {
-    const uint2 b = *reinterpret_cast<const uint2*>(p.bias + col);
-    v.x += bf16_lo(b.x); v.y += bf16_hi(b.x); v.z += bf16_lo(b.y); v.w += bf16_hi(b.y);
-  }
-  return v;
+}
+__device__ __forceinline__ void add_bias4(float4& v, const __nv_bfloat16* bias) {
+  const uint2 b = *reinterpret_cast<const uint2*>(bias);
+  v.x += bf16_lo(b.x); v.y += bf16_hi(b.x); v.z += bf16_lo(b.y); v.w += bf16_hi(b.y);
 }
 __device__ __forceinline__ uint2 pack4_bf16(float a, float b, float c, float d) {
   uint2 o;
@@ -173,47 +212,56 @@ static void dispatch_head_dim(int d, F&& f) {
   }
 }
 
-template <bool F32, int D>
+template <bool F32, int D, int NP>
 __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
   pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
   if (threadIdx.x == 0) { trace_begin(p.tr); l2_prefetch_slice(p.pf, blockIdx.x + gridDim.x * blockIdx.y, gridDim.x * gridDim.y); }
-  pdl_wait();
-  if (threadIdx.x == 0) trace_waited(p.tr);
   constexpr int HALF = D / 2;  // 16 threads per head x 4 pairs cover HALF <= 64 (threads beyond HALF idle: d = 96, 64)
   const int t = blockIdx.x;
   const int hd = blockIdx.y * 16 + (threadIdx.x >> 4);  // q heads, then k heads, then v heads
   const int n_heads = p.n_q + 2 * p.n_kv;
-  if (hd >= n_heads || (int)(threadIdx.x & 15) * 4 >= HALF) return;
-  const int pos = p.pos[t];
-  const int slot = p.slot_of_tok[t];
+  const bool live = hd < n_heads && (int)(threadIdx.x & 15) * 4 < HALF;
   const int qkv_dim = n_heads * D;
   const int i = (threadIdx.x & 15) * 4;  // first of 4 pair indices
   const int col = hd * D + i;
-  const float4 a = qkv_at4<F32>(p, t, col, qkv_dim);
-  const float4 b = qkv_at4<F32>(p, t, col + HALF, qkv_dim);
-  uint2 lo, hi;
-  if (hd < p.n_q + p.n_kv) {
-    const float4 fr = *reinterpret_cast<const float4*>(p.inv_freq + i);
-    float s0, c0, s1, c1, s2, c2, s3, c3;
-    sincosf((float)pos * fr.x, &s0, &c0);
-    sincosf((float)pos * fr.y, &s1, &c1);
-    sincosf((float)pos * fr.z, &s2, &c2);
-    sincosf((float)pos * fr.w, &s3, &c3);
-    lo = pack4_bf16(a.x * c0 - b.x * s0, a.y * c1 - b.y * s1, a.z * c2 - b.z * s2, a.w * c3 - b.w * s3);
-    hi = pack4_bf16(b.x * c0 + a.x * s0, b.y * c1 + a.y * s1, b.z * c2 + a.z * s2, b.w * c3 + a.w * s3);
-  } else {
-    lo = pack4_bf16(a.x, a.y, a.z, a.w);
-    hi = pack4_bf16(b.x, b.y, b.z, b.w);
+  // Everything that does not depend on the QKV GEMM happens BEFORE the dependency wait: positions, the block-table
+  // walk, the bias and the four sin/cos pairs (positions / slot tables are written by the host or by the previous
+  // step's sampler, never by a kernel of this pass).
+  float sn[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {1.f, 1.f, 1.f, 1.f};
+  float4 bias_a = make_float4(0.f, 0.f, 0.f, 0.f), bias_b = bias_a;
+  __nv_bfloat16* dst = nullptr;
+  if (live) {
+    const int pos = p.pos[t];
+    if (hd < p.n_q + p.n_kv) {
+      const float4 fr = *reinterpret_cast<const float4*>(p.inv_freq + i);
+      sincosf((float)pos * fr.x, &sn[0], &cs[0]);
+      sincosf((float)pos * fr.y, &sn[1], &cs[1]);
+      sincosf((float)pos * fr.z, &sn[2], &cs[2]);
+      sincosf((float)pos * fr.w, &sn[3], &cs[3]);
+    }
+    if (p.bias) { add_bias4(bias_a, p.bias + col); add_bias4(bias_b, p.bias + col + HALF); }
+    if (hd < p.n_q) {
+      dst = p.q_out + (size_t)t * p.n_q * D + hd * D;
+    } else {
+      const int slot = p.slot_of_tok[t];
+      const int page = p.block_table[(size_t)slot * p.max_pages + pos / kPageSize];
+      const bool is_k = hd < p.n_q + p.n_kv;
+      const int kvh = is_k ? hd - p.n_q : hd - p.n_q - p.n_kv;
+      dst = (is_k ? p.k_cache : p.v_cache) + (((size_t)page * p.n_kv + kvh) * kPageSize + pos % kPageSize) * D;
+    }
   }
-  __nv_bfloat16* dst;
-  if (hd < p.n_q) {
-    dst = p.q_out + (size_t)t * p.n_q * D + hd * D;
-  } else {
-    const int page = p.block_table[(size_t)slot * p.max_pages + pos / kPageSize];
-    const bool is_k = hd < p.n_q + p.n_kv;
-    const int kvh = is_k ? hd - p.n_q : hd - p.n_q - p.n_kv;
-    dst = (is_k ? p.k_cache : p.v_cache) + (((size_t)page * p.n_kv + kvh) * kPageSize + pos % kPageSize) * D;
-  }
+  pdl_wait();
+  if (threadIdx.x == 0) trace_waited(p.tr);
+  if (!live) return;
+  float4 a, b;
+  qkv_pair4<F32, NP>(p, t, col, HALF, qkv_dim, a, b);
+  a.x += bias_a.x; a.y += bias_a.y; a.z += bias_a.z; a.w += bias_a.w;
+  b.x += bias_b.x; b.y += bias_b.y; b.z += bias_b.z; b.w += bias_b.w;
+  // v heads keep sin = 0, cos = 1: the rotation degenerates to a copy
+  const uint2 lo = pack4_bf16(a.x * cs[0] - b.x * sn[0], a.y * cs[1] - b.y * sn[1], a.z * cs[2] - b.z * sn[2],
+                              a.w * cs[3] - b.w * sn[3]);
+  const uint2 hi = pack4_bf16(b.x * cs[0] + a.x * sn[0], b.y * cs[1] + a.y * sn[1], b.z * cs[2] + a.z * sn[2],
+                              b.w * cs[3] + a.w * sn[3]);
   *reinterpret_cast<uint2*>(dst + i) = lo;
   *reinterpret_cast<uint2*>(dst + i + HALF) = hi;
   if (threadIdx.x == 0) trace_end(p.tr);  // thread 0 always owns a live (head, pair) of its CTA
@@ -222,10 +270,17 @@ void launch_rope_kv(const LaunchCfg& lc, const RopeKvParams& p) {
   const dim3 grid(p.T, (p.n_q + 2 * p.n_kv + 15) / 16);
   auto go = [&](auto dtag) {
     constexpr int D = decltype(dtag)::value;
-    if (p.qkv_is_f32)
-      launch_k(lc, rope_kv_kernel<true, D>, grid, dim3(256), 0, p);
-    else
-      launch_k(lc, rope_kv_kernel<false, D>, grid, dim3(256), 0, p);
+    if (!p.qkv_is_f32) { launch_k(lc, rope_kv_kernel<false, D, 1>, grid, dim3(256), 0, p); return; }
+    switch (p.n_planes) {  // 1 .. kMaxSplitPlanes
+      case 1: launch_k(lc, rope_kv_kernel<true, D, 1>, grid, dim3(256), 0, p); break;
+      case 2: launch_k(lc, rope_kv_kernel<true, D, 2>, grid, dim3(256), 0, p); break;
+      case 3: launch_k(lc, rope_kv_kernel<true, D, 3>, grid, dim3(256), 0, p); break;
+      case 4: launch_k(lc, rope_kv_kernel<true, D, 4>, grid, dim3(256), 0, p); break;
+      case 5: launch_k(lc, rope_kv_kernel<true, D, 5>, grid, dim3(256), 0, p); break;
+      case 6: launch_k(lc, rope_kv_kernel<true, D, 6>, grid, dim3(256), 0, p); break;
+      case 7: launch_k(lc, rope_kv_kernel<true, D, 7>, grid, dim3(256), 0, p); break;
+      default: launch_k(lc, rope_kv_kernel<true, D, 8>, grid, dim3(256), 0, p); break;
+    }
   };
   dispatch_head_dim(p.head_dim, go);
 }
