@@ -369,6 +369,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   }
   if (g->streamk) {
     const long long U = (long long)g->p.m_tiles * kb;
+    g->sk = StreamKParams{};  // (also clears the optional trace slot)
     g->sk.out = out;
     g->sk.ldo = ldo;
     g->sk.T = T;
