@@ -134,6 +134,8 @@ void launch_add_rmsnorm(const LaunchCfg& lc, float* h, const void* partial, bool
                         long long plane_stride, const __nv_bfloat16* gamma, __nv_bfloat16* x, const int* row_idx,
                         int rows, int H, float eps, L2Prefetch pf, Trace tr) {
   const int thr = H / 16;  // H % 512 == 0 is checked at model load
+  // (r01 A/B: a 4-CTA cluster per row with a DSMEM exchange of the partial sums was SLOWER at decode width -
+  //  4.1 / 5.0 us busy against 3.3 / 4.3 us - the cluster barrier costs more than the narrower loads save.)
   auto go = [&](auto f32tag, auto nptag) {
     launch_k(lc, add_rmsnorm_kernel<decltype(f32tag)::value, decltype(nptag)::value>, dim3(rows), dim3(thr), 0, h,
              partial, plane_stride, gamma, x, row_idx, H, eps, pf, tr);
