@@ -272,7 +272,8 @@ int mq_debug_attn_prefill(const void* q, const void* k_cache, const void* v_cach
                           float scale, int head_dim);
 int mq_debug_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* block_table,
                          int max_pages, const int* pos, void* out, float* part_o, float* part_ml, int* split_counter,
-                         int n_q, int n_kv, int n_slots, int n_splits, float scale, int head_dim);
+                         int n_q, int n_kv, int n_slots, int n_splits /* 1..8 grid-level KV splits, or -2 / -4 / -8 =
+                         that many warps per CTA with the shared-memory combine */, float scale, int head_dim);
 /* Timeline of the worker's most recent decode step (worker opened with MQ_TRACE=1 in the environment): for launch
  * slot i, out[4*i+0..3] = %globaltimer ns of {first CTA start, first CTA past its dependency wait, first CTA end,
  * ~(last CTA end)}; untouched slots read as all-ones.  Slots: 1 + 8*layer + {0 norm, 1 qkv, 2 rope, 3 attention,

@@ -133,6 +133,12 @@ int mq_debug_attn_decode(const void* q, const void* k_cache, const void* v_cache
   p.q = (const __nv_bfloat16*)q; p.k_cache = (const __nv_bfloat16*)k_cache; p.v_cache = (const __nv_bfloat16*)v_cache;
   p.block_table = block_table; p.max_pages = max_pages; p.pos = pos; p.out = (__nv_bfloat16*)out;
   p.part_o = part_o; p.part_ml = part_ml; p.split_counter = split_counter; p.n_q = n_q; p.n_kv = n_kv; p.T = n_slots;
+  if (n_splits < 0) {  // -2 / -4 / -8: in-CTA split over that many warps
+    if (n_splits != -2 && n_splits != -4 && n_splits != -8) { mq::set_last_error("n_splits: 1..8, or -2 / -4 / -8"); return MQ_ERR_INVAL; }
+    p.n_warps = -n_splits; n_splits = 1;
+  } else {
+    p.n_warps = 1;
+  }
   p.n_splits = n_splits; p.scale_log2 = scale * 1.4426950408889634f;
   attn_set_attrs();
   launch_attn_decode(LaunchCfg{0, false}, p, n_slots);

@@ -317,7 +317,8 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
     ap.head_dim = c.head_dim;
     ap.q = w->q; ap.k_cache = rp.k_cache; ap.v_cache = rp.v_cache; ap.block_table = w->d_block_table;
     ap.max_pages = w->max_pages; ap.tiles = w->d_tiles; ap.pos = a.pos; ap.out = w->attn; ap.part_o = w->part_o;
-    ap.part_ml = w->part_ml; ap.n_q = c.n_q_heads; ap.n_kv = c.n_kv_heads; ap.T = a.T; ap.n_splits = a.n_splits;
+    ap.part_ml = w->part_ml; ap.n_q = c.n_q_heads; ap.n_kv = c.n_kv_heads; ap.T = a.T;
+    ap.n_splits = a.n_splits < 0 ? 1 : a.n_splits; ap.n_warps = a.n_splits < 0 ? -a.n_splits : 1;
     ap.pf = pf_attn;
     ap.tr = tr();
     ap.split_counter = w->d_split_counter; ap.scale_log2 = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
@@ -601,15 +602,21 @@ static int launch_decode(mq_worker* w) {
     }
   if (hi < 0) return MQ_OK;
   const int Bcap = std::min(MBp, round_up(hi + 1, 16));
-  // split-KV count: fill the GPU with one wave of single-warp CTAs, keep >= 64 tokens per split
-  // split the KV range only when (slots x kv heads) alone leaves SMs idle: every split pays for partial rows, a fence,
-  // a counter and the combine (r01 timeline: 64 slots x 8 kv heads unsplit 25 us per layer, 2-way split 33 us)
-  const int base_ctas = Bcap * w->cfg.n_kv_heads, sms = w->sm_count;
+  // KV splits only when (active slots x kv heads) alone leaves SMs idle (r01 timelines, 64 slots x 8 kv heads:
+  // unsplit 25 us per layer, 2-way grid split 33 us).  Small batches split INSIDE the CTA - 2 / 4 / 8 warps, each
+  // one KV range, merged through shared memory (encoded as a negative count); the grid-level split with its
+  // global-memory combine is the fallback for very long contexts on few slots.
+  const int base_ctas = std::max(1, n_active) * w->cfg.n_kv_heads, sms = w->sm_count;
   int n_splits = 1;
-  if (base_ctas < 2 * sms) n_splits = (3 * sms + base_ctas - 1) / base_ctas;
-  n_splits = std::max(1, std::min({n_splits, attn_decode_resident_ctas() / base_ctas, kMaxDecodeSplits,
-                                   std::max(1, max_ctx / 64)}));
-  if (const char* e = getenv("MQ_ATTN_SPLITS")) n_splits = std::max(1, std::min(atoi(e), kMaxDecodeSplits));  // experiments
+  if (base_ctas < 2 * sms) {
+    int nw = base_ctas > sms ? 4 : 8;  // r01 sweep: 8 / 16 slots -> 8 warps (5.3 / 6.4 us), 24 / 32 slots -> 4 warps (10.4 / 12.3 us)
+    while (nw > 1 && max_ctx / nw < 64) nw >>= 1;  // keep >= 4 pages per warp
+    n_splits = nw > 1 ? -nw : 1;
+  }
+  if (const char* e = getenv("MQ_ATTN_SPLITS")) {  // experiments: 1..8 grid-level, -2 / -4 / -8 in-CTA
+    const int v = atoi(e);
+    if (v == -2 || v == -4 || v == -8 || (v >= 1 && v <= kMaxDecodeSplits)) n_splits = v;
+  }
   upload_slots(w);
   if (w->d_trace) cudaMemsetAsync(w->d_trace, 0xFF, (size_t)kTraceSlots * 4 * 8, w->stream);  // re-arm the timeline
 
@@ -622,7 +629,7 @@ static int launch_decode(mq_worker* w) {
   bool graph_launched = false;
   if (w->cfg.use_graphs) {
     // graphs always write their tokens to ring row 0's alias at the end of the ring buffer (fixed address)
-    const long long key = (long long)Bcap * 1024 + n_splits;
+    const long long key = (long long)Bcap * 1024 + (n_splits + 16);
     auto it = w->graphs.find(key);
     if (it == w->graphs.end()) {
       if (!get_plans(w, Bcap, true) || !get_lm_plan(w, Bcap)) return MQ_ERR_CUDA;

@@ -529,27 +529,36 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
 // lane per tile.  Masking only happens on the boundary tile.  (r01 v2 capture: the generic kernel was issue-bound
 // at 7 warps/SM, 37% issue-active, 3.5 TB/s.)
 // ------------------------------------------------------------------------------------------------
-template <int STAGES, int D>
-__global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
+//
+// NW > 1 (small batches): the NW warps of a CTA each take one KV split of the same (slot, kv head) and merge through
+// SHARED memory - no partial rows in global memory, no fence, no arrival counter (r01 timeline at 8 slots: the
+// global-memory split path spent ~12 us per layer on a 3 us stream).  NW == 1 keeps the grid-level split
+// (blockIdx.z) with the in-kernel global combine for shapes where one warp per CTA already fills the GPU.
+template <int STAGES, int D, int NW>
+__global__ void __launch_bounds__(32 * NW) decode_attn_kernel(const AttnParams p) {
   constexpr int TN = kPageSize, P = kTilePitch, CH = D / 8, KS = D / 16;
+  constexpr int RING = 2 * STAGES * TN * P * 2;  // bytes of one warp's K + V ring
   static_assert(TN == 16, "a KV tile is one page");
+  static_assert(NW == 1 || RING >= (8 * D + 16) * 4, "the ring doubles as the warp's partial-result buffer");
   extern __shared__ __align__(128) uint8_t smem[];
-  uint8_t* Ks = smem;
-  uint8_t* Vs = smem + STAGES * TN * P * 2;
+  const int warp = threadIdx.x >> 5;
+  uint8_t* Ks = smem + warp * RING;
+  uint8_t* Vs = Ks + STAGES * TN * P * 2;
 
   pdl_launch_dependents();
   if (threadIdx.x == 0) trace_begin(p.tr);
 
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const int g = lane >> 2, c = lane & 3;
   const int slot = blockIdx.x, kvh = blockIdx.y;
   const int G = p.n_q / p.n_kv;  // <= 8 (checked on the host)
   const int kv_len = p.pos[slot] + 1;
   int kv_begin = 0, kv_end = kv_len;
-  const bool split = p.n_splits > 1;
-  if (split) {
-    const int chunk = (((kv_len + p.n_splits - 1) / p.n_splits) + 15) & ~15;
-    kv_begin = blockIdx.z * chunk;
+  const bool split = NW == 1 && p.n_splits > 1;   // grid-level split with the global-memory combine
+  const int n_parts = NW > 1 ? NW : p.n_splits;
+  if (n_parts > 1) {
+    const int chunk = (((kv_len + n_parts - 1) / n_parts) + 15) & ~15;
+    kv_begin = (NW > 1 ? warp : (int)blockIdx.z) * chunk;
     kv_end = min(kv_len, kv_begin + chunk);
   }
   const int* btab = p.block_table + (size_t)slot * p.max_pages;
@@ -587,7 +596,7 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
       }
     }
     pdl_wait();
-    if (lane == 0) trace_waited(p.tr);
+    if (threadIdx.x == 0) trace_waited(p.tr);
     if (!early) {
 #pragma unroll
       for (int s0 = 0; s0 < STAGES - 1; ++s0) {
@@ -663,11 +672,11 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
 
   if (n_tiles == 0) {  // empty split: still order this CTA's writes after the previous kernel
     pdl_wait();
-    if (lane == 0) trace_waited(p.tr);
+    if (threadIdx.x == 0) trace_waited(p.tr);
   }
   // KV streaming of this CTA is over: use the combine tail to pull the O-projection weights towards L2
   // (issued late on purpose - the 135 MB KV stream would evict anything prefetched earlier)
-  if (lane == 0)
+  if (threadIdx.x == 0)
     l2_prefetch_slice(p.pf, blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z), gridDim.x * gridDim.y * gridDim.z);
 
   // ---- finalize: l of head g -> full row sum; this thread needs the sums of heads 2c, 2c+1
@@ -675,6 +684,48 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
   l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
   const int h_a = 2 * c, h_b = 2 * c + 1;
   const float l_a = __shfl_sync(0xffffffffu, l_run, h_a * 4), l_b = __shfl_sync(0xffffffffu, l_run, (h_b & 7) * 4);
+  if constexpr (NW > 1) {
+    // ---- in-CTA combine: every warp parks (m, l) and its O^T partial in its own (now idle) ring, then all
+    // threads merge the NW partials; item = (head, 4 consecutive dims)
+    cp_async_wait<0>();
+    __syncwarp();
+    float* part = reinterpret_cast<float*>(Ks);        // [8 heads][D]
+    float2* pml = reinterpret_cast<float2*>(part + 8 * D);  // [8 heads]
+    if (c == 0) pml[g] = make_float2(m_run, l_run);     // rows g >= G hold zeros / -inf: never read
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      const int head = hh ? h_b : h_a;
+#pragma unroll
+      for (int mt = 0; mt < KS; ++mt) {
+        part[head * D + mt * 16 + g] = ot[mt][hh];
+        part[head * D + mt * 16 + g + 8] = ot[mt][2 + hh];
+      }
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < G * (D / 4); item += 32 * NW) {
+      const int hg = item / (D / 4), d4 = item % (D / 4);
+      float M = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) M = fmaxf(M, reinterpret_cast<const float2*>(smem + w * RING + 8 * D * 4)[hg].x);
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float L = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const float2 e = reinterpret_cast<const float2*>(smem + w * RING + 8 * D * 4)[hg];
+        const float wgt = e.x == -INFINITY ? 0.f : exp2f(e.x - M);
+        const float4 v = reinterpret_cast<const float4*>(smem + w * RING)[hg * (D / 4) + d4];
+        L += e.y * wgt;
+        acc.x += v.x * wgt; acc.y += v.y * wgt; acc.z += v.z * wgt; acc.w += v.w * wgt;
+      }
+      const float inv = L > 0.f ? 1.f / L : 0.f;
+      uint2 ov;
+      ov.x = pack_bf16(acc.x * inv, acc.y * inv);
+      ov.y = pack_bf16(acc.z * inv, acc.w * inv);
+      *reinterpret_cast<uint2*>(p.out + ((size_t)slot * p.n_q + kvh * G + hg) * D + d4 * 4) = ov;
+    }
+    if (threadIdx.x == 0) trace_end(p.tr);
+    return;
+  }
   if (split) {
     if (c == 0 && g < G) {
       const size_t base = ((size_t)blockIdx.z * p.T + slot) * p.n_q + kvh * G + g;
@@ -756,7 +807,7 @@ __global__ void __launch_bounds__(32) decode_attn_kernel(const AttnParams p) {
         po[mt * 16 + g + 8] = __float2bfloat16(ot[mt][2 + hh] * inv);
       }
     }
-  }  if (lane == 0) trace_end(p.tr);
+  }  if (threadIdx.x == 0) trace_end(p.tr);
 }
 
 constexpr int kPrefillNW = kPrefillTileRows / 16, kPrefillTN = 64, kPrefillStages = 2;
@@ -769,11 +820,14 @@ void attn_set_attrs() {
     constexpr int D = decltype(dtag)::value;
     cudaFuncSetAttribute(paged_attn_kernel<kPrefillNW, kPrefillTN, kPrefillStages, false, D>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem(kPrefillNW, kPrefillTN, kPrefillStages));
-    cudaFuncSetAttribute(decode_attn_kernel<2, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(decode_attn_kernel<3, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(decode_attn_kernel<4, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(decode_attn_kernel<6, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(decode_attn_kernel<7, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(decode_attn_kernel<2, D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(decode_attn_kernel<3, D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(decode_attn_kernel<4, D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(decode_attn_kernel<6, D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(decode_attn_kernel<7, D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(decode_attn_kernel<6, D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(decode_attn_kernel<3, D, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(decode_attn_kernel<3, D, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 192 * 1024);
   };
   go(std::integral_constant<int, 128>{});
   go(std::integral_constant<int, 96>{});
@@ -794,7 +848,7 @@ int attn_decode_resident_ctas() {
     int per_sm = 0, dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_attn_kernel<kDecodeStages, 128>, 32,
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_attn_kernel<kDecodeStages, 128, 1>, 32,
                                                       kDecodeSmem) != cudaSuccess || per_sm < 1)
       per_sm = 4;
     cached = per_sm * sms;
@@ -815,17 +869,27 @@ static int decode_stages() {
   return st;
 }
 static int decode_smem() { return 2 * decode_stages() * kPageSize * kTilePitch * 2; }
+constexpr int decode_ring_bytes(int stages) { return 2 * stages * kPageSize * kTilePitch * 2; }
 void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots) {
-  const int smem = decode_smem();
   dispatch_head_dim(p.head_dim, [&](auto dtag) {
     constexpr int D = decltype(dtag)::value;
+    if (p.n_warps > 1) {  // in-CTA split: warps = KV splits, shared-memory combine, no grid-level split
+      const dim3 grid(n_slots, p.n_kv, 1);
+      switch (p.n_warps) {
+        case 2: launch_k(lc, decode_attn_kernel<6, D, 2>, grid, dim3(64), 2 * decode_ring_bytes(6), p); break;
+        case 4: launch_k(lc, decode_attn_kernel<3, D, 4>, grid, dim3(128), 4 * decode_ring_bytes(3), p); break;
+        default: launch_k(lc, decode_attn_kernel<3, D, 8>, grid, dim3(256), 8 * decode_ring_bytes(3), p); break;
+      }
+      return;
+    }
+    const int smem = decode_smem();
     const dim3 grid(n_slots, p.n_kv, p.n_splits);
     switch (decode_stages()) {
-      case 2: launch_k(lc, decode_attn_kernel<2, D>, grid, dim3(32), smem, p); break;
-      case 3: launch_k(lc, decode_attn_kernel<3, D>, grid, dim3(32), smem, p); break;
-      case 4: launch_k(lc, decode_attn_kernel<4, D>, grid, dim3(32), smem, p); break;
-      case 7: launch_k(lc, decode_attn_kernel<7, D>, grid, dim3(32), smem, p); break;
-      default: launch_k(lc, decode_attn_kernel<kDecodeStages, D>, grid, dim3(32), smem, p); break;
+      case 2: launch_k(lc, decode_attn_kernel<2, D, 1>, grid, dim3(32), smem, p); break;
+      case 3: launch_k(lc, decode_attn_kernel<3, D, 1>, grid, dim3(32), smem, p); break;
+      case 4: launch_k(lc, decode_attn_kernel<4, D, 1>, grid, dim3(32), smem, p); break;
+      case 7: launch_k(lc, decode_attn_kernel<7, D, 1>, grid, dim3(32), smem, p); break;
+      default: launch_k(lc, decode_attn_kernel<kDecodeStages, D, 1>, grid, dim3(32), smem, p); break;
     }
   });
 }

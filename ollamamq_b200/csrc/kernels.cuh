@@ -61,7 +61,8 @@ struct AttnParams {
   float* part_ml;      // [splits][T][n_q][2]
   int n_q, n_kv, T;
   int head_dim;        // 128, 96 or 64
-  int n_splits;        // decode only: every sequence is cut into n_splits equal 16-aligned ranges
+  int n_splits;        // decode only: every sequence is cut into n_splits equal 16-aligned ranges (grid-level)
+  int n_warps;         // decode only: 1, or 2 / 4 / 8 = in-CTA split over that many warps (then n_splits == 1)
   int* split_counter;  // decode only: [slots][n_kv] arrival counters (zero between launches)
   float scale_log2;    // softmax scale * log2(e)
   L2Prefetch pf;       // optional: weights of an upcoming GEMM to pull into L2 (decode)

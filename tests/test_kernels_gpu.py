@@ -332,7 +332,10 @@ def test_attn_prefill(n_q, n_kv, D):
 
 @pytest.mark.parametrize("n_q,n_kv,n_splits,D", [(32, 8, 4, 128), (32, 8, 1, 128), (28, 4, 3, 128), (32, 8, 8, 128),
                                                   (32, 8, 2, 128), (32, 32, 1, 96), (32, 32, 3, 96), (12, 4, 2, 96),
-                                                  (8, 2, 4, 64), (8, 1, 1, 64)])
+                                                  (8, 2, 4, 64), (8, 1, 1, 64),
+                                                  # negative = that many warps per CTA, shared-memory combine
+                                                  (32, 8, -2, 128), (32, 8, -4, 128), (32, 8, -8, 128), (28, 4, -8, 128),
+                                                  (32, 32, -4, 96), (12, 4, -8, 96), (8, 2, -2, 64), (8, 1, -8, 64)])
 def test_attn_decode(n_q, n_kv, n_splits, D):
     m = _lib()
     n_slots, max_pages = 7, 48
@@ -344,8 +347,8 @@ def test_attn_decode(n_q, n_kv, n_splits, D):
     pos = torch.tensor(pos_list, dtype=torch.int32, device=dev())
     q = torch.randn(n_slots, n_q, D, device=dev()).bfloat16()
     out = torch.zeros(n_slots, n_q, D, device=dev(), dtype=torch.bfloat16)
-    part_o = torch.full((n_splits, n_slots, n_q, D), float("nan"), device=dev())
-    part_ml = torch.full((n_splits, n_slots, n_q, 2), float("nan"), device=dev())
+    part_o = torch.full((max(1, n_splits), n_slots, n_q, D), float("nan"), device=dev())
+    part_ml = torch.full((max(1, n_splits), n_slots, n_q, 2), float("nan"), device=dev())
     counter = torch.zeros(n_slots * n_kv, dtype=torch.int32, device=dev())
     for rep in range(2):  # second launch checks the arrival counters reset themselves
         out.zero_()
