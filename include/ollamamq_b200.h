@@ -228,6 +228,11 @@ int mq_dispatcher_set_online(mq_dispatcher* d, int32_t backend, int32_t online);
  * (:107-115).  Format pinned by the reference: pretty JSON {"ips": [...], "users": [...]} (:21-25); the reference
  * uses "blocked_items.json" in the working directory (:19).                                                   */
 int mq_dispatcher_set_block_file(mq_dispatcher* d, const char* path);
+/* Everything the reference dashboard shows, captured under one lock (tui.rs:55-95 capture_snapshot), as one JSON
+ * object: vip[], boost[], blocked_users[], blocked_ips[], counter, users[{id, ip, queued, processing, processed,
+ * dropped}] in the dashboard's order (tui.rs:70-80), backends[{label, active, processed, online}].  Returns the bytes
+ * needed including the terminator; nothing is written when that exceeds cap.                              */
+long long mq_dispatcher_snapshot_json(mq_dispatcher* d, char* out, size_t cap);
 /* health prober (:171-193): every period_ms (reference: 10 000) copy mq_worker_healthy() into is_online         */
 int mq_dispatcher_start_health(mq_dispatcher* d, uint32_t period_ms);
 /* the HTTP connection behind a queued / in-flight task closed (responder.is_closed(), :278; send error, :305) */

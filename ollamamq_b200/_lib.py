@@ -154,6 +154,7 @@ _sig("mq_debug_attn_prefill", C.c_int, [P, P, P, P, C.c_int, P, C.c_int, P, C.c_
                                          C.c_int])
 _sig("mq_debug_attn_decode", C.c_int, [P, P, P, P, C.c_int, P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_float, C.c_int])
+_sig("mq_dispatcher_snapshot_json", C.c_longlong, [P, P, C.c_size_t])
 _sig("mq_debug_trace_read", C.c_int, [P, P, C.c_int])
 _sig("mq_debug_argmax", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, P, P, P, P])
 _sig("mq_debug_init_normal", C.c_int, [P, C.c_ulonglong, C.c_ulonglong, C.c_float])

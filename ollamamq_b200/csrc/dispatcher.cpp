@@ -479,6 +479,55 @@ int mq_dispatcher_block_ip(mq_dispatcher* d, const char* ip, int32_t blocked) {
   save_blocked(d);
   return MQ_OK;
 }
+// One consistent view of everything the reference dashboard shows (tui.rs:55-95 capture_snapshot): taken under the
+// dispatcher lock, users already in the dashboard's order.  JSON so that a curses / web front end needs one call.
+static void js_str(std::string& o, const std::string& v) {
+  o += '"';
+  for (unsigned char ch : v) {
+    if (ch == '"' || ch == '\\') { o += '\\'; o += (char)ch; }
+    else if (ch < 0x20) { char b[8]; snprintf(b, sizeof b, "\\u%04x", ch); o += b; }
+    else o += (char)ch;
+  }
+  o += '"';
+}
+static void js_list(std::string& o, const char* key, const std::vector<std::string>& v) {
+  o += '"'; o += key; o += "\":[";
+  for (size_t i = 0; i < v.size(); ++i) { if (i) o += ','; js_str(o, v[i]); }
+  o += ']';
+}
+long long mq_dispatcher_snapshot_json(mq_dispatcher* d, char* out, size_t cap) {
+  if (!d) return MQ_ERR_INVAL;
+  std::string o = "{";
+  {
+    std::lock_guard<std::mutex> g(d->mu);
+    const mq::Scheduler& sc = d->sched->s;
+    js_list(o, "vip", sc.vips()); o += ',';
+    js_list(o, "boost", sc.boosts()); o += ',';
+    js_list(o, "blocked_users", std::vector<std::string>(d->blocked_users.begin(), d->blocked_users.end())); o += ',';
+    js_list(o, "blocked_ips", std::vector<std::string>(d->blocked_ips.begin(), d->blocked_ips.end()));
+    o += ",\"counter\":" + std::to_string(sc.counter()) + ",\"users\":[";
+    bool first = true;
+    for (const mq::Scheduler::User* u : sc.users_tui_order()) {
+      if (!first) o += ',';
+      first = false;
+      o += "{\"id\":"; js_str(o, u->name);
+      auto ip = d->user_ips.find(u->name);
+      o += ",\"ip\":"; js_str(o, ip == d->user_ips.end() ? std::string() : ip->second);
+      o += ",\"queued\":" + std::to_string(u->queue.size()) + ",\"processing\":" + std::to_string(u->processing) +
+           ",\"processed\":" + std::to_string(u->processed) + ",\"dropped\":" + std::to_string(u->dropped) + "}";
+    }
+    o += "],\"backends\":[";
+    for (int i = 0; i < sc.n_backends(); ++i) {
+      const mq::Scheduler::Backend* b = sc.backend(i);
+      if (i) o += ',';
+      o += "{\"label\":\"gpu" + std::to_string(i) + "\",\"active\":" + std::to_string(b->active) + ",\"processed\":" +
+           std::to_string(b->processed_count) + ",\"online\":" + (b->online ? "true" : "false") + "}";
+    }
+    o += "]}";
+  }
+  if (out && cap > o.size()) memcpy(out, o.c_str(), o.size() + 1);
+  return (long long)o.size() + 1;  // bytes needed incl. the terminator (call again with a larger buffer if > cap)
+}
 int mq_dispatcher_set_block_file(mq_dispatcher* d, const char* path) {
   if (!d || !path) return MQ_ERR_INVAL;
   std::lock_guard<std::mutex> g(d->mu);

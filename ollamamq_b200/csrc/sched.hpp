@@ -59,6 +59,8 @@ class Scheduler {
   int user_count() const { return (int)users_.size(); }
   std::vector<const User*> users_tui_order() const;  // tui.rs:70-80
   uint64_t counter() const { return counter_; }
+  const std::vector<std::string>& vips() const { return vip_; }
+  const std::vector<std::string>& boosts() const { return boost_; }
   uint64_t pending() const { return pending_; }
 
  private:

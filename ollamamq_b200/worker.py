@@ -273,6 +273,18 @@ class Dispatcher:
         check(lib.mq_dispatcher_log(self._h, arr, n.value, C.byref(n)))
         return [(arr[i].user.decode(), arr[i].user_seq, arr[i].backend) for i in range(n.value)]
 
+    def snapshot(self) -> dict:
+        """Everything the reference dashboard shows, captured under one lock (tui.rs:55-95)."""
+        import json
+        need = lib.mq_dispatcher_snapshot_json(self._h, None, 0)
+        while True:
+            check(need)
+            buf = C.create_string_buffer(int(need) + 256)
+            got = lib.mq_dispatcher_snapshot_json(self._h, buf, len(buf))
+            if 0 < got <= len(buf):
+                return json.loads(buf.value.decode("utf-8", "replace"))
+            need = got
+
     def user_stats(self, user: str) -> dict:
         st = _lib.UserStats()
         check(lib.mq_sched_user_stats(lib.mq_dispatcher_sched(self._h), user.encode(), C.byref(st)))
