@@ -144,6 +144,9 @@ int mq_worker_healthy(mq_worker* w);
 #define MQ_EP_V1_CHAT 2        /* /v1/chat/completions     SSE    */
 #define MQ_EP_V1_COMPLETIONS 3 /* /v1/completions          SSE    */
 #define MQ_EP_RAW_TOKENS 4     /* no framing: chunks are little-endian int32 token ids                    */
+#define MQ_EP_EMBED 6          /* /api/embed, /api/embeddings, /v1/embeddings: one JSON reply, served by the
+                                  embedding worker attached to the backend (section 2b); `path` picks the
+                                  reply shape; 501 when no encoder is attached                             */
 #define MQ_EP_OTHER 5          /* any other routed path (main.rs:92-112): answered by the worker without
                                   touching the GPU (model listings, version) or with 501 (embeddings, model
                                   management); still queued and dispatched like every request               */
@@ -201,6 +204,42 @@ int mq_worker_set_timing(mq_worker* w, int32_t enable);
 int mq_debug_forward(mq_worker* w, const int32_t* tokens, int32_t n, int32_t all_positions, float* logits_out);
 
 /* =====================================================================================================
+ * 2b. Embedding worker - the same seam (dispatcher.rs:287-312) for the embedding routes of main.rs:89-121
+ *     (/api/embed, /api/embeddings, /v1/embeddings): a BERT-family encoder on one B200 (BASELINE configs[4]:
+ *     bge-small), sibling of the generation worker on the same GPU (own stream and host thread).
+ *     Tensors (bf16, torch Linear [out, in]): word_embed [vocab, H], pos_embed [max_positions, H],
+ *     type_embed [type_vocab, H], emb_ln_g / emb_ln_b [H], layers.<i>.{wqkv [3H, H], bqkv [3H], wo [H, H], bo [H],
+ *     attn_ln_g, attn_ln_b [H], w_up [ffn, H], b_up [ffn], w_down [H, ffn], b_down [H], mlp_ln_g, mlp_ln_b [H]}.
+ * ===================================================================================================== */
+typedef struct mq_encoder mq_encoder;
+typedef struct mq_encoder_cfg {
+  int32_t vocab, hidden, ffn, n_layers, n_heads, head_dim; /* heads x head_dim == hidden; head_dim 32/64/96/128 */
+  int32_t max_positions, type_vocab;
+  float ln_eps;
+  int32_t max_seq;               /* inputs are truncated to this many tokens (<= max_positions)             */
+  int32_t max_tokens_per_pass;   /* whole sequences are packed into passes of at most this many tokens      */
+  int32_t use_pdl;
+  char model_name[64];
+} mq_encoder_cfg;
+typedef struct mq_encoder_stats {
+  uint64_t passes, sequences, tokens, kernel_launches;
+} mq_encoder_stats;
+int mq_encoder_open(int32_t gpu, const mq_encoder_cfg* cfg, mq_encoder** out); /* MQ_ERR_NODEV without sm_100 */
+void mq_encoder_close(mq_encoder* e);
+int mq_encoder_load_tensor(mq_encoder* e, const char* name, const void* src, size_t nbytes);
+int mq_encoder_read_tensor(mq_encoder* e, const char* name, void* dst, size_t nbytes);
+int mq_encoder_init_random(mq_encoder* e, uint64_t seed, float std); /* N(0, std^2); LayerNorm gains 1, biases 0 */
+int mq_encoder_healthy(mq_encoder* e);
+int mq_encoder_get_stats(mq_encoder* e, mq_encoder_stats* out);
+/* Blocking compute call (tests, benchmarks, batch jobs): sequence s = tokens[offsets[s] .. offsets[s+1]);
+ * out = fp32 [n_seq][hidden] in host memory, each row the L2-normalised [CLS] state.                       */
+int mq_encoder_embed(mq_encoder* e, const int32_t* tokens, const int32_t* offsets, int32_t n_seq, float* out);
+/* Non-blocking, same contract as mq_submit: body = {"model":..,"input": "s" | ["s",..] | [ids] | [[ids],..]}
+ * (or "prompt": "s" on /api/embeddings), or one sequence in prompt_tokens; exactly one on_status(200,
+ * application/json), one on_chunk with the whole reply (shape chosen by `path`), one on_done.              */
+int mq_encoder_submit(mq_encoder* e, const mq_request* r, const mq_callbacks* cb, void* user, mq_req** out);
+
+/* =====================================================================================================
  * 3. Dispatcher — AppState + run_worker + executor bookkeeping (dispatcher.rs:49-96,164-352) driving a
  *    pool of workers in-process.  This is what `main()` would own in a Rust front (main.rs:82-87).
  * ===================================================================================================== */
@@ -227,6 +266,9 @@ int mq_dispatcher_set_online(mq_dispatcher* d, int32_t backend, int32_t online);
 /* block list persistence: load `path` now (AppState::new, :69,:98-105) and rewrite it on every block / unblock
  * (:107-115).  Format pinned by the reference: pretty JSON {"ips": [...], "users": [...]} (:21-25); the reference
  * uses "blocked_items.json" in the working directory (:19).                                                   */
+/* Give backend `backend` an embedding worker: MQ_EP_EMBED requests dispatched to that backend go to it (without
+ * one they are answered 501 like any unimplemented route).  The dispatcher does not own the encoder.        */
+int mq_dispatcher_attach_encoder(mq_dispatcher* d, int32_t backend, mq_encoder* e);
 int mq_dispatcher_set_block_file(mq_dispatcher* d, const char* path);
 /* Everything the reference dashboard shows, captured under one lock (tui.rs:55-95 capture_snapshot), as one JSON
  * object: vip[], boost[], blocked_users[], blocked_ips[], counter, users[{id, ip, queued, processing, processed,

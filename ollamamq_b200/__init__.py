@@ -5,8 +5,8 @@ implementation of the forward pass: importing the package without a built liboll
 """
 from ._lib import lib, MQError, last_error, check, LIB_PATH  # noqa: F401
 from .dispatcher import Scheduler, Dispatch  # noqa: F401
-from .worker import Worker, Dispatcher, Stream, model_cfg  # noqa: F401
+from .worker import Worker, Dispatcher, Stream, model_cfg, Encoder, encoder_cfg  # noqa: F401
 from . import models  # noqa: F401
 
 __all__ = ["lib", "MQError", "last_error", "check", "Scheduler", "Dispatch", "LIB_PATH", "Worker", "Dispatcher",
-           "Stream", "model_cfg"]
+           "Stream", "model_cfg", "Encoder", "encoder_cfg"]

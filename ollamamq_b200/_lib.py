@@ -48,6 +48,18 @@ class ModelCfg(C.Structure):
                 ("model_name", C.c_char * 64)]
 
 
+class EncoderCfg(C.Structure):
+    _fields_ = [("vocab", C.c_int32), ("hidden", C.c_int32), ("ffn", C.c_int32), ("n_layers", C.c_int32),
+                ("n_heads", C.c_int32), ("head_dim", C.c_int32), ("max_positions", C.c_int32),
+                ("type_vocab", C.c_int32), ("ln_eps", C.c_float), ("max_seq", C.c_int32),
+                ("max_tokens_per_pass", C.c_int32), ("use_pdl", C.c_int32), ("model_name", C.c_char * 64)]
+
+
+class EncoderStats(C.Structure):
+    _fields_ = [("passes", C.c_uint64), ("sequences", C.c_uint64), ("tokens", C.c_uint64),
+                ("kernel_launches", C.c_uint64)]
+
+
 class Request(C.Structure):
     _fields_ = [("endpoint", C.c_int32), ("stream", C.c_int32), ("body", C.c_void_p), ("body_len", C.c_size_t),
                 ("prompt_tokens", C.c_void_p), ("n_prompt_tokens", C.c_int32), ("max_new_tokens", C.c_int32),
@@ -155,6 +167,16 @@ _sig("mq_debug_attn_prefill", C.c_int, [P, P, P, P, C.c_int, P, C.c_int, P, C.c_
 _sig("mq_debug_attn_decode", C.c_int, [P, P, P, P, C.c_int, P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_float, C.c_int])
 _sig("mq_dispatcher_snapshot_json", C.c_longlong, [P, P, C.c_size_t])
+_sig("mq_dispatcher_attach_encoder", C.c_int, [P, C.c_int32, P])
+_sig("mq_encoder_open", C.c_int, [C.c_int32, P, P])
+_sig("mq_encoder_close", None, [P])
+_sig("mq_encoder_load_tensor", C.c_int, [P, C.c_char_p, P, C.c_size_t])
+_sig("mq_encoder_read_tensor", C.c_int, [P, C.c_char_p, P, C.c_size_t])
+_sig("mq_encoder_init_random", C.c_int, [P, C.c_uint64, C.c_float])
+_sig("mq_encoder_healthy", C.c_int, [P])
+_sig("mq_encoder_get_stats", C.c_int, [P, P])
+_sig("mq_encoder_embed", C.c_int, [P, P, P, C.c_int32, P])
+_sig("mq_encoder_submit", C.c_int, [P, P, P, P, P])
 _sig("mq_debug_trace_read", C.c_int, [P, P, C.c_int])
 _sig("mq_debug_argmax", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, P, P, P, P])
 _sig("mq_debug_init_normal", C.c_int, [P, C.c_ulonglong, C.c_ulonglong, C.c_float])

@@ -39,10 +39,21 @@ struct Backend {
 
 struct GpuBackend : Backend {
   mq_worker* w;
+  std::atomic<mq_encoder*> enc{nullptr};  // optional embedding worker on the same GPU (mq_dispatcher_attach_encoder)
   explicit GpuBackend(mq_worker* w_) : w(w_) {}
   int submit(const mq_request* rq, const mq_callbacks* cb, void* user, void** handle) override {
     mq_req* r = nullptr;
-    int rc = mq_submit(w, rq, cb, user, &r);
+    mq_encoder* e = enc.load();
+    int rc;
+    if (rq->endpoint == MQ_EP_EMBED && e) {
+      rc = mq_encoder_submit(e, rq, cb, user, &r);
+    } else if (rq->endpoint == MQ_EP_EMBED) {  // no encoder: the route exists but nothing serves it -> 501
+      mq_request other = *rq;
+      other.endpoint = MQ_EP_OTHER;
+      rc = mq_submit(w, &other, cb, user, &r);
+    } else {
+      rc = mq_submit(w, rq, cb, user, &r);
+    }
     *handle = r;
     return rc;
   }
@@ -353,6 +364,17 @@ int mq_dispatcher_new(mq_worker** workers, int32_t n_workers, int32_t capacity_o
   // reference default: one in-flight request per backend (:204); >1 only when the caller asks for it
   *out = make_dispatcher(std::move(bes), capacity_override > 0 ? capacity_override : 1);
   return *out ? MQ_OK : MQ_ERR_NOMEM;
+}
+
+int mq_dispatcher_attach_encoder(mq_dispatcher* d, int32_t backend, mq_encoder* e) {
+  if (!d || backend < 0 || backend >= (int)d->backends.size()) return MQ_ERR_INVAL;
+  auto* gb = dynamic_cast<GpuBackend*>(d->backends[backend].get());
+  if (!gb) {
+    mq::set_last_error("backend %d is not a GPU worker", backend);
+    return MQ_ERR_INVAL;
+  }
+  gb->enc.store(e);
+  return MQ_OK;
 }
 
 int mq_dispatcher_new_mock(int32_t n_backends, int32_t capacity, mq_dispatcher** out) {

@@ -327,4 +327,115 @@ std::string frame_final(int endpoint, int stream, const char* model, const std::
   return o + buf;
 }
 
+
+// ------------------------------------------------------------------ embeddings
+bool parse_embed_body(const std::string& body, ParsedEmbed* out) {
+  J j{body.data(), body.data() + body.size()};
+  j.ws();
+  if (j.p >= j.e || *j.p != '{') return false;
+  ++j.p;
+  for (;;) {
+    j.ws();
+    if (j.p < j.e && *j.p == '}') return true;
+    std::string k;
+    if (!j.str(&k)) return false;
+    j.ws();
+    if (j.p >= j.e || *j.p != ':') return false;
+    ++j.p;
+    j.ws();
+    if (k == "model") { if (!j.str(&out->model)) return false; }
+    else if (k == "input" || k == "prompt") {
+      if (j.p < j.e && *j.p == '"') { std::string s; if (!j.str(&s)) return false; out->texts.push_back(s); }
+      else if (j.p < j.e && *j.p == '[') {
+        const char* save = j.p;
+        ++j.p;
+        j.ws();
+        if (j.p < j.e && *j.p == ']') { ++j.p; }
+        else if (*j.p == '"') {                       // ["s", ...]
+          for (;;) {
+            std::string s;
+            if (!j.str(&s)) return false;
+            out->texts.push_back(s);
+            j.ws();
+            if (j.p < j.e && *j.p == ',') { ++j.p; continue; }
+            if (j.p < j.e && *j.p == ']') { ++j.p; break; }
+            return false;
+          }
+        } else if (*j.p == '[') {                     // [[ids], ...]
+          for (;;) {
+            std::vector<int32_t> t;
+            if (!j.int_array(&t)) return false;
+            out->token_seqs.push_back(t);
+            j.ws();
+            if (j.p < j.e && *j.p == ',') { ++j.p; continue; }
+            if (j.p < j.e && *j.p == ']') { ++j.p; break; }
+            return false;
+          }
+        } else {                                      // [ids]
+          j.p = save;
+          std::vector<int32_t> t;
+          if (!j.int_array(&t)) return false;
+          out->token_seqs.push_back(t);
+        }
+      } else if (!j.skip()) return false;
+    }
+    else if (!j.skip()) return false;
+    j.ws();
+    if (j.p < j.e && *j.p == ',') ++j.p;
+  }
+}
+
+std::vector<int32_t> embed_tokenize(const std::string& text, int vocab, int max_len) {
+  // BERT conventions where the vocabulary has room for them: [CLS] = 101, [SEP] = 102, bytes from 1000
+  const int cls = vocab > 1300 ? 101 : 1, sep = vocab > 1300 ? 102 : 2, base = vocab > 1300 ? 1000 : 3;
+  std::vector<int32_t> t;
+  t.push_back(cls);
+  for (unsigned char c : text) {
+    if ((int)t.size() >= max_len - 1) break;
+    t.push_back(base + (int)(c % (unsigned)(vocab - base)));
+  }
+  if ((int)t.size() < max_len) t.push_back(sep);
+  return t;
+}
+
+static void append_vec(std::string& o, const float* v, int dim) {
+  char b[32];
+  o += '[';
+  for (int i = 0; i < dim; ++i) {
+    snprintf(b, sizeof b, i ? ",%.8g" : "%.8g", (double)v[i]);
+    o += b;
+  }
+  o += ']';
+}
+std::string frame_embeddings(const std::string& path, const char* model, const float* emb, int n, int dim, int n_tokens) {
+  const std::string m = json_escape(model);
+  std::string o;
+  o.reserve((size_t)n * dim * 14 + 256);
+  char b[160];
+  if (path == "/api/embeddings") {  // legacy Ollama route: one prompt, one vector
+    o = "{\"embedding\":";
+    append_vec(o, emb, n > 0 ? dim : 0);
+    return o + "}";
+  }
+  if (path == "/v1/embeddings") {
+    o = "{\"object\":\"list\",\"data\":[";
+    for (int i = 0; i < n; ++i) {
+      if (i) o += ',';
+      o += "{\"object\":\"embedding\",\"embedding\":";
+      append_vec(o, emb + (size_t)i * dim, dim);
+      snprintf(b, sizeof b, ",\"index\":%d}", i);
+      o += b;
+    }
+    snprintf(b, sizeof b, "],\"model\":\"%s\",\"usage\":{\"prompt_tokens\":%d,\"total_tokens\":%d}}", m.c_str(), n_tokens, n_tokens);
+    return o + b;
+  }
+  o = "{\"model\":\"" + m + "\",\"embeddings\":[";
+  for (int i = 0; i < n; ++i) {
+    if (i) o += ',';
+    append_vec(o, emb + (size_t)i * dim, dim);
+  }
+  snprintf(b, sizeof b, "],\"prompt_eval_count\":%d}", n_tokens);
+  return o + b;
+}
+
 }  // namespace mq

@@ -27,4 +27,16 @@ std::string frame_token(int endpoint, const char* model, int tok);
 void other_route_response(const std::string& path, const char* model, int* status, std::string* ctype, std::string* body);
 std::string frame_final(int endpoint, int stream, const char* model, const std::string& agg, int n_prompt, int n_gen);
 
+// ---- embeddings (/api/embed, /api/embeddings, /v1/embeddings)
+struct ParsedEmbed {
+  std::string model;
+  std::vector<std::string> texts;              // "input": "s" | ["s", ...]   or "prompt": "s" (/api/embeddings)
+  std::vector<std::vector<int32_t>> token_seqs;  // "input": [ids] | [[ids], ...] (OpenAI token inputs)
+};
+bool parse_embed_body(const std::string& body, ParsedEmbed* out);
+// [CLS] bytes... [SEP] over a byte-level vocabulary (random-init weights have no word pieces), truncated to max_len
+std::vector<int32_t> embed_tokenize(const std::string& text, int vocab, int max_len);
+// emb: n rows of `dim` floats; the reply shape follows the route (Ollama /api/embed, legacy /api/embeddings, OpenAI)
+std::string frame_embeddings(const std::string& path, const char* model, const float* emb, int n, int dim, int n_tokens);
+
 }  // namespace mq

@@ -56,6 +56,7 @@ int endpoint_of(const std::string& path) {
   if (path == "/api/chat") return MQ_EP_API_CHAT;
   if (path == "/v1/chat/completions") return MQ_EP_V1_CHAT;
   if (path == "/v1/completions") return MQ_EP_V1_COMPLETIONS;
+  if (path == "/api/embed" || path == "/api/embeddings" || path == "/v1/embeddings") return MQ_EP_EMBED;
   return MQ_EP_OTHER;
 }
 

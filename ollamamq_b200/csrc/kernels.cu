@@ -210,6 +210,7 @@ static void dispatch_head_dim(int d, F&& f) {
     case 128: f(std::integral_constant<int, 128>{}); break;
     case 96: f(std::integral_constant<int, 96>{}); break;
     case 64: f(std::integral_constant<int, 64>{}); break;
+    case 32: f(std::integral_constant<int, 32>{}); break;  // BERT-small heads (encoder path)
     default: break;  // rejected at mq_worker_open / by the debug ABI before any launch
   }
 }
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
     tok0 = t.x; ntok = t.y; slot = t.z; pos0 = t.w;
   }
   const int n_rows = ntok * G;
-  int kv_begin = 0, kv_end = pos0 + ntok;
+  int kv_begin = 0, kv_end = p.bidirectional ? p.seq_len[slot] : pos0 + ntok;  // encoder rows see the whole sequence
   const bool split = DECODE && p.n_splits > 1;
   if (split) {
     // every sequence is cut into n_splits equal 16-aligned ranges of ITS OWN length (balanced CTAs, and no
@@ -440,7 +441,7 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
         for (int e = 0; e < 4; ++e) {
           const int col = t0 + n * 8 + 2 * c + (e & 1);
           const int qpos = (e < 2) ? qpos_a : qpos_b;
-          const bool ok = (col <= qpos) && (col < kv_end);
+          const bool ok = (p.bidirectional || col <= qpos) && (col < kv_end);
           const float v = ok ? s[n][e] * p.scale_log2 : -INFINITY;
           s[n][e] = v;
           if (e < 2) mx_a = fmaxf(mx_a, v); else mx_b = fmaxf(mx_b, v);
@@ -832,6 +833,7 @@ void attn_set_attrs() {
   go(std::integral_constant<int, 128>{});
   go(std::integral_constant<int, 96>{});
   go(std::integral_constant<int, 64>{});
+  go(std::integral_constant<int, 32>{});
 }
 void launch_attn_prefill(const LaunchCfg& lc, const AttnParams& p, int n_tiles) {
   dispatch_head_dim(p.head_dim, [&](auto dtag) {
@@ -969,6 +971,90 @@ __global__ void fill_bf16_kernel(__nv_bfloat16* w, size_t n, float v) {
 }
 void launch_fill_bf16(cudaStream_t st, __nv_bfloat16* w, size_t n, float v) {
   fill_bf16_kernel<<<148, 256, 0, st>>>(w, n, v);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// BERT-style encoder pieces (/api/embed path, BASELINE configs[4]): embeddings + LayerNorm, residual + bias +
+// post-LayerNorm, [CLS] pooling with L2 normalisation.  One CTA per row, H / 4 threads, one float4 per thread.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();  // red may still be read by the previous reduction
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) tot += red[w];
+  return tot;
+}
+__device__ __forceinline__ float4 ld_bf16x4(const __nv_bfloat16* p) {
+  const uint2 a = *reinterpret_cast<const uint2*>(p);
+  return make_float4(bf16_lo(a.x), bf16_hi(a.x), bf16_lo(a.y), bf16_hi(a.y));
+}
+// LayerNorm of the thread-distributed row value v (mean and variance over H), written as fp32 h and bf16 x
+__device__ __forceinline__ void ln_store(float4 v, int H, float eps, const __nv_bfloat16* g, const __nv_bfloat16* b,
+                                         float* h_row, __nv_bfloat16* x_row, float* red) {
+  const int i = threadIdx.x * 4;
+  const float mean = block_sum(v.x + v.y + v.z + v.w, red) / (float)H;
+  const float4 d = make_float4(v.x - mean, v.y - mean, v.z - mean, v.w - mean);
+  const float var = block_sum(d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w, red) / (float)H;
+  const float rstd = rsqrtf(var + eps);
+  const float4 gg = ld_bf16x4(g + i), bb = ld_bf16x4(b + i);
+  const float4 o = make_float4(d.x * rstd * gg.x + bb.x, d.y * rstd * gg.y + bb.y, d.z * rstd * gg.z + bb.z,
+                               d.w * rstd * gg.w + bb.w);
+  *reinterpret_cast<float4*>(h_row + i) = o;
+  *reinterpret_cast<uint2*>(x_row + i) = pack4_bf16(o.x, o.y, o.z, o.w);
+}
+__global__ void enc_embed_ln_kernel(const int* __restrict__ tok, const int* __restrict__ pos,
+                                    const __nv_bfloat16* __restrict__ word, const __nv_bfloat16* __restrict__ pos_emb,
+                                    const __nv_bfloat16* __restrict__ type_emb, const __nv_bfloat16* __restrict__ g,
+                                    const __nv_bfloat16* __restrict__ b, float* __restrict__ h,
+                                    __nv_bfloat16* __restrict__ x, int H, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[32];
+  const int t = blockIdx.x, i = threadIdx.x * 4;
+  const float4 a = ld_bf16x4(word + (size_t)tok[t] * H + i), c = ld_bf16x4(pos_emb + (size_t)pos[t] * H + i),
+               e = ld_bf16x4(type_emb + i);  // token type 0 everywhere (single-segment inputs)
+  ln_store(make_float4(a.x + c.x + e.x, a.y + c.y + e.y, a.z + c.z + e.z, a.w + c.w + e.w), H, eps, g, b,
+           h + (size_t)t * H, x + (size_t)t * H, red);
+}
+void launch_enc_embed_ln(const LaunchCfg& lc, const int* tok, const int* pos, const __nv_bfloat16* word,
+                         const __nv_bfloat16* pos_emb, const __nv_bfloat16* type_emb, const __nv_bfloat16* g,
+                         const __nv_bfloat16* b, float* h, __nv_bfloat16* x, int T, int H, float eps) {
+  launch_k(lc, enc_embed_ln_kernel, dim3(T), dim3(H / 4), 0, tok, pos, word, pos_emb, type_emb, g, b, h, x, H, eps);
+}
+// h = LayerNorm(h + sub + bias) * g + b   (BertSelfOutput / BertOutput: dense output + residual, post-LN)
+__global__ void enc_add_ln_kernel(float* __restrict__ h, const __nv_bfloat16* __restrict__ sub,
+                                  const __nv_bfloat16* __restrict__ bias, const __nv_bfloat16* __restrict__ g,
+                                  const __nv_bfloat16* __restrict__ b, __nv_bfloat16* __restrict__ x, int H, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[32];
+  const int t = blockIdx.x, i = threadIdx.x * 4;
+  const float4 r = *reinterpret_cast<const float4*>(h + (size_t)t * H + i), s = ld_bf16x4(sub + (size_t)t * H + i),
+               bi = ld_bf16x4(bias + i);
+  ln_store(make_float4(r.x + s.x + bi.x, r.y + s.y + bi.y, r.z + s.z + bi.z, r.w + s.w + bi.w), H, eps, g, b,
+           h + (size_t)t * H, x + (size_t)t * H, red);
+}
+void launch_enc_add_ln(const LaunchCfg& lc, float* h, const __nv_bfloat16* sub, const __nv_bfloat16* bias,
+                       const __nv_bfloat16* g, const __nv_bfloat16* b, __nv_bfloat16* x, int T, int H, float eps) {
+  launch_k(lc, enc_add_ln_kernel, dim3(T), dim3(H / 4), 0, h, sub, bias, g, b, x, H, eps);
+}
+// out[s, :] = h[first_tok[s], :] / ||.||_2   ([CLS] pooling + L2 normalisation, the bge recipe)
+__global__ void enc_pool_kernel(const float* __restrict__ h, const int* __restrict__ first_tok, float* __restrict__ out,
+                                int H) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[32];
+  const int s = blockIdx.x, i = threadIdx.x * 4;
+  const float4 v = *reinterpret_cast<const float4*>(h + (size_t)first_tok[s] * H + i);
+  const float n = sqrtf(block_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w, red));
+  const float inv = 1.0f / fmaxf(n, 1e-12f);
+  *reinterpret_cast<float4*>(out + (size_t)s * H + i) = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+}
+void launch_enc_pool(const LaunchCfg& lc, const float* h, const int* first_tok, float* out, int n_seq, int H) {
+  launch_k(lc, enc_pool_kernel, dim3(n_seq), dim3(H / 4), 0, h, first_tok, out, H);
 }
 
 }  // namespace mq

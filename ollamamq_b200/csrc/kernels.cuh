@@ -10,6 +10,7 @@ namespace mq {
 constexpr int kPageSize = 16;  // tokens per KV page
 constexpr int kMaxSplitPlanes = 8;  // split-K planes a reduce kernel (add_rmsnorm / rope_kv) may have to sum
 inline bool head_dim_supported(int d) { return d == 128 || d == 96 || d == 64; }  // Llama-3 / Qwen2.5, Phi-3, small models
+// (the rope / attention kernels also have a head_dim 32 instance, used by the BERT encoder path only)
 
 struct LaunchCfg {
   cudaStream_t stream;
@@ -60,7 +61,9 @@ struct AttnParams {
   float* part_o;       // decode split partials [splits][T][n_q][d]
   float* part_ml;      // [splits][T][n_q][2]
   int n_q, n_kv, T;
-  int head_dim;        // 128, 96 or 64
+  int head_dim;        // 128, 96 or 64 (32: encoder)
+  int bidirectional;   // prefill only: 1 = no causal mask (encoder self-attention); needs seq_len
+  const int* seq_len;  // prefill, bidirectional: [slots] total length of each sequence
   int n_splits;        // decode only: every sequence is cut into n_splits equal 16-aligned ranges (grid-level)
   int n_warps;         // decode only: 1, or 2 / 4 / 8 = in-CTA split over that many warps (then n_splits == 1)
   int* split_counter;  // decode only: [slots][n_kv] arrival counters (zero between launches)
@@ -78,6 +81,14 @@ constexpr int kPrefillTileRows = 64;  // q rows (token x group-head) per prefill
 // next[b] = argmax_v logits[b][v]; optional: cur_token[slot]=next, pos[slot]+=1 for active slots
 void launch_argmax(const LaunchCfg& lc, const float* logits, int rows, int V, int ldl, int* out_tokens,
                    const int* dst_slot, int* cur_token, int* pos_inc, const int* active);
+
+// ---- encoder (BERT) pieces: H % 128 == 0, H / 4 <= 1024 threads
+void launch_enc_embed_ln(const LaunchCfg& lc, const int* tok, const int* pos, const __nv_bfloat16* word,
+                         const __nv_bfloat16* pos_emb, const __nv_bfloat16* type_emb, const __nv_bfloat16* g,
+                         const __nv_bfloat16* b, float* h, __nv_bfloat16* x, int T, int H, float eps);
+void launch_enc_add_ln(const LaunchCfg& lc, float* h, const __nv_bfloat16* sub, const __nv_bfloat16* bias,
+                       const __nv_bfloat16* g, const __nv_bfloat16* b, __nv_bfloat16* x, int T, int H, float eps);
+void launch_enc_pool(const LaunchCfg& lc, const float* h, const int* first_tok, float* out, int n_seq, int H);
 
 // deterministic counter-based N(0, std^2) fill (splitmix64 + Box-Muller), bf16
 void launch_init_normal(cudaStream_t st, __nv_bfloat16* w, size_t n, uint64_t seed, float std);

@@ -29,6 +29,17 @@ def model_cfg(geom: dict, max_batch=64, max_seq=1024, max_prefill_tokens=2048, k
     return c
 
 
+def encoder_cfg(geom: dict, max_seq=512, max_tokens_per_pass=8192, use_pdl=1, model_name="random-init-encoder"):
+    c = _lib.EncoderCfg()
+    for k in ("vocab", "hidden", "ffn", "n_layers", "n_heads", "head_dim", "max_positions"):
+        setattr(c, k, int(geom[k]))
+    c.type_vocab = int(geom.get("type_vocab", 2))
+    c.ln_eps = float(geom.get("ln_eps", 1e-12))
+    c.max_seq, c.max_tokens_per_pass, c.use_pdl = min(max_seq, c.max_positions), max_tokens_per_pass, use_pdl
+    c.model_name = model_name.encode()[:63]
+    return c
+
+
 class Stream:
     """Receives the Status / Chunk / Done parts of one request (the reference's mpsc receiver)."""
 
@@ -185,6 +196,76 @@ class Worker:
         check(lib.mq_worker_set_timing(self._h, 1 if on else 0))
 
 
+class Encoder:
+    """Embedding worker on one B200 (BERT-family encoder; /api/embed, /api/embeddings, /v1/embeddings)."""
+
+    EP_EMBED = 6
+
+    def __init__(self, gpu: int, cfg: _lib.EncoderCfg):
+        self.cfg = cfg
+        h = C.c_void_p()
+        check(lib.mq_encoder_open(gpu, C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            lib.mq_encoder_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def load_weights(self, weights: Dict[str, "object"]):
+        for name, t in weights.items():
+            t = t.contiguous()
+            check(lib.mq_encoder_load_tensor(self._h, name.encode(), C.c_void_p(t.data_ptr()),
+                                             t.numel() * t.element_size()))
+
+    def read_tensor(self, name: str, like):
+        check(lib.mq_encoder_read_tensor(self._h, name.encode(), C.c_void_p(like.data_ptr()),
+                                         like.numel() * like.element_size()))
+        return like
+
+    def init_random(self, seed=0, std=0.05):
+        check(lib.mq_encoder_init_random(self._h, seed, std))
+
+    def healthy(self) -> bool:
+        return bool(lib.mq_encoder_healthy(self._h))
+
+    def stats(self) -> dict:
+        st = _lib.EncoderStats()
+        check(lib.mq_encoder_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in st._fields_}
+
+    def embed(self, sequences: Sequence[Sequence[int]]):
+        """Blocking: numpy fp32 [n_seq, hidden], rows L2-normalised."""
+        import numpy as np
+        flat = [t for s in sequences for t in s]
+        offs = [0]
+        for s in sequences:
+            offs.append(offs[-1] + len(s))
+        toks = (C.c_int32 * max(1, len(flat)))(*flat)
+        off = (C.c_int32 * len(offs))(*offs)
+        out = np.empty((len(sequences), self.cfg.hidden), dtype=np.float32)
+        check(lib.mq_encoder_embed(self._h, toks, off, len(sequences), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def submit(self, sink: "Stream", body: bytes, path: str = "/api/embed") -> "Stream":
+        r, keep = make_request(endpoint=self.EP_EMBED, body=body, path=path)
+        h = C.c_void_p()
+        sink.t_submit = time.perf_counter()
+        check(lib.mq_encoder_submit(self._h, C.byref(r), C.byref(sink.cb), None, C.byref(h)))
+        sink.handle = h
+        return sink
+
+
 class Dispatcher:
     """`AppState` + `run_worker` (dispatcher.rs:49-96,164-352) over GPU workers or step-driven mock backends."""
 
@@ -232,6 +313,9 @@ class Dispatcher:
 
     def set_online(self, backend, online):
         check(lib.mq_dispatcher_set_online(self._h, backend, 1 if online else 0))
+
+    def attach_encoder(self, backend: int, enc: "Encoder"):
+        check(lib.mq_dispatcher_attach_encoder(self._h, backend, enc.handle))
 
     def set_block_file(self, path: str):
         check(lib.mq_dispatcher_set_block_file(self._h, path.encode()))

@@ -1,0 +1,158 @@
+"""GPU: the embedding worker (BASELINE configs[4], /api/embed) against the fp32 BERT oracle (oracle/bert_ref.py, pinned to
+HF BertModel by tests/golden/bert_tiny.json).  Tolerance: bf16 tensor-core GEMMs / bf16 activations vs fp32 -
+per embedding `max|d| <= 3e-2 * max|e|` and cosine >= 0.999 (rows are unit vectors)."""
+import json
+import os
+import urllib.request
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("needs a GPU", allow_module_level=True)
+pytestmark = pytest.mark.gpu
+
+import ollamamq_b200 as mq  # noqa: E402
+from ollamamq_b200.models import LLAMA3_8B  # noqa: E402,F401
+from oracle import bert_ref as B  # noqa: E402
+
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bert_tiny.json")))
+TOL = 3e-2
+
+
+def _close(got, ref):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    err = np.abs(got - ref).max()
+    cos = float((got * ref).sum() / (np.linalg.norm(got) * np.linalg.norm(ref)))
+    assert err <= TOL * np.abs(ref).max() and cos >= 0.999, (err, np.abs(ref).max(), cos)
+
+
+def _open(cfg, w, **kw):
+    e = mq.Encoder(0, mq.encoder_cfg(cfg, **kw))
+    e.load_weights(w)
+    return e
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["cases"])))
+def test_embedding_matches_hf_golden(i):
+    c = GOLD["cases"][i]
+    cfg = B.TINY_BERT
+    w = B.make_weights(cfg, seed=c["seed"])
+    with _open(cfg, w, max_seq=128, max_tokens_per_pass=512) as e:
+        got = e.embed([c["tokens"]])[0]
+    assert abs(float(np.linalg.norm(got)) - 1.0) < 1e-3
+    _close(got, c["embedding"])
+
+
+@pytest.mark.parametrize("pdl", [0, 1])
+def test_ragged_batches_single_and_multi_pass(pdl):
+    cfg = dict(B.TINY_BERT, hidden=256, n_heads=8, ffn=512, n_layers=3)
+    w = B.make_weights(cfg, seed=5, device="cuda")
+    g = torch.Generator().manual_seed(11)
+    lens = [1, 2, 15, 16, 17, 63, 64, 65, 100, 128, 3, 77, 128, 31, 5, 90]
+    seqs = [torch.randint(0, cfg["vocab"], (n,), generator=g).tolist() for n in lens]
+    ref = B.embed(w, cfg, seqs).cpu().numpy()
+    with _open(cfg, w, max_seq=128, max_tokens_per_pass=1024, use_pdl=pdl) as e:     # everything in one pass
+        one = e.embed(seqs)
+        assert e.stats()["passes"] == 1 and e.stats()["sequences"] == len(seqs)
+    with _open(cfg, w, max_seq=128, max_tokens_per_pass=256, use_pdl=pdl) as e:      # several passes
+        many = e.embed(seqs)
+        assert e.stats()["passes"] >= 4
+        solo = e.embed([seqs[8]])[0]
+    for i in range(len(seqs)):
+        _close(one[i], ref[i])
+        _close(many[i], ref[i])
+    # packing must not leak between sequences: a sequence alone gives the same row as inside a batch
+    assert np.abs(solo - many[8]).max() <= 2e-3 and np.abs(one - many).max() <= 2e-3
+    # inputs longer than max_seq are truncated, like a backend context limit
+    with _open(cfg, w, max_seq=64, max_tokens_per_pass=256) as e:
+        _close(e.embed([seqs[9]])[0], B.embed(w, cfg, [seqs[9][:64]])[0].cpu().numpy())
+
+
+def test_full_size_bge_small_geometry():
+    """BASELINE configs[4] geometry at full size (hidden 384, 12 layers, 12 heads of 32, ffn 1536, vocab 30 522):
+    weights initialised on the device, read back so the oracle sees the same bf16 values; 512-token inputs."""
+    cfg = B.BGE_SMALL
+    with mq.Encoder(0, mq.encoder_cfg(cfg, max_seq=512, max_tokens_per_pass=8192)) as e:
+        e.init_random(seed=3, std=0.05)
+        w = {}
+        for name, shape in B.tensor_shapes(cfg).items():
+            w[name] = e.read_tensor(name, torch.empty(shape, dtype=torch.bfloat16, device="cuda"))
+        # give the LayerNorms and biases non-trivial values too (init_random leaves them at 1 / 0)
+        g = torch.Generator().manual_seed(4)
+        for name in list(w):
+            leaf = name.split(".")[-1]
+            if leaf.endswith("ln_g"):
+                w[name] = (1.0 + 0.1 * torch.randn(w[name].shape, generator=g)).to(torch.bfloat16).cuda()
+            elif leaf.endswith("ln_b") or leaf.startswith("b"):
+                w[name] = (0.1 * torch.randn(w[name].shape, generator=g)).to(torch.bfloat16).cuda()
+        e.load_weights(w)
+        rng = np.random.default_rng(2)
+        seqs = [rng.integers(0, cfg["vocab"], n).astype("int32").tolist() for n in (512, 512, 300, 7, 512, 129)]
+        got = e.embed(seqs)
+        ref = B.embed(w, cfg, seqs).cpu().numpy()
+        worst = 0.0
+        for i in range(len(seqs)):
+            _close(got[i], ref[i])
+            worst = max(worst, float(np.abs(got[i] - ref[i]).max() / np.abs(ref[i]).max()))
+        print("bge-small full size: worst max|d| / max|e| = %.4f over %d sequences" % (worst, len(seqs)))
+        # a config-5 sized slice: 64 x 512 tokens in passes of 8192
+        batch = [rng.integers(0, cfg["vocab"], 512).astype("int32").tolist() for _ in range(64)]
+        out = e.embed(batch)
+        assert out.shape == (64, 384) and np.allclose(np.linalg.norm(out, axis=1), 1.0, atol=1e-3)
+        _close(out[63], B.embed(w, cfg, [batch[63]])[0].cpu().numpy())
+        assert e.stats()["passes"] >= 5
+
+
+def test_embed_routes_through_dispatcher_and_http():
+    """The three embedding routes of main.rs:89-121 end to end: HTTP ingress -> fair-share dispatcher -> the backend's
+    embedding worker; without an attached encoder the route answers 501 like any unimplemented backend path."""
+    from tests.test_engine_gpu import MID
+    from oracle import llama_ref as R
+    cfg = B.TINY_BERT
+    w = B.make_weights(cfg, seed=7, device="cuda")
+    lw = R.make_weights(MID, seed=1, device="cuda")
+    with mq.Worker(0, mq.model_cfg(MID, max_batch=4, max_seq=128, max_prefill_tokens=256)) as wk, \
+            _open(cfg, w, max_seq=64, max_tokens_per_pass=256) as enc:
+        wk.load_weights(lw)
+        d = mq.Dispatcher([wk], capacity=4)
+        try:
+            port = d.serve_http()
+
+            def post(path, body, user="alice"):
+                rq = urllib.request.Request("http://127.0.0.1:%d%s" % (port, path), data=json.dumps(body).encode(),
+                                            headers={"X-User-ID": user, "Content-Type": "application/json"})
+                try:
+                    with urllib.request.urlopen(rq, timeout=60) as r:
+                        return r.status, r.headers.get("Content-Type"), r.read()
+                except urllib.error.HTTPError as ex:
+                    return ex.code, ex.headers.get("Content-Type"), ex.read()
+
+            st, _, body = post("/api/embed", {"model": "m", "input": "hello"})
+            assert st == 501 and b"not implemented" in body                  # no encoder attached yet
+            d.attach_encoder(0, enc)
+            st, ct, body = post("/api/embed", {"model": "bge", "input": ["hello world", "a"]})
+            assert st == 200 and ct.startswith("application/json")
+            js = json.loads(body)
+            assert js["model"] == "bge" and len(js["embeddings"]) == 2 and len(js["embeddings"][0]) == cfg["hidden"]
+            # byte-level tokenisation restated: [CLS]=1, bytes from 3, [SEP]=2 for this small vocabulary
+            toks = [1] + [3 + (b % (cfg["vocab"] - 3)) for b in b"hello world"] + [2]
+            _close(js["embeddings"][0], B.embed(w, cfg, [toks])[0].cpu().numpy())
+            assert js["prompt_eval_count"] == len(toks) + 3
+            st, _, body = post("/v1/embeddings", {"model": "bge", "input": [[5, 6, 7], [9]]})
+            js = json.loads(body)
+            assert st == 200 and js["object"] == "list" and [x["index"] for x in js["data"]] == [0, 1]
+            _close(js["data"][0]["embedding"], B.embed(w, cfg, [[5, 6, 7]])[0].cpu().numpy())
+            assert js["usage"]["prompt_tokens"] == 4
+            st, _, body = post("/api/embeddings", {"model": "bge", "prompt": "hello world"})
+            js = json.loads(body)
+            assert st == 200 and len(js["embedding"]) == cfg["hidden"]
+            _close(js["embedding"], B.embed(w, cfg, [toks])[0].cpu().numpy())
+            # chat still works next to it on the same backend, and the embed requests were accounted to the user
+            st, _, body = post("/api/chat", {"model": "m", "messages": [{"role": "user", "content": "hi"}],
+                                             "stream": False, "options": {"num_predict": 3}})
+            assert st == 200 and json.loads(body)["done"] is True
+            assert d.user_stats("alice")["processed"] == 5
+        finally:
+            d.close()
