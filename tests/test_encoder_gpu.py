@@ -108,8 +108,9 @@ def test_full_size_bge_small_geometry():
 def test_embed_routes_through_dispatcher_and_http():
     """The three embedding routes of main.rs:89-121 end to end: HTTP ingress -> fair-share dispatcher -> the backend's
     embedding worker; without an attached encoder the route answers 501 like any unimplemented backend path."""
-    from tests.test_engine_gpu import MID
     from oracle import llama_ref as R
+    MID = dict(vocab=2048, hidden=1024, ffn=2816, n_layers=3, n_q_heads=8, n_kv_heads=2, head_dim=128, qkv_bias=0,
+               rope_theta=500000.0, rms_eps=1e-5)
     cfg = B.TINY_BERT
     w = B.make_weights(cfg, seed=7, device="cuda")
     lw = R.make_weights(MID, seed=1, device="cuda")
