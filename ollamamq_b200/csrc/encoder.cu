@@ -6,10 +6,11 @@
 // steps exactly as two models share one Ollama instance.
 //
 // One pass = whole sequences packed back to back (<= max_tokens_per_pass tokens, <= max_seqs sequences):
-//   embeddings + LayerNorm -> per layer [ QKV GEMM (tcgen05) -> bias + paged K/V scatter (rope kernel with zero
-//   frequencies = identity rotation) -> bidirectional flash attention over the pages -> O GEMM -> bias + residual +
-//   LayerNorm -> up GEMM with bias + erf-GELU epilogue -> down GEMM -> bias + residual + LayerNorm ] -> [CLS] pooling
-//   + L2 normalisation.  K/V pages are reused by every layer and every pass (an encoder keeps no cache).
+//   embeddings + LayerNorm -> per layer [ QKV GEMM (tcgen05) with the bias added in the epilogue -> bidirectional flash
+//   attention reading q / k / v straight out of the packed [T, 3H] activation (an encoder keeps no cache, so there is
+//   no paging and no scatter kernel: r01 measured the decoder's rope/scatter kernel at 47 us per layer for what is a
+//   pure copy here) -> O GEMM -> bias + residual + LayerNorm -> up GEMM with bias + erf-GELU epilogue -> down GEMM ->
+//   bias + residual + LayerNorm ] -> [CLS] pooling + L2 normalisation.
 #include "engine.hpp"
 #include "framing.hpp"
 #include <algorithm>
@@ -56,12 +57,11 @@ struct mq_encoder {
   std::map<std::string, DevTensor> tensors;
   __nv_bfloat16 *word = nullptr, *pos_emb = nullptr, *type_emb = nullptr, *emb_g = nullptr, *emb_b = nullptr;
   std::vector<EncLayer> layers;
-  int MT = 0, max_seqs = 0, pages_per_seq = 0;
+  int MT = 0, max_seqs = 0;
   // activations
-  float *h = nullptr, *d_out = nullptr, *inv_freq_zero = nullptr;
-  __nv_bfloat16 *x = nullptr, *qkv = nullptr, *q = nullptr, *attn = nullptr, *sub = nullptr, *act = nullptr;
-  __nv_bfloat16 *k_cache = nullptr, *v_cache = nullptr;
-  int *d_meta = nullptr, *d_block_table = nullptr;  // meta: tok | pos | slot | first_tok | seq_len | tiles
+  float *h = nullptr, *d_out = nullptr;
+  __nv_bfloat16 *x = nullptr, *qkv = nullptr, *attn = nullptr, *sub = nullptr, *act = nullptr;
+  int* d_meta = nullptr;  // tok | pos | first_tok | seq_len | tiles
   int* h_meta = nullptr;                            // pinned mirror
   float* h_out = nullptr;                           // pinned [max_seqs][H]
   size_t meta_ints = 0;
@@ -123,32 +123,17 @@ int enc_setup(mq_encoder* e) {
   }
 #undef T_
   e->MT = (std::max(c.max_tokens_per_pass, c.max_seq) + 255) / 256 * 256;
-  e->pages_per_seq = (c.max_seq + kPageSize - 1) / kPageSize;
   e->max_seqs = std::max(1, std::min(1024, e->MT / 8));
   const size_t MT = e->MT;
   if ((rc = enc_alloc(&e->h, MT * H))) return rc;
   if ((rc = enc_alloc(&e->x, MT * H))) return rc;
   if ((rc = enc_alloc(&e->qkv, MT * 3 * H))) return rc;
-  if ((rc = enc_alloc(&e->q, MT * H))) return rc;
   if ((rc = enc_alloc(&e->attn, MT * H))) return rc;
   if ((rc = enc_alloc(&e->sub, MT * H))) return rc;
   if ((rc = enc_alloc(&e->act, MT * I))) return rc;
   if ((rc = enc_alloc(&e->d_out, (size_t)e->max_seqs * H))) return rc;
-  if ((rc = enc_alloc(&e->inv_freq_zero, (size_t)c.head_dim))) return rc;
-  ENC_TRY(cudaMemset(e->inv_freq_zero, 0, (size_t)c.head_dim * 4));  // zero angles: the "rotation" is a plain copy
-  // pages: page 0 scratch, then pages_per_seq per sequence slot; only as many as one pass can touch
-  const size_t n_pages = 1 + (size_t)e->max_seqs * e->pages_per_seq;
-  const size_t cache_elems = n_pages * c.n_heads * kPageSize * c.head_dim;
-  if ((rc = enc_alloc(&e->k_cache, cache_elems))) return rc;
-  if ((rc = enc_alloc(&e->v_cache, cache_elems))) return rc;
-  ENC_TRY(cudaMemset(e->k_cache, 0, cache_elems * 2));
-  ENC_TRY(cudaMemset(e->v_cache, 0, cache_elems * 2));
-  std::vector<int> bt((size_t)e->max_seqs * e->pages_per_seq);
-  for (size_t i = 0; i < bt.size(); ++i) bt[i] = 1 + (int)i;  // static: slot s owns pages [1 + s * pps, 1 + (s + 1) * pps)
-  if ((rc = enc_alloc(&e->d_block_table, bt.size()))) return rc;
-  ENC_TRY(cudaMemcpy(e->d_block_table, bt.data(), bt.size() * 4, cudaMemcpyHostToDevice));
   const size_t max_tiles = MT / kEncTileRows + e->max_seqs + 1;
-  e->meta_ints = 3 * MT + 2 * (size_t)e->max_seqs + 4 * max_tiles;
+  e->meta_ints = 2 * MT + 2 * (size_t)e->max_seqs + 4 * max_tiles;
   if ((rc = enc_alloc(&e->d_meta, e->meta_ints))) return rc;
   ENC_TRY(cudaMallocHost((void**)&e->h_meta, e->meta_ints * 4));
   ENC_TRY(cudaMallocHost((void**)&e->h_out, (size_t)e->max_seqs * H * 4));
@@ -162,8 +147,8 @@ int enc_pass(mq_encoder* e, const std::vector<const std::vector<int32_t>*>& seqs
   const LaunchCfg lc{e->stream, c.use_pdl != 0};
   int T = 0;
   for (auto* s : seqs) T += (int)s->size();
-  int *m_tok = e->h_meta, *m_pos = m_tok + e->MT, *m_slot = m_pos + e->MT, *m_first = m_slot + e->MT,
-      *m_len = m_first + e->max_seqs, *m_tiles = m_len + e->max_seqs;
+  int *m_tok = e->h_meta, *m_pos = m_tok + e->MT, *m_first = m_pos + e->MT, *m_len = m_first + e->max_seqs,
+      *m_tiles = m_len + e->max_seqs;
   int t = 0, n_tiles = 0;
   for (int s = 0; s < n; ++s) {
     const int len = (int)seqs[s]->size();
@@ -173,7 +158,6 @@ int enc_pass(mq_encoder* e, const std::vector<const std::vector<int32_t>*>& seqs
       const int id = (*seqs[s])[i];
       m_tok[t + i] = id < 0 ? 0 : (id >= c.vocab ? c.vocab - 1 : id);
       m_pos[t + i] = i;
-      m_slot[t + i] = s;
     }
     for (int i = 0; i < len; i += kEncTileRows) {
       int* tl = m_tiles + 4 * n_tiles++;
@@ -182,7 +166,7 @@ int enc_pass(mq_encoder* e, const std::vector<const std::vector<int32_t>*>& seqs
     t += len;
   }
   ENC_TRY(cudaMemcpyAsync(e->d_meta, e->h_meta, e->meta_ints * 4, cudaMemcpyHostToDevice, e->stream));
-  const int *d_tok = e->d_meta, *d_pos = d_tok + e->MT, *d_slot = d_pos + e->MT, *d_first = d_slot + e->MT;
+  const int *d_tok = e->d_meta, *d_pos = d_tok + e->MT, *d_first = d_pos + e->MT;
   const int* d_len = d_first + e->max_seqs;
   const int4* d_tiles = reinterpret_cast<const int4*>(d_len + e->max_seqs);
   static_assert(sizeof(int4) == 16, "tiles are 4 ints");
@@ -192,19 +176,15 @@ int enc_pass(mq_encoder* e, const std::vector<const std::vector<int32_t>*>& seqs
   for (int l = 0; l < c.n_layers; ++l) {
     const EncLayer& w = e->layers[l];
     GemmPlan g;
-    if (!gemm_plan(&g, w.wqkv, 3 * H, 3 * H, H, e->x, e->MT, T, EPI_BF16, e->qkv, 3 * H, 1, 0, 0)) return MQ_ERR_CUDA;
+    if (!gemm_plan(&g, w.wqkv, 3 * H, 3 * H, H, e->x, e->MT, T, EPI_BIAS_BF16, e->qkv, 3 * H, 1, 0, 0)) return MQ_ERR_CUDA;
+    g.p.bias = w.bqkv;
     if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;
-    RopeKvParams rp = {};
-    rp.qkv = e->qkv; rp.qkv_is_f32 = false; rp.n_planes = 1; rp.plane_stride = 0; rp.bias = w.bqkv;
-    rp.pos = d_pos; rp.slot_of_tok = d_slot; rp.block_table = e->d_block_table; rp.max_pages = e->pages_per_seq;
-    rp.inv_freq = e->inv_freq_zero; rp.q_out = e->q; rp.k_cache = e->k_cache; rp.v_cache = e->v_cache;
-    rp.T = T; rp.n_q = c.n_heads; rp.n_kv = c.n_heads; rp.head_dim = c.head_dim;
-    rp.pf = L2Prefetch{nullptr, 0}; rp.tr = Trace{nullptr, 0};
-    launch_rope_kv(lc, rp);
     AttnParams ap = {};
     ap.head_dim = c.head_dim; ap.bidirectional = 1; ap.seq_len = d_len;
-    ap.q = e->q; ap.k_cache = e->k_cache; ap.v_cache = e->v_cache; ap.block_table = e->d_block_table;
-    ap.max_pages = e->pages_per_seq; ap.tiles = d_tiles; ap.out = e->attn; ap.n_q = c.n_heads; ap.n_kv = c.n_heads;
+    ap.seq_start = d_first; ap.row_stride = 3 * H;          // packed mode: q | k | v column blocks of e->qkv
+    ap.q = e->qkv; ap.k_cache = e->qkv + H; ap.v_cache = e->qkv + 2 * H;
+    ap.block_table = e->d_meta; ap.max_pages = 0;            // unused in packed mode
+    ap.tiles = d_tiles; ap.out = e->attn; ap.n_q = c.n_heads; ap.n_kv = c.n_heads;
     ap.T = T; ap.n_splits = 1; ap.n_warps = 1;
     ap.scale_log2 = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
     launch_attn_prefill(lc, ap, n_tiles);
@@ -217,7 +197,7 @@ int enc_pass(mq_encoder* e, const std::vector<const std::vector<int32_t>*>& seqs
     if (!gemm_plan(&g, w.w_down, H, H, I, e->act, e->MT, T, EPI_BF16, e->sub, H, 1, 0, 0)) return MQ_ERR_CUDA;
     if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;
     launch_enc_add_ln(lc, e->h, e->sub, w.b_down, w.mlp_ln_g, w.mlp_ln_b, e->x, T, H, c.ln_eps);
-    nl += 8;
+    nl += 7;
   }
   launch_enc_pool(lc, e->h, d_first, e->d_out, n, H);
   ++nl;
@@ -345,8 +325,7 @@ void mq_encoder_close(mq_encoder* e) {
   if (e->thr.joinable()) e->thr.join();
   cudaSetDevice(e->gpu);
   for (auto& kv : e->tensors) cudaFree(kv.second.ptr);
-  void* bufs[] = {e->h, e->d_out, e->inv_freq_zero, e->x, e->qkv, e->q, e->attn, e->sub, e->act, e->k_cache, e->v_cache,
-                  e->d_meta, e->d_block_table};
+  void* bufs[] = {e->h, e->d_out, e->x, e->qkv, e->attn, e->sub, e->act, e->d_meta};
   for (void* b : bufs) if (b) cudaFree(b);
   if (e->h_meta) cudaFreeHost(e->h_meta);
   if (e->h_out) cudaFreeHost(e->h_out);

@@ -170,6 +170,7 @@ cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
     case EPI_BF16: return launch_bn<EPI_BF16>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
     case EPI_SILU_BF16: return launch_bn<EPI_SILU_BF16>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
     case EPI_GELU_BF16: return launch_bn<EPI_GELU_BF16>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
+    case EPI_BIAS_BF16: return launch_bn<EPI_BIAS_BF16>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -201,6 +202,7 @@ void gemm_set_attrs() {
   set_attrs_epi<EPI_BF16>();
   set_attrs_epi<EPI_SILU_BF16>();
   set_attrs_epi<EPI_GELU_BF16>();
+  set_attrs_epi<EPI_BIAS_BF16>();
   set_attrs_sk<16, EPI_F32>(); set_attrs_sk<32, EPI_F32>(); set_attrs_sk<64, EPI_F32>();
   set_attrs_sk<16, EPI_BF16>(); set_attrs_sk<32, EPI_BF16>(); set_attrs_sk<64, EPI_BF16>();
   set_attrs_sk<16, EPI_SILU_BF16>(); set_attrs_sk<32, EPI_SILU_BF16>(); set_attrs_sk<64, EPI_SILU_BF16>();
@@ -315,7 +317,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
                const StreamKWorkspace* sk) {
   if (K % kBlockK != 0) return false;
   const int kb = K / kBlockK;
-  g->streamk = sk != nullptr && sk->ws != nullptr && T <= 64 && epi != EPI_GELU_BF16 && streamk_pick((n_out + kBlockM - 1) / kBlockM, sk);
+  g->streamk = sk != nullptr && sk->ws != nullptr && T <= 64 && epi != EPI_GELU_BF16 && epi != EPI_BIAS_BF16 && streamk_pick((n_out + kBlockM - 1) / kBlockM, sk);
   if (g->streamk) splits = 1;  // the kernel finishes shared tiles itself: one complete plane
   if (splits < 1) return false;
   const int kbps = (kb + splits - 1) / splits;  // uneven split-K: the last plane may get fewer k-blocks
@@ -346,7 +348,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   if (gm > g->p.m_tiles) gm = g->p.m_tiles;
   g->p.group_m = g->p.n_tiles == 1 ? g->p.m_tiles : gm;
   g->p.w_policy = g->p.n_tiles == 1 ? kEvictFirst : kEvictNormal;  // decode streams weights exactly once
-  g->twocta = !g->streamk && g->bn == 256 && splits == 1 && n_out % 256 == 0 && epi != EPI_GELU_BF16 && twocta_enabled();
+  g->twocta = !g->streamk && g->bn == 256 && splits == 1 && n_out % 256 == 0 && epi != EPI_GELU_BF16 && epi != EPI_BIAS_BF16 && twocta_enabled();
   if (g->twocta) {
     // the pair computes 256 features x 256 tokens: every CTA stages only its own 128-token half of the activation tile
     if (!tmap_encode_2d(&g->tmB, X, (uint64_t)x_rows_alloc, (uint64_t)K, 128)) return false;
@@ -359,7 +361,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
     g->c2.w_policy = g->p.w_policy;
   }
   g->persist = false;
-  if (!g->twocta && !g->streamk && epi != EPI_SILU_BF16 && epi != EPI_GELU_BF16 && g->bn >= 128 && splits == 1 && persist_enabled()) {
+  if (!g->twocta && !g->streamk && epi != EPI_SILU_BF16 && epi != EPI_GELU_BF16 && epi != EPI_BIAS_BF16 && g->bn >= 128 && splits == 1 && persist_enabled()) {
     const int sms = device_sm_count();
     const int tiles = g->p.m_tiles * g->p.n_tiles;
     if (tiles >= 2 * sms) {  // at least two tiles per CTA, otherwise there is nothing to overlap

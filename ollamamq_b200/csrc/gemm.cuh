@@ -25,7 +25,8 @@ enum GemmEpilogue : int {
   EPI_F32 = 0,       // out_f32[z][t][f] = acc                       (split-K partial planes)
   EPI_BF16 = 1,      // out_bf16[t][f]   = acc
   EPI_SILU_BF16 = 2, // out_bf16[t][f]   = silu(acc_gate) * acc_up   (two A tiles: rows f and f + a2_row_off)
-  EPI_GELU_BF16 = 3  // out_bf16[t][f]   = gelu_erf(acc + bias[f])   (BERT intermediate; plain 1-CTA kernel only)
+  EPI_GELU_BF16 = 3, // out_bf16[t][f]   = gelu_erf(acc + bias[f])   (BERT intermediate; plain 1-CTA kernel only)
+  EPI_BIAS_BF16 = 4  // out_bf16[t][f]   = acc + bias[f]             (encoder QKV; plain 1-CTA kernel only)
 };
 
 struct GemmParams {
@@ -52,7 +53,7 @@ struct GemmParams {
   int norm_planes, norm_H, norm_ctas;
   float norm_eps;
   Trace tr;                      // optional timeline stamps (MQ_TRACE=1)
-  const void* bias;              // EPI_GELU_BF16: bf16 [n_out] (nullable)
+  const void* bias;              // EPI_GELU_BF16 / EPI_BIAS_BF16: bf16 [n_out] (nullable)
 };
 
 constexpr int kGemmThreads = 192;
@@ -274,14 +275,15 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float* o = reinterpret_cast<float*>(stg) + c0 * kBlockM + row;
 #pragma unroll
           for (int j = 0; j < 16; ++j) o[j * kBlockM] = __uint_as_float(v[j]);
-        } else if constexpr (EPI == EPI_GELU_BF16) {
+        } else if constexpr (EPI == EPI_GELU_BF16 || EPI == EPI_BIAS_BF16) {
           const int f = m0 + row;  // this thread's output feature
           const float b = (p.bias && f < p.n_out) ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[f]) : 0.f;
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(stg) + c0 * kBlockM + row;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float a = __uint_as_float(v[j]) + b;
-            o[j * kBlockM] = __float2bfloat16(0.5f * a * (1.0f + erff(a * 0.70710678118654752f)));
+            if constexpr (EPI == EPI_GELU_BF16) o[j * kBlockM] = __float2bfloat16(0.5f * a * (1.0f + erff(a * 0.70710678118654752f)));
+            else o[j * kBlockM] = __float2bfloat16(a);
           }
         } else {
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(stg) + c0 * kBlockM + row;

@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
     kv_end = min(kv_end, kv_begin + chunk);
   }
   const int* btab = p.block_table + (size_t)slot * p.max_pages;
+  const int seq0 = p.seq_start ? p.seq_start[slot] : 0;
   const int n_tiles = kv_begin < kv_end ? (kv_end - kv_begin + TN - 1) / TN : 0;
 
   float o[D / 8][4];
@@ -376,7 +377,8 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
       const bool ok = r < n_rows;
       const int rr = ok ? r : 0;
       const int tok = tok0 + rr / G, head = kvh * G + rr % G;
-      cp_async16(Qs + tile_off(r, ch), p.q + ((size_t)tok * p.n_q + head) * D + ch * 8, ok ? 16 : 0);
+      const size_t qrow = p.seq_start ? (size_t)tok * p.row_stride : (size_t)tok * p.n_q * D;
+      cp_async16(Qs + tile_off(r, ch), p.q + qrow + head * D + ch * 8, ok ? 16 : 0);
     }
     auto load_kv = [&](int stage, int t0) {
       uint8_t* kst = Ks + stage * TN * P * 2;
@@ -386,8 +388,13 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
         const int kvpos = t0 + j;
         const bool ok = kvpos < kv_end;
         const int pp = ok ? kvpos : kv_end - 1;
-        const int page = btab[pp / kPageSize];
-        const size_t off = (((size_t)page * p.n_kv + kvh) * kPageSize + pp % kPageSize) * D + ch * 8;
+        size_t off;
+        if (p.seq_start) {
+          off = (size_t)(seq0 + pp) * p.row_stride + kvh * D + ch * 8;
+        } else {
+          const int page = btab[pp / kPageSize];
+          off = (((size_t)page * p.n_kv + kvh) * kPageSize + pp % kPageSize) * D + ch * 8;
+        }
         cp_async16(kst + tile_off(j, ch), p.k_cache + off, ok ? 16 : 0);
         cp_async16(vst + tile_off(j, ch), p.v_cache + off, ok ? 16 : 0);
       }

@@ -64,6 +64,10 @@ struct AttnParams {
   int head_dim;        // 128, 96 or 64 (32: encoder)
   int bidirectional;   // prefill only: 1 = no causal mask (encoder self-attention); needs seq_len
   const int* seq_len;  // prefill, bidirectional: [slots] total length of each sequence
+  // prefill, packed mode (encoder): q / k / v are column blocks of ONE row-major activation matrix instead of a paged
+  // cache - row (seq_start[slot] + position), `row_stride` elements apart; q, k_cache, v_cache point at the blocks
+  const int* seq_start;  // [slots] first row of each sequence; nullptr = paged cache
+  int row_stride;
   int n_splits;        // decode only: every sequence is cut into n_splits equal 16-aligned ranges (grid-level)
   int n_warps;         // decode only: 1, or 2 / 4 / 8 = in-CTA split over that many warps (then n_splits == 1)
   int* split_counter;  // decode only: [slots][n_kv] arrival counters (zero between launches)
