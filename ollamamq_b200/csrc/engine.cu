@@ -128,6 +128,11 @@ static int worker_alloc(mq_worker* w) {
     const char* e2 = getenv("MQ_L2_PREFETCH");
     w->l2_prefetch = e2 && e2[0] == '1';
     // MQ_TRACE=1: per-launch %globaltimer stamps of the most recent pass (tools/decode_timeline.py)
+    // MQ_FUSE_ROPE=1: decode attention does the QKV split-K reduce + RoPE + KV append itself (one launch less per
+    // layer).  Measured on B200 (r01 timeline, same GPU): 64 slots 29.8 us vs 2.8 + 25.2 us separate, 8 slots
+    // 7.9 vs 2.4 + 5.6 - the three plane round trips land on every warp's critical path, so it is opt-in.
+    const char* e4 = getenv("MQ_FUSE_ROPE");
+    w->fuse_rope = e4 && e4[0] == '1';
     const char* e3 = getenv("MQ_TRACE");
     if (e3 && e3[0] == '1') {
       if (8 * c.n_layers + 1 > kTraceSlots - 2) {
@@ -178,6 +183,13 @@ static int worker_alloc(mq_worker* w) {
   for (int i = 0; i < D / 2; ++i)  // HF: 1.0 / (base ** (arange(0, dim, 2).float() / dim)), fp32
     invf[i] = 1.0f / powf(c.rope_theta, (float)(2 * i) / (float)D);
   CUDA_TRY(cudaMemcpyAsync(w->inv_freq, invf.data(), D / 2 * 4, cudaMemcpyHostToDevice, w->stream));
+  // (cos, sin) of every (position, frequency): computed once by the GPU's own sincosf so the rope kernel and the fused
+  // decode attention read exactly the values the table-less kernel would compute
+  {
+    const size_t n_pos = (size_t)w->max_pages * kPageSize;
+    if ((rc = dalloc(&w->rope_table, n_pos * (D / 2)))) return rc;
+    launch_rope_table(w->stream, w->rope_table, w->inv_freq, (int)n_pos, D / 2);
+  }
   CUDA_TRY(cudaStreamSynchronize(w->stream));
 
   if (streamk_enabled() && streamk_workspace_alloc(&w->sk_ws) != 0) {
@@ -295,24 +307,26 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
     const L2Prefetch pf_rope = pf_none;                                                              // KV stream follows: too early
     const L2Prefetch pf_attn = pfon ? L2Prefetch{lw.wo, b_o} : pf_none;                              // tail of attention -> O GEMM
     const L2Prefetch pf_norm2 = pfon ? L2Prefetch{lw.w_gate_up, std::min(b_gu, (size_t)64 << 20)} : pf_none;  // -> gate/up GEMM
-    auto tr = [&]() { return Trace{w->d_trace, (int)nl}; };  // timeline slot of the launch about to be issued
-    auto tr_gemm = [&](GemmPlan& g) { g.p.tr = tr(); g.sk.tr = tr(); };
+    // timeline slots: 1 + 8 * layer + {0 norm1, 1 qkv, 2 rope, 3 attention, 4 o, 5 norm2, 6 gate/up, 7 down}
+    auto tr = [&](int k) { return Trace{w->d_trace, 1 + 8 * l + k}; };
+    auto tr_gemm = [&](GemmPlan& g, int k) { g.p.tr = tr(k); g.sk.tr = tr(k); };
     if (!fused) {
       launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, prev_planes, (long long)MBp * H, lw.attn_norm, w->x, nullptr, a.T,
-                         H, c.rms_eps, pf_norm1, tr()); ++nl;
+                         H, c.rms_eps, pf_norm1, tr(0)); ++nl;
     }
-    tr_gemm(pp->qkv[l]);
+    tr_gemm(pp->qkv[l], 1);
     if (gemm_launch(pp->qkv[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
+    const bool fuse_rope = a.decode && w->fuse_rope;  // decode: the attention kernel reduces / rotates / appends itself
     RopeKvParams rp;
     rp.qkv = w->qkv_part; rp.qkv_is_f32 = f32p; rp.n_planes = pp->s_qkv; rp.plane_stride = (long long)MBp * w->qkv_dim;
     rp.bias = lw.bqkv; rp.pos = a.pos; rp.slot_of_tok = a.slot_of_tok; rp.block_table = w->d_block_table;
-    rp.max_pages = w->max_pages; rp.inv_freq = w->inv_freq; rp.q_out = w->q;
+    rp.max_pages = w->max_pages; rp.inv_freq = w->inv_freq; rp.rope_table = w->rope_table; rp.q_out = w->q;
     rp.k_cache = w->k_cache + (size_t)l * w->cache_layer_stride;
     rp.v_cache = w->v_cache + (size_t)l * w->cache_layer_stride;
     rp.T = a.T; rp.n_q = c.n_q_heads; rp.n_kv = c.n_kv_heads; rp.head_dim = c.head_dim;
     rp.pf = pf_rope;
-    rp.tr = tr();
-    launch_rope_kv(lc, rp); ++nl;
+    rp.tr = tr(2);
+    if (!fuse_rope) { launch_rope_kv(lc, rp); ++nl; }
     AttnParams ap = {};
     ap.head_dim = c.head_dim;
     ap.q = w->q; ap.k_cache = rp.k_cache; ap.v_cache = rp.v_cache; ap.block_table = w->d_block_table;
@@ -320,19 +334,24 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
     ap.part_ml = w->part_ml; ap.n_q = c.n_q_heads; ap.n_kv = c.n_kv_heads; ap.T = a.T;
     ap.n_splits = a.n_splits < 0 ? 1 : a.n_splits; ap.n_warps = a.n_splits < 0 ? -a.n_splits : 1;
     ap.pf = pf_attn;
-    ap.tr = tr();
+    ap.tr = tr(3);
+    if (fuse_rope) {
+      ap.qkv_planes = reinterpret_cast<const float*>(w->qkv_part); ap.qkv_n_planes = pp->s_qkv;
+      ap.qkv_plane_stride = (long long)MBp * w->qkv_dim; ap.qkv_dim = w->qkv_dim; ap.qkv_bias = lw.bqkv;
+      ap.rope_table = w->rope_table; ap.k_new = rp.k_cache; ap.v_new = rp.v_cache;
+    }
     ap.split_counter = w->d_split_counter; ap.scale_log2 = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
     if (a.decode) { launch_attn_decode(lc, ap, a.T); ++nl; }
     else { launch_attn_prefill(lc, ap, a.n_tiles); ++nl; }
-    tr_gemm(pp->o[l]);
+    tr_gemm(pp->o[l], 4);
     if (gemm_launch(pp->o[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     if (!fused) {
       launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, pp->s_o, (long long)MBp * H, lw.mlp_norm, w->x, nullptr, a.T, H,
-                         c.rms_eps, pf_norm2, tr()); ++nl;
+                         c.rms_eps, pf_norm2, tr(5)); ++nl;
     }
-    tr_gemm(pp->gate_up[l]);
+    tr_gemm(pp->gate_up[l], 6);
     if (gemm_launch(pp->gate_up[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
-    tr_gemm(pp->down[l]);
+    tr_gemm(pp->down[l], 7);
     if (gemm_launch(pp->down[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     prev_planes = pp->s_down;
   }
@@ -663,7 +682,7 @@ static int launch_decode(mq_worker* w) {
     // graph wrote to the fixed row kRing-1; move it to this step's ring slot on the host side copy
     cudaMemcpyAsync(w->h_out_ring + (size_t)ring * MBp, w->d_out_ring + (size_t)(kRing - 1) * MBp, Bcap * 4,
                     cudaMemcpyDeviceToHost, w->stream);
-    nl = (uint64_t)(1 + w->cfg.n_layers * (get_plans(w, Bcap, true)->fused_norm ? 6 : 8) + 3);
+    nl = (uint64_t)(1 + w->cfg.n_layers * ((get_plans(w, Bcap, true)->fused_norm ? 6 : 8) - (w->fuse_rope ? 1 : 0)) + 3);
   } else {
     int rc = decode_body(w, Bcap, n_splits, ring, &nl);
     if (rc) return rc;

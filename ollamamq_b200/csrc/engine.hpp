@@ -86,6 +86,7 @@ struct mq_worker {
   __nv_bfloat16 *x = nullptr, *q = nullptr, *attn = nullptr, *act = nullptr, *x_last = nullptr;
   void *qkv_part = nullptr, *proj_part = nullptr;
   float *logits = nullptr, *part_o = nullptr, *part_ml = nullptr, *inv_freq = nullptr;
+  float2* rope_table = nullptr;  // [max_seq][head_dim / 2] (cos, sin)
   // metadata (device)
   int *d_tok = nullptr, *d_pos_tok = nullptr, *d_slot_tok = nullptr, *d_last_idx = nullptr, *d_dst_slot = nullptr;
   int4* d_tiles = nullptr;
@@ -94,6 +95,7 @@ struct mq_worker {
   int* d_split_counter = nullptr;  // [MB][n_kv] arrival counters of the split-KV decode attention
   int* d_norm_counters = nullptr;  // [2 * layers] arrival counters of the fused norm prologues (zeroed by embed)
   bool fuse_norm = true;
+  bool fuse_rope = false;    // decode: attention kernel does the QKV reduce + RoPE + KV append (MQ_FUSE_ROPE=1; measured no gain)
   unsigned long long* d_trace = nullptr;  // MQ_TRACE=1: [kTraceSlots][4] %globaltimer stamps of the latest pass
   bool l2_prefetch = true;   // decode: small kernels pull the next GEMM's weights into L2 (MQ_L2_PREFETCH=0 disables)
   // pinned host mirrors / staging

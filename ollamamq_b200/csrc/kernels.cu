@@ -236,11 +236,17 @@ __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
   if (live) {
     const int pos = p.pos[t];
     if (hd < p.n_q + p.n_kv) {
-      const float4 fr = *reinterpret_cast<const float4*>(p.inv_freq + i);
-      sincosf((float)pos * fr.x, &sn[0], &cs[0]);
-      sincosf((float)pos * fr.y, &sn[1], &cs[1]);
-      sincosf((float)pos * fr.z, &sn[2], &cs[2]);
-      sincosf((float)pos * fr.w, &sn[3], &cs[3]);
+      if (p.rope_table) {  // (cos, sin) per (position, pair), built once with the sincosf below
+        const float4 t0 = *reinterpret_cast<const float4*>(p.rope_table + (size_t)pos * HALF + i);
+        const float4 t1 = *reinterpret_cast<const float4*>(p.rope_table + (size_t)pos * HALF + i + 2);
+        cs[0] = t0.x; sn[0] = t0.y; cs[1] = t0.z; sn[1] = t0.w; cs[2] = t1.x; sn[2] = t1.y; cs[3] = t1.z; sn[3] = t1.w;
+      } else {
+        const float4 fr = *reinterpret_cast<const float4*>(p.inv_freq + i);
+        sincosf((float)pos * fr.x, &sn[0], &cs[0]);
+        sincosf((float)pos * fr.y, &sn[1], &cs[1]);
+        sincosf((float)pos * fr.z, &sn[2], &cs[2]);
+        sincosf((float)pos * fr.w, &sn[3], &cs[3]);
+      }
     }
     if (p.bias) { add_bias4(bias_a, p.bias + col); add_bias4(bias_b, p.bias + col + HALF); }
     if (hd < p.n_q) {
@@ -268,6 +274,18 @@ __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
   *reinterpret_cast<uint2*>(dst + i) = lo;
   *reinterpret_cast<uint2*>(dst + i + HALF) = hi;
   if (threadIdx.x == 0) trace_end(p.tr);  // thread 0 always owns a live (head, pair) of its CTA
+}
+// table[pos][i] = (cos, sin)(pos * inv_freq[i]) - the very values rope_kv_kernel computes on the fly without a table
+__global__ void rope_table_kernel(float2* __restrict__ table, const float* __restrict__ inv_freq, int n_pos, int half) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_pos * half) return;
+  float s, c;
+  sincosf((float)(idx / half) * inv_freq[idx % half], &s, &c);
+  table[idx] = make_float2(c, s);
+}
+void launch_rope_table(cudaStream_t st, float2* table, const float* inv_freq, int n_pos, int half) {
+  const int n = n_pos * half;
+  rope_table_kernel<<<(n + 255) / 256, 256, 0, st>>>(table, inv_freq, n_pos, half);
 }
 void launch_rope_kv(const LaunchCfg& lc, const RopeKvParams& p) {
   const dim3 grid(p.T, (p.n_q + 2 * p.n_kv + 15) / 16);
@@ -603,6 +621,30 @@ __global__ void __launch_bounds__(32 * NW) decode_attn_kernel(const AttnParams p
         cp_async_commit();
       }
     }
+    // ---- fused RoPE, part 1 (before the dependency wait: needs only the position): the angles of this thread's
+    // q elements.  Thread (g, c) owns elements ks*16 + {2c, 2c+1, 8+2c, 9+2c} of head g; the rotation partner of an
+    // element e < D/2 is e + D/2 = the same offsets KS/2 slices further on, i.e. in this very thread.
+    const bool fused = p.qkv_planes != nullptr;
+    const int new_pos = kv_len - 1;
+    const bool own_tail = fused && kv_begin <= new_pos && new_pos < kv_end;  // this warp's range holds the token appended by this step
+    // (cos, sin) pairs from the per-worker table [position][D / 2] (built once with the same sincosf as the rope kernel)
+    float4 q_rot[KS / 2][2];           // [ks][0] = (cos, sin) of e0, e0 + 1;  [ks][1] = of e0 + 8, e0 + 9
+    float2 k_rot[2] = {make_float2(1.f, 0.f), make_float2(1.f, 0.f)};
+    if (fused) {
+      const float2* tab = p.rope_table + (size_t)new_pos * (D / 2);
+      if (g < G) {
+#pragma unroll
+        for (int ks = 0; ks < KS / 2; ++ks) {
+          q_rot[ks][0] = *reinterpret_cast<const float4*>(tab + ks * 16 + 2 * c);
+          q_rot[ks][1] = *reinterpret_cast<const float4*>(tab + ks * 16 + 8 + 2 * c);
+        }
+      }
+      if (own_tail) {  // the new k row: this lane rotates pairs lane and lane + 32 (where < D/2)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          if (lane + 32 * j < D / 2) k_rot[j] = tab[lane + 32 * j];
+      }
+    }
     pdl_wait();
     if (threadIdx.x == 0) trace_waited(p.tr);
     if (!early) {
@@ -612,15 +654,97 @@ __global__ void __launch_bounds__(32 * NW) decode_attn_kernel(const AttnParams p
         cp_async_commit();
       }
     }
-    // Q fragments straight from global memory: row g = head g of the group (zero for g >= G), rows 8..15 zero
+    // Q fragments: row g = head g of the group (zero for g >= G), rows 8..15 zero
     uint32_t qf[KS][2];
-    {
+    __nv_bfloat16 k_row[4], v_row[4];  // fused: this lane's share of the appended k / v row (own_tail only)
+    if (!fused) {  // q written by rope_kv_kernel
       const bool ok = g < G;
       const __nv_bfloat16* qp = p.q + ((size_t)slot * p.n_q + kvh * G + (ok ? g : 0)) * D + 2 * c;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         qf[ks][0] = ok ? *reinterpret_cast<const uint32_t*>(qp + ks * 16) : 0u;
         qf[ks][1] = ok ? *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 8) : 0u;
+      }
+    } else {
+      // ---- fused RoPE, part 2: sum the split-K planes (+ bias), rotate, keep q in registers.  The plane loop is the
+      // OUTER loop and everything inside is unrolled, so each plane costs one round trip of independent loads
+      // (a per-element plane loop was 48 dependent L2 round trips: +28 us per layer).
+      const float* row = p.qkv_planes + (size_t)slot * p.qkv_dim;
+      if (g < G) {
+        const int qcol = (kvh * G + g) * D + 2 * c;
+        float2 x[KS / 2][2], y[KS / 2][2];
+#pragma unroll
+        for (int ks = 0; ks < KS / 2; ++ks) x[ks][0] = x[ks][1] = y[ks][0] = y[ks][1] = make_float2(0.f, 0.f);
+        for (int s2 = 0; s2 < p.qkv_n_planes; ++s2) {
+          const float* r2 = row + s2 * p.qkv_plane_stride + qcol;
+#pragma unroll
+          for (int ks = 0; ks < KS / 2; ++ks) {
+            const float2 a0 = *reinterpret_cast<const float2*>(r2 + ks * 16), a1 = *reinterpret_cast<const float2*>(r2 + ks * 16 + 8);
+            const float2 b0 = *reinterpret_cast<const float2*>(r2 + ks * 16 + D / 2), b1 = *reinterpret_cast<const float2*>(r2 + ks * 16 + 8 + D / 2);
+            x[ks][0].x += a0.x; x[ks][0].y += a0.y; x[ks][1].x += a1.x; x[ks][1].y += a1.y;
+            y[ks][0].x += b0.x; y[ks][0].y += b0.y; y[ks][1].x += b1.x; y[ks][1].y += b1.y;
+          }
+        }
+        if (p.qkv_bias) {
+          const __nv_bfloat16* bq = p.qkv_bias + qcol;
+#pragma unroll
+          for (int ks = 0; ks < KS / 2; ++ks) {
+            x[ks][0].x += __bfloat162float(bq[ks * 16]); x[ks][0].y += __bfloat162float(bq[ks * 16 + 1]);
+            x[ks][1].x += __bfloat162float(bq[ks * 16 + 8]); x[ks][1].y += __bfloat162float(bq[ks * 16 + 9]);
+            y[ks][0].x += __bfloat162float(bq[ks * 16 + D / 2]); y[ks][0].y += __bfloat162float(bq[ks * 16 + D / 2 + 1]);
+            y[ks][1].x += __bfloat162float(bq[ks * 16 + D / 2 + 8]); y[ks][1].y += __bfloat162float(bq[ks * 16 + D / 2 + 9]);
+          }
+        }
+#pragma unroll
+        for (int ks = 0; ks < KS / 2; ++ks) {
+          const float4 r0 = q_rot[ks][0], r1 = q_rot[ks][1];  // (cos, sin, cos', sin')
+          qf[ks][0] = pack_bf16(x[ks][0].x * r0.x - y[ks][0].x * r0.y, x[ks][0].y * r0.z - y[ks][0].y * r0.w);
+          qf[ks][1] = pack_bf16(x[ks][1].x * r1.x - y[ks][1].x * r1.y, x[ks][1].y * r1.z - y[ks][1].y * r1.w);
+          qf[ks + KS / 2][0] = pack_bf16(y[ks][0].x * r0.x + x[ks][0].x * r0.y, y[ks][0].y * r0.z + x[ks][0].y * r0.w);
+          qf[ks + KS / 2][1] = pack_bf16(y[ks][1].x * r1.x + x[ks][1].x * r1.y, y[ks][1].y * r1.z + x[ks][1].y * r1.w);
+        }
+      } else {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) qf[ks][0] = qf[ks][1] = 0u;
+      }
+      if (own_tail) {
+        // the appended row: k rotated (pairs lane, lane + 32), v copied (elements 4*lane .. +3); written to the cache
+        // for the steps to come and injected into the last tile of THIS step further down
+        const int kcol = (p.n_q + kvh) * D, vcol = (p.n_q + p.n_kv + kvh) * D + lane * 4;
+        const bool k0 = lane < D / 2, k1 = lane + 32 < D / 2, vv = lane * 4 < D;
+        float kx[2] = {0.f, 0.f}, ky[2] = {0.f, 0.f};
+        float4 va = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s2 = 0; s2 < p.qkv_n_planes; ++s2) {
+          const float* r2 = row + s2 * p.qkv_plane_stride;
+          if (k0) { kx[0] += r2[kcol + lane]; ky[0] += r2[kcol + lane + D / 2]; }
+          if (k1) { kx[1] += r2[kcol + lane + 32]; ky[1] += r2[kcol + lane + 32 + D / 2]; }
+          if (vv) { const float4 t4 = *reinterpret_cast<const float4*>(r2 + vcol); va.x += t4.x; va.y += t4.y; va.z += t4.z; va.w += t4.w; }
+        }
+        if (p.qkv_bias) {
+          if (k0) { kx[0] += __bfloat162float(p.qkv_bias[kcol + lane]); ky[0] += __bfloat162float(p.qkv_bias[kcol + lane + D / 2]); }
+          if (k1) { kx[1] += __bfloat162float(p.qkv_bias[kcol + lane + 32]); ky[1] += __bfloat162float(p.qkv_bias[kcol + lane + 32 + D / 2]); }
+          if (vv) {
+            va.x += __bfloat162float(p.qkv_bias[vcol]); va.y += __bfloat162float(p.qkv_bias[vcol + 1]);
+            va.z += __bfloat162float(p.qkv_bias[vcol + 2]); va.w += __bfloat162float(p.qkv_bias[vcol + 3]);
+          }
+        }
+        const int page = btab[new_pos / kPageSize];
+        const size_t cbase = (((size_t)page * p.n_kv + kvh) * kPageSize + new_pos % kPageSize) * D;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int i = lane + 32 * j;
+          if (i < D / 2) {
+            k_row[2 * j] = __float2bfloat16(kx[j] * k_rot[j].x - ky[j] * k_rot[j].y);
+            k_row[2 * j + 1] = __float2bfloat16(ky[j] * k_rot[j].x + kx[j] * k_rot[j].y);
+            p.k_new[cbase + i] = k_row[2 * j];
+            p.k_new[cbase + i + D / 2] = k_row[2 * j + 1];
+          }
+        }
+        if (vv) {
+          v_row[0] = __float2bfloat16(va.x); v_row[1] = __float2bfloat16(va.y);
+          v_row[2] = __float2bfloat16(va.z); v_row[3] = __float2bfloat16(va.w);
+          *reinterpret_cast<uint2*>(p.v_new + cbase + lane * 4) = make_uint2(pack_bf16(va.x, va.y), pack_bf16(va.z, va.w));
+        }
       }
     }
     for (int it = 0; it < n_tiles; ++it) {
@@ -629,6 +753,27 @@ __global__ void __launch_bounds__(32 * NW) decode_attn_kernel(const AttnParams p
       cp_async_commit();
       cp_async_wait<STAGES - 1>();
       __syncwarp();
+      if (own_tail && it == n_tiles - 1) {
+        // fused RoPE, part 3: the page just fetched holds a stale row where this step's token belongs
+        uint8_t* kt = Ks + (it % STAGES) * TN * P * 2;
+        uint8_t* vt = Vs + (it % STAGES) * TN * P * 2;
+        const int r = new_pos - t0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int i = lane + 32 * j;
+          if (i < D / 2) {
+            *reinterpret_cast<__nv_bfloat16*>(kt + tile_off(r, i >> 3) + (i & 7) * 2) = k_row[2 * j];
+            const int i2 = i + D / 2;
+            *reinterpret_cast<__nv_bfloat16*>(kt + tile_off(r, i2 >> 3) + (i2 & 7) * 2) = k_row[2 * j + 1];
+          }
+        }
+        if (lane * 4 < D) {
+          const int i = lane * 4;
+          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(vt + tile_off(r, i >> 3) + (i & 7) * 2);
+          dst[0] = v_row[0]; dst[1] = v_row[1]; dst[2] = v_row[2]; dst[3] = v_row[3];
+        }
+        __syncwarp();
+      }
       const uint32_t kbase = smem_u32(Ks + (it % STAGES) * TN * P * 2);
       const uint32_t vbase = smem_u32(Vs + (it % STAGES) * TN * P * 2);
       // ---- S = Q K^T for the 16 tokens of this page

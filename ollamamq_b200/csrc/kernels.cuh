@@ -39,6 +39,7 @@ struct RopeKvParams {
   const int* block_table;     // [slots][max_pages]
   int max_pages;
   const float* inv_freq;      // [d/2]
+  const float2* rope_table;   // optional [positions][d/2] (cos, sin) of pos * inv_freq: replaces the in-kernel sincosf
   __nv_bfloat16* q_out;       // [T][n_q*d]
   __nv_bfloat16* k_cache;     // layer base: [pages][n_kv][kPageSize][d]
   __nv_bfloat16* v_cache;
@@ -48,6 +49,7 @@ struct RopeKvParams {
   Trace tr;                   // optional timeline stamps (MQ_TRACE=1)
 };
 void launch_rope_kv(const LaunchCfg& lc, const RopeKvParams& p);
+void launch_rope_table(cudaStream_t st, float2* table, const float* inv_freq, int n_pos, int half);
 
 struct AttnParams {
   const __nv_bfloat16* q;        // [T][n_q*d]
@@ -72,6 +74,15 @@ struct AttnParams {
   int n_warps;         // decode only: 1, or 2 / 4 / 8 = in-CTA split over that many warps (then n_splits == 1)
   int* split_counter;  // decode only: [slots][n_kv] arrival counters (zero between launches)
   float scale_log2;    // softmax scale * log2(e)
+  // decode, fused RoPE (qkv_planes != nullptr): the kernel itself sums the QKV GEMM's split-K planes (+ bias), rotates
+  // q and the new k, appends k / v of position pos[slot] to the paged cache and uses them - no rope_kv launch, no q buffer
+  const float* qkv_planes;        // [n_planes][plane_stride], row = slot, qkv_dim columns (q heads | k heads | v heads)
+  int qkv_n_planes, qkv_dim;
+  long long qkv_plane_stride;
+  const __nv_bfloat16* qkv_bias;  // nullable [qkv_dim]
+  const float2* rope_table;       // [positions][head_dim / 2] (cos, sin)
+  __nv_bfloat16* k_new;           // writable aliases of k_cache / v_cache
+  __nv_bfloat16* v_new;
   L2Prefetch pf;       // optional: weights of an upcoming GEMM to pull into L2 (decode)
   Trace tr;            // optional timeline stamps (MQ_TRACE=1)
 };

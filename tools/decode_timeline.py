@@ -75,6 +75,8 @@ print("\n# steady state (layers 1..%d), means in us" % (L - 1))
 print("# kernel      span(start->last_end)  busy(waited->last_end)  exposed(critical path)  lead-in  wait-after-prev-end  tail(first->last CTA end)")
 tot = 0.0
 for nm in names:
+    if nm not in agg:  # e.g. no rope launch when RoPE is fused into the attention kernel
+        continue
     a = np.array(agg[nm])
     m = a.mean(0)
     tot += m[2]
