@@ -109,7 +109,6 @@ struct mq_worker {
   mq::StreamKWorkspace sk_ws;
   std::map<int, mq::PassPlans> plans_decode, plans_prefill;
   std::map<long long, cudaGraphExec_t> graphs;  // key: Bcap * 1024 + n_splits
-  std::vector<mq::GemmPlan> lm_plans_cache_dummy;
   std::map<int, mq::GemmPlan> lm_plans;          // key: rows
 
   // slots / pages

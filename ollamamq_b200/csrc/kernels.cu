@@ -341,7 +341,8 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 constexpr int kTilePitch = 128;  // elements per smem tile row, whatever the head_dim
 __device__ __forceinline__ uint32_t tile_off(int row, int chunk) { return (uint32_t)(row * 16 + (chunk ^ (row & 7))) * 16u; }
 
-template <int NW, int TN, int STAGES, bool DECODE, int D>
+// Prefill / encoder attention: one CTA per (tile of <= NW*16 query rows, kv head).
+template <int NW, int TN, int STAGES, int D>
 __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p) {
   constexpr int P = kTilePitch;  // smem row pitch in elements (256 B for every head_dim: keeps the XOR swizzle valid)
   constexpr int CH = D / 8;      // 16-byte chunks per row that hold data
@@ -360,23 +361,10 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
   const int g = lane >> 2, c = lane & 3;
   const int kvh = blockIdx.y;
   const int G = p.n_q / p.n_kv;
-  int tok0, ntok, slot, pos0;
-  if (DECODE) {
-    slot = blockIdx.x; tok0 = slot; ntok = 1; pos0 = p.pos[slot];
-  } else {
-    const int4 t = p.tiles[blockIdx.x];
-    tok0 = t.x; ntok = t.y; slot = t.z; pos0 = t.w;
-  }
+  const int4 tile = p.tiles[blockIdx.x];
+  const int tok0 = tile.x, ntok = tile.y, slot = tile.z, pos0 = tile.w;
   const int n_rows = ntok * G;
-  int kv_begin = 0, kv_end = p.bidirectional ? p.seq_len[slot] : pos0 + ntok;  // encoder rows see the whole sequence
-  const bool split = DECODE && p.n_splits > 1;
-  if (split) {
-    // every sequence is cut into n_splits equal 16-aligned ranges of ITS OWN length (balanced CTAs, and no
-    // host-side parameter that changes from step to step -> the CUDA graph stays valid as contexts grow)
-    const int chunk = (((kv_end + p.n_splits - 1) / p.n_splits) + 15) & ~15;
-    kv_begin = blockIdx.z * chunk;
-    kv_end = min(kv_end, kv_begin + chunk);
-  }
+  const int kv_begin = 0, kv_end = p.bidirectional ? p.seq_len[slot] : pos0 + ntok;  // encoder rows see the whole sequence
   const int* btab = p.block_table + (size_t)slot * p.max_pages;
   const int seq0 = p.seq_start ? p.seq_start[slot] : 0;
   const int n_tiles = kv_begin < kv_end ? (kv_end - kv_begin + TN - 1) / TN : 0;
@@ -524,17 +512,7 @@ __global__ void __launch_bounds__(NW * 32) paged_attn_kernel(const AttnParams p)
     if (row >= n_rows) continue;
     const int tok = tok0 + row / G, head = kvh * G + row % G;
     const float l = half ? l_b : l_a;
-    if (split) {
-      const size_t base = ((size_t)blockIdx.z * p.T + tok) * p.n_q + head;
-      float* po = p.part_o + base * D;
-#pragma unroll
-      for (int n = 0; n < D / 8; ++n)
-        *reinterpret_cast<float2*>(po + n * 8 + 2 * c) = make_float2(o[n][2 * half], o[n][2 * half + 1]);
-      if (c == 0) {
-        p.part_ml[base * 2] = m_run[half];
-        p.part_ml[base * 2 + 1] = l;
-      }
-    } else {
+    {
       const float inv = l > 0.f ? 1.f / l : 0.f;
       __nv_bfloat16* po = p.out + ((size_t)tok * p.n_q + head) * D;
 #pragma unroll
@@ -971,7 +949,7 @@ constexpr int kDecodeSmem = 2 * kDecodeStages * kPageSize * kTilePitch * 2;
 void attn_set_attrs() {
   auto go = [&](auto dtag) {
     constexpr int D = decltype(dtag)::value;
-    cudaFuncSetAttribute(paged_attn_kernel<kPrefillNW, kPrefillTN, kPrefillStages, false, D>,
+    cudaFuncSetAttribute(paged_attn_kernel<kPrefillNW, kPrefillTN, kPrefillStages, D>,
                          cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem(kPrefillNW, kPrefillTN, kPrefillStages));
     cudaFuncSetAttribute(decode_attn_kernel<2, D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(decode_attn_kernel<3, D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -990,7 +968,7 @@ void attn_set_attrs() {
 void launch_attn_prefill(const LaunchCfg& lc, const AttnParams& p, int n_tiles) {
   dispatch_head_dim(p.head_dim, [&](auto dtag) {
     constexpr int D = decltype(dtag)::value;
-    launch_k(lc, paged_attn_kernel<kPrefillNW, kPrefillTN, kPrefillStages, false, D>, dim3(n_tiles, p.n_kv, 1),
+    launch_k(lc, paged_attn_kernel<kPrefillNW, kPrefillTN, kPrefillStages, D>, dim3(n_tiles, p.n_kv, 1),
              dim3(kPrefillNW * 32), attn_smem(kPrefillNW, kPrefillTN, kPrefillStages), p);
   });
 }
