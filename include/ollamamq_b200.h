@@ -266,6 +266,9 @@ int mq_dispatcher_set_online(mq_dispatcher* d, int32_t backend, int32_t online);
 /* block list persistence: load `path` now (AppState::new, :69,:98-105) and rewrite it on every block / unblock
  * (:107-115).  Format pinned by the reference: pretty JSON {"ips": [...], "users": [...]} (:21-25); the reference
  * uses "blocked_items.json" in the working directory (:19).                                                   */
+/* Whole-request timeout applied to every dispatched request that does not carry its own (the reference builds its
+ * HTTP client with `--timeout` seconds, dispatcher.rs:165-167, main.rs:31-33); 0 = none.                   */
+int mq_dispatcher_set_timeout(mq_dispatcher* d, uint32_t timeout_ms);
 /* Give backend `backend` an embedding worker: MQ_EP_EMBED requests dispatched to that backend go to it (without
  * one they are answered 501 like any unimplemented route).  The dispatcher does not own the encoder.        */
 int mq_dispatcher_attach_encoder(mq_dispatcher* d, int32_t backend, mq_encoder* e);

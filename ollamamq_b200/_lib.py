@@ -168,6 +168,7 @@ _sig("mq_debug_attn_decode", C.c_int, [P, P, P, P, C.c_int, P, P, P, P, P, C.c_i
                                         C.c_float, C.c_int])
 _sig("mq_dispatcher_snapshot_json", C.c_longlong, [P, P, C.c_size_t])
 _sig("mq_dispatcher_attach_encoder", C.c_int, [P, C.c_int32, P])
+_sig("mq_dispatcher_set_timeout", C.c_int, [P, C.c_uint32])
 _sig("mq_encoder_open", C.c_int, [C.c_int32, P, P])
 _sig("mq_encoder_close", None, [P])
 _sig("mq_encoder_load_tensor", C.c_int, [P, C.c_char_p, P, C.c_size_t])

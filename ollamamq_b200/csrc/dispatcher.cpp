@@ -154,6 +154,7 @@ struct mq_dispatcher {
   std::string block_file;           // BLOCKED_FILE = "blocked_items.json" in the reference (:19); empty = no persistence
   std::thread health_thr;
   uint32_t health_period_ms = 0;
+  uint32_t default_timeout_ms = 0;  // --timeout of the reference (main.rs:31-33), 0 = none
   uint64_t outstanding = 0;
   uint64_t wake_seq = 0, handled_seq = 0;
   bool parked = false;
@@ -252,6 +253,7 @@ void run_worker(mq_dispatcher* d) {
     }
     d->sched->s.processing(t->user, +1);  // :283-284
     mq_request rq = t->rq;
+    if (rq.timeout_ms == 0) rq.timeout_ms = d->default_timeout_ms;  // client-wide timeout of the reference (:165-167)
     rq.body = t->body.empty() ? nullptr : t->body.data();
     rq.body_len = t->body.size();
     rq.prompt_tokens = t->tokens.empty() ? nullptr : t->tokens.data();
@@ -364,6 +366,13 @@ int mq_dispatcher_new(mq_worker** workers, int32_t n_workers, int32_t capacity_o
   // reference default: one in-flight request per backend (:204); >1 only when the caller asks for it
   *out = make_dispatcher(std::move(bes), capacity_override > 0 ? capacity_override : 1);
   return *out ? MQ_OK : MQ_ERR_NOMEM;
+}
+
+int mq_dispatcher_set_timeout(mq_dispatcher* d, uint32_t timeout_ms) {
+  if (!d) return MQ_ERR_INVAL;
+  std::lock_guard<std::mutex> g(d->mu);
+  d->default_timeout_ms = timeout_ms;
+  return MQ_OK;
 }
 
 int mq_dispatcher_attach_encoder(mq_dispatcher* d, int32_t backend, mq_encoder* e) {

@@ -314,6 +314,10 @@ class Dispatcher:
     def set_online(self, backend, online):
         check(lib.mq_dispatcher_set_online(self._h, backend, 1 if online else 0))
 
+    def set_timeout(self, seconds: float):
+        """`--timeout` of the reference: whole-request limit for requests without their own."""
+        check(lib.mq_dispatcher_set_timeout(self._h, int(seconds * 1000)))
+
     def attach_encoder(self, backend: int, enc: "Encoder"):
         check(lib.mq_dispatcher_attach_encoder(self._h, backend, enc.handle))
 

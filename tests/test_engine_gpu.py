@@ -416,3 +416,24 @@ def test_full_size_phi3_mini_config4_logits_and_256_user_sse():
                   % (dt, 256 * 32 / dt, st["decode_steps"]))
         finally:
             d.close()
+
+
+def test_dispatcher_wide_timeout_like_the_reference_client_timeout():
+    """`--timeout` of the reference (main.rs:31-33 -> reqwest client timeout, dispatcher.rs:165-167): a whole-request limit
+    for every dispatched request that does not carry its own."""
+    cfg = MID
+    w = R.make_weights(cfg, seed=31, device="cuda")
+    with _open(cfg, w, max_batch=4, max_seq=4096, max_prefill_tokens=256) as wk:
+        d = mq.Dispatcher([wk], capacity=4)
+        try:
+            d.set_timeout(0.05)                       # 50 ms: far less than 3000 decode steps
+            s = d.submit("alice", prompt_tokens=[1, 2, 3], max_new_tokens=3000)
+            s.wait(60)
+            assert s.rc == -110 and 0 < len(s.tokens()) < 3000      # MQ_ERR_TIMEOUT after some tokens were streamed
+            d.set_timeout(0)
+            s = d.submit("alice", prompt_tokens=[1, 2, 3], max_new_tokens=40)
+            s.wait(60)
+            assert s.rc == 0 and len(s.tokens()) == 40
+            assert d.user_stats("alice")["dropped"] >= 1 and d.user_stats("alice")["processed"] == 1
+        finally:
+            d.close()
