@@ -264,6 +264,8 @@ def run_ours(args):
     }
     disp.close()
     wk.close()
+    if rank == 0:
+        line["dispatch"] = dispatch_decisions()
     if rank == 0 and n == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample()
     if rank == 0:
@@ -335,6 +337,17 @@ def _cpu_sample_text(n):
             "value = 128 / (t_prefill + 127 * t_decode_token) from the two MEASURED components, i.e. a linear "
             "extrapolation of the bounded sample to the 128-token requests of the trace; the reference itself "
             "(Rust + Ollama/llama.cpp) cannot be built or installed in this image" % n)
+
+
+def dispatch_decisions():
+    """decisions/s of the C++ scheduler at 64 / 256 users (host CPU, microseconds of work)."""
+    import ctypes as C
+    out = {"unit": "decisions/s", "reqs_per_user": 64}
+    for users in (64, 256):
+        nd, sec = C.c_uint64(), C.c_double()
+        mq.check(mq.lib.mq_debug_sched_bench(users, 64, 1, 1, C.byref(nd), C.byref(sec)))
+        out["users_%d" % users] = nd.value / max(sec.value, 1e-9)
+    return out
 
 
 def cpu_baseline_sample():

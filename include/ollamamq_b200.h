@@ -99,6 +99,10 @@ int32_t mq_sched_user_count(mq_sched* s);
 /* users in TUI order (queued+processing desc, processed+dropped desc, name asc; tui.rs:70-80)           */
 int mq_sched_user_name(mq_sched* s, int32_t index, char* out, size_t cap);
 uint64_t mq_sched_counter(mq_sched* s);
+/* decision micro-benchmark: U users x R requests, unit service time, same driver loop as the
+ * oracle's orc_bench; reports dispatches made and the seconds they took (enqueue excluded)                 */
+int mq_debug_sched_bench(int32_t n_users, int32_t reqs_per_user, int32_t n_backends, int32_t capacity,
+                         uint64_t* dispatches_out, double* seconds_out);
 
 /* =====================================================================================================
  * 2. GPU worker — replaces `client.request(method, backend_url + path).headers(h).body(b).send()` and

@@ -166,6 +166,7 @@ _sig("mq_debug_attn_prefill", C.c_int, [P, P, P, P, C.c_int, P, C.c_int, P, C.c_
                                          C.c_int])
 _sig("mq_debug_attn_decode", C.c_int, [P, P, P, P, C.c_int, P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_float, C.c_int])
+_sig("mq_debug_sched_bench", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, P])
 _sig("mq_dispatcher_snapshot_json", C.c_longlong, [P, P, C.c_size_t])
 _sig("mq_dispatcher_attach_encoder", C.c_int, [P, C.c_int32, P])
 _sig("mq_dispatcher_set_timeout", C.c_int, [P, C.c_uint32])

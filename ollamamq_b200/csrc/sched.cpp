@@ -1,5 +1,7 @@
 // Fair-share scheduler: see sched.hpp for the contract and the reference citations.
 #include "sched.hpp"
+#include <chrono>
+#include <cstdio>
 #include "../../include/ollamamq_b200.h"
 #include <algorithm>
 #include <cstring>
@@ -286,5 +288,36 @@ int mq_sched_user_name(mq_sched* s, int32_t index, char* out, size_t cap) {
   return MQ_OK;
 }
 uint64_t mq_sched_counter(mq_sched* s) { return s ? s->s.counter() : 0; }
+
+// Decision micro-benchmark ("decisions/s of the C++ scheduler at U = 64 / 256"): U users x R requests
+// enqueued user-major, B backends of the given capacity, unit service time, event model of SURVEY.md 3.2 (drain to
+// quiescence, complete the in-flight request on the lowest backend index, repeat) - the same driver loop as
+// oracle/dispatch_oracle.c:orc_bench, so the two dispatch counts must agree.
+int mq_debug_sched_bench(int32_t n_users, int32_t reqs_per_user, int32_t n_backends, int32_t capacity,
+                         uint64_t* dispatches_out, double* seconds_out) {
+  if (n_users < 1 || reqs_per_user < 1 || n_backends < 1 || capacity < 1 || !dispatches_out || !seconds_out) return MQ_ERR_INVAL;
+  mq::Scheduler sc(n_backends, capacity);
+  char name[16];
+  for (int u = 0; u < n_users; ++u) {
+    snprintf(name, sizeof name, "user%03d", u);
+    for (int r = 0; r < reqs_per_user; ++r) sc.enqueue(name);
+  }
+  std::vector<std::pair<int, std::string>> inflight;
+  uint64_t total = 0;
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    mq::SchedDispatch d;
+    while (sc.next(&d)) { inflight.emplace_back(d.backend, d.user); ++total; }
+    if (inflight.empty()) break;
+    size_t best = 0;
+    for (size_t i = 1; i < inflight.size(); ++i) if (inflight[i].first < inflight[best].first) best = i;
+    sc.complete(inflight[best].first, inflight[best].second, 0);
+    inflight[best] = inflight.back();
+    inflight.pop_back();
+  }
+  *seconds_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  *dispatches_out = total;
+  return MQ_OK;
+}
 
 }  // extern "C"
