@@ -342,6 +342,7 @@ def _cpu_sample_text(n):
 def dispatch_decisions():
     """decisions/s of the C++ scheduler at 64 / 256 users (host CPU, microseconds of work)."""
     import ctypes as C
+    import ollamamq_b200 as mq
     out = {"unit": "decisions/s", "reqs_per_user": 64}
     for users in (64, 256):
         nd, sec = C.c_uint64(), C.c_double()
