@@ -29,7 +29,7 @@ def model_cfg(geom: dict, max_batch=64, max_seq=1024, max_prefill_tokens=2048, k
     return c
 
 
-def encoder_cfg(geom: dict, max_seq=512, max_tokens_per_pass=8192, use_pdl=1, model_name="random-init-encoder"):
+def encoder_cfg(geom: dict, max_seq=512, max_tokens_per_pass=32768, use_pdl=1, model_name="random-init-encoder"):
     c = _lib.EncoderCfg()
     for k in ("vocab", "hidden", "ffn", "n_layers", "n_heads", "head_dim", "max_positions"):
         setattr(c, k, int(geom[k]))

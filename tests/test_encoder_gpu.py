@@ -74,7 +74,7 @@ def test_full_size_bge_small_geometry():
     """BASELINE configs[4] geometry at full size (hidden 384, 12 layers, 12 heads of 32, ffn 1536, vocab 30 522):
     weights initialised on the device, read back so the oracle sees the same bf16 values; 512-token inputs."""
     cfg = B.BGE_SMALL
-    with mq.Encoder(0, mq.encoder_cfg(cfg, max_seq=512, max_tokens_per_pass=8192)) as e:
+    with mq.Encoder(0, mq.encoder_cfg(cfg, max_seq=512, max_tokens_per_pass=32768)) as e:
         e.init_random(seed=3, std=0.05)
         w = {}
         for name, shape in B.tensor_shapes(cfg).items():
@@ -97,12 +97,15 @@ def test_full_size_bge_small_geometry():
             _close(got[i], ref[i])
             worst = max(worst, float(np.abs(got[i] - ref[i]).max() / np.abs(ref[i]).max()))
         print("bge-small full size: worst max|d| / max|e| = %.4f over %d sequences" % (worst, len(seqs)))
-        # a config-5 sized slice: 64 x 512 tokens in passes of 8192
-        batch = [rng.integers(0, cfg["vocab"], 512).astype("int32").tolist() for _ in range(64)]
+        # a config-5 sized slice: 80 x 512 tokens = one 32768-token pass (every GEMM large enough for the persistent
+        # double-buffered kernel with the bias / GELU epilogues) + one 8192-token pass (plain kernels)
+        batch = [rng.integers(0, cfg["vocab"], 512).astype("int32").tolist() for _ in range(80)]
+        p0 = e.stats()["passes"]
         out = e.embed(batch)
-        assert out.shape == (64, 384) and np.allclose(np.linalg.norm(out, axis=1), 1.0, atol=1e-3)
-        _close(out[63], B.embed(w, cfg, [batch[63]])[0].cpu().numpy())
-        assert e.stats()["passes"] >= 5
+        assert out.shape == (80, 384) and np.allclose(np.linalg.norm(out, axis=1), 1.0, atol=1e-3)
+        for i in (0, 31, 63, 64, 79):
+            _close(out[i], B.embed(w, cfg, [batch[i]])[0].cpu().numpy())
+        assert e.stats()["passes"] - p0 == 2
 
 
 def test_embed_routes_through_dispatcher_and_http():
