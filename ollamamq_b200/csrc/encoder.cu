@@ -177,7 +177,7 @@ int enc_pass(mq_encoder* e, const std::vector<const std::vector<int32_t>*>& seqs
     const EncLayer& w = e->layers[l];
     GemmPlan g;
     if (!gemm_plan(&g, w.wqkv, 3 * H, 3 * H, H, e->x, e->MT, T, EPI_BIAS_BF16, e->qkv, 3 * H, 1, 0, 0)) return MQ_ERR_CUDA;
-    gemm_plan_set_bias(&g, w.bqkv);
+    g.p.bias = w.bqkv;
     if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;
     AttnParams ap = {};
     ap.head_dim = c.head_dim; ap.bidirectional = 1; ap.seq_len = d_len;
@@ -192,7 +192,7 @@ int enc_pass(mq_encoder* e, const std::vector<const std::vector<int32_t>*>& seqs
     if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;
     launch_enc_add_ln(lc, e->h, e->sub, w.bo, w.attn_ln_g, w.attn_ln_b, e->x, T, H, c.ln_eps);
     if (!gemm_plan(&g, w.w_up, I, I, H, e->x, e->MT, T, EPI_GELU_BF16, e->act, I, 1, 0, 0)) return MQ_ERR_CUDA;
-    gemm_plan_set_bias(&g, w.b_up);
+    g.p.bias = w.b_up;
     if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;
     if (!gemm_plan(&g, w.w_down, H, H, I, e->act, e->MT, T, EPI_BF16, e->sub, H, 1, 0, 0)) return MQ_ERR_CUDA;
     if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;

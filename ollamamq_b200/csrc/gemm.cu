@@ -155,18 +155,8 @@ cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
       default: return cudaErrorInvalidValue;
     }
   if (g.persist) {
-    if (g.bn == 256) switch (g.epi) {
-        case EPI_F32: return launch_pk<256, EPI_F32>(g, lc);
-        case EPI_BIAS_BF16: return launch_pk<256, EPI_BIAS_BF16>(g, lc);
-        case EPI_GELU_BF16: return launch_pk<256, EPI_GELU_BF16>(g, lc);
-        default: return launch_pk<256, EPI_BF16>(g, lc);
-      }
-    switch (g.epi) {
-      case EPI_F32: return launch_pk<128, EPI_F32>(g, lc);
-      case EPI_BIAS_BF16: return launch_pk<128, EPI_BIAS_BF16>(g, lc);
-      case EPI_GELU_BF16: return launch_pk<128, EPI_GELU_BF16>(g, lc);
-      default: return launch_pk<128, EPI_BF16>(g, lc);
-    }
+    if (g.bn == 256) return g.epi == EPI_F32 ? launch_pk<256, EPI_F32>(g, lc) : launch_pk<256, EPI_BF16>(g, lc);
+    return g.epi == EPI_F32 ? launch_pk<128, EPI_F32>(g, lc) : launch_pk<128, EPI_BF16>(g, lc);
   }
   if (g.streamk) switch (g.epi) {
       case EPI_F32: return launch_sk_bn<EPI_F32>(g, lc);
@@ -223,10 +213,6 @@ void gemm_set_attrs() {
   cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_F32, true));
   cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_BF16, true));
   cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_F32, true));
-  cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_BIAS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_BIAS_BF16, true));
-  cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_GELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_GELU_BF16, true));
-  cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_BIAS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_BIAS_BF16, true));
-  cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_GELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_GELU_BF16, true));
 }
 
 // MQ_2CTA=0 turns the cta_group::2 prefill kernel off (A/B switch)
@@ -299,11 +285,6 @@ static bool decode_tiles_shallow() {
     v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;
-}
-
-void gemm_plan_set_bias(GemmPlan* g, const void* bias) {  // EPI_BIAS_BF16 / EPI_GELU_BF16, whichever kernel was planned
-  g->p.bias = bias;
-  g->pk.bias = bias;
 }
 
 void gemm_plan_fuse_norm(GemmPlan* g, float* h, const float* partial, int n_planes, long long plane_stride,
@@ -380,14 +361,14 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
     g->c2.w_policy = g->p.w_policy;
   }
   g->persist = false;
-  if (!g->twocta && !g->streamk && epi != EPI_SILU_BF16 && g->bn >= 128 && splits == 1 && persist_enabled()) {
+  if (!g->twocta && !g->streamk && epi != EPI_SILU_BF16 && epi != EPI_GELU_BF16 && epi != EPI_BIAS_BF16 && g->bn >= 128 && splits == 1 && persist_enabled()) {
     const int sms = device_sm_count();
     const int tiles = g->p.m_tiles * g->p.n_tiles;
     if (tiles >= 2 * sms) {  // at least two tiles per CTA, otherwise there is nothing to overlap
       g->persist = true;
       g->pk.out = out; g->pk.ldo = ldo; g->pk.T = T; g->pk.n_out = n_out; g->pk.k_blocks = kb;
       g->pk.m_tiles = g->p.m_tiles; g->pk.n_tiles = g->p.n_tiles; g->pk.group_m = g->p.group_m;
-      g->pk.n_ctas = sms; g->pk.w_policy = g->p.w_policy; g->pk.bias = nullptr;
+      g->pk.n_ctas = sms; g->pk.w_policy = g->p.w_policy;
     }
   }
   if (g->streamk) {

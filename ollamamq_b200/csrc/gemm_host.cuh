@@ -52,7 +52,6 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
 // Attach the fused residual-add + RMSNorm prologue (decode only; split-K kernel only): see GemmParams::norm_*.
 void gemm_plan_fuse_norm(GemmPlan* g, float* h, const float* partial, int n_planes, long long plane_stride,
                          const void* gamma, void* x, int H, float eps, int* counter);
-void gemm_plan_set_bias(GemmPlan* g, const void* bias);
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc);
 void gemm_set_attrs();
 

@@ -14,7 +14,6 @@ struct PersistParams {
   void* out;  // [T][ldo] bf16 (EPI_BF16) or fp32 (EPI_F32)
   int ldo, T, n_out, k_blocks, m_tiles, n_tiles, group_m, n_ctas;
   unsigned long long w_policy;
-  const void* bias;  // EPI_BIAS_BF16 / EPI_GELU_BF16: bf16 [n_out] (nullable)
 };
 
 template <int BN, int EPI>
@@ -22,7 +21,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const PersistParams p) {
   static_assert(EPI != EPI_SILU_BF16 && 2 * BN <= 512, "single accumulator, two TMEM buffers");
-  constexpr bool kBiasEpi = (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16);
   constexpr int STAGES = gemm_stages(BN, EPI, true);
   constexpr int STAGE_BYTES = gemm_stage_bytes(BN, EPI);
   constexpr int B_OFF = kATileBytes;
@@ -161,14 +159,9 @@ gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __uint_as_float(v[j]);
           } else {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)(n0 + c0) * p.ldo + f;
-            float b = 0.f;
-            if constexpr (kBiasEpi) b = p.bias ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[f]) : 0.f;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float a = __uint_as_float(v[j]) + b;
-              if constexpr (EPI == EPI_GELU_BF16) a = 0.5f * a * (1.0f + erff(a * 0.70710678118654752f));
-              if (n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __float2bfloat16(a);
-            }
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __float2bfloat16(__uint_as_float(v[j]));
           }
         }
       }

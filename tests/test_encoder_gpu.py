@@ -97,8 +97,7 @@ def test_full_size_bge_small_geometry():
             _close(got[i], ref[i])
             worst = max(worst, float(np.abs(got[i] - ref[i]).max() / np.abs(ref[i]).max()))
         print("bge-small full size: worst max|d| / max|e| = %.4f over %d sequences" % (worst, len(seqs)))
-        # a config-5 sized slice: 80 x 512 tokens = one 32768-token pass (every GEMM large enough for the persistent
-        # double-buffered kernel with the bias / GELU epilogues) + one 8192-token pass (plain kernels)
+        # a config-5 sized slice: 80 x 512 tokens = one 32768-token pass + one 8192-token pass
         batch = [rng.integers(0, cfg["vocab"], 512).astype("int32").tolist() for _ in range(80)]
         p0 = e.stats()["passes"]
         out = e.embed(batch)
