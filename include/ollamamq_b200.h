@@ -200,6 +200,12 @@ typedef struct mq_worker_stats {
   double decode_bytes;                /* algorithmic bytes moved by the timed decode steps    */
 } mq_worker_stats;
 int mq_worker_get_stats(mq_worker* w, mq_worker_stats* out);
+/* what the worker holds right now (answered on the worker thread): a drained worker has every page back in
+ * the pool, no slot in use and nothing waiting - the leak check of the soak test                           */
+typedef struct mq_worker_occupancy {
+  uint64_t total_pages, free_pages, active_slots, waiting, in_flight_gpu_passes;
+} mq_worker_occupancy;
+int mq_worker_get_occupancy(mq_worker* w, mq_worker_occupancy* out);
 int mq_worker_reset_stats(mq_worker* w);
 int mq_worker_set_timing(mq_worker* w, int32_t enable);
 

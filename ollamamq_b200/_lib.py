@@ -80,6 +80,11 @@ class ReqStats(C.Structure):
                 ("n_generated", C.c_int32)]
 
 
+class WorkerOccupancy(C.Structure):
+    _fields_ = [("total_pages", C.c_uint64), ("free_pages", C.c_uint64), ("active_slots", C.c_uint64),
+                ("waiting", C.c_uint64), ("in_flight_gpu_passes", C.c_uint64)]
+
+
 class WorkerStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("graph_launches", C.c_uint64), ("decode_steps", C.c_uint64),
                 ("prefill_passes", C.c_uint64), ("prefill_tokens", C.c_uint64), ("decode_tokens", C.c_uint64),
@@ -166,6 +171,7 @@ _sig("mq_debug_attn_prefill", C.c_int, [P, P, P, P, C.c_int, P, C.c_int, P, C.c_
                                          C.c_int])
 _sig("mq_debug_attn_decode", C.c_int, [P, P, P, P, C.c_int, P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_float, C.c_int])
+_sig("mq_worker_get_occupancy", C.c_int, [P, P])
 _sig("mq_debug_sched_bench", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, P])
 _sig("mq_dispatcher_snapshot_json", C.c_longlong, [P, P, C.c_size_t])
 _sig("mq_dispatcher_attach_encoder", C.c_int, [P, C.c_int32, P])

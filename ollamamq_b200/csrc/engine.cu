@@ -1239,6 +1239,19 @@ int mq_worker_get_stats(mq_worker* w, mq_worker_stats* out) {
   *out = w->stats;
   return MQ_OK;
 }
+int mq_worker_get_occupancy(mq_worker* w, mq_worker_occupancy* out) {
+  if (!w || !out) return MQ_ERR_INVAL;
+  return run_job(w, [=] {  // on the worker thread: slot table, page pool and queues are owned by it
+    out->total_pages = (uint64_t)w->n_pages - 1;  // page 0 is the scratch page
+    out->free_pages = (uint64_t)w->free_pages.size();
+    uint64_t act = 0;
+    for (mq_req* r : w->slot_req) act += r != nullptr;
+    out->active_slots = act;
+    out->waiting = (uint64_t)(w->waiting.size() + w->prefilling.size());
+    out->in_flight_gpu_passes = (uint64_t)w->flights.size();
+    return (int)MQ_OK;
+  });
+}
 int mq_worker_reset_stats(mq_worker* w) {
   if (!w) return MQ_ERR_INVAL;
   std::lock_guard<std::mutex> g(w->stats_mu);

@@ -189,6 +189,11 @@ class Worker:
         check(lib.mq_worker_get_stats(self._h, C.byref(st)))
         return {k: getattr(st, k) for k, _ in st._fields_}
 
+    def occupancy(self) -> dict:
+        oc = _lib.WorkerOccupancy()
+        check(lib.mq_worker_get_occupancy(self._h, C.byref(oc)))
+        return {k: getattr(oc, k) for k, _ in oc._fields_}
+
     def reset_stats(self):
         check(lib.mq_worker_reset_stats(self._h))
 

@@ -437,3 +437,57 @@ def test_dispatcher_wide_timeout_like_the_reference_client_timeout():
             assert d.user_stats("alice")["dropped"] >= 1 and d.user_stats("alice")["processed"] == 1
         finally:
             d.close()
+
+
+def test_soak_random_arrivals_cancels_timeouts_leave_nothing_behind():
+    """A few seconds of mixed traffic through dispatcher + worker: ragged prompts (some longer than one prefill pass),
+    more users than slots, random client disconnects and per-request timeouts.  Afterwards: every request ended exactly
+    once, completed ones hold greedy parity, and the worker is EMPTY - all KV pages back in the pool, no slot in use,
+    nothing queued (the leak / lost-wakeup check)."""
+    import random
+    import threading
+    cfg = MID
+    w = R.make_weights(cfg, seed=37, device="cuda")
+    rnd = random.Random(3)
+    with _open(cfg, w, max_batch=8, max_seq=512, max_prefill_tokens=128) as wk:
+        total_pages = wk.occupancy()["total_pages"]
+        assert wk.occupancy()["free_pages"] == total_pages
+        d = mq.Dispatcher([wk], capacity=8)
+        try:
+            g = torch.Generator().manual_seed(12)
+            streams, plan = [], []
+            for i in range(120):
+                n_prompt = rnd.choice([1, 3, 17, 64, 129, 300])
+                n_new = rnd.choice([1, 2, 8, 25, 60])
+                kind = rnd.choices(["ok", "cancel", "timeout"], weights=[6, 2, 1])[0]
+                p = torch.randint(0, cfg["vocab"], (n_prompt,), generator=g).tolist()
+                s = d.submit("user%02d" % rnd.randrange(20), prompt_tokens=p, max_new_tokens=n_new,
+                             timeout_ms=3 if kind == "timeout" else 0)
+                streams.append(s)
+                plan.append((kind, p, n_new))
+                if kind == "cancel":
+                    threading.Timer(rnd.random() * 0.05, d.client_gone, args=(s.task_id,)).start()
+                if i % 10 == 9:
+                    time.sleep(rnd.random() * 0.03)
+            d.drain(120000)
+            done_ok = 0
+            for s, (kind, p, n_new) in zip(streams, plan):
+                s.wait(30)
+                assert s.rc is not None
+                toks = s.tokens()
+                assert len(toks) <= n_new
+                if s.rc == 0:
+                    assert len(toks) == n_new
+                    done_ok += 1
+                    if done_ok % 7 == 0:
+                        _check_greedy(w, cfg, p, toks)
+                else:
+                    assert kind in ("cancel", "timeout") and s.rc in (-125, -110), (kind, s.rc, s.err)
+            assert done_ok >= 60
+            time.sleep(0.2)
+            oc = wk.occupancy()
+            assert oc["free_pages"] == total_pages and oc["active_slots"] == 0 and oc["waiting"] == 0, oc
+            assert oc["in_flight_gpu_passes"] == 0
+            assert wk.healthy()
+        finally:
+            d.close()
