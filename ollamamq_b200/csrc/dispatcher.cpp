@@ -202,11 +202,14 @@ int32_t cb_chunk(void* u, const uint8_t* data, size_t len) {
 void cb_done(void* u, int32_t rc, const char* msg) {
   auto* t = (mq_dispatcher::Task*)u;
   mq_dispatcher* d = t->d;
+  // a disconnect reported through mq_dispatcher_client_gone cancels the backend request at once, so no further chunk
+  // send gets the chance to fail: it is the same event as the failed send of :305-308
+  const bool gone = t->client_gone || (t->status_ok && rc != 0 && t->closed.load());  // rc == 0: the whole body went out
   int outcome;
-  if (t->status_ok) outcome = t->client_gone ? MQ_DONE_DROPPED : MQ_DONE_PROCESSED;  // mid-stream errors count processed (:310,:314)
+  if (t->status_ok) outcome = gone ? MQ_DONE_DROPPED : MQ_DONE_PROCESSED;            // mid-stream errors count processed (:310,:314)
   else if (rc != 0 && !t->closed.load()) outcome = MQ_DONE_DROPPED;                  // ResponsePart::Error (:323-327)
   else outcome = MQ_DONE_UNCOUNTED;                                                  // Status send failed (:299)
-  if (t->cb.on_done) t->cb.on_done(t->user_data, t->status_ok && !t->client_gone ? 0 : (rc ? rc : MQ_ERR_CANCELED), msg);
+  if (t->cb.on_done) t->cb.on_done(t->user_data, t->status_ok && !gone ? 0 : (rc ? rc : MQ_ERR_CANCELED), msg);
   executor_epilogue(d, t, outcome);
 }
 

@@ -429,12 +429,15 @@ def test_dispatcher_wide_timeout_like_the_reference_client_timeout():
             d.set_timeout(0.05)                       # 50 ms: far less than 3000 decode steps
             s = d.submit("alice", prompt_tokens=[1, 2, 3], max_new_tokens=3000)
             s.wait(60)
-            assert s.rc == -110 and 0 < len(s.tokens()) < 3000      # MQ_ERR_TIMEOUT after some tokens were streamed
+            # the worker ends the request with MQ_ERR_TIMEOUT after the head and some chunks went out; behind the
+            # dispatcher that is the reference's mid-stream upstream error: the relay just ends (dispatcher.rs:300-312),
+            # the client sees a truncated 200 body and the request counts as processed (:314-316)
+            assert s.rc == 0 and s.status == 200 and 0 < len(s.tokens()) < 3000
             d.set_timeout(0)
             s = d.submit("alice", prompt_tokens=[1, 2, 3], max_new_tokens=40)
             s.wait(60)
             assert s.rc == 0 and len(s.tokens()) == 40
-            assert d.user_stats("alice")["dropped"] >= 1 and d.user_stats("alice")["processed"] == 1
+            assert d.user_stats("alice")["processed"] == 2 and d.user_stats("alice")["dropped"] == 0
         finally:
             d.close()
 
@@ -477,9 +480,10 @@ def test_soak_random_arrivals_cancels_timeouts_leave_nothing_behind():
                 toks = s.tokens()
                 assert len(toks) <= n_new
                 if s.rc == 0:
-                    assert len(toks) == n_new
+                    # a timeout that fires mid-stream ends the relay like the reference does: truncated body, rc 0
+                    assert len(toks) == n_new or kind == "timeout", (kind, len(toks), n_new)
                     done_ok += 1
-                    if done_ok % 7 == 0:
+                    if done_ok % 7 == 0 and toks:
                         _check_greedy(w, cfg, p, toks)
                 else:
                     assert kind in ("cancel", "timeout") and s.rc in (-125, -110), (kind, s.rc, s.err)
