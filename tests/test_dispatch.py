@@ -320,3 +320,26 @@ def test_a_user_holds_at_most_one_flag_in_the_extension():
     assert [s.next().user for _ in range(1)] == ["b"]     # the only VIP left
     s.complete(0, "b", PROCESSED)
     assert s.next().user in ("a", "c")                     # counter is odd: ordinary round-robin turn
+
+
+def test_decision_bench_matches_the_oracle_driver(capsys):
+    """SURVEY.md 8(d) micro-benchmark: the product's bulk driver (mq_debug_sched_bench) and the oracle's (orc_bench) run
+    the same trace - U users x R requests, unit service time, lowest backend completes first - and must make the same
+    number of dispatches; the rates are printed for profiles/r01_dispatch_bench.txt (pytest -s)."""
+    import ctypes as C
+    import time
+    import ollamamq_b200 as mq
+    L = OracleC(1).L
+    rows = []
+    for users, backends, capacity in ((4, 2, 1), (64, 1, 1), (64, 8, 1), (256, 1, 1), (256, 8, 32)):
+        n, sec = C.c_uint64(), C.c_double()
+        mq.check(mq.lib.mq_debug_sched_bench(users, 32, backends, capacity, C.byref(n), C.byref(sec)))
+        t0 = time.perf_counter()
+        no = L.orc_bench(users, 32, backends, capacity)
+        dt = time.perf_counter() - t0
+        assert n.value == no == users * 32
+        rows.append((users, backends, capacity, n.value / max(sec.value, 1e-9), no / max(dt, 1e-9)))
+    with capsys.disabled():
+        for r in rows:
+            print("dispatch bench: %4d users %d backends capacity %2d | C++ scheduler %.2e decisions/s | oracle "
+                  "(re-sorts per decision, incl. enqueue) %.2e decisions/s" % r)
