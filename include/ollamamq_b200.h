@@ -166,6 +166,13 @@ typedef struct mq_request {
   int32_t ignore_eos;        /* benchmark mode: always generate max_new_tokens                            */
   uint32_t timeout_ms;       /* whole-request timeout (reqwest Client::timeout, :165-167); 0 = none       */
   const char* path;          /* request path (uri.path(), :362); only consulted for MQ_EP_OTHER; may be NULL  */
+  /* sampling (the backend's "sample" step).  All zero = greedy, which is what BASELINE measures.  A JSON body may
+   * carry them too (Ollama "options": {temperature, top_k, top_p, seed}; OpenAI top-level temperature, top_p, seed)
+   * and wins over these fields.                                                                          */
+  float temperature;         /* <= 0: greedy argmax (lowest index wins ties)                              */
+  int32_t top_k;             /* <= 0: off                                                                 */
+  float top_p;               /* <= 0 or >= 1: off; applied to what top_k kept                             */
+  uint64_t seed;             /* stream of the counter-based generator: same seed, same tokens             */
 } mq_request;
 
 typedef struct mq_callbacks {
@@ -339,6 +346,9 @@ int mq_debug_attn_decode(const void* q, const void* k_cache, const void* v_cache
  * ~(last CTA end)}; untouched slots read as all-ones.  Slots: 1 + 8*layer + {0 norm, 1 qkv, 2 rope, 3 attention,
  * 4 o-proj, 5 norm, 6 gate/up, 7 down}; 510 final norm, 511 LM head.  Returns the slot count copied (<= 512). */
 int mq_debug_trace_read(mq_worker* w, unsigned long long* out, int32_t max_slots);
+/* the sampler kernel on given logits: per-row controls (device arrays, row == slot), counter = RNG position  */
+int mq_debug_sample(const float* logits, int rows, int V, int ldl, int* out_tokens, const float* temperature,
+                    const int* top_k, const float* top_p, const unsigned long long* seed, const int* counter);
 int mq_debug_argmax(const float* logits, int rows, int V, int ldl, int* out_tokens, const int* dst_slot,
                     int* cur_token, int* pos_inc, const int* active);
 int mq_debug_init_normal(void* w, unsigned long long n, unsigned long long seed, float std);

@@ -63,7 +63,8 @@ class EncoderStats(C.Structure):
 class Request(C.Structure):
     _fields_ = [("endpoint", C.c_int32), ("stream", C.c_int32), ("body", C.c_void_p), ("body_len", C.c_size_t),
                 ("prompt_tokens", C.c_void_p), ("n_prompt_tokens", C.c_int32), ("max_new_tokens", C.c_int32),
-                ("ignore_eos", C.c_int32), ("timeout_ms", C.c_uint32), ("path", C.c_char_p)]
+                ("ignore_eos", C.c_int32), ("timeout_ms", C.c_uint32), ("path", C.c_char_p),
+                ("temperature", C.c_float), ("top_k", C.c_int32), ("top_p", C.c_float), ("seed", C.c_uint64)]
 
 
 ON_STATUS = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_char_p)
@@ -186,6 +187,7 @@ _sig("mq_encoder_get_stats", C.c_int, [P, P])
 _sig("mq_encoder_embed", C.c_int, [P, P, P, C.c_int32, P])
 _sig("mq_encoder_submit", C.c_int, [P, P, P, P, P])
 _sig("mq_debug_trace_read", C.c_int, [P, P, C.c_int])
+_sig("mq_debug_sample", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, P, P, P, P, P])
 _sig("mq_debug_argmax", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, P, P, P, P])
 _sig("mq_debug_init_normal", C.c_int, [P, C.c_ulonglong, C.c_ulonglong, C.c_float])
 

@@ -155,6 +155,13 @@ static int worker_alloc(mq_worker* w) {
   if ((rc = dalloc(&w->d_cur_token, MBp))) return rc;
   if ((rc = dalloc(&w->d_pos, MBp))) return rc;
   if ((rc = dalloc(&w->d_active, MBp))) return rc;
+  if ((rc = dalloc(&w->d_temp, MBp)) || (rc = dalloc(&w->d_topp, MBp)) || (rc = dalloc(&w->d_topk, MBp)) ||
+      (rc = dalloc(&w->d_seed, MBp)))
+    return rc;
+  CUDA_TRY(cudaMemsetAsync(w->d_temp, 0, MBp * 4, w->stream));
+  CUDA_TRY(cudaMemsetAsync(w->d_topp, 0, MBp * 4, w->stream));
+  CUDA_TRY(cudaMemsetAsync(w->d_topk, 0, MBp * 4, w->stream));
+  CUDA_TRY(cudaMemsetAsync(w->d_seed, 0, MBp * 8, w->stream));
   if ((rc = dalloc(&w->d_identity, MBp))) return rc;
   if ((rc = dalloc(&w->d_block_table, (size_t)MBp * w->max_pages))) return rc;
   if ((rc = dalloc(&w->d_out_ring, (size_t)kRing * MBp))) return rc;
@@ -166,11 +173,16 @@ static int worker_alloc(mq_worker* w) {
   // pinned host
   CUDA_TRY(cudaMallocHost((void**)&w->h_pos, MBp * 4));
   CUDA_TRY(cudaMallocHost((void**)&w->h_active, MBp * 4));
+  CUDA_TRY(cudaMallocHost((void**)&w->h_temp, MBp * 4));
+  CUDA_TRY(cudaMallocHost((void**)&w->h_topp, MBp * 4));
+  CUDA_TRY(cudaMallocHost((void**)&w->h_topk, MBp * 4));
+  CUDA_TRY(cudaMallocHost((void**)&w->h_seed, MBp * 8));
+  memset(w->h_temp, 0, MBp * 4); memset(w->h_topp, 0, MBp * 4); memset(w->h_topk, 0, MBp * 4); memset(w->h_seed, 0, MBp * 8);
   CUDA_TRY(cudaMallocHost((void**)&w->h_block_table, (size_t)MBp * w->max_pages * 4));
   memset(w->h_pos, 0, MBp * 4);
   memset(w->h_active, 0, MBp * 4);
   memset(w->h_block_table, 0, (size_t)MBp * w->max_pages * 4);
-  w->stage_ints = (size_t)3 * MT + 4 * (size_t)(MT + MB) + 4 * (size_t)MBp + (size_t)MBp * w->max_pages + 64;
+  w->stage_ints = (size_t)3 * MT + 4 * (size_t)(MT + MB) + 10 * (size_t)MBp + (size_t)MBp * w->max_pages + 64;
   CUDA_TRY(cudaMallocHost((void**)&w->h_stage, w->stage_ints * 4 * kStageSlots));
   CUDA_TRY(cudaMallocHost((void**)&w->h_out_ring, (size_t)kRing * MBp * 4));
   w->stage_ev.resize(kStageSlots);
@@ -406,6 +418,15 @@ static void upload_slots(mq_worker* w) {
   int* s_pos = st;
   int* s_act = st + MBp;
   int* s_bt = st + 2 * MBp;
+  int* s_samp = s_bt + (size_t)MBp * w->max_pages;  // temperature | top_k | top_p | seed (2 ints each)
+  memcpy(s_samp, w->h_temp, MBp * 4);
+  memcpy(s_samp + MBp, w->h_topk, MBp * 4);
+  memcpy(s_samp + 2 * MBp, w->h_topp, MBp * 4);
+  memcpy(s_samp + 3 * MBp + (MBp & 1), w->h_seed, MBp * 8);
+  cudaMemcpyAsync(w->d_temp, s_samp, MBp * 4, cudaMemcpyHostToDevice, w->stream);
+  cudaMemcpyAsync(w->d_topk, s_samp + MBp, MBp * 4, cudaMemcpyHostToDevice, w->stream);
+  cudaMemcpyAsync(w->d_topp, s_samp + 2 * MBp, MBp * 4, cudaMemcpyHostToDevice, w->stream);
+  cudaMemcpyAsync(w->d_seed, s_samp + 3 * MBp + (MBp & 1), MBp * 8, cudaMemcpyHostToDevice, w->stream);
   memcpy(s_pos, w->h_pos, MBp * 4);
   memcpy(s_act, w->h_active, MBp * 4);
   memcpy(s_bt, w->h_block_table, (size_t)MBp * w->max_pages * 4);
@@ -550,8 +571,9 @@ static int launch_prefill(mq_worker* w, std::vector<PrefillItem>& items) {
     rc = run_head(w, false, w->d_last_idx, n_last, pp, &nl);
     if (rc) return rc;
     const LaunchCfg lc{w->stream, c.use_pdl != 0};
-    launch_argmax(lc, w->logits, n_last, c.vocab, c.vocab, w->d_out_ring + (size_t)ring * MBp, w->d_dst_slot,
-                  w->d_cur_token, nullptr, nullptr);
+    // first generated token of each finished prompt: RNG position 0 (decode steps use the token position >= 1)
+    launch_sample(lc, w->logits, n_last, c.vocab, c.vocab, w->d_out_ring + (size_t)ring * MBp, w->d_dst_slot,
+                  w->d_cur_token, nullptr, nullptr, SampleCtl{w->d_temp, w->d_topk, w->d_topp, w->d_seed, nullptr});
     ++nl;
     cudaMemcpyAsync(w->h_out_ring + (size_t)ring * MBp, w->d_out_ring + (size_t)ring * MBp, n_last * 4,
                     cudaMemcpyDeviceToHost, w->stream);
@@ -602,8 +624,8 @@ static int decode_body(mq_worker* w, int Bcap, int n_splits, int ring, uint64_t*
   const int MBp = round_up(w->MB, 16);
   // NOTE: the ring slot is baked into a captured graph, so graphs write to a fixed staging row (ring 0 of the
   // graph area) and the copy-out below moves it into the real ring slot.
-  launch_argmax(lc, w->logits, Bcap, c.vocab, c.vocab, w->d_out_ring + (size_t)ring * MBp, nullptr, w->d_cur_token,
-                w->d_pos, w->d_active);
+  launch_sample(lc, w->logits, Bcap, c.vocab, c.vocab, w->d_out_ring + (size_t)ring * MBp, nullptr, w->d_cur_token,
+                w->d_pos, w->d_active, SampleCtl{w->d_temp, w->d_topk, w->d_topp, w->d_seed, w->d_pos});
   *nl += 1;
   return MQ_OK;
 }
@@ -793,6 +815,7 @@ static bool admit(mq_worker* w, mq_req* r) {
   }
   w->h_pos[slot] = 0;
   w->h_active[slot] = 0;
+  w->h_temp[slot] = r->temperature; w->h_topk[slot] = r->top_k; w->h_topp[slot] = r->top_p; w->h_seed[slot] = r->seed;
   w->slots_dirty = true;
   return true;
 }
@@ -1189,6 +1212,11 @@ int mq_submit(mq_worker* w, const mq_request* rq, const mq_callbacks* cb, void* 
   if (pb.has_stream && rq->stream < 0) r->rq.stream = pb.stream ? 1 : 0;
   if (r->rq.stream < 0) r->rq.stream = 1;
   r->max_new = rq->max_new_tokens > 0 ? rq->max_new_tokens : (pb.num_predict > 0 ? pb.num_predict : 128);
+  // sampling: body options win over the struct fields; everything unset = greedy (what BASELINE measures)
+  r->temperature = pb.has_temperature ? (float)pb.temperature : rq->temperature;
+  r->top_k = pb.has_top_k ? (int)std::min<long long>(pb.top_k, 1 << 30) : rq->top_k;
+  r->top_p = pb.has_top_p ? (float)pb.top_p : rq->top_p;
+  r->seed = pb.has_seed ? pb.seed : rq->seed;
   if ((int)r->prompt.size() + r->max_new > w->cfg.max_seq) {
     const int n = (int)r->prompt.size();
     delete r;

@@ -53,6 +53,9 @@ struct mq_req {
   int n_sched = 0;       // generated tokens scheduled on the GPU so far
   int n_emitted = 0;     // generated tokens delivered to the callback
   int max_new = 0;
+  float temperature = 0.f, top_p = 0.f;  // sampling controls (0 = greedy / off)
+  int top_k = 0;
+  unsigned long long seed = 0;
   std::atomic<bool> cancel{false};
   bool status_sent = false;
   bool finished = false;
@@ -91,6 +94,10 @@ struct mq_worker {
   int *d_tok = nullptr, *d_pos_tok = nullptr, *d_slot_tok = nullptr, *d_last_idx = nullptr, *d_dst_slot = nullptr;
   int4* d_tiles = nullptr;
   int *d_cur_token = nullptr, *d_pos = nullptr, *d_active = nullptr, *d_block_table = nullptr, *d_identity = nullptr;
+  // per-slot sampling controls (device) + pinned host mirrors, uploaded with the slot table
+  float *d_temp = nullptr, *d_topp = nullptr, *h_temp = nullptr, *h_topp = nullptr;
+  int *d_topk = nullptr, *h_topk = nullptr;
+  unsigned long long *d_seed = nullptr, *h_seed = nullptr;
   int* d_out_ring = nullptr;  // [kRing][MB]
   int* d_split_counter = nullptr;  // [MB][n_kv] arrival counters of the split-KV decode attention
   int* d_norm_counters = nullptr;  // [2 * layers] arrival counters of the fused norm prologues (zeroed by embed)

@@ -180,6 +180,9 @@ bool parse_body(const std::string& body, int endpoint, ParsedBody* out) {
     else if (k == "max_tokens" || k == "max_completion_tokens" || k == "num_predict") {
       double v; if (!j.number(&v)) { if (!j.skip()) return false; } else out->num_predict = (int)v;
     }
+    else if (k == "temperature") { double v; if (j.number(&v)) { out->temperature = v; out->has_temperature = true; } else if (!j.skip()) return false; }
+    else if (k == "top_p") { double v; if (j.number(&v)) { out->top_p = v; out->has_top_p = true; } else if (!j.skip()) return false; }
+    else if (k == "seed") { double v; if (j.number(&v)) { out->seed = (unsigned long long)v; out->has_seed = true; } else if (!j.skip()) return false; }
     else if (k == "options") {
       j.ws();
       if (j.p < j.e && *j.p == '{') {
@@ -191,6 +194,10 @@ bool parse_body(const std::string& body, int endpoint, ParsedBody* out) {
           if (!j.str(&ok)) return false;
           j.ws(); if (j.p < j.e && *j.p == ':') ++j.p;
           if (ok == "num_predict") { double v; if (j.number(&v)) out->num_predict = (int)v; else if (!j.skip()) return false; }
+          else if (ok == "temperature") { double v; if (j.number(&v)) { out->temperature = v; out->has_temperature = true; } else if (!j.skip()) return false; }
+          else if (ok == "top_k") { double v; if (j.number(&v)) { out->top_k = (long long)v; out->has_top_k = true; } else if (!j.skip()) return false; }
+          else if (ok == "top_p") { double v; if (j.number(&v)) { out->top_p = v; out->has_top_p = true; } else if (!j.skip()) return false; }
+          else if (ok == "seed") { double v; if (j.number(&v)) { out->seed = (unsigned long long)v; out->has_seed = true; } else if (!j.skip()) return false; }
           else if (!j.skip()) return false;
           j.ws(); if (j.p < j.e && *j.p == ',') ++j.p;
         }

@@ -16,6 +16,11 @@ struct ParsedBody {
   bool has_stream = false;
   bool stream = true;
   int num_predict = 0;          // options.num_predict | max_tokens | max_completion_tokens
+  // sampling: options.{temperature, top_k, top_p, seed} (Ollama) or top-level temperature / top_p / seed (OpenAI)
+  bool has_temperature = false, has_top_k = false, has_top_p = false, has_seed = false;
+  double temperature = 0, top_p = 0;
+  long long top_k = 0;
+  unsigned long long seed = 0;
 };
 
 bool parse_body(const std::string& body, int endpoint, ParsedBody* out);

@@ -1074,6 +1074,171 @@ void launch_argmax(const LaunchCfg& lc, const float* logits, int rows, int V, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// stochastic sampler: temperature, top-k, top-p, seed (the "sample" step of the backend's forward pass).
+//
+// One CTA per row.  temperature <= 0 (the default) is the greedy path above, bit for bit.  Otherwise:
+//   1. top-k:  radix select (4 passes of 256-bin counts over the order-preserving uint image of the logits) finds the
+//      value of the k-th largest logit; ties at the threshold stay in (the kept set is {l >= thr}).
+//   2. top-p over what top-k kept: the same radix walk with MASS histograms - fixed-point 2^40 * exp((l - max) / T)
+//      in 64-bit integer atomics, so the result does not depend on the order threads arrive in - finds the largest
+//      threshold whose kept mass reaches p * Z.
+//   3. the draw is a Gumbel-max: argmax over the kept set of l / T - log(-log u), u from a counter-based generator
+//      keyed by (seed, position, token id) - an exact sample of softmax(l / T) restricted to the kept set, with no
+//      sort, no prefix sum and no state carried between steps (restated in oracle/sampler_ref.py).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f32_key(float f) {  // order-preserving: a < b  <=>  key(a) < key(b)
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ float gumbel_noise(uint64_t seed, int counter, int idx) {
+  const uint64_t r = mix64(seed ^ ((uint64_t)(uint32_t)counter * 0xD1342543DE82EF95ull) ^ ((uint64_t)(uint32_t)idx * 0xA24BAED4963EE407ull));
+  const float u = ((float)(uint32_t)(r >> 40) + 0.5f) * (1.0f / 16777216.0f);  // (0, 1)
+  return -logf(-logf(u));
+}
+constexpr float kMassScale = 1099511627776.0f;  // 2^40
+
+// Radix walk from the most significant byte: afterwards `prefix` is the key of the threshold element.
+//   MASS == false: the K-th largest key (count walk).   MASS == true: the largest key t with mass{key >= t} >= target.
+// Only keys >= floor_key take part.  All threads of the block call this; the result is returned to all of them.
+template <bool MASS>
+__device__ uint32_t radix_threshold(const float* __restrict__ lp, int V, uint32_t floor_key, unsigned long long target,
+                                    float mx, float inv_t, unsigned long long* hist /* smem [256] */, uint32_t* bcast) {
+  uint32_t prefix = 0, mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0ull;
+    __syncthreads();
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+      const float l = lp[i];
+      const uint32_t k = f32_key(l);
+      if (k >= floor_key && (k & mask) == prefix) {
+        unsigned long long w = 1ull;
+        if (MASS) w = (unsigned long long)(kMassScale * __expf((l - mx) * inv_t));
+        atomicAdd(&hist[(k >> shift) & 255u], w);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long acc = 0ull;
+      int bin = 255;
+      for (; bin > 0; --bin) {
+        if (acc + hist[bin] >= target) break;
+        acc += hist[bin];
+      }
+      bcast[0] = (uint32_t)bin;
+      // what is still to be found inside the chosen bin
+      reinterpret_cast<unsigned long long*>(bcast + 2)[0] = target - acc;
+    }
+    __syncthreads();
+    prefix |= bcast[0] << shift;
+    mask |= 255u << shift;
+    target = reinterpret_cast<unsigned long long*>(bcast + 2)[0];
+    __syncthreads();
+  }
+  return prefix;
+}
+
+__global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ logits, int V, int ldl,
+                                                      int* __restrict__ out_tokens, const int* __restrict__ dst_slot,
+                                                      int* __restrict__ cur_token, int* __restrict__ pos_inc,
+                                                      const int* __restrict__ active, const SampleCtl ctl) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ unsigned long long hist[256];
+  __shared__ __align__(8) uint32_t bcast[4];
+  __shared__ float sb[32];
+  __shared__ int si[32];
+  const int row = blockIdx.x;
+  const int slot = dst_slot ? dst_slot[row] : row;
+  const float* lp = logits + (size_t)row * ldl;
+  const float temp = ctl.temperature ? ctl.temperature[slot] : 0.f;
+  const bool greedy = !(temp > 0.f);
+  const float inv_t = greedy ? 1.f : 1.f / temp;
+  uint32_t thr_key = 0u;  // keep everything
+  uint64_t seed = 0;
+  int counter = 0;
+  if (!greedy) {
+    seed = ctl.seed ? ctl.seed[slot] : 0ull;
+    counter = ctl.counter ? ctl.counter[slot] : 0;
+    // row maximum (for the mass scale)
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, lp[i]);
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = sb[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, sb[w]);
+    __syncthreads();
+    const int k = ctl.top_k ? ctl.top_k[slot] : 0;
+    if (k > 0 && k < V) thr_key = radix_threshold<false>(lp, V, 0u, (unsigned long long)k, mx, inv_t, hist, bcast);
+    const float p = ctl.top_p ? ctl.top_p[slot] : 1.f;
+    if (p > 0.f && p < 1.f) {
+      // total mass of what top-k kept, in the same fixed point
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0ull;
+      __syncthreads();
+      unsigned long long part = 0ull;
+      for (int i = threadIdx.x; i < V; i += blockDim.x) {
+        const float l = lp[i];
+        if (f32_key(l) >= thr_key) part += (unsigned long long)(kMassScale * __expf((l - mx) * inv_t));
+      }
+      atomicAdd(&hist[0], part);
+      __syncthreads();
+      const unsigned long long Z = hist[0];
+      __syncthreads();
+      unsigned long long target = (unsigned long long)((double)Z * (double)p);
+      if (target < 1ull) target = 1ull;
+      const uint32_t tp = radix_threshold<true>(lp, V, thr_key, target, mx, inv_t, hist, bcast);
+      thr_key = tp > thr_key ? tp : thr_key;
+    }
+  }
+  // ---- the draw (greedy: plain argmax, lowest index wins ties)
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float l = lp[i];
+    float sc = l;
+    if (!greedy) {
+      if (f32_key(l) < thr_key) continue;
+      sc = l * inv_t + gumbel_noise(seed, counter, i);
+    }
+    if (sc > best || (sc == best && i < bi)) { best = sc; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sb[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (sb[w] > best || (sb[w] == best && si[w] < bi)) { best = sb[w]; bi = si[w]; }
+    if (bi == 0x7fffffff) bi = 0;  // (cannot happen: the maximum is always kept)
+    out_tokens[row] = bi;
+    if (cur_token) cur_token[slot] = bi;
+    if (pos_inc && (!active || active[slot])) pos_inc[slot] += 1;
+  }
+}
+void launch_sample(const LaunchCfg& lc, const float* logits, int rows, int V, int ldl, int* out_tokens,
+                   const int* dst_slot, int* cur_token, int* pos_inc, const int* active, const SampleCtl& ctl) {
+  launch_k(lc, sample_kernel, dim3(rows), dim3(1024), 0, logits, V, ldl, out_tokens, dst_slot, cur_token, pos_inc, active,
+           ctl);
+}
+
+// ------------------------------------------------------------------------------------------------
 // deterministic weight init (counter-based; the oracle restates it in numpy: oracle/weights.py)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {

@@ -105,6 +105,20 @@ void launch_enc_add_ln(const LaunchCfg& lc, float* h, const __nv_bfloat16* sub, 
                        const __nv_bfloat16* g, const __nv_bfloat16* b, __nv_bfloat16* x, int T, int H, float eps);
 void launch_enc_pool(const LaunchCfg& lc, const float* h, const int* first_tok, float* out, int n_seq, int H);
 
+// Per-slot sampling controls (device arrays indexed by slot; a null array = the default): temperature <= 0 -> greedy;
+// top_k <= 0 or >= V -> off; top_p <= 0 or >= 1 -> off; counter = position of the token being drawn (RNG stream).
+struct SampleCtl {
+  const float* temperature;
+  const int* top_k;
+  const float* top_p;
+  const unsigned long long* seed;
+  const int* counter;
+};
+// like launch_argmax, but rows whose slot has temperature > 0 are drawn from softmax(logits / T) restricted by
+// top-k / top-p (Gumbel-max with a counter-based generator: no state, reproducible per (seed, position))
+void launch_sample(const LaunchCfg& lc, const float* logits, int rows, int V, int ldl, int* out_tokens,
+                   const int* dst_slot, int* cur_token, int* pos_inc, const int* active, const SampleCtl& ctl);
+
 // deterministic counter-based N(0, std^2) fill (splitmix64 + Box-Muller), bf16
 void launch_init_normal(cudaStream_t st, __nv_bfloat16* w, size_t n, uint64_t seed, float std);
 void launch_fill_bf16(cudaStream_t st, __nv_bfloat16* w, size_t n, float v);

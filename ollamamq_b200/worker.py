@@ -95,11 +95,13 @@ class Stream:
 
 
 def make_request(endpoint=EP_RAW_TOKENS, prompt_tokens: Optional[Sequence[int]] = None, body: Optional[bytes] = None,
-                 max_new_tokens=16, stream=1, timeout_ms=0, path: Optional[str] = None):
+                 max_new_tokens=16, stream=1, timeout_ms=0, path: Optional[str] = None, temperature=0.0, top_k=0,
+                 top_p=0.0, seed=0):
     r = _lib.Request()
     if path is not None:
         r.path = path.encode()
     r.endpoint, r.stream, r.max_new_tokens, r.ignore_eos, r.timeout_ms = endpoint, stream, max_new_tokens, 1, timeout_ms
+    r.temperature, r.top_k, r.top_p, r.seed = float(temperature), int(top_k), float(top_p), int(seed)
     keep = []
     if body is not None:
         buf = C.create_string_buffer(body, len(body))

@@ -495,3 +495,50 @@ def test_soak_random_arrivals_cancels_timeouts_leave_nothing_behind():
             assert wk.healthy()
         finally:
             d.close()
+
+
+def test_sampling_temperature_topk_seed_through_the_engine():
+    """The backend's "sample" step: temperature / top_k / top_p / seed per request (struct fields or Ollama "options" in
+    the body).  Same seed -> same tokens across runs and batch compositions; other seed -> other tokens; top_k = 1 is
+    greedy; every sampled token lies in the oracle's top-k of the teacher-forced fp32 logits."""
+    cfg = MID
+    w = R.make_weights(cfg, seed=41, device="cuda")
+    g = torch.Generator().manual_seed(6)
+    prompt = torch.randint(0, cfg["vocab"], (40,), generator=g).tolist()
+    other = torch.randint(0, cfg["vocab"], (23,), generator=g).tolist()
+    with _open(cfg, w, max_batch=8, use_pdl=1, use_graphs=1) as wk:
+        def run(**kw):
+            s = wk.submit(mq.Stream(), prompt_tokens=prompt, max_new_tokens=24, **kw)
+            s.wait(120)
+            assert s.rc == 0, s.err
+            t = s.tokens()
+            mq.lib.mq_req_release(s.handle)
+            return t
+        greedy = run()
+        assert run(temperature=0.9, top_k=1, seed=5) == greedy
+        a = run(temperature=0.9, top_k=40, top_p=0.95, seed=1234)
+        b = run(temperature=0.9, top_k=40, top_p=0.95, seed=1234)
+        c = run(temperature=0.9, top_k=40, top_p=0.95, seed=99)
+        assert a == b and a != c and a != greedy
+        # same request inside a batch of others (different slot, different batch size): same stream of tokens
+        noise = [wk.submit(mq.Stream(), prompt_tokens=other, max_new_tokens=30, temperature=1.0, seed=i) for i in range(5)]
+        d = run(temperature=0.9, top_k=40, top_p=0.95, seed=1234)
+        for s in noise:
+            s.wait(120)
+            mq.lib.mq_req_release(s.handle)
+        assert d == a
+        # every sampled token is one of the 40 most likely under the oracle's fp32 logits (teacher-forced)
+        ref = R.forward(w, cfg, (prompt + a)[:-1], torch.float32)
+        for j, tok in enumerate(a):
+            row = ref[len(prompt) - 1 + j]
+            kth = torch.topk(row, 40).values[-1]
+            assert row[tok] >= kth - TOL * row.abs().max(), (j, tok)
+        # Ollama-style options in a JSON body
+        body = json.dumps({"model": "m", "prompt": "hello", "stream": False,
+                           "options": {"temperature": 0.7, "top_k": 20, "seed": 3, "num_predict": 12}}).encode()
+        s1 = wk.submit(mq.Stream(), endpoint=0, body=body, max_new_tokens=0, stream=-1); s1.wait(60)
+        s2 = wk.submit(mq.Stream(), endpoint=0, body=body, max_new_tokens=0, stream=-1); s2.wait(60)
+        s3 = wk.submit(mq.Stream(), endpoint=0, body=body.replace(b'"seed": 3', b'"seed": 4'), max_new_tokens=0, stream=-1)
+        s3.wait(60)
+        r1, r2, r3 = (json.loads(x.body)["response"] for x in (s1, s2, s3))
+        assert r1 == r2 and r1 != r3

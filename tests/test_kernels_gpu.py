@@ -383,3 +383,74 @@ def test_argmax_and_advance():
     assert torch.equal(out, ref)
     assert torch.equal(cur[dst.long()], ref)
     assert pos.tolist() == [11, 20, 31, 41, 51]
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler (temperature / top-k / top-p / seed) against oracle/sampler_ref.py
+# ------------------------------------------------------------------------------------------------
+def _sample(m, logits, temp, top_k, top_p, seed, counter):
+    rows, V = logits.shape
+    out = torch.zeros(rows, dtype=torch.int32, device=dev())
+    f = lambda v, dt: torch.tensor(v, dtype=dt, device=dev())
+    t, k, p = f(temp, torch.float32), f(top_k, torch.int32), f(top_p, torch.float32)
+    c = f(counter, torch.int32)
+    s = torch.tensor(np.array(seed, dtype=np.uint64).view(np.int64), dtype=torch.int64, device=dev())
+    rc = m.lib.mq_debug_sample(P(logits), rows, V, V, P(out), P(t), P(k), P(p), P(s), P(c))
+    assert rc == 0, m.last_error()
+    return out.cpu().numpy()
+
+
+def test_sampler_greedy_topk1_and_determinism():
+    from oracle import sampler_ref as S  # noqa: F401
+    m = _lib()
+    rows, V = 6, 128256
+    logits = torch.randn(rows, V, device=dev()) * 3
+    ref = logits.argmax(-1).cpu().numpy()
+    # temperature 0 = greedy; top_k = 1 = greedy whatever the temperature and seed
+    assert (_sample(m, logits, [0.0] * rows, [0] * rows, [0.0] * rows, [1] * rows, [0] * rows) == ref).all()
+    assert (_sample(m, logits, [1.3] * rows, [1] * rows, [0.0] * rows, list(range(rows)), [5] * rows) == ref).all()
+    a = _sample(m, logits, [0.9] * rows, [40] * rows, [0.9] * rows, [7] * rows, [3] * rows)
+    b = _sample(m, logits, [0.9] * rows, [40] * rows, [0.9] * rows, [7] * rows, [3] * rows)
+    c = _sample(m, logits, [0.9] * rows, [40] * rows, [0.9] * rows, [7] * rows, [4] * rows)
+    assert (a == b).all() and (a != c).any()              # same (seed, position) -> same token; next position differs
+
+
+@pytest.mark.parametrize("V,temp,top_k,top_p", [(128256, 0.7, 50, 0.0), (32064, 1.0, 0, 0.0), (5000, 0.8, 40, 0.9),
+                                                 (128256, 1.2, 0, 0.95), (4096, 0.5, 7, 0.5)])
+def test_sampler_matches_the_oracle(V, temp, top_k, top_p):
+    from oracle import sampler_ref as S
+    m = _lib()
+    rows = 8
+    g = torch.Generator().manual_seed(V + top_k)
+    logits = (torch.randn(rows, V, generator=g) * 2.5).to(dev())
+    seeds = [11 * (r + 1) for r in range(rows)]
+    counters = [3 + r for r in range(rows)]
+    got = _sample(m, logits, [temp] * rows, [top_k] * rows, [top_p] * rows, seeds, counters)
+    lc = logits.cpu().numpy()
+    exact = 0
+    for r in range(rows):
+        tok, sc = S.sample(lc[r], temp, top_k, top_p, seeds[r], counters[r])
+        keep = S.keep_mask(lc[r], temp, top_k, top_p)
+        # the kernel's token must be in the oracle's kept set (up to a borderline element of the nucleus: the kernel
+        # sums 2^40 fixed-point masses, the oracle float64) and must maximise the perturbed score up to float rounding
+        lo = lc[r][keep].min()
+        assert lc[r][got[r]] >= lo - 2e-3, (r, lc[r][got[r]], lo)
+        assert sc[tok] - (lc[r][got[r]] / np.float32(temp) + S.gumbel(seeds[r], counters[r], V)[got[r]]) <= 1e-3
+        exact += int(got[r] == tok)
+    assert exact >= rows - 1
+
+
+def test_sampler_draws_follow_the_distribution():
+    from oracle import sampler_ref as S
+    m = _lib()
+    V, n = 64, 6000
+    base = torch.linspace(-2.0, 2.0, V)
+    logits = base.repeat(n, 1).to(dev())
+    temp, top_k = 0.8, 12
+    got = _sample(m, logits, [temp] * n, [top_k] * n, [0.0] * n, [99] * n, list(range(n)))   # n positions = n draws
+    keep = S.keep_mask(base.numpy(), temp, top_k, 0.0)
+    assert keep.sum() == top_k and keep[got].all()
+    p = np.where(keep, np.exp(base.numpy().astype(np.float64) / temp), 0.0)
+    p /= p.sum()
+    freq = np.bincount(got, minlength=V) / n
+    assert np.abs(freq - p).max() < 0.02, np.abs(freq - p).max()
