@@ -7,6 +7,8 @@ Floating-point tolerances are stated per test.  bf16 outputs: one bf16 rounding 
 import ctypes as C
 import math
 
+import numpy as np
+
 import pytest
 
 torch = pytest.importorskip("torch")
