@@ -122,6 +122,8 @@ typedef struct mq_model_cfg {
   int32_t kv_pages;        /* paged KV cache size in 16-token pages (0 = derive from max_batch*max_seq)  */
   int32_t use_graphs;      /* 1: CUDA-graph the decode step                                              */
   int32_t use_pdl;         /* 1: programmatic dependent launch between kernels                           */
+  int32_t eos_token_id;    /* > 0: a request without ignore_eos ends when this token is drawn (it is not relayed;
+                              done_reason / finish_reason "stop"); 0 = the model has none                 */
   char model_name[64];     /* echoed in response JSON ("model" field)                                    */
 } mq_model_cfg;
 

@@ -45,7 +45,7 @@ class ModelCfg(C.Structure):
                 ("qkv_bias", C.c_int32), ("rope_theta", C.c_float), ("rms_eps", C.c_float),
                 ("max_batch", C.c_int32), ("max_seq", C.c_int32), ("max_prefill_tokens", C.c_int32),
                 ("kv_pages", C.c_int32), ("use_graphs", C.c_int32), ("use_pdl", C.c_int32),
-                ("model_name", C.c_char * 64)]
+                ("eos_token_id", C.c_int32), ("model_name", C.c_char * 64)]
 
 
 class EncoderCfg(C.Structure):

@@ -472,7 +472,7 @@ static void finish_req(mq_worker* w, mq_req* r, int rc, const char* msg) {
   if (rc == 0) {
     send_status(r);
     std::string tail = frame_final(r->rq.endpoint, r->rq.stream, w->cfg.model_name, r->agg, (int)r->prompt.size(),
-                                   r->n_emitted);
+                                   r->n_emitted, r->stopped);
     if (!tail.empty() && r->cb.on_chunk) r->cb.on_chunk(r->user, (const uint8_t*)tail.data(), tail.size());
   }
   if (r->cb.on_done) r->cb.on_done(r->user, rc, msg ? msg : "");
@@ -481,6 +481,13 @@ static void finish_req(mq_worker* w, mq_req* r, int rc, const char* msg) {
 
 static void emit_token(mq_worker* w, mq_req* r, int tok) {
   if (r->finished) return;
+  if (!r->rq.ignore_eos && w->cfg.eos_token_id > 0 && tok == w->cfg.eos_token_id) {
+    // end of sequence: the EOS token itself is not relayed; steps already in flight for this slot are discarded
+    // (their tokens arrive for a finished request) and the slot / pages are free for the next admission
+    r->stopped = true;
+    finish_req(w, r, 0, nullptr);
+    return;
+  }
   if (r->n_emitted == 0) r->t_first = Clock::now();
   r->n_emitted++;
   send_status(r);

@@ -59,6 +59,7 @@ struct mq_req {
   std::atomic<bool> cancel{false};
   bool status_sent = false;
   bool finished = false;
+  bool stopped = false;  // ended on the model's EOS token rather than on max_new
   int done_rc = 0;
   std::string agg;       // stream=0: aggregated text
   std::vector<int32_t> agg_tokens;

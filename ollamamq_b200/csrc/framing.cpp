@@ -299,7 +299,9 @@ void other_route_response(const std::string& path, const char* model, int* statu
   }
 }
 
-std::string frame_final(int endpoint, int stream, const char* model, const std::string& agg, int n_prompt, int n_gen) {
+std::string frame_final(int endpoint, int stream, const char* model, const std::string& agg, int n_prompt, int n_gen,
+                        bool stopped) {
+  const char* why = stopped ? "stop" : "length";  // EOS reached vs generation budget spent
   if (endpoint == MQ_EP_RAW_TOKENS) return stream ? std::string() : agg;
   const std::string m = json_escape(model), txt = json_escape(agg);
   std::string o;
@@ -308,18 +310,18 @@ std::string frame_final(int endpoint, int stream, const char* model, const std::
     o = "{\"model\":\"" + m + "\",\"created_at\":\"" + now_iso() + "\",";
     if (endpoint == MQ_EP_API_GENERATE) o += "\"response\":\"" + (stream ? std::string() : txt) + "\",";
     else o += "\"message\":{\"role\":\"assistant\",\"content\":\"" + (stream ? std::string() : txt) + "\"},";
-    snprintf(buf, sizeof(buf), "\"done\":true,\"done_reason\":\"length\",\"prompt_eval_count\":%d,\"eval_count\":%d}\n",
-             n_prompt, n_gen);
+    snprintf(buf, sizeof(buf), "\"done\":true,\"done_reason\":\"%s\",\"prompt_eval_count\":%d,\"eval_count\":%d}\n",
+             why, n_prompt, n_gen);
     return o + buf;
   }
   const bool chat = endpoint == MQ_EP_V1_CHAT;
   if (stream) {
     snprintf(buf, sizeof(buf),
              chat ? "data: {\"id\":\"chatcmpl-mq\",\"object\":\"chat.completion.chunk\",\"created\":%ld,\"model\":\"%s\","
-                    "\"choices\":[{\"index\":0,\"delta\":{},\"finish_reason\":\"length\"}]}\n\ndata: [DONE]\n\n"
+                    "\"choices\":[{\"index\":0,\"delta\":{},\"finish_reason\":\"%s\"}]}\n\ndata: [DONE]\n\n"
                   : "data: {\"id\":\"cmpl-mq\",\"object\":\"text_completion\",\"created\":%ld,\"model\":\"%s\","
-                    "\"choices\":[{\"text\":\"\",\"index\":0,\"finish_reason\":\"length\"}]}\n\ndata: [DONE]\n\n",
-             (long)time(nullptr), m.c_str());
+                    "\"choices\":[{\"text\":\"\",\"index\":0,\"finish_reason\":\"%s\"}]}\n\ndata: [DONE]\n\n",
+             (long)time(nullptr), m.c_str(), why);
     return buf;
   }
   snprintf(buf, sizeof(buf), "\"usage\":{\"prompt_tokens\":%d,\"completion_tokens\":%d,\"total_tokens\":%d}}", n_prompt,
@@ -327,10 +329,10 @@ std::string frame_final(int endpoint, int stream, const char* model, const std::
   if (chat)
     o = "{\"id\":\"chatcmpl-mq\",\"object\":\"chat.completion\",\"model\":\"" + m +
         "\",\"choices\":[{\"index\":0,\"message\":{\"role\":\"assistant\",\"content\":\"" + txt +
-        "\"},\"finish_reason\":\"length\"}],";
+        "\"},\"finish_reason\":\"" + std::string(why) + "\"}],";
   else
     o = "{\"id\":\"cmpl-mq\",\"object\":\"text_completion\",\"model\":\"" + m + "\",\"choices\":[{\"text\":\"" + txt +
-        "\",\"index\":0,\"finish_reason\":\"length\"}],";
+        "\",\"index\":0,\"finish_reason\":\"" + std::string(why) + "\"}],";
   return o + buf;
 }
 

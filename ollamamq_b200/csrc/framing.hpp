@@ -30,7 +30,8 @@ const char* content_type_for(int endpoint, int stream);
 std::string frame_token(int endpoint, const char* model, int tok);
 // MQ_EP_OTHER: what the backend answers on the non-generation routes (main.rs:92-112) without touching the GPU
 void other_route_response(const std::string& path, const char* model, int* status, std::string* ctype, std::string* body);
-std::string frame_final(int endpoint, int stream, const char* model, const std::string& agg, int n_prompt, int n_gen);
+std::string frame_final(int endpoint, int stream, const char* model, const std::string& agg, int n_prompt, int n_gen,
+                        bool stopped = false);  // stopped: done_reason / finish_reason "stop" (EOS) instead of "length"
 
 // ---- embeddings (/api/embed, /api/embeddings, /v1/embeddings)
 struct ParsedEmbed {

@@ -249,7 +249,7 @@ void serve_connection(mq_http_server* s, int fd, std::string ip) {
     const bool mentions_stream =
         !rq.body.empty() && std::string((const char*)rq.body.data(), rq.body.size()).find("\"stream\"") != std::string::npos;
     q.stream = mentions_stream ? -1 : ((q.endpoint == MQ_EP_V1_CHAT || q.endpoint == MQ_EP_V1_COMPLETIONS) ? 0 : 1);
-    q.ignore_eos = 1;
+    q.ignore_eos = 0;  // generation ends at the model's EOS when it has one (cfg.eos_token_id); random-init models have none
     mq_callbacks cb{cb_status, cb_chunk, cb_done};
     uint64_t task = 0;
     const int rc = mq_dispatcher_submit(s->d, rq.has_user ? rq.user.c_str() : nullptr, ip.c_str(), &q, &cb, &pend, &task);

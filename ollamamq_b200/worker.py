@@ -16,7 +16,7 @@ ENDPOINT_OF_PATH = {"/api/generate": EP_API_GENERATE, "/api/chat": EP_API_CHAT,
 
 
 def model_cfg(geom: dict, max_batch=64, max_seq=1024, max_prefill_tokens=2048, kv_pages=0, use_graphs=1,
-              use_pdl=0, model_name="random-init") -> _lib.ModelCfg:
+              use_pdl=0, model_name="random-init", eos_token_id=0) -> _lib.ModelCfg:
     c = _lib.ModelCfg()
     for k in ("vocab", "hidden", "ffn", "n_layers", "n_q_heads", "n_kv_heads", "head_dim"):
         setattr(c, k, int(geom[k]))
@@ -25,6 +25,7 @@ def model_cfg(geom: dict, max_batch=64, max_seq=1024, max_prefill_tokens=2048, k
     c.rms_eps = float(geom.get("rms_eps", 1e-5))
     c.max_batch, c.max_seq, c.max_prefill_tokens = max_batch, max_seq, max_prefill_tokens
     c.kv_pages, c.use_graphs, c.use_pdl = kv_pages, use_graphs, use_pdl
+    c.eos_token_id = int(geom.get("eos_token_id", eos_token_id))
     c.model_name = model_name.encode()[:63]
     return c
 
@@ -96,11 +97,11 @@ class Stream:
 
 def make_request(endpoint=EP_RAW_TOKENS, prompt_tokens: Optional[Sequence[int]] = None, body: Optional[bytes] = None,
                  max_new_tokens=16, stream=1, timeout_ms=0, path: Optional[str] = None, temperature=0.0, top_k=0,
-                 top_p=0.0, seed=0):
+                 top_p=0.0, seed=0, ignore_eos=1):
     r = _lib.Request()
     if path is not None:
         r.path = path.encode()
-    r.endpoint, r.stream, r.max_new_tokens, r.ignore_eos, r.timeout_ms = endpoint, stream, max_new_tokens, 1, timeout_ms
+    r.endpoint, r.stream, r.max_new_tokens, r.ignore_eos, r.timeout_ms = endpoint, stream, max_new_tokens, ignore_eos, timeout_ms
     r.temperature, r.top_k, r.top_p, r.seed = float(temperature), int(top_k), float(top_p), int(seed)
     keep = []
     if body is not None:

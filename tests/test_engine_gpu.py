@@ -542,3 +542,32 @@ def test_sampling_temperature_topk_seed_through_the_engine():
         s3.wait(60)
         r1, r2, r3 = (json.loads(x.body)["response"] for x in (s1, s2, s3))
         assert r1 == r2 and r1 != r3
+
+
+def test_eos_token_ends_generation_with_done_reason_stop():
+    """cfg.eos_token_id: a request without ignore_eos ends when that token is drawn - it is not relayed, the final
+    frame says "stop" instead of "length", and the slot is free again."""
+    cfg = MID
+    w = R.make_weights(cfg, seed=43, device="cuda")
+    prompt = torch.randint(0, cfg["vocab"], (30,), generator=torch.Generator().manual_seed(8)).tolist()
+    with _open(cfg, w, max_batch=4) as wk:
+        full = wk.generate(prompt, 20)
+    stop_at = 7
+    eos = full[stop_at]
+    assert eos not in full[:stop_at] and eos > 0
+    with _open(dict(cfg, eos_token_id=eos), w, max_batch=4) as wk:
+        s = wk.submit(mq.Stream(), prompt_tokens=prompt, max_new_tokens=20, ignore_eos=0)
+        s.wait(60)
+        assert s.rc == 0 and s.tokens() == full[:stop_at]
+        mq.lib.mq_req_release(s.handle)
+        s = wk.submit(mq.Stream(), prompt_tokens=prompt, max_new_tokens=20, ignore_eos=1)   # benchmark mode runs on
+        s.wait(60)
+        assert s.tokens() == full
+        mq.lib.mq_req_release(s.handle)
+        body = json.dumps({"model": "m", "prompt": prompt, "stream": False, "options": {"num_predict": 20}}).encode()
+        s = wk.submit(mq.Stream(), endpoint=3, body=body, max_new_tokens=0, stream=-1, ignore_eos=0)
+        s.wait(60)
+        js = json.loads(s.body)
+        assert js["choices"][0]["finish_reason"] == "stop" and js["usage"]["completion_tokens"] == stop_at
+        oc = wk.occupancy()
+        assert oc["active_slots"] == 0 and oc["free_pages"] == oc["total_pages"]
