@@ -348,6 +348,14 @@ int mq_debug_attn_decode(const void* q, const void* k_cache, const void* v_cache
  * ~(last CTA end)}; untouched slots read as all-ones.  Slots: 1 + 8*layer + {0 norm, 1 qkv, 2 rope, 3 attention,
  * 4 o-proj, 5 norm, 6 gate/up, 7 down}; 510 final norm, 511 LM head.  Returns the slot count copied (<= 512). */
 int mq_debug_trace_read(mq_worker* w, unsigned long long* out, int32_t max_slots);
+/* host-only test ABI of the request parsers / response framers (no GPU): each returns the bytes needed incl. the
+ * terminator and writes a JSON description when it fits                                                   */
+long long mq_debug_parse_body(int32_t endpoint, const uint8_t* body, size_t len, int32_t vocab, char* out, size_t cap);
+long long mq_debug_parse_embed(const uint8_t* body, size_t len, int32_t vocab, int32_t max_len, char* out, size_t cap);
+long long mq_debug_frame_embeddings(const char* path, const char* model, const float* emb, int32_t n, int32_t dim,
+                                    int32_t n_tokens, char* out, size_t cap);
+long long mq_debug_frame_final(int32_t endpoint, int32_t stream, const char* model, const char* agg, int32_t n_prompt,
+                               int32_t n_gen, int32_t stopped, char* out, size_t cap);
 /* the sampler kernel on given logits: per-row controls (device arrays, row == slot), counter = RNG position  */
 int mq_debug_sample(const float* logits, int rows, int V, int ldl, int* out_tokens, const float* temperature,
                     const int* top_k, const float* top_p, const unsigned long long* seed, const int* counter);

@@ -187,6 +187,11 @@ _sig("mq_encoder_get_stats", C.c_int, [P, P])
 _sig("mq_encoder_embed", C.c_int, [P, P, P, C.c_int32, P])
 _sig("mq_encoder_submit", C.c_int, [P, P, P, P, P])
 _sig("mq_debug_trace_read", C.c_int, [P, P, C.c_int])
+_sig("mq_debug_parse_body", C.c_longlong, [C.c_int32, P, C.c_size_t, C.c_int32, P, C.c_size_t])
+_sig("mq_debug_parse_embed", C.c_longlong, [P, C.c_size_t, C.c_int32, C.c_int32, P, C.c_size_t])
+_sig("mq_debug_frame_embeddings", C.c_longlong, [C.c_char_p, C.c_char_p, P, C.c_int32, C.c_int32, C.c_int32, P, C.c_size_t])
+_sig("mq_debug_frame_final", C.c_longlong, [C.c_int32, C.c_int32, C.c_char_p, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, P,
+                                              C.c_size_t])
 _sig("mq_debug_sample", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, P, P, P, P, P])
 _sig("mq_debug_argmax", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, P, P, P, P])
 _sig("mq_debug_init_normal", C.c_int, [P, C.c_ulonglong, C.c_ulonglong, C.c_float])

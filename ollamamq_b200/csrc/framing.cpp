@@ -448,3 +448,54 @@ std::string frame_embeddings(const std::string& path, const char* model, const f
 }
 
 }  // namespace mq
+
+// ------------------------------------------------------------------ host-only test ABI for the parsers / framers
+extern "C" {
+static long long emit_json(const std::string& o, char* out, size_t cap) {
+  if (out && cap > o.size()) memcpy(out, o.c_str(), o.size() + 1);
+  return (long long)o.size() + 1;
+}
+long long mq_debug_parse_body(int32_t endpoint, const uint8_t* body, size_t len, int32_t vocab, char* out, size_t cap) {
+  using namespace mq;
+  ParsedBody pb;
+  const bool ok = parse_body(std::string((const char*)body, body ? len : 0), endpoint, &pb);
+  std::string toks = "[";
+  const std::vector<int32_t> t = !pb.tokens.empty() ? pb.tokens : byte_tokenize(pb.text, vocab > 0 ? vocab : 256);
+  for (size_t i = 0; i < t.size(); ++i) toks += (i ? "," : "") + std::to_string(t[i]);
+  toks += "]";
+  char b[512];
+  snprintf(b, sizeof b, "{\"ok\":%s,\"has_stream\":%s,\"stream\":%s,\"num_predict\":%d,\"has_temperature\":%s,\"temperature\":%.9g,"
+           "\"has_top_k\":%s,\"top_k\":%lld,\"has_top_p\":%s,\"top_p\":%.9g,\"has_seed\":%s,\"seed\":%llu,\"n_text\":%zu,",
+           ok ? "true" : "false", pb.has_stream ? "true" : "false", pb.stream ? "true" : "false", pb.num_predict,
+           pb.has_temperature ? "true" : "false", pb.temperature, pb.has_top_k ? "true" : "false", pb.top_k,
+           pb.has_top_p ? "true" : "false", pb.top_p, pb.has_seed ? "true" : "false", pb.seed, pb.text.size());
+  return emit_json(std::string(b) + "\"model\":\"" + json_escape(pb.model) + "\",\"tokens\":" + toks + "}", out, cap);
+}
+long long mq_debug_parse_embed(const uint8_t* body, size_t len, int32_t vocab, int32_t max_len, char* out, size_t cap) {
+  using namespace mq;
+  ParsedEmbed pe;
+  const bool ok = parse_embed_body(std::string((const char*)body, body ? len : 0), &pe);
+  std::string o = std::string("{\"ok\":") + (ok ? "true" : "false") + ",\"model\":\"" + json_escape(pe.model) + "\",\"seqs\":[";
+  bool first = true;
+  auto put = [&](const std::vector<int32_t>& t) {
+    o += first ? "[" : ",[";
+    first = false;
+    for (size_t i = 0; i < t.size(); ++i) o += (i ? "," : "") + std::to_string(t[i]);
+    o += "]";
+  };
+  for (auto& t : pe.texts) put(embed_tokenize(t, vocab, max_len));
+  for (auto& t : pe.token_seqs) put(t);
+  return emit_json(o + "]}", out, cap);
+}
+long long mq_debug_frame_embeddings(const char* path, const char* model, const float* emb, int32_t n, int32_t dim,
+                                    int32_t n_tokens, char* out, size_t cap) {
+  return emit_json(mq::frame_embeddings(path ? path : "/api/embed", model ? model : "", emb, n, dim, n_tokens), out, cap);
+}
+long long mq_debug_frame_final(int32_t endpoint, int32_t stream, const char* model, const char* agg, int32_t n_prompt,
+                               int32_t n_gen, int32_t stopped, char* out, size_t cap) {
+  return emit_json(mq::frame_final(endpoint, stream, model ? model : "", agg ? agg : "", n_prompt, n_gen, stopped != 0), out, cap);
+}
+}  // extern "C"
+
+namespace mq {
+}  // namespace mq
