@@ -132,3 +132,31 @@ def test_client_gone_while_queued_is_dropped():
         assert (st["processed"], st["dropped"]) == (0, 1)             # popped, dropped at pre-flight (:278-280)
     finally:
         s.close()
+
+
+def test_malformed_requests_do_not_take_the_server_down(srv):
+    """Garbage on the wire: every connection is answered or closed, and the server keeps serving."""
+    import random
+    rnd = random.Random(1)
+    blobs = [b"\r\n\r\n", b"GET\r\n\r\n", b"GET /health\r\n\r\n", b"POST /api/chat HTTP/1.1\r\nContent-Length: 99999999999\r\n\r\n",
+             b"POST /api/chat HTTP/1.1\r\nTransfer-Encoding: chunked\r\n\r\n5\r\nhello\r\n0\r\n\r\n",
+             b"POST /api/chat HTTP/1.1\r\nContent-Length: -5\r\n\r\n", b"\x00" * 3000, b"A" * 70000,
+             b"POST /api/chat HTTP/1.1\r\nX-User-ID: " + b"u" * 5000 + b"\r\nContent-Length: 2\r\n\r\n{}",
+             b"POST /api/embed HTTP/1.1\r\nContent-Length: 7\r\n\r\n\xff\xfe{\"a\":"]
+    blobs += [bytes(rnd.randrange(256) for _ in range(rnd.randrange(1, 600))) + b"\r\n\r\n" for _ in range(40)]
+    for blob in blobs:
+        s = socket.create_connection(("127.0.0.1", srv.port), timeout=5)
+        try:
+            s.sendall(blob)
+            s.shutdown(socket.SHUT_WR)
+            s.settimeout(5)
+            while s.recv(65536):
+                pass
+        except (ConnectionError, socket.timeout, OSError):
+            pass
+        finally:
+            s.close()
+    st, _, body = srv.request("GET", "/health")
+    assert st == 200 and body == b"OK"
+    st, _, _ = srv.request("POST", "/api/chat", body=b'{"model":"m","messages":[]}', headers={"X-User-ID": "after-fuzz"})
+    assert st == 200
