@@ -1146,6 +1146,30 @@ __device__ uint32_t radix_threshold(const float* __restrict__ lp, int V, uint32_
   return prefix;
 }
 
+
+// ---- fast top-k path (0 < k <= 1024): two passes over the row instead of the radix walk's eight.
+//   a. every thread keeps the maximum of its strided share of the row; the k-th largest of those 1024 maxima, T0, is a
+//      lower bound of the k-th largest logit (k distinct elements are >= T0);
+//   b. elements >= T0 are compacted into shared memory (a few times k of them for any distribution that is not flat),
+//   c. sorted there (bitonic, value descending / token id ascending, so the result does not depend on arrival order),
+//   d. cut at k (ties at the cut stay in), then at the top-p mass, and the Gumbel-max draw runs over what is left.
+// More candidates than kSampleCand (a nearly constant row) falls back to the radix walk.
+constexpr int kSampleCand = 4096;
+__device__ __forceinline__ bool cand_before(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
+__device__ void bitonic_desc(float* val, int* idx, int n /* power of two */) {
+  for (int size = 2; size <= n; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < n / 2; t += blockDim.x) {
+        const int pos = 2 * t - (t & (stride - 1)), q = pos + stride;
+        const bool desc = (pos & size) == 0;
+        const float va = val[pos], vb = val[q];
+        const int ia = idx[pos], ib = idx[q];
+        if (cand_before(va, ia, vb, ib) != desc) { val[pos] = vb; val[q] = va; idx[pos] = ib; idx[q] = ia; }
+      }
+      __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ logits, int V, int ldl,
                                                       int* __restrict__ out_tokens, const int* __restrict__ dst_slot,
                                                       int* __restrict__ cur_token, int* __restrict__ pos_inc,
@@ -1156,6 +1180,9 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
   __shared__ __align__(8) uint32_t bcast[4];
   __shared__ float sb[32];
   __shared__ int si[32];
+  __shared__ float cval[kSampleCand];
+  __shared__ int cidx[kSampleCand];
+  __shared__ int n_cand, n_keep_s;
   const int row = blockIdx.x;
   const int slot = dst_slot ? dst_slot[row] : row;
   const float* lp = logits + (size_t)row * ldl;
@@ -1171,6 +1198,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
     // row maximum (for the mass scale)
     float mx = -INFINITY;
     for (int i = threadIdx.x; i < V; i += blockDim.x) mx = fmaxf(mx, lp[i]);
+    const float thread_max = mx;  // maximum of this thread's strided share (fast top-k path)
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
@@ -1182,8 +1210,75 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
     for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mx = fmaxf(mx, sb[w]);
     __syncthreads();
     const int k = ctl.top_k ? ctl.top_k[slot] : 0;
-    if (k > 0 && k < V) thr_key = radix_threshold<false>(lp, V, 0u, (unsigned long long)k, mx, inv_t, hist, bcast);
     const float p = ctl.top_p ? ctl.top_p[slot] : 1.f;
+    bool fast_done = false;
+    if (k > 0 && k <= 1024 && k < V && blockDim.x == 1024) {
+      cval[threadIdx.x] = thread_max;
+      cidx[threadIdx.x] = threadIdx.x;
+      if (threadIdx.x == 0) n_cand = 0;
+      __syncthreads();
+      bitonic_desc(cval, cidx, 1024);
+      const float t0 = cval[k - 1];
+      __syncthreads();
+      for (int i = threadIdx.x; i < V; i += blockDim.x) {
+        const float l = lp[i];
+        if (l >= t0) {
+          const int at = atomicAdd(&n_cand, 1);
+          if (at < kSampleCand) { cval[at] = l; cidx[at] = i; }
+        }
+      }
+      __syncthreads();
+      const int nc = n_cand;
+      if (nc <= kSampleCand) {
+        int n2 = 2;
+        while (n2 < nc) n2 <<= 1;
+        for (int i = nc + threadIdx.x; i < n2; i += blockDim.x) { cval[i] = -INFINITY; cidx[i] = 0x7fffffff; }
+        __syncthreads();
+        bitonic_desc(cval, cidx, n2);
+        if (threadIdx.x == 0) {
+          int nk = k;                                                    // nc >= k by construction
+          while (nk < nc && cval[nk] == cval[k - 1]) ++nk;               // ties at the cut stay in
+          if (p > 0.f && p < 1.f) {
+            float total = 0.f;
+            for (int j = 0; j < nk; ++j) total += __expf((cval[j] - mx) * inv_t);
+            const float target = p * total;
+            float cum = 0.f;
+            int n = 0;
+            while (n < nk) { cum += __expf((cval[n] - mx) * inv_t); ++n; if (cum >= target) break; }
+            while (n < nk && cval[n] == cval[n - 1]) ++n;                 // same rule for the nucleus edge
+            nk = n;
+          }
+          n_keep_s = nk;
+        }
+        __syncthreads();
+        const int nk = n_keep_s;
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        for (int j = threadIdx.x; j < nk; j += blockDim.x) {
+          const float sc = cval[j] * inv_t + gumbel_noise(seed, counter, cidx[j]);
+          if (sc > best || (sc == best && cidx[j] < bi)) { best = sc; bi = cidx[j]; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if ((threadIdx.x & 31) == 0) { sb[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (sb[w] > best || (sb[w] == best && si[w] < bi)) { best = sb[w]; bi = si[w]; }
+          out_tokens[row] = bi;
+          if (cur_token) cur_token[slot] = bi;
+          if (pos_inc && (!active || active[slot])) pos_inc[slot] += 1;
+        }
+        fast_done = true;
+      }
+      __syncthreads();
+    }
+    if (fast_done) return;
+    if (k > 0 && k < V) thr_key = radix_threshold<false>(lp, V, 0u, (unsigned long long)k, mx, inv_t, hist, bcast);
     if (p > 0.f && p < 1.f) {
       // total mass of what top-k kept, in the same fixed point
       for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0ull;
