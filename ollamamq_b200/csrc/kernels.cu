@@ -1212,23 +1212,37 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
     const int k = ctl.top_k ? ctl.top_k[slot] : 0;
     const float p = ctl.top_p ? ctl.top_p[slot] : 1.f;
     bool fast_done = false;
-    if (k > 0 && k <= 1024 && k < V && blockDim.x == 1024) {
+    // k_eff: the cut used to bound the candidate set.  With top-p alone (OpenAI-style requests) the 256 largest
+    // thread maxima bound it: the candidates are then the largest elements of the row in order, so if the nucleus
+    // p * Z (Z over the WHOLE row) closes inside them it is exact; otherwise the radix walk below takes over.
+    const bool p_on = p > 0.f && p < 1.f;
+    // (256, not 1024: the 1024-th largest of 1024 thread maxima is the SMALLEST one and admits ~7 % of the row)
+    const int k_eff = (k > 0 && k <= 1024 && k < V) ? k : ((k <= 0 || k >= V) && p_on && V > 1024 ? 256 : 0);
+    const bool p_only = k_eff > 0 && !(k > 0 && k < V);
+    if (k_eff > 0 && blockDim.x == 1024) {
       cval[threadIdx.x] = thread_max;
       cidx[threadIdx.x] = threadIdx.x;
       if (threadIdx.x == 0) n_cand = 0;
       __syncthreads();
       bitonic_desc(cval, cidx, 1024);
-      const float t0 = cval[k - 1];
+      const float t0 = cval[k_eff - 1];
       __syncthreads();
+      float zpart = 0.f;  // top-p alone: mass of the whole row (fixed order per thread, fixed tree below)
       for (int i = threadIdx.x; i < V; i += blockDim.x) {
         const float l = lp[i];
+        if (p_only) zpart += __expf((l - mx) * inv_t);
         if (l >= t0) {
           const int at = atomicAdd(&n_cand, 1);
           if (at < kSampleCand) { cval[at] = l; cidx[at] = i; }
         }
       }
+      zpart = warp_sum(zpart);
+      if ((threadIdx.x & 31) == 0) sb[threadIdx.x >> 5] = zpart;
       __syncthreads();
+      float z_row = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) z_row += sb[w];
       const int nc = n_cand;
+      __syncthreads();
       if (nc <= kSampleCand) {
         int n2 = 2;
         while (n2 < nc) n2 <<= 1;
@@ -1236,22 +1250,68 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
         __syncthreads();
         bitonic_desc(cval, cidx, n2);
         if (threadIdx.x == 0) {
-          int nk = k;                                                    // nc >= k by construction
-          while (nk < nc && cval[nk] == cval[k - 1]) ++nk;               // ties at the cut stay in
-          if (p > 0.f && p < 1.f) {
-            float total = 0.f;
-            for (int j = 0; j < nk; ++j) total += __expf((cval[j] - mx) * inv_t);
-            const float target = p * total;
-            float cum = 0.f;
-            int n = 0;
-            while (n < nk) { cum += __expf((cval[n] - mx) * inv_t); ++n; if (cum >= target) break; }
-            while (n < nk && cval[n] == cval[n - 1]) ++n;                 // same rule for the nucleus edge
-            nk = n;
+          int nk = nc;
+          if (!p_only) {
+            nk = k;                                                      // nc >= k by construction
+            while (nk < nc && cval[nk] == cval[k - 1]) ++nk;             // ties at the cut stay in
           }
           n_keep_s = nk;
         }
         __syncthreads();
+        if (p_on) {
+          // nucleus edge by a block-wide prefix sum over the sorted candidates: thread t owns `per` consecutive ones,
+          // partial sums meet through a warp scan + one shared-memory step (fixed order: reproducible)
+          const int nk0 = n_keep_s;
+          const int per = (nk0 + (int)blockDim.x - 1) / (int)blockDim.x;  // <= kSampleCand / 1024
+          float loc[kSampleCand / 1024];
+          float mine = 0.f;
+#pragma unroll
+          for (int j = 0; j < kSampleCand / 1024; ++j) {
+            const int at = threadIdx.x * per + j;
+            loc[j] = (j < per && at < nk0) ? __expf((cval[at] - mx) * inv_t) : 0.f;
+            mine += loc[j];
+          }
+          float inc = mine;  // inclusive scan inside the warp
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const float v = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)(threadIdx.x & 31) >= o) inc += v;
+          }
+          __syncthreads();  // sb is free again
+          if ((threadIdx.x & 31) == 31) sb[threadIdx.x >> 5] = inc;
+          __syncthreads();
+          float before = 0.f, total = 0.f;
+          for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+            if (w < (int)(threadIdx.x >> 5)) before += sb[w];
+            total += sb[w];
+          }
+          const float target = p * (p_only ? z_row : total);
+          float cum = before + inc - mine;  // mass of everything in front of this thread's share
+          __syncthreads();
+          if (threadIdx.x == 0) n_keep_s = 0x7fffffff;
+          __syncthreads();
+#pragma unroll
+          for (int j = 0; j < kSampleCand / 1024; ++j) {
+            const int at = threadIdx.x * per + j;
+            if (j < per && at < nk0) {
+              if (cum < target && cum + loc[j] >= target) atomicMin(&n_keep_s, at + 1);
+              cum += loc[j];
+            }
+          }
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            int n = n_keep_s;
+            if (n == 0x7fffffff) {
+              n = p_only ? -1 : nk0;                                      // top-p alone and the nucleus is wider: radix walk
+            } else {
+              while (n < nk0 && cval[n] == cval[n - 1]) ++n;              // ties at the nucleus edge stay in
+            }
+            n_keep_s = n;
+          }
+          __syncthreads();
+        }
         const int nk = n_keep_s;
+        if (nk >= 0) {
         float best = -INFINITY;
         int bi = 0x7fffffff;
         for (int j = threadIdx.x; j < nk; j += blockDim.x) {
@@ -1274,12 +1334,13 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
           if (pos_inc && (!active || active[slot])) pos_inc[slot] += 1;
         }
         fast_done = true;
+        }
       }
       __syncthreads();
     }
     if (fast_done) return;
     if (k > 0 && k < V) thr_key = radix_threshold<false>(lp, V, 0u, (unsigned long long)k, mx, inv_t, hist, bcast);
-    if (p > 0.f && p < 1.f) {
+    if (p_on) {
       // total mass of what top-k kept, in the same fixed point
       for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0ull;
       __syncthreads();

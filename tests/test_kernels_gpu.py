@@ -419,7 +419,8 @@ def test_sampler_greedy_topk1_and_determinism():
 
 @pytest.mark.parametrize("V,temp,top_k,top_p", [(128256, 0.7, 50, 0.0), (32064, 1.0, 0, 0.0), (5000, 0.8, 40, 0.9),
                                                  (128256, 1.2, 0, 0.95), (4096, 0.5, 7, 0.5),
-                                                 (128256, 0.9, 2000, 0.0), (32064, 0.9, 1500, 0.8)])  # k > 1024: radix walk
+                                                 (128256, 0.9, 2000, 0.0), (32064, 0.9, 1500, 0.8),   # k > 1024: radix walk
+                                                 (128256, 0.4, 0, 0.5), (32064, 0.3, 0, 0.9)])        # top-p alone, nucleus inside the candidates
 def test_sampler_matches_the_oracle(V, temp, top_k, top_p):
     from oracle import sampler_ref as S
     m = _lib()

@@ -1,3 +1,4 @@
+"""Sampler kernel timings (64 rows x 128 256 logits): greedy vs the stochastic paths.  python tools/sampler_bench.py"""
 import sys, ctypes as C
 sys.path.insert(0, '/root/repo')
 import torch, ollamamq_b200 as m
@@ -21,3 +22,6 @@ print("sample_kernel greedy %.1f us" % t(lambda: m.lib.mq_debug_sample(P(logits)
 print("sample_kernel T=0.8 top_k=40 top_p=0.9 %.1f us" % t(lambda: m.lib.mq_debug_sample(P(logits), rows, V, V, P(out), P(temp1), P(k), P(p), P(seed), P(cnt))))
 k0 = torch.zeros(rows, dtype=torch.int32, device='cuda'); p0 = torch.zeros(rows, device='cuda')
 print("sample_kernel T=0.8 only %.1f us" % t(lambda: m.lib.mq_debug_sample(P(logits), rows, V, V, P(out), P(temp1), P(k0), P(p0), P(seed), P(cnt))))
+sharp = logits * 10
+print("sample_kernel T=0.8 top_p=0.9 alone, peaked row (nucleus inside the candidate set) %.1f us" % t(lambda: m.lib.mq_debug_sample(P(sharp), rows, V, V, P(out), P(temp1), P(k0), P(p), P(seed), P(cnt))))
+print("sample_kernel T=0.8 top_p=0.9 alone, flat row (radix walk) %.1f us" % t(lambda: m.lib.mq_debug_sample(P(logits), rows, V, V, P(out), P(temp1), P(k0), P(p), P(seed), P(cnt))))
