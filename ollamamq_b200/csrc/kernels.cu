@@ -1109,12 +1109,18 @@ constexpr float kMassScale = 1099511627776.0f;  // 2^40
 // Radix walk from the most significant byte: afterwards `prefix` is the key of the threshold element.
 //   MASS == false: the K-th largest key (count walk).   MASS == true: the largest key t with mass{key >= t} >= target.
 // Only keys >= floor_key take part.  All threads of the block call this; the result is returned to all of them.
+// `hist` holds kHistCopies private copies of the 256 bins, picked by lane: the top byte of a float (sign + 7 exponent
+// bits) sends a whole row into a handful of bins, and with one copy every atomic of a warp hit the same address
+// (r01: 1.78 ms per step for this walk; the copies are folded before the bins are read).
+constexpr int kHistCopies = 16;
 template <bool MASS>
 __device__ uint32_t radix_threshold(const float* __restrict__ lp, int V, uint32_t floor_key, unsigned long long target,
-                                    float mx, float inv_t, unsigned long long* hist /* smem [256] */, uint32_t* bcast) {
+                                    float mx, float inv_t, unsigned long long* hist /* smem [kHistCopies][256] */,
+                                    uint32_t* bcast) {
   uint32_t prefix = 0, mask = 0;
+  unsigned long long* mine = hist + (threadIdx.x & (kHistCopies - 1)) * 256;
   for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0ull;
+    for (int i = threadIdx.x; i < 256 * kHistCopies; i += blockDim.x) hist[i] = 0ull;
     __syncthreads();
     for (int i = threadIdx.x; i < V; i += blockDim.x) {
       const float l = lp[i];
@@ -1122,8 +1128,15 @@ __device__ uint32_t radix_threshold(const float* __restrict__ lp, int V, uint32_
       if (k >= floor_key && (k & mask) == prefix) {
         unsigned long long w = 1ull;
         if (MASS) w = (unsigned long long)(kMassScale * __expf((l - mx) * inv_t));
-        atomicAdd(&hist[(k >> shift) & 255u], w);
+        atomicAdd(&mine[(k >> shift) & 255u], w);
       }
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+      unsigned long long sum = 0ull;
+#pragma unroll
+      for (int c = 0; c < kHistCopies; ++c) sum += hist[c * 256 + threadIdx.x];
+      hist[threadIdx.x] = sum;  // copy 0 now holds the folded bins (each thread reads its column before writing it)
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1176,12 +1189,15 @@ __global__ void __launch_bounds__(1024) sample_kernel(const float* __restrict__ 
                                                       const int* __restrict__ active, const SampleCtl ctl) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ unsigned long long hist[256];
+  // one 32 KiB pool: the candidate arrays of the fast path, or the kHistCopies histograms of the radix walk
+  __shared__ __align__(16) unsigned char pool[kSampleCand * 8];
+  static_assert(kSampleCand * 8 >= kHistCopies * 256 * 8, "the histogram copies alias the candidate arrays");
+  float* cval = reinterpret_cast<float*>(pool);
+  int* cidx = reinterpret_cast<int*>(pool + kSampleCand * 4);
+  unsigned long long* hist = reinterpret_cast<unsigned long long*>(pool);
   __shared__ __align__(8) uint32_t bcast[4];
   __shared__ float sb[32];
   __shared__ int si[32];
-  __shared__ float cval[kSampleCand];
-  __shared__ int cidx[kSampleCand];
   __shared__ int n_cand, n_keep_s;
   const int row = blockIdx.x;
   const int slot = dst_slot ? dst_slot[row] : row;
