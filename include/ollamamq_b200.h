@@ -274,6 +274,9 @@ int mq_dispatcher_submit(mq_dispatcher* d, const char* user, const char* ip, con
 mq_sched* mq_dispatcher_sched(mq_dispatcher* d); /* borrowed; guarded by the dispatcher's lock            */
 int mq_dispatcher_set_vip(mq_dispatcher* d, const char* user);
 int mq_dispatcher_set_boost(mq_dispatcher* d, const char* user);
+/* EXTENSION (BASELINE config 3, "2 VIP + 4 Boost"): sets instead of the reference's single slots, see mq_sched_add_* */
+int mq_dispatcher_add_vip(mq_dispatcher* d, const char* user);
+int mq_dispatcher_add_boost(mq_dispatcher* d, const char* user);
 int mq_dispatcher_block_user(mq_dispatcher* d, const char* user, int32_t blocked);   /* :127-153 */
 int mq_dispatcher_block_ip(mq_dispatcher* d, const char* ip, int32_t blocked);       /* :117-144 */
 /* dispatch log: (user, user_seq, backend) of every dispatch so far, in order — the parity observable     */

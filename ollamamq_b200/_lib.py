@@ -176,6 +176,8 @@ _sig("mq_worker_get_occupancy", C.c_int, [P, P])
 _sig("mq_debug_sched_bench", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, P])
 _sig("mq_dispatcher_snapshot_json", C.c_longlong, [P, P, C.c_size_t])
 _sig("mq_dispatcher_attach_encoder", C.c_int, [P, C.c_int32, P])
+_sig("mq_dispatcher_add_vip", C.c_int, [P, C.c_char_p])
+_sig("mq_dispatcher_add_boost", C.c_int, [P, C.c_char_p])
 _sig("mq_dispatcher_set_timeout", C.c_int, [P, C.c_uint32])
 _sig("mq_encoder_open", C.c_int, [C.c_int32, P, P])
 _sig("mq_encoder_close", None, [P])

@@ -371,6 +371,19 @@ int mq_dispatcher_new(mq_worker** workers, int32_t n_workers, int32_t capacity_o
   return *out ? MQ_OK : MQ_ERR_NOMEM;
 }
 
+int mq_dispatcher_add_vip(mq_dispatcher* d, const char* user) {  // EXTENSION (BASELINE config 3): see mq_sched_add_vip
+  if (!d || !user) return MQ_ERR_INVAL;
+  std::lock_guard<std::mutex> g(d->mu);
+  d->sched->s.add_vip(user);
+  return MQ_OK;
+}
+int mq_dispatcher_add_boost(mq_dispatcher* d, const char* user) {
+  if (!d || !user) return MQ_ERR_INVAL;
+  std::lock_guard<std::mutex> g(d->mu);
+  d->sched->s.add_boost(user);
+  return MQ_OK;
+}
+
 int mq_dispatcher_set_timeout(mq_dispatcher* d, uint32_t timeout_ms) {
   if (!d) return MQ_ERR_INVAL;
   std::lock_guard<std::mutex> g(d->mu);

@@ -313,6 +313,12 @@ class Dispatcher:
     def set_boost(self, user):
         check(lib.mq_dispatcher_set_boost(self._h, None if user is None else user.encode()))
 
+    def add_vip(self, user):      # extension: several VIPs (BASELINE config 3)
+        check(lib.mq_dispatcher_add_vip(self._h, user.encode()))
+
+    def add_boost(self, user):
+        check(lib.mq_dispatcher_add_boost(self._h, user.encode()))
+
     def block_user(self, user, blocked=True):
         check(lib.mq_dispatcher_block_user(self._h, user.encode(), 1 if blocked else 0))
 
