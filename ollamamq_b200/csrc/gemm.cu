@@ -323,6 +323,9 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   const int kbps = (kb + splits - 1) / splits;  // uneven split-K: the last plane may get fewer k-blocks
   if ((splits - 1) * kbps >= kb) return false;   // but never zero
   g->bn = gemm_pick_bn(T);
+  // one token tile, no split-K and fewer weight tiles than half the SMs (Phi-3 gate/up at 256 slots: 64 tiles): halve
+  // the token tile so two CTAs share each weight tile through L2 - same HBM bytes, twice the SMs streaming them
+  if (T > 128 && T <= 256 && splits == 1 && (n_out + kBlockM - 1) / kBlockM * 2 <= device_sm_count()) g->bn = 128;
   g->deep = !(g->bn <= 64 && decode_tiles_shallow());
   g->epi = epi;
   g->splits = splits;
