@@ -295,6 +295,7 @@ struct PassArgs {
   const int* tok;              // [T] token ids (device)
   const int* pos;              // [T]
   const int* slot_of_tok;      // [T]
+  int attn_stages = 0;         // decode: ring depth of the one-warp attention CTAs (0 = default)
 };
 
 
@@ -345,6 +346,7 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
     ap.max_pages = w->max_pages; ap.tiles = w->d_tiles; ap.pos = a.pos; ap.out = w->attn; ap.part_o = w->part_o;
     ap.part_ml = w->part_ml; ap.n_q = c.n_q_heads; ap.n_kv = c.n_kv_heads; ap.T = a.T;
     ap.n_splits = a.n_splits < 0 ? 1 : a.n_splits; ap.n_warps = a.n_splits < 0 ? -a.n_splits : 1;
+    ap.stages = a.attn_stages;
     ap.pf = pf_attn;
     ap.tr = tr(3);
     if (fuse_rope) {
@@ -618,11 +620,12 @@ static int launch_prefill(mq_worker* w, std::vector<PrefillItem>& items) {
 // ------------------------------------------------------------------------------------------------
 // decode step
 // ------------------------------------------------------------------------------------------------
-static int decode_body(mq_worker* w, int Bcap, int n_splits, int ring, uint64_t* nl) {
+static int decode_body(mq_worker* w, int Bcap, int n_splits, int attn_stages, int ring, uint64_t* nl) {
   const mq_model_cfg& c = w->cfg;
   PassPlans* pp = get_plans(w, Bcap, true);
   if (!pp) return MQ_ERR_CUDA;
   PassArgs a{Bcap, true, n_splits, 0, w->d_cur_token, w->d_pos, w->d_identity};
+  a.attn_stages = attn_stages;
   int rc = run_layers(w, a, pp, nl);
   if (rc) return rc;
   rc = run_head(w, true, w->d_identity, Bcap, pp, nl);
@@ -661,6 +664,11 @@ static int launch_decode(mq_worker* w) {
     while (nw > 1 && max_ctx / nw < 64) nw >>= 1;  // keep >= 4 pages per warp
     n_splits = nw > 1 ? -nw : 1;
   }
+  // ring depth of the one-warp CTAs: a warp that walks only a few pages gains nothing from a 6-stage (48 KiB) ring and
+  // loses residency (4 CTAs per SM); with many (slot, kv head) pairs and short contexts - Phi-3-mini, 256 users x 32
+  // tokens: 8192 CTAs of 3 pages - the kernel is a latency chain per CTA, so residency is what counts
+  const int pages_per_cta = (max_ctx + kPageSize - 1) / kPageSize;
+  const int attn_stages = pages_per_cta <= 2 ? 2 : pages_per_cta <= 4 ? 3 : pages_per_cta <= 8 ? 4 : 6;
   if (const char* e = getenv("MQ_ATTN_SPLITS")) {  // experiments: 1..8 grid-level, -2 / -4 / -8 in-CTA
     const int v = atoi(e);
     if (v == -2 || v == -4 || v == -8 || (v >= 1 && v <= kMaxDecodeSplits)) n_splits = v;
@@ -677,7 +685,7 @@ static int launch_decode(mq_worker* w) {
   bool graph_launched = false;
   if (w->cfg.use_graphs) {
     // graphs always write their tokens to ring row 0's alias at the end of the ring buffer (fixed address)
-    const long long key = (long long)Bcap * 1024 + (n_splits + 16);
+    const long long key = ((long long)Bcap * 1024 + (n_splits + 16)) * 8 + attn_stages;
     auto it = w->graphs.find(key);
     if (it == w->graphs.end()) {
       if (!get_plans(w, Bcap, true) || !get_lm_plan(w, Bcap)) return MQ_ERR_CUDA;
@@ -685,7 +693,7 @@ static int launch_decode(mq_worker* w) {
       uint64_t tmp = 0;
       cudaGraph_t g = nullptr;
       cudaError_t e = cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal);
-      int rc = e == cudaSuccess ? decode_body(w, Bcap, n_splits, kRing - 1, &tmp) : MQ_ERR_CUDA;
+      int rc = e == cudaSuccess ? decode_body(w, Bcap, n_splits, attn_stages, kRing - 1, &tmp) : MQ_ERR_CUDA;
       cudaError_t e2 = cudaStreamEndCapture(w->stream, &g);
       if (rc != MQ_OK || e2 != cudaSuccess || !g) {
         set_last_error("graph capture failed: %s", cudaGetErrorString(e2 != cudaSuccess ? e2 : cudaGetLastError()));
@@ -713,7 +721,7 @@ static int launch_decode(mq_worker* w) {
                     cudaMemcpyDeviceToHost, w->stream);
     nl = (uint64_t)(1 + w->cfg.n_layers * ((get_plans(w, Bcap, true)->fused_norm ? 6 : 8) - (w->fuse_rope ? 1 : 0)) + 3);
   } else {
-    int rc = decode_body(w, Bcap, n_splits, ring, &nl);
+    int rc = decode_body(w, Bcap, n_splits, attn_stages, ring, &nl);
     if (rc) return rc;
     cudaMemcpyAsync(w->h_out_ring + (size_t)ring * MBp, w->d_out_ring + (size_t)ring * MBp, Bcap * 4,
                     cudaMemcpyDeviceToHost, w->stream);

@@ -1014,9 +1014,11 @@ void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots) {
       }
       return;
     }
-    const int smem = decode_smem();
+    static const bool env_stages = getenv("MQ_ATTN_STAGES") != nullptr;
+    const int st = (!env_stages && (p.stages == 2 || p.stages == 3 || p.stages == 4 || p.stages == 6)) ? p.stages : decode_stages();
+    const int smem = decode_ring_bytes(st);
     const dim3 grid(n_slots, p.n_kv, p.n_splits);
-    switch (decode_stages()) {
+    switch (st) {
       case 2: launch_k(lc, decode_attn_kernel<2, D, 1>, grid, dim3(32), smem, p); break;
       case 3: launch_k(lc, decode_attn_kernel<3, D, 1>, grid, dim3(32), smem, p); break;
       case 4: launch_k(lc, decode_attn_kernel<4, D, 1>, grid, dim3(32), smem, p); break;

@@ -72,6 +72,8 @@ struct AttnParams {
   int row_stride;
   int n_splits;        // decode only: every sequence is cut into n_splits equal 16-aligned ranges (grid-level)
   int n_warps;         // decode only: 1, or 2 / 4 / 8 = in-CTA split over that many warps (then n_splits == 1)
+  int stages;          // decode, n_warps == 1: ring depth 2 / 3 / 4 / 6 (0 = default 6); short contexts want MORE resident
+                       // CTAs rather than a deep ring (a 6-stage CTA holds 48 KiB: 4 per SM)
   int* split_counter;  // decode only: [slots][n_kv] arrival counters (zero between launches)
   float scale_log2;    // softmax scale * log2(e)
   // decode, fused RoPE (qkv_planes != nullptr): the kernel itself sums the QKV GEMM's split-K planes (+ bias), rotates
