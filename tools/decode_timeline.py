@@ -1,6 +1,6 @@
 """Overlapped timeline of ONE live decode step (CUDA graph + PDL chain), from in-kernel %globaltimer stamps.
 
-    MQ_TRACE=1 python tools/decode_timeline.py [users] [gen_len] > profiles/rNN_decode_timeline.txt
+    MQ_TRACE=1 python tools/decode_timeline.py [users] [gen_len] [model] [prompt_len] > profiles/rNN_decode_timeline.txt
 
 ncu serialises launches (cold caches, no overlap) and nsys is not in the image, so this is the only view of how
 the kernels of a step actually overlap: per launch, the first CTA's start, the moment its dependency wait
@@ -17,18 +17,20 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 import ollamamq_b200 as mq  # noqa: E402
-from ollamamq_b200.models import LLAMA3_8B  # noqa: E402
+from ollamamq_b200 import models  # noqa: E402
 
 users = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 gen = int(sys.argv[2]) if len(sys.argv) > 2 else 64
-cfg = LLAMA3_8B
+model = sys.argv[3] if len(sys.argv) > 3 else "LLAMA3_8B"      # LLAMA3_8B | QWEN25_7B | PHI3_MINI
+plen = int(sys.argv[4]) if len(sys.argv) > 4 else 512
+cfg = getattr(models, model)
 L = cfg["n_layers"]
-P = [np.random.default_rng(u).integers(0, cfg["vocab"], 512).astype("int32").tolist() for u in range(users)]
-wk = mq.Worker(0, mq.model_cfg(cfg, max_batch=64, max_seq=512 + 128 + 16, max_prefill_tokens=4736, use_graphs=1,
+P = [np.random.default_rng(u).integers(0, cfg["vocab"], plen).astype("int32").tolist() for u in range(users)]
+wk = mq.Worker(0, mq.model_cfg(cfg, max_batch=max(64, users), max_seq=plen + 128 + 16, max_prefill_tokens=4736, use_graphs=1,
                                use_pdl=int(os.environ.get("MQ_PDL", "1"))))
 wk.init_random(0, 0.02)
 wk.set_timing(True)
-d = mq.Dispatcher([wk], capacity=64)
+d = mq.Dispatcher([wk], capacity=max(64, users))
 for rep in range(2):
     if rep == 1:
         wk.reset_stats()
@@ -49,9 +51,9 @@ ids = [(1 + 8 * l + k, l, names[k]) for l in range(L) for k in range(8)] + [(510
 ids = [(i, l, nm) for i, l, nm in ids if t[i, 0] != FF]
 t0 = min(int(t[i, 0]) for i, _, _ in ids)
 t_end = max(int(t[i, 3]) for i, _, _ in ids)
-print("# live decode step, %d users, ctx ~%d, Llama-3-8B: %.1f us from first kernel start to last kernel end "
+print("# live decode step, %d users, ctx ~%d, %s: %.1f us from first kernel start to last kernel end "
       "(worker stats: %.3f ms/step over %d steps incl. argmax + launch)" %
-      (users, 512 + gen, (t_end - t0) / 1e3, st["decode_ms"] / max(1, st["decode_steps"]), st["decode_steps"]))
+      (users, plen + gen, model, (t_end - t0) / 1e3, st["decode_ms"] / max(1, st["decode_steps"]), st["decode_steps"]))
 print("# per launch: start / dependency-wait-returned / first-CTA-end / last-CTA-end, us from the step's first stamp")
 rows = []
 prev_end = t0
