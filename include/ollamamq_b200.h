@@ -175,7 +175,13 @@ typedef struct mq_request {
   int32_t top_k;             /* <= 0: off                                                                 */
   float top_p;               /* <= 0 or >= 1: off; applied to what top_k kept                             */
   uint64_t seed;             /* stream of the counter-based generator: same seed, same tokens             */
+  int32_t body_kind;         /* MQ_BODY_JSON: `body` is the client's JSON.  MQ_BODY_TEXT: the front already parsed
+                              * it (on its connection thread, never on the scheduler's) and `body` is the extracted
+                              * prompt text; stream / max_new_tokens / sampling fields above carry the rest       */
+  int32_t reserved;
 } mq_request;
+#define MQ_BODY_JSON 0
+#define MQ_BODY_TEXT 1
 
 typedef struct mq_callbacks {
   /* exactly once, first: ResponsePart::Status (:299).                                                    */
@@ -333,6 +339,26 @@ int mq_debug_gemm(const void* W, int w_rows, int n_out, int K, const void* X, in
                   void* out, int ldo, int splits, long long split_stride, int a2_row_off, int pdl, int reps,
                   float* ms_out);
 int mq_debug_embed(const int* token_ids, const void* embed, float* h, int T, int H);
+/* ---- decode chain (csrc/gemm_dk.cuh): cluster split-K GEMM + fused epilogues, RMSNorm folded into the consumer.
+ * `cs` = cluster size = K splits (1..8; <= 0: the engine's own pick).  The RMSNorm fold scales token column t by
+ * rstd[t] = rsqrt(sum_{i < parts} ssq[i * stride + t] * inv_h + eps); ssq == NULL: no scaling.                     */
+int mq_debug_embed_chain(const int* token_ids, const void* embed, float* h, int T, int H, const void* gamma, void* xg,
+                         float* ssq);
+/* out_k[0..7] = co-resident clusters of 1..8 CTAs (occupancy query for the chain kernel's footprint)              */
+int mq_debug_cluster_info(int* out8);
+/* plain kernel with tile_rows (<= 128, multiple of 8; 0 = 128, < 0 = balanced over the SMs) and the rstd fold      */
+int mq_debug_gemm_fold(const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T, int epi,
+                       void* out, int ldo, int a2_row_off, int tile_rows, int streamk, const float* ssq, int parts,
+                       int stride, float inv_h, float eps, int reps, float* ms_out);
+/* h[t,f] += X[t,:] . W[f,:];  xg = bf16(h * gamma_next);  ssq_out[tile][t] = sum_f h^2 per 128-feature tile        */
+int mq_debug_gemm_dk_resid(const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, int cs, float* h,
+                           const void* gamma_next, void* xg, float* ssq_out, int ssq_stride, int reps, float* ms_out);
+/* QKV projection with the rstd fold, bias, rotate-half RoPE (cos / sin of pos * inv_freq) and the q / paged-KV write */
+int mq_debug_gemm_dk_qkv(const void* W, int n_q, int n_kv, int head_dim, int K, const void* X, int x_rows_alloc, int T,
+                         int cs, const float* ssq, int parts, int stride, float inv_h, float eps, const void* bias,
+                         const int* pos, const int* slot_of_tok, const int* block_table, int max_pages,
+                         const float* inv_freq, int max_pos, void* q_out, void* k_cache, void* v_cache, int reps,
+                         float* ms_out);
 int mq_debug_add_rmsnorm(float* h, const void* partial, int partial_is_f32, int n_planes, long long plane_stride,
                          const void* gamma, void* x, const int* row_idx, int rows, int H, float eps);
 int mq_debug_rope_kv(const void* qkv, int qkv_is_f32, int n_planes, long long plane_stride, const void* bias,

@@ -64,7 +64,8 @@ class Request(C.Structure):
     _fields_ = [("endpoint", C.c_int32), ("stream", C.c_int32), ("body", C.c_void_p), ("body_len", C.c_size_t),
                 ("prompt_tokens", C.c_void_p), ("n_prompt_tokens", C.c_int32), ("max_new_tokens", C.c_int32),
                 ("ignore_eos", C.c_int32), ("timeout_ms", C.c_uint32), ("path", C.c_char_p),
-                ("temperature", C.c_float), ("top_k", C.c_int32), ("top_p", C.c_float), ("seed", C.c_uint64)]
+                ("temperature", C.c_float), ("top_k", C.c_int32), ("top_p", C.c_float), ("seed", C.c_uint64),
+                ("body_kind", C.c_int32), ("reserved", C.c_int32)]
 
 
 ON_STATUS = C.CFUNCTYPE(None, C.c_void_p, C.c_int32, C.c_char_p)
@@ -165,6 +166,15 @@ _sig("mq_http_server_stop", None, [P])
 _sig("mq_debug_gemm", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int,
                                  C.c_longlong, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)])
 _sig("mq_debug_embed", C.c_int, [P, P, P, C.c_int, C.c_int])
+_sig("mq_debug_embed_chain", C.c_int, [P, P, P, C.c_int, C.c_int, P, P, P])
+_sig("mq_debug_cluster_info", C.c_int, [P])
+_sig("mq_debug_gemm_fold", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_float)])
+_sig("mq_debug_gemm_dk_resid", C.c_int, [P, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, P, P, P, P, C.c_int, C.c_int,
+                                          C.POINTER(C.c_float)])
+_sig("mq_debug_gemm_dk_qkv", C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int,
+                                        C.c_float, C.c_float, P, P, P, P, C.c_int, P, C.c_int, P, P, P, C.c_int,
+                                        C.POINTER(C.c_float)])
 _sig("mq_debug_add_rmsnorm", C.c_int, [P, P, C.c_int, C.c_int, C.c_longlong, P, P, P, C.c_int, C.c_int, C.c_float])
 _sig("mq_debug_rope_kv", C.c_int, [P, C.c_int, C.c_int, C.c_longlong, P, P, P, P, C.c_int, P, P, P, P, C.c_int,
                                     C.c_int, C.c_int, C.c_int])

@@ -5,6 +5,7 @@
 #include "gemm_host.cuh"
 #include "kernels.cuh"
 #include <cstdio>
+#include <cstdlib>
 
 using namespace mq;
 
@@ -20,6 +21,30 @@ static int check_cuda(const char* what) {
     return MQ_ERR_CUDA;
   }
   return MQ_OK;
+}
+
+template <typename F>
+static int timed_launches(const char* what, F&& launch, int reps, float* ms_out) {
+  cudaError_t e = launch();
+  if (e != cudaSuccess) {
+    mq::set_last_error("%s: %s", what, cudaGetErrorString(e));
+    return MQ_ERR_CUDA;
+  }
+  int rc = check_cuda(what);
+  if (rc != MQ_OK || reps <= 0 || !ms_out) return rc;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, 0);
+  for (int i = 0; i < reps; ++i) launch();
+  cudaEventRecord(b, 0);
+  cudaEventSynchronize(b);
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  *ms_out = ms / reps;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return check_cuda(what);
 }
 
 extern "C" {
@@ -74,6 +99,94 @@ int mq_debug_embed(const int* token_ids, const void* embed, float* h, int T, int
   return check_cuda("mq_debug_embed");
 }
 
+int mq_debug_embed_chain(const int* token_ids, const void* embed, float* h, int T, int H, const void* gamma, void* xg,
+                         float* ssq) {
+  launch_embed(LaunchCfg{0, false}, token_ids, (const __nv_bfloat16*)embed, h, T, H, (const __nv_bfloat16*)gamma,
+               (__nv_bfloat16*)xg, ssq);
+  return check_cuda("mq_debug_embed_chain");
+}
+
+int mq_debug_cluster_info(int* out8) {
+  if (!out8) return MQ_ERR_INVAL;
+  gemm_set_attrs();
+  for (int c = 1; c <= 8; ++c) out8[c - 1] = dk_max_clusters(c);
+  return MQ_OK;
+}
+
+int mq_debug_gemm_fold(const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T, int epi,
+                       void* out, int ldo, int a2_row_off, int tile_rows, int streamk, const float* ssq, int parts,
+                       int stride, float inv_h, float eps, int reps, float* ms_out) {
+  GemmPlan g;
+  gemm_set_attrs();
+  static StreamKWorkspace sk_ws;
+  if (streamk && !sk_ws.ws && streamk_workspace_alloc(&sk_ws) != 0) {
+    mq::set_last_error("stream-K workspace allocation failed");
+    return MQ_ERR_NOMEM;
+  }
+  sk_ws.force = true;
+  if (tile_rows < 0) tile_rows = gemm_balanced_rows(n_out);
+  if (!gemm_plan(&g, W, w_rows, n_out, K, X, x_rows_alloc, T, epi, out, ldo, 1, 0, a2_row_off, streamk ? &sk_ws : nullptr,
+                 tile_rows)) {
+    mq::set_last_error("gemm_plan failed");
+    return MQ_ERR_INVAL;
+  }
+  gemm_plan_set_rstd(&g, RstdIn{ssq, parts, stride, inv_h, eps});
+  LaunchCfg lc{0, false};
+  return timed_launches("mq_debug_gemm_fold", [&] { return gemm_launch(g, lc); }, reps, ms_out);
+}
+
+int mq_debug_gemm_dk_resid(const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, int cs, float* h,
+                           const void* gamma_next, void* xg, float* ssq_out, int ssq_stride, int reps, float* ms_out) {
+  DkPlan g;
+  gemm_set_attrs();
+  if (!dk_plan(&g, DK_RESID, W, n_out, n_out, K, X, x_rows_alloc, T, 128, cs)) {
+    mq::set_last_error("dk_plan failed (T > 64, K %% 64, cluster size / tokens per rank)");
+    return MQ_ERR_INVAL;
+  }
+  g.p.h = h; g.p.ldh = n_out; g.p.gamma_next = (const __nv_bfloat16*)gamma_next; g.p.xg = (__nv_bfloat16*)xg;
+  g.p.ldx = n_out; g.p.ssq_out = ssq_out; g.p.ssq_stride = ssq_stride;
+  LaunchCfg lc{0, false};
+  unsigned long long* dbg = nullptr;
+  if (getenv("MQ_DK_DBG")) { cudaMalloc((void**)&dbg, 16 * 8); cudaMemset(dbg, 0, 16 * 8); g.p.dbg = dbg; }
+  const int rc = timed_launches("mq_debug_gemm_dk_resid", [&] { return dk_launch(g, lc); }, reps, ms_out);
+  if (dbg) {
+    unsigned long long hst[16];
+    cudaMemcpy(hst, dbg, sizeof hst, cudaMemcpyDeviceToHost);
+    const char* nm[10] = {"epi entry", "epi waited", "phase0 done", "tmem full", "scatter done", "cluster barrier", "finalize done", "", "producer done", "mma committed"};
+    fprintf(stderr, "[dk dbg] T=%d n_out=%d K=%d cs=%d bn=%d:", T, n_out, K, g.cs, g.bn);
+    for (int i = 0; i < 10; ++i) if (hst[i]) fprintf(stderr, " %s +%.2fus;", nm[i], (double)((long long)hst[i] - (long long)hst[0]) / 1e3);
+    fprintf(stderr, "\n");
+    cudaFree(dbg);
+  }
+  return rc;
+}
+
+int mq_debug_gemm_dk_qkv(const void* W, int n_q, int n_kv, int head_dim, int K, const void* X, int x_rows_alloc, int T,
+                         int cs, const float* ssq, int parts, int stride, float inv_h, float eps, const void* bias,
+                         const int* pos, const int* slot_of_tok, const int* block_table, int max_pages,
+                         const float* inv_freq, int max_pos, void* q_out, void* k_cache, void* v_cache, int reps,
+                         float* ms_out) {
+  if (!head_dim_supported(head_dim)) { mq::set_last_error("head_dim must be 128, 96 or 64"); return MQ_ERR_INVAL; }
+  DkPlan g;
+  gemm_set_attrs();
+  const int n_out = (n_q + 2 * n_kv) * head_dim;
+  if (!dk_plan(&g, DK_QKV, W, n_out, n_out, K, X, x_rows_alloc, T, head_dim, cs)) {
+    mq::set_last_error("dk_plan failed (T > 64, K %% 64, cluster size / tokens per rank)");
+    return MQ_ERR_INVAL;
+  }
+  float2* table = nullptr;
+  if (cudaMalloc((void**)&table, (size_t)max_pos * (head_dim / 2) * sizeof(float2)) != cudaSuccess) return MQ_ERR_NOMEM;
+  launch_rope_table(0, table, inv_freq, max_pos, head_dim / 2);
+  g.p.rs = RstdIn{ssq, parts, stride, inv_h, eps};
+  g.p.bias = (const __nv_bfloat16*)bias; g.p.pos = pos; g.p.slot_of_tok = slot_of_tok; g.p.block_table = block_table;
+  g.p.max_pages = max_pages; g.p.rope_table = table; g.p.q_out = (__nv_bfloat16*)q_out;
+  g.p.k_cache = (__nv_bfloat16*)k_cache; g.p.v_cache = (__nv_bfloat16*)v_cache; g.p.n_q = n_q; g.p.n_kv = n_kv;
+  LaunchCfg lc{0, false};
+  const int rc = timed_launches("mq_debug_gemm_dk_qkv", [&] { return dk_launch(g, lc); }, reps, ms_out);
+  cudaFree(table);
+  return rc;
+}
+
 int mq_debug_add_rmsnorm(float* h, const void* partial, int partial_is_f32, int n_planes, long long plane_stride,
                          const void* gamma, void* x, const int* row_idx, int rows, int H, float eps) {
   if (H % 512 != 0) {
@@ -104,7 +217,6 @@ int mq_debug_rope_kv(const void* qkv, int qkv_is_f32, int n_planes, long long pl
   p.max_pages = max_pages; p.inv_freq = inv_freq; p.q_out = (__nv_bfloat16*)q_out;
   p.k_cache = (__nv_bfloat16*)k_cache; p.v_cache = (__nv_bfloat16*)v_cache; p.T = T; p.n_q = n_q; p.n_kv = n_kv;
   p.head_dim = head_dim;
-  p.pf = L2Prefetch{nullptr, 0};
   launch_rope_kv(LaunchCfg{0, false}, p);
   return check_cuda("mq_debug_rope_kv");
 }

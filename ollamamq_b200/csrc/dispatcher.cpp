@@ -12,6 +12,7 @@
 // used by the CPU parity tests (the "fake backend the reference never had").
 #include "../../include/ollamamq_b200.h"
 #include "sched.hpp"
+#include "framing.hpp"
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -136,6 +137,7 @@ struct mq_dispatcher {
     mq_dispatcher* d;
     int backend = -1;
     void* handle = nullptr;
+    bool bad_json = false;           // body failed to parse on the connection thread: answered 400 at dispatch time
     bool status_ok = false;          // Status delivered (:299)
     bool client_gone = false;        // chunk send failed (:305-308)
     std::atomic<bool> closed{false}; // responder.is_closed() (:278)
@@ -150,7 +152,8 @@ struct mq_dispatcher {
   std::map<uint64_t, std::unique_ptr<Task>> tasks;
   std::map<std::string, std::string> user_ips;
   std::set<std::string> blocked_users, blocked_ips;
-  std::vector<mq_dispatch> log;
+  std::deque<mq_dispatch> log;      // most recent dispatch decisions (parity tests read it): bounded ring
+  size_t log_cap = 1 << 16;
   std::string block_file;           // BLOCKED_FILE = "blocked_items.json" in the reference (:19); empty = no persistence
   std::thread health_thr;
   uint32_t health_period_ms = 0;
@@ -233,6 +236,7 @@ void run_worker(mq_dispatcher* d) {
     rec.backend = sd.backend;
     strncpy(rec.user, sd.user.c_str(), MQ_USER_MAX - 1);
     d->log.push_back(rec);
+    if (d->log.size() > d->log_cap) d->log.pop_front();
     auto it = d->tasks.find(sd.task_id);
     if (it == d->tasks.end()) continue;
     mq_dispatcher::Task* t = it->second.get();
@@ -265,6 +269,15 @@ void run_worker(mq_dispatcher* d) {
     mq_callbacks cb{cb_status, cb_chunk, cb_done};
     Backend* be = d->backends[sd.backend].get();
     lk.unlock();  // the reference spawns the executor and loops immediately (:270)
+    if (t->bad_json) {
+      // what a backend answers to a malformed body (the reference relays it like any response: processed, :314-316)
+      static const char kMsg[] = "{\"error\":\"invalid JSON request body\"}";
+      cb_status(t, 400, "application/json");
+      cb_chunk(t, (const uint8_t*)kMsg, sizeof(kMsg) - 1);
+      cb_done(t, 0, "");
+      lk.lock();
+      continue;
+    }
     void* h = nullptr;
     int rc = be->submit(&rq, &cb, t, &h);
     if (rc != MQ_OK) {
@@ -465,6 +478,26 @@ int mq_dispatcher_submit(mq_dispatcher* d, const char* user, const char* ip, con
   t->cb = *cb;
   t->user_data = user_data;
   t->d = d;
+  // The JSON body of a generation request is parsed HERE, on the caller's (HTTP connection) thread: the scheduler thread
+  // only ever moves the result (advisor finding r01: a parser stall froze dispatch for every user and GPU).
+  const bool gen_ep = r->endpoint == MQ_EP_API_GENERATE || r->endpoint == MQ_EP_API_CHAT || r->endpoint == MQ_EP_V1_CHAT ||
+                      r->endpoint == MQ_EP_V1_COMPLETIONS || r->endpoint == MQ_EP_RAW_TOKENS;
+  if (gen_ep && r->body_kind == MQ_BODY_JSON && !t->body.empty() && t->tokens.empty()) {
+    ParsedBody pb;
+    if (!parse_body(std::string((const char*)t->body.data(), t->body.size()), r->endpoint, &pb)) {
+      t->bad_json = true;
+      t->body.clear();
+    } else {
+      if (!pb.tokens.empty()) { t->tokens = pb.tokens; t->body.clear(); }
+      else { t->body.assign(pb.text.begin(), pb.text.end()); t->rq.body_kind = MQ_BODY_TEXT; }
+      if (pb.has_stream && t->rq.stream < 0) t->rq.stream = pb.stream ? 1 : 0;
+      if (t->rq.max_new_tokens <= 0 && pb.num_predict > 0) t->rq.max_new_tokens = pb.num_predict;
+      if (pb.has_temperature) t->rq.temperature = (float)pb.temperature;
+      if (pb.has_top_k) t->rq.top_k = (int32_t)(pb.top_k < (1 << 30) ? pb.top_k : (1 << 30));
+      if (pb.has_top_p) t->rq.top_p = (float)pb.top_p;
+      if (pb.has_seed) t->rq.seed = pb.seed;
+    }
+  }
   {
     std::lock_guard<std::mutex> g(d->mu);
     if (ip && d->blocked_ips.count(t->ip)) {  // :370-373

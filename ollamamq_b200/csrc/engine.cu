@@ -117,22 +117,13 @@ static int worker_alloc(mq_worker* w) {
   if ((rc = dalloc(&w->logits, (size_t)MBp * V))) return rc;
   if ((rc = dalloc(&w->part_o, (size_t)kMaxDecodeSplits * MBp * c.n_q_heads * D))) return rc;
   if ((rc = dalloc(&w->part_ml, (size_t)kMaxDecodeSplits * MBp * c.n_q_heads * 2))) return rc;
-  if ((rc = dalloc(&w->d_norm_counters, (size_t)2 * L + 2))) return rc;
-  CUDA_TRY(cudaMemsetAsync(w->d_norm_counters, 0, ((size_t)2 * L + 2) * 4, w->stream));
   {
-    // Measured on B200 (r01): the flag-based fusion is SLOWER than the standalone kernels under PDL
-    // (4.75 vs 4.44 ms per decode step), so it is opt-in.
-    const char* e = getenv("MQ_FUSE_NORM");
-    w->fuse_norm = e && e[0] == '1';
-    // Measured on B200 (r01): the hints make the decode step slower (4.71 vs 4.44 ms): opt-in only.
-    const char* e2 = getenv("MQ_L2_PREFETCH");
-    w->l2_prefetch = e2 && e2[0] == '1';
+    const size_t tiles_h = (size_t)(H + 127) / 128;
+    if ((rc = dalloc(&w->ssq_e, (size_t)MBp)) || (rc = dalloc(&w->ssq_o, tiles_h * MBp)) || (rc = dalloc(&w->ssq_d, tiles_h * MBp)))
+      return rc;
+    const char* e = getenv("MQ_DECODE_CHAIN");
+    w->chain = !(e && e[0] == '0');
     // MQ_TRACE=1: per-launch %globaltimer stamps of the most recent pass (tools/decode_timeline.py)
-    // MQ_FUSE_ROPE=1: decode attention does the QKV split-K reduce + RoPE + KV append itself (one launch less per
-    // layer).  Measured on B200 (r01 timeline, same GPU): 64 slots 29.8 us vs 2.8 + 25.2 us separate, 8 slots
-    // 7.9 vs 2.4 + 5.6 - the three plane round trips land on every warp's critical path, so it is opt-in.
-    const char* e4 = getenv("MQ_FUSE_ROPE");
-    w->fuse_rope = e4 && e4[0] == '1';
     const char* e3 = getenv("MQ_TRACE");
     if (e3 && e3[0] == '1') {
       if (8 * c.n_layers + 1 > kTraceSlots - 2) {
@@ -236,6 +227,44 @@ static int build_plans(mq_worker* w, PassPlans* pp, int T, bool decode) {
   }
   const int epi_part = decode ? EPI_F32 : EPI_BF16;
   const int x_rows = w->MT;
+  // ---- decode chain: servable when every GEMM of the layer fits the cluster kernel (T <= 64, one head per QKV tile)
+  const int tiles_h = (H + 127) / 128;
+  pp->chain = decode && !sk && w->chain && T <= 64 &&
+              dk_pick_cluster(c.n_q_heads + 2 * c.n_kv_heads, H / 64, T) > 0 && dk_pick_cluster(tiles_h, qd / 64, T) > 0 &&
+              dk_pick_cluster(tiles_h, I / 64, T) > 0;
+  if (pp->chain) {
+    pp->qkv_dk.resize(c.n_layers); pp->o_dk.resize(c.n_layers); pp->down_dk.resize(c.n_layers); pp->gate_up.resize(c.n_layers);
+    const RstdIn rs_o{w->ssq_o, tiles_h, MBp, 1.0f / (float)H, c.rms_eps};
+    const RstdIn rs_d{w->ssq_d, tiles_h, MBp, 1.0f / (float)H, c.rms_eps};
+    const RstdIn rs_e{w->ssq_e, 1, MBp, 1.0f / (float)H, c.rms_eps};
+    for (int l = 0; l < c.n_layers; ++l) {
+      const LayerWeights& lw = w->layers[l];
+      DkPlan& q = pp->qkv_dk[l];
+      DkPlan& o = pp->o_dk[l];
+      DkPlan& d = pp->down_dk[l];
+      bool ok = dk_plan(&q, DK_QKV, lw.wqkv, w->qkv_dim, w->qkv_dim, H, w->x, x_rows, T, D, 0);
+      ok &= dk_plan(&o, DK_RESID, lw.wo, H, H, qd, w->attn, x_rows, T, 128, 0);
+      ok &= dk_plan(&d, DK_RESID, lw.w_down, H, H, I, w->act, x_rows, T, 128, 0);
+      ok &= gemm_plan(&pp->gate_up[l], lw.w_gate_up, 2 * I, I, H, w->x, x_rows, T, EPI_SILU_BF16, w->act, I, 1, 0, I,
+                      nullptr, getenv("MQ_GU_ROWS") ? atoi(getenv("MQ_GU_ROWS")) : gemm_balanced_rows(I));
+      if (!ok) {
+        set_last_error("decode-chain plan failed (layer %d, T=%d)", l, T);
+        return MQ_ERR_CUDA;
+      }
+      q.p.rs = l == 0 ? rs_e : rs_d;
+      q.p.bias = lw.bqkv; q.p.pos = w->d_pos; q.p.slot_of_tok = w->d_identity; q.p.block_table = w->d_block_table;
+      q.p.max_pages = w->max_pages; q.p.rope_table = w->rope_table; q.p.q_out = w->q;
+      q.p.k_cache = w->k_cache + (size_t)l * w->cache_layer_stride;
+      q.p.v_cache = w->v_cache + (size_t)l * w->cache_layer_stride;
+      q.p.n_q = c.n_q_heads; q.p.n_kv = c.n_kv_heads;
+      o.p.h = w->h; o.p.ldh = H; o.p.gamma_next = lw.mlp_norm; o.p.xg = w->x; o.p.ldx = H; o.p.ssq_out = w->ssq_o;
+      o.p.ssq_stride = MBp;
+      d.p.h = w->h; d.p.ldh = H; d.p.gamma_next = l + 1 < c.n_layers ? w->layers[l + 1].attn_norm : w->final_norm;
+      d.p.xg = w->x; d.p.ldx = H; d.p.ssq_out = w->ssq_d; d.p.ssq_stride = MBp;
+      gemm_plan_set_rstd(&pp->gate_up[l], rs_o);
+    }
+    return MQ_OK;
+  }
   pp->qkv.resize(c.n_layers); pp->o.resize(c.n_layers); pp->gate_up.resize(c.n_layers); pp->down.resize(c.n_layers);
   for (int l = 0; l < c.n_layers; ++l) {
     const LayerWeights& lw = w->layers[l];
@@ -251,13 +280,6 @@ static int build_plans(mq_worker* w, PassPlans* pp, int T, bool decode) {
       set_last_error("gemm_plan failed (layer %d, T=%d)", l, T);
       return MQ_ERR_CUDA;
     }
-    if (decode && w->fuse_norm && T <= 64 && !pp->qkv[l].streamk && !pp->gate_up[l].streamk) {
-      pp->fused_norm = true;
-      gemm_plan_fuse_norm(&pp->qkv[l], w->h, (const float*)w->proj_part, l == 0 ? 0 : pp->s_down, (long long)MBp * H,
-                          lw.attn_norm, w->x, H, c.rms_eps, w->d_norm_counters + 2 * l);
-      gemm_plan_fuse_norm(&pp->gate_up[l], w->h, (const float*)w->proj_part, pp->s_o, (long long)MBp * H, lw.mlp_norm,
-                          w->x, H, c.rms_eps, w->d_norm_counters + 2 * l + 1);
-    }
   }
   return MQ_OK;
 }
@@ -271,17 +293,22 @@ static PassPlans* get_plans(mq_worker* w, int T, bool decode) {
   return &(m[T] = std::move(pp));
 }
 
-static GemmPlan* get_lm_plan(mq_worker* w, int rows) {
-  auto it = w->lm_plans.find(rows);
+// chain: the activation operand is the decode chain's xg = bf16(h * final_norm) (rows 0..rows-1 of w->x) and the
+// final RMSNorm is the per-token scale of the epilogue (ssq_d of the last down projection)
+static GemmPlan* get_lm_plan(mq_worker* w, int rows, bool chain = false) {
+  const int key = rows + (chain ? (1 << 20) : 0);
+  auto it = w->lm_plans.find(key);
   if (it != w->lm_plans.end()) return &it->second;
   GemmPlan g;
   const int MBp = round_up(w->MB, 16);
-  if (!gemm_plan(&g, w->lm_head, w->cfg.vocab, w->cfg.vocab, w->cfg.hidden, w->x_last, MBp, rows, EPI_F32, w->logits,
-                 w->cfg.vocab, 1, 0, 0, (rows <= 64 && w->sk_ws.ws) ? &w->sk_ws : nullptr)) {
+  if (!gemm_plan(&g, w->lm_head, w->cfg.vocab, w->cfg.vocab, w->cfg.hidden, chain ? w->x : w->x_last, chain ? w->MT : MBp,
+                 rows, EPI_F32, w->logits, w->cfg.vocab, 1, 0, 0, (rows <= 64 && w->sk_ws.ws) ? &w->sk_ws : nullptr)) {
     set_last_error("gemm_plan(lm_head) failed");
     return nullptr;
   }
-  return &(w->lm_plans[rows] = g);
+  if (chain)
+    gemm_plan_set_rstd(&g, RstdIn{w->ssq_d, (w->cfg.hidden + 127) / 128, MBp, 1.0f / (float)w->cfg.hidden, w->cfg.rms_eps});
+  return &(w->lm_plans[key] = g);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -299,37 +326,66 @@ struct PassArgs {
 };
 
 
+static void fill_attn_params(mq_worker* w, const PassArgs& a, int l, AttnParams* ap, Trace tr) {
+  const mq_model_cfg& c = w->cfg;
+  *ap = AttnParams{};
+  ap->head_dim = c.head_dim;
+  ap->q = w->q;
+  ap->k_cache = w->k_cache + (size_t)l * w->cache_layer_stride;
+  ap->v_cache = w->v_cache + (size_t)l * w->cache_layer_stride;
+  ap->block_table = w->d_block_table;
+  ap->max_pages = w->max_pages; ap->tiles = w->d_tiles; ap->pos = a.pos; ap->out = w->attn; ap->part_o = w->part_o;
+  ap->part_ml = w->part_ml; ap->n_q = c.n_q_heads; ap->n_kv = c.n_kv_heads; ap->T = a.T;
+  ap->n_splits = a.n_splits < 0 ? 1 : a.n_splits; ap->n_warps = a.n_splits < 0 ? -a.n_splits : 1;
+  ap->stages = a.attn_stages;
+  ap->tr = tr;
+  ap->split_counter = w->d_split_counter; ap->scale_log2 = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
+}
+
+// Decode chain: 5 launches per layer.  Timeline slots (tools/decode_timeline.py): 1 + 8 * layer + {1 qkv, 3 attention,
+// 4 o, 6 gate/up, 7 down}; slots 0 / 2 / 5 (norm1, rope, norm2 of the plane-based path) stay unused.
+static int run_layers_chain(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* n_launch) {
+  const mq_model_cfg& c = w->cfg;
+  const LaunchCfg lc{w->stream, c.use_pdl != 0};
+  uint64_t nl = 0;
+  launch_embed(lc, a.tok, w->embed, w->h, a.T, c.hidden, w->layers[0].attn_norm, w->x, w->ssq_e); ++nl;
+  for (int l = 0; l < c.n_layers; ++l) {
+    auto tr = [&](int k) { return Trace{w->d_trace, 1 + 8 * l + k}; };
+    pp->qkv_dk[l].p.tr = tr(1);
+    if (dk_launch(pp->qkv_dk[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
+    AttnParams ap;
+    fill_attn_params(w, a, l, &ap, tr(3));
+    launch_attn_decode(lc, ap, a.T); ++nl;
+    pp->o_dk[l].p.tr = tr(4);
+    if (dk_launch(pp->o_dk[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
+    pp->gate_up[l].p.tr = tr(6);
+    if (gemm_launch(pp->gate_up[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
+    pp->down_dk[l].p.tr = tr(7);
+    if (dk_launch(pp->down_dk[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
+  }
+  *n_launch += nl;
+  return MQ_OK;
+}
+
 static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* n_launch) {
+  if (a.decode && pp->chain) return run_layers_chain(w, a, pp, n_launch);
   const mq_model_cfg& c = w->cfg;
   const LaunchCfg lc{w->stream, c.use_pdl != 0};
   const int H = c.hidden;
   const int MBp = round_up(w->MB, 16);
   const bool f32p = a.decode;
   uint64_t nl = 0;
-  launch_embed(lc, a.tok, w->embed, w->h, a.T, H, w->d_norm_counters, 2 * c.n_layers); ++nl;
-  const bool fused = a.decode && pp->fused_norm;
+  launch_embed(lc, a.tok, w->embed, w->h, a.T, H); ++nl;
   int prev_planes = 0;
   for (int l = 0; l < c.n_layers; ++l) {
     const LayerWeights& lw = w->layers[l];
-    // decode: bytes of upcoming weights that the latency-bound kernels pull into L2 while HBM idles
-    const bool pfon = a.decode && w->l2_prefetch;
-    const size_t b_qkv = (size_t)w->qkv_dim * H * 2, b_o = (size_t)H * c.n_q_heads * c.head_dim * 2;
-    const size_t b_gu = (size_t)2 * c.ffn * H * 2;
-    const L2Prefetch pf_none{nullptr, 0};
-    const L2Prefetch pf_norm1 = pfon ? L2Prefetch{lw.wqkv, b_qkv} : pf_none;                         // before the QKV GEMM
-    const L2Prefetch pf_rope = pf_none;                                                              // KV stream follows: too early
-    const L2Prefetch pf_attn = pfon ? L2Prefetch{lw.wo, b_o} : pf_none;                              // tail of attention -> O GEMM
-    const L2Prefetch pf_norm2 = pfon ? L2Prefetch{lw.w_gate_up, std::min(b_gu, (size_t)64 << 20)} : pf_none;  // -> gate/up GEMM
     // timeline slots: 1 + 8 * layer + {0 norm1, 1 qkv, 2 rope, 3 attention, 4 o, 5 norm2, 6 gate/up, 7 down}
     auto tr = [&](int k) { return Trace{w->d_trace, 1 + 8 * l + k}; };
     auto tr_gemm = [&](GemmPlan& g, int k) { g.p.tr = tr(k); g.sk.tr = tr(k); };
-    if (!fused) {
-      launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, prev_planes, (long long)MBp * H, lw.attn_norm, w->x, nullptr, a.T,
-                         H, c.rms_eps, pf_norm1, tr(0)); ++nl;
-    }
+    launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, prev_planes, (long long)MBp * H, lw.attn_norm, w->x, nullptr, a.T,
+                       H, c.rms_eps, tr(0)); ++nl;
     tr_gemm(pp->qkv[l], 1);
     if (gemm_launch(pp->qkv[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
-    const bool fuse_rope = a.decode && w->fuse_rope;  // decode: the attention kernel reduces / rotates / appends itself
     RopeKvParams rp;
     rp.qkv = w->qkv_part; rp.qkv_is_f32 = f32p; rp.n_planes = pp->s_qkv; rp.plane_stride = (long long)MBp * w->qkv_dim;
     rp.bias = lw.bqkv; rp.pos = a.pos; rp.slot_of_tok = a.slot_of_tok; rp.block_table = w->d_block_table;
@@ -337,32 +393,16 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
     rp.k_cache = w->k_cache + (size_t)l * w->cache_layer_stride;
     rp.v_cache = w->v_cache + (size_t)l * w->cache_layer_stride;
     rp.T = a.T; rp.n_q = c.n_q_heads; rp.n_kv = c.n_kv_heads; rp.head_dim = c.head_dim;
-    rp.pf = pf_rope;
     rp.tr = tr(2);
-    if (!fuse_rope) { launch_rope_kv(lc, rp); ++nl; }
-    AttnParams ap = {};
-    ap.head_dim = c.head_dim;
-    ap.q = w->q; ap.k_cache = rp.k_cache; ap.v_cache = rp.v_cache; ap.block_table = w->d_block_table;
-    ap.max_pages = w->max_pages; ap.tiles = w->d_tiles; ap.pos = a.pos; ap.out = w->attn; ap.part_o = w->part_o;
-    ap.part_ml = w->part_ml; ap.n_q = c.n_q_heads; ap.n_kv = c.n_kv_heads; ap.T = a.T;
-    ap.n_splits = a.n_splits < 0 ? 1 : a.n_splits; ap.n_warps = a.n_splits < 0 ? -a.n_splits : 1;
-    ap.stages = a.attn_stages;
-    ap.pf = pf_attn;
-    ap.tr = tr(3);
-    if (fuse_rope) {
-      ap.qkv_planes = reinterpret_cast<const float*>(w->qkv_part); ap.qkv_n_planes = pp->s_qkv;
-      ap.qkv_plane_stride = (long long)MBp * w->qkv_dim; ap.qkv_dim = w->qkv_dim; ap.qkv_bias = lw.bqkv;
-      ap.rope_table = w->rope_table; ap.k_new = rp.k_cache; ap.v_new = rp.v_cache;
-    }
-    ap.split_counter = w->d_split_counter; ap.scale_log2 = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
+    launch_rope_kv(lc, rp); ++nl;
+    AttnParams ap;
+    fill_attn_params(w, a, l, &ap, tr(3));
     if (a.decode) { launch_attn_decode(lc, ap, a.T); ++nl; }
     else { launch_attn_prefill(lc, ap, a.n_tiles); ++nl; }
     tr_gemm(pp->o[l], 4);
     if (gemm_launch(pp->o[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
-    if (!fused) {
-      launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, pp->s_o, (long long)MBp * H, lw.mlp_norm, w->x, nullptr, a.T, H,
-                         c.rms_eps, pf_norm2, tr(5)); ++nl;
-    }
+    launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, pp->s_o, (long long)MBp * H, lw.mlp_norm, w->x, nullptr, a.T, H,
+                       c.rms_eps, tr(5)); ++nl;
     tr_gemm(pp->gate_up[l], 6);
     if (gemm_launch(pp->gate_up[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     tr_gemm(pp->down[l], 7);
@@ -378,13 +418,17 @@ static int run_head(mq_worker* w, bool decode, const int* row_idx, int rows, Pas
   const mq_model_cfg& c = w->cfg;
   const LaunchCfg lc{w->stream, c.use_pdl != 0};
   const int MBp = round_up(w->MB, 16);
-  launch_add_rmsnorm(lc, w->h, w->proj_part, decode, pp->s_down, (long long)MBp * c.hidden, w->final_norm, w->x_last,
-                     row_idx, rows, c.hidden, c.rms_eps, L2Prefetch{nullptr, 0}, Trace{w->d_trace, kTraceSlots - 2});
-  GemmPlan* g = get_lm_plan(w, rows);
+  const bool chain = decode && pp->chain;  // final norm folded into the LM head (rows are the batch rows themselves)
+  if (!chain) {
+    launch_add_rmsnorm(lc, w->h, w->proj_part, decode, pp->s_down, (long long)MBp * c.hidden, w->final_norm, w->x_last,
+                       row_idx, rows, c.hidden, c.rms_eps, Trace{w->d_trace, kTraceSlots - 2});
+    *n_launch += 1;
+  }
+  GemmPlan* g = get_lm_plan(w, rows, chain);
   if (!g) return MQ_ERR_CUDA;
   g->p.tr = g->sk.tr = Trace{w->d_trace, kTraceSlots - 1};
   if (gemm_launch(*g, lc) != cudaSuccess) return MQ_ERR_CUDA;
-  *n_launch += 2;
+  *n_launch += 1;
   return MQ_OK;
 }
 
@@ -689,7 +733,8 @@ static int launch_decode(mq_worker* w) {
     const long long key = ((long long)Bcap * 1024 + (n_splits + 16)) * 8 + attn_stages;
     auto it = w->graphs.find(key);
     if (it == w->graphs.end()) {
-      if (!get_plans(w, Bcap, true) || !get_lm_plan(w, Bcap)) return MQ_ERR_CUDA;
+      PassPlans* pp0 = get_plans(w, Bcap, true);
+      if (!pp0 || !get_lm_plan(w, Bcap, pp0->chain)) return MQ_ERR_CUDA;
       // warm-up launch outside capture so every kernel's attributes are set before capturing
       uint64_t tmp = 0;
       cudaGraph_t g = nullptr;
@@ -720,7 +765,7 @@ static int launch_decode(mq_worker* w) {
     // graph wrote to the fixed row kRing-1; move it to this step's ring slot on the host side copy
     cudaMemcpyAsync(w->h_out_ring + (size_t)ring * MBp, w->d_out_ring + (size_t)(kRing - 1) * MBp, Bcap * 4,
                     cudaMemcpyDeviceToHost, w->stream);
-    nl = (uint64_t)(1 + w->cfg.n_layers * ((get_plans(w, Bcap, true)->fused_norm ? 6 : 8) - (w->fuse_rope ? 1 : 0)) + 3);
+    nl = get_plans(w, Bcap, true)->chain ? (uint64_t)(1 + w->cfg.n_layers * 5 + 2) : (uint64_t)(1 + w->cfg.n_layers * 8 + 3);
   } else {
     int rc = decode_body(w, Bcap, n_splits, attn_stages, ring, &nl);
     if (rc) return rc;
@@ -859,7 +904,8 @@ static void worker_main(mq_worker* w) {
     for (mq_req* r : others) {  // non-generation routes: immediate answer, same Status/Chunk/Done sequence
       int status = 200;
       std::string ctype, body;
-      other_route_response(r->path, w->cfg.model_name, &status, &ctype, &body);
+      if (r->bad_request) { status = 400; ctype = "application/json"; body = "{\"error\":\"invalid JSON request body\"}"; }
+      else other_route_response(r->path, w->cfg.model_name, &status, &ctype, &body);
       r->t_first = r->t_last = Clock::now();
       r->finished = true;
       if (r->cb.on_status) r->cb.on_status(r->user, status, ctype.c_str());
@@ -880,7 +926,7 @@ static void worker_main(mq_worker* w) {
       while (!w->inbox.empty()) {
         mq_req* r = w->inbox.front();
         w->inbox.pop_front();
-        if (r->rq.endpoint == MQ_EP_OTHER) others.push_back(r);
+        if (r->rq.endpoint == MQ_EP_OTHER || r->bad_request) others.push_back(r);
         else w->waiting.push_back(r);
       }
       if (idle && !w->jobs.empty()) {
@@ -1127,7 +1173,7 @@ void mq_worker_close(mq_worker* w) {
   void* bufs[] = {w->k_cache, w->v_cache, w->h, w->x, w->q, w->attn, w->act, w->x_last, w->qkv_part, w->proj_part,
                   w->logits, w->part_o, w->part_ml, w->inv_freq, w->d_tok, w->d_pos_tok, w->d_slot_tok, w->d_last_idx,
                   w->d_dst_slot, w->d_tiles, w->d_cur_token, w->d_pos, w->d_active, w->d_block_table, w->d_identity,
-                  w->d_out_ring, w->d_split_counter, w->d_norm_counters};
+                  w->d_out_ring, w->d_split_counter, w->ssq_e, w->ssq_o, w->ssq_d};
   for (void* b : bufs) if (b) cudaFree(b);
   void* pinned[] = {w->h_pos, w->h_active, w->h_block_table, w->h_stage, w->h_out_ring};
   for (void* b : pinned) if (b) cudaFreeHost(b);
@@ -1215,31 +1261,46 @@ int mq_submit(mq_worker* w, const mq_request* rq, const mq_callbacks* cb, void* 
     return MQ_OK;
   }
   ParsedBody pb;
-  if (!r->body.empty()) parse_body(r->body, rq->endpoint, &pb);
+  const bool text_body = rq->body_kind == MQ_BODY_TEXT;  // the front parsed the JSON already (dispatcher.cpp)
+  if (!r->body.empty() && !text_body && !(rq->prompt_tokens && rq->n_prompt_tokens > 0) &&
+      !parse_body(r->body, rq->endpoint, &pb)) {
+    // what the backend of the reference answers to a malformed body: 400 + {"error": ...}, relayed like any response
+    r->bad_request = true;
+    r->rq.body = nullptr; r->rq.prompt_tokens = nullptr;
+    if (out) *out = r; else r->refs.store(1);
+    { std::lock_guard<std::mutex> g(w->mu); w->inbox.push_back(r); }
+    w->cv.notify_all();
+    return MQ_OK;
+  }
   if (rq->prompt_tokens && rq->n_prompt_tokens > 0)
     r->prompt.assign(rq->prompt_tokens, rq->prompt_tokens + rq->n_prompt_tokens);
   else if (!pb.tokens.empty())
     r->prompt = pb.tokens;
   else
-    r->prompt = byte_tokenize(pb.text, w->cfg.vocab);
+    r->prompt = byte_tokenize(text_body ? r->body : pb.text, w->cfg.vocab);
   if (r->prompt.empty()) r->prompt.push_back(0);
   for (int32_t& t : r->prompt) if (t < 0 || t >= w->cfg.vocab) t = 0;
   r->rq.body = nullptr; r->rq.prompt_tokens = nullptr;
   if (pb.has_stream && rq->stream < 0) r->rq.stream = pb.stream ? 1 : 0;
   if (r->rq.stream < 0) r->rq.stream = 1;
-  r->max_new = rq->max_new_tokens > 0 ? rq->max_new_tokens : (pb.num_predict > 0 ? pb.num_predict : 128);
+  // generation length: validated BEFORE any arithmetic with the prompt length ("num_predict": 2147483647 used to wrap
+  // prompt + max_new negative, pass both checks below and die in vector::resize on the worker thread)
+  long long want = rq->max_new_tokens > 0 ? rq->max_new_tokens : (pb.num_predict > 0 ? pb.num_predict : 128);
+  if (want > (long long)w->cfg.max_seq - (long long)r->prompt.size()) {
+    const int n = (int)r->prompt.size();
+    delete r;
+    set_last_error("prompt (%d) + max_new_tokens (%lld) exceeds max_seq %d", n, want, w->cfg.max_seq);
+    return MQ_ERR_INVAL;
+  }
+  r->max_new = (int)want;
   // sampling: body options win over the struct fields; everything unset = greedy (what BASELINE measures)
   r->temperature = pb.has_temperature ? (float)pb.temperature : rq->temperature;
   r->top_k = pb.has_top_k ? (int)std::min<long long>(pb.top_k, 1 << 30) : rq->top_k;
   r->top_p = pb.has_top_p ? (float)pb.top_p : rq->top_p;
   r->seed = pb.has_seed ? pb.seed : rq->seed;
-  if ((int)r->prompt.size() + r->max_new > w->cfg.max_seq) {
-    const int n = (int)r->prompt.size();
-    delete r;
-    set_last_error("prompt (%d) + max_new_tokens exceeds max_seq %d", n, w->cfg.max_seq);
-    return MQ_ERR_INVAL;
-  }
-  if (((int)r->prompt.size() + r->max_new + kPageSize - 1) / kPageSize > w->n_pages - 1) {
+  if (!(r->temperature == r->temperature)) r->temperature = 0.f;  // NaN from a C-ABI caller: greedy
+  if (!(r->top_p == r->top_p)) r->top_p = 0.f;
+  if (((long long)r->prompt.size() + r->max_new + kPageSize - 1) / kPageSize > w->n_pages - 1) {
     delete r;
     set_last_error("request needs more KV pages than the worker owns (%d)", w->n_pages - 1);
     return MQ_ERR_NOMEM;

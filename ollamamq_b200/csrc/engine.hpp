@@ -33,8 +33,11 @@ struct PassPlans {
   int T = 0;
   bool decode = false;
   int s_qkv = 1, s_o = 1, s_down = 1;
-  bool fused_norm = false;  // decode: norm1/norm2 run inside the QKV / gate-up GEMM prologues
   std::vector<GemmPlan> qkv, o, gate_up, down;  // per layer
+  // decode chain (gemm_dk.cuh): cluster split-K GEMMs with fused RoPE / residual epilogues, RMSNorm folded into the
+  // consumers - 5 launches per layer instead of 8; `gate_up` then carries the rstd fold and balanced tile rows
+  bool chain = false;
+  std::vector<DkPlan> qkv_dk, o_dk, down_dk;
 };
 
 }  // namespace mq
@@ -60,6 +63,7 @@ struct mq_req {
   bool status_sent = false;
   bool finished = false;
   bool stopped = false;  // ended on the model's EOS token rather than on max_new
+  bool bad_request = false;  // malformed JSON body: answered 400 on the worker thread, never scheduled
   int done_rc = 0;
   std::string agg;       // stream=0: aggregated text
   std::vector<int32_t> agg_tokens;
@@ -101,11 +105,10 @@ struct mq_worker {
   unsigned long long *d_seed = nullptr, *h_seed = nullptr;
   int* d_out_ring = nullptr;  // [kRing][MB]
   int* d_split_counter = nullptr;  // [MB][n_kv] arrival counters of the split-KV decode attention
-  int* d_norm_counters = nullptr;  // [2 * layers] arrival counters of the fused norm prologues (zeroed by embed)
-  bool fuse_norm = true;
-  bool fuse_rope = false;    // decode: attention kernel does the QKV reduce + RoPE + KV append (MQ_FUSE_ROPE=1; measured no gain)
+  // decode chain: per-weight-tile partial sums of h^2 (RMSNorm fold, gemm.cuh RstdIn), [tiles][round_up(MB, 16)]
+  float *ssq_e = nullptr, *ssq_o = nullptr, *ssq_d = nullptr;
+  bool chain = true;         // MQ_DECODE_CHAIN=0: the round-1 plane-based decode path (A/B and parity cross-check)
   unsigned long long* d_trace = nullptr;  // MQ_TRACE=1: [kTraceSlots][4] %globaltimer stamps of the latest pass
-  bool l2_prefetch = true;   // decode: small kernels pull the next GEMM's weights into L2 (MQ_L2_PREFETCH=0 disables)
   // pinned host mirrors / staging
   int *h_pos = nullptr, *h_active = nullptr, *h_block_table = nullptr;
   int* h_stage = nullptr;     // ring of staging areas for metadata uploads

@@ -9,41 +9,87 @@
 namespace mq {
 
 // ------------------------------------------------------------------ minimal JSON walker
+// Strict by construction (round-1 advisor findings): every loop consumes at least one byte per turn or fails, nesting
+// is bounded (kMaxDepth) so the recursion cannot be driven into the guard page, numbers are clamped before they are
+// narrowed (NaN / inf / 1e300 never reach a cast), and \u escapes are validated (surrogate pairs are combined).
 namespace {
+constexpr int kMaxDepth = 64;
+
+double clamp_num(double v, double lo, double hi) { return !(v == v) ? 0.0 : (v < lo ? lo : (v > hi ? hi : v)); }
+
 struct J {
   const char* p;
   const char* e;
+  int depth = 0;
   void ws() { while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) ++p; }
+  bool at(char c) { ws(); return p < e && *p == c; }
   bool lit(const char* s) {
     size_t n = strlen(s);
     if ((size_t)(e - p) >= n && memcmp(p, s, n) == 0) { p += n; return true; }
     return false;
+  }
+  static int hexv(char c) {
+    if (c >= '0' && c <= '9') return c - '0';
+    if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+    if (c >= 'A' && c <= 'F') return c - 'A' + 10;
+    return -1;
+  }
+  bool hex4(unsigned* cp) {
+    if (e - p < 4) return false;
+    unsigned v = 0;
+    for (int i = 0; i < 4; ++i) {
+      const int h = hexv(p[i]);
+      if (h < 0) return false;
+      v = v * 16 + (unsigned)h;
+    }
+    p += 4;
+    *cp = v;
+    return true;
+  }
+  static void utf8(std::string* out, unsigned cp) {
+    if (!out) return;
+    if (cp < 0x80) out->push_back((char)cp);
+    else if (cp < 0x800) { out->push_back((char)(0xC0 | (cp >> 6))); out->push_back((char)(0x80 | (cp & 0x3F))); }
+    else if (cp < 0x10000) {
+      out->push_back((char)(0xE0 | (cp >> 12))); out->push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out->push_back((char)(0x80 | (cp & 0x3F)));
+    } else {
+      out->push_back((char)(0xF0 | (cp >> 18))); out->push_back((char)(0x80 | ((cp >> 12) & 0x3F)));
+      out->push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out->push_back((char)(0x80 | (cp & 0x3F)));
+    }
   }
   bool str(std::string* out) {
     ws();
     if (p >= e || *p != '"') return false;
     ++p;
     while (p < e && *p != '"') {
-      if (*p == '\\' && p + 1 < e) {
+      if (*p == '\\') {
+        if (p + 1 >= e) return false;
         ++p;
-        char c = *p++;
+        const char c = *p++;
         switch (c) {
           case 'n': if (out) out->push_back('\n'); break;
           case 't': if (out) out->push_back('\t'); break;
           case 'r': if (out) out->push_back('\r'); break;
           case 'b': if (out) out->push_back('\b'); break;
           case 'f': if (out) out->push_back('\f'); break;
+          case '"': case '\\': case '/': if (out) out->push_back(c); break;
           case 'u': {
             unsigned cp = 0;
-            for (int i = 0; i < 4 && p < e; ++i, ++p) cp = cp * 16 + (unsigned)(isdigit((unsigned char)*p) ? *p - '0' : (tolower(*p) - 'a' + 10));
-            if (out) {
-              if (cp < 0x80) out->push_back((char)cp);
-              else if (cp < 0x800) { out->push_back((char)(0xC0 | (cp >> 6))); out->push_back((char)(0x80 | (cp & 0x3F))); }
-              else { out->push_back((char)(0xE0 | (cp >> 12))); out->push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out->push_back((char)(0x80 | (cp & 0x3F))); }
+            if (!hex4(&cp)) return false;
+            if (cp >= 0xD800 && cp <= 0xDBFF) {  // high surrogate: a low one must follow
+              unsigned lo = 0;
+              if (e - p >= 6 && p[0] == '\\' && p[1] == 'u') {
+                p += 2;
+                if (!hex4(&lo)) return false;
+              }
+              cp = (lo >= 0xDC00 && lo <= 0xDFFF) ? 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00) : 0xFFFD;
+            } else if (cp >= 0xDC00 && cp <= 0xDFFF) {
+              cp = 0xFFFD;  // lone low surrogate
             }
+            utf8(out, cp);
             break;
           }
-          default: if (out) out->push_back(c);
+          default: return false;
         }
       } else {
         if (out) out->push_back(*p);
@@ -54,159 +100,161 @@ struct J {
     ++p;
     return true;
   }
-  bool skip() {  // skip any value
+  // {"k": v, ...}: f(key) consumes the value.  Fails on anything but `,` or `}` after a member.
+  template <class F>
+  bool object(F&& f) {
+    if (!at('{') || depth >= kMaxDepth) return false;
+    ++p;
+    ++depth;
+    if (at('}')) { ++p; --depth; return true; }
+    for (;;) {
+      std::string k;
+      if (!str(&k)) return false;
+      if (!at(':')) return false;
+      ++p;
+      if (!f(k)) return false;
+      if (at(',')) { ++p; continue; }
+      if (at('}')) { ++p; --depth; return true; }
+      return false;
+    }
+  }
+  // [v, ...]: f() consumes one element
+  template <class F>
+  bool array(F&& f) {
+    if (!at('[') || depth >= kMaxDepth) return false;
+    ++p;
+    ++depth;
+    if (at(']')) { ++p; --depth; return true; }
+    for (;;) {
+      if (!f()) return false;
+      if (at(',')) { ++p; continue; }
+      if (at(']')) { ++p; --depth; return true; }
+      return false;
+    }
+  }
+  bool skip() {  // skip any value; recursion is bounded by kMaxDepth
     ws();
     if (p >= e) return false;
     if (*p == '"') return str(nullptr);
-    if (*p == '{' || *p == '[') {
-      const char open = *p, close = open == '{' ? '}' : ']';
-      ++p;
-      ws();
-      if (p < e && *p == close) { ++p; return true; }
-      for (;;) {
-        if (open == '{') { if (!str(nullptr)) return false; ws(); if (p >= e || *p != ':') return false; ++p; }
-        if (!skip()) return false;
-        ws();
-        if (p < e && *p == ',') { ++p; continue; }
-        if (p < e && *p == close) { ++p; return true; }
-        return false;
-      }
-    }
-    while (p < e && *p != ',' && *p != '}' && *p != ']' && !isspace((unsigned char)*p)) ++p;
-    return true;
+    if (*p == '{') return object([&](const std::string&) { return skip(); });
+    if (*p == '[') return array([&] { return skip(); });
+    const char* b = p;  // number / true / false / null: must consume at least one byte
+    while (p < e && *p != ',' && *p != '}' && *p != ']' && *p != ' ' && *p != '\n' && *p != '\t' && *p != '\r') ++p;
+    return p > b;
   }
   bool number(double* v) {
     ws();
+    if (p >= e || !(*p == '-' || (*p >= '0' && *p <= '9'))) return false;  // JSON numbers only: no nan / inf / hex
     char* end = nullptr;
-    *v = strtod(p, &end);
-    if (end == p) return false;
+    *v = strtod(p, &end);  // the buffer is a std::string: NUL-terminated
+    if (end == p || end > e) return false;
     p = end;
     return true;
   }
   bool int_array(std::vector<int32_t>* out) {
-    ws();
-    if (p >= e || *p != '[') return false;
-    ++p;
-    ws();
-    if (p < e && *p == ']') { ++p; return true; }
-    for (;;) {
+    return array([&] {
       double v;
       if (!number(&v)) return false;
-      out->push_back((int32_t)v);
-      ws();
-      if (p < e && *p == ',') { ++p; continue; }
-      if (p < e && *p == ']') { ++p; return true; }
-      return false;
-    }
+      out->push_back((int32_t)clamp_num(v, -2147483647.0, 2147483647.0));
+      return true;
+    });
+  }
+  // number into *v, or skip whatever else is there (null, a string, ...): *got tells which
+  bool number_or_skip(double* v, bool* got) {
+    const char* save = p;
+    *got = number(v);
+    if (*got) return true;
+    p = save;
+    return skip();
   }
 };
 
-void parse_content(J& j, std::string* text) {  // string or [{type:text,text:..},..]
-  j.ws();
-  if (j.p < j.e && *j.p == '"') { std::string s; if (j.str(&s)) *text += s; return; }
-  if (j.p < j.e && *j.p == '[') {
-    ++j.p;
-    for (;;) {
-      j.ws();
-      if (j.p < j.e && *j.p == ']') { ++j.p; return; }
-      if (j.p < j.e && *j.p == '{') {
-        ++j.p;
-        for (;;) {
-          std::string k;
-          j.ws();
-          if (j.p < j.e && *j.p == '}') { ++j.p; break; }
-          if (!j.str(&k)) return;
-          j.ws(); if (j.p < j.e && *j.p == ':') ++j.p;
-          if (k == "text") { std::string s; if (j.str(&s)) *text += s; } else if (!j.skip()) return;
-          j.ws(); if (j.p < j.e && *j.p == ',') ++j.p;
-        }
-      } else if (!j.skip()) return;
-      j.ws(); if (j.p < j.e && *j.p == ',') ++j.p;
-    }
-  }
-  j.skip();
+bool parse_content(J& j, std::string* text) {  // string or [{type:text,text:..},..]
+  if (j.at('"')) { std::string s; if (!j.str(&s)) return false; *text += s; return true; }
+  if (j.at('['))
+    return j.array([&] {
+      if (!j.at('{')) return j.skip();
+      return j.object([&](const std::string& k) {
+        if (k == "text" && j.at('"')) { std::string s; if (!j.str(&s)) return false; *text += s; return true; }
+        return j.skip();
+      });
+    });
+  return j.skip();
 }
 
-void parse_messages(J& j, std::string* text) {
-  j.ws();
-  if (j.p >= j.e || *j.p != '[') { j.skip(); return; }
-  ++j.p;
-  for (;;) {
-    j.ws();
-    if (j.p < j.e && *j.p == ']') { ++j.p; return; }
-    if (j.p >= j.e || *j.p != '{') return;
-    ++j.p;
-    for (;;) {
-      j.ws();
-      if (j.p < j.e && *j.p == '}') { ++j.p; break; }
-      std::string k;
-      if (!j.str(&k)) return;
-      j.ws(); if (j.p < j.e && *j.p == ':') ++j.p;
-      if (k == "content") { parse_content(j, text); text->push_back('\n'); }
-      else if (!j.skip()) return;
-      j.ws(); if (j.p < j.e && *j.p == ',') ++j.p;
-    }
-    j.ws(); if (j.p < j.e && *j.p == ',') ++j.p;
+bool parse_messages(J& j, std::string* text) {
+  if (!j.at('[')) return j.skip();
+  return j.array([&] {
+    if (!j.at('{')) return j.skip();
+    return j.object([&](const std::string& k) {
+      if (k == "content") { if (!parse_content(j, text)) return false; text->push_back('\n'); return true; }
+      return j.skip();
+    });
+  });
+}
+
+bool parse_sampling(J& j, const std::string& k, ParsedBody* out, bool* used) {
+  double v;
+  bool got;
+  *used = true;
+  if (k == "num_predict" || k == "max_tokens" || k == "max_completion_tokens") {
+    if (!j.number_or_skip(&v, &got)) return false;
+    if (got) out->num_predict = (int)clamp_num(v, -1.0, 1073741824.0);
+  } else if (k == "temperature") {
+    if (!j.number_or_skip(&v, &got)) return false;
+    if (got) { out->temperature = clamp_num(v, 0.0, 1e6); out->has_temperature = true; }
+  } else if (k == "top_k") {
+    if (!j.number_or_skip(&v, &got)) return false;
+    if (got) { out->top_k = (long long)clamp_num(v, 0.0, 1073741824.0); out->has_top_k = true; }
+  } else if (k == "top_p") {
+    if (!j.number_or_skip(&v, &got)) return false;
+    if (got) { out->top_p = clamp_num(v, 0.0, 1.0); out->has_top_p = true; }
+  } else if (k == "seed") {
+    if (!j.number_or_skip(&v, &got)) return false;
+    if (got) { out->seed = (unsigned long long)clamp_num(v, 0.0, 9007199254740992.0); out->has_seed = true; }
+  } else {
+    *used = false;
   }
+  return true;
 }
 }  // namespace
 
 bool parse_body(const std::string& body, int endpoint, ParsedBody* out) {
   (void)endpoint;
   J j{body.data(), body.data() + body.size()};
-  j.ws();
-  if (j.p >= j.e || *j.p != '{') return false;
-  ++j.p;
-  for (;;) {
-    j.ws();
-    if (j.p < j.e && *j.p == '}') return true;
-    std::string k;
-    if (!j.str(&k)) return false;
-    j.ws();
-    if (j.p >= j.e || *j.p != ':') return false;
-    ++j.p;
-    j.ws();
-    if (k == "model") { if (!j.str(&out->model)) return false; }
-    else if (k == "prompt") {
-      if (j.p < j.e && *j.p == '[') { if (!j.int_array(&out->tokens)) return false; }
-      else if (!j.str(&out->text)) { if (!j.skip()) return false; }
+  const bool ok = j.object([&](const std::string& k) {
+    bool used = false;
+    if (k == "model") return j.at('"') ? j.str(&out->model) : j.skip();
+    if (k == "prompt") {
+      if (j.at('[')) return j.int_array(&out->tokens);
+      if (j.at('"')) return j.str(&out->text);
+      return j.skip();
     }
-    else if (k == "context") { if (!j.int_array(&out->tokens)) return false; }
-    else if (k == "messages") parse_messages(j, &out->text);
-    else if (k == "stream") {
-      out->has_stream = true;
-      if (j.lit("true")) out->stream = true; else if (j.lit("false")) out->stream = false; else if (!j.skip()) return false;
-    }
-    else if (k == "max_tokens" || k == "max_completion_tokens" || k == "num_predict") {
-      double v; if (!j.number(&v)) { if (!j.skip()) return false; } else out->num_predict = (int)v;
-    }
-    else if (k == "temperature") { double v; if (j.number(&v)) { out->temperature = v; out->has_temperature = true; } else if (!j.skip()) return false; }
-    else if (k == "top_p") { double v; if (j.number(&v)) { out->top_p = v; out->has_top_p = true; } else if (!j.skip()) return false; }
-    else if (k == "seed") { double v; if (j.number(&v)) { out->seed = (unsigned long long)v; out->has_seed = true; } else if (!j.skip()) return false; }
-    else if (k == "options") {
+    if (k == "context") return j.at('[') ? j.int_array(&out->tokens) : j.skip();
+    if (k == "messages") return parse_messages(j, &out->text);
+    if (k == "stream") {
       j.ws();
-      if (j.p < j.e && *j.p == '{') {
-        ++j.p;
-        for (;;) {
-          j.ws();
-          if (j.p < j.e && *j.p == '}') { ++j.p; break; }
-          std::string ok;
-          if (!j.str(&ok)) return false;
-          j.ws(); if (j.p < j.e && *j.p == ':') ++j.p;
-          if (ok == "num_predict") { double v; if (j.number(&v)) out->num_predict = (int)v; else if (!j.skip()) return false; }
-          else if (ok == "temperature") { double v; if (j.number(&v)) { out->temperature = v; out->has_temperature = true; } else if (!j.skip()) return false; }
-          else if (ok == "top_k") { double v; if (j.number(&v)) { out->top_k = (long long)v; out->has_top_k = true; } else if (!j.skip()) return false; }
-          else if (ok == "top_p") { double v; if (j.number(&v)) { out->top_p = v; out->has_top_p = true; } else if (!j.skip()) return false; }
-          else if (ok == "seed") { double v; if (j.number(&v)) { out->seed = (unsigned long long)v; out->has_seed = true; } else if (!j.skip()) return false; }
-          else if (!j.skip()) return false;
-          j.ws(); if (j.p < j.e && *j.p == ',') ++j.p;
-        }
-      } else if (!j.skip()) return false;
+      if (j.lit("true")) { out->has_stream = true; out->stream = true; return true; }
+      if (j.lit("false")) { out->has_stream = true; out->stream = false; return true; }
+      return j.skip();
     }
-    else if (!j.skip()) return false;
-    j.ws();
-    if (j.p < j.e && *j.p == ',') ++j.p;
-  }
+    if (k == "options") {
+      if (!j.at('{')) return j.skip();
+      return j.object([&](const std::string& ok2) {
+        bool u2 = false;
+        if (!parse_sampling(j, ok2, out, &u2)) return false;
+        return u2 ? true : j.skip();
+      });
+    }
+    if (k != "top_k") {  // OpenAI top level: temperature, top_p, seed, max_tokens (top_k lives in Ollama's options only)
+      if (!parse_sampling(j, k, out, &used)) return false;
+      if (used) return true;
+    }
+    return j.skip();
+  });
+  if (!ok) return false;
+  j.ws();
+  return j.p == j.e;  // nothing but whitespace after the object
 }
 
 // deterministic byte-level tokenizer: random-init weights have no vocabulary
@@ -248,36 +296,33 @@ static std::string now_iso() {
   return b;
 }
 
+// model names are client-visible strings of ours (cfg.model_name) or, for embeddings, of the client's: cap them so a
+// frame stays a frame
+static std::string model_field(const char* model) {
+  std::string m = model ? model : "";
+  if (m.size() > 256) m.resize(256);
+  return json_escape(m);
+}
+
 std::string frame_token(int endpoint, const char* model, int tok) {
-  const std::string m = json_escape(model), txt = json_escape(token_text(tok));
-  char buf[512];
+  const std::string m = model_field(model), txt = json_escape(token_text(tok));
   switch (endpoint) {
     case MQ_EP_API_GENERATE:
-      snprintf(buf, sizeof(buf), "{\"model\":\"%s\",\"created_at\":\"%s\",\"response\":\"%s\",\"done\":false}\n",
-               m.c_str(), now_iso().c_str(), txt.c_str());
-      break;
+      return "{\"model\":\"" + m + "\",\"created_at\":\"" + now_iso() + "\",\"response\":\"" + txt + "\",\"done\":false}\n";
     case MQ_EP_API_CHAT:
-      snprintf(buf, sizeof(buf),
-               "{\"model\":\"%s\",\"created_at\":\"%s\",\"message\":{\"role\":\"assistant\",\"content\":\"%s\"},\"done\":false}\n",
-               m.c_str(), now_iso().c_str(), txt.c_str());
-      break;
+      return "{\"model\":\"" + m + "\",\"created_at\":\"" + now_iso() + "\",\"message\":{\"role\":\"assistant\",\"content\":\"" + txt +
+             "\"},\"done\":false}\n";
     case MQ_EP_V1_CHAT:
-      snprintf(buf, sizeof(buf),
-               "data: {\"id\":\"chatcmpl-mq\",\"object\":\"chat.completion.chunk\",\"created\":%ld,\"model\":\"%s\","
-               "\"choices\":[{\"index\":0,\"delta\":{\"content\":\"%s\"},\"finish_reason\":null}]}\n\n",
-               (long)time(nullptr), m.c_str(), txt.c_str());
-      break;
+      return "data: {\"id\":\"chatcmpl-mq\",\"object\":\"chat.completion.chunk\",\"created\":" + std::to_string((long)time(nullptr)) +
+             ",\"model\":\"" + m + "\",\"choices\":[{\"index\":0,\"delta\":{\"content\":\"" + txt + "\"},\"finish_reason\":null}]}\n\n";
     default:
-      snprintf(buf, sizeof(buf),
-               "data: {\"id\":\"cmpl-mq\",\"object\":\"text_completion\",\"created\":%ld,\"model\":\"%s\","
-               "\"choices\":[{\"text\":\"%s\",\"index\":0,\"finish_reason\":null}]}\n\n",
-               (long)time(nullptr), m.c_str(), txt.c_str());
+      return "data: {\"id\":\"cmpl-mq\",\"object\":\"text_completion\",\"created\":" + std::to_string((long)time(nullptr)) +
+             ",\"model\":\"" + m + "\",\"choices\":[{\"text\":\"" + txt + "\",\"index\":0,\"finish_reason\":null}]}\n\n";
   }
-  return buf;
 }
 
 void other_route_response(const std::string& path, const char* model, int* status, std::string* ctype, std::string* body) {
-  const std::string m = json_escape(model);
+  const std::string m = model_field(model);
   *status = 200;
   *ctype = "application/json";
   if (path == "/") {
@@ -303,9 +348,9 @@ std::string frame_final(int endpoint, int stream, const char* model, const std::
                         bool stopped) {
   const char* why = stopped ? "stop" : "length";  // EOS reached vs generation budget spent
   if (endpoint == MQ_EP_RAW_TOKENS) return stream ? std::string() : agg;
-  const std::string m = json_escape(model), txt = json_escape(agg);
+  const std::string m = model_field(model), txt = json_escape(agg);
   std::string o;
-  char buf[512];
+  char buf[256];  // integers and the fixed words only: cannot truncate
   if (endpoint == MQ_EP_API_GENERATE || endpoint == MQ_EP_API_CHAT) {
     o = "{\"model\":\"" + m + "\",\"created_at\":\"" + now_iso() + "\",";
     if (endpoint == MQ_EP_API_GENERATE) o += "\"response\":\"" + (stream ? std::string() : txt) + "\",";
@@ -316,13 +361,11 @@ std::string frame_final(int endpoint, int stream, const char* model, const std::
   }
   const bool chat = endpoint == MQ_EP_V1_CHAT;
   if (stream) {
-    snprintf(buf, sizeof(buf),
-             chat ? "data: {\"id\":\"chatcmpl-mq\",\"object\":\"chat.completion.chunk\",\"created\":%ld,\"model\":\"%s\","
-                    "\"choices\":[{\"index\":0,\"delta\":{},\"finish_reason\":\"%s\"}]}\n\ndata: [DONE]\n\n"
-                  : "data: {\"id\":\"cmpl-mq\",\"object\":\"text_completion\",\"created\":%ld,\"model\":\"%s\","
-                    "\"choices\":[{\"text\":\"\",\"index\":0,\"finish_reason\":\"%s\"}]}\n\ndata: [DONE]\n\n",
-             (long)time(nullptr), m.c_str(), why);
-    return buf;
+    const std::string head = std::string(chat ? "data: {\"id\":\"chatcmpl-mq\",\"object\":\"chat.completion.chunk\",\"created\":"
+                                              : "data: {\"id\":\"cmpl-mq\",\"object\":\"text_completion\",\"created\":") +
+                             std::to_string((long)time(nullptr)) + ",\"model\":\"" + m + "\",";
+    return head + (chat ? "\"choices\":[{\"index\":0,\"delta\":{},\"finish_reason\":\"" : "\"choices\":[{\"text\":\"\",\"index\":0,\"finish_reason\":\"") +
+           why + "\"}]}\n\ndata: [DONE]\n\n";
   }
   snprintf(buf, sizeof(buf), "\"usage\":{\"prompt_tokens\":%d,\"completion_tokens\":%d,\"total_tokens\":%d}}", n_prompt,
            n_gen, n_prompt + n_gen);
@@ -340,58 +383,34 @@ std::string frame_final(int endpoint, int stream, const char* model, const std::
 // ------------------------------------------------------------------ embeddings
 bool parse_embed_body(const std::string& body, ParsedEmbed* out) {
   J j{body.data(), body.data() + body.size()};
-  j.ws();
-  if (j.p >= j.e || *j.p != '{') return false;
-  ++j.p;
-  for (;;) {
-    j.ws();
-    if (j.p < j.e && *j.p == '}') return true;
-    std::string k;
-    if (!j.str(&k)) return false;
-    j.ws();
-    if (j.p >= j.e || *j.p != ':') return false;
+  const bool ok = j.object([&](const std::string& k) {
+    if (k == "model") return j.at('"') ? j.str(&out->model) : j.skip();
+    if (k != "input" && k != "prompt") return j.skip();
+    if (j.at('"')) { std::string s; if (!j.str(&s)) return false; out->texts.push_back(s); return true; }
+    if (!j.at('[')) return j.skip();
+    // ["s", ...] | [[ids], ...] | [ids]: decided by the first element
+    const char* save = j.p;
     ++j.p;
     j.ws();
-    if (k == "model") { if (!j.str(&out->model)) return false; }
-    else if (k == "input" || k == "prompt") {
-      if (j.p < j.e && *j.p == '"') { std::string s; if (!j.str(&s)) return false; out->texts.push_back(s); }
-      else if (j.p < j.e && *j.p == '[') {
-        const char* save = j.p;
-        ++j.p;
-        j.ws();
-        if (j.p < j.e && *j.p == ']') { ++j.p; }
-        else if (*j.p == '"') {                       // ["s", ...]
-          for (;;) {
-            std::string s;
-            if (!j.str(&s)) return false;
-            out->texts.push_back(s);
-            j.ws();
-            if (j.p < j.e && *j.p == ',') { ++j.p; continue; }
-            if (j.p < j.e && *j.p == ']') { ++j.p; break; }
-            return false;
-          }
-        } else if (*j.p == '[') {                     // [[ids], ...]
-          for (;;) {
-            std::vector<int32_t> t;
-            if (!j.int_array(&t)) return false;
-            out->token_seqs.push_back(t);
-            j.ws();
-            if (j.p < j.e && *j.p == ',') { ++j.p; continue; }
-            if (j.p < j.e && *j.p == ']') { ++j.p; break; }
-            return false;
-          }
-        } else {                                      // [ids]
-          j.p = save;
-          std::vector<int32_t> t;
-          if (!j.int_array(&t)) return false;
-          out->token_seqs.push_back(t);
-        }
-      } else if (!j.skip()) return false;
-    }
-    else if (!j.skip()) return false;
-    j.ws();
-    if (j.p < j.e && *j.p == ',') ++j.p;
-  }
+    const char first = j.p < j.e ? *j.p : 0;
+    j.p = save;
+    if (first == '"') return j.array([&] { std::string s; if (!j.str(&s)) return false; out->texts.push_back(s); return true; });
+    if (first == '[')
+      return j.array([&] {
+        std::vector<int32_t> t;
+        if (!j.int_array(&t)) return false;
+        out->token_seqs.push_back(t);
+        return true;
+      });
+    if (first == ']') return j.skip();
+    std::vector<int32_t> t;
+    if (!j.int_array(&t)) return false;
+    out->token_seqs.push_back(t);
+    return true;
+  });
+  if (!ok) return false;
+  j.ws();
+  return j.p == j.e;
 }
 
 std::vector<int32_t> embed_tokenize(const std::string& text, int vocab, int max_len) {
@@ -417,10 +436,10 @@ static void append_vec(std::string& o, const float* v, int dim) {
   o += ']';
 }
 std::string frame_embeddings(const std::string& path, const char* model, const float* emb, int n, int dim, int n_tokens) {
-  const std::string m = json_escape(model);
+  const std::string m = model_field(model);
   std::string o;
   o.reserve((size_t)n * dim * 14 + 256);
-  char b[160];
+  char b[96];  // integers only
   if (path == "/api/embeddings") {  // legacy Ollama route: one prompt, one vector
     o = "{\"embedding\":";
     append_vec(o, emb, n > 0 ? dim : 0);
@@ -435,8 +454,8 @@ std::string frame_embeddings(const std::string& path, const char* model, const f
       snprintf(b, sizeof b, ",\"index\":%d}", i);
       o += b;
     }
-    snprintf(b, sizeof b, "],\"model\":\"%s\",\"usage\":{\"prompt_tokens\":%d,\"total_tokens\":%d}}", m.c_str(), n_tokens, n_tokens);
-    return o + b;
+    snprintf(b, sizeof b, "\",\"usage\":{\"prompt_tokens\":%d,\"total_tokens\":%d}}", n_tokens, n_tokens);
+    return o + "],\"model\":\"" + m + b;
   }
   o = "{\"model\":\"" + m + "\",\"embeddings\":[";
   for (int i = 0; i < n; ++i) {

@@ -38,28 +38,28 @@ bool tmap_encode_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
 // output tile map: row-major [.., T, ldo] with the feature dimension innermost; rows >= T and features >= n_out are
 // outside the tensor and therefore dropped by the TMA store
 static bool tmap_encode_out(CUtensorMap* out, void* base, int epi, int n_out, int T, int ldo, int splits,
-                            long long split_stride, int bn) {
+                            long long split_stride, int bn, int tile_rows) {
   auto fn = get_encode_fn();
   if (!fn) return false;
   const cuuint32_t estr[3] = {1, 1, 1};
   if (epi == EPI_F32) {
     const cuuint64_t dims[3] = {(cuuint64_t)n_out, (cuuint64_t)T, (cuuint64_t)splits};
     const cuuint64_t strides[2] = {(cuuint64_t)ldo * 4, (cuuint64_t)(splits > 1 ? split_stride : (long long)T * ldo) * 4};
-    const cuuint32_t box[3] = {(cuuint32_t)kBlockM, (cuuint32_t)bn, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)tile_rows, (cuuint32_t)bn, 1};
     return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
   }
   const cuuint64_t dims[2] = {(cuuint64_t)n_out, (cuuint64_t)T};
   const cuuint64_t strides[1] = {(cuuint64_t)ldo * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kBlockM, (cuuint32_t)bn};
+  const cuuint32_t box[2] = {(cuuint32_t)tile_rows, (cuuint32_t)bn};
   return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, int EPI, bool DEEP>
+template <int BN, int EPI>
 static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const GemmParams& p,
                               dim3 grid, const LaunchCfg& lc) {
-  constexpr int smem = gemm_smem_bytes(BN, EPI, DEEP);
+  constexpr int smem = gemm_smem_bytes(BN, EPI);
   // dynamic-smem opt-in happens once per device in gemm_set_attrs() (never inside a graph capture)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
@@ -71,24 +71,18 @@ static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = lc.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gemm_wx_kernel<BN, EPI, DEEP>, a, b, c, p);
+  return cudaLaunchKernelEx(&cfg, gemm_wx_kernel<BN, EPI>, a, b, c, p);
 }
 
 template <int EPI>
-static cudaError_t launch_bn(int bn, bool deep, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+static cudaError_t launch_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
                              const GemmParams& p, dim3 grid, const LaunchCfg& lc) {
-  if (!deep) switch (bn) {  // only the decode tile widths have a shallow variant
-      case 16: return launch_one<16, EPI, false>(a, b, c, p, grid, lc);
-      case 32: return launch_one<32, EPI, false>(a, b, c, p, grid, lc);
-      case 64: return launch_one<64, EPI, false>(a, b, c, p, grid, lc);
-      default: break;
-    }
   switch (bn) {
-    case 16: return launch_one<16, EPI, true>(a, b, c, p, grid, lc);
-    case 32: return launch_one<32, EPI, true>(a, b, c, p, grid, lc);
-    case 64: return launch_one<64, EPI, true>(a, b, c, p, grid, lc);
-    case 128: return launch_one<128, EPI, true>(a, b, c, p, grid, lc);
-    case 256: return launch_one<256, EPI, true>(a, b, c, p, grid, lc);
+    case 16: return launch_one<16, EPI>(a, b, c, p, grid, lc);
+    case 32: return launch_one<32, EPI>(a, b, c, p, grid, lc);
+    case 64: return launch_one<64, EPI>(a, b, c, p, grid, lc);
+    case 128: return launch_one<128, EPI>(a, b, c, p, grid, lc);
+    case 256: return launch_one<256, EPI>(a, b, c, p, grid, lc);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -122,7 +116,7 @@ static cudaError_t launch_pk(const GemmPlan& g, const LaunchCfg& lc) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g.pk.n_ctas);
   cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = gemm_smem_bytes(BN, EPI, true);
+  cfg.dynamicSmemBytes = gemm_smem_bytes(BN, EPI);
   cfg.stream = lc.stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -166,11 +160,11 @@ cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
     }
   dim3 grid(g.p.m_tiles * g.p.n_tiles, 1, g.splits);
   switch (g.epi) {
-    case EPI_F32: return launch_bn<EPI_F32>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
-    case EPI_BF16: return launch_bn<EPI_BF16>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
-    case EPI_SILU_BF16: return launch_bn<EPI_SILU_BF16>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
-    case EPI_GELU_BF16: return launch_bn<EPI_GELU_BF16>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
-    case EPI_BIAS_BF16: return launch_bn<EPI_BIAS_BF16>(g.bn, g.deep, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
+    case EPI_F32: return launch_bn<EPI_F32>(g.bn, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
+    case EPI_BF16: return launch_bn<EPI_BF16>(g.bn, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
+    case EPI_SILU_BF16: return launch_bn<EPI_SILU_BF16>(g.bn, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
+    case EPI_GELU_BF16: return launch_bn<EPI_GELU_BF16>(g.bn, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
+    case EPI_BIAS_BF16: return launch_bn<EPI_BIAS_BF16>(g.bn, g.tmA, g.tmB, g.tmC, g.p, grid, lc);
     default: return cudaErrorInvalidValue;
   }
 }
@@ -181,11 +175,7 @@ static void set_attrs_sk() {
 }
 template <int BN, int EPI>
 static void set_attrs_one() {
-  cudaFuncSetAttribute(gemm_wx_kernel<BN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       gemm_smem_bytes(BN, EPI, true));
-  if (BN <= 64)
-    cudaFuncSetAttribute(gemm_wx_kernel<(BN <= 64 ? BN : 64), EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         gemm_smem_bytes(BN <= 64 ? BN : 64, EPI, false));
+  cudaFuncSetAttribute(gemm_wx_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(BN, EPI));
 }
 template <int EPI>
 static void set_attrs_epi() {
@@ -197,7 +187,9 @@ static void set_attrs_epi() {
 }
 // Opt every instantiation into its dynamic shared memory size up front (per device), so nothing but
 // launches happens while a decode step is being captured into a CUDA graph.
+void dk_set_attrs();
 void gemm_set_attrs() {
+  dk_set_attrs();
   set_attrs_epi<EPI_F32>();
   set_attrs_epi<EPI_BF16>();
   set_attrs_epi<EPI_SILU_BF16>();
@@ -209,10 +201,10 @@ void gemm_set_attrs() {
   cudaFuncSetAttribute(gemm_2cta_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_F32));
   cudaFuncSetAttribute(gemm_2cta_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_BF16));
   cudaFuncSetAttribute(gemm_2cta_kernel<EPI_SILU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_SILU_BF16));
-  cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_BF16, true));
-  cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_F32, true));
-  cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_BF16, true));
-  cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_F32, true));
+  cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_BF16));
+  cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_F32));
+  cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_BF16));
+  cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_F32));
 }
 
 // MQ_2CTA=0 turns the cta_group::2 prefill kernel off (A/B switch)
@@ -276,34 +268,6 @@ void streamk_workspace_free(StreamKWorkspace* w) {
   w->flags = nullptr;
 }
 
-// MQ_GEMM_SHALLOW=1 selects the co-residency-friendly (<=120 KiB) pipeline for decode tiles.  Measured on B200
-// (r01): shallow 4.64 ms/decode step vs deep 4.36 ms -> deep stays the default; the switch is kept for profiling.
-static bool decode_tiles_shallow() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("MQ_GEMM_SHALLOW");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
-}
-
-void gemm_plan_fuse_norm(GemmPlan* g, float* h, const float* partial, int n_planes, long long plane_stride,
-                         const void* gamma, void* x, int H, float eps, int* counter) {
-  if (g->streamk || g->p.n_tiles != 1) return;  // decode tile widths, split-K kernel only
-  g->p.norm_h = h;
-  g->p.norm_partial = partial;
-  g->p.norm_planes = n_planes;
-  g->p.norm_plane_stride = plane_stride;
-  g->p.norm_gamma = gamma;
-  g->p.norm_x = x;
-  g->p.norm_H = H;
-  g->p.norm_eps = eps;
-  g->p.norm_counter = counter;
-  const int ctas = g->p.m_tiles * g->splits;
-  // rows go to the lowest CTA ids only: those are scheduled first, so the spin in the producers cannot starve them
-  g->p.norm_ctas = ctas < 96 ? ctas : 96;
-}
-
 int gemm_pick_bn(int T) {
   if (T <= 16) return 16;
   if (T <= 32) return 32;
@@ -312,9 +276,16 @@ int gemm_pick_bn(int T) {
   return 256;
 }
 
+int gemm_balanced_rows(int n_out) {
+  const int sms = device_sm_count();
+  if ((n_out + kBlockM - 1) / kBlockM >= sms) return kBlockM;  // more 128-row tiles than SMs anyway
+  int r = ((n_out + sms - 1) / sms + 7) & ~7;
+  return r < 64 ? 64 : (r > kBlockM ? kBlockM : r);
+}
+
 bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T,
                int epi, void* out, int ldo, int splits, long long split_stride, int a2_row_off,
-               const StreamKWorkspace* sk) {
+               const StreamKWorkspace* sk, int tile_rows) {
   if (K % kBlockK != 0) return false;
   const int kb = K / kBlockK;
   g->streamk = sk != nullptr && sk->ws != nullptr && T <= 64 && epi != EPI_GELU_BF16 && epi != EPI_BIAS_BF16 && streamk_pick((n_out + kBlockM - 1) / kBlockM, sk);
@@ -326,12 +297,13 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   // one token tile, no split-K and fewer weight tiles than half the SMs (Phi-3 gate/up at 256 slots: 64 tiles): halve
   // the token tile so two CTAs share each weight tile through L2 - same HBM bytes, twice the SMs streaming them
   if (T > 128 && T <= 256 && splits == 1 && (n_out + kBlockM - 1) / kBlockM * 2 <= device_sm_count()) g->bn = 128;
-  g->deep = !(g->bn <= 64 && decode_tiles_shallow());
   g->epi = epi;
   g->splits = splits;
-  if (!tmap_encode_2d(&g->tmA, W, (uint64_t)w_rows, (uint64_t)K, kBlockM)) return false;
+  // tile_rows < 128 only for the plain decode-width kernel (one token tile): see GemmParams::tile_rows
+  if (tile_rows <= 0 || tile_rows > kBlockM || tile_rows % 8 != 0 || g->streamk || T > g->bn) tile_rows = kBlockM;
+  if (!tmap_encode_2d(&g->tmA, W, (uint64_t)w_rows, (uint64_t)K, (uint32_t)tile_rows)) return false;
   if (!tmap_encode_2d(&g->tmB, X, (uint64_t)x_rows_alloc, (uint64_t)K, (uint32_t)g->bn)) return false;
-  if (!tmap_encode_out(&g->tmC, out, epi, n_out, T, ldo, splits, split_stride, g->bn)) return false;
+  if (!tmap_encode_out(&g->tmC, out, epi, n_out, T, ldo, splits, split_stride, g->bn, tile_rows)) return false;
   g->p = GemmParams{};
   g->p.out = out;
   g->p.split_stride = split_stride;
@@ -341,7 +313,8 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   g->p.k_blocks = kb;
   g->p.kb_per_split = kbps;
   g->p.a2_row_off = a2_row_off;
-  g->p.m_tiles = (n_out + kBlockM - 1) / kBlockM;
+  g->p.tile_rows = tile_rows;
+  g->p.m_tiles = (n_out + tile_rows - 1) / tile_rows;
   g->p.n_tiles = (T + g->bn - 1) / g->bn;
   // super-tile height: minimise the bytes one wave of 148 CTAs must pull through L2,
   //   group_m * (weight tile bytes) + (148 / group_m) * (activation tile bytes)
@@ -351,7 +324,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   if (gm > g->p.m_tiles) gm = g->p.m_tiles;
   g->p.group_m = g->p.n_tiles == 1 ? g->p.m_tiles : gm;
   g->p.w_policy = g->p.n_tiles == 1 ? kEvictFirst : kEvictNormal;  // decode streams weights exactly once
-  g->twocta = !g->streamk && g->bn == 256 && splits == 1 && n_out % 256 == 0 && epi != EPI_GELU_BF16 && epi != EPI_BIAS_BF16 && twocta_enabled();
+  g->twocta = !g->streamk && tile_rows == kBlockM && g->bn == 256 && splits == 1 && n_out % 256 == 0 && epi != EPI_GELU_BF16 && epi != EPI_BIAS_BF16 && twocta_enabled();
   if (g->twocta) {
     // the pair computes 256 features x 256 tokens: every CTA stages only its own 128-token half of the activation tile
     if (!tmap_encode_2d(&g->tmB, X, (uint64_t)x_rows_alloc, (uint64_t)K, 128)) return false;
@@ -364,7 +337,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
     g->c2.w_policy = g->p.w_policy;
   }
   g->persist = false;
-  if (!g->twocta && !g->streamk && epi != EPI_SILU_BF16 && epi != EPI_GELU_BF16 && epi != EPI_BIAS_BF16 && g->bn >= 128 && splits == 1 && persist_enabled()) {
+  if (!g->twocta && !g->streamk && tile_rows == kBlockM && epi != EPI_SILU_BF16 && epi != EPI_GELU_BF16 && epi != EPI_BIAS_BF16 && g->bn >= 128 && splits == 1 && persist_enabled()) {
     const int sms = device_sm_count();
     const int tiles = g->p.m_tiles * g->p.n_tiles;
     if (tiles >= 2 * sms) {  // at least two tiles per CTA, otherwise there is nothing to overlap
@@ -390,6 +363,111 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
     g->sk.w_policy = kEvictFirst;
   }
   return true;
+}
+
+// ------------------------------------------------------------------------------------------------ decode chain
+void gemm_plan_set_rstd(GemmPlan* g, const RstdIn& rs) {
+  g->p.rs = rs;
+  g->sk.rs = rs;
+}
+
+template <int BN, int EPI>
+static int dk_query_clusters(int cs) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(cs * 64);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = dk_smem_bytes(BN);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_dk_kernel<BN, EPI>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+// clusters of `cs` CTAs (one per SM, ~200 KiB of shared memory each) the device runs at once; cached per process
+int dk_max_clusters(int cs) {
+  static int cache[kDkMaxCluster + 1] = {0};
+  static std::once_flag once;
+  std::call_once(once, [] {
+    for (int c = 1; c <= kDkMaxCluster; ++c) cache[c] = c == 1 ? device_sm_count() : dk_query_clusters<64, DK_RESID>(c);
+  });
+  return (cs >= 1 && cs <= kDkMaxCluster) ? cache[cs] : 0;
+}
+
+// Cluster size (= K splits) for a decode-chain GEMM: the most CTAs that are all resident at once, with >= 4 k-blocks
+// per rank, and few enough tokens per rank for the register-resident epilogue (kDkMaxTok).
+int dk_pick_cluster(int m_tiles, int k_blocks, int T) {
+  int best = 0, best_ctas = 0;
+  for (int cs = 1; cs <= kDkMaxCluster; ++cs) {
+    if (m_tiles > dk_max_clusters(cs)) continue;
+    if (cs > 1 && k_blocks / cs < 4) continue;
+    if ((T + cs - 1) / cs > kDkMaxTok) continue;
+    if (m_tiles * cs > best_ctas) { best = cs; best_ctas = m_tiles * cs; }
+  }
+  return best;  // 0: shape not servable by the chain kernel (caller falls back to the plane-based path)
+}
+
+bool dk_plan(DkPlan* g, int epi, const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T,
+             int tile_rows, int cs) {
+  if (K % kBlockK != 0 || T < 1 || T > 64 || tile_rows < 8 || tile_rows > kBlockM || tile_rows % 8 != 0) return false;
+  const int kb = K / kBlockK;
+  const int m_tiles = (n_out + tile_rows - 1) / tile_rows;
+  if (cs <= 0) cs = dk_pick_cluster(m_tiles, kb, T);
+  if (cs < 1 || cs > kDkMaxCluster || (T + cs - 1) / cs > kDkMaxTok) return false;
+  g->bn = gemm_pick_bn(T);
+  g->epi = epi;
+  g->cs = cs;
+  g->m_tiles = m_tiles;
+  if (!tmap_encode_2d(&g->tmA, W, (uint64_t)w_rows, (uint64_t)K, (uint32_t)tile_rows)) return false;
+  if (!tmap_encode_2d(&g->tmB, X, (uint64_t)x_rows_alloc, (uint64_t)K, (uint32_t)g->bn)) return false;
+  g->p = DkParams{};
+  g->p.T = T;
+  g->p.n_out = n_out;
+  g->p.tile_rows = tile_rows;
+  g->p.k_blocks = kb;
+  g->p.kb_per_split = (kb + cs - 1) / cs;
+  g->p.w_policy = kEvictFirst;  // decode streams every weight exactly once
+  return true;
+}
+
+template <int BN, int EPI>
+static cudaError_t launch_dk(const DkPlan& g, const LaunchCfg& lc) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g.m_tiles * g.cs);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = dk_smem_bytes(BN);
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = g.cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lc.pdl ? 2 : 1;
+  return cudaLaunchKernelEx(&cfg, gemm_dk_kernel<BN, EPI>, g.tmA, g.tmB, g.p);
+}
+template <int EPI>
+static cudaError_t launch_dk_bn(const DkPlan& g, const LaunchCfg& lc) {
+  switch (g.bn) {
+    case 16: return launch_dk<16, EPI>(g, lc);
+    case 32: return launch_dk<32, EPI>(g, lc);
+    case 64: return launch_dk<64, EPI>(g, lc);
+    default: return cudaErrorInvalidValue;
+  }
+}
+cudaError_t dk_launch(const DkPlan& g, const LaunchCfg& lc) {
+  return g.epi == DK_QKV ? launch_dk_bn<DK_QKV>(g, lc) : launch_dk_bn<DK_RESID>(g, lc);
+}
+template <int BN, int EPI>
+static void set_attrs_dk() {
+  cudaFuncSetAttribute(gemm_dk_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, dk_smem_bytes(BN));
+  cudaFuncSetAttribute(gemm_dk_kernel<BN, EPI>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+}
+void dk_set_attrs() {
+  set_attrs_dk<16, DK_RESID>(); set_attrs_dk<32, DK_RESID>(); set_attrs_dk<64, DK_RESID>();
+  set_attrs_dk<16, DK_QKV>(); set_attrs_dk<32, DK_QKV>(); set_attrs_dk<64, DK_QKV>();
 }
 
 }  // namespace mq

@@ -29,6 +29,23 @@ enum GemmEpilogue : int {
   EPI_BIAS_BF16 = 4  // out_bf16[t][f]   = acc + bias[f]             (encoder QKV; plain 1-CTA kernel only)
 };
 
+// RMSNorm fold (decode chain): the activation operand of a GEMM is xg = bf16(h * gamma) and the epilogue scales token
+// column t of the accumulator by rstd[t] = rsqrt(sum_i ssq[i * stride + t] * inv_h + eps).  `ssq` holds per-weight-tile
+// partial sums of h^2 written by the producer of h (gemm_dk.cuh DK_RESID, or the embedding gather: 1 part); they are
+// added in index order, so the result does not depend on scheduling.  ssq == nullptr: no scaling.
+struct RstdIn {
+  const float* ssq;
+  int parts;
+  int stride;
+  float inv_h;
+  float eps;
+};
+__device__ __forceinline__ float rstd_of(const RstdIn& r, int t) {
+  float s = 0.f;
+  for (int i = 0; i < r.parts; ++i) s += __ldcg(r.ssq + (size_t)i * r.stride + t);
+  return rsqrtf(s * r.inv_h + r.eps);
+}
+
 struct GemmParams {
   void* out;               // (kept for reference; the epilogue writes through the tmC tensor map)
   long long split_stride;  // elements between split-K planes of `out`
@@ -40,20 +57,14 @@ struct GemmParams {
   int a2_row_off;          // EPI_SILU_BF16: row offset of the "up" half inside W
   int m_tiles, n_tiles;    // tile grid; blockIdx.x = linear tile id, rasterised in groups of `group_m` weight tiles
   int group_m;             // so that one wave of 148 CTAs touches ~group_m weight tiles x ~148/group_m token tiles
+  int tile_rows;           // weight rows per tile: 128, or fewer (multiple of 8) so that m_tiles ~ the SM count: an
+                           // HBM-bound launch is as fast as its busiest SM (14336 gate/up rows: 112 tiles of 128 rows leave
+                           // 36 SMs idle, 138 tiles of 104 rows do not).  The MMA still runs M = 128; lanes >= tile_rows
+                           // hold garbage that is never read.
   unsigned long long w_policy;  // L2 policy for weight tiles: stream-once (decode) vs re-used inside a wave (prefill)
-  // ---- optional fused prologue (decode): h += sum(partial planes); x = RMSNorm(h) * gamma, where x IS this GEMM's
-  // activation operand.  Row r is normalised by the epilogue warps of CTA (r % norm_ctas) while every producer
-  // already streams weights; producers wait for `norm_counter` to reach T before they load activations.
-  float* norm_h;                 // nullptr = no fused prologue
-  const float* norm_partial;     // fp32 planes [n_planes][plane_stride] (row-major [T][H])
-  const void* norm_gamma;        // bf16 [H]
-  void* norm_x;                  // bf16 [T][H]
-  int* norm_counter;             // zero at kernel start, += 1 per finished row
-  long long norm_plane_stride;
-  int norm_planes, norm_H, norm_ctas;
-  float norm_eps;
-  Trace tr;                      // optional timeline stamps (MQ_TRACE=1)
-  const void* bias;              // EPI_GELU_BF16 / EPI_BIAS_BF16: bf16 [n_out] (nullable)
+  RstdIn rs;                    // optional RMSNorm fold (see above)
+  Trace tr;                     // optional timeline stamps (MQ_TRACE=1)
+  const void* bias;             // EPI_GELU_BF16 / EPI_BIAS_BF16: bf16 [n_out] (nullable)
 };
 
 constexpr int kGemmThreads = 192;
@@ -64,32 +75,29 @@ constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
 __host__ __device__ constexpr int gemm_stage_bytes(int bn, int epi) {
   return kATileBytes * (epi == EPI_SILU_BF16 ? 2 : 1) + bn * kBlockK * 2;
 }
-// deep = true : fill the SM (up to 8 stages / 200 KiB) - one CTA per SM, best for tensor-bound prefill tiles.
-// deep = false: decode tiles (BN <= 64) stay under ~120 KiB so that the CTA of the NEXT kernel in the PDL chain
-//               can already be resident on the same SM and stream its first weight tiles while this one drains.
-__host__ __device__ constexpr int gemm_stages(int bn, int epi, bool deep = true) {
-  int budget = 200 * 1024;
-  if (!deep && bn <= 64) budget = (epi == EPI_SILU_BF16 ? 122 : 98) * 1024;
-  int s = budget / gemm_stage_bytes(bn, epi);
+// The ring fills the SM (up to 8 stages / 200 KiB), one CTA per SM.  (r01 A/B: a <= 120 KiB ring that lets the next
+// kernel's CTA be co-resident was slower, 4.64 vs 4.36 ms per decode step - bytes in flight per SM win.)
+__host__ __device__ constexpr int gemm_stages(int bn, int epi) {
+  int s = (200 * 1024) / gemm_stage_bytes(bn, epi);
   return s > 8 ? 8 : (s < 2 ? 2 : s);
 }
 __host__ __device__ constexpr int gemm_out_tile_bytes(int bn, int epi) {
-  return bn * kBlockM * (epi == EPI_F32 ? 4 : 2);  // epilogue staging tile [BN tokens][128 features]
+  return bn * kBlockM * (epi == EPI_F32 ? 4 : 2);  // epilogue staging tile [BN tokens][<= 128 features]
 }
-__host__ __device__ constexpr int gemm_smem_bytes(int bn, int epi, bool deep = true) {
-  return gemm_stages(bn, epi, deep) * gemm_stage_bytes(bn, epi) + 1024 /*align*/ + 256 /*barriers*/;
+__host__ __device__ constexpr int gemm_smem_bytes(int bn, int epi) {
+  return gemm_stages(bn, epi) * gemm_stage_bytes(bn, epi) + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*rstd[BN]*/;
 }
 __host__ __device__ constexpr uint32_t gemm_tmem_cols(int bn, int epi) {
   int need = bn * (epi == EPI_SILU_BF16 ? 2 : 1);
   return need <= 32 ? 32u : need <= 64 ? 64u : need <= 128 ? 128u : need <= 256 ? 256u : 512u;
 }
 
-template <int BN, int EPI, bool DEEP>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   constexpr bool kDual = (EPI == EPI_SILU_BF16);
-  constexpr int STAGES = gemm_stages(BN, EPI, DEEP);
+  constexpr int STAGES = gemm_stages(BN, EPI);
   constexpr int STAGE_BYTES = gemm_stage_bytes(BN, EPI);
   constexpr int B_OFF = kATileBytes * (kDual ? 2 : 1);
   constexpr uint32_t TMEM_COLS = gemm_tmem_cols(BN, EPI);
@@ -104,6 +112,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* rstd_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -119,10 +128,12 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tile_m = first_m + r % gsz;
     tile_n = r / gsz;
   }
-  const int m0 = tile_m * kBlockM;
+  const int R = p.tile_rows;
+  const int m0 = tile_m * R;
   const int n0 = tile_n * BN;
   const int kb0 = blockIdx.z * p.kb_per_split;
   const int nkb = min(p.kb_per_split, p.k_blocks - kb0);
+  const uint32_t stage_tx = (uint32_t)(R * kBlockK * 2 * (kDual ? 2 : 1) + BN * kBlockK * 2);
 
   if (warp == 0 && lane == 0) {
     trace_begin(p.tr);
@@ -151,17 +162,12 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int npre = nkb < STAGES ? nkb : STAGES;
       for (int s = 0; s < npre; ++s) {
         uint8_t* st = smem + s * STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        mbar_expect_tx(&full_bar[s], stage_tx);
         tma_load_2d(st, &tmA, &full_bar[s], (kb0 + s) * kBlockK, m0, p.w_policy);
         if (kDual) tma_load_2d(st + kATileBytes, &tmA, &full_bar[s], (kb0 + s) * kBlockK, m0 + p.a2_row_off, p.w_policy);
       }
       pdl_wait();  // activations are produced by the previous kernel
       trace_waited(p.tr);
-      if (p.norm_h) {  // ... or by the fused norm prologue of this very grid
-        while (ld_acquire_s32(p.norm_counter) < p.T) {
-        }
-        asm volatile("fence.proxy.async;" ::: "memory");  // rows were written through the generic proxy
-      }
       for (int s = 0; s < npre; ++s)
         tma_load_2d(smem + s * STAGE_BYTES + B_OFF, &tmB, &full_bar[s], (kb0 + s) * kBlockK, n0, kEvictLast);
       for (int kb = npre; kb < nkb; ++kb) {
@@ -169,7 +175,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* st = smem + s * STAGE_BYTES;
-        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+        mbar_expect_tx(&full_bar[s], stage_tx);
         tma_load_2d(st, &tmA, &full_bar[s], (kb0 + kb) * kBlockK, m0, p.w_policy);
         if (kDual) tma_load_2d(st + kATileBytes, &tmA, &full_bar[s], (kb0 + kb) * kBlockK, m0 + p.a2_row_off, p.w_policy);
         tma_load_2d(st + B_OFF, &tmB, &full_bar[s], (kb0 + kb) * kBlockK, n0, kEvictLast);
@@ -199,96 +205,60 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ---------------- epilogue: TMEM lane = output feature, TMEM column = token ----------------
     // The accumulator is transposed on its way out: each thread owns one feature (TMEM lane) and walks the
-    // token columns, writing a [token][128 features] tile into the (now idle) pipeline smem; one TMA tensor
+    // token columns, writing a [token][tile_rows features] tile into the (now idle) pipeline smem; one TMA tensor
     // store then moves the whole tile to global memory, coalesced and clipped to the tensor bounds.
-    if (p.norm_h) {
-      // ---- fused prologue: residual add + split-K reduce + RMSNorm of the rows this CTA owns (128 threads)
-      const int cta = blockIdx.x + gridDim.x * blockIdx.z;
-      if (cta < p.norm_ctas) {
-        pdl_wait();  // the planes come from the previous kernel
-        float* red = reinterpret_cast<float*>(tmem_slot + 2);  // 4 floats behind the barriers
-        const int tid = threadIdx.x - 64;                      // 0..127
-        const int nvec = p.norm_H >> 2;                        // float4 per row
-        for (int r = cta; r < p.T; r += p.norm_ctas) {
-          float4 v[16];  // H <= 8192
-          float ss = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int i4 = tid + j * 128;
-            if (i4 < nvec) {
-              float4 a = reinterpret_cast<const float4*>(p.norm_h + (size_t)r * p.norm_H)[i4];
-              for (int s2 = 0; s2 < p.norm_planes; ++s2) {
-                const float4 b = reinterpret_cast<const float4*>(p.norm_partial + s2 * p.norm_plane_stride + (size_t)r * p.norm_H)[i4];
-                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-              }
-              v[j] = a;
-              ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
-              reinterpret_cast<float4*>(p.norm_h + (size_t)r * p.norm_H)[i4] = a;
-            }
-          }
-          ss = warp_sum(ss);
-          if (lane == 0) red[warp - 2] = ss;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          const float rstd = rsqrtf((red[0] + red[1] + red[2] + red[3]) / (float)p.norm_H + p.norm_eps);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int i4 = tid + j * 128;
-            if (i4 < nvec) {
-              const uint2 gm = reinterpret_cast<const uint2*>(p.norm_gamma)[i4];
-              uint2 o;
-              o.x = pack_bf16(v[j].x * rstd * bf16_lo(gm.x), v[j].y * rstd * bf16_hi(gm.x));
-              o.y = pack_bf16(v[j].z * rstd * bf16_lo(gm.y), v[j].w * rstd * bf16_hi(gm.y));
-              reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.norm_x) + (size_t)r * p.norm_H)[i4] = o;
-            }
-          }
-          __threadfence();
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          if (tid == 0) atomicAdd(p.norm_counter, 1);
-        }
-      }
+    const bool fold = p.rs.ssq != nullptr;
+    if (fold) {  // RMSNorm fold: per-token scale, computed while the mainloop streams (sums are from the previous kernel)
+      pdl_wait();
+      for (int t = threadIdx.x - 64; t < BN; t += 128) rstd_s[t] = (n0 + t < p.T) ? rstd_of(p.rs, n0 + t) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
     const int q = warp & 3;  // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
+    const bool live = row < R;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint8_t* stg = smem;  // every MMA has retired (tmem_full), so all stage buffers are free
+    const uint32_t stg_a = smem_u32(stg), rstd_a = smem_u32(rstd_s);
+    constexpr int ESZ = EPI == EPI_F32 ? 4 : 2;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 16) {
       if (n0 + c0 >= p.T) break;  // warp-uniform; columns past T are clipped by the store anyway
       uint32_t v[16];
       tmem_ld16(t_lane + c0, v);
+      const uint32_t o = stg_a + (uint32_t)(c0 * R + row) * ESZ;  // explicit st.shared: see ptx.cuh
       if constexpr (kDual) {
         uint32_t u[16];
         tmem_ld16(t_lane + BN + c0, u);
         tmem_ld_wait();
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(stg) + c0 * kBlockM + row;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float g = __uint_as_float(v[j]);
-          const float up = __uint_as_float(u[j]);
-          o[j * kBlockM] = __float2bfloat16(g / (1.0f + __expf(-g)) * up);
+          const float sc = fold ? lds_f32(rstd_a + (uint32_t)(c0 + j) * 4u) : 1.f;
+          const float g = __uint_as_float(v[j]) * sc;
+          const float up = __uint_as_float(u[j]) * sc;
+          if (live) sts_bf16(o + (uint32_t)(j * R) * 2u, g / (1.0f + __expf(-g)) * up);
         }
       } else {
         tmem_ld_wait();
         if constexpr (EPI == EPI_F32) {
-          float* o = reinterpret_cast<float*>(stg) + c0 * kBlockM + row;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j * kBlockM] = __uint_as_float(v[j]);
+          for (int j = 0; j < 16; ++j)
+            if (live) sts_f32(o + (uint32_t)(j * R) * 4u, __uint_as_float(v[j]) * (fold ? lds_f32(rstd_a + (uint32_t)(c0 + j) * 4u) : 1.f));
         } else if constexpr (EPI == EPI_GELU_BF16 || EPI == EPI_BIAS_BF16) {
           const int f = m0 + row;  // this thread's output feature
           const float b = (p.bias && f < p.n_out) ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.bias)[f]) : 0.f;
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(stg) + c0 * kBlockM + row;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float a = __uint_as_float(v[j]) + b;
-            if constexpr (EPI == EPI_GELU_BF16) o[j * kBlockM] = __float2bfloat16(0.5f * a * (1.0f + erff(a * 0.70710678118654752f)));
-            else o[j * kBlockM] = __float2bfloat16(a);
+            if (!live) continue;
+            if constexpr (EPI == EPI_GELU_BF16) sts_bf16(o + (uint32_t)(j * R) * 2u, 0.5f * a * (1.0f + erff(a * 0.70710678118654752f)));
+            else sts_bf16(o + (uint32_t)(j * R) * 2u, a);
           }
         } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(stg) + c0 * kBlockM + row;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j * kBlockM] = __float2bfloat16(__uint_as_float(v[j]));
+          for (int j = 0; j < 16; ++j)
+            if (live) sts_bf16(o + (uint32_t)(j * R) * 2u, __uint_as_float(v[j]) * (fold ? lds_f32(rstd_a + (uint32_t)(c0 + j) * 4u) : 1.f));
         }
       }
     }

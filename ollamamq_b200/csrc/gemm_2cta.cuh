@@ -33,11 +33,6 @@ __host__ __device__ constexpr int c2_stages(int epi) {
 }
 __host__ __device__ constexpr int c2_smem_bytes(int epi) { return c2_stages(epi) * c2_stage_bytes(epi) + 1024 + 256; }
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");

@@ -4,6 +4,7 @@
 #include "gemm_streamk.cuh"
 #include "gemm_persist.cuh"
 #include "gemm_2cta.cuh"
+#include "gemm_dk.cuh"
 #include "kernels.cuh"
 
 namespace mq {
@@ -16,7 +17,6 @@ struct GemmPlan {
   int bn;
   int epi;
   int splits;
-  bool deep;  // pipeline depth variant (see gemm_stages)
   bool twocta;       // prefill regime: cta_group::2 kernel (gemm_2cta.cuh); tmB then has a 128-row box
   TwoCtaParams c2;
   bool persist;      // prefill regime, single accumulator: persistent double-buffered kernel (gemm_persist.cuh)
@@ -47,11 +47,26 @@ int gemm_pick_bn(int T);
 //   x_rows_alloc rows the activation buffer really has (TMA bounds; rows >= T read as-is, >= alloc as zero)
 bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T,
                int epi, void* out, int ldo, int splits, long long split_stride, int a2_row_off,
-               const StreamKWorkspace* sk = nullptr);  // with sk (and T <= 64): stream-K, `splits` is ignored (1 plane)
+               const StreamKWorkspace* sk = nullptr,  // with sk (and T <= 64): stream-K, `splits` is ignored (1 plane)
+               int tile_rows = 0);                    // weight rows per tile (0 = 128); see GemmParams::tile_rows
+// Tile height that spreads n_out weight rows over (almost) all SMs of the device: multiple of 8, 64..128.
+int gemm_balanced_rows(int n_out);
+// RMSNorm fold: scale token column t of the result by rstd[t] (GemmParams::rs / StreamKParams::rs).
+void gemm_plan_set_rstd(GemmPlan* g, const RstdIn& rs);
 
-// Attach the fused residual-add + RMSNorm prologue (decode only; split-K kernel only): see GemmParams::norm_*.
-void gemm_plan_fuse_norm(GemmPlan* g, float* h, const float* partial, int n_planes, long long plane_stride,
-                         const void* gamma, void* x, int H, float eps, int* counter);
+// ---- decode chain (gemm_dk.cuh): cluster split-K GEMM with fused residual / RoPE epilogues
+struct DkPlan {
+  CUtensorMap tmA;  // weights [w_rows, K], box {64, tile_rows}
+  CUtensorMap tmB;  // activations [x_rows, K], box {64, bn}
+  DkParams p;       // the caller fills the epilogue fields after dk_plan()
+  int bn, epi, cs, m_tiles;
+};
+int dk_max_clusters(int cs);                          // co-resident clusters of `cs` CTAs on this device (occupancy query)
+int dk_pick_cluster(int m_tiles, int k_blocks, int T);  // 0 = shape not servable
+// cs <= 0: pick.  false: shape not servable by the chain kernel (T > 64, too many tiles, ...)
+bool dk_plan(DkPlan* g, int epi, const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T,
+             int tile_rows, int cs);
+cudaError_t dk_launch(const DkPlan& g, const LaunchCfg& lc);
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc);
 void gemm_set_attrs();
 

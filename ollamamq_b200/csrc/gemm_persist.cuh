@@ -21,7 +21,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const PersistParams p) {
   static_assert(EPI != EPI_SILU_BF16 && 2 * BN <= 512, "single accumulator, two TMEM buffers");
-  constexpr int STAGES = gemm_stages(BN, EPI, true);
+  constexpr int STAGES = gemm_stages(BN, EPI);
   constexpr int STAGE_BYTES = gemm_stage_bytes(BN, EPI);
   constexpr int B_OFF = kATileBytes;
   constexpr uint32_t TMEM_COLS = 2 * BN <= 256 ? 256u : 512u;

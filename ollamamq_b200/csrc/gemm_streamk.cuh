@@ -31,6 +31,7 @@ struct StreamKParams {
   float* ws;       // [P][planes][BN*128] fp32 partial accumulators
   int* flags;      // [P] arrival counters, zero between launches
   unsigned long long w_policy;
+  RstdIn rs;       // optional RMSNorm fold: token column t of the finished tile is scaled by rstd[t] (gemm.cuh)
   Trace tr;        // optional timeline stamps (MQ_TRACE=1)
 };
 
@@ -42,7 +43,7 @@ __host__ __device__ constexpr int sk_stages(int bn, int epi) {
   return s > 8 ? 8 : s;
 }
 __host__ __device__ constexpr int sk_smem_bytes(int bn, int epi) {
-  return sk_stages(bn, epi) * gemm_stage_bytes(bn, epi) + 1024 + 256;
+  return sk_stages(bn, epi) * gemm_stage_bytes(bn, epi) + 1024 + 256 + 256 /*rstd[64]*/;
 }
 __host__ __device__ constexpr uint32_t sk_tmem_cols(int bn, int epi) {
   int need = 2 * bn * (epi == EPI_SILU_BF16 ? 2 : 1);  // two accumulator buffers
@@ -77,6 +78,7 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = empty_bar + STAGES;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* rstd_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [BN]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -183,6 +185,12 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const bool leader = (warp == 2 && lane == 0);
+    const bool fold = p.rs.ssq != nullptr;
+    if (fold) {  // per-token RMSNorm scale, computed while the mainloop streams
+      pdl_wait();
+      if ((int)threadIdx.x - 64 < BN) rstd_s[threadIdx.x - 64] = ((int)threadIdx.x - 64 < p.T) ? rstd_of(p.rs, threadIdx.x - 64) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     float* my_ws = p.ws + (size_t)c * (kDual ? 2 : 1) * TILE;
     int seg = 0;
     for (int t = tile_last; t >= tile_first; --t, ++seg) {
@@ -258,6 +266,13 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 16; ++j) {
               v[j] += __ldcg(w + j * kBlockM);
               if constexpr (kDual) u[j] += __ldcg(w + TILE + j * kBlockM);
+            }
+          }
+          if (fold) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              v[j] *= rstd_s[c0 + j];
+              if constexpr (kDual) u[j] *= rstd_s[c0 + j];
             }
           }
           const int f = t * kBlockM + row;

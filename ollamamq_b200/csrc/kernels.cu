@@ -42,25 +42,46 @@ static void launch_k(const LaunchCfg& lc, void (*kern)(KArgs...), dim3 grid, dim
 // ------------------------------------------------------------------------------------------------
 // embedding gather
 // ------------------------------------------------------------------------------------------------
-__global__ void embed_kernel(const int* __restrict__ token_ids, const __nv_bfloat16* __restrict__ embed,
-                             float* __restrict__ h, int H, int* __restrict__ zero, int n_zero) {
+// gamma != nullptr (decode chain): also emit xg = bf16(h * gamma) - the activation operand of the first QKV GEMM - and
+// ssq[t] = sum h^2, the single "partial" of the first RMSNorm fold (RstdIn with parts = 1; see gemm.cuh).
+__global__ void __launch_bounds__(128) embed_kernel(const int* __restrict__ token_ids, const __nv_bfloat16* __restrict__ embed,
+                                                    float* __restrict__ h, int H, const __nv_bfloat16* __restrict__ gamma,
+                                                    __nv_bfloat16* __restrict__ xg, float* __restrict__ ssq) {
   pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
   pdl_wait();
-  if (blockIdx.x == 0)  // first kernel of a pass: re-arm the arrival counters of the fused norm prologues
-    for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero[i] = 0;
   const int t = blockIdx.x;
   const int tok = token_ids[t];
   const uint4* src = reinterpret_cast<const uint4*>(embed + (size_t)tok * H);
   float4* dst = reinterpret_cast<float4*>(h + (size_t)t * H);
+  float ss = 0.f;
   for (int i = threadIdx.x; i < H / 8; i += blockDim.x) {
     const uint4 v = src[i];
-    dst[2 * i] = make_float4(bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y));
-    dst[2 * i + 1] = make_float4(bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w));
+    const float e[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y), bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
+    dst[2 * i] = make_float4(e[0], e[1], e[2], e[3]);
+    dst[2 * i + 1] = make_float4(e[4], e[5], e[6], e[7]);
+    if (gamma) {
+      const uint4 g = reinterpret_cast<const uint4*>(gamma)[i];
+      uint4 o;
+      o.x = pack_bf16(e[0] * bf16_lo(g.x), e[1] * bf16_hi(g.x));
+      o.y = pack_bf16(e[2] * bf16_lo(g.y), e[3] * bf16_hi(g.y));
+      o.z = pack_bf16(e[4] * bf16_lo(g.z), e[5] * bf16_hi(g.z));
+      o.w = pack_bf16(e[6] * bf16_lo(g.w), e[7] * bf16_hi(g.w));
+      reinterpret_cast<uint4*>(xg + (size_t)t * H)[i] = o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ss += e[k] * e[k];
+    }
+  }
+  if (gamma) {
+    __shared__ float red[4];
+    ss = warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) ssq[t] = (red[0] + red[1]) + (red[2] + red[3]);
   }
 }
 void launch_embed(const LaunchCfg& lc, const int* token_ids, const __nv_bfloat16* embed, float* h, int T, int H,
-                  int* zero, int n_zero) {
-  launch_k(lc, embed_kernel, dim3(T), dim3(128), 0, token_ids, embed, h, H, zero, n_zero);
+                  const __nv_bfloat16* gamma, __nv_bfloat16* xg, float* ssq) {
+  launch_k(lc, embed_kernel, dim3(T), dim3(128), 0, token_ids, embed, h, H, gamma, xg, ssq);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -72,9 +93,9 @@ void launch_embed(const LaunchCfg& lc, const int* token_ids, const __nv_bfloat16
 template <bool F32, int NP>
 __global__ void add_rmsnorm_kernel(float* __restrict__ h, const void* __restrict__ partial, long long plane_stride,
                                    const __nv_bfloat16* __restrict__ gamma, __nv_bfloat16* __restrict__ x,
-                                   const int* __restrict__ row_idx, int H, float eps, L2Prefetch pf, Trace tr) {
+                                   const int* __restrict__ row_idx, int H, float eps, Trace tr) {
   pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
-  if (threadIdx.x == 0) { trace_begin(tr); l2_prefetch_slice(pf, blockIdx.x, gridDim.x); }  // weights: independent of the previous kernel
+  if (threadIdx.x == 0) trace_begin(tr);
   const int row = blockIdx.x;
   const int nthr = blockDim.x;
   uint2 gm[4];
@@ -132,13 +153,13 @@ __global__ void add_rmsnorm_kernel(float* __restrict__ h, const void* __restrict
 }
 void launch_add_rmsnorm(const LaunchCfg& lc, float* h, const void* partial, bool partial_is_f32, int n_planes,
                         long long plane_stride, const __nv_bfloat16* gamma, __nv_bfloat16* x, const int* row_idx,
-                        int rows, int H, float eps, L2Prefetch pf, Trace tr) {
+                        int rows, int H, float eps, Trace tr) {
   const int thr = H / 16;  // H % 512 == 0 is checked at model load
   // (r01 A/B: a 4-CTA cluster per row with a DSMEM exchange of the partial sums was SLOWER at decode width -
   //  4.1 / 5.0 us busy against 3.3 / 4.3 us - the cluster barrier costs more than the narrower loads save.)
   auto go = [&](auto f32tag, auto nptag) {
     launch_k(lc, add_rmsnorm_kernel<decltype(f32tag)::value, decltype(nptag)::value>, dim3(rows), dim3(thr), 0, h,
-             partial, plane_stride, gamma, x, row_idx, H, eps, pf, tr);
+             partial, plane_stride, gamma, x, row_idx, H, eps, tr);
   };
   using T = std::true_type;
   using F = std::false_type;
@@ -218,7 +239,7 @@ static void dispatch_head_dim(int d, F&& f) {
 template <bool F32, int D, int NP>
 __global__ void __launch_bounds__(256) rope_kv_kernel(const RopeKvParams p) {
   pdl_launch_dependents();  // let the next kernel start its prologue (weight prefetch) right away
-  if (threadIdx.x == 0) { trace_begin(p.tr); l2_prefetch_slice(p.pf, blockIdx.x + gridDim.x * blockIdx.y, gridDim.x * gridDim.y); }
+  if (threadIdx.x == 0) trace_begin(p.tr);
   constexpr int HALF = D / 2;  // 16 threads per head x 4 pairs cover HALF <= 64 (threads beyond HALF idle: d = 96, 64)
   const int t = blockIdx.x;
   const int hd = blockIdx.y * 16 + (threadIdx.x >> 4);  // q heads, then k heads, then v heads
@@ -599,30 +620,6 @@ __global__ void __launch_bounds__(32 * NW) decode_attn_kernel(const AttnParams p
         cp_async_commit();
       }
     }
-    // ---- fused RoPE, part 1 (before the dependency wait: needs only the position): the angles of this thread's
-    // q elements.  Thread (g, c) owns elements ks*16 + {2c, 2c+1, 8+2c, 9+2c} of head g; the rotation partner of an
-    // element e < D/2 is e + D/2 = the same offsets KS/2 slices further on, i.e. in this very thread.
-    const bool fused = p.qkv_planes != nullptr;
-    const int new_pos = kv_len - 1;
-    const bool own_tail = fused && kv_begin <= new_pos && new_pos < kv_end;  // this warp's range holds the token appended by this step
-    // (cos, sin) pairs from the per-worker table [position][D / 2] (built once with the same sincosf as the rope kernel)
-    float4 q_rot[KS / 2][2];           // [ks][0] = (cos, sin) of e0, e0 + 1;  [ks][1] = of e0 + 8, e0 + 9
-    float2 k_rot[2] = {make_float2(1.f, 0.f), make_float2(1.f, 0.f)};
-    if (fused) {
-      const float2* tab = p.rope_table + (size_t)new_pos * (D / 2);
-      if (g < G) {
-#pragma unroll
-        for (int ks = 0; ks < KS / 2; ++ks) {
-          q_rot[ks][0] = *reinterpret_cast<const float4*>(tab + ks * 16 + 2 * c);
-          q_rot[ks][1] = *reinterpret_cast<const float4*>(tab + ks * 16 + 8 + 2 * c);
-        }
-      }
-      if (own_tail) {  // the new k row: this lane rotates pairs lane and lane + 32 (where < D/2)
-#pragma unroll
-        for (int j = 0; j < 2; ++j)
-          if (lane + 32 * j < D / 2) k_rot[j] = tab[lane + 32 * j];
-      }
-    }
     pdl_wait();
     if (threadIdx.x == 0) trace_waited(p.tr);
     if (!early) {
@@ -634,95 +631,13 @@ __global__ void __launch_bounds__(32 * NW) decode_attn_kernel(const AttnParams p
     }
     // Q fragments: row g = head g of the group (zero for g >= G), rows 8..15 zero
     uint32_t qf[KS][2];
-    __nv_bfloat16 k_row[4], v_row[4];  // fused: this lane's share of the appended k / v row (own_tail only)
-    if (!fused) {  // q written by rope_kv_kernel
+    {
       const bool ok = g < G;
       const __nv_bfloat16* qp = p.q + ((size_t)slot * p.n_q + kvh * G + (ok ? g : 0)) * D + 2 * c;
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         qf[ks][0] = ok ? *reinterpret_cast<const uint32_t*>(qp + ks * 16) : 0u;
         qf[ks][1] = ok ? *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 8) : 0u;
-      }
-    } else {
-      // ---- fused RoPE, part 2: sum the split-K planes (+ bias), rotate, keep q in registers.  The plane loop is the
-      // OUTER loop and everything inside is unrolled, so each plane costs one round trip of independent loads
-      // (a per-element plane loop was 48 dependent L2 round trips: +28 us per layer).
-      const float* row = p.qkv_planes + (size_t)slot * p.qkv_dim;
-      if (g < G) {
-        const int qcol = (kvh * G + g) * D + 2 * c;
-        float2 x[KS / 2][2], y[KS / 2][2];
-#pragma unroll
-        for (int ks = 0; ks < KS / 2; ++ks) x[ks][0] = x[ks][1] = y[ks][0] = y[ks][1] = make_float2(0.f, 0.f);
-        for (int s2 = 0; s2 < p.qkv_n_planes; ++s2) {
-          const float* r2 = row + s2 * p.qkv_plane_stride + qcol;
-#pragma unroll
-          for (int ks = 0; ks < KS / 2; ++ks) {
-            const float2 a0 = *reinterpret_cast<const float2*>(r2 + ks * 16), a1 = *reinterpret_cast<const float2*>(r2 + ks * 16 + 8);
-            const float2 b0 = *reinterpret_cast<const float2*>(r2 + ks * 16 + D / 2), b1 = *reinterpret_cast<const float2*>(r2 + ks * 16 + 8 + D / 2);
-            x[ks][0].x += a0.x; x[ks][0].y += a0.y; x[ks][1].x += a1.x; x[ks][1].y += a1.y;
-            y[ks][0].x += b0.x; y[ks][0].y += b0.y; y[ks][1].x += b1.x; y[ks][1].y += b1.y;
-          }
-        }
-        if (p.qkv_bias) {
-          const __nv_bfloat16* bq = p.qkv_bias + qcol;
-#pragma unroll
-          for (int ks = 0; ks < KS / 2; ++ks) {
-            x[ks][0].x += __bfloat162float(bq[ks * 16]); x[ks][0].y += __bfloat162float(bq[ks * 16 + 1]);
-            x[ks][1].x += __bfloat162float(bq[ks * 16 + 8]); x[ks][1].y += __bfloat162float(bq[ks * 16 + 9]);
-            y[ks][0].x += __bfloat162float(bq[ks * 16 + D / 2]); y[ks][0].y += __bfloat162float(bq[ks * 16 + D / 2 + 1]);
-            y[ks][1].x += __bfloat162float(bq[ks * 16 + D / 2 + 8]); y[ks][1].y += __bfloat162float(bq[ks * 16 + D / 2 + 9]);
-          }
-        }
-#pragma unroll
-        for (int ks = 0; ks < KS / 2; ++ks) {
-          const float4 r0 = q_rot[ks][0], r1 = q_rot[ks][1];  // (cos, sin, cos', sin')
-          qf[ks][0] = pack_bf16(x[ks][0].x * r0.x - y[ks][0].x * r0.y, x[ks][0].y * r0.z - y[ks][0].y * r0.w);
-          qf[ks][1] = pack_bf16(x[ks][1].x * r1.x - y[ks][1].x * r1.y, x[ks][1].y * r1.z - y[ks][1].y * r1.w);
-          qf[ks + KS / 2][0] = pack_bf16(y[ks][0].x * r0.x + x[ks][0].x * r0.y, y[ks][0].y * r0.z + x[ks][0].y * r0.w);
-          qf[ks + KS / 2][1] = pack_bf16(y[ks][1].x * r1.x + x[ks][1].x * r1.y, y[ks][1].y * r1.z + x[ks][1].y * r1.w);
-        }
-      } else {
-#pragma unroll
-        for (int ks = 0; ks < KS; ++ks) qf[ks][0] = qf[ks][1] = 0u;
-      }
-      if (own_tail) {
-        // the appended row: k rotated (pairs lane, lane + 32), v copied (elements 4*lane .. +3); written to the cache
-        // for the steps to come and injected into the last tile of THIS step further down
-        const int kcol = (p.n_q + kvh) * D, vcol = (p.n_q + p.n_kv + kvh) * D + lane * 4;
-        const bool k0 = lane < D / 2, k1 = lane + 32 < D / 2, vv = lane * 4 < D;
-        float kx[2] = {0.f, 0.f}, ky[2] = {0.f, 0.f};
-        float4 va = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s2 = 0; s2 < p.qkv_n_planes; ++s2) {
-          const float* r2 = row + s2 * p.qkv_plane_stride;
-          if (k0) { kx[0] += r2[kcol + lane]; ky[0] += r2[kcol + lane + D / 2]; }
-          if (k1) { kx[1] += r2[kcol + lane + 32]; ky[1] += r2[kcol + lane + 32 + D / 2]; }
-          if (vv) { const float4 t4 = *reinterpret_cast<const float4*>(r2 + vcol); va.x += t4.x; va.y += t4.y; va.z += t4.z; va.w += t4.w; }
-        }
-        if (p.qkv_bias) {
-          if (k0) { kx[0] += __bfloat162float(p.qkv_bias[kcol + lane]); ky[0] += __bfloat162float(p.qkv_bias[kcol + lane + D / 2]); }
-          if (k1) { kx[1] += __bfloat162float(p.qkv_bias[kcol + lane + 32]); ky[1] += __bfloat162float(p.qkv_bias[kcol + lane + 32 + D / 2]); }
-          if (vv) {
-            va.x += __bfloat162float(p.qkv_bias[vcol]); va.y += __bfloat162float(p.qkv_bias[vcol + 1]);
-            va.z += __bfloat162float(p.qkv_bias[vcol + 2]); va.w += __bfloat162float(p.qkv_bias[vcol + 3]);
-          }
-        }
-        const int page = btab[new_pos / kPageSize];
-        const size_t cbase = (((size_t)page * p.n_kv + kvh) * kPageSize + new_pos % kPageSize) * D;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int i = lane + 32 * j;
-          if (i < D / 2) {
-            k_row[2 * j] = __float2bfloat16(kx[j] * k_rot[j].x - ky[j] * k_rot[j].y);
-            k_row[2 * j + 1] = __float2bfloat16(ky[j] * k_rot[j].x + kx[j] * k_rot[j].y);
-            p.k_new[cbase + i] = k_row[2 * j];
-            p.k_new[cbase + i + D / 2] = k_row[2 * j + 1];
-          }
-        }
-        if (vv) {
-          v_row[0] = __float2bfloat16(va.x); v_row[1] = __float2bfloat16(va.y);
-          v_row[2] = __float2bfloat16(va.z); v_row[3] = __float2bfloat16(va.w);
-          *reinterpret_cast<uint2*>(p.v_new + cbase + lane * 4) = make_uint2(pack_bf16(va.x, va.y), pack_bf16(va.z, va.w));
-        }
       }
     }
     for (int it = 0; it < n_tiles; ++it) {
@@ -731,27 +646,6 @@ __global__ void __launch_bounds__(32 * NW) decode_attn_kernel(const AttnParams p
       cp_async_commit();
       cp_async_wait<STAGES - 1>();
       __syncwarp();
-      if (own_tail && it == n_tiles - 1) {
-        // fused RoPE, part 3: the page just fetched holds a stale row where this step's token belongs
-        uint8_t* kt = Ks + (it % STAGES) * TN * P * 2;
-        uint8_t* vt = Vs + (it % STAGES) * TN * P * 2;
-        const int r = new_pos - t0;
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const int i = lane + 32 * j;
-          if (i < D / 2) {
-            *reinterpret_cast<__nv_bfloat16*>(kt + tile_off(r, i >> 3) + (i & 7) * 2) = k_row[2 * j];
-            const int i2 = i + D / 2;
-            *reinterpret_cast<__nv_bfloat16*>(kt + tile_off(r, i2 >> 3) + (i2 & 7) * 2) = k_row[2 * j + 1];
-          }
-        }
-        if (lane * 4 < D) {
-          const int i = lane * 4;
-          __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(vt + tile_off(r, i >> 3) + (i & 7) * 2);
-          dst[0] = v_row[0]; dst[1] = v_row[1]; dst[2] = v_row[2]; dst[3] = v_row[3];
-        }
-        __syncwarp();
-      }
       const uint32_t kbase = smem_u32(Ks + (it % STAGES) * TN * P * 2);
       const uint32_t vbase = smem_u32(Vs + (it % STAGES) * TN * P * 2);
       // ---- S = Q K^T for the 16 tokens of this page
@@ -805,11 +699,6 @@ __global__ void __launch_bounds__(32 * NW) decode_attn_kernel(const AttnParams p
     pdl_wait();
     if (threadIdx.x == 0) trace_waited(p.tr);
   }
-  // KV streaming of this CTA is over: use the combine tail to pull the O-projection weights towards L2
-  // (issued late on purpose - the 135 MB KV stream would evict anything prefetched earlier)
-  if (threadIdx.x == 0)
-    l2_prefetch_slice(p.pf, blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z), gridDim.x * gridDim.y * gridDim.z);
-
   // ---- finalize: l of head g -> full row sum; this thread needs the sums of heads 2c, 2c+1
   l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
   l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);

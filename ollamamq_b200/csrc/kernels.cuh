@@ -17,16 +17,15 @@ struct LaunchCfg {
   bool pdl;  // launch with programmatic stream serialization
 };
 
-// h_f32[t,:] = embed[token_ids[t], :]
+// h_f32[t,:] = embed[token_ids[t], :];  with gamma (decode chain): xg[t,:] = bf16(h * gamma), ssq[t] = sum h^2
 void launch_embed(const LaunchCfg& lc, const int* token_ids, const __nv_bfloat16* embed, float* h, int T, int H,
-                  int* zero = nullptr, int n_zero = 0);  // also zeroes `zero[0..n_zero)` (arrival counters)
+                  const __nv_bfloat16* gamma = nullptr, __nv_bfloat16* xg = nullptr, float* ssq = nullptr);
 
 // v = h[src,:] + sum_s partial[s][src,:];  if (!row_idx) h[src,:] = v;  x[row,:] = bf16(v * rsqrt(mean v^2 + eps) * gamma)
 // partial_is_f32: planes are fp32 (decode split-K) else one bf16 plane (prefill).
 void launch_add_rmsnorm(const LaunchCfg& lc, float* h, const void* partial, bool partial_is_f32, int n_planes,
                         long long plane_stride, const __nv_bfloat16* gamma, __nv_bfloat16* x, const int* row_idx,
-                        int rows, int H, float eps, L2Prefetch pf = L2Prefetch{nullptr, 0},
-                        Trace tr = Trace{nullptr, 0});
+                        int rows, int H, float eps, Trace tr = Trace{nullptr, 0});
 
 struct RopeKvParams {
   const void* qkv;        // partial planes [S][T][qkv_dim] fp32, or one bf16 plane
@@ -45,7 +44,6 @@ struct RopeKvParams {
   __nv_bfloat16* v_cache;
   int T, n_q, n_kv;
   int head_dim;               // 128, 96 or 64
-  L2Prefetch pf;              // optional: weights of an upcoming GEMM to pull into L2
   Trace tr;                   // optional timeline stamps (MQ_TRACE=1)
 };
 void launch_rope_kv(const LaunchCfg& lc, const RopeKvParams& p);
@@ -76,16 +74,6 @@ struct AttnParams {
                        // CTAs rather than a deep ring (a 6-stage CTA holds 48 KiB: 4 per SM)
   int* split_counter;  // decode only: [slots][n_kv] arrival counters (zero between launches)
   float scale_log2;    // softmax scale * log2(e)
-  // decode, fused RoPE (qkv_planes != nullptr): the kernel itself sums the QKV GEMM's split-K planes (+ bias), rotates
-  // q and the new k, appends k / v of position pos[slot] to the paged cache and uses them - no rope_kv launch, no q buffer
-  const float* qkv_planes;        // [n_planes][plane_stride], row = slot, qkv_dim columns (q heads | k heads | v heads)
-  int qkv_n_planes, qkv_dim;
-  long long qkv_plane_stride;
-  const __nv_bfloat16* qkv_bias;  // nullable [qkv_dim]
-  const float2* rope_table;       // [positions][head_dim / 2] (cos, sin)
-  __nv_bfloat16* k_new;           // writable aliases of k_cache / v_cache
-  __nv_bfloat16* v_new;
-  L2Prefetch pf;       // optional: weights of an upcoming GEMM to pull into L2 (decode)
   Trace tr;            // optional timeline stamps (MQ_TRACE=1)
 };
 void launch_attn_prefill(const LaunchCfg& lc, const AttnParams& p, int n_tiles);

@@ -91,31 +91,6 @@ __device__ __forceinline__ void tma_store_3d(const void* tmap, const void* smem_
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
-// Asynchronous L2 prefetch of a contiguous global range (hint only; bytes must be a multiple of 16).
-__device__ __forceinline__ void l2_prefetch_bulk(const void* gptr, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(gptr)), "r"(bytes) : "memory");
-}
-// Every CTA of a grid prefetches its slice of [ptr, ptr + bytes): used by the small / latency-bound kernels of the
-// decode chain to pull the NEXT GEMM's weights towards L2 while HBM would otherwise idle (r01 profiles).
-struct L2Prefetch {
-  const void* ptr;
-  unsigned long long bytes;
-};
-__device__ __forceinline__ void l2_prefetch_slice(const L2Prefetch& pf, unsigned cta, unsigned n_ctas) {
-  if (pf.ptr == nullptr || pf.bytes == 0) return;
-  unsigned long long per = ((pf.bytes / n_ctas) + 15ull) & ~15ull;
-  const unsigned long long off = per * cta;
-  if (off >= pf.bytes) return;
-  if (off + per > pf.bytes) per = (pf.bytes - off) & ~15ull;
-  const char* base = reinterpret_cast<const char*>(pf.ptr) + off;
-  while (per > 0) {  // keep single requests modest
-    const unsigned chunk = per > 65536ull ? 65536u : (unsigned)per;
-    l2_prefetch_bulk(base, chunk);
-    base += chunk;
-    per -= chunk;
-  }
-}
-
 // ---------------------------------------------------------------- per-launch timeline stamps (diagnostics)
 // MQ_TRACE=1: every kernel of a step records %globaltimer (ns) into buf[4 * id + k]:
 //   k = 0 first CTA entered the kernel (min)      k = 1 first CTA got past griddepcontrol.wait (min)
@@ -155,6 +130,49 @@ __device__ __forceinline__ int ld_acquire_s32(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
+}
+
+// ---------------------------------------------------------------- thread-block clusters / distributed shared memory
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+// shared::cta address of THIS CTA -> shared::cluster address of the same offset inside CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+// bulk copy from this CTA's shared memory into a peer CTA's (both addresses / the peer's mbarrier as shared::cluster
+// addresses from mapa_shared); completes `bytes` transaction bytes on the PEER's mbarrier.  bytes % 16 == 0.
+__device__ __forceinline__ void dsmem_bulk_copy(uint32_t dst_cluster_addr, uint32_t src_cta_addr, uint32_t bytes,
+                                                uint32_t mbar_cluster_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster_addr),
+               "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// every thread of every CTA of the cluster executes both; the warp must be converged (.aligned)
+__device__ __forceinline__ void cluster_arrive_release() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait_acquire() {
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
@@ -225,6 +243,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// explicit shared-space accesses by 32-bit address (pointers rebuilt from the aligned dynamic-smem base lose their
+// address space and compile to generic LD / ST: ~2x the latency on the epilogue's dependent chains)
+__device__ __forceinline__ float lds_f32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_bf16(uint32_t a, float v) {
+  const __nv_bfloat16 h = __float2bfloat16(v);
+  asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(*reinterpret_cast<const unsigned short*>(&h)) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
 
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ float warp_sum(float v) {

@@ -104,62 +104,42 @@ def test_generation_single_and_concurrent(pdl, graphs):
             mq.lib.mq_req_release(s.handle)
 
 
-def test_generation_with_and_without_fused_norm_prologue(monkeypatch):
-    """MQ_FUSE_NORM=1 moves add+RMSNorm into the consuming GEMM's prologue (opt-in: measured slower); both paths
-    must hold parity."""
-    monkeypatch.setenv("MQ_FUSE_NORM", "0")
-    cfg = MID
-    w = R.make_weights(cfg, seed=23, device="cuda")
-    g = torch.Generator().manual_seed(4)
-    prompts = [torch.randint(0, cfg["vocab"], (n,), generator=g).tolist() for n in (9, 70, 33)]
-    with _open(cfg, w, max_batch=4, use_pdl=1, use_graphs=1) as wk:
-        streams = [wk.submit(mq.Stream(), prompt_tokens=p, max_new_tokens=10) for p in prompts]
-        for p, s in zip(prompts, streams):
-            s.wait(120)
-            assert s.rc == 0, s.err
-            _check_greedy(w, cfg, p, s.tokens())
-            mq.lib.mq_req_release(s.handle)
-        n_fused_off = wk.stats()["kernel_launches"]
-    monkeypatch.setenv("MQ_FUSE_NORM", "1")
-    with _open(cfg, w, max_batch=4, use_pdl=1, use_graphs=1) as wk:
-        streams = [wk.submit(mq.Stream(), prompt_tokens=p, max_new_tokens=10) for p in prompts]
-        for p, s in zip(prompts, streams):
-            s.wait(120)
-            assert s.rc == 0, s.err
-            _check_greedy(w, cfg, p, s.tokens())
-            mq.lib.mq_req_release(s.handle)
-        assert wk.stats()["kernel_launches"] < n_fused_off      # two launches per layer fewer in every decode step
-
-
-@pytest.mark.parametrize("cfg_name", ["mid", "qwen_bias_gqa7", "phi_d96"])
-def test_generation_with_rope_fused_into_decode_attention(monkeypatch, cfg_name):
-    """MQ_FUSE_ROPE=1: the decode attention kernel sums the QKV planes, rotates q / k and appends k / v itself (opt-in:
-    measured no gain).  Parity must hold for GQA 4, GQA 7 + q/k/v bias, and head_dim 96 MHA, at batch sizes that take the
-    one-warp and the multi-warp (in-CTA split) forms of the kernel."""
+@pytest.mark.parametrize("cfg_name", ["mid", "qwen_bias_gqa7", "phi_d96", "d64"])
+def test_decode_chain_and_plane_path_both_hold_parity(monkeypatch, cfg_name):
+    """The decode chain (cluster split-K GEMMs with fused RoPE / residual epilogues, RMSNorm folded into the consumers:
+    5 launches per layer) is the default; MQ_DECODE_CHAIN=0 selects the round-1 plane-based path (8 launches per layer).
+    Both must hold parity with the fp32 oracle - GQA 4, GQA 7 + q/k/v bias, head_dim 96 MHA, head_dim 64 - at batch
+    sizes that take the one-warp and the multi-warp forms of the attention kernel, and the chain must be deterministic."""
     cfg = {"mid": MID,
            "qwen_bias_gqa7": dict(MID, hidden=1024, n_q_heads=7, n_kv_heads=1, qkv_bias=1, rope_theta=1000000.0),
-           "phi_d96": dict(MID, hidden=1536, n_q_heads=16, n_kv_heads=16, head_dim=96, rope_theta=10000.0)}[cfg_name]
+           "phi_d96": dict(MID, hidden=1536, n_q_heads=16, n_kv_heads=16, head_dim=96, rope_theta=10000.0),
+           "d64": dict(MID, hidden=512, n_q_heads=8, n_kv_heads=4, head_dim=64, rope_theta=10000.0)}[cfg_name]
     w = R.make_weights(cfg, seed=29, device="cuda")
     g = torch.Generator().manual_seed(5)
     prompts = [torch.randint(0, cfg["vocab"], (n,), generator=g).tolist() for n in (9, 70, 33, 15, 16, 17, 130, 1)]
-    monkeypatch.setenv("MQ_FUSE_ROPE", "1")
-    with _open(cfg, w, max_batch=8, use_pdl=1, use_graphs=1) as wk:
-        streams = [wk.submit(mq.Stream(), prompt_tokens=p, max_new_tokens=20) for p in prompts]
-        for p, s in zip(prompts, streams):
-            s.wait(120)
-            assert s.rc == 0, s.err
-            _check_greedy(w, cfg, p, s.tokens())
-            mq.lib.mq_req_release(s.handle)
-        n_fused = wk.stats()["kernel_launches"]
-        solo = wk.generate(prompts[1], 12)          # batch of one: 8 warps per CTA
-        _check_greedy(w, cfg, prompts[1], solo)
-    monkeypatch.setenv("MQ_FUSE_ROPE", "0")
-    with _open(cfg, w, max_batch=8, use_pdl=1, use_graphs=1) as wk:
-        streams = [wk.submit(mq.Stream(), prompt_tokens=p, max_new_tokens=20) for p in prompts]
-        for s in streams:
-            s.wait(120)
-            mq.lib.mq_req_release(s.handle)
-        assert n_fused < wk.stats()["kernel_launches"]          # one launch per layer fewer in every decode step
+
+    def run(chain):
+        monkeypatch.setenv("MQ_DECODE_CHAIN", "1" if chain else "0")
+        with _open(cfg, w, max_batch=8, use_pdl=1, use_graphs=1) as wk:
+            streams = [wk.submit(mq.Stream(), prompt_tokens=p, max_new_tokens=20) for p in prompts]
+            toks = []
+            for p, s in zip(prompts, streams):
+                s.wait(120)
+                assert s.rc == 0, s.err
+                _check_greedy(w, cfg, p, s.tokens())
+                toks.append(s.tokens())
+                mq.lib.mq_req_release(s.handle)
+            st = wk.stats()
+            solo = wk.generate(prompts[1], 12)          # batch of one: 8 warps per attention CTA
+            _check_greedy(w, cfg, prompts[1], solo)
+            return toks, st["kernel_launches"], st["decode_steps"]
+
+    toks_chain, n_chain, steps_chain = run(True)
+    toks_chain2, _, _ = run(True)
+    toks_plane, n_plane, steps_plane = run(False)
+    assert toks_chain == toks_chain2                    # fixed-order reductions: bit-reproducible
+    assert steps_chain == steps_plane
+    assert n_chain < n_plane                            # three launches per layer fewer in every decode step
 
 
 def test_cancel_timeout_and_framing():

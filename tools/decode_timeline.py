@@ -54,6 +54,7 @@ t_end = max(int(t[i, 3]) for i, _, _ in ids)
 print("# live decode step, %d users, ctx ~%d, %s: %.1f us from first kernel start to last kernel end "
       "(worker stats: %.3f ms/step over %d steps incl. argmax + launch)" %
       (users, plen + gen, model, (t_end - t0) / 1e3, st["decode_ms"] / max(1, st["decode_steps"]), st["decode_steps"]))
+print("# kernels per layer: %d (%s)" % (sum(1 for _, l, _ in ids if l == 1), ", ".join(nm for _, l, nm in ids if l == 1)))
 print("# per launch: start / dependency-wait-returned / first-CTA-end / last-CTA-end, us from the step's first stamp")
 rows = []
 prev_end = t0
