@@ -226,6 +226,12 @@ int mq_worker_set_timing(mq_worker* w, int32_t enable);
 
 /* kernel-level test ABI (not on the serving path): logits of the last position of `tokens` (fp32 [vocab]),
  * or of every position when all_positions != 0 (fp32 [n][vocab]); logits_out is host memory.              */
+/* Fault injection for the health path (dispatcher.rs:171-193).  probe_fail = 1: mq_worker_healthy() reports 0 while
+ * the engine keeps serving what it has (a backend whose /api/tags stopped answering); 0 restores it.
+ * mq_debug_worker_inject_fault: the sticky fault a CUDA error raises - every request on the worker fails with `msg`
+ * and the worker stays unhealthy until it is closed.                                                          */
+int mq_debug_worker_set_probe_fail(mq_worker* w, int32_t probe_fail);
+int mq_debug_worker_inject_fault(mq_worker* w, const char* msg);
 int mq_debug_forward(mq_worker* w, const int32_t* tokens, int32_t n, int32_t all_positions, float* logits_out);
 
 /* =====================================================================================================
@@ -306,6 +312,14 @@ int mq_dispatcher_set_block_file(mq_dispatcher* d, const char* path);
  * dropped}] in the dashboard's order (tui.rs:70-80), backends[{label, active, processed, online}].  Returns the bytes
  * needed including the terminator; nothing is written when that exceeds cap.                              */
 long long mq_dispatcher_snapshot_json(mq_dispatcher* d, char* out, size_t cap);
+/* The dashboard's control keys (tui.rs:126-237) as one atomic call, for front ends without a terminal (the HTTP
+ * ingress exposes it as loopback-only POST /admin/{vip,boost,block,unblock}, body {"user": ..} / {"ip": ..} /
+ * {"mode": "add" | "clear" | ..}, and GET /admin/state = the snapshot above).  action:
+ *   "vip" | "boost"           the 'p' | 'b' key on `user`: toggle; clears the other flag when it names the same user
+ *   "vip_add" | "boost_add"   EXTENSION (BASELINE config 3): add `user` to the set;  "vip_clear" | "boost_clear"
+ *   "block_user"  'x';  "block_ip"  'X' (`ip`, or the address `user` was last seen from);
+ *   "unblock"  'u' on the users panel (user + its address);  "unblock_user" | "unblock_ip"  'u' on the blocked panel */
+int mq_dispatcher_control(mq_dispatcher* d, const char* action, const char* user, const char* ip);
 /* health prober (:171-193): every period_ms (reference: 10 000) copy mq_worker_healthy() into is_online         */
 int mq_dispatcher_start_health(mq_dispatcher* d, uint32_t period_ms);
 /* the HTTP connection behind a queued / in-flight task closed (responder.is_closed(), :278; send error, :305) */
@@ -320,6 +334,8 @@ int mq_dispatcher_wait_parked(mq_dispatcher* d, uint32_t timeout_ms);
 int mq_dispatcher_new_mock(int32_t n_backends, int32_t capacity, mq_dispatcher** out);
 int mq_dispatcher_mock_complete(mq_dispatcher* d, int32_t backend, int32_t rc);
 int mq_dispatcher_mock_fail_next(mq_dispatcher* d, int32_t backend, int32_t n);
+/* what mock backend `backend` answers to the health prober from now on (0 = GET /api/tags unreachable, :181-183)    */
+int mq_dispatcher_mock_set_healthy(mq_dispatcher* d, int32_t backend, int32_t healthy);
 
 /* =====================================================================================================
  * 3b. HTTP/1.1 ingress: the route table of main.rs:89-121 and the proxy_handler
@@ -353,12 +369,6 @@ int mq_debug_gemm_fold(const void* W, int w_rows, int n_out, int K, const void* 
 /* h[t,f] += X[t,:] . W[f,:];  xg = bf16(h * gamma_next);  ssq_out[tile][t] = sum_f h^2 per 128-feature tile        */
 int mq_debug_gemm_dk_resid(const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, int cs, float* h,
                            const void* gamma_next, void* xg, float* ssq_out, int ssq_stride, int reps, float* ms_out);
-/* QKV projection with the rstd fold, bias, rotate-half RoPE (cos / sin of pos * inv_freq) and the q / paged-KV write */
-int mq_debug_gemm_dk_qkv(const void* W, int n_q, int n_kv, int head_dim, int K, const void* X, int x_rows_alloc, int T,
-                         int cs, const float* ssq, int parts, int stride, float inv_h, float eps, const void* bias,
-                         const int* pos, const int* slot_of_tok, const int* block_table, int max_pages,
-                         const float* inv_freq, int max_pos, void* q_out, void* k_cache, void* v_cache, int reps,
-                         float* ms_out);
 int mq_debug_add_rmsnorm(float* h, const void* partial, int partial_is_f32, int n_planes, long long plane_stride,
                          const void* gamma, void* x, const int* row_idx, int rows, int H, float eps);
 int mq_debug_rope_kv(const void* qkv, int qkv_is_f32, int n_planes, long long plane_stride, const void* bias,

@@ -159,6 +159,9 @@ _sig("mq_dispatcher_wait_parked", C.c_int, [P, C.c_uint32])
 _sig("mq_dispatcher_new_mock", C.c_int, [C.c_int32, C.c_int32, C.POINTER(P)])
 _sig("mq_dispatcher_mock_complete", C.c_int, [P, C.c_int32, C.c_int32])
 _sig("mq_dispatcher_mock_fail_next", C.c_int, [P, C.c_int32, C.c_int32])
+_sig("mq_dispatcher_mock_set_healthy", C.c_int, [P, C.c_int32, C.c_int32])
+_sig("mq_debug_worker_set_probe_fail", C.c_int, [P, C.c_int32])
+_sig("mq_debug_worker_inject_fault", C.c_int, [P, C.c_char_p])
 _sig("mq_http_server_start", C.c_int, [P, C.c_char_p, C.c_int32, C.c_int32, C.POINTER(P)])
 _sig("mq_http_server_port", C.c_int, [P])
 _sig("mq_http_server_stop", None, [P])
@@ -172,9 +175,6 @@ _sig("mq_debug_gemm_fold", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, C.c_int, C
                                       C.c_int, P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_float)])
 _sig("mq_debug_gemm_dk_resid", C.c_int, [P, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, P, P, P, P, C.c_int, C.c_int,
                                           C.POINTER(C.c_float)])
-_sig("mq_debug_gemm_dk_qkv", C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int,
-                                        C.c_float, C.c_float, P, P, P, P, C.c_int, P, C.c_int, P, P, P, C.c_int,
-                                        C.POINTER(C.c_float)])
 _sig("mq_debug_add_rmsnorm", C.c_int, [P, P, C.c_int, C.c_int, C.c_longlong, P, P, P, C.c_int, C.c_int, C.c_float])
 _sig("mq_debug_rope_kv", C.c_int, [P, C.c_int, C.c_int, C.c_longlong, P, P, P, P, C.c_int, P, P, P, P, C.c_int,
                                     C.c_int, C.c_int, C.c_int])
@@ -185,6 +185,7 @@ _sig("mq_debug_attn_decode", C.c_int, [P, P, P, P, C.c_int, P, P, P, P, P, C.c_i
 _sig("mq_worker_get_occupancy", C.c_int, [P, P])
 _sig("mq_debug_sched_bench", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, P, P])
 _sig("mq_dispatcher_snapshot_json", C.c_longlong, [P, P, C.c_size_t])
+_sig("mq_dispatcher_control", C.c_int, [P, C.c_char_p, C.c_char_p, C.c_char_p])
 _sig("mq_dispatcher_attach_encoder", C.c_int, [P, C.c_int32, P])
 _sig("mq_dispatcher_add_vip", C.c_int, [P, C.c_char_p])
 _sig("mq_dispatcher_add_boost", C.c_int, [P, C.c_char_p])

@@ -139,7 +139,7 @@ int mq_debug_gemm_dk_resid(const void* W, int n_out, int K, const void* X, int x
                            const void* gamma_next, void* xg, float* ssq_out, int ssq_stride, int reps, float* ms_out) {
   DkPlan g;
   gemm_set_attrs();
-  if (!dk_plan(&g, DK_RESID, W, n_out, n_out, K, X, x_rows_alloc, T, 128, cs)) {
+  if (!dk_plan(&g, W, n_out, n_out, K, X, x_rows_alloc, T, 128, cs)) {
     mq::set_last_error("dk_plan failed (T > 64, K %% 64, cluster size / tokens per rank)");
     return MQ_ERR_INVAL;
   }
@@ -152,38 +152,12 @@ int mq_debug_gemm_dk_resid(const void* W, int n_out, int K, const void* X, int x
   if (dbg) {
     unsigned long long hst[16];
     cudaMemcpy(hst, dbg, sizeof hst, cudaMemcpyDeviceToHost);
-    const char* nm[10] = {"epi entry", "epi waited", "phase0 done", "tmem full", "scatter done", "cluster barrier", "finalize done", "", "producer done", "mma committed"};
+    const char* nm[14] = {"epi entry", "epi waited", "phase0 done", "tmem full", "copies issued", "recv+bar", "finalize done", "", "producer done", "mma committed", "tok loop done", "bar2", "cpasync waited", "recv waited"};
     fprintf(stderr, "[dk dbg] T=%d n_out=%d K=%d cs=%d bn=%d:", T, n_out, K, g.cs, g.bn);
-    for (int i = 0; i < 10; ++i) if (hst[i]) fprintf(stderr, " %s +%.2fus;", nm[i], (double)((long long)hst[i] - (long long)hst[0]) / 1e3);
+    for (int i = 0; i < 14; ++i) if (hst[i]) fprintf(stderr, " %s +%.2fus;", nm[i], (double)((long long)hst[i] - (long long)hst[0]) / 1e3);
     fprintf(stderr, "\n");
     cudaFree(dbg);
   }
-  return rc;
-}
-
-int mq_debug_gemm_dk_qkv(const void* W, int n_q, int n_kv, int head_dim, int K, const void* X, int x_rows_alloc, int T,
-                         int cs, const float* ssq, int parts, int stride, float inv_h, float eps, const void* bias,
-                         const int* pos, const int* slot_of_tok, const int* block_table, int max_pages,
-                         const float* inv_freq, int max_pos, void* q_out, void* k_cache, void* v_cache, int reps,
-                         float* ms_out) {
-  if (!head_dim_supported(head_dim)) { mq::set_last_error("head_dim must be 128, 96 or 64"); return MQ_ERR_INVAL; }
-  DkPlan g;
-  gemm_set_attrs();
-  const int n_out = (n_q + 2 * n_kv) * head_dim;
-  if (!dk_plan(&g, DK_QKV, W, n_out, n_out, K, X, x_rows_alloc, T, head_dim, cs)) {
-    mq::set_last_error("dk_plan failed (T > 64, K %% 64, cluster size / tokens per rank)");
-    return MQ_ERR_INVAL;
-  }
-  float2* table = nullptr;
-  if (cudaMalloc((void**)&table, (size_t)max_pos * (head_dim / 2) * sizeof(float2)) != cudaSuccess) return MQ_ERR_NOMEM;
-  launch_rope_table(0, table, inv_freq, max_pos, head_dim / 2);
-  g.p.rs = RstdIn{ssq, parts, stride, inv_h, eps};
-  g.p.bias = (const __nv_bfloat16*)bias; g.p.pos = pos; g.p.slot_of_tok = slot_of_tok; g.p.block_table = block_table;
-  g.p.max_pages = max_pages; g.p.rope_table = table; g.p.q_out = (__nv_bfloat16*)q_out;
-  g.p.k_cache = (__nv_bfloat16*)k_cache; g.p.v_cache = (__nv_bfloat16*)v_cache; g.p.n_q = n_q; g.p.n_kv = n_kv;
-  LaunchCfg lc{0, false};
-  const int rc = timed_launches("mq_debug_gemm_dk_qkv", [&] { return dk_launch(g, lc); }, reps, ms_out);
-  cudaFree(table);
   return rc;
 }
 

@@ -13,6 +13,7 @@
 #include "../../include/ollamamq_b200.h"
 #include "sched.hpp"
 #include "framing.hpp"
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -74,6 +75,7 @@ struct MockBackend : Backend {
   std::mutex mu;
   std::deque<std::shared_ptr<Pending>> q;
   int fail_next = 0;
+  std::atomic<bool> answers_probe{true};  // what the health prober sees (GET /api/tags answered or not, :181-183)
   int submit(const mq_request* rq, const mq_callbacks* cb, void* user, void** handle) override {
     std::lock_guard<std::mutex> g(mu);
     if (fail_next > 0) {
@@ -94,7 +96,7 @@ struct MockBackend : Backend {
     for (auto& p : q) if (p.get() == h) p->canceled = true;
   }
   void release(void*) override {}
-  bool healthy() override { return true; }
+  bool healthy() override { return answers_probe.load(); }
   // returns 1 when a request was completed
   int complete_oldest(int rc) {
     std::shared_ptr<Pending> p;
@@ -441,6 +443,12 @@ int mq_dispatcher_mock_fail_next(mq_dispatcher* d, int32_t backend, int32_t n) {
   d->mocks[backend]->fail_next = n;
   return MQ_OK;
 }
+// what mock backend `backend` answers to the health probe from now on (0: like an unreachable /api/tags)
+int mq_dispatcher_mock_set_healthy(mq_dispatcher* d, int32_t backend, int32_t healthy) {
+  if (!d || backend < 0 || backend >= (int)d->mocks.size()) return MQ_ERR_INVAL;
+  d->mocks[backend]->answers_probe.store(healthy != 0);
+  return MQ_OK;
+}
 
 void mq_dispatcher_free(mq_dispatcher* d) {
   if (!d) return;
@@ -559,6 +567,58 @@ int mq_dispatcher_block_ip(mq_dispatcher* d, const char* ip, int32_t blocked) {
   save_blocked(d);
   return MQ_OK;
 }
+// The dashboard's control keys as ONE atomic call (tui.rs:126-237), for front ends without a terminal (HTTP /admin/*):
+//   "vip" / "boost"            the 'p' / 'b' key on `user`: toggle, and clear the other flag when it names the same user
+//   "vip_add" / "boost_add"    EXTENSION (BASELINE config 3): add `user` to the set; "vip_clear" / "boost_clear": empty it
+//   "block_user"               'x'         "block_ip"  'X' (`ip`, or the last address `user` was seen from)
+//   "unblock"                  'u' on the users panel: the user AND its last address
+//   "unblock_user" / "unblock_ip"   'u' on an entry of the blocked panel
+int mq_dispatcher_control(mq_dispatcher* d, const char* action, const char* user, const char* ip) {
+  if (!d || !action) return MQ_ERR_INVAL;
+  const std::string a = action;
+  std::lock_guard<std::mutex> g(d->mu);  // no notify: takes effect at the next natural wake-up, like the reference
+  auto has = [](const std::vector<std::string>& v, const char* u) { return u && std::find(v.begin(), v.end(), u) != v.end(); };
+  auto need_user = [&]() { if (!user || !*user) { set_last_error("'%s' needs a user", action); return false; } return true; };
+  auto last_ip = [&]() -> std::string {
+    if (ip && *ip) return ip;
+    auto it = user ? d->user_ips.find(user) : d->user_ips.end();
+    return it == d->user_ips.end() ? std::string() : it->second;
+  };
+  Scheduler& s = d->sched->s;
+  if (a == "vip" || a == "boost") {
+    if (!need_user()) return MQ_ERR_INVAL;
+    const bool is_vip = a == "vip";
+    const bool on = has(is_vip ? s.vips() : s.boosts(), user);
+    const bool other = has(is_vip ? s.boosts() : s.vips(), user);
+    if (is_vip) { s.set_vip(on ? nullptr : user); if (other) s.set_boost(nullptr); }
+    else { s.set_boost(on ? nullptr : user); if (other) s.set_vip(nullptr); }
+    return MQ_OK;
+  }
+  if (a == "vip_add") { if (!need_user()) return MQ_ERR_INVAL; s.add_vip(user); return MQ_OK; }
+  if (a == "boost_add") { if (!need_user()) return MQ_ERR_INVAL; s.add_boost(user); return MQ_OK; }
+  if (a == "vip_clear") { s.set_vip(nullptr); return MQ_OK; }
+  if (a == "boost_clear") { s.set_boost(nullptr); return MQ_OK; }
+  if (a == "block_user") { if (!need_user()) return MQ_ERR_INVAL; d->blocked_users.insert(user); save_blocked(d); return MQ_OK; }
+  if (a == "unblock_user") { if (!need_user()) return MQ_ERR_INVAL; d->blocked_users.erase(user); save_blocked(d); return MQ_OK; }
+  if (a == "block_ip" || a == "unblock_ip") {
+    const std::string v = last_ip();
+    if (v.empty()) { set_last_error("'%s' needs an ip (or a user that has been seen)", action); return MQ_ERR_INVAL; }
+    if (a == "block_ip") d->blocked_ips.insert(v); else d->blocked_ips.erase(v);
+    save_blocked(d);
+    return MQ_OK;
+  }
+  if (a == "unblock") {
+    if (!need_user()) return MQ_ERR_INVAL;
+    d->blocked_users.erase(user);
+    const std::string v = last_ip();
+    if (!v.empty()) d->blocked_ips.erase(v);
+    save_blocked(d);
+    return MQ_OK;
+  }
+  set_last_error("unknown control action '%s'", action);
+  return MQ_ERR_INVAL;
+}
+
 // One consistent view of everything the reference dashboard shows (tui.rs:55-95 capture_snapshot): taken under the
 // dispatcher lock, users already in the dashboard's order.  JSON so that a curses / web front end needs one call.
 static void js_str(std::string& o, const std::string& v) {

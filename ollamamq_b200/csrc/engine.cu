@@ -229,34 +229,32 @@ static int build_plans(mq_worker* w, PassPlans* pp, int T, bool decode) {
   const int x_rows = w->MT;
   // ---- decode chain: servable when every GEMM of the layer fits the cluster kernel (T <= 64, one head per QKV tile)
   const int tiles_h = (H + 127) / 128;
-  pp->chain = decode && !sk && w->chain && T <= 64 &&
-              dk_pick_cluster(c.n_q_heads + 2 * c.n_kv_heads, H / 64, T) > 0 && dk_pick_cluster(tiles_h, qd / 64, T) > 0 &&
+  pp->chain = decode && !sk && w->chain && T <= 64 && dk_pick_cluster(tiles_h, qd / 64, T) > 0 &&
               dk_pick_cluster(tiles_h, I / 64, T) > 0;
   if (pp->chain) {
-    pp->qkv_dk.resize(c.n_layers); pp->o_dk.resize(c.n_layers); pp->down_dk.resize(c.n_layers); pp->gate_up.resize(c.n_layers);
+    pp->qkv.resize(c.n_layers); pp->o_dk.resize(c.n_layers); pp->down_dk.resize(c.n_layers); pp->gate_up.resize(c.n_layers);
+    pp->s_qkv = decode_splits((w->qkv_dim + 127) / 128, H / 64);
     const RstdIn rs_o{w->ssq_o, tiles_h, MBp, 1.0f / (float)H, c.rms_eps};
     const RstdIn rs_d{w->ssq_d, tiles_h, MBp, 1.0f / (float)H, c.rms_eps};
     const RstdIn rs_e{w->ssq_e, 1, MBp, 1.0f / (float)H, c.rms_eps};
     for (int l = 0; l < c.n_layers; ++l) {
       const LayerWeights& lw = w->layers[l];
-      DkPlan& q = pp->qkv_dk[l];
       DkPlan& o = pp->o_dk[l];
       DkPlan& d = pp->down_dk[l];
-      bool ok = dk_plan(&q, DK_QKV, lw.wqkv, w->qkv_dim, w->qkv_dim, H, w->x, x_rows, T, D, 0);
-      ok &= dk_plan(&o, DK_RESID, lw.wo, H, H, qd, w->attn, x_rows, T, 128, 0);
-      ok &= dk_plan(&d, DK_RESID, lw.w_down, H, H, I, w->act, x_rows, T, 128, 0);
+      // QKV stays a plane-writing split-K GEMM on all SMs (48 head tiles x 3 splits; a cluster kernel fits only 45
+      // clusters of 3, and 48 x 2 CTAs measured 4.3 us per layer slower) with the RMSNorm fold in its epilogue; the
+      // small rope kernel sums the planes, rotates and writes q / the paged KV
+      bool ok = gemm_plan(&pp->qkv[l], lw.wqkv, w->qkv_dim, w->qkv_dim, H, w->x, x_rows, T, EPI_F32, w->qkv_part, w->qkv_dim,
+                          pp->s_qkv, (long long)MBp * w->qkv_dim, 0, nullptr);
+      ok &= dk_plan(&o, lw.wo, H, H, qd, w->attn, x_rows, T, 128, 0);
+      ok &= dk_plan(&d, lw.w_down, H, H, I, w->act, x_rows, T, 128, 0);
       ok &= gemm_plan(&pp->gate_up[l], lw.w_gate_up, 2 * I, I, H, w->x, x_rows, T, EPI_SILU_BF16, w->act, I, 1, 0, I,
                       nullptr, getenv("MQ_GU_ROWS") ? atoi(getenv("MQ_GU_ROWS")) : gemm_balanced_rows(I));
       if (!ok) {
         set_last_error("decode-chain plan failed (layer %d, T=%d)", l, T);
         return MQ_ERR_CUDA;
       }
-      q.p.rs = l == 0 ? rs_e : rs_d;
-      q.p.bias = lw.bqkv; q.p.pos = w->d_pos; q.p.slot_of_tok = w->d_identity; q.p.block_table = w->d_block_table;
-      q.p.max_pages = w->max_pages; q.p.rope_table = w->rope_table; q.p.q_out = w->q;
-      q.p.k_cache = w->k_cache + (size_t)l * w->cache_layer_stride;
-      q.p.v_cache = w->v_cache + (size_t)l * w->cache_layer_stride;
-      q.p.n_q = c.n_q_heads; q.p.n_kv = c.n_kv_heads;
+      gemm_plan_set_rstd(&pp->qkv[l], l == 0 ? rs_e : rs_d);
       o.p.h = w->h; o.p.ldh = H; o.p.gamma_next = lw.mlp_norm; o.p.xg = w->x; o.p.ldx = H; o.p.ssq_out = w->ssq_o;
       o.p.ssq_stride = MBp;
       d.p.h = w->h; d.p.ldh = H; d.p.gamma_next = l + 1 < c.n_layers ? w->layers[l + 1].attn_norm : w->final_norm;
@@ -342,8 +340,8 @@ static void fill_attn_params(mq_worker* w, const PassArgs& a, int l, AttnParams*
   ap->split_counter = w->d_split_counter; ap->scale_log2 = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
 }
 
-// Decode chain: 5 launches per layer.  Timeline slots (tools/decode_timeline.py): 1 + 8 * layer + {1 qkv, 3 attention,
-// 4 o, 6 gate/up, 7 down}; slots 0 / 2 / 5 (norm1, rope, norm2 of the plane-based path) stay unused.
+// Decode chain: 6 launches per layer (no RMSNorm kernels).  Timeline slots (tools/decode_timeline.py): 1 + 8 * layer +
+// {1 qkv, 2 rope, 3 attention, 4 o, 6 gate/up, 7 down}; slots 0 / 5 (norm1, norm2 of the plane-based path) stay unused.
 static int run_layers_chain(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* n_launch) {
   const mq_model_cfg& c = w->cfg;
   const LaunchCfg lc{w->stream, c.use_pdl != 0};
@@ -351,8 +349,17 @@ static int run_layers_chain(mq_worker* w, const PassArgs& a, PassPlans* pp, uint
   launch_embed(lc, a.tok, w->embed, w->h, a.T, c.hidden, w->layers[0].attn_norm, w->x, w->ssq_e); ++nl;
   for (int l = 0; l < c.n_layers; ++l) {
     auto tr = [&](int k) { return Trace{w->d_trace, 1 + 8 * l + k}; };
-    pp->qkv_dk[l].p.tr = tr(1);
-    if (dk_launch(pp->qkv_dk[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
+    pp->qkv[l].p.tr = tr(1);
+    if (gemm_launch(pp->qkv[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
+    RopeKvParams rp;
+    rp.qkv = w->qkv_part; rp.qkv_is_f32 = true; rp.n_planes = pp->s_qkv; rp.plane_stride = (long long)round_up(w->MB, 16) * w->qkv_dim;
+    rp.bias = w->layers[l].bqkv; rp.pos = a.pos; rp.slot_of_tok = a.slot_of_tok; rp.block_table = w->d_block_table;
+    rp.max_pages = w->max_pages; rp.inv_freq = w->inv_freq; rp.rope_table = w->rope_table; rp.q_out = w->q;
+    rp.k_cache = w->k_cache + (size_t)l * w->cache_layer_stride;
+    rp.v_cache = w->v_cache + (size_t)l * w->cache_layer_stride;
+    rp.T = a.T; rp.n_q = c.n_q_heads; rp.n_kv = c.n_kv_heads; rp.head_dim = c.head_dim;
+    rp.tr = tr(2);
+    launch_rope_kv(lc, rp); ++nl;
     AttnParams ap;
     fill_attn_params(w, a, l, &ap, tr(3));
     launch_attn_decode(lc, ap, a.T); ++nl;
@@ -765,7 +772,7 @@ static int launch_decode(mq_worker* w) {
     // graph wrote to the fixed row kRing-1; move it to this step's ring slot on the host side copy
     cudaMemcpyAsync(w->h_out_ring + (size_t)ring * MBp, w->d_out_ring + (size_t)(kRing - 1) * MBp, Bcap * 4,
                     cudaMemcpyDeviceToHost, w->stream);
-    nl = get_plans(w, Bcap, true)->chain ? (uint64_t)(1 + w->cfg.n_layers * 5 + 2) : (uint64_t)(1 + w->cfg.n_layers * 8 + 3);
+    nl = get_plans(w, Bcap, true)->chain ? (uint64_t)(1 + w->cfg.n_layers * 6 + 2) : (uint64_t)(1 + w->cfg.n_layers * 8 + 3);
   } else {
     int rc = decode_body(w, Bcap, n_splits, attn_stages, ring, &nl);
     if (rc) return rc;
@@ -1235,7 +1242,22 @@ int mq_worker_init_random(mq_worker* w, uint64_t seed, float std) {
 }
 
 int mq_worker_capacity(mq_worker* w) { return w ? w->MB : 0; }
-int mq_worker_healthy(mq_worker* w) { return w && w->healthy.load() ? 1 : 0; }
+int mq_worker_healthy(mq_worker* w) { return w && w->healthy.load() && !w->probe_fail.load() ? 1 : 0; }
+int mq_debug_worker_set_probe_fail(mq_worker* w, int32_t probe_fail) {
+  if (!w) return MQ_ERR_INVAL;
+  w->probe_fail.store(probe_fail != 0);
+  return MQ_OK;
+}
+int mq_debug_worker_inject_fault(mq_worker* w, const char* msg) {
+  if (!w) return MQ_ERR_INVAL;
+  {
+    std::lock_guard<std::mutex> g(w->mu);  // w->fatal is read by the worker thread after it sees healthy == false
+    w->fatal = std::string("GPU fault: ") + (msg ? msg : "injected");
+  }
+  w->healthy.store(false);
+  w->cv.notify_all();
+  return MQ_OK;
+}
 
 int mq_submit(mq_worker* w, const mq_request* rq, const mq_callbacks* cb, void* user, mq_req** out) {
   if (!w || !rq || !cb) return MQ_ERR_INVAL;

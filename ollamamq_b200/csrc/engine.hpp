@@ -34,10 +34,11 @@ struct PassPlans {
   bool decode = false;
   int s_qkv = 1, s_o = 1, s_down = 1;
   std::vector<GemmPlan> qkv, o, gate_up, down;  // per layer
-  // decode chain (gemm_dk.cuh): cluster split-K GEMMs with fused RoPE / residual epilogues, RMSNorm folded into the
-  // consumers - 5 launches per layer instead of 8; `gate_up` then carries the rstd fold and balanced tile rows
+  // decode chain (gemm_dk.cuh): O and down are cluster split-K GEMMs with the residual add / next-norm partials fused,
+  // RMSNorm itself is folded into the consumers' epilogues - 6 launches per layer instead of 8, no norm kernels;
+  // `qkv` (planes) and `gate_up` then carry the rstd fold
   bool chain = false;
-  std::vector<DkPlan> qkv_dk, o_dk, down_dk;
+  std::vector<DkPlan> o_dk, down_dk;
 };
 
 }  // namespace mq
@@ -135,6 +136,7 @@ struct mq_worker {
   std::deque<std::function<void()>> jobs;
   bool stop = false;
   std::atomic<bool> healthy{true};
+  std::atomic<bool> probe_fail{false};  // fault injection: the health probe fails while the engine keeps serving
   std::string fatal;
 
   // in-flight GPU work (FIFO)

@@ -63,7 +63,7 @@ static cudaError_t launch_one(const CUtensorMap& a, const CUtensorMap& b, const 
   // dynamic-smem opt-in happens once per device in gemm_set_attrs() (never inside a graph capture)
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(BN <= 64 ? kGemmThreadsDecode : kGemmThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = lc.stream;
   cudaLaunchAttribute attr[1];
@@ -297,7 +297,6 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   // one token tile, no split-K and fewer weight tiles than half the SMs (Phi-3 gate/up at 256 slots: 64 tiles): halve
   // the token tile so two CTAs share each weight tile through L2 - same HBM bytes, twice the SMs streaming them
   if (T > 128 && T <= 256 && splits == 1 && (n_out + kBlockM - 1) / kBlockM * 2 <= device_sm_count()) g->bn = 128;
-  g->epi = epi;
   g->splits = splits;
   // tile_rows < 128 only for the plain decode-width kernel (one token tile): see GemmParams::tile_rows
   if (tile_rows <= 0 || tile_rows > kBlockM || tile_rows % 8 != 0 || g->streamk || T > g->bn) tile_rows = kBlockM;
@@ -371,11 +370,11 @@ void gemm_plan_set_rstd(GemmPlan* g, const RstdIn& rs) {
   g->sk.rs = rs;
 }
 
-template <int BN, int EPI>
+template <int BN>
 static int dk_query_clusters(int cs) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cs * 64);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(kDkThreads);
   cfg.dynamicSmemBytes = dk_smem_bytes(BN);
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -383,7 +382,7 @@ static int dk_query_clusters(int cs) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gemm_dk_kernel<BN, EPI>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_dk_kernel<BN>, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
   return n;
 }
 // clusters of `cs` CTAs (one per SM, ~200 KiB of shared memory each) the device runs at once; cached per process
@@ -391,7 +390,7 @@ int dk_max_clusters(int cs) {
   static int cache[kDkMaxCluster + 1] = {0};
   static std::once_flag once;
   std::call_once(once, [] {
-    for (int c = 1; c <= kDkMaxCluster; ++c) cache[c] = c == 1 ? device_sm_count() : dk_query_clusters<64, DK_RESID>(c);
+    for (int c = 1; c <= kDkMaxCluster; ++c) cache[c] = c == 1 ? device_sm_count() : dk_query_clusters<64>(c);
   });
   return (cs >= 1 && cs <= kDkMaxCluster) ? cache[cs] : 0;
 }
@@ -409,7 +408,7 @@ int dk_pick_cluster(int m_tiles, int k_blocks, int T) {
   return best;  // 0: shape not servable by the chain kernel (caller falls back to the plane-based path)
 }
 
-bool dk_plan(DkPlan* g, int epi, const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T,
+bool dk_plan(DkPlan* g, const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T,
              int tile_rows, int cs) {
   if (K % kBlockK != 0 || T < 1 || T > 64 || tile_rows < 8 || tile_rows > kBlockM || tile_rows % 8 != 0) return false;
   const int kb = K / kBlockK;
@@ -417,7 +416,6 @@ bool dk_plan(DkPlan* g, int epi, const void* W, int w_rows, int n_out, int K, co
   if (cs <= 0) cs = dk_pick_cluster(m_tiles, kb, T);
   if (cs < 1 || cs > kDkMaxCluster || (T + cs - 1) / cs > kDkMaxTok) return false;
   g->bn = gemm_pick_bn(T);
-  g->epi = epi;
   g->cs = cs;
   g->m_tiles = m_tiles;
   if (!tmap_encode_2d(&g->tmA, W, (uint64_t)w_rows, (uint64_t)K, (uint32_t)tile_rows)) return false;
@@ -432,11 +430,11 @@ bool dk_plan(DkPlan* g, int epi, const void* W, int w_rows, int n_out, int K, co
   return true;
 }
 
-template <int BN, int EPI>
+template <int BN>
 static cudaError_t launch_dk(const DkPlan& g, const LaunchCfg& lc) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(g.m_tiles * g.cs);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(kDkThreads);
   cfg.dynamicSmemBytes = dk_smem_bytes(BN);
   cfg.stream = lc.stream;
   cudaLaunchAttribute attr[2];
@@ -446,28 +444,22 @@ static cudaError_t launch_dk(const DkPlan& g, const LaunchCfg& lc) {
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = lc.pdl ? 2 : 1;
-  return cudaLaunchKernelEx(&cfg, gemm_dk_kernel<BN, EPI>, g.tmA, g.tmB, g.p);
+  return cudaLaunchKernelEx(&cfg, gemm_dk_kernel<BN>, g.tmA, g.tmB, g.p);
 }
-template <int EPI>
-static cudaError_t launch_dk_bn(const DkPlan& g, const LaunchCfg& lc) {
+cudaError_t dk_launch(const DkPlan& g, const LaunchCfg& lc) {
   switch (g.bn) {
-    case 16: return launch_dk<16, EPI>(g, lc);
-    case 32: return launch_dk<32, EPI>(g, lc);
-    case 64: return launch_dk<64, EPI>(g, lc);
+    case 16: return launch_dk<16>(g, lc);
+    case 32: return launch_dk<32>(g, lc);
+    case 64: return launch_dk<64>(g, lc);
     default: return cudaErrorInvalidValue;
   }
 }
-cudaError_t dk_launch(const DkPlan& g, const LaunchCfg& lc) {
-  return g.epi == DK_QKV ? launch_dk_bn<DK_QKV>(g, lc) : launch_dk_bn<DK_RESID>(g, lc);
-}
-template <int BN, int EPI>
+template <int BN>
 static void set_attrs_dk() {
-  cudaFuncSetAttribute(gemm_dk_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, dk_smem_bytes(BN));
-  cudaFuncSetAttribute(gemm_dk_kernel<BN, EPI>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
+  cudaFuncSetAttribute(gemm_dk_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, dk_smem_bytes(BN));
 }
 void dk_set_attrs() {
-  set_attrs_dk<16, DK_RESID>(); set_attrs_dk<32, DK_RESID>(); set_attrs_dk<64, DK_RESID>();
-  set_attrs_dk<16, DK_QKV>(); set_attrs_dk<32, DK_QKV>(); set_attrs_dk<64, DK_QKV>();
+  set_attrs_dk<16>(); set_attrs_dk<32>(); set_attrs_dk<64>();
 }
 
 }  // namespace mq

@@ -67,7 +67,8 @@ struct GemmParams {
   const void* bias;             // EPI_GELU_BF16 / EPI_BIAS_BF16: bf16 [n_out] (nullable)
 };
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 192;        // producer warp + MMA warp + 4 epilogue warps
+constexpr int kGemmThreadsDecode = 320;  // ... + 8 epilogue warps (decode widths: the epilogue is on the critical path)
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kATileBytes = kBlockM * kBlockK * 2;  // 16 KiB
@@ -93,7 +94,7 @@ __host__ __device__ constexpr uint32_t gemm_tmem_cols(int bn, int epi) {
 }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreadsDecode, 1)
 gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   constexpr bool kDual = (EPI == EPI_SILU_BF16);
@@ -207,11 +208,14 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // The accumulator is transposed on its way out: each thread owns one feature (TMEM lane) and walks the
     // token columns, writing a [token][tile_rows features] tile into the (now idle) pipeline smem; one TMA tensor
     // store then moves the whole tile to global memory, coalesced and clipped to the tensor bounds.
+    // 4 or 8 epilogue warps (blockDim): two warps may share a TMEM lane quarter and split the token columns
+    const int n_epi = (int)blockDim.x - 64;
+    const int hid = (warp - 2) >> 2, n_half = n_epi >> 7;
     const bool fold = p.rs.ssq != nullptr;
     if (fold) {  // RMSNorm fold: per-token scale, computed while the mainloop streams (sums are from the previous kernel)
       pdl_wait();
-      for (int t = threadIdx.x - 64; t < BN; t += 128) rstd_s[t] = (n0 + t < p.T) ? rstd_of(p.rs, n0 + t) : 0.f;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int t = threadIdx.x - 64; t < BN; t += n_epi) rstd_s[t] = (n0 + t < p.T) ? rstd_of(p.rs, n0 + t) : 0.f;
+      asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory");
     }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
@@ -223,7 +227,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t stg_a = smem_u32(stg), rstd_a = smem_u32(rstd_s);
     constexpr int ESZ = EPI == EPI_F32 ? 4 : 2;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
+    for (int c0 = hid * 16; c0 < BN; c0 += 16 * n_half) {
       if (n0 + c0 >= p.T) break;  // warp-uniform; columns past T are clipped by the store anyway
       uint32_t v[16];
       tmem_ld16(t_lane + c0, v);
@@ -237,7 +241,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const float sc = fold ? lds_f32(rstd_a + (uint32_t)(c0 + j) * 4u) : 1.f;
           const float g = __uint_as_float(v[j]) * sc;
           const float up = __uint_as_float(u[j]) * sc;
-          if (live) sts_bf16(o + (uint32_t)(j * R) * 2u, g / (1.0f + __expf(-g)) * up);
+          if (live) sts_bf16(o + (uint32_t)(j * R) * 2u, __fdividef(g, 1.0f + __expf(-g)) * up);
         }
       } else {
         tmem_ld_wait();
@@ -263,7 +267,7 @@ gemm_wx_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     fence_proxy_async();                                   // generic-proxy smem writes -> visible to the TMA engine
-    asm volatile("bar.sync 1, 128;" ::: "memory");         // the four epilogue warps only
+    asm volatile("bar.sync 1, %0;" ::"r"(n_epi) : "memory");  // the epilogue warps only
     if (warp == 2 && lane == 0) {
       if constexpr (EPI == EPI_F32) tma_store_3d(&tmC, stg, m0, n0, blockIdx.z);
       else tma_store_2d(&tmC, stg, m0, n0);

@@ -215,7 +215,7 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const float g = __uint_as_float(v[j]);
-          o[j * kBlockM] = __float2bfloat16(g / (1.0f + __expf(-g)) * __uint_as_float(u[j]));
+          o[j * kBlockM] = __float2bfloat16(__fdividef(g, 1.0f + __expf(-g)) * __uint_as_float(u[j]));
         }
       } else {
         tmem_ld_wait();

@@ -14,29 +14,26 @@
 //   3. one barrier.cluster (release / acquire);
 //   4. every CTA finishes ITS token range for all 128 features of the tile, partial sums added in rank order
 //      (deterministic), then the fused epilogue:
-//        DK_RESID (O and down projections):  h[t,f] += sum;  xg[t,f] = bf16(h * gamma_next[f]);
-//                                            ssq_out[tile][t] = sum_f h^2      (per-tile partial of the next RMSNorm)
-//        DK_QKV:  v = sum * rstd[t] (+ bias[f]);  rotate-half RoPE on q / k heads (tile = one head, the partner
-//                 feature f +- D/2 sits in the same receive buffer);  q -> q_out, k / v -> the paged KV cache.
+//        h[t,f] += sum;  xg[t,f] = bf16(h * gamma_next[f]);  ssq_out[tile][t] = sum_f h^2  (per-tile partial of the
+//        next RMSNorm) - the O and down projections.  (A DK_QKV variant with RoPE and the paged-KV write in the epilogue
+//        was built, parity-tested and measured: 48 head tiles fit only 2-CTA clusters = 96 SMs, 4.3 us per layer slower
+//        than the 144-CTA plane GEMM + the small rope kernel, so QKV stays on that path - profiles/r02_ablations.md.)
 // RMSNorm itself never runs as a kernel: x = h * rstd * gamma feeds only GEMMs, and rstd[t] is a per-token scalar,
 // so the producer emits xg = bf16(h * gamma) and the consumer scales its accumulator column t by
 // rstd[t] = rsqrt(sum_tiles ssq[tile][t] / H + eps)  (RstdIn; summed in tile order: deterministic).
 #pragma once
 #include "gemm.cuh"
+#include <type_traits>
 
 namespace mq {
-
-enum DkEpilogue : int { DK_RESID = 0, DK_QKV = 1 };
 
 struct DkParams {
   int T;             // valid activation rows (<= BN)
   int n_out;         // valid output features
-  int tile_rows;     // weight rows per tile (<= 128, multiple of 8); DK_QKV: = head_dim, so a tile is one head
+  int tile_rows;     // weight rows per tile (<= 128, multiple of 8)
   int k_blocks;      // K / 64
   int kb_per_split;  // k-blocks per cluster rank
   unsigned long long w_policy;
-  RstdIn rs;         // DK_QKV: RMSNorm fold of the activation operand
-  // ---- DK_RESID
   float* h;          // [T][ldh] fp32 residual stream, updated in place
   int ldh;
   const __nv_bfloat16* gamma_next;  // [n_out] weight of the NEXT RMSNorm
@@ -44,26 +41,17 @@ struct DkParams {
   int ldx;
   float* ssq_out;    // [m_tiles][ssq_stride]
   int ssq_stride;
-  // ---- DK_QKV
-  const __nv_bfloat16* bias;  // nullable [n_out]
-  const int* pos;             // [T]
-  const int* slot_of_tok;     // [T]
-  const int* block_table;     // [slots][max_pages]
-  int max_pages;
-  const float2* rope_table;   // [positions][tile_rows / 2] (cos, sin)
-  __nv_bfloat16* q_out;       // [T][n_q * D]
-  __nv_bfloat16* k_cache;     // layer base: [pages][n_kv][16][D]
-  __nv_bfloat16* v_cache;
-  int n_q, n_kv;
   Trace tr;
-  unsigned long long* dbg;  // optional: phase stamps of CTA 0 (%globaltimer ns), see tests/tools (nullptr in production)
+  unsigned long long* dbg;  // optional: phase stamps of CTA 0 (%globaltimer ns), tools/dk_bench.py (nullptr in production)
 };
 __device__ __forceinline__ void dk_stamp(const DkParams& p, int k) {
   if (p.dbg && blockIdx.x == 0) p.dbg[k] = globaltimer_ns();
 }
 
 constexpr int kDkMaxCluster = 8;  // portable cluster size limit
-constexpr int kDkPage = 16;    // tokens per KV page (= kPageSize, kernels.cuh)
+constexpr int kDkThreads = 64 + 256;  // TMA producer warp, MMA issuer warp, 8 epilogue warps (two per TMEM lane quarter:
+                                      // the epilogue runs on single-warp schedulers, so halving its per-thread work
+                                      // halves its time - measured 2.4 -> ... us per launch)
 constexpr int kDkMaxTok = 32;  // tokens one CTA finishes (its preload buffer): T > 32 needs CS >= 2
 // shared memory: [TMA ring][receive buffer: CS slots x tok_per tokens x 128 fp32][preload: MAXTOK x 128 fp32][misc]
 __host__ __device__ constexpr int dk_maxtok(int bn) { return bn < kDkMaxTok ? bn : kDkMaxTok; }
@@ -81,8 +69,8 @@ __host__ __device__ constexpr int dk_smem_bytes(int bn) {
 // Code-size note (measured, B200): a first version kept the per-token preloads in registers and unrolled the token
 // loops 32x - 200 KB of SASS per instance, and the finalize phase ran at ~1 us per token on instruction fetch alone.
 // Everything per-token now lives in shared memory and the loops are rolled.
-template <int BN, int EPI>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BN>
+__global__ void __launch_bounds__(kDkThreads, 1)
 gemm_dk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const DkParams p) {
   constexpr int STAGES = dk_stages(BN);
   constexpr int STAGE_BYTES = gemm_stage_bytes(BN, EPI_F32);
@@ -105,9 +93,6 @@ gemm_dk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* recv_bar = tmem_full_bar + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(recv_bar + 1);
-  float* rstd_s = reinterpret_cast<float*>(tail + 256);                  // [MAXTOK]
-  uint32_t* dst_s = reinterpret_cast<uint32_t*>(rstd_s + MAXTOK);        // [MAXTOK] element offset of (token, feature 0)
-  int* pos_s = reinterpret_cast<int*>(dst_s + MAXTOK);                   // [MAXTOK]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -150,9 +135,8 @@ gemm_dk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int row = q * 32 + lane;       // epilogue: feature row of the tile
   const int f = m0 + row;
   const bool frow = warp >= 2 && row < R && f < p.n_out;
-  const int et = threadIdx.x - 64;     // epilogue thread index 0..127
-  const int half = R >> 1;
-  const int head = tile_m;             // DK_QKV: q heads, then k heads, then v heads
+  const int et = threadIdx.x - 64;     // epilogue thread index 0..255
+  const int hid = et >> 7;             // which of the two warps of this lane quarter: takes every other token / column chunk
 
   if (warp == 0) {
     if (lane == 0) {
@@ -206,37 +190,12 @@ gemm_dk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (et == 0) dk_stamp(p, 0);
     pdl_wait();
     if (et == 0) dk_stamp(p, 1);
-    float gm = 0.f, bs = 0.f, bs2 = 0.f;  // gamma_next[f] / bias of this feature and of its rotation partner
-    if constexpr (EPI == DK_RESID) {
-      if (frow) {
-        gm = __bfloat162float(p.gamma_next[f]);
-        const uint32_t dsts = smem_u32(pre + row);
-        const float* src = p.h + (size_t)t0 * p.ldh + f;
-        for (int i = 0; i < ntok; ++i) cp_async4(dsts + (uint32_t)(i * kBlockM) * 4u, src + (size_t)i * p.ldh);
-      }
-    } else {
-      if (p.bias && frow) {
-        bs = __bfloat162float(p.bias[f]);
-        bs2 = __bfloat162float(p.bias[m0 + (row < half ? row + half : row - half)]);
-      }
-      if (et < ntok) {
-        const int t = t0 + et;
-        const int ps = p.pos[t];
-        pos_s[et] = ps;
-        rstd_s[et] = rstd_of(p.rs, t);
-        if (head < p.n_q) {
-          dst_s[et] = (uint32_t)(((size_t)t * p.n_q + head) * R);
-        } else {
-          const int kvh = head < p.n_q + p.n_kv ? head - p.n_q : head - p.n_q - p.n_kv;
-          const int page = p.block_table[(size_t)p.slot_of_tok[t] * p.max_pages + ps / kDkPage];
-          dst_s[et] = (uint32_t)((((size_t)page * p.n_kv + kvh) * kDkPage + ps % kDkPage) * R);
-        }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (head < p.n_q + p.n_kv && row < half) {  // (cos, sin) rows of this rank's tokens: [MAXTOK][half] float2
-        const uint32_t dsts = smem_u32(pre) + (uint32_t)row * 8u;
-        for (int i = 0; i < ntok; ++i) cp_async8(dsts + (uint32_t)(i * half) * 8u, p.rope_table + (size_t)pos_s[i] * half + row);
-      }
+    float gm = 0.f;  // gamma_next[f]
+    if (frow) {
+      gm = __bfloat162float(p.gamma_next[f]);
+      const uint32_t dsts = smem_u32(pre + row);
+      const float* src = p.h + (size_t)t0 * p.ldh + f;
+      for (int i = hid; i < ntok; i += 2) cp_async4(dsts + (uint32_t)(i * kBlockM) * 4u, src + (size_t)i * p.ldh);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     // ---- phase 1: partial accumulator -> [token][feature] tile in the idle ring -> bulk copies to the owners
@@ -246,7 +205,7 @@ gemm_dk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (et == 0) dk_stamp(p, 3);
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
+    for (int c0 = hid * 16; c0 < BN; c0 += 32) {
       if (c0 >= p.T) break;
       uint32_t v[16];
       if (nkb > 0) {
@@ -263,7 +222,7 @@ gemm_dk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     fence_proxy_async();                            // generic-proxy smem writes -> visible to the bulk-copy engine
     cluster_wait_acquire();                         // barrier #1: every peer's receive barrier is armed
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // whole tile staged
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // whole tile staged
     if (et == 0) {
       for (int r = 0; r < CS; ++r) {
         const int n_r = max(0, min(tok_per, p.T - r * tok_per));
@@ -276,43 +235,81 @@ gemm_dk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     // ---- phase 2: the peers' partials for this rank's tokens, and this rank's own preloads
     cp_async_wait_all();
+    if (et == 0) dk_stamp(p, 12);
     if (ntok > 0) mbar_wait(recv_bar, 0);
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // (cp.async data of the other epilogue threads)
+    if (et == 0) dk_stamp(p, 13);
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // (cp.async data of the other epilogue threads)
     if (et == 0) dk_stamp(p, 5);
     // ---- phase 3: finish this rank's tokens: partials added in rank order (deterministic)
     // (token loops are rolled and the rank loop is a plain strided walk: the first cut spent ~230 instructions per
     //  token here, 3.7 us for 16 tokens on four single-warp schedulers)
     const uint32_t slot_bytes = (uint32_t)(tok_per * kBlockM) * 4u;  // bytes between the slots of two sender ranks
-    // partial sums of one (token, feature): all CS loads are issued before the first add (predicated, unrolled to the
-    // largest cluster), then added in rank order
-    auto rank_sum = [&](uint32_t a) {
-      float v[kDkMaxCluster];
+    // The token loops are instantiated per cluster size (dispatch OUTSIDE the loop): with a run-time rank loop the body
+    // was ~70 instructions per token on a single-warp scheduler (290 cycles per token measured); straight-line it is ~25.
+    auto finalize = [&](auto cs_tag) {
+      constexpr int kCS = decltype(cs_tag)::value;  // 0 = generic (run-time CS)
+      auto rank_sum = [&](uint32_t a) {
+        if constexpr (kCS == 0) {
+          float v[kDkMaxCluster];
 #pragma unroll
-      for (int r = 0; r < kDkMaxCluster; ++r) v[r] = r < CS ? lds_f32(a + (uint32_t)r * slot_bytes) : 0.f;
-      float s = v[0];
+          for (int r = 0; r < kDkMaxCluster; ++r) v[r] = r < CS ? lds_f32(a + (uint32_t)r * slot_bytes) : 0.f;
+          float s = v[0];
 #pragma unroll
-      for (int r = 1; r < kDkMaxCluster; ++r) s += v[r];
-      return s;
-    };
-    if constexpr (EPI == DK_RESID) {
-      float* hp = p.h + (size_t)t0 * p.ldh + f;
-      __nv_bfloat16* xp = p.xg + (size_t)t0 * p.ldx + f;
-      uint32_t ra = smem_u32(recv) + (uint32_t)row * 4u, pa = smem_u32(pre) + (uint32_t)row * 4u;
-#pragma unroll 2
-      for (int i = 0; i < ntok; ++i) {
-        const float s = rank_sum(ra);
-        const float hv = frow ? lds_f32(pa) + s : 0.f;
-        if (frow) {
-          *hp = hv;
-          *xp = __float2bfloat16(hv * gm);
+          for (int r = 1; r < kDkMaxCluster; ++r) s += v[r];
+          return s;
+        } else {
+          float v[kCS];
+#pragma unroll
+          for (int r = 0; r < kCS; ++r) v[r] = lds_f32(a + (uint32_t)r * slot_bytes);  // all loads before the first add
+          float s = v[0];
+#pragma unroll
+          for (int r = 1; r < kCS; ++r) s += v[r];                                     // rank order: deterministic
+          return s;
         }
-        sts_f32(pa, hv * hv);
-        ra += kBlockM * 4; pa += kBlockM * 4; hp += p.ldh; xp += p.ldx;
+      };
+      {
+        float* hp = p.h + (size_t)(t0 + hid) * p.ldh + f;
+        __nv_bfloat16* xp = p.xg + (size_t)(t0 + hid) * p.ldx + f;
+        const size_t hstep = 2 * (size_t)p.ldh, xstep = 2 * (size_t)p.ldx;
+        uint32_t ra = smem_u32(recv) + (uint32_t)(hid * kBlockM + row) * 4u, pa = smem_u32(pre) + (uint32_t)(hid * kBlockM + row) * 4u;
+        // batches of 4 tokens: every shared-memory load of a batch is issued before its first use (the loads are volatile
+        // asm, i.e. kept in program order - token by token they formed one dependent chain per token)
+        for (int i0 = hid; i0 < ntok; i0 += 8) {
+          float sv[4], pv[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const bool ok = i0 + 2 * b < ntok;
+            sv[b] = ok ? rank_sum(ra + (uint32_t)b * (2 * kBlockM * 4)) : 0.f;
+            pv[b] = ok ? lds_f32(pa + (uint32_t)b * (2 * kBlockM * 4)) : 0.f;
+          }
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            if (i0 + 2 * b < ntok) {
+              const float hv = frow ? pv[b] + sv[b] : 0.f;
+              if (frow) {
+                hp[(size_t)b * hstep] = hv;
+                xp[(size_t)b * xstep] = __float2bfloat16(hv * gm);
+              }
+              sts_f32(pa + (uint32_t)b * (2 * kBlockM * 4), hv * hv);
+            }
+          }
+          ra += 4 * 2 * kBlockM * 4; pa += 4 * 2 * kBlockM * 4; hp += 4 * hstep; xp += 4 * xstep;
+        }
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+    };
+    switch (CS) {
+      case 1: finalize(std::integral_constant<int, 1>{}); break;
+      case 2: finalize(std::integral_constant<int, 2>{}); break;
+      case 3: finalize(std::integral_constant<int, 3>{}); break;
+      case 4: finalize(std::integral_constant<int, 4>{}); break;
+      default: finalize(std::integral_constant<int, 0>{}); break;
+    }
+    {
+      if (et == 0) dk_stamp(p, 10);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       // sum of squares per token: 4 threads per token, 32 features each (rotated start: conflict-free), fixed order
       // (all lanes run the shuffles: ntok need not be a multiple of the 8 tokens a warp covers)
-      const int ti = et >> 2, part = et & 3;
+      const int ti = et >> 2, part = et & 3;  // (ti >= 32 >= ntok for the second half of the threads)
       float ss = 0.f;
       if (ti < ntok) {
         const uint32_t base = smem_u32(pre) + (uint32_t)(ti * kBlockM + part * 32) * 4u;
@@ -322,26 +319,6 @@ gemm_dk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ss += __shfl_xor_sync(0xffffffffu, ss, 1);
       ss += __shfl_xor_sync(0xffffffffu, ss, 2);
       if (ti < ntok && part == 0) p.ssq_out[(size_t)tile_m * p.ssq_stride + t0 + ti] = ss;
-    } else {
-      const int prow = row < half ? row + half : row - half;  // rotate-half partner feature, same tile
-      const float sgn = row < half ? -1.f : 1.f;
-      const bool rot = head < p.n_q + p.n_kv;                 // v heads: copy
-      __nv_bfloat16* dst = (head < p.n_q ? p.q_out : (head < p.n_q + p.n_kv ? p.k_cache : p.v_cache)) + row;
-      uint32_t ra = smem_u32(recv) + (uint32_t)row * 4u, ra2 = smem_u32(recv) + (uint32_t)(prow < R ? prow : row) * 4u;
-      uint32_t ca = smem_u32(pre) + (uint32_t)(row < half ? row : row - half) * 8u;
-      const uint32_t rsa = smem_u32(rstd_s), dsa = smem_u32(dst_s);
-      if (frow) {
-#pragma unroll 2
-        for (int i = 0; i < ntok; ++i) {
-          const float s = rank_sum(ra), s2 = rank_sum(ra2);
-          const float rs = lds_f32(rsa + (uint32_t)i * 4u);
-          const float a = s * rs + bs, b = s2 * rs + bs2;
-          const float2 cs = rot ? lds_f32x2(ca) : make_float2(1.f, 0.f);
-          // lo' = lo cos - hi sin;  hi' = hi cos + lo sin   (v heads: cos = 1, sin = 0)
-          dst[lds_u32(dsa + (uint32_t)i * 4u)] = __float2bfloat16(a * cs.x + sgn * b * cs.y);
-          ra += kBlockM * 4; ra2 += kBlockM * 4; ca += (uint32_t)half * 8u;
-        }
-      }
     }
     if (et == 0) dk_stamp(p, 6);
   }

@@ -54,17 +54,17 @@ int gemm_balanced_rows(int n_out);
 // RMSNorm fold: scale token column t of the result by rstd[t] (GemmParams::rs / StreamKParams::rs).
 void gemm_plan_set_rstd(GemmPlan* g, const RstdIn& rs);
 
-// ---- decode chain (gemm_dk.cuh): cluster split-K GEMM with fused residual / RoPE epilogues
+// ---- decode chain (gemm_dk.cuh): cluster split-K GEMM with the residual add / next-norm partials fused
 struct DkPlan {
   CUtensorMap tmA;  // weights [w_rows, K], box {64, tile_rows}
   CUtensorMap tmB;  // activations [x_rows, K], box {64, bn}
   DkParams p;       // the caller fills the epilogue fields after dk_plan()
-  int bn, epi, cs, m_tiles;
+  int bn, cs, m_tiles;
 };
 int dk_max_clusters(int cs);                          // co-resident clusters of `cs` CTAs on this device (occupancy query)
 int dk_pick_cluster(int m_tiles, int k_blocks, int T);  // 0 = shape not servable
 // cs <= 0: pick.  false: shape not servable by the chain kernel (T > 64, too many tiles, ...)
-bool dk_plan(DkPlan* g, int epi, const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T,
+bool dk_plan(DkPlan* g, const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T,
              int tile_rows, int cs);
 cudaError_t dk_launch(const DkPlan& g, const LaunchCfg& lc);
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc);

@@ -281,7 +281,7 @@ gemm_streamk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)c0 * p.ldo + f;
 #pragma unroll
               for (int j = 0; j < 16; ++j)
-                if (c0 + j < p.T) o[(size_t)j * p.ldo] = __float2bfloat16(v[j] / (1.0f + __expf(-v[j])) * u[j]);
+                if (c0 + j < p.T) o[(size_t)j * p.ldo] = __float2bfloat16(__fdividef(v[j], 1.0f + __expf(-v[j])) * u[j]);
             } else if constexpr (EPI == EPI_F32) {
               float* o = reinterpret_cast<float*>(p.out) + (size_t)c0 * p.ldo + f;
 #pragma unroll

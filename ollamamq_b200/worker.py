@@ -319,6 +319,11 @@ class Dispatcher:
     def add_boost(self, user):
         check(lib.mq_dispatcher_add_boost(self._h, user.encode()))
 
+    def control(self, action: str, user: Optional[str] = None, ip: Optional[str] = None):
+        """The dashboard's control keys as one atomic call (tui.rs:126-237): see mq_dispatcher_control."""
+        check(lib.mq_dispatcher_control(self._h, action.encode(), user.encode() if user is not None else None,
+                                        ip.encode() if ip is not None else None))
+
     def block_user(self, user, blocked=True):
         check(lib.mq_dispatcher_block_user(self._h, user.encode(), 1 if blocked else 0))
 
@@ -349,6 +354,9 @@ class Dispatcher:
 
     def mock_complete(self, backend, rc=0) -> bool:
         return check(lib.mq_dispatcher_mock_complete(self._h, backend, rc)) == 1
+
+    def mock_set_healthy(self, backend, healthy=True):
+        check(lib.mq_dispatcher_mock_set_healthy(self._h, backend, 1 if healthy else 0))
 
     def mock_fail_next(self, backend, n=1):
         check(lib.mq_dispatcher_mock_fail_next(self._h, backend, n))

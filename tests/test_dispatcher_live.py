@@ -210,3 +210,54 @@ def test_health_prober_keeps_mock_backends_online():
         assert d.backend_stats(1)["is_online"]
     finally:
         d.close()
+
+
+def test_health_prober_takes_a_backend_offline_and_recovery_does_not_wake_the_scheduler():
+    """dispatcher.rs:171-193 with a backend that stops answering the probe: is_online flips, NEW work skips it (:201-209),
+    what it has in flight still completes and is accounted (:314-341), and when it answers again the flag flips back but
+    nobody notifies the scheduler (the prober never calls notify): queued work moves only at the next natural wake-up."""
+    import time
+    d = mq.Dispatcher(mock_backends=2, capacity=1)
+    try:
+        d.start_health(10)
+        a = d.submit("alice", max_new_tokens=1)                # -> backend 1 (first dispatch, :248-254)
+        b = d.submit("bob", max_new_tokens=1)                  # -> backend 0
+        d.wait_parked()
+        assert sorted(x[2] for x in d.log()) == [0, 1]
+        d.mock_set_healthy(0, False)                           # backend 0's /api/tags stops answering
+        for _ in range(200):
+            if not d.backend_stats(0)["is_online"]:
+                break
+            time.sleep(0.005)
+        assert not d.backend_stats(0)["is_online"] and d.backend_stats(1)["is_online"]
+        assert d.mock_complete(0)                              # its in-flight request still completes ...
+        d.wait_parked()
+        assert d.user_stats("bob")["processed"] == 1           # ... and is counted
+        assert d.backend_stats(0)["active_requests"] == 0
+        c = d.submit("carol", max_new_tokens=1)                # backend 1 busy, backend 0 offline: stays queued
+        d.wait_parked()
+        assert d.user_stats("carol")["queued"] == 1 and len(d.log()) == 2
+        assert d.mock_complete(1)                              # backend 1 frees -> carol goes THERE, not to 0
+        d.wait_parked()
+        assert d.log()[-1] == ("carol", 0, 1)
+        e = d.submit("erin", max_new_tokens=1)                 # every eligible backend busy / offline
+        d.wait_parked()
+        assert d.user_stats("erin")["queued"] == 1
+        d.mock_set_healthy(0, True)                            # backend 0 answers again
+        for _ in range(200):
+            if d.backend_stats(0)["is_online"]:
+                break
+            time.sleep(0.005)
+        assert d.backend_stats(0)["is_online"]
+        time.sleep(0.1)
+        assert d.user_stats("erin")["queued"] == 1             # recovery did not wake run_worker (:181-191 has no notify)
+        f = d.submit("frank", max_new_tokens=1)                # the next notify does; who goes first is the positional
+        d.wait_parked()                                        # round-robin's business (:236-240), where is not: backend 0
+        assert d.log()[-1][2] == 0 and d.log()[-1][0] in ("erin", "frank") and len(d.log()) == 4
+        while d.mock_complete(0) or d.mock_complete(1):
+            d.wait_parked()
+        d.drain(5000)
+        for s in (a, b, c, e, f):
+            assert s.rc == 0
+    finally:
+        d.close()

@@ -160,3 +160,121 @@ def test_malformed_requests_do_not_take_the_server_down(srv):
     assert st == 200 and body == b"OK"
     st, _, _ = srv.request("POST", "/api/chat", body=b'{"model":"m","messages":[]}', headers={"X-User-ID": "after-fuzz"})
     assert st == 200
+
+
+def _admin(srv, path, obj=None, method="POST"):
+    st, _, body = srv.request(method, path, json.dumps(obj).encode() if obj is not None else None,
+                              {"Content-Type": "application/json"})
+    return st, body
+
+
+def test_admin_control_surface_has_the_dashboard_key_semantics(srv):
+    """Headless control path: POST /admin/{vip,boost,block,unblock} = the p / b / x / X / u keys of
+    tui.rs:126-237 - VIP and Boost toggle, setting one clears the other when it names the same user; GET /admin/state is
+    the dashboard snapshot.  With one VIP / one Boost the scheduler is exactly the reference's."""
+    for u in ("alice", "bob"):                                        # users appear once they have sent something
+        assert srv.request("POST", "/api/chat", b"{}", {"X-User-ID": u})[0] == 200
+    state = lambda: json.loads(_admin(srv, "/admin/state", method="GET")[1])
+    assert state()["vip"] == [] and [u["id"] for u in state()["users"]] == ["alice", "bob"]
+    assert _admin(srv, "/admin/vip", {"user": "alice"})[0] == 200
+    assert state()["vip"] == ["alice"]
+    assert _admin(srv, "/admin/boost", {"user": "alice"})[0] == 200   # 'b' on the VIP user: Boost set, VIP cleared
+    assert state()["vip"] == [] and state()["boost"] == ["alice"]
+    assert _admin(srv, "/admin/vip", {"user": "bob"})[0] == 200
+    assert _admin(srv, "/admin/vip", {"user": "alice"})[0] == 200     # one VIP slot: replaces bob; clears alice's Boost
+    assert state()["vip"] == ["alice"] and state()["boost"] == []
+    assert _admin(srv, "/admin/vip", {"user": "alice"})[0] == 200     # 'p' again: toggled off
+    assert state()["vip"] == []
+    # extension (BASELINE config 3): sets
+    assert _admin(srv, "/admin/vip", {"user": "alice", "mode": "add"})[0] == 200
+    assert _admin(srv, "/admin/vip", {"user": "bob", "mode": "add"})[0] == 200
+    assert sorted(state()["vip"]) == ["alice", "bob"]
+    assert _admin(srv, "/admin/vip", {"mode": "clear"})[0] == 200 and state()["vip"] == []
+    # block / unblock: 'x' blocks the user, 'X' its last address, 'u' lifts both
+    assert _admin(srv, "/admin/block", {"user": "bob"})[0] == 200
+    assert srv.request("POST", "/api/chat", b"{}", {"X-User-ID": "bob"})[:1] == (403,)
+    assert state()["blocked_users"] == ["bob"]
+    assert _admin(srv, "/admin/block", {"user": "alice", "mode": "ip"})[0] == 200
+    assert state()["blocked_ips"] == ["127.0.0.1"]
+    assert srv.request("POST", "/api/chat", b"{}", {"X-User-ID": "carol"})[2] == b"IP blocked"
+    assert _admin(srv, "/admin/unblock", {"user": "alice"})[0] == 200 # admin routes are not behind the block list
+    assert state()["blocked_ips"] == []
+    assert _admin(srv, "/admin/unblock", {"user": "bob"})[0] == 200 and state()["blocked_users"] == []
+    assert srv.request("POST", "/api/chat", b"{}", {"X-User-ID": "bob"})[0] == 200
+    assert _admin(srv, "/admin/block", {"ip": "10.1.2.3"})[0] == 200 and state()["blocked_ips"] == ["10.1.2.3"]
+    assert _admin(srv, "/admin/unblock", {"ip": "10.1.2.3"})[0] == 200 and state()["blocked_ips"] == []
+    # errors
+    assert _admin(srv, "/admin/vip", {})[0] == 400 and _admin(srv, "/admin/nope", {"user": "a"})[0] == 404
+    assert srv.request("GET", "/admin/vip")[0] == 405
+
+
+def test_vip_set_over_http_changes_dispatch_order_like_the_reference():
+    """config 1 with vip = charlie set through the admin route: the dispatch log equals the oracle's."""
+    from oracle.dispatch_oracle import OracleC, simulate
+    s = Served(backends=2, auto=False)
+    try:
+        users = ["alice", "bob", "charlie", "david"]
+        for b in range(2):
+            s.d.set_online(b, False)                                  # queue everything first (the t=0 arrival trace)
+        assert _admin(s, "/admin/vip", {"user": "charlie"})[0] == 200
+        streams = [s.d.submit(u, max_new_tokens=1) for u in users for _ in range(8)]
+        for b in range(2):
+            s.d.set_online(b, True)
+        s.d.submit("zz-wake", max_new_tokens=1)                       # a notify wakes the scheduler (recovery does not)
+        s.d.wait_parked()
+        for _ in range(200):
+            progressed = False
+            for b in range(2):                                        # completions ordered by backend index, one per event
+                if s.d.mock_complete(b):
+                    progressed = True
+                    s.d.wait_parked()
+            if not progressed:
+                break
+        s.d.drain(5000)
+        got = [(u, seq, b) for u, seq, b in s.d.log() if u != "zz-wake"]
+        arr = [(0, u) for u in users for _ in range(8)]
+        ref = [r for r in simulate(OracleC(2), arr + [(0, "zz-wake")], lambda u, q, b: 1, vip="charlie") if r[0] != "zz-wake"]
+        assert [g[0] for g in got][:8] == ["charlie"] * 8             # VIP absolute priority (:230)
+        assert sorted(got) == sorted(ref)
+    finally:
+        s.close()
+
+
+def test_a_thousand_connections_on_one_loop():
+    """1 024 simultaneous keep-alive connections, every one with a request in flight, then answered: the epoll loop holds
+    them all (round 1 ran a thread per connection), and stop() joins it with requests still open."""
+    s = Served(backends=4, auto=False)
+    N = 1024
+    try:
+        socks = []
+        for i in range(N):
+            sk = socket.create_connection(("127.0.0.1", s.port), timeout=20)
+            body = b'{"prompt":"hello %d"}' % i
+            sk.sendall(b"POST /api/generate HTTP/1.1\r\nHost: x\r\nX-User-ID: u%03d\r\nContent-Length: %d\r\n\r\n" % (i % 100, len(body)) + body)
+            socks.append(sk)
+        deadline = time.time() + 20
+        while time.time() < deadline:
+            snap = s.d.snapshot()
+            if sum(u["queued"] + u["processing"] for u in snap["users"]) == N:
+                break
+            time.sleep(0.02)
+        assert sum(u["queued"] + u["processing"] for u in s.d.snapshot()["users"]) == N
+        s.auto = True                                                 # now let the mock backends answer
+        got = 0
+        for sk in socks:
+            data = b""
+            while b"0\r\n\r\n" not in data:
+                chunk = sk.recv(65536)
+                assert chunk, "connection closed before the response ended"
+                data += chunk
+            assert data.startswith(b"HTTP/1.1 200 OK") and b'{"tok":0}' in data
+            got += 1
+        assert got == N
+        # second request on every 8th connection: still alive after the burst
+        for sk in socks[::8]:
+            sk.sendall(b"GET /health HTTP/1.1\r\nHost: x\r\n\r\n")
+            assert sk.recv(4096).startswith(b"HTTP/1.1 200 OK")
+        for sk in socks:
+            sk.close()
+    finally:
+        s.close()
