@@ -1,6 +1,7 @@
 // Host side of the tcgen05 GEMM: TMA descriptor construction + template dispatch.
 #include "gemm_host.cuh"
 #include <cudaTypedefs.h>
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <mutex>
@@ -129,7 +130,7 @@ static cudaError_t launch_pk(const GemmPlan& g, const LaunchCfg& lc) {
 template <int EPI>
 static cudaError_t launch_c2(const GemmPlan& g, const LaunchCfg& lc) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * g.c2.m_tiles * g.c2.n_tiles);  // cluster dims (2,1,1) are compiled into the kernel
+  cfg.gridDim = dim3(2 * g.c2.n_pairs);  // persistent pairs; cluster dims (2,1,1) are compiled into the kernel
   cfg.blockDim = dim3(kC2Threads);
   cfg.dynamicSmemBytes = c2_smem_bytes(EPI);
   cfg.stream = lc.stream;
@@ -138,7 +139,7 @@ static cudaError_t launch_c2(const GemmPlan& g, const LaunchCfg& lc) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = lc.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gemm_2cta_kernel<EPI>, g.tmA, g.tmB, g.tmC, g.c2);
+  return cudaLaunchKernelEx(&cfg, gemm_2cta_kernel<EPI>, g.tmA, g.tmB, g.c2);
 }
 
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
@@ -297,6 +298,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   // one token tile, no split-K and fewer weight tiles than half the SMs (Phi-3 gate/up at 256 slots: 64 tiles): halve
   // the token tile so two CTAs share each weight tile through L2 - same HBM bytes, twice the SMs streaming them
   if (T > 128 && T <= 256 && splits == 1 && (n_out + kBlockM - 1) / kBlockM * 2 <= device_sm_count()) g->bn = 128;
+  g->epi = epi;
   g->splits = splits;
   // tile_rows < 128 only for the plain decode-width kernel (one token tile): see GemmParams::tile_rows
   if (tile_rows <= 0 || tile_rows > kBlockM || tile_rows % 8 != 0 || g->streamk || T > g->bn) tile_rows = kBlockM;
@@ -325,14 +327,21 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   g->p.w_policy = g->p.n_tiles == 1 ? kEvictFirst : kEvictNormal;  // decode streams weights exactly once
   g->twocta = !g->streamk && tile_rows == kBlockM && g->bn == 256 && splits == 1 && n_out % 256 == 0 && epi != EPI_GELU_BF16 && epi != EPI_BIAS_BF16 && twocta_enabled();
   if (g->twocta) {
-    // the pair computes 256 features x 256 tokens: every CTA stages only its own 128-token half of the activation tile
-    if (!tmap_encode_2d(&g->tmB, X, (uint64_t)x_rows_alloc, (uint64_t)K, 128)) return false;
+    // the pair computes 256 features x c2_bn tokens: every CTA stages only its own half of the activation tile
+    const int bn2 = c2_bn(epi);
+    if (!tmap_encode_2d(&g->tmB, X, (uint64_t)x_rows_alloc, (uint64_t)K, (uint32_t)(bn2 / 2))) return false;
+    g->c2.out = out; g->c2.ldo = ldo;
     g->c2.T = T; g->c2.n_out = n_out; g->c2.k_blocks = kb; g->c2.a2_row_off = a2_row_off;
     g->c2.m_tiles = n_out / 256;
-    g->c2.n_tiles = (T + 255) / 256;
-    int gm2 = (int)(sqrt(74.0 * 256.0 / (epi == EPI_SILU_BF16 ? 512.0 : 256.0)) + 0.5);
+    g->c2.n_tiles = (T + bn2 - 1) / bn2;
+    const int pairs = device_sm_count() / 2;
+    int gm2 = (int)(sqrt((double)pairs * bn2 / (epi == EPI_SILU_BF16 ? 512.0 : 256.0)) + 0.5);
     if (gm2 > g->c2.m_tiles) gm2 = g->c2.m_tiles;
     g->c2.group_m = gm2 < 1 ? 1 : gm2;
+    g->c2.n_pairs = std::min(pairs, g->c2.m_tiles * g->c2.n_tiles);
+    if (const char* e = getenv("MQ_C2_PERSIST")) {  // A/B: 0 = one tile per CTA pair (the round-1 grid shape)
+      if (e[0] == '0') g->c2.n_pairs = g->c2.m_tiles * g->c2.n_tiles;
+    }
     g->c2.w_policy = g->p.w_policy;
   }
   g->persist = false;

@@ -14,19 +14,38 @@
 //   * the leader's MMA thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256) and releases a stage with a
 //     multicast tcgen05.commit that arrives on the empty barrier of BOTH CTAs; the final commit arrives on both
 //     tmem_full barriers;
-//   * each CTA drains its own 128 TMEM lanes (its half of the features) and TMA-stores its half tile.
+//   * each CTA drains its own 128 TMEM lanes (its half of the features).
+//
+// Round 2: PERSISTENT, two TMEM accumulator buffers.  r01's ncu showed the tensor pipe 61-67 % active: every 256x256
+// tile paid its pipeline fill and its epilogue (TMEM -> registers -> smem -> TMA store) un-overlapped, 3.9 waves per
+// GEMM with a ragged last one.  Now one CTA pair per SM pair walks tiles pair, pair + P, ...: the producers keep the
+// TMA ring full across tile boundaries, the MMA thread flips between two accumulator buffers (2 x 256 TMEM columns;
+// the dual SiLU epilogue uses 128-token tiles so that gate + up of both buffers fit the 512 columns), and the eight
+// epilogue warps drain buffer b (straight from registers to global memory - no staging tile, so the ring keeps its
+// depth) while the tensor cores fill buffer b ^ 1.  tmem_empty[b] (count 2: one arrive per CTA of the pair, the
+// peer's through mapa) tells the leader's MMA thread that both halves of buffer b have been read.
 #pragma once
 #include "gemm.cuh"
 
 namespace mq {
 
 struct TwoCtaParams {
+  void* out;       // [T][ldo] bf16 (EPI_BF16 / EPI_SILU_BF16) or fp32 (EPI_F32)
+  int ldo;
   int T, n_out, k_blocks, a2_row_off;
-  int m_tiles, n_tiles, group_m;  // tiles of 256 features x 256 tokens
+  int m_tiles, n_tiles, group_m;  // tiles of 256 features x c2_bn(epi) tokens
+  int n_pairs;                    // persistent CTA pairs launched
   unsigned long long w_policy;
 };
 
-__host__ __device__ constexpr int c2_stage_bytes(int epi) { return kATileBytes * (epi == EPI_SILU_BF16 ? 2 : 1) + 128 * kBlockK * 2; }
+// token columns per tile.  The dual SiLU epilogue keeps 256 too: gate + up then fill all 512 TMEM columns, i.e. ONE
+// accumulator buffer (no MMA / epilogue overlap) - a 128-token tile would double-buffer but reads 12 KB of operands per
+// MFLOP from shared memory instead of 8 and is bound by that (measured: prefill 432 -> 459 ms).
+__host__ __device__ constexpr int c2_bn(int epi) { return 256; }
+__host__ __device__ constexpr int c2_nbuf(int epi) { return epi == EPI_SILU_BF16 ? 1 : 2; }
+__host__ __device__ constexpr int c2_stage_bytes(int epi) {
+  return kATileBytes * (epi == EPI_SILU_BF16 ? 2 : 1) + (c2_bn(epi) / 2) * kBlockK * 2;  // own weight rows + own half of the tokens
+}
 __host__ __device__ constexpr int c2_stages(int epi) {
   int s = (200 * 1024) / c2_stage_bytes(epi);
   return s > 8 ? 8 : s;
@@ -88,52 +107,53 @@ constexpr int kC2Threads = 64 + 256;  // producer warp, MMA warp, 8 epilogue war
 
 template <int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC2Threads, 1)
-gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const TwoCtaParams p) {
+gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TwoCtaParams p) {
   constexpr bool kDual = (EPI == EPI_SILU_BF16);
-  constexpr int BN = 256;                       // token columns of the pair's accumulator
+  constexpr int BN = c2_bn(EPI);                // token columns of the pair's accumulator
   constexpr int STAGES = c2_stages(EPI);
   constexpr int STAGE_BYTES = c2_stage_bytes(EPI);
   constexpr int B_OFF = kATileBytes * (kDual ? 2 : 1);
-  constexpr uint32_t TMEM_COLS = kDual ? 512u : 256u;
+  constexpr int ACC_COLS = BN * (kDual ? 2 : 1);  // TMEM columns of one accumulator buffer
+  constexpr int NBUF = c2_nbuf(EPI);              // 2: the epilogue of tile i overlaps the MMAs of tile i + 1
+  constexpr uint32_t TMEM_COLS = 512u;
   constexpr uint32_t IDESC = umma_idesc_bf16(256, BN);
-  static_assert(gemm_out_tile_bytes(BN, EPI) <= STAGES * STAGE_BYTES, "epilogue tile is staged in the pipeline smem");
+  static_assert(NBUF * ACC_COLS <= 512, "the accumulator buffers must fit TMEM");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // used in the leader only
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator buffer complete (multicast commit: both CTAs)
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2] used in the leader only: both CTAs have drained the buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader_cta = rank == 0;
-  int tile_m, tile_n;
-  {
-    const int pid = blockIdx.x >> 1;
-    const int per_group = p.group_m * p.n_tiles;
-    const int first_m = (pid / per_group) * p.group_m;
-    const int gsz = min(p.m_tiles - first_m, p.group_m);
-    const int r = pid % per_group;
-    tile_m = first_m + r % gsz;
-    tile_n = r / gsz;
-  }
-  const int m0 = tile_m * 256 + (int)rank * kBlockM;  // my 128 weight rows
-  const int n0 = tile_n * BN;                         // the pair's 256 tokens
-  const int nb0 = n0 + (int)rank * 128;               // my half of the token tile
+  const int pair = blockIdx.x >> 1;
+  const int n_tiles_total = p.m_tiles * p.n_tiles;
   const int nkb = p.k_blocks;
+  auto tile_of = [&](int t, int* tile_m, int* tile_n) {  // grouped rasterisation (see gemm.cuh)
+    const int per_group = p.group_m * p.n_tiles;
+    const int first_m = (t / per_group) * p.group_m;
+    const int gsz = min(p.m_tiles - first_m, p.group_m);
+    const int r = t % per_group;
+    *tile_m = first_m + r % gsz;
+    *tile_n = r / gsz;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    tma_prefetch_desc(&tmC);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx + the peer producer's remote arrive
       mbar_init(&empty_bar[s], 1);  // multicast commit from the leader's MMA thread
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 2);
+    }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(tmem_slot);
@@ -145,98 +165,120 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   if (warp == 0) {
     if (lane == 0) {
-      // ---------------- TMA producer (both CTAs): own weight rows + own half of the token tile ----------------
-      auto arm = [&](int s) {
+      // ---------------- TMA producer (both CTAs): own weight rows + own half of the token tile, all tiles ----------------
+      const int my_tiles = pair < n_tiles_total ? (n_tiles_total - pair + p.n_pairs - 1) / p.n_pairs : 0;
+      const int total = my_tiles * nkb;  // k-blocks this producer issues (ring position = it)
+      auto coords = [&](int it, int* kb, int* m0, int* nb0) {
+        int tile_m, tile_n;
+        tile_of(pair + (it / nkb) * p.n_pairs, &tile_m, &tile_n);
+        *kb = it % nkb;
+        *m0 = tile_m * 256 + (int)rank * kBlockM;   // my 128 weight rows
+        *nb0 = tile_n * BN + (int)rank * (BN / 2);  // my half of the token tile
+      };
+      auto load_a = [&](int it) {
+        int kb, m0, nb0;
+        coords(it, &kb, &m0, &nb0);
+        const int s = it % STAGES;
         if (leader_cta) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);
         else mbar_arrive_remote(&full_bar[s], 0);
-      };
-      auto load_a = [&](int s, int kb) {
         uint8_t* st = smem + s * STAGE_BYTES;
         tma_load_2d_2cta(st, &tmA, &full_bar[s], kb * kBlockK, m0, p.w_policy);
         if (kDual) tma_load_2d_2cta(st + kATileBytes, &tmA, &full_bar[s], kb * kBlockK, m0 + p.a2_row_off, p.w_policy);
       };
-      const int npre = nkb < STAGES ? nkb : STAGES;
-      for (int s = 0; s < npre; ++s) {
-        arm(s);
-        load_a(s, s);
-      }
-      pdl_wait();  // activations are produced by the previous kernel
-      for (int s = 0; s < npre; ++s)
-        tma_load_2d_2cta(smem + s * STAGE_BYTES + B_OFF, &tmB, &full_bar[s], s * kBlockK, nb0, kEvictLast);
-      for (int kb = npre; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        arm(s);
-        load_a(s, kb);
-        tma_load_2d_2cta(smem + s * STAGE_BYTES + B_OFF, &tmB, &full_bar[s], kb * kBlockK, nb0, kEvictLast);
+      auto load_b = [&](int it) {
+        int kb, m0, nb0;
+        coords(it, &kb, &m0, &nb0);
+        tma_load_2d_2cta(smem + (it % STAGES) * STAGE_BYTES + B_OFF, &tmB, &full_bar[it % STAGES], kb * kBlockK, nb0, kEvictLast);
+      };
+      const int npre = total < STAGES ? total : STAGES;
+      for (int it = 0; it < npre; ++it) load_a(it);  // weights of the first ring pass: no dependency on the previous kernel
+      pdl_wait();                                    // activations are produced by the previous kernel
+      for (int it = 0; it < npre; ++it) load_b(it);
+      for (int it = npre; it < total; ++it) {
+        mbar_wait(&empty_bar[it % STAGES], ((it / STAGES) & 1) ^ 1);
+        load_a(it);
+        load_b(it);
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && leader_cta) {
-      // ---------------- MMA issuer: leader CTA only, one thread for the pair ----------------
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      // ---------------- MMA issuer: leader CTA only; tile i accumulates into buffer i & 1 ----------------
+      int it = 0, i = 0;
+      for (int t = pair; t < n_tiles_total; t += p.n_pairs, ++i) {
+        const int buf = i % NBUF, use = i / NBUF;
+        mbar_wait(&tempty_bar[buf], (use & 1) ^ 1);  // both CTAs have drained this buffer (first use: passes at once)
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
-        const uint32_t b_addr = a_addr + B_OFF;
+        const uint32_t acc_base = tmem_base + (uint32_t)(buf * ACC_COLS);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + B_OFF;
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t db = umma_desc_sw128(b_addr + k * 32);
-          const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-          umma_bf16_2cta(tmem_base, umma_desc_sw128(a_addr + k * 32), db, IDESC, acc);
-          if (kDual) umma_bf16_2cta(tmem_base + BN, umma_desc_sw128(a_addr + kATileBytes + k * 32), db, IDESC, acc);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t db = umma_desc_sw128(b_addr + k * 32);
+            const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+            umma_bf16_2cta(acc_base, umma_desc_sw128(a_addr + k * 32), db, IDESC, acc);
+            if (kDual) umma_bf16_2cta(acc_base + BN, umma_desc_sw128(a_addr + kATileBytes + k * 32), db, IDESC, acc);
+          }
+          umma_commit_2cta(&empty_bar[s]);  // stage s reusable in BOTH CTAs once these MMAs retire
         }
-        umma_commit_2cta(&empty_bar[s]);  // stage s reusable in BOTH CTAs once these MMAs retire
+        umma_commit_2cta(&tfull_bar[buf]);  // accumulator buffer complete, in both CTAs
       }
-      umma_commit_2cta(tmem_full_bar);  // accumulators complete, in both CTAs
     }
   } else {
-    // ---------------- epilogue (both CTAs): my 128 TMEM lanes = my 128 features, 256 token columns ----------------
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int q = warp & 3;                 // TMEM lane quarter (warps w and w+4 share one)
-    const int chalf = (warp - 2) >> 2;      // which half of the 256 token columns this warp drains
+    // ---------------- epilogue (both CTAs): my 128 TMEM lanes = my 128 features; registers -> global ----------------
+    const int q = warp & 3;                 // TMEM lane quarter (warps w and w + 4 share one)
+    const int chalf = (warp - 2) >> 2;      // which half of the token columns this warp drains
     const int row = q * 32 + lane;
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    uint8_t* stg = smem;  // every MMA of the pair has retired: all stage buffers of this CTA are free
+    int i = 0;
+    for (int t = pair; t < n_tiles_total; t += p.n_pairs, ++i) {
+      int tile_m, tile_n;
+      tile_of(t, &tile_m, &tile_n);
+      const int f = tile_m * 256 + (int)rank * kBlockM + row;  // this thread's output feature
+      const int n0 = tile_n * BN;
+      const int buf = i % NBUF, use = i / NBUF;
+      mbar_wait(&tfull_bar[buf], use & 1);
+      tc_fence_after();
+      const uint32_t t_lane = tmem_base + (uint32_t)(buf * ACC_COLS) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 16) {
-      if (n0 + c0 >= p.T) break;
-      uint32_t v[16];
-      tmem_ld16(t_lane + c0, v);
-      if constexpr (kDual) {
-        uint32_t u[16];
-        tmem_ld16(t_lane + BN + c0, u);
-        tmem_ld_wait();
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(stg) + c0 * kBlockM + row;
+      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 16) {
+        if (n0 + c0 >= p.T) break;
+        uint32_t v[16];
+        tmem_ld16(t_lane + c0, v);
+        if constexpr (kDual) {
+          uint32_t u[16];
+          tmem_ld16(t_lane + BN + c0, u);
+          tmem_ld_wait();
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)(n0 + c0) * p.ldo + f;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float g = __uint_as_float(v[j]);
-          o[j * kBlockM] = __float2bfloat16(__fdividef(g, 1.0f + __expf(-g)) * __uint_as_float(u[j]));
-        }
-      } else {
-        tmem_ld_wait();
-        if constexpr (EPI == EPI_F32) {
-          float* o = reinterpret_cast<float*>(stg) + c0 * kBlockM + row;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) o[j * kBlockM] = __uint_as_float(v[j]);
+          for (int j = 0; j < 16; ++j) {
+            const float g = __uint_as_float(v[j]);
+            if (n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __float2bfloat16(__fdividef(g, 1.0f + __expf(-g)) * __uint_as_float(u[j]));
+          }
         } else {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(stg) + c0 * kBlockM + row;
+          tmem_ld_wait();
+          if constexpr (EPI == EPI_F32) {
+            float* o = reinterpret_cast<float*>(p.out) + (size_t)(n0 + c0) * p.ldo + f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) o[j * kBlockM] = __float2bfloat16(__uint_as_float(v[j]));
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __uint_as_float(v[j]);
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)(n0 + c0) * p.ldo + f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __float2bfloat16(__uint_as_float(v[j]));
+          }
         }
       }
-    }
-    fence_proxy_async();
-    asm volatile("bar.sync 1, 256;" ::: "memory");
-    if (warp == 2 && lane == 0) {
-      if constexpr (EPI == EPI_F32) tma_store_3d(&tmC, stg, m0, n0, 0);
-      else tma_store_2d(&tmC, stg, m0, n0);
-      tma_store_commit();
-      tma_store_wait_read();
+      // this CTA's half of buffer `buf` is in registers / on its way to memory: hand the buffer back to the MMA thread
+      tc_fence_before();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp == 2 && lane == 0) {
+        if (leader_cta) mbar_arrive(&tempty_bar[buf]);
+        else mbar_arrive_remote(&tempty_bar[buf], 0);
+      }
     }
   }
 

@@ -551,3 +551,68 @@ def test_eos_token_ends_generation_with_done_reason_stop():
         assert js["choices"][0]["finish_reason"] == "stop" and js["usage"]["completion_tokens"] == stop_at
         oc = wk.occupancy()
         assert oc["active_slots"] == 0 and oc["free_pages"] == oc["total_pages"]
+
+
+def test_health_path_on_a_real_worker_probe_failure_and_sticky_fault():
+    """dispatcher.rs:171-193 over a GPU worker.  (1) The probe stops answering (mq_debug_worker_set_probe_fail): the
+    prober flips is_online, new work is not dispatched to it, the request it has in flight still completes and is
+    counted, and when the probe answers again nobody wakes the scheduler - the queued request moves at the next notify.
+    (2) A sticky fault (what a CUDA error raises): requests on the worker end with an error value, the backend goes
+    offline and stays there."""
+    cfg = MID
+    w = R.make_weights(cfg, seed=31, device="cuda")
+    g = torch.Generator().manual_seed(2)
+    prompts = [torch.randint(0, cfg["vocab"], (n,), generator=g).tolist() for n in (40, 33, 21, 60)]
+    with _open(cfg, w, max_batch=4, use_pdl=1, use_graphs=1) as wk:
+        d = mq.Dispatcher([wk], capacity=4)
+        try:
+            d.start_health(10)
+            s1 = d.submit("alice", prompt_tokens=prompts[0], max_new_tokens=200)
+            for _ in range(500):                                   # in flight
+                if d.user_stats("alice")["processing"] == 1:
+                    break
+                time.sleep(0.002)
+            mq.check(mq.lib.mq_debug_worker_set_probe_fail(wk._h, 1))
+            for _ in range(500):
+                if not d.backend_stats(0)["is_online"]:
+                    break
+                time.sleep(0.005)
+            assert not d.backend_stats(0)["is_online"]
+            s2 = d.submit("bob", prompt_tokens=prompts[1], max_new_tokens=8)
+            s1.wait(120)
+            assert s1.rc == 0 and len(s1.tokens()) == 200          # in-flight work completes ...
+            _check_greedy(w, cfg, prompts[0], s1.tokens()[:16])
+            d.wait_parked()
+            assert d.user_stats("alice")["processed"] == 1         # ... and is accounted
+            assert d.user_stats("bob")["queued"] == 1              # offline backend: not dispatched (:201-209)
+            mq.check(mq.lib.mq_debug_worker_set_probe_fail(wk._h, 0))
+            for _ in range(500):
+                if d.backend_stats(0)["is_online"]:
+                    break
+                time.sleep(0.005)
+            assert d.backend_stats(0)["is_online"]
+            time.sleep(0.1)
+            assert d.user_stats("bob")["queued"] == 1              # recovery does not notify run_worker
+            s3 = d.submit("carol", prompt_tokens=prompts[2], max_new_tokens=8)   # the next notify does
+            for s in (s2, s3):
+                s.wait(120)
+                assert s.rc == 0 and len(s.tokens()) == 8
+            # (2) sticky fault with a request in flight
+            s4 = d.submit("dave", prompt_tokens=prompts[3], max_new_tokens=400)
+            for _ in range(500):
+                if d.user_stats("dave")["processing"] == 1:
+                    break
+                time.sleep(0.002)
+            mq.check(mq.lib.mq_debug_worker_inject_fault(wk._h, b"injected by the test"))
+            s4.wait(60)
+            assert len(s4.tokens()) < 400                          # cut short (a mid-stream upstream error ends the body, :310), no CPU fallback
+            for _ in range(500):
+                if not d.backend_stats(0)["is_online"]:
+                    break
+                time.sleep(0.005)
+            assert not d.backend_stats(0)["is_online"] and not wk.healthy()
+            s5 = d.submit("erin", prompt_tokens=prompts[1], max_new_tokens=4)
+            d.wait_parked()
+            assert d.user_stats("erin")["queued"] == 1             # nothing is dispatched to a faulted worker
+        finally:
+            d.close()
