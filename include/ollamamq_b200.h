@@ -366,6 +366,11 @@ int mq_debug_cluster_info(int* out8);
 int mq_debug_gemm_fold(const void* W, int w_rows, int n_out, int K, const void* X, int x_rows_alloc, int T, int epi,
                        void* out, int ldo, int a2_row_off, int tile_rows, int streamk, const float* ssq, int parts,
                        int stride, float inv_h, float eps, int reps, float* ms_out);
+/* the same epilogue on the persistent 2-CTA prefill kernel (T > 128, n_out % 256 == 0); ssq_in != NULL additionally
+ * scales the product by rstd[t] before it is added (not used by the engine: exercises the fold on this kernel)          */
+int mq_debug_gemm_resid_prefill(const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, float* h,
+                                const void* gamma_next, void* xg, float* ssq_out, int ssq_stride, const float* ssq_in, int parts,
+                                int stride_in, float inv_h, float eps, int reps, float* ms_out);
 /* h[t,f] += X[t,:] . W[f,:];  xg = bf16(h * gamma_next);  ssq_out[tile][t] = sum_f h^2 per 128-feature tile        */
 int mq_debug_gemm_dk_resid(const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, int cs, float* h,
                            const void* gamma_next, void* xg, float* ssq_out, int ssq_stride, int reps, float* ms_out);
@@ -378,6 +383,9 @@ int mq_debug_rope_kv(const void* qkv, int qkv_is_f32, int n_planes, long long pl
 int mq_debug_attn_prefill(const void* q, const void* k_cache, const void* v_cache, const int* block_table,
                           int max_pages, const int* tiles, int n_tiles, void* out, int n_q, int n_kv, int T,
                           float scale, int head_dim);
+/* prefill attention on tcgen05 (csrc/attn_tc.cu): head_dim 128; q is [q_rows][n_q * 128], the caches hold n_pages pages */
+int mq_debug_attn_prefill_tc(const void* q, int q_rows, const void* k_cache, const void* v_cache, int n_pages, const int* block_table,
+                             int max_pages, const int* tiles, int n_tiles, void* out, int n_q, int n_kv, float scale);
 int mq_debug_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* block_table,
                          int max_pages, const int* pos, void* out, float* part_o, float* part_ml, int* split_counter,
                          int n_q, int n_kv, int n_slots, int n_splits /* 1..8 grid-level KV splits, or -2 / -4 / -8 =

@@ -173,6 +173,8 @@ _sig("mq_debug_embed_chain", C.c_int, [P, P, P, C.c_int, C.c_int, P, P, P])
 _sig("mq_debug_cluster_info", C.c_int, [P])
 _sig("mq_debug_gemm_fold", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int,
                                       C.c_int, P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_float)])
+_sig("mq_debug_gemm_resid_prefill", C.c_int, [P, C.c_int, C.c_int, P, C.c_int, C.c_int, P, P, P, P, C.c_int, P, C.c_int, C.c_int,
+                                               C.c_float, C.c_float, C.c_int, C.POINTER(C.c_float)])
 _sig("mq_debug_gemm_dk_resid", C.c_int, [P, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, P, P, P, P, C.c_int, C.c_int,
                                           C.POINTER(C.c_float)])
 _sig("mq_debug_add_rmsnorm", C.c_int, [P, P, C.c_int, C.c_int, C.c_longlong, P, P, P, C.c_int, C.c_int, C.c_float])
@@ -180,6 +182,7 @@ _sig("mq_debug_rope_kv", C.c_int, [P, C.c_int, C.c_int, C.c_longlong, P, P, P, P
                                     C.c_int, C.c_int, C.c_int])
 _sig("mq_debug_attn_prefill", C.c_int, [P, P, P, P, C.c_int, P, C.c_int, P, C.c_int, C.c_int, C.c_int, C.c_float,
                                          C.c_int])
+_sig("mq_debug_attn_prefill_tc", C.c_int, [P, C.c_int, P, P, C.c_int, P, C.c_int, P, C.c_int, P, C.c_int, C.c_int, C.c_float])
 _sig("mq_debug_attn_decode", C.c_int, [P, P, P, P, C.c_int, P, P, P, P, P, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_float, C.c_int])
 _sig("mq_worker_get_occupancy", C.c_int, [P, P])

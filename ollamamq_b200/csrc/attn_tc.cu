@@ -1,0 +1,357 @@
+// Prefill attention on the 5th-generation tensor cores (tcgen05 + TMEM), head_dim 128.
+// Part of the forward pass that stands where the reference calls a remote backend (/root/reference/src/dispatcher.rs:287-290);
+// BASELINE.json north_star: "prefill as tcgen05 tensor-core GEMMs fed by TMA into shared memory".  Round 1 ran prefill
+// attention on the legacy mma.sync pipe (33 % tensor-active, 7.4 % of a prefill pass).
+//
+// One CTA per (query tile, kv head).  A query tile is 128 rows = 128/G tokens x the G query heads of the GQA group
+// (row = token * G + head), so K / V tiles are shared by the whole group.  Per 128-token KV tile j:
+//
+//   warp 0 (one thread)   TMA: the 8 pages of K and V of the tile, each page = one 16 x 128 block of the paged cache,
+//                         fetched as two {64 d, 16 token} boxes with the 128-byte swizzle -> [128 tokens][64 d] x 2
+//                         sub-tiles = the canonical K-major (K) / MN-major (V) UMMA operand layouts; Q once, as
+//                         {64 d, G heads, 128/G tokens} boxes of the [T][n_q][128] activation
+//   warp 1 (one thread)   S[j & 1] = Q . K_j^T          tcgen05.mma, A and B from shared memory, fp32 in TMEM
+//                         O_j      = P[j & 1] . V_j     tcgen05.mma, A = P from TENSOR MEMORY (bf16), B = V MN-major
+//   warps 2-5 (128 thr)   one query row per thread (TMEM lane = row: no shuffles anywhere): two passes over its 128
+//                         scores (row max, then p = exp2(s - m)), P written back into the S buffer's first 64 columns
+//                         as packed bf16 (tcgen05.st), then O_j is pulled out of TMEM and folded into the fp32
+//                         accumulator in registers: o = o * exp2(m_old - m_new) + O_j
+//
+// S / P are double-buffered so the tensor cores compute S_{j+1} while the softmax warps work on tile j.
+// TMEM: columns [0,128) S0/P0, [128,256) S1/P1, [256,384) O_j.
+#include "kernels.cuh"
+#include "gemm.cuh"
+#include <cudaTypedefs.h>
+#include <mutex>
+
+namespace mq {
+
+constexpr int kTcRows = 128;       // query rows per CTA
+constexpr int kTcKv = 128;         // kv tokens per tile (8 pages)
+constexpr int kTcD = 128;          // head_dim
+constexpr int kTcSub = 128 * 128;  // bytes of one [128 rows][64 elements] bf16 sub-tile
+constexpr int kTcSmem = 2 * kTcSub /*Q*/ + 2 * (2 * kTcSub /*K*/ + 2 * kTcSub /*V*/) + 1024 /*align*/ + 256 /*barriers*/;
+
+struct AttnTcParams {
+  CUtensorMap tmQ;   // [T][n_q][128] bf16: box {64, G, 128 / G}
+  CUtensorMap tmK;   // [pages][n_kv][16][128] bf16: box {64, 16, 1, 1}
+  CUtensorMap tmV;
+  const int* block_table;
+  int max_pages;
+  const int4* tiles;  // {tok0, ntok, slot, pos0} per query tile
+  __nv_bfloat16* out; // [T][n_q * 128]
+  int n_q, n_kv;
+  float scale_log2;
+};
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (here the probabilities) is read from tensor memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// MN-major operand, 128-byte swizzle: rows along K are 128 B apart, 8-row groups SBO apart, the two 64-element halves
+// of the MN extent LBO apart (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units)
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(uint32_t M, uint32_t N) {  // B operand MN-major
+  return umma_idesc_bf16(M, N) | (1u << 16);
+}
+
+__global__ void __launch_bounds__(192, 1) prefill_attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;                      // 2 sub-tiles
+  uint8_t* KVs = smem + 2 * kTcSub;        // stage s: K sub0, K sub1, V sub0, V sub1
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kTcSub + 2 * 4 * kTcSub);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* kv_full = bars + 1;            // [2]
+  uint64_t* kv_empty = bars + 3;           // [2]
+  uint64_t* s_full = bars + 5;             // [2]
+  uint64_t* p_full = bars + 7;             // [2] count 4 (one per softmax warp)
+  uint64_t* o_full = bars + 9;             // [1]
+  uint64_t* o_empty = bars + 10;           // [1] count 4
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kvh = blockIdx.y;
+  const int G = p.n_q / p.n_kv;
+  const int4 tile = p.tiles[blockIdx.x];
+  const int tok0 = tile.x, ntok = tile.y, slot = tile.z, pos0 = tile.w;
+  const int kv_end = pos0 + ntok;                       // causal: the tile's last token sees positions < kv_end
+  const int n_tiles = (kv_end + kTcKv - 1) / kTcKv;
+  const int* btab = p.block_table + (size_t)slot * p.max_pages;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+    }
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 4);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();  // q and this pass's K / V rows come from the rope kernel
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      mbar_expect_tx(q_full, 2 * kTcSub);
+      // rows >= ntok * G of the tile belong to other sequences (or lie past T): they are computed and never stored
+      tma_load_3d(Qs, &p.tmQ, q_full, 0, kvh * G, tok0);
+      tma_load_3d(Qs + kTcSub, &p.tmQ, q_full, 64, kvh * G, tok0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        if (j >= 2) mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+        uint8_t* st = KVs + s * 4 * kTcSub;
+        mbar_expect_tx(&kv_full[s], 4 * kTcSub);
+        for (int pg = 0; pg < kTcKv / kPageSize; ++pg) {
+          const int t = j * kTcKv + pg * kPageSize;
+          const int page = t < kv_end ? btab[t / kPageSize] : 0;  // past the end: the scratch page (masked below)
+          tma_load_4d(st + pg * 2048, &p.tmK, &kv_full[s], 0, 0, kvh, page);
+          tma_load_4d(st + kTcSub + pg * 2048, &p.tmK, &kv_full[s], 64, 0, kvh, page);
+          tma_load_4d(st + 2 * kTcSub + pg * 2048, &p.tmV, &kv_full[s], 0, 0, kvh, page);
+          tma_load_4d(st + 3 * kTcSub + pg * 2048, &p.tmV, &kv_full[s], 64, 0, kvh, page);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t IDESC_S = umma_idesc_bf16(kTcRows, kTcKv);     // S = Q K^T: both operands K-major
+      constexpr uint32_t IDESC_O = umma_idesc_bf16_bmn(kTcRows, kTcD);  // O = P V: V is MN-major
+      const uint32_t q_addr = smem_u32(Qs);
+      auto mma_s = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(&kv_full[s], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(KVs + s * 4 * kTcSub);
+#pragma unroll
+        for (int k = 0; k < kTcD / 16; ++k) {  // 8 k-steps over d: 4 per 64-wide sub-tile
+          const uint32_t off = (uint32_t)(k >> 2) * kTcSub + (uint32_t)(k & 3) * 32;
+          umma_bf16(tmem_base + (uint32_t)(s * 128), umma_desc_sw128(q_addr + off), umma_desc_sw128(k_addr + off), IDESC_S, k != 0);
+        }
+        umma_commit(&s_full[s]);
+      };
+      mbar_wait(q_full, 0);
+      mma_s(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        if (j + 1 < n_tiles) mma_s(j + 1);                 // the tensor cores run ahead of the softmax warps
+        mbar_wait(&p_full[s], (j >> 1) & 1);               // P_j is in TMEM
+        if (j > 0) mbar_wait(o_empty, (j - 1) & 1);        // O_{j-1} has been folded into the registers
+        tc_fence_after();
+        const uint32_t v_addr = smem_u32(KVs + s * 4 * kTcSub + 2 * kTcSub);
+#pragma unroll
+        for (int k = 0; k < kTcKv / 16; ++k)               // 8 k-steps over the kv tokens: 16 rows = 2 KB each
+          umma_bf16_ts(tmem_base + 256, tmem_base + (uint32_t)(s * 128 + k * 8), umma_desc_sw128_mn(v_addr + k * 2048, kTcSub), IDESC_O,
+                       k != 0);
+        umma_commit(o_full);
+        umma_commit(&kv_empty[s]);
+      }
+    }
+  } else {
+    // ---------------- softmax + output: one query row per thread ----------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int qpos = pos0 + row / G;
+    float o[kTcD];
+#pragma unroll
+    for (int i = 0; i < kTcD; ++i) o[i] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j & 1;
+      const int t0 = j * kTcKv;
+      const bool edge = t0 + kTcKv > qpos + 1;             // some column of this tile is masked for this row
+      mbar_wait(&s_full[s], (j >> 1) & 1);
+      tc_fence_after();
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kTcKv; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_lane + (uint32_t)(s * 128 + c0), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float x = __uint_as_float(v[i]);
+          mx = fmaxf(mx, (!edge || t0 + c0 + i <= qpos) ? x : -INFINITY);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx * p.scale_log2);  // finite: column t0 <= qpos for every tile this row walks
+      const float alpha = exp2f(m_run - m_new);
+      // pass 2: probabilities -> packed bf16 into the first 64 columns of the same buffer
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kTcKv; c0 += 32) {
+        uint32_t a[16], b[16], pk[16];
+        tmem_ld16(t_lane + (uint32_t)(s * 128 + c0), a);
+        tmem_ld16(t_lane + (uint32_t)(s * 128 + c0 + 16), b);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float p0 = exp2f(__uint_as_float(a[2 * i]) * p.scale_log2 - m_new);
+          float p1 = exp2f(__uint_as_float(a[2 * i + 1]) * p.scale_log2 - m_new);
+          float p2 = exp2f(__uint_as_float(b[2 * i]) * p.scale_log2 - m_new);
+          float p3 = exp2f(__uint_as_float(b[2 * i + 1]) * p.scale_log2 - m_new);
+          if (edge) {
+            if (t0 + c0 + 2 * i > qpos) p0 = 0.f;
+            if (t0 + c0 + 2 * i + 1 > qpos) p1 = 0.f;
+            if (t0 + c0 + 16 + 2 * i > qpos) p2 = 0.f;
+            if (t0 + c0 + 16 + 2 * i + 1 > qpos) p3 = 0.f;
+          }
+          lsum += (p0 + p1) + (p2 + p3);
+          pk[i] = pack_bf16(p0, p1);
+          pk[8 + i] = pack_bf16(p2, p3);
+        }
+        tmem_st16(t_lane + (uint32_t)(s * 128 + c0 / 2), pk);  // 32 probabilities = 16 packed columns
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[s]);
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+      // O_j: fold into the register accumulator
+      mbar_wait(o_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < kTcD; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_lane + (uint32_t)(256 + c0), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[c0 + i] = o[c0 + i] * alpha + __uint_as_float(v[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    }
+    // ---- normalise and store this row (256 contiguous bytes)
+    if (row < ntok * G) {
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      __nv_bfloat16* po = p.out + ((size_t)(tok0 + row / G) * p.n_q + kvh * G + row % G) * kTcD;
+#pragma unroll
+      for (int c0 = 0; c0 < kTcD; c0 += 8) {
+        uint4 w;
+        w.x = pack_bf16(o[c0] * inv, o[c0 + 1] * inv);
+        w.y = pack_bf16(o[c0 + 2] * inv, o[c0 + 3] * inv);
+        w.z = pack_bf16(o[c0 + 4] * inv, o[c0 + 5] * inv);
+        w.w = pack_bf16(o[c0 + 6] * inv, o[c0 + 7] * inv);
+        *reinterpret_cast<uint4*>(po + c0) = w;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  });
+  return fn;
+}
+
+bool attn_tc_supported(int head_dim, int n_q, int n_kv) {
+  const int G = n_kv > 0 ? n_q / n_kv : 0;
+  return head_dim == kTcD && G >= 1 && G <= 8 && kTcRows % G == 0 && n_q % n_kv == 0;
+}
+
+bool attn_tc_encode_q(CUtensorMap* out, const void* q, int rows, int n_q, int G) {
+  auto fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)kTcD, (cuuint64_t)n_q, (cuuint64_t)rows};
+  const cuuint64_t strides[2] = {(cuuint64_t)kTcD * 2, (cuuint64_t)n_q * kTcD * 2};
+  const cuuint32_t box[3] = {64, (cuuint32_t)G, (cuuint32_t)(kTcRows / G)};
+  const cuuint32_t es[3] = {1, 1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(q), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool attn_tc_encode_kv(CUtensorMap* out, const void* cache, int n_pages, int n_kv) {
+  auto fn = encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)kTcD, (cuuint64_t)kPageSize, (cuuint64_t)n_kv, (cuuint64_t)n_pages};
+  const cuuint64_t strides[3] = {(cuuint64_t)kTcD * 2, (cuuint64_t)kPageSize * kTcD * 2, (cuuint64_t)n_kv * kPageSize * kTcD * 2};
+  const cuuint32_t box[4] = {64, (cuuint32_t)kPageSize, 1, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(cache), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+void attn_tc_set_attrs() {
+  cudaFuncSetAttribute(prefill_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+}
+
+cudaError_t launch_attn_prefill_tc(const LaunchCfg& lc, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                                   const AttnParams& a, int n_tiles) {
+  AttnTcParams p;
+  p.tmQ = tmQ; p.tmK = tmK; p.tmV = tmV;
+  p.block_table = a.block_table; p.max_pages = a.max_pages; p.tiles = a.tiles; p.out = a.out; p.n_q = a.n_q; p.n_kv = a.n_kv;
+  p.scale_log2 = a.scale_log2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(n_tiles, a.n_kv, 1);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = kTcSmem;
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lc.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, prefill_attn_tc_kernel, p);
+}
+
+}  // namespace mq

@@ -135,6 +135,21 @@ int mq_debug_gemm_fold(const void* W, int w_rows, int n_out, int K, const void* 
   return timed_launches("mq_debug_gemm_fold", [&] { return gemm_launch(g, lc); }, reps, ms_out);
 }
 
+int mq_debug_gemm_resid_prefill(const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, float* h,
+                                const void* gamma_next, void* xg, float* ssq_out, int ssq_stride, const float* ssq_in, int parts,
+                                int stride_in, float inv_h, float eps, int reps, float* ms_out) {
+  GemmPlan g;
+  gemm_set_attrs();
+  if (!gemm_plan(&g, W, n_out, n_out, K, X, x_rows_alloc, T, EPI_RESID, h, n_out, 1, 0, 0, nullptr) ||
+      !gemm_plan_set_resid(&g, gamma_next, xg, n_out, ssq_out, ssq_stride)) {
+    mq::set_last_error("EPI_RESID needs the 2-CTA kernel: T > 128, n_out %% 256 == 0, K %% 64 == 0");
+    return MQ_ERR_INVAL;
+  }
+  if (ssq_in) gemm_plan_set_rstd(&g, RstdIn{ssq_in, parts, stride_in, inv_h, eps});
+  LaunchCfg lc{0, false};
+  return timed_launches("mq_debug_gemm_resid_prefill", [&] { return gemm_launch(g, lc); }, reps, ms_out);
+}
+
 int mq_debug_gemm_dk_resid(const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, int cs, float* h,
                            const void* gamma_next, void* xg, float* ssq_out, int ssq_stride, int reps, float* ms_out) {
   DkPlan g;
@@ -208,6 +223,26 @@ int mq_debug_attn_prefill(const void* q, const void* k_cache, const void* v_cach
   attn_set_attrs();
   launch_attn_prefill(LaunchCfg{0, false}, p, n_tiles);
   return check_cuda("mq_debug_attn_prefill");
+}
+
+int mq_debug_attn_prefill_tc(const void* q, int q_rows, const void* k_cache, const void* v_cache, int n_pages, const int* block_table,
+                             int max_pages, const int* tiles /* int4 per tile, <= 128 / G tokens each */, int n_tiles, void* out,
+                             int n_q, int n_kv, float scale) {
+  if (!attn_tc_supported(128, n_q, n_kv)) { mq::set_last_error("tcgen05 attention: head_dim 128, GQA group 1 / 2 / 4 / 8"); return MQ_ERR_INVAL; }
+  CUtensorMap tq, tk, tv;
+  if (!attn_tc_encode_q(&tq, q, q_rows, n_q, n_q / n_kv) || !attn_tc_encode_kv(&tk, k_cache, n_pages, n_kv) ||
+      !attn_tc_encode_kv(&tv, v_cache, n_pages, n_kv)) {
+    mq::set_last_error("cuTensorMapEncodeTiled failed");
+    return MQ_ERR_CUDA;
+  }
+  AttnParams p = {};
+  p.head_dim = 128;
+  p.block_table = block_table; p.max_pages = max_pages; p.tiles = (const int4*)tiles; p.out = (__nv_bfloat16*)out;
+  p.n_q = n_q; p.n_kv = n_kv; p.scale_log2 = scale * 1.4426950408889634f;
+  attn_tc_set_attrs();
+  cudaError_t e = launch_attn_prefill_tc(LaunchCfg{0, false}, tq, tk, tv, p, n_tiles);
+  if (e != cudaSuccess) { mq::set_last_error("launch: %s", cudaGetErrorString(e)); return MQ_ERR_CUDA; }
+  return check_cuda("mq_debug_attn_prefill_tc");
 }
 
 int mq_debug_attn_decode(const void* q, const void* k_cache, const void* v_cache, const int* block_table,

@@ -119,7 +119,9 @@ static int worker_alloc(mq_worker* w) {
   if ((rc = dalloc(&w->part_ml, (size_t)kMaxDecodeSplits * MBp * c.n_q_heads * 2))) return rc;
   {
     const size_t tiles_h = (size_t)(H + 127) / 128;
-    if ((rc = dalloc(&w->ssq_e, (size_t)MBp)) || (rc = dalloc(&w->ssq_o, tiles_h * MBp)) || (rc = dalloc(&w->ssq_d, tiles_h * MBp)))
+    w->ssq_stride = round_up(std::max(MT, MBp), 16);
+    const size_t st = (size_t)w->ssq_stride;
+    if ((rc = dalloc(&w->ssq_e, st)) || (rc = dalloc(&w->ssq_o, tiles_h * st)) || (rc = dalloc(&w->ssq_d, tiles_h * st)))
       return rc;
     const char* e = getenv("MQ_DECODE_CHAIN");
     w->chain = !(e && e[0] == '0');
@@ -195,6 +197,23 @@ static int worker_alloc(mq_worker* w) {
   }
   CUDA_TRY(cudaStreamSynchronize(w->stream));
 
+  {
+    const char* e = getenv("MQ_ATTN_TC");
+    w->attn_tc = attn_tc_supported(D, c.n_q_heads, c.n_kv_heads) && !(e && e[0] == '0');
+    if (w->attn_tc) {
+      const int G = c.n_q_heads / c.n_kv_heads;
+      w->tm_k.resize(L); w->tm_v.resize(L);
+      bool ok = attn_tc_encode_q(&w->tm_q, w->q, MT, c.n_q_heads, G);
+      for (int l = 0; l < L && ok; ++l)
+        ok = attn_tc_encode_kv(&w->tm_k[l], w->k_cache + (size_t)l * w->cache_layer_stride, w->n_pages, c.n_kv_heads) &&
+             attn_tc_encode_kv(&w->tm_v[l], w->v_cache + (size_t)l * w->cache_layer_stride, w->n_pages, c.n_kv_heads);
+      if (!ok) {
+        set_last_error("cuTensorMapEncodeTiled failed for the attention tensor maps");
+        return MQ_ERR_CUDA;
+      }
+      w->prefill_tile_rows = kPrefillTileRowsTc;
+    }
+  }
   if (streamk_enabled() && streamk_workspace_alloc(&w->sk_ws) != 0) {
     set_last_error("stream-K workspace allocation failed");
     return MQ_ERR_NOMEM;
@@ -229,14 +248,14 @@ static int build_plans(mq_worker* w, PassPlans* pp, int T, bool decode) {
   const int x_rows = w->MT;
   // ---- decode chain: servable when every GEMM of the layer fits the cluster kernel (T <= 64, one head per QKV tile)
   const int tiles_h = (H + 127) / 128;
-  pp->chain = decode && !sk && w->chain && T <= 64 && dk_pick_cluster(tiles_h, qd / 64, T) > 0 &&
+  pp->chain = decode && !sk && w->chain && T <= 64 && !(getenv("MQ_DECODE_FOLD") && getenv("MQ_DECODE_FOLD")[0] == '0') && dk_pick_cluster(tiles_h, qd / 64, T) > 0 &&
               dk_pick_cluster(tiles_h, I / 64, T) > 0;
   if (pp->chain) {
     pp->qkv.resize(c.n_layers); pp->o_dk.resize(c.n_layers); pp->down_dk.resize(c.n_layers); pp->gate_up.resize(c.n_layers);
     pp->s_qkv = decode_splits((w->qkv_dim + 127) / 128, H / 64);
-    const RstdIn rs_o{w->ssq_o, tiles_h, MBp, 1.0f / (float)H, c.rms_eps};
-    const RstdIn rs_d{w->ssq_d, tiles_h, MBp, 1.0f / (float)H, c.rms_eps};
-    const RstdIn rs_e{w->ssq_e, 1, MBp, 1.0f / (float)H, c.rms_eps};
+    const RstdIn rs_o{w->ssq_o, tiles_h, w->ssq_stride, 1.0f / (float)H, c.rms_eps};
+    const RstdIn rs_d{w->ssq_d, tiles_h, w->ssq_stride, 1.0f / (float)H, c.rms_eps};
+    const RstdIn rs_e{w->ssq_e, 1, w->ssq_stride, 1.0f / (float)H, c.rms_eps};
     for (int l = 0; l < c.n_layers; ++l) {
       const LayerWeights& lw = w->layers[l];
       DkPlan& o = pp->o_dk[l];
@@ -256,14 +275,41 @@ static int build_plans(mq_worker* w, PassPlans* pp, int T, bool decode) {
       }
       gemm_plan_set_rstd(&pp->qkv[l], l == 0 ? rs_e : rs_d);
       o.p.h = w->h; o.p.ldh = H; o.p.gamma_next = lw.mlp_norm; o.p.xg = w->x; o.p.ldx = H; o.p.ssq_out = w->ssq_o;
-      o.p.ssq_stride = MBp;
+      o.p.ssq_stride = w->ssq_stride;
       d.p.h = w->h; d.p.ldh = H; d.p.gamma_next = l + 1 < c.n_layers ? w->layers[l + 1].attn_norm : w->final_norm;
-      d.p.xg = w->x; d.p.ldx = H; d.p.ssq_out = w->ssq_d; d.p.ssq_stride = MBp;
+      d.p.xg = w->x; d.p.ldx = H; d.p.ssq_out = w->ssq_d; d.p.ssq_stride = w->ssq_stride;
       gemm_plan_set_rstd(&pp->gate_up[l], rs_o);
     }
     return MQ_OK;
   }
   pp->qkv.resize(c.n_layers); pp->o.resize(c.n_layers); pp->gate_up.resize(c.n_layers); pp->down.resize(c.n_layers);
+  // ---- prefill with the RMSNorm fold: servable when all four GEMMs run on the persistent 2-CTA kernel
+  if (!decode && w->chain && T > 128 && !(getenv("MQ_PREFILL_FOLD") && getenv("MQ_PREFILL_FOLD")[0] == '0')) {
+    const RstdIn rs_o{w->ssq_o, tiles_h, w->ssq_stride, 1.0f / (float)H, c.rms_eps};
+    const RstdIn rs_d{w->ssq_d, tiles_h, w->ssq_stride, 1.0f / (float)H, c.rms_eps};
+    const RstdIn rs_e{w->ssq_e, 1, w->ssq_stride, 1.0f / (float)H, c.rms_eps};
+    bool ok = true;
+    for (int l = 0; l < c.n_layers && ok; ++l) {
+      const LayerWeights& lw = w->layers[l];
+      ok &= gemm_plan(&pp->qkv[l], lw.wqkv, w->qkv_dim, w->qkv_dim, H, w->x, x_rows, T, EPI_BF16, w->qkv_part, w->qkv_dim, 1, 0, 0, nullptr);
+      ok &= gemm_plan(&pp->o[l], lw.wo, H, H, qd, w->attn, x_rows, T, EPI_RESID, w->h, H, 1, 0, 0, nullptr);
+      ok &= gemm_plan(&pp->gate_up[l], lw.w_gate_up, 2 * I, I, H, w->x, x_rows, T, EPI_SILU_BF16, w->act, I, 1, 0, I, nullptr);
+      ok &= gemm_plan(&pp->down[l], lw.w_down, H, H, I, w->act, x_rows, T, EPI_RESID, w->h, H, 1, 0, 0, nullptr);
+      ok = ok && pp->qkv[l].twocta && pp->gate_up[l].twocta &&
+           gemm_plan_set_resid(&pp->o[l], lw.mlp_norm, w->x, H, w->ssq_o, w->ssq_stride) &&
+           gemm_plan_set_resid(&pp->down[l], l + 1 < c.n_layers ? w->layers[l + 1].attn_norm : w->final_norm, w->x, H, w->ssq_d,
+                               w->ssq_stride);
+      if (ok) {
+        gemm_plan_set_rstd(&pp->qkv[l], l == 0 ? rs_e : rs_d);
+        gemm_plan_set_rstd(&pp->gate_up[l], rs_o);
+      }
+    }
+    if (ok) {
+      pp->pfold = true;
+      pp->s_qkv = pp->s_o = pp->s_down = 1;
+      return MQ_OK;
+    }
+  }
   for (int l = 0; l < c.n_layers; ++l) {
     const LayerWeights& lw = w->layers[l];
     bool ok = true;
@@ -305,7 +351,7 @@ static GemmPlan* get_lm_plan(mq_worker* w, int rows, bool chain = false) {
     return nullptr;
   }
   if (chain)
-    gemm_plan_set_rstd(&g, RstdIn{w->ssq_d, (w->cfg.hidden + 127) / 128, MBp, 1.0f / (float)w->cfg.hidden, w->cfg.rms_eps});
+    gemm_plan_set_rstd(&g, RstdIn{w->ssq_d, (w->cfg.hidden + 127) / 128, w->ssq_stride, 1.0f / (float)w->cfg.hidden, w->cfg.rms_eps});
   return &(w->lm_plans[key] = g);
 }
 
@@ -382,15 +428,20 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
   const int MBp = round_up(w->MB, 16);
   const bool f32p = a.decode;
   uint64_t nl = 0;
-  launch_embed(lc, a.tok, w->embed, w->h, a.T, H); ++nl;
+  const bool pfold = !a.decode && pp->pfold;
+  if (pfold) launch_embed(lc, a.tok, w->embed, w->h, a.T, H, w->layers[0].attn_norm, w->x, w->ssq_e);
+  else launch_embed(lc, a.tok, w->embed, w->h, a.T, H);
+  ++nl;
   int prev_planes = 0;
   for (int l = 0; l < c.n_layers; ++l) {
     const LayerWeights& lw = w->layers[l];
     // timeline slots: 1 + 8 * layer + {0 norm1, 1 qkv, 2 rope, 3 attention, 4 o, 5 norm2, 6 gate/up, 7 down}
     auto tr = [&](int k) { return Trace{w->d_trace, 1 + 8 * l + k}; };
     auto tr_gemm = [&](GemmPlan& g, int k) { g.p.tr = tr(k); g.sk.tr = tr(k); };
-    launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, prev_planes, (long long)MBp * H, lw.attn_norm, w->x, nullptr, a.T,
-                       H, c.rms_eps, tr(0)); ++nl;
+    if (!pfold) {
+      launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, prev_planes, (long long)MBp * H, lw.attn_norm, w->x, nullptr, a.T,
+                         H, c.rms_eps, tr(0)); ++nl;
+    }
     tr_gemm(pp->qkv[l], 1);
     if (gemm_launch(pp->qkv[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     RopeKvParams rp;
@@ -405,11 +456,14 @@ static int run_layers(mq_worker* w, const PassArgs& a, PassPlans* pp, uint64_t* 
     AttnParams ap;
     fill_attn_params(w, a, l, &ap, tr(3));
     if (a.decode) { launch_attn_decode(lc, ap, a.T); ++nl; }
+    else if (w->attn_tc) { if (launch_attn_prefill_tc(lc, w->tm_q, w->tm_k[l], w->tm_v[l], ap, a.n_tiles) != cudaSuccess) return MQ_ERR_CUDA; ++nl; }
     else { launch_attn_prefill(lc, ap, a.n_tiles); ++nl; }
     tr_gemm(pp->o[l], 4);
     if (gemm_launch(pp->o[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
-    launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, pp->s_o, (long long)MBp * H, lw.mlp_norm, w->x, nullptr, a.T, H,
-                       c.rms_eps, tr(5)); ++nl;
+    if (!pfold) {
+      launch_add_rmsnorm(lc, w->h, w->proj_part, f32p, pp->s_o, (long long)MBp * H, lw.mlp_norm, w->x, nullptr, a.T, H,
+                         c.rms_eps, tr(5)); ++nl;
+    }
     tr_gemm(pp->gate_up[l], 6);
     if (gemm_launch(pp->gate_up[l], lc) != cudaSuccess) return MQ_ERR_CUDA; ++nl;
     tr_gemm(pp->down[l], 7);
@@ -427,7 +481,8 @@ static int run_head(mq_worker* w, bool decode, const int* row_idx, int rows, Pas
   const int MBp = round_up(w->MB, 16);
   const bool chain = decode && pp->chain;  // final norm folded into the LM head (rows are the batch rows themselves)
   if (!chain) {
-    launch_add_rmsnorm(lc, w->h, w->proj_part, decode, pp->s_down, (long long)MBp * c.hidden, w->final_norm, w->x_last,
+    // (prefill with the fold: the last down projection already added into h - nothing left to sum)
+    launch_add_rmsnorm(lc, w->h, w->proj_part, decode, (!decode && pp->pfold) ? 0 : pp->s_down, (long long)MBp * c.hidden, w->final_norm, w->x_last,
                        row_idx, rows, c.hidden, c.rms_eps, Trace{w->d_trace, kTraceSlots - 2});
     *n_launch += 1;
   }
@@ -572,7 +627,7 @@ struct PrefillItem { mq_req* r; int n_tok; bool completes; };
 static int launch_prefill(mq_worker* w, std::vector<PrefillItem>& items) {
   const mq_model_cfg& c = w->cfg;
   const int G = c.n_q_heads / c.n_kv_heads;
-  const int tok_per_tile = kPrefillTileRows / G;
+  const int tok_per_tile = w->prefill_tile_rows / G;
   int T = 0;
   for (auto& it : items) T += it.n_tok;
   int ss;
@@ -1018,7 +1073,7 @@ int engine_forward_logits(mq_worker* w, const int32_t* tokens, int n, int all_po
     return MQ_ERR_INVAL;
   }
   const int MBp = round_up(w->MB, 16);
-  const int G = c.n_q_heads / c.n_kv_heads, tok_per_tile = kPrefillTileRows / G;
+  const int G = c.n_q_heads / c.n_kv_heads, tok_per_tile = w->prefill_tile_rows / G;
   const int need = (n + kPageSize - 1) / kPageSize;
   if ((int)w->free_pages.size() < need || w->slot_req[0]) {
     set_last_error("mq_debug_forward: worker busy");
@@ -1147,6 +1202,7 @@ int mq_worker_open(int32_t gpu, const mq_model_cfg* cfg, mq_worker** out) {
   CUDA_TRY(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
   gemm_set_attrs();
   attn_set_attrs();
+  attn_tc_set_attrs();
   int rc = worker_alloc(w);
   if (rc != MQ_OK) {
     mq_worker_close(w);

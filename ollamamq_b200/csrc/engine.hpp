@@ -39,6 +39,9 @@ struct PassPlans {
   // `qkv` (planes) and `gate_up` then carry the rstd fold
   bool chain = false;
   std::vector<DkPlan> o_dk, down_dk;
+  // prefill with the same fold (all four GEMMs on the persistent 2-CTA kernel): O / down add into the residual stream and
+  // emit xg + h^2 partials (EPI_RESID), QKV / gate-up scale by rstd - no add_rmsnorm launches (4 GEMMs + rope + attention)
+  bool pfold = false;
 };
 
 }  // namespace mq
@@ -108,6 +111,12 @@ struct mq_worker {
   int* d_split_counter = nullptr;  // [MB][n_kv] arrival counters of the split-KV decode attention
   // decode chain: per-weight-tile partial sums of h^2 (RMSNorm fold, gemm.cuh RstdIn), [tiles][round_up(MB, 16)]
   float *ssq_e = nullptr, *ssq_o = nullptr, *ssq_d = nullptr;
+  int ssq_stride = 0;        // tokens per partial row: max(prefill pass, decode batch)
+  // prefill attention on tcgen05 (attn_tc.cu): tensor maps of q and of every layer's K / V cache; 128-row query tiles
+  bool attn_tc = false;      // head_dim 128 && MQ_ATTN_TC != 0
+  int prefill_tile_rows = 64;
+  CUtensorMap tm_q;
+  std::vector<CUtensorMap> tm_k, tm_v;
   bool chain = true;         // MQ_DECODE_CHAIN=0: the round-1 plane-based decode path (A/B and parity cross-check)
   unsigned long long* d_trace = nullptr;  // MQ_TRACE=1: [kTraceSlots][4] %globaltimer stamps of the latest pass
   // pinned host mirrors / staging

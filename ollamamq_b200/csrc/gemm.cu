@@ -43,7 +43,7 @@ static bool tmap_encode_out(CUtensorMap* out, void* base, int epi, int n_out, in
   auto fn = get_encode_fn();
   if (!fn) return false;
   const cuuint32_t estr[3] = {1, 1, 1};
-  if (epi == EPI_F32) {
+  if (epi == EPI_F32 || epi == EPI_RESID) {
     const cuuint64_t dims[3] = {(cuuint64_t)n_out, (cuuint64_t)T, (cuuint64_t)splits};
     const cuuint64_t strides[2] = {(cuuint64_t)ldo * 4, (cuuint64_t)(splits > 1 ? split_stride : (long long)T * ldo) * 4};
     const cuuint32_t box[3] = {(cuuint32_t)tile_rows, (cuuint32_t)bn, 1};
@@ -147,6 +147,7 @@ cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
       case EPI_F32: return launch_c2<EPI_F32>(g, lc);
       case EPI_BF16: return launch_c2<EPI_BF16>(g, lc);
       case EPI_SILU_BF16: return launch_c2<EPI_SILU_BF16>(g, lc);
+      case EPI_RESID: return launch_c2<EPI_RESID>(g, lc);
       default: return cudaErrorInvalidValue;
     }
   if (g.persist) {
@@ -202,6 +203,7 @@ void gemm_set_attrs() {
   cudaFuncSetAttribute(gemm_2cta_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_F32));
   cudaFuncSetAttribute(gemm_2cta_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_BF16));
   cudaFuncSetAttribute(gemm_2cta_kernel<EPI_SILU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_SILU_BF16));
+  cudaFuncSetAttribute(gemm_2cta_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_RESID));
   cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_BF16));
   cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_F32));
   cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_BF16));
@@ -330,6 +332,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
     // the pair computes 256 features x c2_bn tokens: every CTA stages only its own half of the activation tile
     const int bn2 = c2_bn(epi);
     if (!tmap_encode_2d(&g->tmB, X, (uint64_t)x_rows_alloc, (uint64_t)K, (uint32_t)(bn2 / 2))) return false;
+    g->c2 = TwoCtaParams{};
     g->c2.out = out; g->c2.ldo = ldo;
     g->c2.T = T; g->c2.n_out = n_out; g->c2.k_blocks = kb; g->c2.a2_row_off = a2_row_off;
     g->c2.m_tiles = n_out / 256;
@@ -350,6 +353,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
     const int tiles = g->p.m_tiles * g->p.n_tiles;
     if (tiles >= 2 * sms) {  // at least two tiles per CTA, otherwise there is nothing to overlap
       g->persist = true;
+      g->pk = PersistParams{};
       g->pk.out = out; g->pk.ldo = ldo; g->pk.T = T; g->pk.n_out = n_out; g->pk.k_blocks = kb;
       g->pk.m_tiles = g->p.m_tiles; g->pk.n_tiles = g->p.n_tiles; g->pk.group_m = g->p.group_m;
       g->pk.n_ctas = sms; g->pk.w_policy = g->p.w_policy;
@@ -377,6 +381,17 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
 void gemm_plan_set_rstd(GemmPlan* g, const RstdIn& rs) {
   g->p.rs = rs;
   g->sk.rs = rs;
+  g->c2.rs = rs;
+}
+// EPI_RESID plans (2-CTA kernel): `out` given to gemm_plan is the fp32 residual stream h
+bool gemm_plan_set_resid(GemmPlan* g, const void* gamma_next, void* xg, int ldx, float* ssq_out, int ssq_stride) {
+  if (!g->twocta || g->epi != EPI_RESID) return false;
+  g->c2.gamma_next = (const __nv_bfloat16*)gamma_next;
+  g->c2.xg = (__nv_bfloat16*)xg;
+  g->c2.ldx = ldx;
+  g->c2.ssq_out = ssq_out;
+  g->c2.ssq_stride = ssq_stride;
+  return true;
 }
 
 template <int BN>

@@ -26,7 +26,9 @@ enum GemmEpilogue : int {
   EPI_BF16 = 1,      // out_bf16[t][f]   = acc
   EPI_SILU_BF16 = 2, // out_bf16[t][f]   = silu(acc_gate) * acc_up   (two A tiles: rows f and f + a2_row_off)
   EPI_GELU_BF16 = 3, // out_bf16[t][f]   = gelu_erf(acc + bias[f])   (BERT intermediate; plain 1-CTA kernel only)
-  EPI_BIAS_BF16 = 4  // out_bf16[t][f]   = acc + bias[f]             (encoder QKV; plain 1-CTA kernel only)
+  EPI_BIAS_BF16 = 4, // out_bf16[t][f]   = acc + bias[f]             (encoder QKV; plain 1-CTA kernel only)
+  EPI_RESID = 5      // h[t][f] += acc;  xg[t][f] = bf16(h * gamma_next[f]);  ssq[tile][t] = sum_f h^2   (prefill O / down
+                     // projections with the RMSNorm fold; 2-CTA kernel only - gemm_2cta.cuh)
 };
 
 // RMSNorm fold (decode chain): the activation operand of a GEMM is xg = bf16(h * gamma) and the epilogue scales token

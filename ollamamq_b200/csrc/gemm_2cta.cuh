@@ -36,6 +36,13 @@ struct TwoCtaParams {
   int m_tiles, n_tiles, group_m;  // tiles of 256 features x c2_bn(epi) tokens
   int n_pairs;                    // persistent CTA pairs launched
   unsigned long long w_policy;
+  RstdIn rs;                      // RMSNorm fold of the activation operand: token column t is scaled by rstd[t] (gemm.cuh)
+  // EPI_RESID: out = the fp32 residual stream h (ldo = its leading dimension), updated in place
+  const __nv_bfloat16* gamma_next;  // [n_out] weight of the NEXT RMSNorm
+  __nv_bfloat16* xg;                // [T][ldx] bf16(h * gamma_next)
+  int ldx;
+  float* ssq_out;                   // [n_out / 128][ssq_stride] per-128-feature-tile partial sums of h^2
+  int ssq_stride;
 };
 
 // token columns per tile.  The dual SiLU epilogue keeps 256 too: gate + up then fill all 512 TMEM columns, i.e. ONE
@@ -43,6 +50,7 @@ struct TwoCtaParams {
 // MFLOP from shared memory instead of 8 and is bound by that (measured: prefill 432 -> 459 ms).
 __host__ __device__ constexpr int c2_bn(int epi) { return 256; }
 __host__ __device__ constexpr int c2_nbuf(int epi) { return epi == EPI_SILU_BF16 ? 1 : 2; }
+__host__ __device__ constexpr int c2_tail_bytes() { return 256 /*barriers*/ + 256 * 4 /*rstd*/ + 4 * 256 * 4 /*h^2 partials*/; }
 __host__ __device__ constexpr int c2_stage_bytes(int epi) {
   return kATileBytes * (epi == EPI_SILU_BF16 ? 2 : 1) + (c2_bn(epi) / 2) * kBlockK * 2;  // own weight rows + own half of the tokens
 }
@@ -50,7 +58,7 @@ __host__ __device__ constexpr int c2_stages(int epi) {
   int s = (200 * 1024) / c2_stage_bytes(epi);
   return s > 8 ? 8 : s;
 }
-__host__ __device__ constexpr int c2_smem_bytes(int epi) { return c2_stages(epi) * c2_stage_bytes(epi) + 1024 + 256; }
+__host__ __device__ constexpr int c2_smem_bytes(int epi) { return c2_stages(epi) * c2_stage_bytes(epi) + 1024 + c2_tail_bytes(); }
 
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -126,6 +134,8 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator buffer complete (multicast commit: both CTAs)
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] used in the leader only: both CTAs have drained the buffer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* rstd_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [256] rstd of the tile's tokens
+  float* ssq_s = rstd_s + 256;                                                  // [4 lane quarters][256 tokens]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -232,6 +242,9 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;                 // TMEM lane quarter (warps w and w + 4 share one)
     const int chalf = (warp - 2) >> 2;      // which half of the token columns this warp drains
     const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;        // 0..255
+    const bool fold = p.rs.ssq != nullptr;
+    if (fold || EPI == EPI_RESID) pdl_wait();  // rstd partials / the residual stream come from earlier kernels
     int i = 0;
     for (int t = pair; t < n_tiles_total; t += p.n_pairs, ++i) {
       int tile_m, tile_n;
@@ -239,12 +252,27 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int f = tile_m * 256 + (int)rank * kBlockM + row;  // this thread's output feature
       const int n0 = tile_n * BN;
       const int buf = i % NBUF, use = i / NBUF;
+      if (fold) {  // per-token RMSNorm scale of this tile's 256 tokens (under the MMAs of the tile)
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done with rstd_s
+        rstd_s[et] = (n0 + et < p.T) ? rstd_of(p.rs, n0 + et) : 0.f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      float gm = 0.f;
+      if constexpr (EPI == EPI_RESID) gm = __bfloat162float(p.gamma_next[f]);
       mbar_wait(&tfull_bar[buf], use & 1);
       tc_fence_after();
       const uint32_t t_lane = tmem_base + (uint32_t)(buf * ACC_COLS) + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 16) {
-        if (n0 + c0 >= p.T) break;
+        if (n0 + c0 >= p.T) {
+          if constexpr (EPI == EPI_RESID) {  // columns past T: zero partials so the tile's sums stay defined
+            if (lane == 0)
+              for (int j = 0; j < 16; ++j) ssq_s[q * 256 + c0 + j] = 0.f;
+            continue;
+          } else {
+            break;
+          }
+        }
         uint32_t v[16];
         tmem_ld16(t_lane + c0, v);
         if constexpr (kDual) {
@@ -254,8 +282,27 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)(n0 + c0) * p.ldo + f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float g = __uint_as_float(v[j]);
-            if (n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __float2bfloat16(__fdividef(g, 1.0f + __expf(-g)) * __uint_as_float(u[j]));
+            const float sc = fold ? rstd_s[c0 + j] : 1.f;
+            const float g = __uint_as_float(v[j]) * sc;
+            if (n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __float2bfloat16(__fdividef(g, 1.0f + __expf(-g)) * (__uint_as_float(u[j]) * sc));
+          }
+        } else if constexpr (EPI == EPI_RESID) {
+          float* hp = reinterpret_cast<float*>(p.out) + (size_t)(n0 + c0) * p.ldo + f;
+          float hv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) hv[j] = (n0 + c0 + j < p.T) ? hp[(size_t)j * p.ldo] : 0.f;  // all loads before the first use
+          tmem_ld_wait();
+          __nv_bfloat16* xp = p.xg + (size_t)(n0 + c0) * p.ldx + f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const bool ok = n0 + c0 + j < p.T;
+            hv[j] = ok ? hv[j] + __uint_as_float(v[j]) : 0.f;
+            if (ok) {
+              hp[(size_t)j * p.ldo] = hv[j];
+              xp[(size_t)j * p.ldx] = __float2bfloat16(hv[j] * gm);
+            }
+            const float ss = warp_sum(hv[j] * hv[j]);  // over this warp's 32 features, fixed order
+            if (lane == 0) ssq_s[q * 256 + c0 + j] = ss;
           }
         } else {
           tmem_ld_wait();
@@ -263,12 +310,12 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float* o = reinterpret_cast<float*>(p.out) + (size_t)(n0 + c0) * p.ldo + f;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __uint_as_float(v[j]);
+              if (n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __uint_as_float(v[j]) * (fold ? rstd_s[c0 + j] : 1.f);
           } else {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)(n0 + c0) * p.ldo + f;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __float2bfloat16(__uint_as_float(v[j]));
+              if (n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __float2bfloat16(__uint_as_float(v[j]) * (fold ? rstd_s[c0 + j] : 1.f));
           }
         }
       }
@@ -278,6 +325,12 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (warp == 2 && lane == 0) {
         if (leader_cta) mbar_arrive(&tempty_bar[buf]);
         else mbar_arrive_remote(&tempty_bar[buf], 0);
+      }
+      if constexpr (EPI == EPI_RESID) {  // this CTA's 128 features of the tile: one partial per token, quarters in order
+        if (n0 + et < p.T)
+          p.ssq_out[(size_t)(tile_m * 2 + (int)rank) * p.ssq_stride + n0 + et] =
+              (ssq_s[et] + ssq_s[256 + et]) + (ssq_s[512 + et] + ssq_s[768 + et]);
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // ssq_s is rewritten by the next tile
       }
     }
   }

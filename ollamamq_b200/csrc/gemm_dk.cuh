@@ -56,7 +56,13 @@ constexpr int kDkMaxTok = 32;  // tokens one CTA finishes (its preload buffer): 
 // shared memory: [TMA ring][receive buffer: CS slots x tok_per tokens x 128 fp32][preload: MAXTOK x 128 fp32][misc]
 __host__ __device__ constexpr int dk_maxtok(int bn) { return bn < kDkMaxTok ? bn : kDkMaxTok; }
 __host__ __device__ constexpr int dk_recv_bytes(int bn) { return (bn + 8) * kBlockM * 4; }
-__host__ __device__ constexpr int dk_pre_bytes(int bn) { return dk_maxtok(bn) * kBlockM * 4; }
+// preload / h^2 buffer: token rows are 132 floats apart and every 32-feature quarter is shifted by one more float, so that
+// the per-token sum of squares (4 threads per token, 32 features each) walks its values in a FIXED order - the same for
+// every token slot - without bank conflicts.  (A lane-rotated start was conflict-free too, but made the rounding of a
+// token's RMSNorm depend on its slot: the trace's tokens changed with the order the users were submitted in.)
+constexpr int kDkPreStride = 132;
+__host__ __device__ constexpr int dk_pre_bytes(int bn) { return (dk_maxtok(bn) * kDkPreStride + 8) * 4; }
+__device__ __forceinline__ uint32_t dk_pre_idx(int tok, int row) { return (uint32_t)(tok * kDkPreStride + row + (row >> 5)); }
 __host__ __device__ constexpr int dk_stages(int bn) {
   int s = (222 * 1024 - dk_recv_bytes(bn) - dk_pre_bytes(bn)) / gemm_stage_bytes(bn, EPI_F32);
   return s > 8 ? 8 : s;
@@ -193,9 +199,9 @@ gemm_dk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float gm = 0.f;  // gamma_next[f]
     if (frow) {
       gm = __bfloat162float(p.gamma_next[f]);
-      const uint32_t dsts = smem_u32(pre + row);
+      const uint32_t dsts = smem_u32(pre);
       const float* src = p.h + (size_t)t0 * p.ldh + f;
-      for (int i = hid; i < ntok; i += 2) cp_async4(dsts + (uint32_t)(i * kBlockM) * 4u, src + (size_t)i * p.ldh);
+      for (int i = hid; i < ntok; i += 2) cp_async4(dsts + dk_pre_idx(i, row) * 4u, src + (size_t)i * p.ldh);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     // ---- phase 1: partial accumulator -> [token][feature] tile in the idle ring -> bulk copies to the owners
@@ -271,7 +277,7 @@ gemm_dk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         float* hp = p.h + (size_t)(t0 + hid) * p.ldh + f;
         __nv_bfloat16* xp = p.xg + (size_t)(t0 + hid) * p.ldx + f;
         const size_t hstep = 2 * (size_t)p.ldh, xstep = 2 * (size_t)p.ldx;
-        uint32_t ra = smem_u32(recv) + (uint32_t)(hid * kBlockM + row) * 4u, pa = smem_u32(pre) + (uint32_t)(hid * kBlockM + row) * 4u;
+        uint32_t ra = smem_u32(recv) + (uint32_t)(hid * kBlockM + row) * 4u, pa = smem_u32(pre) + dk_pre_idx(hid, row) * 4u;
         // batches of 4 tokens: every shared-memory load of a batch is issued before its first use (the loads are volatile
         // asm, i.e. kept in program order - token by token they formed one dependent chain per token)
         for (int i0 = hid; i0 < ntok; i0 += 8) {
@@ -280,7 +286,7 @@ gemm_dk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int b = 0; b < 4; ++b) {
             const bool ok = i0 + 2 * b < ntok;
             sv[b] = ok ? rank_sum(ra + (uint32_t)b * (2 * kBlockM * 4)) : 0.f;
-            pv[b] = ok ? lds_f32(pa + (uint32_t)b * (2 * kBlockM * 4)) : 0.f;
+            pv[b] = ok ? lds_f32(pa + (uint32_t)b * (2 * kDkPreStride * 4)) : 0.f;
           }
 #pragma unroll
           for (int b = 0; b < 4; ++b) {
@@ -290,10 +296,10 @@ gemm_dk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 hp[(size_t)b * hstep] = hv;
                 xp[(size_t)b * xstep] = __float2bfloat16(hv * gm);
               }
-              sts_f32(pa + (uint32_t)b * (2 * kBlockM * 4), hv * hv);
+              sts_f32(pa + (uint32_t)b * (2 * kDkPreStride * 4), hv * hv);
             }
           }
-          ra += 4 * 2 * kBlockM * 4; pa += 4 * 2 * kBlockM * 4; hp += 4 * hstep; xp += 4 * xstep;
+          ra += 4 * 2 * kBlockM * 4; pa += 4 * 2 * kDkPreStride * 4; hp += 4 * hstep; xp += 4 * xstep;
         }
       }
     };
@@ -307,14 +313,14 @@ gemm_dk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     {
       if (et == 0) dk_stamp(p, 10);
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      // sum of squares per token: 4 threads per token, 32 features each (rotated start: conflict-free), fixed order
+      // sum of squares per token: 4 threads per token, 32 features each, in feature order (see kDkPreStride)
       // (all lanes run the shuffles: ntok need not be a multiple of the 8 tokens a warp covers)
       const int ti = et >> 2, part = et & 3;  // (ti >= 32 >= ntok for the second half of the threads)
       float ss = 0.f;
       if (ti < ntok) {
-        const uint32_t base = smem_u32(pre) + (uint32_t)(ti * kBlockM + part * 32) * 4u;
+        const uint32_t base = smem_u32(pre) + dk_pre_idx(ti, part * 32) * 4u;
 #pragma unroll 8
-        for (int k = 0; k < 32; ++k) ss += lds_f32(base + (uint32_t)((k + lane) & 31) * 4u);
+        for (int k = 0; k < 32; ++k) ss += lds_f32(base + (uint32_t)k * 4u);
       }
       ss += __shfl_xor_sync(0xffffffffu, ss, 1);
       ss += __shfl_xor_sync(0xffffffffu, ss, 2);

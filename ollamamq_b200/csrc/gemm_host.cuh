@@ -53,6 +53,9 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
 int gemm_balanced_rows(int n_out);
 // RMSNorm fold: scale token column t of the result by rstd[t] (GemmParams::rs / StreamKParams::rs).
 void gemm_plan_set_rstd(GemmPlan* g, const RstdIn& rs);
+// EPI_RESID (prefill O / down with the fold; only servable by the 2-CTA kernel: n_out % 256 == 0, T > 128): `out` of
+// gemm_plan is the fp32 residual stream.  false: the plan is not a 2-CTA EPI_RESID plan.
+bool gemm_plan_set_resid(GemmPlan* g, const void* gamma_next, void* xg, int ldx, float* ssq_out, int ssq_stride);
 
 // ---- decode chain (gemm_dk.cuh): cluster split-K GEMM with the residual add / next-norm partials fused
 struct DkPlan {

@@ -1,5 +1,6 @@
 // Launch wrappers for the non-GEMM kernels of the forward pass (see kernels.cu for the designs).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -77,6 +78,15 @@ struct AttnParams {
   Trace tr;            // optional timeline stamps (MQ_TRACE=1)
 };
 void launch_attn_prefill(const LaunchCfg& lc, const AttnParams& p, int n_tiles);
+// ---- prefill attention on tcgen05 (attn_tc.cu): head_dim 128, GQA group 1 / 2 / 4 / 8, query tiles of 128 rows
+// (= 128 / G tokens x G heads).  Tensor maps: q = the [rows][n_q][128] activation, k / v = one layer of the paged cache.
+constexpr int kPrefillTileRowsTc = 128;
+bool attn_tc_supported(int head_dim, int n_q, int n_kv);
+bool attn_tc_encode_q(CUtensorMap* out, const void* q, int rows, int n_q, int G);
+bool attn_tc_encode_kv(CUtensorMap* out, const void* cache, int n_pages, int n_kv);
+void attn_tc_set_attrs();
+cudaError_t launch_attn_prefill_tc(const LaunchCfg& lc, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
+                                   const AttnParams& a, int n_tiles);
 void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots);
 void attn_set_attrs();
 int attn_decode_resident_ctas();

@@ -147,3 +147,35 @@ def test_lm_head_fold(T, V, K, sk):
     assert rc == 0, m.last_error()
     assert torch.isfinite(out).all()
     assert _relerr(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("T,n_out,K", [(4608, 4096, 4096), (300, 1024, 2048), (1000, 512, 14336), (257, 256, 512)])
+def test_prefill_resid_epilogue_on_the_persistent_2cta_kernel(T, n_out, K):
+    """Prefill O / down projection with the RMSNorm fold: h += X W^T, xg = bf16(h * gamma), per-128-feature-tile sum of h^2
+    (ragged last token tile included), deterministic."""
+    m = _lib()
+    g = torch.Generator(device="cuda").manual_seed(T + n_out + K)
+    W = (torch.randn(n_out, K, device=dev(), generator=g) * 0.03).bfloat16()
+    X = torch.randn(T, K, device=dev(), generator=g).bfloat16()
+    h0 = torch.randn(T, n_out, device=dev(), generator=g)
+    gamma = (1 + 0.1 * torch.randn(n_out, device=dev(), generator=g)).bfloat16()
+    tiles = n_out // 128
+    stride = ((T + 15) // 16) * 16
+    ref_h = h0 + X.float() @ W.float().T
+    outs = []
+    for rep in range(2):
+        h = h0.clone()
+        xg = torch.full((T, n_out), float("nan"), device=dev(), dtype=torch.bfloat16)
+        ssq = torch.full((tiles, stride), float("nan"), device=dev())
+        rc = m.lib.mq_debug_gemm_resid_prefill(P(W), n_out, K, P(X), T, T, P(h), P(gamma), P(xg), P(ssq), stride, None, 0, 0, 0.0,
+                                               0.0, 0, None)
+        assert rc == 0, m.last_error()
+        outs.append((h, xg, ssq))
+    h, xg, ssq = outs[0]
+    assert torch.isfinite(h).all() and torch.isfinite(xg.float()).all()
+    assert _relerr(h, ref_h) < 2e-3
+    assert _relerr(xg, h * gamma.float()) < 4e-3
+    got = ssq[:, :T].sum(0)
+    assert torch.isfinite(got).all()
+    assert torch.allclose(got, h.pow(2).sum(-1), rtol=1e-4)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][2][:, :T], outs[1][2][:, :T])

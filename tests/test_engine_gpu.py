@@ -118,10 +118,11 @@ def test_decode_chain_and_plane_path_both_hold_parity(monkeypatch, cfg_name):
     g = torch.Generator().manual_seed(5)
     prompts = [torch.randint(0, cfg["vocab"], (n,), generator=g).tolist() for n in (9, 70, 33, 15, 16, 17, 130, 1)]
 
-    def run(chain):
+    def run(chain, order=None):
         monkeypatch.setenv("MQ_DECODE_CHAIN", "1" if chain else "0")
         with _open(cfg, w, max_batch=8, use_pdl=1, use_graphs=1) as wk:
-            streams = [wk.submit(mq.Stream(), prompt_tokens=p, max_new_tokens=20) for p in prompts]
+            subs = {i: wk.submit(mq.Stream(), prompt_tokens=prompts[i], max_new_tokens=20) for i in (order or range(len(prompts)))}
+            streams = [subs[i] for i in range(len(prompts))]
             toks = []
             for p, s in zip(prompts, streams):
                 s.wait(120)
@@ -136,8 +137,10 @@ def test_decode_chain_and_plane_path_both_hold_parity(monkeypatch, cfg_name):
 
     toks_chain, n_chain, steps_chain = run(True)
     toks_chain2, _, _ = run(True)
+    toks_rev, _, _ = run(True, order=list(range(len(prompts)))[::-1])
     toks_plane, n_plane, steps_plane = run(False)
     assert toks_chain == toks_chain2                    # fixed-order reductions: bit-reproducible
+    assert toks_chain == toks_rev                       # ... and independent of the slot a sequence lands in
     assert steps_chain == steps_plane
     assert n_chain < n_plane                            # three launches per layer fewer in every decode step
 

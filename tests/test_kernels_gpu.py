@@ -332,6 +332,45 @@ def test_attn_prefill(n_q, n_kv, D):
         r0 += L
 
 
+@pytest.mark.parametrize("n_q,n_kv", [(32, 8), (8, 8), (16, 8), (8, 1), (32, 16)])
+def test_attn_prefill_tcgen05(n_q, n_kv):
+    """Prefill attention on the tcgen05 pipe (csrc/attn_tc.cu): S = Q K^T and O = P V as UMMA, P in tensor memory, one
+    query row per softmax thread; 128-row query tiles (128 / G tokens x G heads), causal on absolute positions, chunks
+    that attend to cached context, ragged tiles."""
+    m = _lib()
+    D = 128
+    G = n_q // n_kv
+    tok_per_tile = 128 // G
+    n_slots, max_pages = 3, 40
+    bt, kc, vc = _make_cache(n_slots, max_pages, n_kv, seed=1, D=D)
+    kc = torch.randn_like(kc.float()).bfloat16()
+    vc = torch.randn_like(vc.float()).bfloat16()
+    bt, kc, vc = bt.to(dev()), kc.to(dev()), vc.to(dev())
+    seqs = [(0, 0, 512), (1, 100, 77), (2, 0, 5)]
+    T = sum(s[2] for s in seqs)
+    q = torch.randn(T, n_q, D, device=dev()).bfloat16()
+    tiles = []
+    r0 = 0
+    for slot, ctx, L in seqs:
+        for i in range(0, L, tok_per_tile):
+            tiles.append([r0 + i, min(tok_per_tile, L - i), slot, ctx + i])
+        r0 += L
+    tiles_t = torch.tensor(tiles, dtype=torch.int32, device=dev())
+    out = torch.zeros(T, n_q, D, device=dev(), dtype=torch.bfloat16)
+    rc = m.lib.mq_debug_attn_prefill_tc(P(q), T, P(kc), P(vc), kc.shape[0], P(bt), max_pages, P(tiles_t), len(tiles), P(out), n_q, n_kv,
+                                        1.0 / math.sqrt(D))
+    assert rc == 0, m.last_error()
+    assert torch.isfinite(out.float()).all()
+    r0 = 0
+    for slot, ctx, L in seqs:
+        k, v = _gather_kv(kc, vc, bt[slot], ctx + L)
+        qpos = torch.arange(ctx, ctx + L, device=dev())
+        ref = _attn_ref(q[r0:r0 + L].float(), k, v, qpos)
+        err = _relerr(out[r0:r0 + L], ref)
+        assert err < 1e-2, f"slot {slot}: rel err {err}"
+        r0 += L
+
+
 @pytest.mark.parametrize("n_q,n_kv,n_splits,D", [(32, 8, 4, 128), (32, 8, 1, 128), (28, 4, 3, 128), (32, 8, 8, 128),
                                                   (32, 8, 2, 128), (32, 32, 1, 96), (32, 32, 3, 96), (12, 4, 2, 96),
                                                   (8, 2, 4, 64), (8, 1, 1, 64),
