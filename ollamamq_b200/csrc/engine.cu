@@ -248,7 +248,7 @@ static int build_plans(mq_worker* w, PassPlans* pp, int T, bool decode) {
   const int x_rows = w->MT;
   // ---- decode chain: servable when every GEMM of the layer fits the cluster kernel (T <= 64, one head per QKV tile)
   const int tiles_h = (H + 127) / 128;
-  pp->chain = decode && !sk && w->chain && T <= 64 && !(getenv("MQ_DECODE_FOLD") && getenv("MQ_DECODE_FOLD")[0] == '0') && dk_pick_cluster(tiles_h, qd / 64, T) > 0 &&
+  pp->chain = decode && !sk && w->chain && T <= 64 && dk_pick_cluster(tiles_h, qd / 64, T) > 0 &&
               dk_pick_cluster(tiles_h, I / 64, T) > 0;
   if (pp->chain) {
     pp->qkv.resize(c.n_layers); pp->o_dk.resize(c.n_layers); pp->down_dk.resize(c.n_layers); pp->gate_up.resize(c.n_layers);
@@ -268,7 +268,7 @@ static int build_plans(mq_worker* w, PassPlans* pp, int T, bool decode) {
       ok &= dk_plan(&o, lw.wo, H, H, qd, w->attn, x_rows, T, 128, 0);
       ok &= dk_plan(&d, lw.w_down, H, H, I, w->act, x_rows, T, 128, 0);
       ok &= gemm_plan(&pp->gate_up[l], lw.w_gate_up, 2 * I, I, H, w->x, x_rows, T, EPI_SILU_BF16, w->act, I, 1, 0, I,
-                      nullptr, getenv("MQ_GU_ROWS") ? atoi(getenv("MQ_GU_ROWS")) : gemm_balanced_rows(I));
+                      nullptr, gemm_balanced_rows(I));
       if (!ok) {
         set_last_error("decode-chain plan failed (layer %d, T=%d)", l, T);
         return MQ_ERR_CUDA;
@@ -284,7 +284,7 @@ static int build_plans(mq_worker* w, PassPlans* pp, int T, bool decode) {
   }
   pp->qkv.resize(c.n_layers); pp->o.resize(c.n_layers); pp->gate_up.resize(c.n_layers); pp->down.resize(c.n_layers);
   // ---- prefill with the RMSNorm fold: servable when all four GEMMs run on the persistent 2-CTA kernel
-  if (!decode && w->chain && T > 128 && !(getenv("MQ_PREFILL_FOLD") && getenv("MQ_PREFILL_FOLD")[0] == '0')) {
+  if (!decode && w->chain && T > 128) {
     const RstdIn rs_o{w->ssq_o, tiles_h, w->ssq_stride, 1.0f / (float)H, c.rms_eps};
     const RstdIn rs_d{w->ssq_d, tiles_h, w->ssq_stride, 1.0f / (float)H, c.rms_eps};
     const RstdIn rs_e{w->ssq_e, 1, w->ssq_stride, 1.0f / (float)H, c.rms_eps};

@@ -342,9 +342,6 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
     if (gm2 > g->c2.m_tiles) gm2 = g->c2.m_tiles;
     g->c2.group_m = gm2 < 1 ? 1 : gm2;
     g->c2.n_pairs = std::min(pairs, g->c2.m_tiles * g->c2.n_tiles);
-    if (const char* e = getenv("MQ_C2_PERSIST")) {  // A/B: 0 = one tile per CTA pair (the round-1 grid shape)
-      if (e[0] == '0') g->c2.n_pairs = g->c2.m_tiles * g->c2.n_tiles;
-    }
     g->c2.w_policy = g->p.w_policy;
   }
   g->persist = false;

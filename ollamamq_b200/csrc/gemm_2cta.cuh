@@ -258,7 +258,14 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       float gm = 0.f;
-      if constexpr (EPI == EPI_RESID) gm = __bfloat162float(p.gamma_next[f]);
+      float hnext[16];  // EPI_RESID: residual values of the chunk about to be processed
+      if constexpr (EPI == EPI_RESID) {
+        gm = __bfloat162float(p.gamma_next[f]);
+        const int c0 = chalf * (BN / 2);
+        const float* hp = reinterpret_cast<const float*>(p.out) + (size_t)(n0 + c0) * p.ldo + f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hnext[j] = (n0 + c0 + j < p.T) ? hp[(size_t)j * p.ldo] : 0.f;
+      }
       mbar_wait(&tfull_bar[buf], use & 1);
       tc_fence_after();
       const uint32_t t_lane = tmem_base + (uint32_t)(buf * ACC_COLS) + (static_cast<uint32_t>(q * 32) << 16);
@@ -290,9 +297,19 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float* hp = reinterpret_cast<float*>(p.out) + (size_t)(n0 + c0) * p.ldo + f;
           float hv[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) hv[j] = (n0 + c0 + j < p.T) ? hp[(size_t)j * p.ldo] : 0.f;  // all loads before the first use
+          for (int j = 0; j < 16; ++j) hv[j] = hnext[j];
+          // the residual rows of the NEXT chunk are requested before this one is touched: one L2 round trip per
+          // chunk on the critical path made this epilogue slower than the kernel it replaces
+          {
+            const int c1 = c0 + 16;
+            const float* hn = hp + (size_t)16 * p.ldo;
+            const bool more = c1 < (chalf + 1) * (BN / 2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hnext[j] = (more && n0 + c1 + j < p.T) ? hn[(size_t)j * p.ldo] : 0.f;
+          }
           tmem_ld_wait();
           __nv_bfloat16* xp = p.xg + (size_t)(n0 + c0) * p.ldx + f;
+          float sq[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const bool ok = n0 + c0 + j < p.T;
@@ -301,8 +318,38 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               hp[(size_t)j * p.ldo] = hv[j];
               xp[(size_t)j * p.ldx] = __float2bfloat16(hv[j] * gm);
             }
-            const float ss = warp_sum(hv[j] * hv[j]);  // over this warp's 32 features, fixed order
-            if (lane == 0) ssq_s[q * 256 + c0 + j] = ss;
+            sq[j] = hv[j] * hv[j];
+          }
+          // 16 column sums over the warp's 32 features with 16 + 15 shuffles instead of 80: at every step a lane keeps
+          // half of its values and receives the partner's other half (fixed pattern: deterministic, slot-independent)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const bool up = lane & 16;
+            const float send = up ? sq[j] : sq[j + 8], keep = up ? sq[j + 8] : sq[j];
+            sq[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const bool up = lane & 8;
+            const float send = up ? sq[j] : sq[j + 4], keep = up ? sq[j + 4] : sq[j];
+            sq[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const bool up = lane & 4;
+            const float send = up ? sq[j] : sq[j + 2], keep = up ? sq[j + 2] : sq[j];
+            sq[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+          }
+          {
+            const bool up = lane & 2;
+            const float send = up ? sq[0] : sq[1], keep = up ? sq[1] : sq[0];
+            sq[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+          }
+          sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
+          // lane l now holds the sum of column ((l >> 4) & 1) * 8 + ((l >> 3) & 1) * 4 + ((l >> 2) & 1) * 2 + ((l >> 1) & 1)
+          if ((lane & 1) == 0) {
+            const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            ssq_s[q * 256 + c0 + col] = sq[0];
           }
         } else {
           tmem_ld_wait();
