@@ -74,6 +74,32 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
         "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+// 32 consecutive fp32 columns per thread in one instruction (the softmax warps issue two of these per wait: a
+// tcgen05.ld + wait round trip is ~250 cycles, and 24 of them per KV tile made the first version 5 us per tile)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, "
+      "%26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, "
+      "%27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+        "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+        "r"(v[30]), "r"(v[31])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // MN-major operand, 128-byte swizzle: rows along K are 128 B apart, 8-row groups SBO apart, the two 64-element halves
 // of the MN extent LBO apart (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units)
@@ -210,46 +236,44 @@ __global__ void __launch_bounds__(192, 1) prefill_attn_tc_kernel(const __grid_co
       const bool edge = t0 + kTcKv > qpos + 1;             // some column of this tile is masked for this row
       mbar_wait(&s_full[s], (j >> 1) & 1);
       tc_fence_after();
-      // pass 1: row maximum
+      // pass 1: row maximum (64 columns per TMEM round trip)
       float mx = -INFINITY;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kTcKv; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_lane + (uint32_t)(s * 128 + c0), v);
+      for (int c0 = 0; c0 < kTcKv; c0 += 64) {
+        uint32_t v[64];
+        tmem_ld32(t_lane + (uint32_t)(s * 128 + c0), v);
+        tmem_ld32(t_lane + (uint32_t)(s * 128 + c0 + 32), v + 32);
         tmem_ld_wait();
+        if (!edge) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float x = __uint_as_float(v[i]);
-          mx = fmaxf(mx, (!edge || t0 + c0 + i <= qpos) ? x : -INFINITY);
+          for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) mx = fmaxf(mx, t0 + c0 + i <= qpos ? __uint_as_float(v[i]) : -INFINITY);
         }
       }
       const float m_new = fmaxf(m_run, mx * p.scale_log2);  // finite: column t0 <= qpos for every tile this row walks
       const float alpha = exp2f(m_run - m_new);
-      // pass 2: probabilities -> packed bf16 into the first 64 columns of the same buffer
+      // pass 2: probabilities -> packed bf16 into the first 64 columns of the same buffer (columns already consumed)
       float lsum = 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kTcKv; c0 += 32) {
-        uint32_t a[16], b[16], pk[16];
-        tmem_ld16(t_lane + (uint32_t)(s * 128 + c0), a);
-        tmem_ld16(t_lane + (uint32_t)(s * 128 + c0 + 16), b);
+      for (int c0 = 0; c0 < kTcKv; c0 += 64) {
+        uint32_t v[64], pk[32];
+        tmem_ld32(t_lane + (uint32_t)(s * 128 + c0), v);
+        tmem_ld32(t_lane + (uint32_t)(s * 128 + c0 + 32), v + 32);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float p0 = exp2f(__uint_as_float(a[2 * i]) * p.scale_log2 - m_new);
-          float p1 = exp2f(__uint_as_float(a[2 * i + 1]) * p.scale_log2 - m_new);
-          float p2 = exp2f(__uint_as_float(b[2 * i]) * p.scale_log2 - m_new);
-          float p3 = exp2f(__uint_as_float(b[2 * i + 1]) * p.scale_log2 - m_new);
+        for (int i = 0; i < 32; ++i) {
+          float p0 = exp2f(__uint_as_float(v[2 * i]) * p.scale_log2 - m_new);
+          float p1 = exp2f(__uint_as_float(v[2 * i + 1]) * p.scale_log2 - m_new);
           if (edge) {
             if (t0 + c0 + 2 * i > qpos) p0 = 0.f;
             if (t0 + c0 + 2 * i + 1 > qpos) p1 = 0.f;
-            if (t0 + c0 + 16 + 2 * i > qpos) p2 = 0.f;
-            if (t0 + c0 + 16 + 2 * i + 1 > qpos) p3 = 0.f;
           }
-          lsum += (p0 + p1) + (p2 + p3);
+          lsum += p0 + p1;
           pk[i] = pack_bf16(p0, p1);
-          pk[8 + i] = pack_bf16(p2, p3);
         }
-        tmem_st16(t_lane + (uint32_t)(s * 128 + c0 / 2), pk);  // 32 probabilities = 16 packed columns
+        tmem_st32(t_lane + (uint32_t)(s * 128 + c0 / 2), pk);  // 64 probabilities = 32 packed columns
       }
       tmem_st_wait();
       tc_fence_before();
@@ -261,12 +285,13 @@ __global__ void __launch_bounds__(192, 1) prefill_attn_tc_kernel(const __grid_co
       mbar_wait(o_full, j & 1);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < kTcD; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(t_lane + (uint32_t)(256 + c0), v);
+      for (int c0 = 0; c0 < kTcD; c0 += 64) {
+        uint32_t v[64];
+        tmem_ld32(t_lane + (uint32_t)(256 + c0), v);
+        tmem_ld32(t_lane + (uint32_t)(256 + c0 + 32), v + 32);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[c0 + i] = o[c0 + i] * alpha + __uint_as_float(v[i]);
+        for (int i = 0; i < 64; ++i) o[c0 + i] = o[c0 + i] * alpha + __uint_as_float(v[i]);
       }
       tc_fence_before();
       __syncwarp();
