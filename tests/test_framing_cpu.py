@@ -95,3 +95,39 @@ def test_parsers_survive_well_formed_json_of_any_shape(obj):
     assert isinstance(parse(1, body)["ok"], bool)
     out = parse_embed(body)
     assert isinstance(out["ok"], bool) and all(isinstance(s, list) for s in out["seqs"])
+
+
+def test_round1_advisor_inputs_fail_fast_instead_of_hanging_or_crashing():
+    """The two inputs of ADVICE.md (round 1): a value position holding '}' used to spin the parser forever, and a body
+    nested two million levels deep used to overflow the stack.  Both now return ok = false at once; so do near misses."""
+    import time
+    t0 = time.time()
+    assert not parse(1, b'{"messages":[{"content":[}')["ok"]
+    assert not parse(1, b'{"x":' + b"[" * 2_000_000)["ok"]
+    assert not parse(1, b'{"x":' + b'{"a":' * 500_000)["ok"]
+    assert not parse_embed(b'{"input":' + b"[" * 1_000_000)["ok"]
+    for bad in (b'{"a":}', b'{"a":1 "b":2}', b'{"a":[1 2]}', b'{"a":[1,]}', b'{"a":1,}', b'{"a":1}x', b'{"a":"\\u12G4"}',
+                b'{"a":"\\q"}', b'{"messages":[{"content":[{"text":}]}]}', b'{,}', b'{"a"}', b'{"a":nul'):
+        assert not parse(0, bad)["ok"], bad
+    assert time.time() - t0 < 5.0
+    # depth 64 is the limit; 60 levels of a skipped value still parse
+    assert parse(0, b'{"x":' + b"[" * 60 + b"]" * 60 + b',"prompt":"ok"}')["ok"]
+    assert not parse(0, b'{"x":' + b"[" * 70 + b"]" * 70 + b"}")["ok"]
+
+
+def test_numbers_are_clamped_before_they_are_narrowed():
+    p = parse(0, b'{"prompt":"a","options":{"num_predict":1e300,"top_k":1e300,"seed":-5,"temperature":-3,"top_p":7}}')
+    assert p["ok"] and p["num_predict"] == 1073741824 and p["top_k"] == 1073741824 and p["seed"] == 0
+    assert p["temperature"] == 0 and p["top_p"] == 1
+    p = parse(0, b'{"prompt":"a","options":{"num_predict":nan,"temperature":inf}}')     # not JSON numbers: skipped as bare words
+    assert p["ok"] and p["num_predict"] == 0 and not p["has_temperature"]
+    p = parse(0, b'{"prompt":[1e300,-1e300,3]}')
+    assert p["ok"] and p["tokens"] == [2147483647, -2147483647, 3]   # clamped, not UB; mq_submit maps ids outside the vocabulary to 0
+
+
+def test_unicode_escapes_and_long_model_names():
+    p = parse(0, '{"prompt":"\\ud83d\\ude00é\\u00e9"}'.encode())
+    assert p["ok"] and bytes(p["tokens"]) == "\U0001F600éé".encode()   # surrogate pair combined: valid UTF-8
+    f = _call(mq.lib.mq_debug_frame_final, 1, 0, b"m" * 5000, b"x", 1, 1, 0)
+    j = json.loads(f)                                                  # a 5 000-byte model name no longer truncates the frame
+    assert j["done"] and len(j["model"]) == 256

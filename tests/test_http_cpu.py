@@ -278,3 +278,16 @@ def test_a_thousand_connections_on_one_loop():
             sk.close()
     finally:
         s.close()
+
+
+def test_malformed_json_body_is_a_400_and_dispatch_goes_on(srv):
+    """ADVICE.md (round 1): `{"messages":[{"content":[}` froze the scheduler thread for every user and GPU.  The body is now
+    parsed on the connection thread; the request still takes its fair-share turn and is answered like a backend would
+    answer it (400 + an error object, counted as processed, :314-316), and the next request is served."""
+    st, _, body = srv.request("POST", "/api/chat", b'{"messages":[{"content":[}', {"X-User-ID": "mallory"})
+    assert st == 400 and json.loads(body)["error"]
+    st, _, body = srv.request("POST", "/api/chat", b'{"x":' + b"[" * 200000, {"X-User-ID": "mallory"})
+    assert st == 400
+    assert srv.d.user_stats("mallory")["processed"] == 2
+    st, _, data = srv.request("POST", "/api/chat", b'{"messages":[{"role":"user","content":"hi"}]}', {"X-User-ID": "alice"})
+    assert st == 200 and data.startswith(b'{"tok":0}')
