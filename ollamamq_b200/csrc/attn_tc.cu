@@ -3,22 +3,25 @@
 // BASELINE.json north_star: "prefill as tcgen05 tensor-core GEMMs fed by TMA into shared memory".  Round 1 ran prefill
 // attention on the legacy mma.sync pipe (33 % tensor-active, 7.4 % of a prefill pass).
 //
-// One CTA per (query tile, kv head).  A query tile is 128 rows = 128/G tokens x the G query heads of the GQA group
+// One CTA per (query tile, kv head), TWO CTAs resident per SM (96 KB of shared memory, 256 TMEM columns, <= 168
+// registers each): inside a CTA the tensor pipe and the softmax warps alternate, and the SM overlaps the MMAs of one CTA
+// with the exponentials of the other.  A query tile is 128 rows = 128/G tokens x the G query heads of the GQA group
 // (row = token * G + head), so K / V tiles are shared by the whole group.  Per 128-token KV tile j:
 //
-//   warp 0 (one thread)   TMA: the 8 pages of K and V of the tile, each page = one 16 x 128 block of the paged cache,
-//                         fetched as two {64 d, 16 token} boxes with the 128-byte swizzle -> [128 tokens][64 d] x 2
-//                         sub-tiles = the canonical K-major (K) / MN-major (V) UMMA operand layouts; Q once, as
-//                         {64 d, G heads, 128/G tokens} boxes of the [T][n_q][128] activation
-//   warp 1 (one thread)   S[j & 1] = Q . K_j^T          tcgen05.mma, A and B from shared memory, fp32 in TMEM
-//                         O_j      = P[j & 1] . V_j     tcgen05.mma, A = P from TENSOR MEMORY (bf16), B = V MN-major
+//   warp 0 (one thread)   TMA: the 8 pages of K and of V of the tile (separate single-stage buffers, each refilled as soon
+//                         as its MMA retires), each page = one 16 x 128 block of the paged cache fetched as two
+//                         {64 d, 16 token} boxes with the 128-byte swizzle -> [128 tokens][64 d] x 2 sub-tiles = the
+//                         canonical K-major (K) / MN-major (V) UMMA operand layouts; Q once, as {64 d, G heads,
+//                         128/G tokens} boxes of the [T][n_q][128] activation
+//   warp 1 (one thread)   S  = Q . K_j^T     tcgen05.mma, A and B from shared memory, fp32 in TMEM
+//                         O += P . V_j       tcgen05.mma, A = P from TENSOR MEMORY (bf16), B = V MN-major; O stays in TMEM
 //   warps 2-5 (128 thr)   one query row per thread (TMEM lane = row: no shuffles anywhere): two passes over its 128
 //                         scores (row max, then p = exp2(s - m)), P written back into the S buffer's first 64 columns
-//                         as packed bf16 (tcgen05.st), then O_j is pulled out of TMEM and folded into the fp32
-//                         accumulator in registers: o = o * exp2(m_old - m_new) + O_j
+//                         as packed bf16 (tcgen05.st).  The running maximum is only raised - and the O row in TMEM
+//                         rescaled by exp2(m_old - m_new) - when a warp sees a score more than 2^8 above it (the
+//                         probabilities then stay below 256: exact in fp32 sums, 8 bits of headroom in bf16).
 //
-// S / P are double-buffered so the tensor cores compute S_{j+1} while the softmax warps work on tile j.
-// TMEM: columns [0,128) S0/P0, [128,256) S1/P1, [256,384) O_j.
+// TMEM: columns [0,128) S / P, [128,256) O.
 #include "kernels.cuh"
 #include "gemm.cuh"
 #include <cudaTypedefs.h>
