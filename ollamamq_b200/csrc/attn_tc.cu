@@ -33,7 +33,8 @@ constexpr int kTcRows = 128;       // query rows per CTA
 constexpr int kTcKv = 128;         // kv tokens per tile (8 pages)
 constexpr int kTcD = 128;          // head_dim
 constexpr int kTcSub = 128 * 128;  // bytes of one [128 rows][64 elements] bf16 sub-tile
-constexpr int kTcSmem = 2 * kTcSub /*Q*/ + 2 * (2 * kTcSub /*K*/ + 2 * kTcSub /*V*/) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kTcSmem = 2 * kTcSub /*Q*/ + 2 * kTcSub /*K*/ + 2 * kTcSub /*V*/ + 1024 /*align*/ + 256 /*barriers*/;  // 97.25 KB
+constexpr float kTcRescale = 8.f;  // log2 units: raise the running maximum only when a score tops it by more than 2^8
 
 struct AttnTcParams {
   CUtensorMap tmQ;   // [T][n_q][128] bf16: box {64, G, 128 / G}
@@ -103,6 +104,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
         "r"(v[30]), "r"(v[31])
       : "memory");
 }
+// one MUFU.EX2: exp2f() adds a range check and two multiplies per element for denormal results, which flush to zero here
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // MN-major operand, 128-byte swizzle: rows along K are 128 B apart, 8-row groups SBO apart, the two 64-element halves
 // of the MN extent LBO apart (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units)
@@ -119,20 +126,22 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_bmn(uint32_t M, uint32_t 
   return umma_idesc_bf16(M, N) | (1u << 16);
 }
 
-__global__ void __launch_bounds__(192, 1) prefill_attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
+__global__ void __launch_bounds__(192, 2) prefill_attn_tc_kernel(const __grid_constant__ AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* Qs = smem;                      // 2 sub-tiles
-  uint8_t* KVs = smem + 2 * kTcSub;        // stage s: K sub0, K sub1, V sub0, V sub1
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kTcSub + 2 * 4 * kTcSub);
-  uint64_t* q_full = bars;                 // [1]
-  uint64_t* kv_full = bars + 1;            // [2]
-  uint64_t* kv_empty = bars + 3;           // [2]
-  uint64_t* s_full = bars + 5;             // [2]
-  uint64_t* p_full = bars + 7;             // [2] count 4 (one per softmax warp)
-  uint64_t* o_full = bars + 9;             // [1]
-  uint64_t* o_empty = bars + 10;           // [1] count 4
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint8_t* Qs = smem;                      // 2 sub-tiles each
+  uint8_t* Ks = smem + 2 * kTcSub;
+  uint8_t* Vs = smem + 4 * kTcSub;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * kTcSub);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 2;
+  uint64_t* v_full = bars + 3;
+  uint64_t* v_empty = bars + 4;
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;             // count 4 (one per softmax warp)
+  uint64_t* o_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kvh = blockIdx.y;
@@ -147,22 +156,15 @@ __global__ void __launch_bounds__(192, 1) prefill_attn_tc_kernel(const __grid_co
     tma_prefetch_desc(&p.tmQ);
     tma_prefetch_desc(&p.tmK);
     tma_prefetch_desc(&p.tmV);
-    mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
-    }
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, 4);
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], i == 6 ? 4 : 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) tmem_alloc<256>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_o = tmem_base + 128;
   pdl_launch_dependents();
   pdl_wait();  // q and this pass's K / V rows come from the rope kernel
 
@@ -173,19 +175,20 @@ __global__ void __launch_bounds__(192, 1) prefill_attn_tc_kernel(const __grid_co
       // rows >= ntok * G of the tile belong to other sequences (or lie past T): they are computed and never stored
       tma_load_3d(Qs, &p.tmQ, q_full, 0, kvh * G, tok0);
       tma_load_3d(Qs + kTcSub, &p.tmQ, q_full, 64, kvh * G, tok0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        if (j >= 2) mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
-        uint8_t* st = KVs + s * 4 * kTcSub;
-        mbar_expect_tx(&kv_full[s], 4 * kTcSub);
+      auto load = [&](const CUtensorMap* tm, uint8_t* dst, uint64_t* bar, int j) {
+        mbar_expect_tx(bar, 2 * kTcSub);
         for (int pg = 0; pg < kTcKv / kPageSize; ++pg) {
           const int t = j * kTcKv + pg * kPageSize;
           const int page = t < kv_end ? btab[t / kPageSize] : 0;  // past the end: the scratch page (masked below)
-          tma_load_4d(st + pg * 2048, &p.tmK, &kv_full[s], 0, 0, kvh, page);
-          tma_load_4d(st + kTcSub + pg * 2048, &p.tmK, &kv_full[s], 64, 0, kvh, page);
-          tma_load_4d(st + 2 * kTcSub + pg * 2048, &p.tmV, &kv_full[s], 0, 0, kvh, page);
-          tma_load_4d(st + 3 * kTcSub + pg * 2048, &p.tmV, &kv_full[s], 64, 0, kvh, page);
+          tma_load_4d(dst + pg * 2048, tm, bar, 0, 0, kvh, page);
+          tma_load_4d(dst + kTcSub + pg * 2048, tm, bar, 64, 0, kvh, page);
         }
+      };
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j >= 1) mbar_wait(k_empty, (j - 1) & 1);   // S_{j-1} = Q K_{j-1}^T has retired
+        load(&p.tmK, Ks, k_full, j);
+        if (j >= 1) mbar_wait(v_empty, (j - 1) & 1);   // O += P_{j-1} V_{j-1} has retired
+        load(&p.tmV, Vs, v_full, j);
       }
     }
   } else if (warp == 1) {
@@ -193,34 +196,28 @@ __global__ void __launch_bounds__(192, 1) prefill_attn_tc_kernel(const __grid_co
       // ---------------- MMA issuer ----------------
       constexpr uint32_t IDESC_S = umma_idesc_bf16(kTcRows, kTcKv);     // S = Q K^T: both operands K-major
       constexpr uint32_t IDESC_O = umma_idesc_bf16_bmn(kTcRows, kTcD);  // O = P V: V is MN-major
-      const uint32_t q_addr = smem_u32(Qs);
-      auto mma_s = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&kv_full[s], (j >> 1) & 1);
+      const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(k_full, j & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(KVs + s * 4 * kTcSub);
+        // (the S / P columns are free: P_{j-1} V_{j-1} was issued before this and the pipe runs in order)
 #pragma unroll
         for (int k = 0; k < kTcD / 16; ++k) {  // 8 k-steps over d: 4 per 64-wide sub-tile
           const uint32_t off = (uint32_t)(k >> 2) * kTcSub + (uint32_t)(k & 3) * 32;
-          umma_bf16(tmem_base + (uint32_t)(s * 128), umma_desc_sw128(q_addr + off), umma_desc_sw128(k_addr + off), IDESC_S, k != 0);
+          umma_bf16(tmem_base, umma_desc_sw128(q_addr + off), umma_desc_sw128(k_addr + off), IDESC_S, k != 0);
         }
-        umma_commit(&s_full[s]);
-      };
-      mbar_wait(q_full, 0);
-      mma_s(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        if (j + 1 < n_tiles) mma_s(j + 1);                 // the tensor cores run ahead of the softmax warps
-        mbar_wait(&p_full[s], (j >> 1) & 1);               // P_j is in TMEM
-        if (j > 0) mbar_wait(o_empty, (j - 1) & 1);        // O_{j-1} has been folded into the registers
+        umma_commit(s_full);   // also tells the softmax warps that O holds every earlier P V (commit covers all prior MMAs)
+        umma_commit(k_empty);
+        mbar_wait(p_full, j & 1);                          // P_j is in TMEM (and O has been rescaled if it had to be)
+        mbar_wait(v_full, j & 1);
         tc_fence_after();
-        const uint32_t v_addr = smem_u32(KVs + s * 4 * kTcSub + 2 * kTcSub);
 #pragma unroll
         for (int k = 0; k < kTcKv / 16; ++k)               // 8 k-steps over the kv tokens: 16 rows = 2 KB each
-          umma_bf16_ts(tmem_base + 256, tmem_base + (uint32_t)(s * 128 + k * 8), umma_desc_sw128_mn(v_addr + k * 2048, kTcSub), IDESC_O,
-                       k != 0);
-        umma_commit(o_full);
-        umma_commit(&kv_empty[s]);
+          umma_bf16_ts(tmem_o, tmem_base + (uint32_t)(k * 8), umma_desc_sw128_mn(v_addr + k * 2048, kTcSub), IDESC_O,
+                       (j | k) != 0);
+        umma_commit(v_empty);
+        if (j + 1 == n_tiles) umma_commit(o_full);
       }
     }
   } else {
@@ -228,96 +225,117 @@ __global__ void __launch_bounds__(192, 1) prefill_attn_tc_kernel(const __grid_co
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t_o = t_lane + 128;
     const int qpos = pos0 + row / G;
-    float o[kTcD];
-#pragma unroll
-    for (int i = 0; i < kTcD; ++i) o[i] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
-      const int s = j & 1;
       const int t0 = j * kTcKv;
       const bool edge = t0 + kTcKv > qpos + 1;             // some column of this tile is masked for this row
-      mbar_wait(&s_full[s], (j >> 1) & 1);
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
+      // the diagonal tile masks columns per row; every other tile takes the unmasked loops (warp-uniform choice)
+      const bool edge_w = __any_sync(0xffffffffu, edge);
+      const int lim = qpos - t0;                          // columns <= lim are visible to this row
       // pass 1: row maximum (64 columns per TMEM round trip)
       float mx = -INFINITY;
 #pragma unroll 1
       for (int c0 = 0; c0 < kTcKv; c0 += 64) {
         uint32_t v[64];
-        tmem_ld32(t_lane + (uint32_t)(s * 128 + c0), v);
-        tmem_ld32(t_lane + (uint32_t)(s * 128 + c0 + 32), v + 32);
+        tmem_ld32(t_lane + (uint32_t)c0, v);
+        tmem_ld32(t_lane + (uint32_t)(c0 + 32), v + 32);
         tmem_ld_wait();
-        if (!edge) {
+        if (!edge_w) {
 #pragma unroll
-          for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 64; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
         } else {
 #pragma unroll
-          for (int i = 0; i < 64; ++i) mx = fmaxf(mx, t0 + c0 + i <= qpos ? __uint_as_float(v[i]) : -INFINITY);
+          for (int i = 0; i < 64; ++i) mx = fmaxf(mx, c0 + i <= lim ? __uint_as_float(v[i]) : -INFINITY);
         }
       }
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);  // finite: column t0 <= qpos for every tile this row walks
-      const float alpha = exp2f(m_run - m_new);
+      mx *= p.scale_log2;   // finite: column t0 <= qpos for every tile this row walks
+      // raise the running maximum (and rescale the O row in TMEM) only when some row of this warp needs it
+      const bool raise = __any_sync(0xffffffffu, mx > m_run + kTcRescale);
+      if (raise) {
+        const float m_new = fmaxf(m_run, mx);
+        const float alpha = ex2_ftz(m_run - m_new);        // 0 on the first tile (m_run = -inf): O is not read then
+        m_run = m_new;
+        l_run *= alpha;
+        if (j > 0) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < kTcD; c0 += 64) {
+            uint32_t v[64];
+            tmem_ld32(t_o + (uint32_t)c0, v);
+            tmem_ld32(t_o + (uint32_t)(c0 + 32), v + 32);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st32(t_o + (uint32_t)c0, v);
+            tmem_st32(t_o + (uint32_t)(c0 + 32), v + 32);
+          }
+        }
+      }
       // pass 2: probabilities -> packed bf16 into the first 64 columns of the same buffer (columns already consumed)
       float lsum = 0.f;
 #pragma unroll 1
       for (int c0 = 0; c0 < kTcKv; c0 += 64) {
         uint32_t v[64], pk[32];
-        tmem_ld32(t_lane + (uint32_t)(s * 128 + c0), v);
-        tmem_ld32(t_lane + (uint32_t)(s * 128 + c0 + 32), v + 32);
+        tmem_ld32(t_lane + (uint32_t)c0, v);
+        tmem_ld32(t_lane + (uint32_t)(c0 + 32), v + 32);
         tmem_ld_wait();
+        if (!edge_w) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float p0 = exp2f(__uint_as_float(v[2 * i]) * p.scale_log2 - m_new);
-          float p1 = exp2f(__uint_as_float(v[2 * i + 1]) * p.scale_log2 - m_new);
-          if (edge) {
-            if (t0 + c0 + 2 * i > qpos) p0 = 0.f;
-            if (t0 + c0 + 2 * i + 1 > qpos) p1 = 0.f;
+          for (int i = 0; i < 32; ++i) {
+            const float p0 = ex2_ftz(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_run));
+            const float p1 = ex2_ftz(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m_run));
+            lsum += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
           }
-          lsum += p0 + p1;
-          pk[i] = pack_bf16(p0, p1);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float p0 = ex2_ftz(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m_run));
+            float p1 = ex2_ftz(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m_run));
+            if (c0 + 2 * i > lim) p0 = 0.f;
+            if (c0 + 2 * i + 1 > lim) p1 = 0.f;
+            lsum += p0 + p1;
+            pk[i] = pack_bf16(p0, p1);
+          }
         }
-        tmem_st32(t_lane + (uint32_t)(s * 128 + c0 / 2), pk);  // 64 probabilities = 32 packed columns
+        tmem_st32(t_lane + (uint32_t)(c0 / 2), pk);  // 64 probabilities = 32 packed columns
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[s]);
-      l_run = l_run * alpha + lsum;
-      m_run = m_new;
-      // O_j: fold into the register accumulator
-      mbar_wait(o_full, j & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < kTcD; c0 += 64) {
-        uint32_t v[64];
-        tmem_ld32(t_lane + (uint32_t)(256 + c0), v);
-        tmem_ld32(t_lane + (uint32_t)(256 + c0 + 32), v + 32);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 64; ++i) o[c0 + i] = o[c0 + i] * alpha + __uint_as_float(v[i]);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty);
+      if (lane == 0) mbar_arrive(p_full);
+      l_run += lsum;
     }
     // ---- normalise and store this row (256 contiguous bytes)
-    if (row < ntok * G) {
-      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      __nv_bfloat16* po = p.out + ((size_t)(tok0 + row / G) * p.n_q + kvh * G + row % G) * kTcD;
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    __nv_bfloat16* po = p.out + ((size_t)(tok0 + row / G) * p.n_q + kvh * G + row % G) * kTcD;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kTcD; c0 += 64) {
+      uint32_t v[64];
+      tmem_ld32(t_o + (uint32_t)c0, v);
+      tmem_ld32(t_o + (uint32_t)(c0 + 32), v + 32);
+      tmem_ld_wait();
+      if (row < ntok * G) {
 #pragma unroll
-      for (int c0 = 0; c0 < kTcD; c0 += 8) {
-        uint4 w;
-        w.x = pack_bf16(o[c0] * inv, o[c0 + 1] * inv);
-        w.y = pack_bf16(o[c0 + 2] * inv, o[c0 + 3] * inv);
-        w.z = pack_bf16(o[c0 + 4] * inv, o[c0 + 5] * inv);
-        w.w = pack_bf16(o[c0 + 6] * inv, o[c0 + 7] * inv);
-        *reinterpret_cast<uint4*>(po + c0) = w;
+        for (int i = 0; i < 64; i += 8) {
+          uint4 w;
+          w.x = pack_bf16(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+          w.y = pack_bf16(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+          w.z = pack_bf16(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+          w.w = pack_bf16(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+          *reinterpret_cast<uint4*>(po + c0 + i) = w;
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc<512>(tmem_base);
+  if (warp == 1) tmem_dealloc<256>(tmem_base);
 }
 
 // ------------------------------------------------------------------------------------------------ host
