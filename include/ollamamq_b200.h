@@ -254,6 +254,7 @@ typedef struct mq_encoder_cfg {
 } mq_encoder_cfg;
 typedef struct mq_encoder_stats {
   uint64_t passes, sequences, tokens, kernel_launches;
+  uint64_t gpu_us; /* device time of the passes (CUDA events on the worker's stream around each pass), microseconds */
 } mq_encoder_stats;
 int mq_encoder_open(int32_t gpu, const mq_encoder_cfg* cfg, mq_encoder** out); /* MQ_ERR_NODEV without sm_100 */
 void mq_encoder_close(mq_encoder* e);

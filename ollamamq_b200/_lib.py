@@ -57,7 +57,7 @@ class EncoderCfg(C.Structure):
 
 class EncoderStats(C.Structure):
     _fields_ = [("passes", C.c_uint64), ("sequences", C.c_uint64), ("tokens", C.c_uint64),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("gpu_us", C.c_uint64)]
 
 
 class Request(C.Structure):

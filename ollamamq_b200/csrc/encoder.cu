@@ -61,6 +61,8 @@ struct mq_encoder {
   // activations
   float *h = nullptr, *d_out = nullptr;
   __nv_bfloat16 *x = nullptr, *qkv = nullptr, *attn = nullptr, *sub = nullptr, *act = nullptr;
+  CUtensorMap tm_qkv{};   // tcgen05 attention: {32 d, 64 rows} boxes of the packed q | k | v activation
+  bool attn_tc = false;
   int* d_meta = nullptr;  // tok | pos | first_tok | seq_len | tiles
   int* h_meta = nullptr;                            // pinned mirror
   float* h_out = nullptr;                           // pinned [max_seqs][H]
@@ -72,7 +74,8 @@ struct mq_encoder {
   std::deque<EncJob*> queue;
   bool stop = false;
   std::atomic<bool> healthy{true};
-  std::atomic<uint64_t> passes{0}, sequences{0}, tokens{0}, launches{0};
+  std::atomic<uint64_t> passes{0}, sequences{0}, tokens{0}, launches{0}, gpu_us{0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 };
 
 namespace {
@@ -128,6 +131,13 @@ int enc_setup(mq_encoder* e) {
   if ((rc = enc_alloc(&e->h, MT * H))) return rc;
   if ((rc = enc_alloc(&e->x, MT * H))) return rc;
   if ((rc = enc_alloc(&e->qkv, MT * 3 * H))) return rc;
+  // the tcgen05 attention loads whole 64-row boxes: rows past a pass's last token must hold finite values (they meet
+  // probabilities of exactly 0)
+  ENC_TRY(cudaMemset(e->qkv, 0, MT * 3 * H * sizeof(__nv_bfloat16)));
+  const char* tc_env = getenv("MQ_ENC_ATTN_TC");
+  e->attn_tc = enc_attn_tc_supported(c.head_dim, c.max_seq, H) && !(tc_env && tc_env[0] == '0') &&
+               enc_attn_tc_encode(&e->tm_qkv, e->qkv, (int)MT, H);
+  if (e->attn_tc) enc_attn_tc_set_attrs();
   if ((rc = enc_alloc(&e->attn, MT * H))) return rc;
   if ((rc = enc_alloc(&e->sub, MT * H))) return rc;
   if ((rc = enc_alloc(&e->act, MT * I))) return rc;
@@ -159,12 +169,20 @@ int enc_pass(mq_encoder* e, const std::vector<const std::vector<int32_t>*>& seqs
       m_tok[t + i] = id < 0 ? 0 : (id >= c.vocab ? c.vocab - 1 : id);
       m_pos[t + i] = i;
     }
-    for (int i = 0; i < len; i += kEncTileRows) {
-      int* tl = m_tiles + 4 * n_tiles++;
-      tl[0] = t + i; tl[1] = std::min(kEncTileRows, len - i); tl[2] = s; tl[3] = i;
+    if (e->attn_tc) {
+      for (int i = 0; i < len; i += kEncAttnItemRows) {
+        int* tl = m_tiles + 4 * n_tiles++;
+        tl[0] = t + i; tl[1] = std::min(kEncAttnItemRows, len - i); tl[2] = t; tl[3] = len;
+      }
+    } else {
+      for (int i = 0; i < len; i += kEncTileRows) {
+        int* tl = m_tiles + 4 * n_tiles++;
+        tl[0] = t + i; tl[1] = std::min(kEncTileRows, len - i); tl[2] = s; tl[3] = i;
+      }
     }
     t += len;
   }
+  ENC_TRY(cudaEventRecord(e->ev0, e->stream));
   ENC_TRY(cudaMemcpyAsync(e->d_meta, e->h_meta, e->meta_ints * 4, cudaMemcpyHostToDevice, e->stream));
   const int *d_tok = e->d_meta, *d_pos = d_tok + e->MT, *d_first = d_pos + e->MT;
   const int* d_len = d_first + e->max_seqs;
@@ -177,32 +195,48 @@ int enc_pass(mq_encoder* e, const std::vector<const std::vector<int32_t>*>& seqs
     const EncLayer& w = e->layers[l];
     GemmPlan g;
     if (!gemm_plan(&g, w.wqkv, 3 * H, 3 * H, H, e->x, e->MT, T, EPI_BIAS_BF16, e->qkv, 3 * H, 1, 0, 0)) return MQ_ERR_CUDA;
-    g.p.bias = w.bqkv;
+    gemm_plan_set_bias(&g, w.bqkv);
     if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;
-    AttnParams ap = {};
-    ap.head_dim = c.head_dim; ap.bidirectional = 1; ap.seq_len = d_len;
-    ap.seq_start = d_first; ap.row_stride = 3 * H;          // packed mode: q | k | v column blocks of e->qkv
-    ap.q = e->qkv; ap.k_cache = e->qkv + H; ap.v_cache = e->qkv + 2 * H;
-    ap.block_table = e->d_meta; ap.max_pages = 0;            // unused in packed mode
-    ap.tiles = d_tiles; ap.out = e->attn; ap.n_q = c.n_heads; ap.n_kv = c.n_heads;
-    ap.T = T; ap.n_splits = 1; ap.n_warps = 1;
-    ap.scale_log2 = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
-    launch_attn_prefill(lc, ap, n_tiles);
-    if (!gemm_plan(&g, w.wo, H, H, H, e->attn, e->MT, T, EPI_BF16, e->sub, H, 1, 0, 0)) return MQ_ERR_CUDA;
+    const float scale_log2 = (1.0f / sqrtf((float)c.head_dim)) * 1.4426950408889634f;
+    if (e->attn_tc) {
+      if (launch_enc_attn_tc(lc, e->tm_qkv, d_tiles, n_tiles, c.n_heads, H, e->attn, scale_log2) != cudaSuccess) {
+        set_last_error("encoder attention launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return MQ_ERR_CUDA;
+      }
+    } else {
+      AttnParams ap = {};
+      ap.head_dim = c.head_dim; ap.bidirectional = 1; ap.seq_len = d_len;
+      ap.seq_start = d_first; ap.row_stride = 3 * H;          // packed mode: q | k | v column blocks of e->qkv
+      ap.q = e->qkv; ap.k_cache = e->qkv + H; ap.v_cache = e->qkv + 2 * H;
+      ap.block_table = e->d_meta; ap.max_pages = 0;            // unused in packed mode
+      ap.tiles = d_tiles; ap.out = e->attn; ap.n_q = c.n_heads; ap.n_kv = c.n_heads;
+      ap.T = T; ap.n_splits = 1; ap.n_warps = 1;
+      ap.scale_log2 = scale_log2;
+      launch_attn_prefill(lc, ap, n_tiles);
+    }
+    if (!gemm_plan(&g, w.wo, H, H, H, e->attn, e->MT, T, EPI_BIAS_BF16, e->sub, H, 1, 0, 0)) return MQ_ERR_CUDA;  // (bias: in the LayerNorm kernel)
     if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;
-    launch_enc_add_ln(lc, e->h, e->sub, w.bo, w.attn_ln_g, w.attn_ln_b, e->x, T, H, c.ln_eps);
+    const bool ln_warp = enc_add_ln_warp_supported(H);
+    if (ln_warp) launch_enc_add_ln_warp(lc, e->x, e->sub, w.bo, w.attn_ln_g, w.attn_ln_b, nullptr, T, H, c.ln_eps);
+    else launch_enc_add_ln(lc, e->h, e->sub, w.bo, w.attn_ln_g, w.attn_ln_b, e->x, T, H, c.ln_eps);
     if (!gemm_plan(&g, w.w_up, I, I, H, e->x, e->MT, T, EPI_GELU_BF16, e->act, I, 1, 0, 0)) return MQ_ERR_CUDA;
-    g.p.bias = w.b_up;
+    gemm_plan_set_bias(&g, w.b_up);
     if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;
-    if (!gemm_plan(&g, w.w_down, H, H, I, e->act, e->MT, T, EPI_BF16, e->sub, H, 1, 0, 0)) return MQ_ERR_CUDA;
+    if (!gemm_plan(&g, w.w_down, H, H, I, e->act, e->MT, T, EPI_BIAS_BF16, e->sub, H, 1, 0, 0)) return MQ_ERR_CUDA;
     if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;
-    launch_enc_add_ln(lc, e->h, e->sub, w.b_down, w.mlp_ln_g, w.mlp_ln_b, e->x, T, H, c.ln_eps);
+    if (ln_warp)  // (the model's last LayerNorm also leaves an fp32 copy for the pooling kernel)
+      launch_enc_add_ln_warp(lc, e->x, e->sub, w.b_down, w.mlp_ln_g, w.mlp_ln_b, l + 1 == c.n_layers ? e->h : nullptr, T, H,
+                             c.ln_eps);
+    else launch_enc_add_ln(lc, e->h, e->sub, w.b_down, w.mlp_ln_g, w.mlp_ln_b, e->x, T, H, c.ln_eps);
     nl += 7;
   }
   launch_enc_pool(lc, e->h, d_first, e->d_out, n, H);
   ++nl;
   ENC_TRY(cudaMemcpyAsync(e->h_out, e->d_out, (size_t)n * H * 4, cudaMemcpyDeviceToHost, e->stream));
+  ENC_TRY(cudaEventRecord(e->ev1, e->stream));
   ENC_TRY(cudaStreamSynchronize(e->stream));
+  float pass_ms = 0.f;
+  if (cudaEventElapsedTime(&pass_ms, e->ev0, e->ev1) == cudaSuccess) e->gpu_us += (uint64_t)(pass_ms * 1e3f);
   e->passes++; e->sequences += n; e->tokens += T; e->launches += nl;
   return MQ_OK;
 }
@@ -308,6 +342,7 @@ int mq_encoder_open(int32_t gpu, const mq_encoder_cfg* cfg, mq_encoder** out) {
   gemm_set_attrs();
   attn_set_attrs();
   if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; return MQ_ERR_CUDA; }
+  if (cudaEventCreate(&e->ev0) != cudaSuccess || cudaEventCreate(&e->ev1) != cudaSuccess) { delete e; return MQ_ERR_CUDA; }
   int rc = enc_setup(e);
   if (rc) { mq_encoder_close(e); return rc; }
   e->thr = std::thread(enc_main, e);
@@ -329,6 +364,8 @@ void mq_encoder_close(mq_encoder* e) {
   for (void* b : bufs) if (b) cudaFree(b);
   if (e->h_meta) cudaFreeHost(e->h_meta);
   if (e->h_out) cudaFreeHost(e->h_out);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -435,6 +472,7 @@ int mq_encoder_get_stats(mq_encoder* e, mq_encoder_stats* out) {
   if (!e || !out) return MQ_ERR_INVAL;
   out->passes = e->passes.load(); out->sequences = e->sequences.load(); out->tokens = e->tokens.load();
   out->kernel_launches = e->launches.load();
+  out->gpu_us = e->gpu_us.load();
   return MQ_OK;
 }
 

@@ -131,7 +131,7 @@ template <int EPI>
 static cudaError_t launch_c2(const GemmPlan& g, const LaunchCfg& lc) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * g.c2.n_pairs);  // persistent pairs; cluster dims (2,1,1) are compiled into the kernel
-  cfg.blockDim = dim3(kC2Threads);
+  cfg.blockDim = dim3(c2_threads(EPI));
   cfg.dynamicSmemBytes = c2_smem_bytes(EPI);
   cfg.stream = lc.stream;
   cudaLaunchAttribute attr[1];
@@ -139,7 +139,7 @@ static cudaError_t launch_c2(const GemmPlan& g, const LaunchCfg& lc) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = lc.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gemm_2cta_kernel<EPI>, g.tmA, g.tmB, g.c2);
+  return cudaLaunchKernelEx(&cfg, gemm_2cta_kernel<EPI>, g.tmA, g.tmB, g.tmC, g.c2);
 }
 
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
@@ -148,6 +148,8 @@ cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc) {
       case EPI_BF16: return launch_c2<EPI_BF16>(g, lc);
       case EPI_SILU_BF16: return launch_c2<EPI_SILU_BF16>(g, lc);
       case EPI_RESID: return launch_c2<EPI_RESID>(g, lc);
+      case EPI_BIAS_BF16: return launch_c2<EPI_BIAS_BF16>(g, lc);
+      case EPI_GELU_BF16: return launch_c2<EPI_GELU_BF16>(g, lc);
       default: return cudaErrorInvalidValue;
     }
   if (g.persist) {
@@ -204,6 +206,8 @@ void gemm_set_attrs() {
   cudaFuncSetAttribute(gemm_2cta_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_BF16));
   cudaFuncSetAttribute(gemm_2cta_kernel<EPI_SILU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_SILU_BF16));
   cudaFuncSetAttribute(gemm_2cta_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_RESID));
+  cudaFuncSetAttribute(gemm_2cta_kernel<EPI_BIAS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_BIAS_BF16));
+  cudaFuncSetAttribute(gemm_2cta_kernel<EPI_GELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_GELU_BF16));
   cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_BF16));
   cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_F32));
   cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_BF16));
@@ -327,7 +331,11 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
   if (gm > g->p.m_tiles) gm = g->p.m_tiles;
   g->p.group_m = g->p.n_tiles == 1 ? g->p.m_tiles : gm;
   g->p.w_policy = g->p.n_tiles == 1 ? kEvictFirst : kEvictNormal;  // decode streams weights exactly once
-  g->twocta = !g->streamk && tile_rows == kBlockM && g->bn == 256 && splits == 1 && n_out % 256 == 0 && epi != EPI_GELU_BF16 && epi != EPI_BIAS_BF16 && twocta_enabled();
+  // a ragged last 256-feature tile is fine for the plain epilogues (stores are guarded); the dual / residual ones keep
+  // whole tiles (their per-128-feature partials are indexed by tile)
+  const bool whole = n_out % 256 == 0;
+  g->twocta = !g->streamk && tile_rows == kBlockM && g->bn == 256 && splits == 1 && twocta_enabled() &&
+              (whole || (epi != EPI_SILU_BF16 && epi != EPI_RESID && n_out % 8 == 0));
   if (g->twocta) {
     // the pair computes 256 features x c2_bn tokens: every CTA stages only its own half of the activation tile
     const int bn2 = c2_bn(epi);
@@ -335,7 +343,7 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
     g->c2 = TwoCtaParams{};
     g->c2.out = out; g->c2.ldo = ldo;
     g->c2.T = T; g->c2.n_out = n_out; g->c2.k_blocks = kb; g->c2.a2_row_off = a2_row_off;
-    g->c2.m_tiles = n_out / 256;
+    g->c2.m_tiles = (n_out + 255) / 256;
     g->c2.n_tiles = (T + bn2 - 1) / bn2;
     const int pairs = device_sm_count() / 2;
     int gm2 = (int)(sqrt((double)pairs * bn2 / (epi == EPI_SILU_BF16 ? 512.0 : 256.0)) + 0.5);
@@ -372,6 +380,11 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
     g->sk.w_policy = kEvictFirst;
   }
   return true;
+}
+
+void gemm_plan_set_bias(GemmPlan* g, const void* bias) {
+  g->p.bias = bias;
+  g->c2.bias = (const __nv_bfloat16*)bias;
 }
 
 // ------------------------------------------------------------------------------------------------ decode chain

@@ -30,8 +30,9 @@
 namespace mq {
 
 struct TwoCtaParams {
-  void* out;       // [T][ldo] bf16 (EPI_BF16 / EPI_SILU_BF16) or fp32 (EPI_F32)
+  void* out;       // [T][ldo] bf16 (EPI_BF16 / EPI_SILU_BF16 / EPI_BIAS_BF16 / EPI_GELU_BF16) or fp32 (EPI_F32)
   int ldo;
+  const __nv_bfloat16* bias;  // EPI_BIAS_BF16 / EPI_GELU_BF16: [n_out] (nullable)
   int T, n_out, k_blocks, a2_row_off;
   int m_tiles, n_tiles, group_m;  // tiles of 256 features x c2_bn(epi) tokens
   int n_pairs;                    // persistent CTA pairs launched
@@ -54,11 +55,20 @@ __host__ __device__ constexpr int c2_tail_bytes() { return 256 /*barriers*/ + 25
 __host__ __device__ constexpr int c2_stage_bytes(int epi) {
   return kATileBytes * (epi == EPI_SILU_BF16 ? 2 : 1) + (c2_bn(epi) / 2) * kBlockK * 2;  // own weight rows + own half of the tokens
 }
+// The bias / GELU epilogues (encoder GEMMs: K = 384 or 1536, i.e. 6 - 24 k-blocks per tile) stage their 128-feature x
+// 256-token half of the tile in shared memory and write it with ONE bulk tensor store: with so few k-blocks per tile
+// the epilogue, not the MMAs, sets the tile time, and 2-byte stores straight from registers (64 B per warp instruction)
+// took 14 000 cycles per tile against 3 000 cycles of MMAs.  The staging tile costs two of the six pipeline stages,
+// which a 6-k-block tile does not miss.
+__host__ __device__ constexpr bool c2_staged(int epi) { return epi == EPI_BIAS_BF16 || epi == EPI_GELU_BF16; }
+__host__ __device__ constexpr int c2_stage_tile_bytes(int epi) { return c2_staged(epi) ? c2_bn(epi) * kBlockM * 2 : 0; }
 __host__ __device__ constexpr int c2_stages(int epi) {
-  int s = (200 * 1024) / c2_stage_bytes(epi);
+  int s = (200 * 1024 - c2_stage_tile_bytes(epi)) / c2_stage_bytes(epi);
   return s > 8 ? 8 : s;
 }
-__host__ __device__ constexpr int c2_smem_bytes(int epi) { return c2_stages(epi) * c2_stage_bytes(epi) + 1024 + c2_tail_bytes(); }
+__host__ __device__ constexpr int c2_smem_bytes(int epi) {
+  return c2_stages(epi) * c2_stage_bytes(epi) + c2_stage_tile_bytes(epi) + 1024 + c2_tail_bytes();
+}
 
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -111,11 +121,37 @@ __device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
 
-constexpr int kC2Threads = 64 + 256;  // producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
+// producer warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter); the staged epilogues run 16 (four per quarter,
+// 64 token columns each): their tiles have 6 - 24 k-blocks, the epilogue sets the tile time and is a chain of
+// TMEM-load / ALU latencies that only more warps hide
+__host__ __device__ constexpr int c2_epi_warps(int epi) { return c2_staged(epi) ? 16 : 8; }
+__host__ __device__ constexpr int c2_threads(int epi) { return 64 + 32 * c2_epi_warps(epi); }
+
+// erf-GELU with the Abramowitz-Stegun 7.1.26 rational form (|error of erf| < 1.5e-7, far below the bf16 output's 2^-9):
+// 14 instructions and two MUFU results per element where erff() compiles to ~35 with divergent range branches - the
+// encoder's up-projection epilogue is instruction-bound (6 k-blocks of MMAs per 256 x 256 tile).
+__device__ __forceinline__ float gelu_erf_fast(float a) {
+  const float x = a * 0.70710678118654752f;
+  const float ax = fabsf(x);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * ax * -1.4426950408889634f));
+  const float erf_abs = fmaf(-poly, e, 1.0f);
+  const float erf_x = copysignf(erf_abs, x);
+  const float ha = 0.5f * a;
+  return fmaf(ha, erf_x, ha);
+}
 
 template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kC2Threads, 1)
-gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TwoCtaParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(c2_threads(EPI), 1)
+gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const TwoCtaParams p) {
   constexpr bool kDual = (EPI == EPI_SILU_BF16);
   constexpr int BN = c2_bn(EPI);                // token columns of the pair's accumulator
   constexpr int STAGES = c2_stages(EPI);
@@ -123,18 +159,21 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int B_OFF = kATileBytes * (kDual ? 2 : 1);
   constexpr int ACC_COLS = BN * (kDual ? 2 : 1);  // TMEM columns of one accumulator buffer
   constexpr int NBUF = c2_nbuf(EPI);              // 2: the epilogue of tile i overlaps the MMAs of tile i + 1
+  constexpr bool kStaged = c2_staged(EPI);        // output through a shared-memory tile + one bulk tensor store
+  constexpr int STG_BYTES = c2_stage_tile_bytes(EPI);
   constexpr uint32_t TMEM_COLS = 512u;
   constexpr uint32_t IDESC = umma_idesc_bf16(256, BN);
   static_assert(NBUF * ACC_COLS <= 512, "the accumulator buffers must fit TMEM");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);  // used in the leader only
+  uint8_t* stg = smem + STAGES * STAGE_BYTES;     // [256 tokens][128 features] bf16 (kStaged)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STG_BYTES);  // used in the leader only
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;   // [2] accumulator buffer complete (multicast commit: both CTAs)
   uint64_t* tempty_bar = tfull_bar + 2;       // [2] used in the leader only: both CTAs have drained the buffer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float* rstd_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);  // [256] rstd of the tile's tokens
+  float* rstd_s = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + STG_BYTES + 256);  // [256] rstd of the tile's tokens
   float* ssq_s = rstd_s + 256;                                                  // [4 lane quarters][256 tokens]
 
   const int warp = threadIdx.x >> 5;
@@ -240,9 +279,11 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ---------------- epilogue (both CTAs): my 128 TMEM lanes = my 128 features; registers -> global ----------------
     const int q = warp & 3;                 // TMEM lane quarter (warps w and w + 4 share one)
-    const int chalf = (warp - 2) >> 2;      // which half of the token columns this warp drains
+    constexpr int NEPI = 32 * c2_epi_warps(EPI);   // epilogue threads (named barrier 1)
+    constexpr int CPW = BN / (c2_epi_warps(EPI) / 4);  // token columns per warp: 128 (8 warps) or 64 (16)
+    const int chalf = (warp - 2) >> 2;      // which slice of the token columns this warp drains
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;        // 0..255
+    const int et = threadIdx.x - 64;        // 0..NEPI-1
     const bool fold = p.rs.ssq != nullptr;
     if (fold || EPI == EPI_RESID) pdl_wait();  // rstd partials / the residual stream come from earlier kernels
     int i = 0;
@@ -250,18 +291,26 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int tile_m, tile_n;
       tile_of(t, &tile_m, &tile_n);
       const int f = tile_m * 256 + (int)rank * kBlockM + row;  // this thread's output feature
+      const bool f_ok = f < p.n_out;  // n_out need not fill the last 256-row tile (encoder: 384 / 1152 features)
+      float bias_f = 0.f;
+      if constexpr (EPI == EPI_BIAS_BF16 || EPI == EPI_GELU_BF16)
+        bias_f = (p.bias != nullptr && f_ok) ? __bfloat162float(p.bias[f]) : 0.f;
       const int n0 = tile_n * BN;
       const int buf = i % NBUF, use = i / NBUF;
+      if (kStaged && i > 0) {  // the previous tile's bulk store has read the staging tile
+        if (warp == 2 && lane == 0) tma_store_wait_read();
+        asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
+      }
       if (fold) {  // per-token RMSNorm scale of this tile's 256 tokens (under the MMAs of the tile)
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's readers are done with rstd_s
-        rstd_s[et] = (n0 + et < p.T) ? rstd_of(p.rs, n0 + et) : 0.f;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");  // previous tile's readers are done with rstd_s
+        if (et < 256) rstd_s[et] = (n0 + et < p.T) ? rstd_of(p.rs, n0 + et) : 0.f;
+        asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
       }
       float gm = 0.f;
       float hnext[16];  // EPI_RESID: residual values of the chunk about to be processed
       if constexpr (EPI == EPI_RESID) {
         gm = __bfloat162float(p.gamma_next[f]);
-        const int c0 = chalf * (BN / 2);
+        const int c0 = chalf * CPW;
         const float* hp = reinterpret_cast<const float*>(p.out) + (size_t)(n0 + c0) * p.ldo + f;
 #pragma unroll
         for (int j = 0; j < 16; ++j) hnext[j] = (n0 + c0 + j < p.T) ? hp[(size_t)j * p.ldo] : 0.f;
@@ -269,8 +318,40 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tfull_bar[buf], use & 1);
       tc_fence_after();
       const uint32_t t_lane = tmem_base + (uint32_t)(buf * ACC_COLS) + (static_cast<uint32_t>(q * 32) << 16);
+      if constexpr (kStaged) {
+        // two 16-column chunks in flight: the TMEM load of the next chunk is issued before the current one is converted
+        const int cbeg = chalf * CPW;
+        const int cend = min((chalf + 1) * CPW, (p.T - n0 + 15) & ~15);  // columns past T are clipped by the store
+        const uint32_t stg_a = smem_u32(stg) + (uint32_t)row * 2u;
+        auto emit = [&](const uint32_t (&v)[16], int c0) {
+          const uint32_t o = stg_a + (uint32_t)(c0 * kBlockM) * 2u;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = __uint_as_float(v[j]);
+            if (fold) a *= rstd_s[c0 + j];
+            a += bias_f;
+            if constexpr (EPI == EPI_GELU_BF16) a = gelu_erf_fast(a);
+            sts_bf16(o + (uint32_t)(j * kBlockM) * 2u, a);
+          }
+        };
+        uint32_t va[16], vb[16];
+        if (cbeg < cend) tmem_ld16(t_lane + cbeg, va);
 #pragma unroll 1
-      for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 16) {
+        for (int c0 = cbeg; c0 < cend; c0 += 32) {
+          tmem_ld_wait();
+          const bool has_b = c0 + 16 < cend;
+          if (has_b) tmem_ld16(t_lane + c0 + 16, vb);
+          emit(va, c0);
+          if (has_b) {
+            tmem_ld_wait();
+            if (c0 + 32 < cend) tmem_ld16(t_lane + c0 + 32, va);
+            emit(vb, c0 + 16);
+          }
+        }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA engine
+      } else {
+#pragma unroll 1
+      for (int c0 = chalf * CPW; c0 < (chalf + 1) * CPW; c0 += 16) {
         if (n0 + c0 >= p.T) {
           if constexpr (EPI == EPI_RESID) {  // columns past T: zero partials so the tile's sums stay defined
             if (lane == 0)
@@ -303,7 +384,7 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           {
             const int c1 = c0 + 16;
             const float* hn = hp + (size_t)16 * p.ldo;
-            const bool more = c1 < (chalf + 1) * (BN / 2);
+            const bool more = c1 < (chalf + 1) * CPW;
 #pragma unroll
             for (int j = 0; j < 16; ++j) hnext[j] = (more && n0 + c1 + j < p.T) ? hn[(size_t)j * p.ldo] : 0.f;
           }
@@ -357,31 +438,37 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float* o = reinterpret_cast<float*>(p.out) + (size_t)(n0 + c0) * p.ldo + f;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __uint_as_float(v[j]) * (fold ? rstd_s[c0 + j] : 1.f);
+              if (f_ok && n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __uint_as_float(v[j]) * (fold ? rstd_s[c0 + j] : 1.f);
           } else {
             __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)(n0 + c0) * p.ldo + f;
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __float2bfloat16(__uint_as_float(v[j]) * (fold ? rstd_s[c0 + j] : 1.f));
+              if (f_ok && n0 + c0 + j < p.T) o[(size_t)j * p.ldo] = __float2bfloat16(__uint_as_float(v[j]) * (fold ? rstd_s[c0 + j] : 1.f));
           }
         }
       }
+      }  // !kStaged
       // this CTA's half of buffer `buf` is in registers / on its way to memory: hand the buffer back to the MMA thread
       tc_fence_before();
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");
       if (warp == 2 && lane == 0) {
         if (leader_cta) mbar_arrive(&tempty_bar[buf]);
         else mbar_arrive_remote(&tempty_bar[buf], 0);
+        if constexpr (kStaged) {  // rows past n_out / columns past T are clipped by the tensor map
+          tma_store_2d(&tmC, stg, tile_m * 256 + (int)rank * kBlockM, n0);
+          tma_store_commit();
+        }
       }
       if constexpr (EPI == EPI_RESID) {  // this CTA's 128 features of the tile: one partial per token, quarters in order
         if (n0 + et < p.T)
           p.ssq_out[(size_t)(tile_m * 2 + (int)rank) * p.ssq_stride + n0 + et] =
               (ssq_s[et] + ssq_s[256 + et]) + (ssq_s[512 + et] + ssq_s[768 + et]);
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // ssq_s is rewritten by the next tile
+        asm volatile("bar.sync 1, %0;" ::"n"(NEPI) : "memory");  // ssq_s is rewritten by the next tile
       }
     }
   }
 
+  if (kStaged && warp == 2 && lane == 0) tma_store_wait_read();  // the staging tile must outlive the last bulk store's read
   tc_fence_before();
   cluster_sync_all();  // neither CTA may free TMEM / exit while the pair's MMAs or epilogues still use its memory
   if (warp == 1) tmem_dealloc_2cta<TMEM_COLS>(tmem_base);

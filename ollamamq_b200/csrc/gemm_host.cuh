@@ -51,6 +51,8 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
                int tile_rows = 0);                    // weight rows per tile (0 = 128); see GemmParams::tile_rows
 // Tile height that spreads n_out weight rows over (almost) all SMs of the device: multiple of 8, 64..128.
 int gemm_balanced_rows(int n_out);
+// EPI_BIAS_BF16 / EPI_GELU_BF16: bf16 [n_out] bias added before the activation (whichever kernel the plan picked).
+void gemm_plan_set_bias(GemmPlan* g, const void* bias);
 // RMSNorm fold: scale token column t of the result by rstd[t] (GemmParams::rs / StreamKParams::rs).
 void gemm_plan_set_rstd(GemmPlan* g, const RstdIn& rs);
 // EPI_RESID (prefill O / down with the fold; only servable by the 2-CTA kernel: n_out % 256 == 0, T > 128): `out` of

@@ -87,6 +87,14 @@ bool attn_tc_encode_kv(CUtensorMap* out, const void* cache, int n_pages, int n_k
 void attn_tc_set_attrs();
 cudaError_t launch_attn_prefill_tc(const LaunchCfg& lc, const CUtensorMap& tmQ, const CUtensorMap& tmK, const CUtensorMap& tmV,
                                    const AttnParams& a, int n_tiles);
+// ---- encoder attention on tcgen05 (enc_attn_tc.cu): head_dim 32, bidirectional, sequences <= 512 tokens packed in one
+// [rows][3H] activation.  items = {row0, n_rows <= 256, first row of the sequence, its length} per CTA column.
+constexpr int kEncAttnItemRows = 256;
+bool enc_attn_tc_supported(int head_dim, int max_seq, int hidden);
+bool enc_attn_tc_encode(CUtensorMap* out, const void* qkv, int rows, int H);
+void enc_attn_tc_set_attrs();
+cudaError_t launch_enc_attn_tc(const LaunchCfg& lc, const CUtensorMap& tm, const int4* items, int n_items, int n_heads, int H,
+                               __nv_bfloat16* out, float scale_log2);
 void launch_attn_decode(const LaunchCfg& lc, const AttnParams& p, int n_slots);
 void attn_set_attrs();
 int attn_decode_resident_ctas();
@@ -103,6 +111,10 @@ void launch_enc_embed_ln(const LaunchCfg& lc, const int* tok, const int* pos, co
                          const __nv_bfloat16* b, float* h, __nv_bfloat16* x, int T, int H, float eps);
 void launch_enc_add_ln(const LaunchCfg& lc, float* h, const __nv_bfloat16* sub, const __nv_bfloat16* bias,
                        const __nv_bfloat16* g, const __nv_bfloat16* b, __nv_bfloat16* x, int T, int H, float eps);
+// warp-per-token form, bf16 residual stream (x is read as the residual and overwritten); h32 nullable
+bool enc_add_ln_warp_supported(int H);
+void launch_enc_add_ln_warp(const LaunchCfg& lc, __nv_bfloat16* x, const __nv_bfloat16* sub, const __nv_bfloat16* bias,
+                            const __nv_bfloat16* g, const __nv_bfloat16* b, float* h32, int T, int H, float eps);
 void launch_enc_pool(const LaunchCfg& lc, const float* h, const int* first_tok, float* out, int n_seq, int H);
 
 // Per-slot sampling controls (device arrays indexed by slot; a null array = the default): temperature <= 0 -> greedy;

@@ -255,14 +255,21 @@ class Encoder:
     def embed(self, sequences: Sequence[Sequence[int]]):
         """Blocking: numpy fp32 [n_seq, hidden], rows L2-normalised."""
         import numpy as np
-        flat = [t for s in sequences for t in s]
-        offs = [0]
-        for s in sequences:
-            offs.append(offs[-1] + len(s))
-        toks = (C.c_int32 * max(1, len(flat)))(*flat)
-        off = (C.c_int32 * len(offs))(*offs)
-        out = np.empty((len(sequences), self.cfg.hidden), dtype=np.float32)
-        check(lib.mq_encoder_embed(self._h, toks, off, len(sequences), out.ctypes.data_as(C.c_void_p)))
+        if isinstance(sequences, np.ndarray) and sequences.ndim == 2:   # [n_seq, seq_len] ids: no per-token python work
+            toks = np.ascontiguousarray(sequences, dtype=np.int32).reshape(-1)
+            off = np.arange(0, (sequences.shape[0] + 1) * sequences.shape[1], max(1, sequences.shape[1]), dtype=np.int32)
+            n = sequences.shape[0]
+        else:
+            arrs = [np.asarray(s, dtype=np.int32).reshape(-1) for s in sequences]
+            n = len(arrs)
+            toks = np.concatenate(arrs) if arrs else np.zeros(0, np.int32)
+            off = np.zeros(n + 1, dtype=np.int32)
+            np.cumsum([len(a) for a in arrs], out=off[1:])
+        if toks.size == 0:
+            toks = np.zeros(1, np.int32)
+        out = np.empty((n, self.cfg.hidden), dtype=np.float32)
+        check(lib.mq_encoder_embed(self._h, toks.ctypes.data_as(C.c_void_p), off.ctypes.data_as(C.c_void_p), n,
+                                   out.ctypes.data_as(C.c_void_p)))
         return out
 
     def submit(self, sink: "Stream", body: bytes, path: str = "/api/embed") -> "Stream":

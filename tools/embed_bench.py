@@ -33,7 +33,19 @@ with mq.Encoder(0, mq.encoder_cfg(cfg, max_seq=seq_len, max_tokens_per_pass=per_
         t0 = time.perf_counter()
         out = e.embed(seqs)
         best = min(best, time.perf_counter() - t0)
+    arr = np.asarray(seqs, dtype=np.int32)            # [n_seq, seq_len]: the same batch without per-token python work
+    s0 = e.stats()
+    best_np = 1e9
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        out2 = e.embed(arr)
+        best_np = min(best_np, time.perf_counter() - t0)
     st = e.stats()
+    gpu_ms = (st["gpu_us"] - s0["gpu_us"]) / 1e3 / reps
+    assert np.array_equal(out, out2)
+    print("  same batch as one int32 array: %.1f ms per batch = %.0f sequences/s; device time of its passes (CUDA events) %.1f ms "
+          "= %.1f TFLOP/s = %.1f %% of the sustained 1 457.8 TFLOP/s" %
+          (best_np * 1e3, n_seq / best_np, gpu_ms, flops / (gpu_ms * 1e-3) / 1e12, 100 * flops / (gpu_ms * 1e-3) / 1457.8e12))
     print("bge-small %d x %d tokens, passes of %d: %.1f ms per batch = %.0f sequences/s, %.2f M tokens/s, %.1f TFLOP/s "
           "(algorithmic %.1f TFLOP; end to end through mq_encoder_embed incl. python list marshalling) | %d launches per pass"
           % (n_seq, seq_len, per_pass, best * 1e3, n_seq / best, n_seq * seq_len / best / 1e6, flops / best / 1e12,
