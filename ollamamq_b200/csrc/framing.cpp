@@ -145,6 +145,17 @@ struct J {
   bool number(double* v) {
     ws();
     if (p >= e || !(*p == '-' || (*p >= '0' && *p <= '9'))) return false;  // JSON numbers only: no nan / inf / hex
+    {  // plain integers of up to 15 digits (token ids, num_predict, seeds): no strtod
+      const char* q = p + (*p == '-');
+      double acc = 0.0;
+      int nd = 0;
+      while (q < e && *q >= '0' && *q <= '9' && nd < 15) { acc = acc * 10.0 + (*q - '0'); ++q; ++nd; }
+      if (nd > 0 && (q >= e || (*q != '.' && *q != 'e' && *q != 'E' && !(*q >= '0' && *q <= '9')))) {
+        *v = *p == '-' ? -acc : acc;
+        p = q;
+        return true;
+      }
+    }
     char* end = nullptr;
     *v = strtod(p, &end);  // the buffer is a std::string: NUL-terminated
     if (end == p || end > e) return false;
@@ -426,14 +437,51 @@ std::vector<int32_t> embed_tokenize(const std::string& text, int vocab, int max_
   return t;
 }
 
-static void append_vec(std::string& o, const float* v, int dim) {
-  char b[32];
-  o += '[';
-  for (int i = 0; i < dim; ++i) {
-    snprintf(b, sizeof b, i ? ",%.8g" : "%.8g", (double)v[i]);
-    o += b;
+// One float as a JSON number with 9 significant digits (enough to round-trip a float32), trailing zeros trimmed.
+// Fixed notation through 64-bit integer arithmetic for 1e-5 <= |x| < 1e9 (every component of a unit-norm embedding
+// that matters); snprintf for the rest.  r02: "%.8g" per component was 5.2 ms for a 64 x 384 reply - on the embedding
+// worker's thread, i.e. longer than the 3.4 ms the GPU needs for the 32 768 tokens of that request.
+static char* put_float(char* w, float f) {
+  if (!(f == f) || f - f != 0.f) { *w++ = '0'; return w; }  // NaN / inf have no JSON spelling
+  double x = f;
+  if (x < 0) { *w++ = '-'; x = -x; }
+  if (x == 0.0) { *w++ = '0'; return w; }
+  if (x < 1e-5 || x >= 1e9) return w + snprintf(w, 24, "%.9g", x);
+  static const double p10[] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14};
+  int ex = x >= 1.0 ? 0 : -1;  // decimal exponent: 10^ex <= x < 10^(ex+1)
+  if (x >= 1.0) { while (ex < 8 && x >= p10[ex + 1]) ++ex; }
+  else { while (ex > -5 && x < 1.0 / p10[-ex]) --ex; }
+  unsigned long long d = (unsigned long long)(x * p10[8 - ex] + 0.5);  // 9 significant digits
+  if (d >= 1000000000ull) { d /= 10; ++ex; }
+  if (d < 100000000ull) { d *= 10; --ex; }   // (x sat just below a power of ten)
+  char dig[9];
+  for (int i = 8; i >= 0; --i) { dig[i] = (char)('0' + d % 10); d /= 10; }
+  int last = 8;
+  while (last > 0 && dig[last] == '0') --last;  // significant digits to print: dig[0 .. last]
+  if (ex >= 0) {
+    for (int i = 0; i <= ex; ++i) *w++ = i <= 8 ? dig[i] : '0';
+    if (last > ex) {
+      *w++ = '.';
+      for (int i = ex + 1; i <= last; ++i) *w++ = dig[i];
+    }
+  } else {
+    *w++ = '0'; *w++ = '.';
+    for (int i = -1; i > ex; --i) *w++ = '0';
+    for (int i = 0; i <= last; ++i) *w++ = dig[i];
   }
-  o += ']';
+  return w;
+}
+static void append_vec(std::string& o, const float* v, int dim) {
+  const size_t at = o.size();
+  o.resize(at + (size_t)dim * 26 + 2);
+  char* w = &o[at];
+  *w++ = '[';
+  for (int i = 0; i < dim; ++i) {
+    if (i) *w++ = ',';
+    w = put_float(w, v[i]);
+  }
+  *w++ = ']';
+  o.resize((size_t)(w - o.data()));
 }
 std::string frame_embeddings(const std::string& path, const char* model, const float* emb, int n, int dim, int n_tokens) {
   const std::string m = model_field(model);

@@ -131,3 +131,24 @@ def test_unicode_escapes_and_long_model_names():
     f = _call(mq.lib.mq_debug_frame_final, 1, 0, b"m" * 5000, b"x", 1, 1, 0)
     j = json.loads(f)                                                  # a 5 000-byte model name no longer truncates the frame
     assert j["done"] and len(j["model"]) == 256
+
+
+def test_embedding_floats_round_trip_float32_exactly():
+    """frame_embeddings writes 9 significant digits through integer arithmetic (no printf on the embedding worker's
+    thread): every finite float32 must parse back to the same float32; NaN / inf have no JSON spelling and become 0."""
+    rng = np.random.default_rng(7)
+    special = np.array([0, 1, -1, 0.1, 0.5, 1e-5, 9.9999999e-6, 123456789.0, 999999999.0, 1e9, 1e-7, 3.4e38, -2.5e-3,
+                        0.99999994, 1.0000001, 7.0, 1234.5678, 1e-45, 16777216.0, 99999.9921875, 0.001, 0.01, 10.0, 100.0,
+                        99999999.0, 1e8], dtype=np.float32)
+    rnd = (rng.standard_normal(50000) * 10.0 ** rng.integers(-7, 11, 50000)).astype(np.float32)
+    unit = rng.standard_normal((8, 384)).astype(np.float32)
+    unit /= np.linalg.norm(unit, axis=1, keepdims=True)
+    v = np.concatenate([special, rnd, unit.reshape(-1)]).reshape(1, -1)
+    buf = C.create_string_buffer(v.size * 30 + 256)
+    n = mq.lib.mq_debug_frame_embeddings(b"/api/embeddings", b"m", v.ctypes.data_as(C.c_void_p), 1, v.shape[1], 1, buf, len(buf))
+    assert 0 < n <= len(buf)
+    got = np.array(json.loads(buf.value)["embedding"], dtype=np.float32)
+    assert np.array_equal(got, v[0])
+    bad = np.array([[np.nan, np.inf, -np.inf, 0.25]], dtype=np.float32)
+    n = mq.lib.mq_debug_frame_embeddings(b"/api/embeddings", b"m", bad.ctypes.data_as(C.c_void_p), 1, 4, 1, buf, len(buf))
+    assert json.loads(buf.value) == {"embedding": [0, 0, 0, 0.25]}
