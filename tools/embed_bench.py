@@ -17,7 +17,7 @@ from ollamamq_b200.models import BGE_SMALL  # noqa: E402
 
 n_seq = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 seq_len = int(sys.argv[2]) if len(sys.argv) > 2 else 512
-per_pass = int(sys.argv[3]) if len(sys.argv) > 3 else 8192
+per_pass = int(sys.argv[3]) if len(sys.argv) > 3 else 75776   # 2 x 148 x 256: whole waves on 148 SMs for 512-token inputs
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 cfg = BGE_SMALL
 H, I, L = cfg["hidden"], cfg["ffn"], cfg["n_layers"]
