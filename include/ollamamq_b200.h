@@ -361,6 +361,13 @@ int mq_debug_embed(const int* token_ids, const void* embed, float* h, int T, int
  * rstd[t] = rsqrt(sum_{i < parts} ssq[i * stride + t] * inv_h + eps); ssq == NULL: no scaling.                     */
 int mq_debug_embed_chain(const int* token_ids, const void* embed, float* h, int T, int H, const void* gamma, void* xg,
                          float* ssq);
+/* encoder GEMM epilogues: out[t][f] = act(sum_k X[t][k] W[f][k] + bias[f]), epi = 4 (bias) or 3 (bias + erf-GELU), bf16 out */
+int mq_debug_gemm_bias(const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, int epi, const void* bias,
+                       void* out, int ldo);
+/* encoder attention on tcgen05 (head_dim 32, bidirectional): qkv = device [rows_alloc][3H] bf16, sequences packed back to
+ * back (host arrays seq_first / seq_len, lengths 1..512), out = device [rows][H] bf16                                 */
+int mq_debug_enc_attn(const void* qkv, int rows_alloc, int H, int n_heads, const int* seq_first, const int* seq_len, int n_seq,
+                      void* out);
 /* out_k[0..7] = co-resident clusters of 1..8 CTAs (occupancy query for the chain kernel's footprint)              */
 int mq_debug_cluster_info(int* out8);
 /* plain kernel with tile_rows (<= 128, multiple of 8; 0 = 128, < 0 = balanced over the SMs) and the rstd fold      */

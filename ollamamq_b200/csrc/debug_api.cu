@@ -6,6 +6,9 @@
 #include "kernels.cuh"
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
+#include <cmath>
+#include <vector>
 
 using namespace mq;
 
@@ -173,6 +176,62 @@ int mq_debug_gemm_dk_resid(const void* W, int n_out, int K, const void* X, int x
     fprintf(stderr, "\n");
     cudaFree(dbg);
   }
+  return rc;
+}
+
+// Encoder GEMM epilogues (EPI_BIAS_BF16 = 4, EPI_GELU_BF16 = 3): out[t][f] = act(sum_k X[t][k] W[f][k] + bias[f]); T > 128
+// takes the persistent 2-CTA kernel with the staged epilogue, smaller T the one-tile-per-CTA kernel.
+int mq_debug_gemm_bias(const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, int epi, const void* bias,
+                       void* out, int ldo) {
+  if (epi != EPI_BIAS_BF16 && epi != EPI_GELU_BF16) { mq::set_last_error("mq_debug_gemm_bias: epi must be 3 or 4"); return MQ_ERR_INVAL; }
+  GemmPlan g;
+  gemm_set_attrs();
+  if (!gemm_plan(&g, W, n_out, n_out, K, X, x_rows_alloc, T, epi, out, ldo, 1, 0, 0)) {
+    mq::set_last_error("mq_debug_gemm_bias: unsupported shape");
+    return MQ_ERR_INVAL;
+  }
+  gemm_plan_set_bias(&g, bias);
+  const LaunchCfg lc{0, false};
+  if (gemm_launch(g, lc) != cudaSuccess) { mq::set_last_error("mq_debug_gemm_bias: launch failed"); return MQ_ERR_CUDA; }
+  return check_cuda("mq_debug_gemm_bias");
+}
+
+// Encoder attention on tcgen05 (enc_attn_tc.cu): qkv = [rows_alloc][3H] bf16 (q | k | v column blocks), sequences packed
+// back to back: sequence s = rows seq_first[s] .. + seq_len[s] (host arrays); out = [rows][H] bf16.  head_dim = H / n_heads = 32.
+int mq_debug_enc_attn(const void* qkv, int rows_alloc, int H, int n_heads, const int* seq_first, const int* seq_len, int n_seq,
+                      void* out) {
+  if (n_heads < 1 || H % n_heads != 0 || !enc_attn_tc_supported(H / n_heads, 512, H)) {
+    mq::set_last_error("mq_debug_enc_attn: needs head_dim 32");
+    return MQ_ERR_INVAL;
+  }
+  std::vector<int> items;
+  for (int s = 0; s < n_seq; ++s) {
+    if (seq_len[s] < 1 || seq_len[s] > 512) { mq::set_last_error("mq_debug_enc_attn: sequence length must be 1..512"); return MQ_ERR_INVAL; }
+    for (int i = 0; i < seq_len[s]; i += kEncAttnItemRows) {
+      items.push_back(seq_first[s] + i);
+      items.push_back(std::min(kEncAttnItemRows, seq_len[s] - i));
+      items.push_back(seq_first[s]);
+      items.push_back(seq_len[s]);
+    }
+  }
+  int4* d_items = nullptr;
+  if (cudaMalloc(&d_items, items.size() * sizeof(int)) != cudaSuccess) return MQ_ERR_NOMEM;
+  cudaMemcpy(d_items, items.data(), items.size() * sizeof(int), cudaMemcpyHostToDevice);
+  CUtensorMap tm;
+  int rc = MQ_OK;
+  if (!enc_attn_tc_encode(&tm, qkv, rows_alloc, H)) { mq::set_last_error("mq_debug_enc_attn: tensor map"); rc = MQ_ERR_CUDA; }
+  if (rc == MQ_OK) {
+    enc_attn_tc_set_attrs();
+    const LaunchCfg lc{0, false};
+    const float scale_log2 = (1.0f / sqrtf((float)(H / n_heads))) * 1.4426950408889634f;
+    if (launch_enc_attn_tc(lc, tm, d_items, (int)items.size() / 4, n_heads, H, (__nv_bfloat16*)out, scale_log2) != cudaSuccess) {
+      mq::set_last_error("mq_debug_enc_attn: launch failed");
+      rc = MQ_ERR_CUDA;
+    } else {
+      rc = check_cuda("mq_debug_enc_attn");
+    }
+  }
+  cudaFree(d_items);
   return rc;
 }
 

@@ -159,3 +159,74 @@ def test_embed_routes_through_dispatcher_and_http():
             assert d.user_stats("alice")["processed"] == 5
         finally:
             d.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# kernel level: the round-2 encoder kernels against plain torch fp32 references of the same op
+# ---------------------------------------------------------------------------------------------------------------
+import ctypes as C  # noqa: E402
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+@pytest.mark.parametrize("T,n_out,K,epi,with_bias", [
+    (32768, 1536, 384, 3, True),     # bge-small up projection: bias + erf-GELU, 6 k-blocks per tile
+    (32768, 1152, 384, 4, True),     # QKV: ragged last 256-feature tile (1152 = 4.5 tiles)
+    (4096, 384, 1536, 4, False),     # down projection: 384 features = 1.5 tiles, no bias (added by the LayerNorm kernel)
+    (777, 384, 384, 4, True),        # ragged token tile
+    (300, 1000, 512, 3, True),       # features not a multiple of 128
+    (129, 256, 128, 3, True),        # smallest shape on the 2-CTA kernel
+    (100, 384, 384, 3, True),        # T <= 128: the one-tile-per-CTA kernel, same epilogue semantics
+])
+def test_encoder_gemm_bias_gelu_epilogues(T, n_out, K, epi, with_bias):
+    g = torch.Generator(device="cuda").manual_seed(T + n_out + K + epi)
+    rows = (T + 255) // 256 * 256
+    W = (torch.randn(n_out, K, device="cuda", generator=g) * 0.05).bfloat16()
+    X = torch.randn(rows, K, device="cuda", generator=g).bfloat16()
+    bias = (torch.randn(n_out, device="cuda", generator=g) * 0.5).bfloat16() if with_bias else None
+    out = torch.full((T, n_out), float("nan"), device="cuda", dtype=torch.bfloat16)
+    rc = mq.lib.mq_debug_gemm_bias(_p(W), n_out, K, _p(X), rows, T, epi, _p(bias), _p(out), n_out)
+    assert rc == 0, mq.last_error()
+    ref = X[:T].float() @ W.float().T
+    if with_bias:
+        ref = ref + bias.float()
+    if epi == 3:
+        ref = torch.nn.functional.gelu(ref)          # exact erf form, like BertIntermediate
+    assert torch.isfinite(out.float()).all(), "unwritten / non-finite outputs"
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 2 ** -7 * ref.abs().max().item() + 1e-3, (err, ref.abs().max().item())
+    rel = ((out.float() - ref).norm() / ref.norm()).item()
+    assert rel < 5e-3, rel
+
+
+@pytest.mark.parametrize("lens,H,heads", [
+    ([512] * 6, 384, 12),                                   # bge-small
+    ([1, 2, 63, 64, 65, 127, 128, 129, 255, 256, 257, 300, 511, 512, 7, 77], 384, 12),
+    ([200, 33, 512, 5], 256, 8),
+])
+def test_encoder_attention_tcgen05_vs_torch(lens, H, heads):
+    """Bidirectional softmax(Q K^T / sqrt(32)) V per sequence and head, packed q | k | v rows; rows of OTHER sequences and
+    stale rows behind the last one are loaded by the 64-row TMA boxes and must not leak in."""
+    g = torch.Generator(device="cuda").manual_seed(sum(lens) + H)
+    T = sum(lens)
+    rows = (T + 255) // 256 * 256 + 256
+    qkv = torch.randn(rows, 3 * H, device="cuda", generator=g).bfloat16()     # rows >= T: finite garbage
+    first = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    ln = np.asarray(lens, dtype=np.int32)
+    out = torch.full((T, H), float("nan"), device="cuda", dtype=torch.bfloat16)
+    rc = mq.lib.mq_debug_enc_attn(_p(qkv), rows, H, heads, first.ctypes.data_as(C.c_void_p), ln.ctypes.data_as(C.c_void_p),
+                                  len(lens), _p(out))
+    assert rc == 0, mq.last_error()
+    d = H // heads
+    worst = 0.0
+    for s, n in enumerate(lens):
+        blk = qkv[first[s]: first[s] + n].float()
+        q, k, v = (blk[:, i * H:(i + 1) * H].reshape(n, heads, d).transpose(0, 1) for i in range(3))
+        ref = torch.softmax(q @ k.transpose(1, 2) / d ** 0.5, dim=-1) @ v              # [heads, n, d]
+        ref = ref.transpose(0, 1).reshape(n, H)
+        got = out[first[s]: first[s] + n].float()
+        assert torch.isfinite(got).all()
+        worst = max(worst, ((got - ref).abs().max() / ref.abs().max()).item())
+    assert worst < 2e-2, worst     # bf16 probabilities (2^-9 each) and a bf16 result
