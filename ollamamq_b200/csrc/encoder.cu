@@ -73,6 +73,13 @@ struct mq_encoder {
   std::condition_variable cv, cv_done;
   std::deque<EncJob*> queue;
   bool stop = false;
+  // replies (JSON framing + callbacks) run on their own thread: a 64 x 384 reply takes ~1 ms to format, a third of the
+  // GPU time of the request it answers, and the pass thread has the next request's pass to launch
+  std::thread reply_thr;
+  std::mutex reply_mu;
+  std::condition_variable reply_cv;
+  std::deque<std::pair<EncJob*, int>> replies;
+  bool reply_stop = false;
   std::atomic<bool> healthy{true};
   std::atomic<uint64_t> passes{0}, sequences{0}, tokens{0}, launches{0}, gpu_us{0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -269,6 +276,37 @@ void enc_req_unref(mq_req* r) {
   if (r->refs.fetch_sub(1) == 1) delete r;
 }
 
+// Status, one JSON chunk, Done (the relay of dispatcher.rs:294-312) for finished dispatcher-form jobs
+void enc_reply_main(mq_encoder* e) {
+  for (;;) {
+    std::pair<EncJob*, int> it;
+    {
+      std::unique_lock<std::mutex> lk(e->reply_mu);
+      e->reply_cv.wait(lk, [&] { return e->reply_stop || !e->replies.empty(); });
+      if (e->replies.empty()) return;  // stop requested and drained
+      it = e->replies.front();
+      e->replies.pop_front();
+    }
+    EncJob* j = it.first;
+    const int rc = it.second;
+    mq_req* r = j->req;
+    if (rc == MQ_OK) {
+      int n_tok = 0;
+      for (auto& s : j->seqs) n_tok += (int)s.size();
+      const std::string body = frame_embeddings(j->path, j->model.c_str(), j->out.data(), (int)j->seqs.size(),
+                                                e->cfg.hidden, n_tok);
+      r->cb.on_status(r->user, 200, "application/json");
+      r->cb.on_chunk(r->user, (const uint8_t*)body.data(), body.size());
+      r->cb.on_done(r->user, 0, nullptr);
+    } else {
+      r->cb.on_done(r->user, rc, rc == MQ_ERR_CANCELED ? "cancelled" : "embedding pass failed");
+    }
+    r->finished = true;
+    enc_req_unref(r);
+    delete j;
+  }
+}
+
 void enc_main(mq_encoder* e) {
   cudaSetDevice(e->gpu);
   for (;;) {
@@ -282,22 +320,12 @@ void enc_main(mq_encoder* e) {
     }
     int rc = e->healthy.load() ? enc_run_job(e, j) : MQ_ERR_CUDA;
     if (rc == MQ_ERR_CUDA) e->healthy.store(false);  // sticky, like mq_worker_healthy
-    if (j->req) {  // dispatcher form: Status, one JSON chunk, Done (the relay of dispatcher.rs:294-312)
-      mq_req* r = j->req;
-      if (rc == MQ_OK) {
-        int n_tok = 0;
-        for (auto& s : j->seqs) n_tok += (int)s.size();
-        const std::string body = frame_embeddings(j->path, j->model.c_str(), j->out.data(), (int)j->seqs.size(),
-                                                  e->cfg.hidden, n_tok);
-        r->cb.on_status(r->user, 200, "application/json");
-        r->cb.on_chunk(r->user, (const uint8_t*)body.data(), body.size());
-        r->cb.on_done(r->user, 0, nullptr);
-      } else {
-        r->cb.on_done(r->user, rc, rc == MQ_ERR_CANCELED ? "cancelled" : "embedding pass failed");
+    if (j->req) {  // dispatcher form: answered by the reply thread, in submission order
+      {
+        std::lock_guard<std::mutex> g(e->reply_mu);
+        e->replies.emplace_back(j, rc);
       }
-      r->finished = true;
-      enc_req_unref(r);
-      delete j;
+      e->reply_cv.notify_one();
     } else {
       std::lock_guard<std::mutex> g(e->mu);
       j->rc = rc;
@@ -346,6 +374,7 @@ int mq_encoder_open(int32_t gpu, const mq_encoder_cfg* cfg, mq_encoder** out) {
   int rc = enc_setup(e);
   if (rc) { mq_encoder_close(e); return rc; }
   e->thr = std::thread(enc_main, e);
+  e->reply_thr = std::thread(enc_reply_main, e);
   *out = e;
   return MQ_OK;
 }
@@ -357,7 +386,13 @@ void mq_encoder_close(mq_encoder* e) {
     e->stop = true;
   }
   e->cv.notify_all();
-  if (e->thr.joinable()) e->thr.join();
+  if (e->thr.joinable()) e->thr.join();     // drains the pass queue: every job has been handed to the reply thread
+  {
+    std::lock_guard<std::mutex> g(e->reply_mu);
+    e->reply_stop = true;
+  }
+  e->reply_cv.notify_all();
+  if (e->reply_thr.joinable()) e->reply_thr.join();
   cudaSetDevice(e->gpu);
   for (auto& kv : e->tensors) cudaFree(kv.second.ptr);
   void* bufs[] = {e->h, e->d_out, e->x, e->qkv, e->attn, e->sub, e->act, e->d_meta};
