@@ -257,6 +257,9 @@ __device__ __forceinline__ float2 lds_f32x2(uint32_t a) {
   return v;
 }
 __device__ __forceinline__ void sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) {  // low 16 bits of v
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory");
+}
 __device__ __forceinline__ void sts_bf16(uint32_t a, float v) {
   const __nv_bfloat16 h = __float2bfloat16(v);
   asm volatile("st.shared.b16 [%0], %1;" ::"r"(a), "h"(*reinterpret_cast<const unsigned short*>(&h)) : "memory");
