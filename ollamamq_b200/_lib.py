@@ -172,6 +172,7 @@ _sig("mq_debug_embed", C.c_int, [P, P, P, C.c_int, C.c_int])
 _sig("mq_debug_embed_chain", C.c_int, [P, P, P, C.c_int, C.c_int, P, P, P])
 _sig("mq_debug_cluster_info", C.c_int, [P])
 _sig("mq_debug_gemm_bias", C.c_int, [P, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, P, P, C.c_int])
+_sig("mq_debug_gemm_rowln", C.c_int, [P, C.c_int, C.c_int, P, C.c_int, C.c_int, P, P, P, P, C.c_float, P])
 _sig("mq_debug_enc_attn", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, P, C.c_int, P])
 _sig("mq_debug_gemm_fold", C.c_int, [P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int, P, C.c_int, C.c_int, C.c_int,
                                       C.c_int, P, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.POINTER(C.c_float)])

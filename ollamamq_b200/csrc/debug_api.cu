@@ -196,6 +196,21 @@ int mq_debug_gemm_bias(const void* W, int n_out, int K, const void* X, int x_row
   return check_cuda("mq_debug_gemm_bias");
 }
 
+// x = LayerNorm(x + X W^T + bias) * gamma + beta in one kernel (gemm_rowln.cuh): x = device bf16 [T][n_out] residual in /
+// result out, n_out in {256, 384, 512}; h32 (nullable) = fp32 copy of the result.
+int mq_debug_gemm_rowln(const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, void* x, const void* bias,
+                        const void* gamma, const void* beta, float eps, float* h32) {
+  gemm_set_attrs();
+  RowLnPlan g;
+  if (!rowln_plan(&g, W, n_out, K, X, x_rows_alloc, T, x, bias, gamma, beta, eps, h32)) {
+    mq::set_last_error("mq_debug_gemm_rowln: unsupported shape (n_out in {256, 384, 512}, K %% 64 == 0)");
+    return MQ_ERR_INVAL;
+  }
+  const LaunchCfg lc{0, false};
+  if (rowln_launch(g, lc) != cudaSuccess) { mq::set_last_error("mq_debug_gemm_rowln: launch failed"); return MQ_ERR_CUDA; }
+  return check_cuda("mq_debug_gemm_rowln");
+}
+
 // Encoder attention on tcgen05 (enc_attn_tc.cu): qkv = [rows_alloc][3H] bf16 (q | k | v column blocks), sequences packed
 // back to back: sequence s = rows seq_first[s] .. + seq_len[s] (host arrays); out = [rows][H] bf16.  head_dim = H / n_heads = 32.
 int mq_debug_enc_attn(const void* qkv, int rows_alloc, int H, int n_heads, const int* seq_first, const int* seq_len, int n_seq,

@@ -63,6 +63,7 @@ struct mq_encoder {
   __nv_bfloat16 *x = nullptr, *qkv = nullptr, *attn = nullptr, *sub = nullptr, *act = nullptr;
   CUtensorMap tm_qkv{};   // tcgen05 attention: {32 d, 64 rows} boxes of the packed q | k | v activation
   bool attn_tc = false;
+  bool rowln = false;      // O / down projections fused with bias + residual + LayerNorm (gemm_rowln.cuh)
   int* d_meta = nullptr;  // tok | pos | first_tok | seq_len | tiles
   int* h_meta = nullptr;                            // pinned mirror
   float* h_out = nullptr;                           // pinned [max_seqs][H]
@@ -145,6 +146,8 @@ int enc_setup(mq_encoder* e) {
   e->attn_tc = enc_attn_tc_supported(c.head_dim, c.max_seq, H) && !(tc_env && tc_env[0] == '0') &&
                enc_attn_tc_encode(&e->tm_qkv, e->qkv, (int)MT, H);
   if (e->attn_tc) enc_attn_tc_set_attrs();
+  const char* rl_env = getenv("MQ_ENC_ROWLN");
+  e->rowln = rowln_supported(H, H) && rowln_supported(H, I) && !(rl_env && rl_env[0] == '0');
   if ((rc = enc_alloc(&e->attn, MT * H))) return rc;
   if ((rc = enc_alloc(&e->sub, MT * H))) return rc;
   if ((rc = enc_alloc(&e->act, MT * I))) return rc;
@@ -221,21 +224,33 @@ int enc_pass(mq_encoder* e, const std::vector<const std::vector<int32_t>*>& seqs
       ap.scale_log2 = scale_log2;
       launch_attn_prefill(lc, ap, n_tiles);
     }
-    if (!gemm_plan(&g, w.wo, H, H, H, e->attn, e->MT, T, EPI_BIAS_BF16, e->sub, H, 1, 0, 0)) return MQ_ERR_CUDA;  // (bias: in the LayerNorm kernel)
-    if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;
     const bool ln_warp = enc_add_ln_warp_supported(H);
-    if (ln_warp) launch_enc_add_ln_warp(lc, e->x, e->sub, w.bo, w.attn_ln_g, w.attn_ln_b, nullptr, T, H, c.ln_eps);
-    else launch_enc_add_ln(lc, e->h, e->sub, w.bo, w.attn_ln_g, w.attn_ln_b, e->x, T, H, c.ln_eps);
+    RowLnPlan rl;
+    if (e->rowln) {  // x = LayerNorm(x + attn W_o^T + b_o): one kernel, no `sub` round trip
+      if (!rowln_plan(&rl, w.wo, H, H, e->attn, e->MT, T, e->x, w.bo, w.attn_ln_g, w.attn_ln_b, c.ln_eps, nullptr) ||
+          rowln_launch(rl, lc) != cudaSuccess)
+        return MQ_ERR_CUDA;
+    } else {
+      if (!gemm_plan(&g, w.wo, H, H, H, e->attn, e->MT, T, EPI_BIAS_BF16, e->sub, H, 1, 0, 0)) return MQ_ERR_CUDA;  // (bias: in the LayerNorm kernel)
+      if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;
+      if (ln_warp) launch_enc_add_ln_warp(lc, e->x, e->sub, w.bo, w.attn_ln_g, w.attn_ln_b, nullptr, T, H, c.ln_eps);
+      else launch_enc_add_ln(lc, e->h, e->sub, w.bo, w.attn_ln_g, w.attn_ln_b, e->x, T, H, c.ln_eps);
+    }
     if (!gemm_plan(&g, w.w_up, I, I, H, e->x, e->MT, T, EPI_GELU_BF16, e->act, I, 1, 0, 0)) return MQ_ERR_CUDA;
     gemm_plan_set_bias(&g, w.b_up);
     if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;
-    if (!gemm_plan(&g, w.w_down, H, H, I, e->act, e->MT, T, EPI_BIAS_BF16, e->sub, H, 1, 0, 0)) return MQ_ERR_CUDA;
-    if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;
-    if (ln_warp)  // (the model's last LayerNorm also leaves an fp32 copy for the pooling kernel)
-      launch_enc_add_ln_warp(lc, e->x, e->sub, w.b_down, w.mlp_ln_g, w.mlp_ln_b, l + 1 == c.n_layers ? e->h : nullptr, T, H,
-                             c.ln_eps);
-    else launch_enc_add_ln(lc, e->h, e->sub, w.b_down, w.mlp_ln_g, w.mlp_ln_b, e->x, T, H, c.ln_eps);
-    nl += 7;
+    float* h_last = l + 1 == c.n_layers ? e->h : nullptr;  // the model's last LayerNorm also leaves an fp32 copy for the pooling kernel
+    if (e->rowln) {
+      if (!rowln_plan(&rl, w.w_down, H, I, e->act, e->MT, T, e->x, w.b_down, w.mlp_ln_g, w.mlp_ln_b, c.ln_eps, h_last) ||
+          rowln_launch(rl, lc) != cudaSuccess)
+        return MQ_ERR_CUDA;
+    } else {
+      if (!gemm_plan(&g, w.w_down, H, H, I, e->act, e->MT, T, EPI_BIAS_BF16, e->sub, H, 1, 0, 0)) return MQ_ERR_CUDA;
+      if (gemm_launch(g, lc) != cudaSuccess) return MQ_ERR_CUDA;
+      if (ln_warp) launch_enc_add_ln_warp(lc, e->x, e->sub, w.b_down, w.mlp_ln_g, w.mlp_ln_b, h_last, T, H, c.ln_eps);
+      else launch_enc_add_ln(lc, e->h, e->sub, w.b_down, w.mlp_ln_g, w.mlp_ln_b, e->x, T, H, c.ln_eps);
+    }
+    nl += e->rowln ? 5 : 7;
   }
   launch_enc_pool(lc, e->h, d_first, e->d_out, n, H);
   ++nl;

@@ -208,6 +208,9 @@ void gemm_set_attrs() {
   cudaFuncSetAttribute(gemm_2cta_kernel<EPI_RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_RESID));
   cudaFuncSetAttribute(gemm_2cta_kernel<EPI_BIAS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_BIAS_BF16));
   cudaFuncSetAttribute(gemm_2cta_kernel<EPI_GELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_GELU_BF16));
+  cudaFuncSetAttribute(gemm_rowln_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, rl_smem_bytes<256>());
+  cudaFuncSetAttribute(gemm_rowln_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, rl_smem_bytes<384>());
+  cudaFuncSetAttribute(gemm_rowln_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, rl_smem_bytes<512>());
   cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_BF16));
   cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_F32));
   cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_BF16));
@@ -380,6 +383,52 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
     g->sk.w_policy = kEvictFirst;
   }
   return true;
+}
+
+// ------------------------------------------------------------------------------------------------ gemm_rowln.cuh
+bool rowln_supported(int n_out, int K) {
+  return (n_out == 256 || n_out == 384 || n_out == 512) && K > 0 && K % kBlockK == 0 && twocta_enabled();
+}
+bool rowln_plan(RowLnPlan* g, const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, void* x_resid,
+                const void* bias, const void* gamma, const void* beta, float eps, float* h32) {
+  if (!rowln_supported(n_out, K) || T < 1) return false;
+  if (!tmap_encode_2d(&g->tmA, X, (uint64_t)x_rows_alloc, (uint64_t)K, 128u)) return false;
+  if (!tmap_encode_2d(&g->tmB, W, (uint64_t)n_out, (uint64_t)K, 64u)) return false;
+  g->n_out = n_out;
+  g->p = RowLnParams{};
+  g->p.x = (__nv_bfloat16*)x_resid;
+  g->p.bias = (const __nv_bfloat16*)bias;
+  g->p.gamma = (const __nv_bfloat16*)gamma;
+  g->p.beta = (const __nv_bfloat16*)beta;
+  g->p.h32 = h32;
+  g->p.T = T;
+  g->p.k_blocks = K / kBlockK;
+  g->p.n_tiles = (T + 255) / 256;
+  g->p.n_pairs = std::min(device_sm_count() / 2, g->p.n_tiles);
+  g->p.eps = eps;
+  return true;
+}
+template <int N_OUT>
+static cudaError_t launch_rowln(const RowLnPlan& g, const LaunchCfg& lc) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * g.p.n_pairs);  // persistent pairs; cluster dims (2,1,1) are compiled into the kernel
+  cfg.blockDim = dim3(kRlThreads);
+  cfg.dynamicSmemBytes = rl_smem_bytes<N_OUT>();
+  cfg.stream = lc.stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lc.pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, gemm_rowln_kernel<N_OUT>, g.tmA, g.tmB, g.p);
+}
+cudaError_t rowln_launch(const RowLnPlan& g, const LaunchCfg& lc) {
+  switch (g.n_out) {
+    case 256: return launch_rowln<256>(g, lc);
+    case 384: return launch_rowln<384>(g, lc);
+    case 512: return launch_rowln<512>(g, lc);
+    default: return cudaErrorInvalidValue;
+  }
 }
 
 void gemm_plan_set_bias(GemmPlan* g, const void* bias) {

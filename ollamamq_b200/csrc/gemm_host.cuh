@@ -5,6 +5,7 @@
 #include "gemm_persist.cuh"
 #include "gemm_2cta.cuh"
 #include "gemm_dk.cuh"
+#include "gemm_rowln.cuh"
 #include "kernels.cuh"
 
 namespace mq {
@@ -73,6 +74,19 @@ bool dk_plan(DkPlan* g, const void* W, int w_rows, int n_out, int K, const void*
              int tile_rows, int cs);
 cudaError_t dk_launch(const DkPlan& g, const LaunchCfg& lc);
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc);
+
+// ---- projection + bias + residual + LayerNorm (gemm_rowln.cuh): x = LayerNorm(x + X W^T + bias) * gamma + beta, in place
+// over the bf16 residual stream x [T][n_out]; n_out in {256, 384, 512}, K % 64 == 0, X rows allocated to a multiple of 128.
+struct RowLnPlan {
+  CUtensorMap tmA;  // activations [x_rows, K], box {64, 128}
+  CUtensorMap tmB;  // weights [n_out, K], box {64, 64}
+  RowLnParams p;
+  int n_out;
+};
+bool rowln_supported(int n_out, int K);
+bool rowln_plan(RowLnPlan* g, const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, void* x_resid,
+                const void* bias, const void* gamma, const void* beta, float eps, float* h32);
+cudaError_t rowln_launch(const RowLnPlan& g, const LaunchCfg& lc);
 void gemm_set_attrs();
 
 }  // namespace mq

@@ -230,3 +230,39 @@ def test_encoder_attention_tcgen05_vs_torch(lens, H, heads):
         assert torch.isfinite(got).all()
         worst = max(worst, ((got - ref).abs().max() / ref.abs().max()).item())
     assert worst < 2e-2, worst     # bf16 probabilities (2^-9 each) and a bf16 result
+
+
+@pytest.mark.parametrize("T,n_out,K,with_bias,want_h32", [
+    (32768, 384, 384, True, False),     # bge-small attention output
+    (4096, 384, 1536, True, True),      # bge-small MLP output (+ the fp32 copy of the model's last LayerNorm)
+    (777, 384, 384, False, False),      # ragged last token tile
+    (300, 256, 512, True, True),        # one MMA per k-step
+    (1000, 512, 256, True, False),      # 256 + 256 columns: all of tensor memory
+    (1, 384, 64, True, False),
+])
+def test_projection_residual_layernorm_in_one_kernel(T, n_out, K, with_bias, want_h32):
+    """x <- LayerNorm(x + X W^T + bias) * gamma + beta (BertSelfOutput / BertOutput), tokens on the TMEM lanes; rows behind T
+    of the (128-row padded) operand are garbage and must leave x untouched."""
+    g = torch.Generator(device="cuda").manual_seed(T + n_out + K)
+    rows = (T + 255) // 256 * 256
+    W = (torch.randn(n_out, K, device="cuda", generator=g) * 0.05).bfloat16()
+    X = torch.randn(rows, K, device="cuda", generator=g).bfloat16()
+    x0 = torch.randn(rows, n_out, device="cuda", generator=g).bfloat16()
+    bias = (torch.randn(n_out, device="cuda", generator=g) * 0.3).bfloat16() if with_bias else None
+    gamma = (1 + 0.2 * torch.randn(n_out, device="cuda", generator=g)).bfloat16()
+    beta = (0.2 * torch.randn(n_out, device="cuda", generator=g)).bfloat16()
+    eps = 1e-12
+    x = x0.clone()
+    h32 = torch.full((T, n_out), float("nan"), device="cuda") if want_h32 else None
+    rc = mq.lib.mq_debug_gemm_rowln(_p(W), n_out, K, _p(X), rows, T, _p(x), _p(bias), _p(gamma), _p(beta), eps, _p(h32))
+    assert rc == 0, mq.last_error()
+    pre = x0[:T].float() + X[:T].float() @ W.float().T + (bias.float() if with_bias else 0.0)
+    ref = torch.nn.functional.layer_norm(pre, (n_out,), gamma.float(), beta.float(), eps)
+    got = x[:T].float()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item() + 2e-3
+    assert ((got - ref).norm() / ref.norm()).item() < 5e-3
+    assert torch.equal(x[T:], x0[T:]), "rows behind T were written"
+    if want_h32:
+        assert torch.isfinite(h32).all() and (h32 - ref).abs().max().item() <= 4e-3 * ref.abs().max().item() + 1e-3
+        assert torch.equal(h32.bfloat16(), x[:T])
