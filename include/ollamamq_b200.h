@@ -364,7 +364,7 @@ int mq_debug_embed_chain(const int* token_ids, const void* embed, float* h, int 
 /* encoder GEMM epilogues: out[t][f] = act(sum_k X[t][k] W[f][k] + bias[f]), epi = 4 (bias) or 3 (bias + erf-GELU), bf16 out */
 int mq_debug_gemm_bias(const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, int epi, const void* bias,
                        void* out, int ldo);
-/* x = LayerNorm(x + X W^T + bias) * gamma + beta in one kernel: x = device bf16 [T][n_out], n_out in {256, 384, 512} */
+/* x = LayerNorm(x + X W^T + bias) * gamma + beta in one kernel: x = device bf16 [T][n_out], n_out in {256, 384} */
 int mq_debug_gemm_rowln(const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, void* x, const void* bias,
                         const void* gamma, const void* beta, float eps, float* h32);
 /* encoder attention on tcgen05 (head_dim 32, bidirectional): qkv = device [rows_alloc][3H] bf16, sequences packed back to

@@ -197,13 +197,13 @@ int mq_debug_gemm_bias(const void* W, int n_out, int K, const void* X, int x_row
 }
 
 // x = LayerNorm(x + X W^T + bias) * gamma + beta in one kernel (gemm_rowln.cuh): x = device bf16 [T][n_out] residual in /
-// result out, n_out in {256, 384, 512}; h32 (nullable) = fp32 copy of the result.
+// result out, n_out in {256, 384}; h32 (nullable) = fp32 copy of the result.
 int mq_debug_gemm_rowln(const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, void* x, const void* bias,
                         const void* gamma, const void* beta, float eps, float* h32) {
   gemm_set_attrs();
   RowLnPlan g;
   if (!rowln_plan(&g, W, n_out, K, X, x_rows_alloc, T, x, bias, gamma, beta, eps, h32)) {
-    mq::set_last_error("mq_debug_gemm_rowln: unsupported shape (n_out in {256, 384, 512}, K %% 64 == 0)");
+    mq::set_last_error("mq_debug_gemm_rowln: unsupported shape (n_out in {256, 384}, K %% 64 == 0)");
     return MQ_ERR_INVAL;
   }
   const LaunchCfg lc{0, false};

@@ -210,7 +210,6 @@ void gemm_set_attrs() {
   cudaFuncSetAttribute(gemm_2cta_kernel<EPI_GELU_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, c2_smem_bytes(EPI_GELU_BF16));
   cudaFuncSetAttribute(gemm_rowln_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, rl_smem_bytes<256>());
   cudaFuncSetAttribute(gemm_rowln_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, rl_smem_bytes<384>());
-  cudaFuncSetAttribute(gemm_rowln_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, rl_smem_bytes<512>());
   cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_BF16));
   cudaFuncSetAttribute(gemm_persist_kernel<256, EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(256, EPI_F32));
   cudaFuncSetAttribute(gemm_persist_kernel<128, EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes(128, EPI_BF16));
@@ -387,13 +386,14 @@ bool gemm_plan(GemmPlan* g, const void* W, int w_rows, int n_out, int K, const v
 
 // ------------------------------------------------------------------------------------------------ gemm_rowln.cuh
 bool rowln_supported(int n_out, int K) {
-  return (n_out == 256 || n_out == 384 || n_out == 512) && K > 0 && K % kBlockK == 0 && twocta_enabled();
+  return (n_out == 256 || n_out == 384) && K > 0 && K % kBlockK == 0 && twocta_enabled();
 }
 bool rowln_plan(RowLnPlan* g, const void* W, int n_out, int K, const void* X, int x_rows_alloc, int T, void* x_resid,
                 const void* bias, const void* gamma, const void* beta, float eps, float* h32) {
   if (!rowln_supported(n_out, K) || T < 1) return false;
   if (!tmap_encode_2d(&g->tmA, X, (uint64_t)x_rows_alloc, (uint64_t)K, 128u)) return false;
   if (!tmap_encode_2d(&g->tmB, W, (uint64_t)n_out, (uint64_t)K, 64u)) return false;
+  if (!tmap_encode_2d(&g->tmX, x_resid, (uint64_t)T, (uint64_t)n_out, 128u)) return false;  // rows past T: zero-filled / clipped
   g->n_out = n_out;
   g->p = RowLnParams{};
   g->p.x = (__nv_bfloat16*)x_resid;
@@ -420,13 +420,12 @@ static cudaError_t launch_rowln(const RowLnPlan& g, const LaunchCfg& lc) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = lc.pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, gemm_rowln_kernel<N_OUT>, g.tmA, g.tmB, g.p);
+  return cudaLaunchKernelEx(&cfg, gemm_rowln_kernel<N_OUT>, g.tmA, g.tmB, g.tmX, g.p);
 }
 cudaError_t rowln_launch(const RowLnPlan& g, const LaunchCfg& lc) {
   switch (g.n_out) {
     case 256: return launch_rowln<256>(g, lc);
     case 384: return launch_rowln<384>(g, lc);
-    case 512: return launch_rowln<512>(g, lc);
     default: return cudaErrorInvalidValue;
   }
 }

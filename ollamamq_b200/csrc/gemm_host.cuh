@@ -76,10 +76,11 @@ cudaError_t dk_launch(const DkPlan& g, const LaunchCfg& lc);
 cudaError_t gemm_launch(const GemmPlan& g, const LaunchCfg& lc);
 
 // ---- projection + bias + residual + LayerNorm (gemm_rowln.cuh): x = LayerNorm(x + X W^T + bias) * gamma + beta, in place
-// over the bf16 residual stream x [T][n_out]; n_out in {256, 384, 512}, K % 64 == 0, X rows allocated to a multiple of 128.
+// over the bf16 residual stream x [T][n_out]; n_out in {256, 384}, K % 64 == 0, X rows allocated to a multiple of 128.
 struct RowLnPlan {
   CUtensorMap tmA;  // activations [x_rows, K], box {64, 128}
   CUtensorMap tmB;  // weights [n_out, K], box {64, 64}
+  CUtensorMap tmX;  // residual / result [T, n_out], box {64, 128}
   RowLnParams p;
   int n_out;
 };

@@ -237,7 +237,7 @@ def test_encoder_attention_tcgen05_vs_torch(lens, H, heads):
     (4096, 384, 1536, True, True),      # bge-small MLP output (+ the fp32 copy of the model's last LayerNorm)
     (777, 384, 384, False, False),      # ragged last token tile
     (300, 256, 512, True, True),        # one MMA per k-step
-    (1000, 512, 256, True, False),      # 256 + 256 columns: all of tensor memory
+    (1000, 256, 256, True, False),
     (1, 384, 64, True, False),
 ])
 def test_projection_residual_layernorm_in_one_kernel(T, n_out, K, with_bias, want_h32):
