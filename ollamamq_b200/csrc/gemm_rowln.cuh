@@ -6,8 +6,8 @@
 // The other tcgen05 GEMMs of this library put WEIGHT rows on the TMEM lanes (a thread owns one output feature across the
 // tile's tokens).  A LayerNorm needs the opposite: every feature of one token.  Here the TOKENS are the M operand: a CTA
 // pair computes 256 tokens x N_OUT features with tcgen05.mma.cta_group::2 (M = 256; N = 256 + (N_OUT - 256) as two MMAs
-// per k-step, N_OUT <= 512 fp32 columns = the whole of tensor memory), so thread = token and its TMEM lane holds the
-// complete output row:
+// per k-step; N_OUT = 256 or 384 fp32 columns of tensor memory - 512 would fit TMEM but leave one pipeline stage beside
+// the row tile in shared memory), so thread = token and its TMEM lane holds the complete output row:
 //   pass 1  x = acc + bias + residual, x written BACK into tensor memory, partial sum / sum of squares
 //   pass 2  y = (x - mean) * rstd * gamma + beta  ->  bf16, in place over the residual
 // The residual / result tile (128 tokens x N_OUT bf16 per CTA) travels through shared memory by TMA, as N_OUT / 64
